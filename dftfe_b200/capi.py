@@ -1,0 +1,323 @@
+"""ctypes binding of libdftfe_b200.so (include/dftfe_b200.h).
+
+Host-side mirror of the reference interface for the hot path: ``Operator``
+carries the ``operatorDFTDeviceClass`` methods (HX, HXCheby, XtHX, overlap;
+include/operatorDevice.h:43-420) and ``ChebyshevSolver.solve`` mirrors
+``chebyshevOrthogonalizedSubspaceIterationSolverDevice::solve``
+(include/chebyshevOrthogonalizedSubspaceIterationSolverDevice.h:48-124).  PyTorch is
+used only to own device memory and streams; every compute call goes through the
+C ABI into hand-written sm_100a kernels.  There is no CPU fallback: if the shared
+library is missing or no sm_100a device is present the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from pathlib import Path
+from typing import Optional, Sequence
+
+import numpy as np
+
+_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libdftfe_b200.so"
+_lib = None
+
+
+class DftfeB200Error(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"dftfe_b200 error {code}: {msg}")
+        self.code = code
+
+
+class ProblemDesc(C.Structure):
+    _fields_ = [
+        ("nodes_per_cell", C.c_int32),
+        ("cheby_block", C.c_int32),
+        ("n_cells", C.c_int64),
+        ("n_owned", C.c_int64),
+        ("n_ghost", C.c_int64),
+        ("n_global_dofs", C.c_int64),
+        ("device", C.c_int32),
+        ("reserved", C.c_int32),
+    ]
+
+
+class SolveParams(C.Structure):
+    _fields_ = [
+        ("chebyshev_order", C.c_int32),
+        ("wfc_block", C.c_int32),
+        ("is_first_filtering_call", C.c_int32),
+        ("reuse_lanczos_upper_bound", C.c_int32),
+        ("is_first_scf", C.c_int32),
+        ("is_pseudopotential", C.c_int32),
+        ("compute_residual", C.c_int32),
+        ("use_cgs_rr", C.c_int32),
+        ("reproducible_output", C.c_int32),
+        ("reserved", C.c_int32),
+        ("first_scf_scaling", C.c_double),
+    ]
+
+
+# every symbol include/dftfe_b200.h declares (checked by tests/test_abi.py)
+EXPORTED_SYMBOLS = [
+    "dftfe_b200_version", "dftfe_b200_last_error", "dftfe_b200_create", "dftfe_b200_destroy",
+    "dftfe_b200_set_stream", "dftfe_b200_sync", "dftfe_b200_build_index_map", "dftfe_b200_set_index_map",
+    "dftfe_b200_set_constraints", "dftfe_b200_set_mass", "dftfe_b200_set_ghost_pattern",
+    "dftfe_b200_nccl_unique_id", "dftfe_b200_comm_init", "dftfe_b200_comm_init_loopback",
+    "dftfe_b200_set_cell_hamiltonian", "dftfe_b200_set_cell_hamiltonian_host",
+    "dftfe_b200_update_ghost_values", "dftfe_b200_accumulate_add_locally_owned", "dftfe_b200_zero_out_ghosts",
+    "dftfe_b200_constraints_distribute", "dftfe_b200_constraints_distribute_slave_to_master",
+    "dftfe_b200_constraints_set_zero", "dftfe_b200_hx", "dftfe_b200_hx_cheby", "dftfe_b200_cheb_filter",
+    "dftfe_b200_xtx", "dftfe_b200_xthx", "dftfe_b200_rotate", "dftfe_b200_lanczos_bounds",
+    "dftfe_b200_residual_norms", "dftfe_b200_reinit_spectrum_bounds", "dftfe_b200_solve",
+    "dftfe_b200_get_spectrum_bounds", "dftfe_b200_get_colouring", "dftfe_b200_profile_enable",
+    "dftfe_b200_profile_get", "dftfe_b200_profile_reset", "dftfe_b200_launch_count",
+]
+
+
+def lib_path() -> Path:
+    return _LIB_PATH
+
+
+def load() -> C.CDLL:
+    """Load the shared library (fails loudly when it has not been built)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not _LIB_PATH.exists():
+        raise DftfeB200Error(-2, f"{_LIB_PATH} is missing: run `python -m dftfe_b200.build` (there is no CPU fallback)")
+    lib = C.CDLL(str(_LIB_PATH), mode=C.RTLD_GLOBAL)
+    lib.dftfe_b200_version.restype = C.c_char_p
+    lib.dftfe_b200_last_error.restype = C.c_char_p
+    lib.dftfe_b200_launch_count.restype = C.c_int64
+    lib.dftfe_b200_launch_count.argtypes = [C.c_void_p]
+    lib.dftfe_b200_destroy.restype = None
+    lib.dftfe_b200_destroy.argtypes = [C.c_void_p]
+    _lib = lib
+    return lib
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise DftfeB200Error(rc, load().dftfe_b200_last_error().decode())
+
+
+def _np(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+def _dptr(t) -> C.c_void_p:
+    """device pointer of a torch CUDA tensor (float64, contiguous)."""
+    import torch
+
+    assert isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float64 and t.is_contiguous(), \
+        "expected a contiguous float64 CUDA tensor"
+    return C.c_void_p(t.data_ptr())
+
+
+def build_index_map(cell_global_dofs: np.ndarray, owned_start: int, owned_end: int, ghost_sorted: np.ndarray,
+                    block: int) -> np.ndarray:
+    """vectorTools::computeCellLocalIndexSetMap (utils/vectorTools/vectorUtilities.cc:473-502), host C++."""
+    lib = load()
+    cg = _np(cell_global_dofs, np.int64)
+    gh = _np(ghost_sorted, np.int64)
+    out = np.empty(cg.size, dtype=np.uint64)
+    nC, n = cg.shape
+    _check(lib.dftfe_b200_build_index_map(_ptr(cg), C.c_int64(nC), C.c_int32(n), C.c_int64(owned_start),
+                                          C.c_int64(owned_end), _ptr(gh), C.c_int64(gh.size), C.c_int32(block),
+                                          _ptr(out)))
+    return out
+
+
+def nccl_unique_id() -> bytes:
+    buf = (C.c_uint8 * 128)()
+    _check(load().dftfe_b200_nccl_unique_id(buf))
+    return bytes(buf)
+
+
+class Operator:
+    """One rank's ChFSI context.  Mirrors ``kohnShamDFTOperatorDeviceClass`` for the
+    hot path: ``reinit`` == constructor, then HX / HXCheby / XtHX / overlap."""
+
+    def __init__(self, prob, block: int, device: int = 0, use_torch_stream: bool = True):
+        import torch
+
+        self.lib = load()
+        self.prob = prob
+        self.B = int(block)
+        self.M, self.G, self.n = int(prob.M), int(prob.G), int(prob.n)
+        self.device = device
+        desc = ProblemDesc(nodes_per_cell=prob.n, cheby_block=block, n_cells=prob.nCells, n_owned=prob.M,
+                           n_ghost=prob.G, n_global_dofs=prob.nGlobalDofs, device=device, reserved=0)
+        h = C.c_void_p()
+        _check(self.lib.dftfe_b200_create(C.byref(desc), C.byref(h)))
+        self.h = h
+        if use_torch_stream:
+            with torch.cuda.device(device):
+                self.set_stream(torch.cuda.current_stream().cuda_stream)
+        imap = build_index_map(prob.cellGlobalDofs, prob.ownedStart, prob.ownedEnd, prob.ghostGlobal, block)
+        self.index_map = imap
+        _check(self.lib.dftfe_b200_set_index_map(self.h, _ptr(imap)))
+        self._keep = []
+        rows, sizes, starts = _np(prob.rowIdsLocal, np.uint32), _np(prob.rowSizes, np.uint32), _np(prob.rowStarts, np.uint32)
+        cols, vals, inh = _np(prob.colIdsLocal, np.uint32), _np(prob.colValues, np.float64), _np(prob.inhomogeneities, np.float64)
+        _check(self.lib.dftfe_b200_set_constraints(self.h, C.c_int64(rows.size), _ptr(rows), _ptr(sizes), _ptr(starts),
+                                                   _ptr(cols), _ptr(vals), _ptr(inh)))
+        sq, isq = _np(prob.sqrtMass, np.float64), _np(prob.invSqrtMass, np.float64)
+        _check(self.lib.dftfe_b200_set_mass(self.h, _ptr(sq), _ptr(isq)))
+        gp, gr = _np(prob.ghostProcIds, np.int32), _np(prob.ghostLocalRanges, np.int32)
+        tp, tc = _np(prob.targetProcIds, np.int32), _np(prob.numOwnedForTargets, np.int32)
+        ti = _np(prob.ownedLocalIdxForTargets, np.uint32)
+        _check(self.lib.dftfe_b200_set_ghost_pattern(self.h, C.c_int32(prob.rank), C.c_int32(prob.nranks),
+                                                     C.c_int32(gp.size), _ptr(gp), _ptr(gr), C.c_int32(tp.size),
+                                                     _ptr(tp), _ptr(tc), _ptr(ti)))
+
+    # ---- lifetime -------------------------------------------------------
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.dftfe_b200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream: int):
+        """cuda_stream: a cudaStream_t handle; torch reports its default stream as 0, which is
+        passed on as cudaStreamLegacy (0x1) because NULL selects the context-owned stream."""
+        _check(self.lib.dftfe_b200_set_stream(self.h, C.c_void_p(cuda_stream if cuda_stream else 1)))
+
+    def sync(self):
+        _check(self.lib.dftfe_b200_sync(self.h))
+
+    # ---- communicator -----------------------------------------------------
+    def comm_init(self, unique_id: bytes, rank: int, nranks: int):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        _check(self.lib.dftfe_b200_comm_init(self.h, buf, C.c_int32(rank), C.c_int32(nranks)))
+
+    def comm_init_loopback(self, group_id: int, rank: int, nranks: int):
+        _check(self.lib.dftfe_b200_comm_init_loopback(self.h, C.c_int32(group_id), C.c_int32(rank), C.c_int32(nranks)))
+
+    # ---- Hamiltonian ------------------------------------------------------
+    def set_cell_hamiltonian(self, H):
+        """H: torch CUDA tensor or numpy array [nCells, n, n] (mem[c,I,J] = H_c(I,J))."""
+        if isinstance(H, np.ndarray):
+            Hc = _np(H, np.float64)
+            _check(self.lib.dftfe_b200_set_cell_hamiltonian_host(self.h, _ptr(Hc)))
+        else:
+            _check(self.lib.dftfe_b200_set_cell_hamiltonian(self.h, _dptr(H)))
+
+    # ---- MultiVector / constraints ---------------------------------------
+    def update_ghost_values(self, x):
+        _check(self.lib.dftfe_b200_update_ghost_values(self.h, _dptr(x), C.c_int32(x.shape[1])))
+
+    def accumulate_add_locally_owned(self, x):
+        _check(self.lib.dftfe_b200_accumulate_add_locally_owned(self.h, _dptr(x), C.c_int32(x.shape[1])))
+
+    def zero_out_ghosts(self, x):
+        _check(self.lib.dftfe_b200_zero_out_ghosts(self.h, _dptr(x), C.c_int32(x.shape[1])))
+
+    def distribute(self, x):
+        _check(self.lib.dftfe_b200_constraints_distribute(self.h, _dptr(x), C.c_int32(x.shape[1])))
+
+    def distribute_slave_to_master(self, x):
+        _check(self.lib.dftfe_b200_constraints_distribute_slave_to_master(self.h, _dptr(x), C.c_int32(x.shape[1])))
+
+    def set_zero(self, x):
+        _check(self.lib.dftfe_b200_constraints_set_zero(self.h, _dptr(x), C.c_int32(x.shape[1])))
+
+    # ---- operatorDFTDeviceClass -------------------------------------------
+    def HX(self, src, dst, scaleFlag: bool, scalar: float, doUnscalingSrc: bool = True):
+        """kohnShamDFTOperatorDevice.cc:3765-3860."""
+        _check(self.lib.dftfe_b200_hx(self.h, _dptr(src), _dptr(dst), C.c_int32(src.shape[1]), C.c_int32(int(scaleFlag)),
+                                      C.c_double(scalar), C.c_int32(int(doUnscalingSrc))))
+
+    def HXCheby(self, src, dst):
+        """kohnShamDFTOperatorDevice.cc:3874-3997 (FP64)."""
+        _check(self.lib.dftfe_b200_hx_cheby(self.h, _dptr(src), _dptr(dst), C.c_int32(src.shape[1])))
+
+    def chebyshevFilter(self, X, Y, m: int, a: float, b: float, a0: float):
+        """linearAlgebraOperationsDevice.cc:531-727; X in/out (Loewdin basis), Y scratch."""
+        _check(self.lib.dftfe_b200_cheb_filter(self.h, _dptr(X), _dptr(Y), C.c_int32(X.shape[1]), C.c_int32(m),
+                                               C.c_double(a), C.c_double(b), C.c_double(a0)))
+
+    def XtX(self, X, S):
+        _check(self.lib.dftfe_b200_xtx(self.h, _dptr(X), C.c_int32(X.shape[1]), _dptr(S)))
+
+    def XtHX(self, X, Hp):
+        """kohnShamDFTOperatorDevice.cc:4001-4157."""
+        _check(self.lib.dftfe_b200_xthx(self.h, _dptr(X), C.c_int32(X.shape[1]), _dptr(Hp)))
+
+    def subspaceRotation(self, X, Q):
+        _check(self.lib.dftfe_b200_rotate(self.h, _dptr(X), C.c_int32(X.shape[1]), _dptr(Q)))
+
+    def lanczosLowerUpperBoundEigenSpectrum(self, reproducible: bool = False):
+        out = (C.c_double * 2)()
+        _check(self.lib.dftfe_b200_lanczos_bounds(self.h, C.c_int32(int(reproducible)), out))
+        return out[0], out[1]
+
+    def computeEigenResidualNorm(self, X, eig: Sequence[float]) -> np.ndarray:
+        N = X.shape[1]
+        e = _np(eig, np.float64)
+        out = np.empty(N)
+        _check(self.lib.dftfe_b200_residual_norms(self.h, _dptr(X), C.c_int32(N), _ptr(e), _ptr(out)))
+        return out
+
+    # ---- introspection ----------------------------------------------------
+    def colouring(self):
+        nc = C.c_int32()
+        col = np.empty(self.prob.nCells, dtype=np.int32)
+        _check(self.lib.dftfe_b200_get_colouring(self.h, C.byref(nc), _ptr(col)))
+        return nc.value, col
+
+    def profile_enable(self, on: bool = True):
+        _check(self.lib.dftfe_b200_profile_enable(self.h, C.c_int32(int(on))))
+
+    def profile_reset(self):
+        _check(self.lib.dftfe_b200_profile_reset(self.h))
+
+    def profile_get(self, name: str):
+        ms, n = C.c_double(), C.c_int64()
+        _check(self.lib.dftfe_b200_profile_get(self.h, name.encode(), C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    def launch_count(self) -> int:
+        return int(self.lib.dftfe_b200_launch_count(self.h))
+
+
+class ChebyshevSolver:
+    """chebyshevOrthogonalizedSubspaceIterationSolverDevice (solver .cc:155-736)."""
+
+    def __init__(self, op: Operator):
+        self.op = op
+
+    def reinitSpectrumBounds(self, lowerWanted: float, lowerUnwanted: float):
+        _check(self.op.lib.dftfe_b200_reinit_spectrum_bounds(self.op.h, C.c_double(lowerWanted), C.c_double(lowerUnwanted)))
+
+    def spectrumBounds(self):
+        out = (C.c_double * 3)()
+        _check(self.op.lib.dftfe_b200_get_spectrum_bounds(self.op.h, out))
+        return out[0], out[1], out[2]
+
+    def solve(self, X, isFirstFilteringCall: bool, computeResidual: bool = True, chebyshevOrder: int = 0,
+              isFirstScf: bool = False, isPseudopotential: bool = True, useCgsRR: bool = False,
+              reuseLanczos: bool = False, reproducible: bool = False, firstScfScaling: float = 1.34):
+        """X: torch CUDA [M, N] float64, in/out.  Returns (eigenvalues, residuals, upper bound)."""
+        N = X.shape[1]
+        p = SolveParams(chebyshev_order=chebyshevOrder, wfc_block=0,
+                        is_first_filtering_call=int(isFirstFilteringCall),
+                        reuse_lanczos_upper_bound=int(reuseLanczos), is_first_scf=int(isFirstScf),
+                        is_pseudopotential=int(isPseudopotential), compute_residual=int(computeResidual),
+                        use_cgs_rr=int(useCgsRR), reproducible_output=int(reproducible), reserved=0,
+                        first_scf_scaling=firstScfScaling)
+        eig = np.empty(N)
+        res = np.empty(N)
+        ub = C.c_double()
+        _check(self.op.lib.dftfe_b200_solve(self.op.h, _dptr(X), C.c_int32(N), C.byref(p), _ptr(eig), _ptr(res),
+                                            C.byref(ub)))
+        return eig, (res if computeResidual else None), ub.value

@@ -1,0 +1,309 @@
+// Fused cell-level Hamiltonian apply for sm_100a.
+//
+// Replaces, in ONE kernel per cell colour, the reference's per-degree sequence
+//   K1 stridedCopyToBlock gather      (utils/DeviceKernelsGeneric.cc:101-126)
+//   K2 cuBLAS gemmStridedBatched       (src/dftOperator/matrixVectorProductImplementationsDevice.cc:51-79)
+//   K3 axpyStridedBlockAtomicAdd       (utils/DeviceKernelsGeneric.cc:296-318)
+//   K5 stridedBlockScale x4            (src/dftOperator/kohnShamDFTOperatorDevice.cc:3790-3859)
+//   K7 combinedDeviceKernel            (src/linAlg/linearAlgebraOperationsDevice.cc:37-64)
+// i.e. for every owned cell c and wavefunction column tile:
+//   Xc[k,:]   = rowIn[row(c,k)] * src[row(c,k), tile]            (gather through the index map)
+//   Yc        = Hm_c * Xc            with Hm_c[i][k] = mem[c*n*n + i*n + k]      (FP64 DMMA)
+//   dst[row(c,i), tile] (first touch) = a*rowA*src + b*rowB*dst + s*rowOut*Yc[i,:]
+//                        (otherwise) += s*rowOut*Yc[i,:]
+// Cells of one colour share no row, so the read-modify-write needs no atomics and
+// the summation order is fixed (deterministic, unlike the reference's atomicAdd).
+//
+// Tensor path: Blackwell's tcgen05.mma has no FP64 kind; FP64 tensor work on
+// sm_100a is the warp-level DMMA.8x8x4 (all mma.sync f64 shapes lower to it).
+// Measured on this pool's B200: 37.0 TFLOP/s raw DMMA issue, 35.7 cuBLAS DGEMM
+// (profiles/r01_fp64_peaks.jsonl).
+//
+// Work decomposition (p=6: n=343): a CTA owns (cell, 32-column tile); the 43
+// m8 row tiles are dealt round-robin to 12 warps so each of the SM's four
+// tensor pipes gets 11/11/11/10 tiles (97.7 % balance).  A fragments stream
+// straight from L2/HBM into registers out of a fragment-major copy of H_c made
+// once per set_cell_hamiltonian (every H element is used exactly once per CTA,
+// so staging it through shared memory buys nothing); the gathered X tile lives
+// in shared memory with a row pitch of 36 doubles (conflict-free B-fragment
+// reads).
+#include "common.cuh"
+
+namespace dftfe_b200 {
+
+namespace {
+
+constexpr int BT = 32;       // wavefunction columns per CTA tile
+constexpr int NT = BT / 8;   // n8 tiles per warp
+constexpr int LDS = BT + 4;  // shared-memory row pitch in doubles ( = 4 mod 16 )
+
+template <int NODES>
+struct CellCfg {
+  static constexpr int MT = (NODES + 7) / 8;  // m8 row tiles
+  static constexpr int KS = (NODES + 3) / 4;  // k4 steps
+  static constexpr int KPAD = KS * 4;
+  static constexpr int WARPS = MT >= 12 ? 12 : (MT >= 8 ? 8 : 4);
+  static constexpr int TPW = (MT + WARPS - 1) / WARPS;  // row tiles per warp (max)
+  static constexpr int THREADS = WARPS * 32;
+  static constexpr size_t SMEM = (size_t)KPAD * LDS * sizeof(double);
+  static constexpr size_t HT_PER_CELL = (size_t)KS * MT * 32;  // doubles
+};
+
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+// H_c (row-major n x n as stored by the reference) -> fragment-major:
+// Ht[cell][ks][mt][lane] = Hm[mt*8 + lane/4][ks*4 + lane%4], zero padded.
+template <int NODES>
+__global__ void retile_H_kernel(const double *__restrict__ H, double *__restrict__ Ht, int64_t nCells) {
+  using C = CellCfg<NODES>;
+  const int64_t total = nCells * (int64_t)C::HT_PER_CELL;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int lane = idx % 32;
+    int64_t r = idx / 32;
+    const int mt = r % C::MT;
+    r /= C::MT;
+    const int ks = r % C::KS;
+    const int64_t cell = r / C::KS;
+    const int i = mt * 8 + lane / 4;
+    const int k = ks * 4 + lane % 4;
+    double v = 0.0;
+    if (i < NODES && k < NODES) v = H[cell * (int64_t)NODES * NODES + (int64_t)i * NODES + k];
+    Ht[idx] = v;
+  }
+}
+
+template <int NODES>
+__global__ void __launch_bounds__(CellCfg<NODES>::THREADS, 1)
+cell_matvec_kernel(const double *__restrict__ Ht, const uint32_t *__restrict__ cellRows,
+                   const int32_t *__restrict__ cells, const double *__restrict__ src,
+                   double *__restrict__ dst, int ncols, int ldx, int nColTiles, EpilogueParams ep) {
+  using C = CellCfg<NODES>;
+  extern __shared__ __align__(16) double Xs[];  // [KPAD][LDS]
+  __shared__ uint32_t rowsS[NODES];
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+  const int item = blockIdx.x;
+  const int cell = cells[item / nColTiles];
+  const int col0 = (item % nColTiles) * BT;
+
+  for (int i = tid; i < NODES; i += C::THREADS) rowsS[i] = cellRows[(size_t)cell * NODES + i];
+  __syncthreads();
+
+  // ---- gather: one 256-byte row segment per warp instruction
+  const bool colOk = (col0 + lane) < ncols;
+#pragma unroll 4
+  for (int k = warp; k < C::KPAD; k += C::WARPS) {
+    double v = 0.0;
+    if (k < NODES && colOk) {
+      const uint32_t r = rowsS[k] & 0x7fffffffu;
+      v = __ldg(src + (size_t)r * ldx + col0 + lane);
+      if (ep.rowIn) v *= __ldg(ep.rowIn + r);
+    }
+    Xs[k * LDS + lane] = v;
+  }
+  __syncthreads();
+
+  // ---- DMMA main loop
+  double acc[C::TPW][NT][2];
+#pragma unroll
+  for (int t = 0; t < C::TPW; ++t)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) acc[t][nt][0] = acc[t][nt][1] = 0.0;
+
+  const double *Hc = Ht + (size_t)cell * C::HT_PER_CELL + lane;
+  const double *xb = Xs + (lane & 3) * LDS + (lane >> 2);
+
+  double a0[C::TPW], a1[C::TPW];
+#pragma unroll
+  for (int t = 0; t < C::TPW; ++t) {
+    const int mt = warp + t * C::WARPS;
+    a0[t] = (mt < C::MT) ? __ldg(Hc + (size_t)(0 * C::MT + mt) * 32) : 0.0;
+    a1[t] = (mt < C::MT && C::KS > 1) ? __ldg(Hc + (size_t)(1 * C::MT + mt) * 32) : 0.0;
+  }
+
+  for (int ks = 0; ks < C::KS; ks += 2) {
+    // prefetch A for ks+2, ks+3
+    double n0[C::TPW], n1[C::TPW];
+#pragma unroll
+    for (int t = 0; t < C::TPW; ++t) {
+      const int mt = warp + t * C::WARPS;
+      n0[t] = (mt < C::MT && ks + 2 < C::KS) ? __ldg(Hc + (size_t)((ks + 2) * C::MT + mt) * 32) : 0.0;
+      n1[t] = (mt < C::MT && ks + 3 < C::KS) ? __ldg(Hc + (size_t)((ks + 3) * C::MT + mt) * 32) : 0.0;
+    }
+    {
+      double b[NT];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) b[nt] = xb[(ks * 4) * LDS + nt * 8];
+#pragma unroll
+      for (int t = 0; t < C::TPW; ++t)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) dmma884(acc[t][nt][0], acc[t][nt][1], a0[t], b[nt]);
+    }
+    if (ks + 1 < C::KS) {
+      double b[NT];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) b[nt] = xb[((ks + 1) * 4) * LDS + nt * 8];
+#pragma unroll
+      for (int t = 0; t < C::TPW; ++t)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) dmma884(acc[t][nt][0], acc[t][nt][1], a1[t], b[nt]);
+    }
+#pragma unroll
+    for (int t = 0; t < C::TPW; ++t) {
+      a0[t] = n0[t];
+      a1[t] = n1[t];
+    }
+  }
+
+  // ---- epilogue: recurrence + scaling + coloured (atomics-free) assembly
+  const bool vec2 = ((ldx & 1) == 0) && (col0 + BT <= ncols);
+#pragma unroll
+  for (int t = 0; t < C::TPW; ++t) {
+    const int mt = warp + t * C::WARPS;
+    const int i = mt * 8 + (lane >> 2);
+    if (mt < C::MT && i < NODES) {
+      const uint32_t fr = rowsS[i];
+      const uint32_t r = fr & 0x7fffffffu;
+      const bool first = (fr >> 31) != 0;
+      const double so = ep.s * (ep.rowOut ? __ldg(ep.rowOut + r) : 1.0);
+      double ca = 0.0, cb = 1.0;
+      if (first) {
+        ca = ep.a * (ep.rowA ? __ldg(ep.rowA + r) : 1.0);
+        cb = ep.b * (ep.rowB ? __ldg(ep.rowB + r) : 1.0);
+      }
+      double *drow = dst + (size_t)r * ldx + col0 + (lane & 3) * 2;
+      const double *srow = src + (size_t)r * ldx + col0 + (lane & 3) * 2;
+      if (vec2) {
+        double2 d[NT], sv[NT];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          d[nt] = (cb != 0.0) ? *reinterpret_cast<const double2 *>(drow + nt * 8) : make_double2(0.0, 0.0);
+          sv[nt] = (ca != 0.0) ? *reinterpret_cast<const double2 *>(srow + nt * 8) : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          double2 o;
+          o.x = so * acc[t][nt][0] + ca * sv[nt].x + cb * d[nt].x;
+          o.y = so * acc[t][nt][1] + ca * sv[nt].y + cb * d[nt].y;
+          *reinterpret_cast<double2 *>(drow + nt * 8) = o;
+        }
+      } else {
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int col = col0 + nt * 8 + (lane & 3) * 2 + e;
+            if (col < ncols) {
+              double o = so * acc[t][nt][e];
+              if (ca != 0.0) o += ca * srow[nt * 8 + e];
+              if (cb != 0.0) o += cb * drow[nt * 8 + e];
+              drow[nt * 8 + e] = o;
+            }
+          }
+      }
+    }
+  }
+}
+
+// rows that no owned cell touches still need the first-touch formula (contrib = 0)
+__global__ void orphan_first_touch_kernel(const uint32_t *__restrict__ rows, int64_t nRows,
+                                          const double *__restrict__ src, double *__restrict__ dst, int ncols,
+                                          int ldx, EpilogueParams ep) {
+  const int64_t total = nRows * ncols;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const uint32_t r = rows[idx / ncols];
+    const int col = idx % ncols;
+    const double ca = ep.a * (ep.rowA ? ep.rowA[r] : 1.0);
+    const double cb = ep.b * (ep.rowB ? ep.rowB[r] : 1.0);
+    double o = 0.0;
+    if (ca != 0.0) o += ca * src[(size_t)r * ldx + col];
+    if (cb != 0.0) o += cb * dst[(size_t)r * ldx + col];
+    dst[(size_t)r * ldx + col] = o;
+  }
+}
+
+template <int NODES>
+int launch_impl(dftfe_b200_ctx *ctx, const double *src, double *dst, int ncols, int ldx,
+                const EpilogueParams &ep) {
+  using C = CellCfg<NODES>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    DB_CUDA(cudaFuncSetAttribute(cell_matvec_kernel<NODES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)C::SMEM));
+    attr_set = true;
+  }
+  const int nColTiles = (ncols + BT - 1) / BT;
+  for (int k = 0; k < ctx->nColours; ++k) {
+    const int nCellsK = ctx->colourStart_h[k + 1] - ctx->colourStart_h[k];
+    if (nCellsK == 0) continue;
+    ProfScope ps(ctx, "cell_matvec");
+    cell_matvec_kernel<NODES><<<nCellsK * nColTiles, C::THREADS, C::SMEM, ctx->stream>>>(
+        ctx->Htiled.p, ctx->cellRowsFlagged.p, ctx->colourCells.p + ctx->colourStart_h[k], src, dst, ncols, ldx,
+        nColTiles, ep);
+  }
+  DB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+template <int NODES>
+int retile_impl(dftfe_b200_ctx *ctx, const double *H_d) {
+  using C = CellCfg<NODES>;
+  DB_TRY(ctx->Htiled.alloc((size_t)ctx->nC * C::HT_PER_CELL));
+  ctx->launches += 1;
+  retile_H_kernel<NODES><<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(H_d, ctx->Htiled.p, ctx->nC);
+  DB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+#define DB_DISPATCH_NODES(n, FN, ...)                                  \
+  switch (n) {                                                         \
+    case 8: return FN<8>(__VA_ARGS__);                                 \
+    case 27: return FN<27>(__VA_ARGS__);                               \
+    case 64: return FN<64>(__VA_ARGS__);                               \
+    case 125: return FN<125>(__VA_ARGS__);                             \
+    case 216: return FN<216>(__VA_ARGS__);                             \
+    case 343: return FN<343>(__VA_ARGS__);                             \
+    case 512: return FN<512>(__VA_ARGS__);                             \
+    default:                                                           \
+      set_error("no cell kernel instantiated for %d nodes per cell", n); \
+      return DFTFE_B200_ERR_UNSUPPORTED;                               \
+  }
+
+int cell_kernel_supported(int n) {
+  return n == 8 || n == 27 || n == 64 || n == 125 || n == 216 || n == 343 || n == 512;
+}
+
+int retile_cell_hamiltonian(dftfe_b200_ctx *ctx, const double *H_d) {
+  DB_DISPATCH_NODES(ctx->n, retile_impl, ctx, H_d);
+}
+
+int launch_cell_matvec(dftfe_b200_ctx *ctx, const double *src, double *dst, int ncols, int ldx,
+                       const EpilogueParams &ep) {
+  DB_CHECK(ctx->have_map && ctx->have_H, "cell matvec needs set_index_map and set_cell_hamiltonian first");
+  DB_CHECK(src != dst, "cell matvec: src and dst must not alias");
+  DB_DISPATCH_NODES(ctx->n, launch_impl, ctx, src, dst, ncols, ldx, ep);
+}
+
+int launch_orphan_first_touch(dftfe_b200_ctx *ctx, const double *src, double *dst, int ncols, int ldx,
+                              const EpilogueParams &ep) {
+  if (ctx->nOrphan == 0) return 0;
+  ProfScope ps(ctx, "orphan_rows");
+  const int64_t total = ctx->nOrphan * ncols;
+  const int grid = (int)std::min<int64_t>((total + 255) / 256, ctx->num_sms * 16);
+  orphan_first_touch_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->orphanRows.p, ctx->nOrphan, src, dst, ncols, ldx,
+                                                          ep);
+  DB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace dftfe_b200

@@ -1,0 +1,218 @@
+// Ghost-DoF exchange and projected-matrix all-reduce.
+//
+// Reference: MPICommunicatorP2P<T,DEVICE>::updateGhostValues[Begin/End] /
+// accumulateAddLocallyOwned[Begin/End] (utils/MPICommunicatorP2P.cc:103-418) move
+// the packed rows with MPI_Isend/Irecv staged through pinned host memory;
+// DeviceCCLWrapper (utils/DeviceDirectCCLWrapper.cc:96-261) all-reduces the
+// projected blocks.  Here both go over NCCL (ncclSend/ncclRecv grouped per
+// direction, ncclAllReduce) on the context stream - NVLink5/NVSwitch, no host hop.
+//
+// A second, in-process transport ("loopback") lets several ranks share ONE GPU:
+// each rank is a context driven by its own host thread; buffers are exchanged with
+// device-to-device copies between two process-wide barriers.  It exists so that
+// the multi-rank path (pack -> exchange -> unpack-add, all-reduce) can be
+// parity-tested on a single B200.
+#include <condition_variable>
+#include <cstring>
+#include <memory>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace dftfe_b200 {
+
+int launch_pack_rows(dftfe_b200_ctx *ctx, const double *x, int ncols, int ldx, int64_t nRows, const uint32_t *rows,
+                     double *buf);
+int launch_copy_rows(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx, int64_t row0, int64_t nRows, double *buf,
+                     int toBuf);
+int launch_unpack_add(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx, const double *buf,
+                      const double *rowScale);
+
+struct LoopbackGroup {
+  int nranks = 0;
+  std::vector<dftfe_b200_ctx *> members;
+  std::vector<const double *> pub;  // per-rank published pointer
+  std::mutex mu;
+  std::condition_variable cv;
+  int waiting = 0;
+  int64_t generation = 0;
+  void barrier() {
+    std::unique_lock<std::mutex> lk(mu);
+    const int64_t gen = generation;
+    if (++waiting == nranks) {
+      waiting = 0;
+      ++generation;
+      cv.notify_all();
+    } else {
+      cv.wait(lk, [&] { return generation != gen; });
+    }
+  }
+};
+
+static std::mutex g_groups_mu;
+static std::map<int, std::shared_ptr<LoopbackGroup>> g_groups;
+
+struct LoopbackHandle {
+  std::shared_ptr<LoopbackGroup> grp;
+};
+static std::map<dftfe_b200_ctx *, LoopbackHandle> g_handles;
+
+static LoopbackGroup *loopback_of(dftfe_b200_ctx *ctx) {
+  std::lock_guard<std::mutex> lk(g_groups_mu);
+  auto it = g_handles.find(ctx);
+  return it == g_handles.end() ? nullptr : it->second.grp.get();
+}
+
+void loopback_forget(dftfe_b200_ctx *ctx) {
+  std::lock_guard<std::mutex> lk(g_groups_mu);
+  g_handles.erase(ctx);
+}
+
+int loopback_join(dftfe_b200_ctx *ctx, int group_id, int rank, int nranks) {
+  std::lock_guard<std::mutex> lk(g_groups_mu);
+  auto &g = g_groups[group_id];
+  if (!g || g->nranks != nranks || (int)g->members.size() != nranks || g->members[rank] != nullptr) {
+    g = std::make_shared<LoopbackGroup>();
+    g->nranks = nranks;
+    g->members.assign(nranks, nullptr);
+    g->pub.assign(nranks, nullptr);
+  }
+  g->members[rank] = ctx;
+  g_handles[ctx] = LoopbackHandle{g};
+  return 0;
+}
+
+static int64_t target_offset(const dftfe_b200_ctx *c, int targetRank) {
+  for (size_t t = 0; t < c->targetProcs_h.size(); ++t)
+    if (c->targetProcs_h[t] == targetRank) return c->targetOffsets_h[t];
+  return -1;
+}
+
+// forward: owned rows needed by my targets -> their ghost rows
+int ghost_update(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx) {
+  if (ctx->nranks == 1) return 0;
+  DB_CHECK(ctx->nccl || loopback_of(ctx), "ghost exchange needs comm_init (NCCL) or a loopback group");
+  DB_TRY(ctx->sendBuf.alloc((size_t)ctx->nSend * ctx->B));
+  DB_TRY(ctx->recvBuf.alloc((size_t)std::max<int64_t>(ctx->G, ctx->nSend) * ctx->B));
+  DB_TRY(launch_pack_rows(ctx, x, ncols, ldx, ctx->nSend, ctx->sendRows.p, ctx->sendBuf.p));
+  const bool direct = (ldx == ncols);
+  double *ghostBase = direct ? x + (size_t)ctx->M * ldx : ctx->recvBuf.p;
+  if (ctx->nccl) {
+    DB_NCCL(ncclGroupStart());
+    for (size_t t = 0; t < ctx->targetProcs_h.size(); ++t)
+      DB_NCCL(ncclSend(ctx->sendBuf.p + (size_t)ctx->targetOffsets_h[t] * ncols,
+                       (size_t)ctx->nOwnedForTargets_h[t] * ncols, ncclDouble, ctx->targetProcs_h[t], ctx->nccl,
+                       ctx->stream));
+    for (size_t g = 0; g < ctx->ghostProcs_h.size(); ++g) {
+      const int64_t s = ctx->ghostRanges_h[2 * g], e = ctx->ghostRanges_h[2 * g + 1];
+      DB_NCCL(ncclRecv(ghostBase + (size_t)s * ncols, (size_t)(e - s) * ncols, ncclDouble, ctx->ghostProcs_h[g],
+                       ctx->nccl, ctx->stream));
+    }
+    DB_NCCL(ncclGroupEnd());
+  } else {
+    LoopbackGroup *grp = loopback_of(ctx);
+    DB_CUDA(cudaStreamSynchronize(ctx->stream));
+    grp->barrier();
+    for (size_t g = 0; g < ctx->ghostProcs_h.size(); ++g) {
+      const int64_t s = ctx->ghostRanges_h[2 * g], e = ctx->ghostRanges_h[2 * g + 1];
+      dftfe_b200_ctx *peer = grp->members[ctx->ghostProcs_h[g]];
+      const int64_t off = target_offset(peer, ctx->rank);
+      DB_CHECK(off >= 0, "loopback: rank %d is not a target of rank %d", ctx->rank, ctx->ghostProcs_h[g]);
+      DB_CUDA(cudaMemcpyAsync(ghostBase + (size_t)s * ncols, peer->sendBuf.p + (size_t)off * ncols,
+                              (size_t)(e - s) * ncols * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    DB_CUDA(cudaStreamSynchronize(ctx->stream));
+    grp->barrier();
+  }
+  if (!direct) DB_TRY(launch_copy_rows(ctx, x, ncols, ldx, ctx->M, ctx->G, ctx->recvBuf.p, 0));
+  return 0;
+}
+
+// reverse: my ghost rows -> added into their owners' rows (optionally scaled by rowScale[owner row])
+int ghost_accumulate(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx, const double *rowScale) {
+  if (ctx->nranks == 1) return 0;
+  DB_CHECK(ctx->nccl || loopback_of(ctx), "ghost exchange needs comm_init (NCCL) or a loopback group");
+  DB_TRY(ctx->sendBuf.alloc((size_t)std::max<int64_t>(ctx->G, ctx->nSend) * ctx->B));
+  DB_TRY(ctx->recvBuf.alloc((size_t)std::max<int64_t>(ctx->G, ctx->nSend) * ctx->B));
+  const bool direct = (ldx == ncols);
+  double *ghostBase = direct ? x + (size_t)ctx->M * ldx : ctx->sendBuf.p;
+  if (!direct) DB_TRY(launch_copy_rows(ctx, x, ncols, ldx, ctx->M, ctx->G, ctx->sendBuf.p, 1));
+  if (ctx->nccl) {
+    DB_NCCL(ncclGroupStart());
+    for (size_t g = 0; g < ctx->ghostProcs_h.size(); ++g) {
+      const int64_t s = ctx->ghostRanges_h[2 * g], e = ctx->ghostRanges_h[2 * g + 1];
+      DB_NCCL(ncclSend(ghostBase + (size_t)s * ncols, (size_t)(e - s) * ncols, ncclDouble, ctx->ghostProcs_h[g],
+                       ctx->nccl, ctx->stream));
+    }
+    for (size_t t = 0; t < ctx->targetProcs_h.size(); ++t)
+      DB_NCCL(ncclRecv(ctx->recvBuf.p + (size_t)ctx->targetOffsets_h[t] * ncols,
+                       (size_t)ctx->nOwnedForTargets_h[t] * ncols, ncclDouble, ctx->targetProcs_h[t], ctx->nccl,
+                       ctx->stream));
+    DB_NCCL(ncclGroupEnd());
+  } else {
+    LoopbackGroup *grp = loopback_of(ctx);
+    // publish where my ghost payload lives
+    DB_CUDA(cudaStreamSynchronize(ctx->stream));
+    grp->pub[ctx->rank] = ghostBase;
+    grp->barrier();
+    for (size_t t = 0; t < ctx->targetProcs_h.size(); ++t) {
+      dftfe_b200_ctx *peer = grp->members[ctx->targetProcs_h[t]];
+      // find my range inside the peer's ghost segment
+      int64_t s = -1, e = -1;
+      for (size_t g = 0; g < peer->ghostProcs_h.size(); ++g)
+        if (peer->ghostProcs_h[g] == ctx->rank) {
+          s = peer->ghostRanges_h[2 * g];
+          e = peer->ghostRanges_h[2 * g + 1];
+        }
+      DB_CHECK(s >= 0 && (e - s) == ctx->nOwnedForTargets_h[t], "loopback: inconsistent ghost pattern");
+      DB_CUDA(cudaMemcpyAsync(ctx->recvBuf.p + (size_t)ctx->targetOffsets_h[t] * ncols,
+                              grp->pub[peer->rank] + (size_t)s * ncols, (size_t)(e - s) * ncols * sizeof(double),
+                              cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+    DB_CUDA(cudaStreamSynchronize(ctx->stream));
+    grp->barrier();
+  }
+  DB_TRY(launch_unpack_add(ctx, x, ncols, ldx, ctx->recvBuf.p, rowScale));
+  return 0;
+}
+
+int ghost_zero(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx) {
+  if (ctx->G == 0) return 0;
+  ctx->launches += 1;
+  if (ldx == ncols) {
+    DB_CUDA(cudaMemsetAsync(x + (size_t)ctx->M * ldx, 0, (size_t)ctx->G * ldx * sizeof(double), ctx->stream));
+  } else {
+    DB_CUDA(cudaMemset2DAsync(x + (size_t)ctx->M * ldx, (size_t)ldx * sizeof(double), 0,
+                              (size_t)ncols * sizeof(double), (size_t)ctx->G, ctx->stream));
+  }
+  return 0;
+}
+
+int allreduce_sum(dftfe_b200_ctx *ctx, double *buf, size_t count) {
+  if (ctx->nranks == 1) return 0;
+  if (ctx->nccl) {
+    DB_NCCL(ncclAllReduce(buf, buf, count, ncclDouble, ncclSum, ctx->nccl, ctx->stream));
+    return 0;
+  }
+  LoopbackGroup *grp = loopback_of(ctx);
+  DB_CHECK(grp, "allreduce needs comm_init (NCCL) or a loopback group");
+  DB_TRY(ctx->arTmp.alloc(count));
+  DB_CUDA(cudaStreamSynchronize(ctx->stream));
+  grp->pub[ctx->rank] = buf;
+  grp->barrier();
+  // rank-ordered sum so every rank gets the identical result
+  DB_CUDA(cudaMemcpyAsync(ctx->arTmp.p, grp->pub[0], count * sizeof(double), cudaMemcpyDeviceToDevice,
+                          ctx->stream));
+  const double one = 1.0;
+  DB_CUBLAS(cublasSetStream(ctx->cublas, ctx->stream));
+  for (int r = 1; r < grp->nranks; ++r)
+    DB_CUBLAS(cublasDaxpy(ctx->cublas, (int)count, &one, grp->pub[r], 1, ctx->arTmp.p, 1));
+  DB_CUDA(cudaStreamSynchronize(ctx->stream));
+  grp->barrier();
+  DB_CUDA(cudaMemcpyAsync(buf, ctx->arTmp.p, count * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+  DB_CUDA(cudaStreamSynchronize(ctx->stream));
+  grp->barrier();
+  return 0;
+}
+
+}  // namespace dftfe_b200

@@ -1,0 +1,270 @@
+// Internal declarations shared by the translation units of libdftfe_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <cublas_v2.h>
+#include <cusolverDn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/dftfe_b200.h"
+
+namespace dftfe_b200 {
+
+void set_error(const char *fmt, ...);
+
+#define DB_CUDA(call)                                                                      \
+  do {                                                                                     \
+    cudaError_t e__ = (call);                                                              \
+    if (e__ != cudaSuccess) {                                                              \
+      ::dftfe_b200::set_error("CUDA error '%s' at %s:%d (%s)", cudaGetErrorString(e__),    \
+                              __FILE__, __LINE__, #call);                                  \
+      return DFTFE_B200_ERR_CUDA;                                                          \
+    }                                                                                      \
+  } while (0)
+
+#define DB_CUBLAS(call)                                                                    \
+  do {                                                                                     \
+    cublasStatus_t s__ = (call);                                                           \
+    if (s__ != CUBLAS_STATUS_SUCCESS) {                                                    \
+      ::dftfe_b200::set_error("cuBLAS error %d at %s:%d (%s)", (int)s__, __FILE__,         \
+                              __LINE__, #call);                                            \
+      return DFTFE_B200_ERR_CUDA;                                                          \
+    }                                                                                      \
+  } while (0)
+
+#define DB_CUSOLVER(call)                                                                  \
+  do {                                                                                     \
+    cusolverStatus_t s__ = (call);                                                         \
+    if (s__ != CUSOLVER_STATUS_SUCCESS) {                                                  \
+      ::dftfe_b200::set_error("cuSOLVER error %d at %s:%d (%s)", (int)s__, __FILE__,       \
+                              __LINE__, #call);                                            \
+      return DFTFE_B200_ERR_CUDA;                                                          \
+    }                                                                                      \
+  } while (0)
+
+#define DB_NCCL(call)                                                                      \
+  do {                                                                                     \
+    ncclResult_t r__ = (call);                                                             \
+    if (r__ != ncclSuccess) {                                                              \
+      ::dftfe_b200::set_error("NCCL error '%s' at %s:%d (%s)", ncclGetErrorString(r__),    \
+                              __FILE__, __LINE__, #call);                                  \
+      return DFTFE_B200_ERR_NCCL;                                                          \
+    }                                                                                      \
+  } while (0)
+
+#define DB_CHECK(cond, ...)                                                                \
+  do {                                                                                     \
+    if (!(cond)) {                                                                         \
+      ::dftfe_b200::set_error(__VA_ARGS__);                                                \
+      return DFTFE_B200_ERR_INVALID;                                                       \
+    }                                                                                      \
+  } while (0)
+
+#define DB_TRY(call)                                                                       \
+  do {                                                                                     \
+    int rc__ = (call);                                                                     \
+    if (rc__ != 0) return rc__;                                                            \
+  } while (0)
+
+template <typename T>
+struct DevBuf {
+  T *p = nullptr;
+  size_t n = 0;
+  ~DevBuf() { release(); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    n = 0;
+  }
+  int alloc(size_t count) {
+    if (count <= n && p) return 0;
+    release();
+    if (count == 0) return 0;
+    cudaError_t e = cudaMalloc(&p, count * sizeof(T));
+    if (e != cudaSuccess) {
+      set_error("cudaMalloc of %zu bytes failed: %s", count * sizeof(T), cudaGetErrorString(e));
+      p = nullptr;
+      return DFTFE_B200_ERR_CUDA;
+    }
+    n = count;
+    return 0;
+  }
+  int upload(const T *h, size_t count, cudaStream_t s) {
+    int rc = alloc(count);
+    if (rc) return rc;
+    if (count == 0) return 0;
+    cudaError_t e = cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) {
+      set_error("H2D copy failed: %s", cudaGetErrorString(e));
+      return DFTFE_B200_ERR_CUDA;
+    }
+    return 0;
+  }
+};
+
+struct ProfileSlot {
+  double total_ms = 0;
+  int64_t launches = 0;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
+};
+
+// Parameters of the fused cell kernel's epilogue (see cell_matvec.cu).
+struct EpilogueParams {
+  double a = 0.0;       // first touch: dst = rowA*a*src + rowB*b*dst + s*rowOut*(H src)
+  double b = 1.0;
+  double s = 1.0;
+  const double *rowIn = nullptr;   // gather scale per local row (nullptr -> 1)
+  const double *rowOut = nullptr;  // output scale per local row (nullptr -> 1)
+  const double *rowA = nullptr;    // multiplies a*src on first touch (nullptr -> 1)
+  const double *rowB = nullptr;    // multiplies b*dst on first touch (nullptr -> 1)
+};
+
+}  // namespace dftfe_b200
+
+struct dftfe_b200_ctx {
+  dftfe_b200_problem_desc desc{};
+  int n = 0;          // nodes per cell
+  int B = 0;          // cheby block
+  int64_t nC = 0, M = 0, G = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  cudaStream_t owned_stream = nullptr;
+  cudaStream_t comm_stream = nullptr;
+  cublasHandle_t cublas = nullptr;
+  cusolverDnHandle_t cusolver = nullptr;
+  int num_sms = 148;
+
+  // --- index map / colouring
+  bool have_map = false;
+  std::vector<uint32_t> cellRows_h;      // nC*n local row ids (map / B)
+  std::vector<int32_t> cellColour_h;     // nC
+  int nColours = 0;
+  std::vector<int32_t> colourStart_h;    // nColours+1
+  dftfe_b200::DevBuf<uint32_t> cellRowsFlagged;  // nC*n: bit31 = first touch, bits 0..30 = row
+  dftfe_b200::DevBuf<int32_t> colourCells;       // nC cell ids grouped by colour
+  dftfe_b200::DevBuf<uint32_t> orphanRows;       // rows no owned cell touches
+  int64_t nOrphan = 0;
+
+  // --- constraints
+  int64_t nCon = 0, nnz = 0;
+  std::vector<uint32_t> conRows_h;
+  dftfe_b200::DevBuf<uint32_t> conRows, conSizes, conStarts, conCols;
+  dftfe_b200::DevBuf<double> conVals, conInhom;
+  // transposed CSR (master -> slaves) for the atomics-free slave->master
+  int64_t nMasters = 0;
+  dftfe_b200::DevBuf<uint32_t> masterRows, masterStarts, masterSlaves;
+  dftfe_b200::DevBuf<double> masterVals;
+
+  // --- mass and derived per-row scale vectors (M+G each)
+  bool have_mass = false;
+  std::vector<double> sqrtM_h, invSqrtM_h;
+  dftfe_b200::DevBuf<double> sqrtM, invSqrtM;
+  dftfe_b200::DevBuf<double> rowIn;      // invSqrtM on free rows, 1 on constrained rows
+  dftfe_b200::DevBuf<double> rowOut;     // invSqrtM on owned free rows, 1 elsewhere
+  dftfe_b200::DevBuf<double> rowLive;    // 1 on owned free rows, 0 elsewhere
+  dftfe_b200::DevBuf<double> rowLiveInvSqrtM;  // invSqrtM on owned free rows, 0 elsewhere
+  dftfe_b200::DevBuf<double> rowOutRaw;  // 1 everywhere (owned) - used by bare HXCheby paths
+
+  // --- ghost pattern / NCCL
+  int rank = 0, nranks = 1;
+  std::vector<int32_t> ghostProcs_h, ghostRanges_h, targetProcs_h, nOwnedForTargets_h;
+  std::vector<int64_t> targetOffsets_h;
+  int64_t nSend = 0;
+  dftfe_b200::DevBuf<uint32_t> sendRows;         // ownedLocalIndicesForTargetProcs
+  dftfe_b200::DevBuf<double> sendBuf, recvBuf;   // nSend*B each
+  // transposed unpack map: boundary row -> positions in recvBuf
+  int64_t nBoundaryRows = 0;
+  dftfe_b200::DevBuf<uint32_t> bndRows, bndStarts, bndSlots;
+  ncclComm_t nccl = nullptr;
+  cudaEvent_t evCompute = nullptr, evComm = nullptr;
+
+  // --- cell Hamiltonian (fragment-major)
+  bool have_H = false;
+  dftfe_b200::DevBuf<double> Htiled;
+  dftfe_b200::DevBuf<double> Hstage;   // staging for host uploads
+
+  // --- solver state / scratch
+  dftfe_b200::DevBuf<double> blockX, blockY;      // (M+G)*B
+  dftfe_b200::DevBuf<double> HXfull;              // M*Bw
+  dftfe_b200::DevBuf<double> denseA, denseB, denseC, denseW;  // N*N scratch
+  dftfe_b200::DevBuf<double> eigDev, resDev;
+  dftfe_b200::DevBuf<double> partials;            // split-K / reduction workspace
+  dftfe_b200::DevBuf<double> arTmp;               // loopback all-reduce scratch
+  dftfe_b200::DevBuf<double> rotScratch;
+  dftfe_b200::DevBuf<int> devInfo;
+  dftfe_b200::DevBuf<double> cusolverWork;
+  double a0 = 0, bLow = 0, bUp = 0;
+  bool bounds_valid = false;
+
+  // --- profiling
+  bool profiling = false;
+  std::map<std::string, dftfe_b200::ProfileSlot> prof;
+  int64_t launches = 0;
+};
+
+namespace dftfe_b200 {
+
+// RAII-less helper: brackets a launch with events when profiling is on.
+struct ProfScope {
+  dftfe_b200_ctx *ctx;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  const char *name;
+  ProfScope(dftfe_b200_ctx *c, const char *nm, int nlaunch = 1) : ctx(c), name(nm) {
+    ctx->launches += nlaunch;
+    if (ctx->profiling) {
+      cudaEventCreate(&e0);
+      cudaEventCreate(&e1);
+      cudaEventRecord(e0, ctx->stream);
+    }
+  }
+  ~ProfScope() {
+    if (e0) {
+      cudaEventRecord(e1, ctx->stream);
+      auto &slot = ctx->prof[name];
+      slot.pending.emplace_back(e0, e1);
+      slot.launches += 1;
+    }
+  }
+};
+
+// ---- kernels / launchers implemented across the .cu files -----------------
+int cell_kernel_supported(int nodes_per_cell);
+int retile_cell_hamiltonian(dftfe_b200_ctx *ctx, const double *H_d);
+// dst (op)= H src through the coloured fused kernel; ncols must be a multiple of 32.
+int launch_cell_matvec(dftfe_b200_ctx *ctx, const double *src, double *dst, int ncols, int ldx,
+                       const EpilogueParams &ep);
+
+int launch_distribute(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx, const double *colScale);
+int launch_slave_to_master(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx, const double *masterScale);
+int launch_set_zero_rows(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx);
+
+int ghost_update(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx);
+int ghost_accumulate(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx, const double *rowScale);
+int ghost_zero(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx);
+
+int launch_row_scale(dftfe_b200_ctx *ctx, double *x, int64_t rows, int ncols, int ldx, double alpha,
+                     const double *rowScale);
+int launch_block_copy_from_full(dftfe_b200_ctx *ctx, const double *X, int N, int j0, double *blk, int ncols,
+                                int64_t rows, const double *rowScale);
+int launch_block_copy_to_full(dftfe_b200_ctx *ctx, double *X, int N, int j0, const double *blk, int ncols,
+                              int64_t rows, const double *rowScale);
+int launch_orphan_first_touch(dftfe_b200_ctx *ctx, const double *src, double *dst, int ncols, int ldx,
+                              const EpilogueParams &ep);
+
+int allreduce_sum(dftfe_b200_ctx *ctx, double *buf, size_t count);
+
+// high-level pieces (solver.cu)
+int op_hx(dftfe_b200_ctx *ctx, double *src, double *dst, int ncols, int scaleFlag, double scalar,
+          int doUnscale);
+int op_hx_cheby(dftfe_b200_ctx *ctx, double *src, double *dst, int ncols);
+int op_fused_apply(dftfe_b200_ctx *ctx, double *src, double *dst, int ncols, double a, double b, double s);
+
+}  // namespace dftfe_b200

@@ -1,0 +1,485 @@
+// Context lifetime and setup: the B200-native equivalent of
+// kohnShamDFTOperatorDeviceClass::reinit (src/dftOperator/kohnShamDFTOperatorDevice.cc:492-933).
+#include <algorithm>
+#include <cstring>
+#include <numeric>
+
+#include "common.cuh"
+
+namespace dftfe_b200 {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int loopback_join(dftfe_b200_ctx *ctx, int group_id, int rank, int nranks);
+void loopback_forget(dftfe_b200_ctx *ctx);
+
+// derived per-row scale vectors (see solver.cu: fused_apply_impl)
+static int rebuild_row_vectors(dftfe_b200_ctx *ctx, const double *sqrtM_h, const double *invSqrtM_h) {
+  const int64_t R = ctx->M + ctx->G;
+  std::vector<char> con(R, 0);
+  for (uint32_t r : ctx->conRows_h) con[r] = 1;
+  std::vector<double> rowIn(R), rowOut(R), rowLive(R), rowLiveInv(R);
+  for (int64_t r = 0; r < R; ++r) {
+    const bool owned = r < ctx->M;
+    rowIn[r] = con[r] ? 1.0 : invSqrtM_h[r];
+    rowOut[r] = (owned && !con[r]) ? invSqrtM_h[r] : 1.0;
+    rowLive[r] = (owned && !con[r]) ? 1.0 : 0.0;
+    rowLiveInv[r] = (owned && !con[r]) ? invSqrtM_h[r] : 0.0;
+  }
+  DB_TRY(ctx->rowIn.upload(rowIn.data(), R, ctx->stream));
+  DB_TRY(ctx->rowOut.upload(rowOut.data(), R, ctx->stream));
+  DB_TRY(ctx->rowLive.upload(rowLive.data(), R, ctx->stream));
+  DB_TRY(ctx->rowLiveInvSqrtM.upload(rowLiveInv.data(), R, ctx->stream));
+  (void)sqrtM_h;
+  return 0;
+}
+
+}  // namespace dftfe_b200
+
+using namespace dftfe_b200;
+
+#define DB_CTX(ctx)                                                   \
+  do {                                                                \
+    if (!(ctx)) {                                                     \
+      set_error("null context");                                      \
+      return DFTFE_B200_ERR_INVALID;                                  \
+    }                                                                 \
+    cudaError_t e__ = cudaSetDevice((ctx)->desc.device);              \
+    if (e__ != cudaSuccess) {                                         \
+      set_error("cudaSetDevice failed: %s", cudaGetErrorString(e__)); \
+      return DFTFE_B200_ERR_CUDA;                                     \
+    }                                                                 \
+  } while (0)
+
+extern "C" {
+
+const char *dftfe_b200_version(void) { return "dftfe_b200 0.1.0 (sm_100a)"; }
+const char *dftfe_b200_last_error(void) { return g_err; }
+
+int dftfe_b200_create(const dftfe_b200_problem_desc *desc, dftfe_b200_ctx **out) {
+  DB_CHECK(desc && out, "create: null argument");
+  DB_CHECK(desc->n_cells >= 0 && desc->n_owned >= 0 && desc->n_ghost >= 0, "create: negative size");
+  DB_CHECK(desc->cheby_block >= 1, "create: cheby_block must be >= 1");
+  DB_CHECK((desc->n_owned + desc->n_ghost) < (int64_t)0x7fffffff, "create: more than 2^31-1 local rows");
+  if (!cell_kernel_supported(desc->nodes_per_cell)) {
+    set_error("create: no sm_100a cell kernel for %d nodes per cell (supported FE orders 1..7)",
+              desc->nodes_per_cell);
+    return DFTFE_B200_ERR_UNSUPPORTED;
+  }
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    set_error("create: no CUDA device available (%s); this library has no CPU fallback",
+              e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    return DFTFE_B200_ERR_CUDA;
+  }
+  DB_CHECK(desc->device >= 0 && desc->device < ndev, "create: device %d out of range [0,%d)", desc->device, ndev);
+  DB_CUDA(cudaSetDevice(desc->device));
+  cudaDeviceProp prop;
+  DB_CUDA(cudaGetDeviceProperties(&prop, desc->device));
+  if (prop.major != 10) {
+    set_error("create: device %d is sm_%d%d; this library is built for sm_100a only", desc->device, prop.major,
+              prop.minor);
+    return DFTFE_B200_ERR_UNSUPPORTED;
+  }
+  auto *ctx = new dftfe_b200_ctx();
+  ctx->desc = *desc;
+  ctx->n = desc->nodes_per_cell;
+  ctx->B = desc->cheby_block;
+  ctx->nC = desc->n_cells;
+  ctx->M = desc->n_owned;
+  ctx->G = desc->n_ghost;
+  ctx->num_sms = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cublasCreate(&ctx->cublas) != CUBLAS_STATUS_SUCCESS ||
+      cusolverDnCreate(&ctx->cusolver) != CUSOLVER_STATUS_SUCCESS) {
+    set_error("create: stream / cuBLAS / cuSOLVER handle creation failed");
+    delete ctx;
+    return DFTFE_B200_ERR_CUDA;
+  }
+  ctx->own_stream = true;
+  ctx->owned_stream = ctx->stream;
+  *out = ctx;
+  return 0;
+}
+
+void dftfe_b200_destroy(dftfe_b200_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->desc.device);
+  cudaDeviceSynchronize();
+  loopback_forget(ctx);
+  for (auto &kv : ctx->prof)
+    for (auto &pr : kv.second.pending) {
+      cudaEventDestroy(pr.first);
+      cudaEventDestroy(pr.second);
+    }
+  if (ctx->nccl) ncclCommDestroy(ctx->nccl);
+  if (ctx->cusolver) cusolverDnDestroy(ctx->cusolver);
+  if (ctx->cublas) cublasDestroy(ctx->cublas);
+  if (ctx->owned_stream) cudaStreamDestroy(ctx->owned_stream);
+  delete ctx;
+}
+
+int dftfe_b200_set_stream(dftfe_b200_ctx *ctx, void *cuda_stream) {
+  DB_CTX(ctx);
+  DB_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->owned_stream;
+  return 0;
+}
+
+int dftfe_b200_sync(dftfe_b200_ctx *ctx) {
+  DB_CTX(ctx);
+  DB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int dftfe_b200_build_index_map(const int64_t *cell_global_dofs_h, int64_t n_cells, int32_t nodes_per_cell,
+                               int64_t owned_start, int64_t owned_end, const int64_t *ghost_sorted_h,
+                               int64_t n_ghost, int32_t block, uint64_t *map_out_h) {
+  DB_CHECK(cell_global_dofs_h && map_out_h && (n_ghost == 0 || ghost_sorted_h), "build_index_map: null argument");
+  const int64_t M = owned_end - owned_start;
+  const int64_t total = n_cells * nodes_per_cell;
+  for (int64_t k = 0; k < total; ++k) {
+    const int64_t g = cell_global_dofs_h[k];
+    int64_t loc;
+    if (g >= owned_start && g < owned_end) {
+      loc = g - owned_start;
+    } else {
+      const int64_t *it = std::lower_bound(ghost_sorted_h, ghost_sorted_h + n_ghost, g);
+      DB_CHECK(it != ghost_sorted_h + n_ghost && *it == g,
+               "build_index_map: global DoF %lld of cell entry %lld is neither owned nor ghost", (long long)g,
+               (long long)k);
+      loc = M + (it - ghost_sorted_h);
+    }
+    map_out_h[k] = (uint64_t)loc * (uint64_t)block;
+  }
+  return 0;
+}
+
+int dftfe_b200_set_index_map(dftfe_b200_ctx *ctx, const uint64_t *map_h) {
+  DB_CTX(ctx);
+  DB_CHECK(map_h || ctx->nC == 0, "set_index_map: null map");
+  const int n = ctx->n;
+  const int64_t nC = ctx->nC, R = ctx->M + ctx->G;
+  const int64_t total = nC * n;
+  ctx->cellRows_h.resize(total);
+  for (int64_t k = 0; k < total; ++k) {
+    DB_CHECK(map_h[k] % (uint64_t)ctx->B == 0, "set_index_map: entry %lld is not a multiple of the block size",
+             (long long)k);
+    const uint64_t r = map_h[k] / (uint64_t)ctx->B;
+    DB_CHECK((int64_t)r < R, "set_index_map: entry %lld points past the local vector (%llu >= %lld)", (long long)k,
+             (unsigned long long)r, (long long)R);
+    ctx->cellRows_h[k] = (uint32_t)r;
+  }
+  // row -> cells adjacency (CSR)
+  std::vector<int64_t> rowStart(R + 1, 0);
+  for (int64_t k = 0; k < total; ++k) rowStart[ctx->cellRows_h[k] + 1]++;
+  for (int64_t r = 0; r < R; ++r) rowStart[r + 1] += rowStart[r];
+  std::vector<int32_t> rowCells(total);
+  {
+    std::vector<int64_t> fill(rowStart.begin(), rowStart.end() - 1);
+    for (int64_t c = 0; c < nC; ++c)
+      for (int i = 0; i < n; ++i) rowCells[fill[ctx->cellRows_h[c * n + i]]++] = (int32_t)c;
+  }
+  // a cell must not list the same row twice (the assembly would race inside one CTA)
+  for (int64_t r = 0; r < R; ++r)
+    for (int64_t k = rowStart[r] + 1; k < rowStart[r + 1]; ++k)
+      DB_CHECK(rowCells[k] != rowCells[k - 1], "set_index_map: cell %d references local row %lld twice",
+               rowCells[k], (long long)r);
+  // greedy colouring of the cell adjacency graph (cells sharing a row are adjacent)
+  ctx->cellColour_h.assign(nC, -1);
+  int nColours = 0;
+  {
+    std::vector<int64_t> stamp;  // stamp[colour] == c  <=> colour used by a neighbour of c
+    for (int64_t c = 0; c < nC; ++c) {
+      for (int i = 0; i < n; ++i) {
+        const uint32_t r = ctx->cellRows_h[c * n + i];
+        for (int64_t k = rowStart[r]; k < rowStart[r + 1]; ++k) {
+          const int col = ctx->cellColour_h[rowCells[k]];
+          if (col >= 0) {
+            if ((int)stamp.size() <= col) stamp.resize(col + 1, -1);
+            stamp[col] = c;
+          }
+        }
+      }
+      int pick = 0;
+      while (pick < (int)stamp.size() && stamp[pick] == c) ++pick;
+      if ((int)stamp.size() <= pick) stamp.resize(pick + 1, -1);
+      ctx->cellColour_h[c] = pick;
+      nColours = std::max(nColours, pick + 1);
+    }
+  }
+  ctx->nColours = nColours;
+  ctx->colourStart_h.assign(nColours + 1, 0);
+  for (int64_t c = 0; c < nC; ++c) ctx->colourStart_h[ctx->cellColour_h[c] + 1]++;
+  for (int k = 0; k < nColours; ++k) ctx->colourStart_h[k + 1] += ctx->colourStart_h[k];
+  std::vector<int32_t> colourCells(nC);
+  {
+    std::vector<int32_t> fill(ctx->colourStart_h.begin(), ctx->colourStart_h.end() - 1);
+    for (int64_t c = 0; c < nC; ++c) colourCells[fill[ctx->cellColour_h[c]]++] = (int32_t)c;
+  }
+  // first-touch flags in colour processing order
+  std::vector<uint32_t> flagged(ctx->cellRows_h);
+  std::vector<char> touched(R, 0);
+  for (int64_t q = 0; q < nC; ++q) {
+    const int64_t c = colourCells[q];
+    for (int i = 0; i < n; ++i) {
+      const uint32_t r = ctx->cellRows_h[c * n + i];
+      if (!touched[r]) {
+        touched[r] = 1;
+        flagged[c * n + i] |= 0x80000000u;
+      }
+    }
+  }
+  std::vector<uint32_t> orphans;
+  for (int64_t r = 0; r < R; ++r)
+    if (!touched[r]) orphans.push_back((uint32_t)r);
+  ctx->nOrphan = (int64_t)orphans.size();
+  DB_TRY(ctx->cellRowsFlagged.upload(flagged.data(), flagged.size(), ctx->stream));
+  DB_TRY(ctx->colourCells.upload(colourCells.data(), colourCells.size(), ctx->stream));
+  DB_TRY(ctx->orphanRows.upload(orphans.data(), orphans.size(), ctx->stream));
+  ctx->have_map = true;
+  return 0;
+}
+
+int dftfe_b200_set_constraints(dftfe_b200_ctx *ctx, int64_t nCon, const uint32_t *rows_h, const uint32_t *sizes_h,
+                               const uint32_t *starts_h, const uint32_t *cols_h, const double *vals_h,
+                               const double *inhom_h) {
+  DB_CTX(ctx);
+  DB_CHECK(nCon >= 0, "set_constraints: negative count");
+  const int64_t R = ctx->M + ctx->G;
+  int64_t nnz = 0;
+  std::vector<char> isCon(R, 0);
+  for (int64_t i = 0; i < nCon; ++i) {
+    DB_CHECK((int64_t)rows_h[i] < R, "set_constraints: row %lld out of range", (long long)i);
+    DB_CHECK(!isCon[rows_h[i]], "set_constraints: row %u constrained twice", rows_h[i]);
+    isCon[rows_h[i]] = 1;
+    DB_CHECK((int64_t)starts_h[i] == nnz, "set_constraints: row_starts must be the exclusive prefix sum of sizes");
+    nnz += sizes_h[i];
+  }
+  for (int64_t k = 0; k < nnz; ++k) {
+    DB_CHECK((int64_t)cols_h[k] < R, "set_constraints: column entry %lld out of range", (long long)k);
+    DB_CHECK(!isCon[cols_h[k]], "set_constraints: column %u is itself constrained (constraints must be closed)",
+             cols_h[k]);
+  }
+  ctx->nCon = nCon;
+  ctx->nnz = nnz;
+  ctx->conRows_h.assign(rows_h, rows_h + nCon);
+  DB_TRY(ctx->conRows.upload(rows_h, nCon, ctx->stream));
+  DB_TRY(ctx->conSizes.upload(sizes_h, nCon, ctx->stream));
+  DB_TRY(ctx->conStarts.upload(starts_h, nCon, ctx->stream));
+  DB_TRY(ctx->conCols.upload(cols_h, nnz, ctx->stream));
+  DB_TRY(ctx->conVals.upload(vals_h, nnz, ctx->stream));
+  DB_TRY(ctx->conInhom.upload(inhom_h, nCon, ctx->stream));
+  // transposed CSR: master -> (slave, weight), entries in ascending (constraint, column) order
+  std::vector<uint32_t> cnt(R, 0);
+  for (int64_t k = 0; k < nnz; ++k) cnt[cols_h[k]]++;
+  std::vector<uint32_t> masters, mstarts(1, 0);
+  std::vector<int64_t> slotOf(R, -1);
+  for (int64_t r = 0; r < R; ++r)
+    if (cnt[r]) {
+      slotOf[r] = (int64_t)masters.size();
+      masters.push_back((uint32_t)r);
+      mstarts.push_back(mstarts.back() + cnt[r]);
+    }
+  std::vector<uint32_t> slaves(nnz), fill(mstarts.begin(), mstarts.end() - 1);
+  std::vector<double> mvals(nnz);
+  for (int64_t i = 0; i < nCon; ++i)
+    for (uint32_t j = 0; j < sizes_h[i]; ++j) {
+      const int64_t k = (int64_t)starts_h[i] + j;
+      const int64_t s = slotOf[cols_h[k]];
+      slaves[fill[s]] = rows_h[i];
+      mvals[fill[s]] = vals_h[k];
+      fill[s]++;
+    }
+  ctx->nMasters = (int64_t)masters.size();
+  DB_TRY(ctx->masterRows.upload(masters.data(), masters.size(), ctx->stream));
+  DB_TRY(ctx->masterStarts.upload(mstarts.data(), mstarts.size(), ctx->stream));
+  DB_TRY(ctx->masterSlaves.upload(slaves.data(), slaves.size(), ctx->stream));
+  DB_TRY(ctx->masterVals.upload(mvals.data(), mvals.size(), ctx->stream));
+  if (ctx->have_mass) DB_TRY(rebuild_row_vectors(ctx, ctx->sqrtM_h.data(), ctx->invSqrtM_h.data()));
+  return 0;
+}
+
+int dftfe_b200_set_mass(dftfe_b200_ctx *ctx, const double *sqrt_mass_h, const double *inv_sqrt_mass_h) {
+  DB_CTX(ctx);
+  DB_CHECK(sqrt_mass_h && inv_sqrt_mass_h, "set_mass: null argument");
+  const int64_t R = ctx->M + ctx->G;
+  ctx->sqrtM_h.assign(sqrt_mass_h, sqrt_mass_h + R);
+  ctx->invSqrtM_h.assign(inv_sqrt_mass_h, inv_sqrt_mass_h + R);
+  DB_TRY(ctx->sqrtM.upload(sqrt_mass_h, R, ctx->stream));
+  DB_TRY(ctx->invSqrtM.upload(inv_sqrt_mass_h, R, ctx->stream));
+  ctx->have_mass = true;
+  return rebuild_row_vectors(ctx, sqrt_mass_h, inv_sqrt_mass_h);
+}
+
+int dftfe_b200_set_ghost_pattern(dftfe_b200_ctx *ctx, int32_t rank, int32_t nranks, int32_t nGhostProcs,
+                                 const int32_t *ghostProcs_h, const int32_t *ghostRanges_h, int32_t nTargetProcs,
+                                 const int32_t *targetProcs_h, const int32_t *nOwnedForTargets_h,
+                                 const uint32_t *ownedIdx_h) {
+  DB_CTX(ctx);
+  DB_CHECK(nranks >= 1 && rank >= 0 && rank < nranks, "set_ghost_pattern: bad rank/nranks");
+  ctx->rank = rank;
+  ctx->nranks = nranks;
+  ctx->ghostProcs_h.assign(ghostProcs_h, ghostProcs_h + nGhostProcs);
+  ctx->ghostRanges_h.assign(ghostRanges_h, ghostRanges_h + 2 * nGhostProcs);
+  ctx->targetProcs_h.assign(targetProcs_h, targetProcs_h + nTargetProcs);
+  ctx->nOwnedForTargets_h.assign(nOwnedForTargets_h, nOwnedForTargets_h + nTargetProcs);
+  int64_t covered = 0;
+  for (int g = 0; g < nGhostProcs; ++g) {
+    DB_CHECK(ghostRanges_h[2 * g] == covered && ghostRanges_h[2 * g + 1] >= ghostRanges_h[2 * g],
+             "set_ghost_pattern: ghost ranges must tile the ghost segment contiguously");
+    covered = ghostRanges_h[2 * g + 1];
+  }
+  DB_CHECK(covered == ctx->G, "set_ghost_pattern: ghost ranges cover %lld rows, expected %lld", (long long)covered,
+           (long long)ctx->G);
+  ctx->targetOffsets_h.assign(nTargetProcs + 1, 0);
+  for (int t = 0; t < nTargetProcs; ++t)
+    ctx->targetOffsets_h[t + 1] = ctx->targetOffsets_h[t] + nOwnedForTargets_h[t];
+  ctx->nSend = ctx->targetOffsets_h[nTargetProcs];
+  for (int64_t k = 0; k < ctx->nSend; ++k)
+    DB_CHECK((int64_t)ownedIdx_h[k] < ctx->M, "set_ghost_pattern: send index %lld is not an owned row", (long long)k);
+  DB_TRY(ctx->sendRows.upload(ownedIdx_h, ctx->nSend, ctx->stream));
+  // transposed unpack map: boundary row -> receive slots (ascending = target order)
+  std::vector<uint32_t> cnt(ctx->M, 0);
+  for (int64_t k = 0; k < ctx->nSend; ++k) cnt[ownedIdx_h[k]]++;
+  std::vector<uint32_t> rows, starts(1, 0);
+  std::vector<int64_t> slotOf(ctx->M, -1);
+  for (int64_t r = 0; r < ctx->M; ++r)
+    if (cnt[r]) {
+      slotOf[r] = (int64_t)rows.size();
+      rows.push_back((uint32_t)r);
+      starts.push_back(starts.back() + cnt[r]);
+    }
+  std::vector<uint32_t> slots(ctx->nSend), fill(starts.begin(), starts.end() - 1);
+  for (int64_t k = 0; k < ctx->nSend; ++k) slots[fill[slotOf[ownedIdx_h[k]]]++] = (uint32_t)k;
+  ctx->nBoundaryRows = (int64_t)rows.size();
+  DB_TRY(ctx->bndRows.upload(rows.data(), rows.size(), ctx->stream));
+  DB_TRY(ctx->bndStarts.upload(starts.data(), starts.size(), ctx->stream));
+  DB_TRY(ctx->bndSlots.upload(slots.data(), slots.size(), ctx->stream));
+  return 0;
+}
+
+int dftfe_b200_nccl_unique_id(uint8_t id_out_h[128]) {
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
+  ncclUniqueId id;
+  DB_NCCL(ncclGetUniqueId(&id));
+  std::memcpy(id_out_h, &id, 128);
+  return 0;
+}
+
+int dftfe_b200_comm_init(dftfe_b200_ctx *ctx, const uint8_t id_h[128], int32_t rank, int32_t nranks) {
+  DB_CTX(ctx);
+  DB_CHECK(!ctx->nccl, "comm_init: communicator already initialised");
+  ncclUniqueId id;
+  std::memcpy(&id, id_h, 128);
+  DB_NCCL(ncclCommInitRank(&ctx->nccl, nranks, id, rank));
+  ctx->rank = rank;
+  ctx->nranks = nranks;
+  return 0;
+}
+
+int dftfe_b200_comm_init_loopback(dftfe_b200_ctx *ctx, int32_t group_id, int32_t rank, int32_t nranks) {
+  DB_CTX(ctx);
+  DB_CHECK(nranks >= 1 && rank >= 0 && rank < nranks, "comm_init_loopback: bad rank/nranks");
+  ctx->rank = rank;
+  ctx->nranks = nranks;
+  return loopback_join(ctx, group_id, rank, nranks);
+}
+
+int dftfe_b200_set_cell_hamiltonian(dftfe_b200_ctx *ctx, const double *H_d) {
+  DB_CTX(ctx);
+  DB_CHECK(H_d || ctx->nC == 0, "set_cell_hamiltonian: null pointer");
+  if (ctx->nC > 0) DB_TRY(retile_cell_hamiltonian(ctx, H_d));
+  DB_CUDA(cudaStreamSynchronize(ctx->stream));  // caller's buffer is free after return
+  ctx->have_H = true;
+  return 0;
+}
+
+int dftfe_b200_set_cell_hamiltonian_host(dftfe_b200_ctx *ctx, const double *H_h) {
+  DB_CTX(ctx);
+  const size_t count = (size_t)ctx->nC * ctx->n * ctx->n;
+  DB_TRY(ctx->Hstage.upload(H_h, count, ctx->stream));
+  int rc = dftfe_b200_set_cell_hamiltonian(ctx, ctx->Hstage.p);
+  ctx->Hstage.release();
+  return rc;
+}
+
+int dftfe_b200_update_ghost_values(dftfe_b200_ctx *ctx, double *x_d, int32_t ncols) {
+  DB_CTX(ctx);
+  return ghost_update(ctx, x_d, ncols, ncols);
+}
+int dftfe_b200_accumulate_add_locally_owned(dftfe_b200_ctx *ctx, double *x_d, int32_t ncols) {
+  DB_CTX(ctx);
+  return ghost_accumulate(ctx, x_d, ncols, ncols, nullptr);
+}
+int dftfe_b200_zero_out_ghosts(dftfe_b200_ctx *ctx, double *x_d, int32_t ncols) {
+  DB_CTX(ctx);
+  return ghost_zero(ctx, x_d, ncols, ncols);
+}
+int dftfe_b200_constraints_distribute(dftfe_b200_ctx *ctx, double *x_d, int32_t ncols) {
+  DB_CTX(ctx);
+  return launch_distribute(ctx, x_d, ncols, ncols, nullptr);
+}
+int dftfe_b200_constraints_distribute_slave_to_master(dftfe_b200_ctx *ctx, double *x_d, int32_t ncols) {
+  DB_CTX(ctx);
+  return launch_slave_to_master(ctx, x_d, ncols, ncols, nullptr);
+}
+int dftfe_b200_constraints_set_zero(dftfe_b200_ctx *ctx, double *x_d, int32_t ncols) {
+  DB_CTX(ctx);
+  return launch_set_zero_rows(ctx, x_d, ncols, ncols);
+}
+
+int dftfe_b200_get_colouring(dftfe_b200_ctx *ctx, int32_t *n_colours_out, int32_t *cell_colour_out_h) {
+  DB_CTX(ctx);
+  DB_CHECK(ctx->have_map, "get_colouring: set_index_map first");
+  if (n_colours_out) *n_colours_out = ctx->nColours;
+  if (cell_colour_out_h) std::memcpy(cell_colour_out_h, ctx->cellColour_h.data(), ctx->nC * sizeof(int32_t));
+  return 0;
+}
+
+int dftfe_b200_profile_enable(dftfe_b200_ctx *ctx, int32_t enable) {
+  DB_CTX(ctx);
+  ctx->profiling = enable != 0;
+  return 0;
+}
+
+static void profile_drain(dftfe_b200_ctx *ctx) {
+  cudaStreamSynchronize(ctx->stream);
+  for (auto &kv : ctx->prof) {
+    for (auto &pr : kv.second.pending) {
+      float ms = 0;
+      if (cudaEventElapsedTime(&ms, pr.first, pr.second) == cudaSuccess) kv.second.total_ms += ms;
+      cudaEventDestroy(pr.first);
+      cudaEventDestroy(pr.second);
+    }
+    kv.second.pending.clear();
+  }
+}
+
+int dftfe_b200_profile_get(dftfe_b200_ctx *ctx, const char *name, double *total_ms_out, int64_t *launches_out) {
+  DB_CTX(ctx);
+  profile_drain(ctx);
+  auto it = ctx->prof.find(name ? name : "");
+  if (total_ms_out) *total_ms_out = it == ctx->prof.end() ? 0.0 : it->second.total_ms;
+  if (launches_out) *launches_out = it == ctx->prof.end() ? 0 : it->second.launches;
+  return 0;
+}
+
+int dftfe_b200_profile_reset(dftfe_b200_ctx *ctx) {
+  DB_CTX(ctx);
+  profile_drain(ctx);
+  ctx->prof.clear();
+  return 0;
+}
+
+int64_t dftfe_b200_launch_count(dftfe_b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+}  // extern "C"

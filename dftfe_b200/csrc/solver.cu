@@ -1,0 +1,651 @@
+// Operator application, Chebyshev filter, projections, Rayleigh-Ritz and the
+// solve() driver.  Host C++ orchestration over the kernels of this library.
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+
+#include "common.cuh"
+
+namespace dftfe_b200 {
+
+// ---------------------------------------------------------------------------
+// operator
+// ---------------------------------------------------------------------------
+
+// dst = live*(a*src + b*dst) + s * M^-1/2 H M^-1/2 src   (Loewdin basis, fused)
+// One pass: ghost update -> distribute -> coloured fused cell kernel -> slave->master
+// -> ghost accumulate.  Constrained and ghost rows of dst end at 0.
+static int fused_apply_impl(dftfe_b200_ctx *ctx, double *src, double *dst, int ncols, double a, double b,
+                            double s, const double *rowB) {
+  DB_CHECK(ctx->have_mass, "set_mass must be called before applying the operator");
+  const int ldx = ncols;
+  DB_TRY(ghost_update(ctx, src, ncols, ldx));
+  DB_TRY(launch_distribute(ctx, src, ncols, ldx, ctx->invSqrtM.p));
+  EpilogueParams ep;
+  ep.a = a;
+  ep.b = b;
+  ep.s = s;
+  ep.rowIn = ctx->rowIn.p;
+  ep.rowOut = ctx->rowOut.p;
+  ep.rowA = ctx->rowLive.p;
+  ep.rowB = rowB;
+  DB_TRY(launch_cell_matvec(ctx, src, dst, ncols, ldx, ep));
+  DB_TRY(launch_orphan_first_touch(ctx, src, dst, ncols, ldx, ep));
+  DB_TRY(launch_slave_to_master(ctx, dst, ncols, ldx, ctx->rowOut.p));
+  DB_TRY(ghost_accumulate(ctx, dst, ncols, ldx, ctx->rowOut.p));
+  DB_TRY(ghost_zero(ctx, dst, ncols, ldx));
+  DB_TRY(ghost_zero(ctx, src, ncols, ldx));
+  return 0;
+}
+
+int op_fused_apply(dftfe_b200_ctx *ctx, double *src, double *dst, int ncols, double a, double b, double s) {
+  return fused_apply_impl(ctx, src, dst, ncols, a, b, s, ctx->rowLive.p);
+}
+
+// operatorDFTDeviceClass::HX net effect (kohnShamDFTOperatorDevice.cc:3765-3860)
+int op_hx(dftfe_b200_ctx *ctx, double *src, double *dst, int ncols, int scaleFlag, double scalar, int doUnscale) {
+  // dst <- (scaleFlag ? dst : M^-1/2 dst) + scalar * H~ src on owned free rows, 0 on constrained rows
+  DB_TRY(fused_apply_impl(ctx, src, dst, ncols, 0.0, 1.0, scalar,
+                          scaleFlag ? ctx->rowLive.p : ctx->rowLiveInvSqrtM.p));
+  // src side effects of the reference: constrained rows end at 0 (x M^1/2 = 0), ghosts zeroed;
+  // without unscaling the caller sees scalar * M^-1/2 * src.
+  if (doUnscale) {
+    DB_TRY(launch_set_zero_rows(ctx, src, ncols, ncols));
+  } else {
+    // (constrained rows keep the distributed, scaled values exactly as the reference leaves them)
+    DB_TRY(launch_row_scale(ctx, src, ctx->M, ncols, ncols, scalar, ctx->rowIn.p));
+  }
+  return 0;
+}
+
+// operatorDFTDeviceClass::HXCheby, FP64 (kohnShamDFTOperatorDevice.cc:3874-3997): dst += H src
+int op_hx_cheby(dftfe_b200_ctx *ctx, double *src, double *dst, int ncols) {
+  const int ldx = ncols;
+  DB_TRY(ghost_update(ctx, src, ncols, ldx));
+  DB_TRY(launch_distribute(ctx, src, ncols, ldx, nullptr));
+  EpilogueParams ep;  // a=0, b=1, s=1, no row scalings: pure accumulate
+  DB_TRY(launch_cell_matvec(ctx, src, dst, ncols, ldx, ep));
+  DB_TRY(launch_slave_to_master(ctx, dst, ncols, ldx, nullptr));
+  DB_TRY(ghost_zero(ctx, src, ncols, ldx));
+  DB_TRY(ghost_accumulate(ctx, dst, ncols, ldx, nullptr));
+  DB_TRY(ghost_zero(ctx, dst, ncols, ldx));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Chebyshev filter (linearAlgebraOperationsDevice.cc:531-727), Loewdin basis,
+// recurrence fused into the cell kernel epilogue: one HBM pass per degree.
+// ---------------------------------------------------------------------------
+static int cheb_filter_impl(dftfe_b200_ctx *ctx, double *x_d, double *y_d, int ncols, int m, double a, double b,
+                            double a0) {
+  DB_CHECK(m >= 1, "Chebyshev degree must be >= 1");
+  const double e = (b - a) / 2.0;
+  const double c = (b + a) / 2.0;
+  double sigma = e / (a0 - c);
+  const double sigma1 = sigma;
+  const double gamma = 2.0 / sigma1;
+  double *X = x_d, *Y = y_d;
+  // degree 1: Y = (sigma1/e) (H~ X - c X)
+  DB_TRY(op_fused_apply(ctx, X, Y, ncols, -c * sigma1 / e, 0.0, sigma1 / e));
+  for (int degree = 2; degree <= m; ++degree) {
+    const double sigma2 = 1.0 / (gamma - sigma);
+    const double alpha1 = 2.0 * sigma2 / e, alpha2 = -(sigma * sigma2);
+    // X <- alpha1 (H~ - c) Y + alpha2 X
+    DB_TRY(op_fused_apply(ctx, Y, X, ncols, -c * alpha1, alpha2, alpha1));
+    std::swap(X, Y);
+    sigma = sigma2;
+  }
+  if (Y != x_d) {
+    ctx->launches += 1;
+    DB_CUDA(cudaMemcpyAsync(x_d, Y, (size_t)(ctx->M + ctx->G) * ncols * sizeof(double), cudaMemcpyDeviceToDevice,
+                            ctx->stream));
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// projections / rotation
+// ---------------------------------------------------------------------------
+namespace {
+
+__global__ void symmetrise_from_lower_kernel(double *S, int N) {
+  // column-major lower -> full
+  const int64_t total = (int64_t)N * N;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int i = idx % N, j = idx / N;  // element (i,j) col-major
+    if (i < j) S[idx] = S[(int64_t)j + (int64_t)i * N];
+  }
+}
+
+// partial[blockIdx.x][col] = sum over this block's rows of (hx - lambda*x)^2
+__global__ void residual_partial_kernel(const double *__restrict__ X, int N, int j0, const double *__restrict__ HXb,
+                                        int ncols, int64_t rows, const double *__restrict__ eig,
+                                        double *__restrict__ partial) {
+  __shared__ double red[8][33];
+  const int col = blockIdx.y * 32 + threadIdx.x;
+  double acc = 0.0;
+  if (col < ncols) {
+    const double lam = eig[j0 + col];
+    for (int64_t r = blockIdx.x * 8 + threadIdx.y; r < rows; r += (int64_t)gridDim.x * 8) {
+      const double d = HXb[(size_t)r * ncols + col] - lam * X[(size_t)r * N + j0 + col];
+      acc += d * d;
+    }
+  }
+  red[threadIdx.y][threadIdx.x] = acc;
+  __syncthreads();
+  if (threadIdx.y == 0 && col < ncols) {
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) s += red[k][threadIdx.x];
+    partial[(size_t)blockIdx.x * ncols + col] = s;
+  }
+}
+
+__global__ void residual_final_kernel(const double *__restrict__ partial, int nParts, int ncols,
+                                      double *__restrict__ out) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col < ncols) {
+    double s = 0.0;
+    for (int p = 0; p < nParts; ++p) s += partial[(size_t)p * ncols + col];
+    out[col] = s;
+  }
+}
+
+__global__ void column_dot_partial_kernel(const double *__restrict__ x, const double *__restrict__ y, int64_t n,
+                                          double *__restrict__ partial) {
+  __shared__ double red[256];
+  double acc = 0.0;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    acc += x[i] * y[i];
+  red[threadIdx.x] = acc;
+  __syncthreads();
+  for (int s = 128; s > 0; s >>= 1) {
+    if (threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
+}
+
+__global__ void axpy_kernel(double *__restrict__ y, const double *__restrict__ x, double alpha, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] += alpha * x[i];
+}
+
+__global__ void scale_copy_kernel(double *__restrict__ y, const double *__restrict__ x, double alpha, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    y[i] = alpha * x[i];
+}
+
+}  // namespace
+
+static int ensure_block_scratch(dftfe_b200_ctx *ctx) {
+  DB_TRY(ctx->blockX.alloc((size_t)(ctx->M + ctx->G) * ctx->B));
+  DB_TRY(ctx->blockY.alloc((size_t)(ctx->M + ctx->G) * ctx->B));
+  return 0;
+}
+
+// S (col-major == row-major after symmetrisation) = X^T X, lower blocks then mirror
+static int xtx_impl(dftfe_b200_ctx *ctx, const double *X, int N, double *S) {
+  const int Bw = std::min(ctx->B, N);
+  const double one = 1.0, zero = 0.0;
+  DB_CUBLAS(cublasSetStream(ctx->cublas, ctx->stream));
+  DB_CUDA(cudaMemsetAsync(S, 0, (size_t)N * N * sizeof(double), ctx->stream));
+  if (ctx->M > 0) {
+    for (int j = 0; j < N; j += Bw) {
+      const int Bc = std::min(Bw, N - j), D = N - j;
+      ProfScope ps(ctx, "projection");
+      // block(D x Bc) = X_cm[j:, :] (D x M) * X_cm[j:j+Bc, :]^T
+      DB_CUBLAS(cublasDgemm(ctx->cublas, CUBLAS_OP_N, CUBLAS_OP_T, D, Bc, (int)ctx->M, &one, X + j, N, X + j, N,
+                            &zero, S + j + (size_t)j * N, N));
+    }
+  }
+  ctx->launches += 1;
+  symmetrise_from_lower_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(S, N);
+  DB_CUDA(cudaGetLastError());
+  DB_TRY(allreduce_sum(ctx, S, (size_t)N * N));
+  return 0;
+}
+
+// HXb(M x ncols, dense) = H~ * X[:, j0:j0+ncols]
+static int apply_H_to_columns(dftfe_b200_ctx *ctx, const double *X, int N, int j0, int ncols) {
+  DB_TRY(ensure_block_scratch(ctx));
+  DB_TRY(launch_block_copy_from_full(ctx, X, N, j0, ctx->blockX.p, ncols, ctx->M, nullptr));
+  DB_TRY(ghost_zero(ctx, ctx->blockX.p, ncols, ncols));
+  // dst = H~ src (b = 0: dst is never read)
+  DB_TRY(op_fused_apply(ctx, ctx->blockX.p, ctx->blockY.p, ncols, 0.0, 0.0, 1.0));
+  return 0;
+}
+
+static int xthx_impl(dftfe_b200_ctx *ctx, const double *X, int N, double *Hp) {
+  const int Bc0 = std::min(ctx->B, N);
+  const double one = 1.0, zero = 0.0;
+  DB_CUBLAS(cublasSetStream(ctx->cublas, ctx->stream));
+  DB_CUDA(cudaMemsetAsync(Hp, 0, (size_t)N * N * sizeof(double), ctx->stream));
+  for (int j = 0; j < N; j += Bc0) {
+    const int Bc = std::min(Bc0, N - j), D = N - j;
+    DB_TRY(apply_H_to_columns(ctx, X, N, j, Bc));
+    if (ctx->M > 0) {
+      ProfScope ps(ctx, "projection");
+      // block(D x Bc) = X_cm[j:, :] (D x M) * HXb_cm (Bc x M)^T
+      DB_CUBLAS(cublasDgemm(ctx->cublas, CUBLAS_OP_N, CUBLAS_OP_T, D, Bc, (int)ctx->M, &one, X + j, N,
+                            ctx->blockY.p, Bc, &zero, Hp + j + (size_t)j * N, N));
+    }
+  }
+  ctx->launches += 1;
+  symmetrise_from_lower_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(Hp, N);
+  DB_CUDA(cudaGetLastError());
+  DB_TRY(allreduce_sum(ctx, Hp, (size_t)N * N));
+  return 0;
+}
+
+// X <- X * Q.  qColMajor: Q memory holds Q(i,j) at i + j*N (cuSOLVER output), else row-major.
+static int rotate_impl(dftfe_b200_ctx *ctx, double *X, int N, const double *Q, bool qColMajor) {
+  if (ctx->M == 0) return 0;
+  const int64_t chunk = std::min<int64_t>(ctx->M, 16384);
+  DB_TRY(ctx->rotScratch.alloc((size_t)chunk * N));
+  const double one = 1.0, zero = 0.0;
+  DB_CUBLAS(cublasSetStream(ctx->cublas, ctx->stream));
+  for (int64_t r0 = 0; r0 < ctx->M; r0 += chunk) {
+    const int mc = (int)std::min<int64_t>(chunk, ctx->M - r0);
+    ProfScope ps(ctx, "rotation", 2);
+    // Xnew_cm (N x mc) = Q^T_(math) * X_cm ; row-major Q memory is col-major Q^T
+    DB_CUBLAS(cublasDgemm(ctx->cublas, qColMajor ? CUBLAS_OP_T : CUBLAS_OP_N, CUBLAS_OP_N, N, mc, N, &one, Q, N,
+                          X + (size_t)r0 * N, N, &zero, ctx->rotScratch.p, N));
+    DB_CUDA(cudaMemcpyAsync(X + (size_t)r0 * N, ctx->rotScratch.p, (size_t)mc * N * sizeof(double),
+                            cudaMemcpyDeviceToDevice, ctx->stream));
+  }
+  return 0;
+}
+
+static int residual_impl(dftfe_b200_ctx *ctx, const double *X, int N, const double *eig_h, double *res_h) {
+  DB_TRY(ctx->eigDev.alloc(N));
+  DB_TRY(ctx->resDev.alloc(N));
+  DB_CUDA(cudaMemcpyAsync(ctx->eigDev.p, eig_h, N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  const int Bc0 = std::min(ctx->B, N);
+  const int nParts = ctx->num_sms * 2;
+  DB_TRY(ctx->partials.alloc((size_t)nParts * Bc0));
+  for (int j = 0; j < N; j += Bc0) {
+    const int Bc = std::min(Bc0, N - j);
+    DB_TRY(apply_H_to_columns(ctx, X, N, j, Bc));
+    ProfScope ps(ctx, "residual", 2);
+    dim3 grid(nParts, (Bc + 31) / 32), block(32, 8);
+    residual_partial_kernel<<<grid, block, 0, ctx->stream>>>(X, N, j, ctx->blockY.p, Bc, ctx->M, ctx->eigDev.p,
+                                                             ctx->partials.p);
+    residual_final_kernel<<<(Bc + 127) / 128, 128, 0, ctx->stream>>>(ctx->partials.p, nParts, Bc,
+                                                                     ctx->resDev.p + j);
+    DB_CUDA(cudaGetLastError());
+  }
+  DB_TRY(allreduce_sum(ctx, ctx->resDev.p, N));
+  DB_CUDA(cudaMemcpyAsync(res_h, ctx->resDev.p, N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  DB_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < N; ++i) res_h[i] = std::sqrt(res_h[i]);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// Lanczos (linearAlgebraOperationsDevice.cc:340-527) - vectors stay on device
+// ---------------------------------------------------------------------------
+static int global_dot(dftfe_b200_ctx *ctx, const double *x, const double *y, double *out) {
+  const int nParts = 256;
+  DB_TRY(ctx->partials.alloc(nParts + 8));
+  ctx->launches += 2;
+  column_dot_partial_kernel<<<nParts, 256, 0, ctx->stream>>>(x, y, ctx->M, ctx->partials.p);
+  residual_final_kernel<<<1, 32, 0, ctx->stream>>>(ctx->partials.p, nParts, 1, ctx->partials.p + nParts);
+  DB_CUDA(cudaGetLastError());
+  DB_TRY(allreduce_sum(ctx, ctx->partials.p + nParts, 1));
+  DB_CUDA(cudaMemcpyAsync(out, ctx->partials.p + nParts, sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  DB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// symmetric eigenvalues by cyclic Jacobi (n <= 40)
+static void jacobi_eigenvalues(std::vector<double> &A, int n, std::vector<double> &ev) {
+  for (int sweep = 0; sweep < 100; ++sweep) {
+    double off = 0.0;
+    for (int i = 0; i < n; ++i)
+      for (int j = 0; j < i; ++j) off += A[i * n + j] * A[i * n + j];
+    if (off < 1e-30) break;
+    for (int p = 0; p < n; ++p)
+      for (int q = p + 1; q < n; ++q) {
+        const double apq = A[p * n + q];
+        if (std::fabs(apq) < 1e-300) continue;
+        const double theta = (A[q * n + q] - A[p * n + p]) / (2.0 * apq);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (std::fabs(theta) + std::sqrt(theta * theta + 1.0));
+        const double cs = 1.0 / std::sqrt(t * t + 1.0), sn = t * cs;
+        for (int k = 0; k < n; ++k) {
+          const double akp = A[k * n + p], akq = A[k * n + q];
+          A[k * n + p] = cs * akp - sn * akq;
+          A[k * n + q] = sn * akp + cs * akq;
+        }
+        for (int k = 0; k < n; ++k) {
+          const double apk = A[p * n + k], aqk = A[q * n + k];
+          A[p * n + k] = cs * apk - sn * aqk;
+          A[q * n + k] = sn * apk + cs * aqk;
+        }
+      }
+  }
+  ev.resize(n);
+  for (int i = 0; i < n; ++i) ev[i] = A[i * n + i];
+  std::sort(ev.begin(), ev.end());
+}
+
+static int lanczos_impl(dftfe_b200_ctx *ctx, int reproducible, double out[2]) {
+  const int iters = reproducible ? 40 : 20;
+  const int64_t rows = ctx->M + ctx->G;
+  DB_TRY(ensure_block_scratch(ctx));
+  DB_CHECK(ctx->B >= 4 || rows == 0 || true, "unreachable");
+  // three single-column vectors carved out of blockX/blockY scratch would alias the
+  // operator scratch, so use a dedicated buffer
+  DB_TRY(ctx->HXfull.alloc((size_t)rows * 4));
+  double *v = ctx->HXfull.p, *f = v + rows, *v0 = f + rows, *src = v0 + rows;
+  std::vector<double> hv(rows, 0.0);
+  std::srand(ctx->rank);
+  for (int64_t i = 0; i < ctx->M; ++i) hv[i] = ((double)std::rand()) / ((double)RAND_MAX);
+  for (uint32_t r : ctx->conRows_h)
+    if (r < ctx->M) hv[r] = 0.0;
+  DB_CUDA(cudaMemcpyAsync(v, hv.data(), rows * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  double nrm2 = 0;
+  DB_TRY(global_dot(ctx, v, v, &nrm2));
+  const int g = ctx->num_sms * 4;
+  ctx->launches += 1;
+  scale_copy_kernel<<<g, 256, 0, ctx->stream>>>(v, v, 1.0 / std::sqrt(nrm2), rows);
+
+  auto applyH = [&](const double *in, double *outv) -> int {
+    ctx->launches += 1;
+    DB_CUDA(cudaMemcpyAsync(src, in, rows * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    return op_fused_apply(ctx, src, outv, 1, 0.0, 0.0, 1.0);
+  };
+  std::vector<double> T((size_t)iters * iters, 0.0);
+  double alpha = 0, beta = 0;
+  DB_TRY(applyH(v, f));
+  DB_TRY(global_dot(ctx, f, v, &alpha));
+  ctx->launches += 1;
+  axpy_kernel<<<g, 256, 0, ctx->stream>>>(f, v, -alpha, ctx->M);
+  T[0] = alpha;
+  for (int j = 1; j < iters; ++j) {
+    double ff = 0;
+    DB_TRY(global_dot(ctx, f, f, &ff));
+    beta = std::sqrt(ff);
+    ctx->launches += 3;
+    DB_CUDA(cudaMemcpyAsync(v0, v, rows * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    scale_copy_kernel<<<g, 256, 0, ctx->stream>>>(v, f, 1.0 / beta, ctx->M);
+    DB_TRY(applyH(v, f));
+    axpy_kernel<<<g, 256, 0, ctx->stream>>>(f, v0, -beta, ctx->M);
+    DB_TRY(global_dot(ctx, f, v, &alpha));
+    ctx->launches += 1;
+    axpy_kernel<<<g, 256, 0, ctx->stream>>>(f, v, -alpha, ctx->M);
+    T[(size_t)j * iters + j - 1] = beta;
+    T[(size_t)(j - 1) * iters + j] = beta;
+    T[(size_t)j * iters + j] = alpha;
+  }
+  DB_CUDA(cudaGetLastError());
+  std::vector<double> ev;
+  jacobi_eigenvalues(T, iters, ev);
+  double ff = 0;
+  DB_TRY(global_dot(ctx, f, f, &ff));
+  const double fnorm = std::sqrt(ff);
+  out[0] = std::floor(ev[0]);
+  out[1] = std::ceil(ev[iters - 1] + (reproducible ? fnorm : fnorm / 10.0));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
+// dense N x N step on device (reference: host ScaLAPACK/ELPA,
+// src/linAlg/rayleighRitzDevice.cc:485-782)
+// ---------------------------------------------------------------------------
+static int dense_check_info(dftfe_b200_ctx *ctx, const char *what) {
+  int info = 0;
+  DB_CUDA(cudaMemcpyAsync(&info, ctx->devInfo.p, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  DB_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (info != 0) {
+    set_error("%s failed: info = %d", what, info);
+    return DFTFE_B200_ERR_NUMERIC;
+  }
+  return 0;
+}
+
+static int dense_cholesky(dftfe_b200_ctx *ctx, double *S, int N) {
+  DB_CUSOLVER(cusolverDnSetStream(ctx->cusolver, ctx->stream));
+  DB_TRY(ctx->devInfo.alloc(1));
+  int lwork = 0;
+  DB_CUSOLVER(cusolverDnDpotrf_bufferSize(ctx->cusolver, CUBLAS_FILL_MODE_LOWER, N, S, N, &lwork));
+  DB_TRY(ctx->cusolverWork.alloc(lwork));
+  ctx->launches += 1;
+  DB_CUSOLVER(cusolverDnDpotrf(ctx->cusolver, CUBLAS_FILL_MODE_LOWER, N, S, N, ctx->cusolverWork.p, lwork,
+                               ctx->devInfo.p));
+  return dense_check_info(ctx, "Cholesky factorisation of X^T X (cusolverDnDpotrf)");
+}
+
+static int dense_eigh(dftfe_b200_ctx *ctx, double *A, int N, double *W) {
+  DB_CUSOLVER(cusolverDnSetStream(ctx->cusolver, ctx->stream));
+  DB_TRY(ctx->devInfo.alloc(1));
+  int lwork = 0;
+  DB_CUSOLVER(cusolverDnDsyevd_bufferSize(ctx->cusolver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, N, A, N,
+                                          W, &lwork));
+  DB_TRY(ctx->cusolverWork.alloc(lwork));
+  ctx->launches += 1;
+  DB_CUSOLVER(cusolverDnDsyevd(ctx->cusolver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, N, A, N, W,
+                               ctx->cusolverWork.p, lwork, ctx->devInfo.p));
+  return dense_check_info(ctx, "eigendecomposition of the projected Hamiltonian (cusolverDnDsyevd)");
+}
+
+// rayleighRitzGEP (src/linAlg/rayleighRitzDevice.cc:355-819)
+static int rr_gep(dftfe_b200_ctx *ctx, double *X, int N, double *eig_h) {
+  const size_t nn = (size_t)N * N;
+  DB_TRY(ctx->denseA.alloc(nn));
+  DB_TRY(ctx->denseB.alloc(nn));
+  DB_TRY(ctx->eigDev.alloc(N));
+  double *S = ctx->denseA.p, *Hp = ctx->denseB.p;
+  const double one = 1.0;
+  DB_TRY(xtx_impl(ctx, X, N, S));
+  DB_TRY(dense_cholesky(ctx, S, N));  // S lower <- L
+  DB_TRY(xthx_impl(ctx, X, N, Hp));
+  DB_CUBLAS(cublasSetStream(ctx->cublas, ctx->stream));
+  ctx->launches += 2;
+  // Hs = L^-1 Hp L^-T
+  DB_CUBLAS(cublasDtrsm(ctx->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, N,
+                        N, &one, S, N, Hp, N));
+  DB_CUBLAS(cublasDtrsm(ctx->cublas, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT,
+                        N, N, &one, S, N, Hp, N));
+  DB_TRY(dense_eigh(ctx, Hp, N, ctx->eigDev.p));  // Hp <- Q' (columns)
+  // R = L^-T Q'
+  ctx->launches += 1;
+  DB_CUBLAS(cublasDtrsm(ctx->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, N,
+                        N, &one, S, N, Hp, N));
+  DB_TRY(rotate_impl(ctx, X, N, Hp, true));
+  DB_CUDA(cudaMemcpyAsync(eig_h, ctx->eigDev.p, N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  DB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// pseudoGramSchmidtOrthogonalization + rayleighRitz
+// (src/linAlg/pseudoGSDevice.cc:81-463, src/linAlg/rayleighRitzDevice.cc:81-353)
+static int cgs_rr(dftfe_b200_ctx *ctx, double *X, int N, double *eig_h) {
+  const size_t nn = (size_t)N * N;
+  DB_TRY(ctx->denseA.alloc(nn));
+  DB_TRY(ctx->denseB.alloc(nn));
+  DB_TRY(ctx->eigDev.alloc(N));
+  double *S = ctx->denseA.p, *Hp = ctx->denseB.p;
+  const double one = 1.0;
+  DB_TRY(xtx_impl(ctx, X, N, S));
+  DB_TRY(dense_cholesky(ctx, S, N));
+  // Linv^T as a column-major matrix: solve L^T Z = I
+  ctx->launches += 2;
+  DB_CUDA(cudaMemsetAsync(Hp, 0, nn * sizeof(double), ctx->stream));
+  {
+    std::vector<double> eye(nn, 0.0);
+    for (int i = 0; i < N; ++i) eye[(size_t)i * N + i] = 1.0;
+    DB_CUDA(cudaMemcpyAsync(Hp, eye.data(), nn * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    DB_CUDA(cudaStreamSynchronize(ctx->stream));
+  }
+  DB_CUBLAS(cublasSetStream(ctx->cublas, ctx->stream));
+  DB_CUBLAS(cublasDtrsm(ctx->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, N,
+                        N, &one, S, N, Hp, N));
+  DB_TRY(rotate_impl(ctx, X, N, Hp, true));  // X <- X L^-T
+  DB_TRY(xthx_impl(ctx, X, N, Hp));
+  DB_TRY(dense_eigh(ctx, Hp, N, ctx->eigDev.p));
+  DB_TRY(rotate_impl(ctx, X, N, Hp, true));
+  DB_CUDA(cudaMemcpyAsync(eig_h, ctx->eigDev.p, N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  DB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+static const unsigned int order_lookup[][2] = {{500, 24},     {750, 30},     {1000, 39},    {1500, 50},
+                                               {2000, 53},    {3000, 57},    {4000, 62},    {5000, 69},
+                                               {9000, 77},    {14000, 104},  {20000, 119},  {30000, 162},
+                                               {50000, 300},  {80000, 450},  {100000, 550}, {200000, 700},
+                                               {500000, 1000}};
+
+static unsigned int set_chebyshev_order(double upperBound) {
+  for (const auto &row : order_lookup)
+    if (upperBound <= row[0]) return row[1];
+  return 1250;
+}
+
+static int solve_impl(dftfe_b200_ctx *ctx, double *X, int N, const dftfe_b200_solve_params *p, double *eig_h,
+                      double *res_h, double *upper_h) {
+  const int B = std::min(ctx->B, N);
+  DB_CHECK(N % B == 0, "number of wavefunctions (%d) must be a multiple of the Chebyshev block size (%d)", N, B);
+  DB_TRY(ensure_block_scratch(ctx));
+  // spectrum bounds (solver .cc:241-297)
+  if (p->is_first_filtering_call || !ctx->bounds_valid) {
+    double bounds[2];
+    DB_TRY(lanczos_impl(ctx, p->reproducible_output, bounds));
+    ctx->a0 = bounds[0];
+    ctx->bUp = bounds[1];
+    ctx->bLow = ctx->a0 + (ctx->bUp - ctx->a0) * (double)N / (double)ctx->desc.n_global_dofs *
+                              (p->reproducible_output ? 10.0 : 200.0);
+    ctx->bounds_valid = true;
+  } else if (!p->reuse_lanczos_upper_bound) {
+    double bounds[2];
+    DB_TRY(lanczos_impl(ctx, p->reproducible_output, bounds));
+    ctx->bUp = bounds[1];
+  }
+  unsigned int order = p->chebyshev_order;
+  if (order == 0) {
+    order = set_chebyshev_order(ctx->bUp);
+    if (p->use_cgs_rr == 0 && !p->is_pseudopotential) {
+      // orthogType == "CGS" on device and all-electron: half degree (solver .cc:314-316)
+      order = (unsigned int)(order * 0.5);
+    }
+  }
+  if (p->is_first_scf && p->is_pseudopotential) order = (unsigned int)(order * p->first_scf_scaling);
+  if (order < 1) order = 1;
+
+  // X <- M^1/2 X (solver .cc:358-363) fused into the block copy; filter; copy back (:376-526)
+  for (int j = 0; j < N; j += B) {
+    DB_TRY(launch_block_copy_from_full(ctx, X, N, j, ctx->blockX.p, B, ctx->M, ctx->sqrtM.p));
+    DB_TRY(ghost_zero(ctx, ctx->blockX.p, B, B));
+    DB_TRY(cheb_filter_impl(ctx, ctx->blockX.p, ctx->blockY.p, B, (int)order, ctx->bLow, ctx->bUp, ctx->a0));
+    DB_TRY(launch_block_copy_to_full(ctx, X, N, j, ctx->blockX.p, B, ctx->M, nullptr));
+  }
+  if (p->use_cgs_rr)
+    DB_TRY(cgs_rr(ctx, X, N, eig_h));
+  else
+    DB_TRY(rr_gep(ctx, X, N, eig_h));
+  if (p->compute_residual && res_h) DB_TRY(residual_impl(ctx, X, N, eig_h, res_h));
+  // X <- M^-1/2 X (solver .cc:719-733)
+  DB_TRY(launch_row_scale(ctx, X, ctx->M, N, N, 1.0, ctx->invSqrtM.p));
+  if (upper_h) *upper_h = ctx->bUp;
+  DB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+}  // namespace dftfe_b200
+
+// ===========================================================================
+// C ABI
+// ===========================================================================
+using namespace dftfe_b200;
+
+#define DB_CTX(ctx)                                  \
+  do {                                               \
+    if (!(ctx)) {                                    \
+      set_error("null context");                     \
+      return DFTFE_B200_ERR_INVALID;                 \
+    }                                                \
+    cudaError_t e__ = cudaSetDevice((ctx)->desc.device); \
+    if (e__ != cudaSuccess) {                        \
+      set_error("cudaSetDevice failed: %s", cudaGetErrorString(e__)); \
+      return DFTFE_B200_ERR_CUDA;                    \
+    }                                                \
+  } while (0)
+
+static int check_cols(dftfe_b200_ctx *ctx, int ncols) {
+  DB_CHECK(ncols >= 1 && ncols <= ctx->B, "ncols (%d) must be in [1, cheby_block=%d]", ncols, ctx->B);
+  return 0;
+}
+
+extern "C" {
+
+int dftfe_b200_hx(dftfe_b200_ctx *ctx, double *src_d, double *dst_d, int32_t ncols, int32_t scale_flag,
+                  double scalar, int32_t do_unscaling_src) {
+  DB_CTX(ctx);
+  DB_TRY(check_cols(ctx, ncols));
+  DB_CHECK(scalar != 0.0, "HX: scalar must be non-zero");
+  return op_hx(ctx, src_d, dst_d, ncols, scale_flag, scalar, do_unscaling_src);
+}
+
+int dftfe_b200_hx_cheby(dftfe_b200_ctx *ctx, double *src_d, double *dst_d, int32_t ncols) {
+  DB_CTX(ctx);
+  DB_TRY(check_cols(ctx, ncols));
+  return op_hx_cheby(ctx, src_d, dst_d, ncols);
+}
+
+int dftfe_b200_cheb_filter(dftfe_b200_ctx *ctx, double *x_d, double *y_d, int32_t ncols, int32_t m, double a,
+                           double b, double a0) {
+  DB_CTX(ctx);
+  DB_TRY(check_cols(ctx, ncols));
+  return cheb_filter_impl(ctx, x_d, y_d, ncols, m, a, b, a0);
+}
+
+int dftfe_b200_xtx(dftfe_b200_ctx *ctx, const double *X_d, int32_t N, double *S_d) {
+  DB_CTX(ctx);
+  return xtx_impl(ctx, X_d, N, S_d);
+}
+
+int dftfe_b200_xthx(dftfe_b200_ctx *ctx, const double *X_d, int32_t N, double *Hp_d) {
+  DB_CTX(ctx);
+  return xthx_impl(ctx, X_d, N, Hp_d);
+}
+
+int dftfe_b200_rotate(dftfe_b200_ctx *ctx, double *X_d, int32_t N, const double *Q_d) {
+  DB_CTX(ctx);
+  return rotate_impl(ctx, X_d, N, Q_d, false);
+}
+
+int dftfe_b200_lanczos_bounds(dftfe_b200_ctx *ctx, int32_t reproducible, double bounds_out_h[2]) {
+  DB_CTX(ctx);
+  return lanczos_impl(ctx, reproducible, bounds_out_h);
+}
+
+int dftfe_b200_residual_norms(dftfe_b200_ctx *ctx, const double *X_d, int32_t N, const double *eig_h,
+                              double *res_out_h) {
+  DB_CTX(ctx);
+  return residual_impl(ctx, X_d, N, eig_h, res_out_h);
+}
+
+int dftfe_b200_reinit_spectrum_bounds(dftfe_b200_ctx *ctx, double lower_wanted, double lower_unwanted) {
+  DB_CTX(ctx);
+  ctx->a0 = lower_wanted;
+  ctx->bLow = lower_unwanted;
+  return 0;
+}
+
+int dftfe_b200_get_spectrum_bounds(dftfe_b200_ctx *ctx, double out_h[3]) {
+  DB_CTX(ctx);
+  out_h[0] = ctx->a0;
+  out_h[1] = ctx->bLow;
+  out_h[2] = ctx->bUp;
+  return 0;
+}
+
+int dftfe_b200_solve(dftfe_b200_ctx *ctx, double *X_d, int32_t N, const dftfe_b200_solve_params *params,
+                     double *eig_out_h, double *res_out_h, double *upper_bound_out_h) {
+  DB_CTX(ctx);
+  DB_CHECK(params && eig_out_h, "solve: params and eig_out_h are required");
+  return solve_impl(ctx, X_d, N, params, eig_out_h, res_out_h, upper_bound_out_h);
+}
+
+}  // extern "C"

@@ -1,0 +1,215 @@
+/*
+ * dftfe_b200 - C ABI of the B200-native Chebyshev-filtered subspace iteration
+ * (ChFSI) hot path of DFT-FE.
+ *
+ * DFT-FE has no plugin/FFI layer: its boundary for this path is the pure
+ * virtual C++ class operatorDFTDeviceClass (include/operatorDevice.h:43-420) and
+ * chebyshevOrthogonalizedSubspaceIterationSolverDevice
+ * (include/chebyshevOrthogonalizedSubspaceIterationSolverDevice.h:48-124), whose
+ * signatures leak deal.II / ScaLAPACK / MPI types.  This header is the flat
+ * equivalent over plain arrays; dftfe_b200/shim/ holds the C++ adapter classes
+ * with the reference's method names and argument order, INTEGRATION.md shows the
+ * binding a DFT-FE maintainer adds.  Every entry point cites the reference
+ * interface it replaces (paths relative to the dftfeDevelopers/dftfe tree).
+ *
+ * Conventions
+ *  - one context per (rank, GPU); not re-entrant; all device work is enqueued on
+ *    the context's stream (dftfe_b200_set_stream) and is asynchronous unless the
+ *    entry point returns host data (then it synchronises that stream).
+ *  - every function returns 0 on success or a negative dftfe_b200_status;
+ *    dftfe_b200_last_error() gives the message.  No exit(), no exceptions
+ *    (the reference printf+exit()s on CUDA/NCCL errors,
+ *    include/DeviceExceptions.cu.h:21-47).
+ *  - pointers suffixed _h are host pointers (copied during the call), _d are
+ *    device pointers (borrowed for the duration of the call unless stated).
+ *  - multivectors are row-major (M+G) x B doubles, wavefunction index fastest,
+ *    ghost rows after the M owned rows (include/MultiVector.h:41-75).  The full
+ *    wavefunction matrix X is row-major M x N, owned rows only
+ *    (src/dft/kohnShamEigenSolve.cc:571-581).
+ *  - there is NO CPU fallback: every compute entry point runs CUDA kernels built
+ *    for sm_100a and fails with DFTFE_B200_ERR_CUDA when no such device exists.
+ */
+#ifndef DFTFE_B200_H
+#define DFTFE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct dftfe_b200_ctx dftfe_b200_ctx;
+
+typedef enum {
+  DFTFE_B200_OK = 0,
+  DFTFE_B200_ERR_INVALID = -1, /* bad argument / call order            */
+  DFTFE_B200_ERR_CUDA = -2,    /* CUDA runtime / cuSOLVER / cuBLAS     */
+  DFTFE_B200_ERR_NCCL = -3,
+  DFTFE_B200_ERR_UNSUPPORTED = -4, /* e.g. nodes_per_cell without a kernel */
+  DFTFE_B200_ERR_NUMERIC = -5      /* Cholesky / eigensolver failure       */
+} dftfe_b200_status;
+
+/* Sizes of one rank's share of the FE problem.  Mirrors what
+ * kohnShamDFTOperatorDeviceClass::reinit(B, flag) reads from dftClass /
+ * MatrixFree (src/dftOperator/kohnShamDFTOperatorDevice.cc:492-624). */
+typedef struct {
+  int32_t nodes_per_cell;  /* n = (FEOrder+1)^3                                 */
+  int32_t cheby_block;     /* B = chebyWfcBlockSize (utils/dftParameters.cc:899) */
+  int64_t n_cells;         /* locally owned cells                               */
+  int64_t n_owned;         /* M: locally owned DoFs                             */
+  int64_t n_ghost;         /* G: ghost DoFs                                     */
+  int64_t n_global_dofs;   /* size of the global vector (Lanczos bLow heuristic) */
+  int32_t device;          /* CUDA device ordinal                               */
+  int32_t reserved;
+} dftfe_b200_problem_desc;
+
+/* Knobs of solve(); restates the dftParameters members the hot path reads
+ * (utils/dftParameters.cc). */
+typedef struct {
+  int32_t chebyshev_order;       /* 0 = table lookup on the upper bound (solver .cc:29-46) */
+  int32_t wfc_block;             /* Bw = wfcBlockSize; 0 -> cheby_block                     */
+  int32_t is_first_filtering_call; /* run Lanczos and reset a0/bLow (solver .cc:241-271)   */
+  int32_t reuse_lanczos_upper_bound; /* reuseLanczosUpperBoundFromFirstCall                */
+  int32_t is_first_scf;          /* scale the degree by first_scf_scaling (solver .cc:322) */
+  int32_t is_pseudopotential;
+  int32_t compute_residual;
+  int32_t use_cgs_rr;            /* 1: CGS + RR (useSubspaceProjectedSHEPGPU), 0: RR-GEP    */
+  int32_t reproducible_output;   /* 40 Lanczos steps, |f| instead of |f|/10                */
+  int32_t reserved;
+  double first_scf_scaling;      /* chebyshevFilterPolyDegreeFirstScfScalingFactor (1.34)  */
+} dftfe_b200_solve_params;
+
+/* ---- lifetime ---------------------------------------------------------- */
+const char *dftfe_b200_version(void);
+const char *dftfe_b200_last_error(void);
+int dftfe_b200_create(const dftfe_b200_problem_desc *desc, dftfe_b200_ctx **out);
+void dftfe_b200_destroy(dftfe_b200_ctx *ctx);
+/* Use an existing cudaStream_t (passed as void*) for all work; NULL = context-owned stream. */
+int dftfe_b200_set_stream(dftfe_b200_ctx *ctx, void *cuda_stream);
+int dftfe_b200_sync(dftfe_b200_ctx *ctx);
+
+/* ---- setup (replaces reinit(), src/dftOperator/kohnShamDFTOperatorDevice.cc:492-933) ---- */
+
+/* Host helper restating vectorTools::computeCellLocalIndexSetMap
+ * (utils/vectorTools/vectorUtilities.cc:473-502): map[c*n+i] =
+ * globalToLocal(cell_dofs[c*n+i]) * B.  Pure host integer code. */
+int dftfe_b200_build_index_map(const int64_t *cell_global_dofs_h, int64_t n_cells, int32_t nodes_per_cell,
+                               int64_t owned_start, int64_t owned_end, const int64_t *ghost_sorted_h,
+                               int64_t n_ghost, int32_t block, uint64_t *map_out_h);
+
+/* flattenedArrayCellLocalProcIndexIdMap, nC*n entries pre-multiplied by B
+ * (kohnShamDFTOperatorDevice.cc:583-596).  Also builds the atomics-free cell
+ * colouring and the first-touch flags used by the fused recurrence epilogue. */
+int dftfe_b200_set_index_map(dftfe_b200_ctx *ctx, const uint64_t *map_h);
+
+/* constraintMatrixInfoDevice::initialize arrays
+ * (utils/constraintMatrixInfoDevice.cc:446-542). */
+int dftfe_b200_set_constraints(dftfe_b200_ctx *ctx, int64_t n_constraints, const uint32_t *row_ids_local_h,
+                               const uint32_t *row_sizes_h, const uint32_t *row_starts_h,
+                               const uint32_t *col_ids_local_h, const double *col_values_h,
+                               const double *inhomogeneities_h);
+
+/* computeMassVector results, M+G entries each, 0 on constrained rows
+ * (kohnShamDFTOperatorDevice.cc:938-1031). */
+int dftfe_b200_set_mass(dftfe_b200_ctx *ctx, const double *sqrt_mass_h, const double *inv_sqrt_mass_h);
+
+/* MPIPatternP2P arrays (utils/MPIPatternP2P.t.cc; include/MultiVector.h:124-490).
+ * ghost_ranges_h holds [start,end) pairs inside the ghost segment. */
+int dftfe_b200_set_ghost_pattern(dftfe_b200_ctx *ctx, int32_t rank, int32_t nranks, int32_t n_ghost_procs,
+                                 const int32_t *ghost_proc_ids_h, const int32_t *ghost_ranges_h,
+                                 int32_t n_target_procs, const int32_t *target_proc_ids_h,
+                                 const int32_t *n_owned_for_targets_h,
+                                 const uint32_t *owned_local_idx_for_targets_h);
+
+/* NCCL bootstrap (replaces DeviceCCLWrapper::init, utils/DeviceDirectCCLWrapper.cc:56-80).
+ * Rank 0 calls get_unique_id and ships the 128 bytes to the others by any means. */
+int dftfe_b200_nccl_unique_id(uint8_t id_out_h[128]);
+int dftfe_b200_comm_init(dftfe_b200_ctx *ctx, const uint8_t id_h[128], int32_t rank, int32_t nranks);
+/* In-process transport for several ranks sharing ONE GPU (each rank = one context
+ * driven by its own host thread; device-to-device copies between two barriers).
+ * Test facility for the multi-rank path; production uses dftfe_b200_comm_init. */
+int dftfe_b200_comm_init_loopback(dftfe_b200_ctx *ctx, int32_t group_id, int32_t rank, int32_t nranks);
+
+/* Cell Hamiltonian for the active (k-point, spin): nC * n * n doubles,
+ * mem[c*n*n + I*n + J] = H_c(I,J) as d_cellHamiltonianMatrixFlattenedDevice
+ * (kohnShamDFTOperatorDevice.cc:602-606; hamiltonianMatrixCalculatorFlattenedDevice.cc:23-60).
+ * The data is re-tiled into the kernel's fragment-major layout; the caller's
+ * buffer is not referenced after the call returns. */
+int dftfe_b200_set_cell_hamiltonian(dftfe_b200_ctx *ctx, const double *H_d);
+int dftfe_b200_set_cell_hamiltonian_host(dftfe_b200_ctx *ctx, const double *H_h);
+
+/* ---- distributed-vector primitives (MultiVector / MPICommunicatorP2P) ---- */
+int dftfe_b200_update_ghost_values(dftfe_b200_ctx *ctx, double *x_d, int32_t ncols);
+int dftfe_b200_accumulate_add_locally_owned(dftfe_b200_ctx *ctx, double *x_d, int32_t ncols);
+int dftfe_b200_zero_out_ghosts(dftfe_b200_ctx *ctx, double *x_d, int32_t ncols);
+
+/* ---- constraints (utils/constraintMatrixInfoDevice.cc:544-588, 596-725, 817-851) ---- */
+int dftfe_b200_constraints_distribute(dftfe_b200_ctx *ctx, double *x_d, int32_t ncols);
+int dftfe_b200_constraints_distribute_slave_to_master(dftfe_b200_ctx *ctx, double *x_d, int32_t ncols);
+int dftfe_b200_constraints_set_zero(dftfe_b200_ctx *ctx, double *x_d, int32_t ncols);
+
+/* ---- operator ------------------------------------------------------------ */
+/* operatorDFTDeviceClass::HX (kohnShamDFTOperatorDevice.cc:3765-3860):
+ *   dst = (scale_flag ? dst : M^-1/2 dst) + scalar * M^-1/2 H M^-1/2 src
+ * on owned rows; constrained rows of dst end at 0; ghosts of src and dst end at 0;
+ * src is left unscaled (do_unscaling_src != 0) or scaled by scalar*M^-1/2. */
+int dftfe_b200_hx(dftfe_b200_ctx *ctx, double *src_d, double *dst_d, int32_t ncols, int32_t scale_flag,
+                  double scalar, int32_t do_unscaling_src);
+/* operatorDFTDeviceClass::HXCheby (kohnShamDFTOperatorDevice.cc:3874-3997),
+ * FP64, no compute/communication split: dst += H src (no mass scalings). */
+int dftfe_b200_hx_cheby(dftfe_b200_ctx *ctx, double *src_d, double *dst_d, int32_t ncols);
+
+/* linearAlgebraOperationsDevice::chebyshevFilter
+ * (src/linAlg/linearAlgebraOperationsDevice.cc:531-727): degree-m scaled Chebyshev
+ * polynomial of M^-1/2 H M^-1/2 applied in place to one (M+G) x B block held in
+ * the Loewdin basis.  y_d is the caller's scratch block of the same shape.
+ * One fused HBM pass per degree. */
+int dftfe_b200_cheb_filter(dftfe_b200_ctx *ctx, double *x_d, double *y_d, int32_t ncols, int32_t m, double a,
+                           double b, double a0);
+
+/* ---- subspace projections / rotation ------------------------------------- */
+/* S = X^T X, all-reduced; full symmetric N x N written to S_d (row-major)
+ * (fillParallelOverlapMatScalapack, linearAlgebraOperationsDevice.cc:3078-3240). */
+int dftfe_b200_xtx(dftfe_b200_ctx *ctx, const double *X_d, int32_t N, double *S_d);
+/* Hp = X^T (M^-1/2 H M^-1/2) X, all-reduced, full symmetric N x N
+ * (operatorDFTDeviceClass::XtHX, kohnShamDFTOperatorDevice.cc:4001-4157). */
+int dftfe_b200_xthx(dftfe_b200_ctx *ctx, const double *X_d, int32_t N, double *Hp_d);
+/* X <- X Q with Q row-major N x N on device (subspaceRotationScalapack,
+ * linearAlgebraOperationsDevice.cc:1832-2241). */
+int dftfe_b200_rotate(dftfe_b200_ctx *ctx, double *X_d, int32_t N, const double *Q_d);
+
+/* ---- eigensolver --------------------------------------------------------- */
+/* lanczosLowerUpperBoundEigenSpectrum (linearAlgebraOperationsDevice.cc:340-527):
+ * bounds_out_h = {floor(lambda_min), ceil(lambda_max + |f|/10)}. */
+int dftfe_b200_lanczos_bounds(dftfe_b200_ctx *ctx, int32_t reproducible, double bounds_out_h[2]);
+/* computeEigenResidualNorm (linearAlgebraOperationsDevice.cc:4610-4766). */
+int dftfe_b200_residual_norms(dftfe_b200_ctx *ctx, const double *X_d, int32_t N, const double *eig_h,
+                              double *res_out_h);
+/* reinitSpectrumBounds (include/chebyshevOrthogonalizedSubspaceIterationSolverDevice.h). */
+int dftfe_b200_reinit_spectrum_bounds(dftfe_b200_ctx *ctx, double lower_wanted, double lower_unwanted);
+/* chebyshevOrthogonalizedSubspaceIterationSolverDevice::solve
+ * (src/solvers/eigenSolvers/chebyshevOrthogonalizedSubspaceIterationSolverDevice.cc:155-736).
+ * X_d: M x N, in/out.  eig_out_h[N], res_out_h[N] (may be NULL).  Returns the
+ * upper bound of the unwanted spectrum through upper_bound_out_h. */
+int dftfe_b200_solve(dftfe_b200_ctx *ctx, double *X_d, int32_t N, const dftfe_b200_solve_params *params,
+                     double *eig_out_h, double *res_out_h, double *upper_bound_out_h);
+/* bounds currently held by the solver object: {a0, bLow, bUp}. */
+int dftfe_b200_get_spectrum_bounds(dftfe_b200_ctx *ctx, double out_h[3]);
+
+/* ---- introspection / measurement ----------------------------------------- */
+/* Number of cell colours, and per-colour cell counts (n_out entries filled). */
+int dftfe_b200_get_colouring(dftfe_b200_ctx *ctx, int32_t *n_colours_out, int32_t *cell_colour_out_h);
+/* Per-kernel CUDA-event timing on the context stream.  names: "cell_matvec",
+ * "distribute", "slave_to_master", "ghost_pack", "ghost_unpack", "projection",
+ * "rotation".  enable!=0 starts recording (adds an event pair per launch). */
+int dftfe_b200_profile_enable(dftfe_b200_ctx *ctx, int32_t enable);
+int dftfe_b200_profile_get(dftfe_b200_ctx *ctx, const char *name, double *total_ms_out, int64_t *launches_out);
+int dftfe_b200_profile_reset(dftfe_b200_ctx *ctx);
+/* Total number of kernels this library launched on the context since creation. */
+int64_t dftfe_b200_launch_count(dftfe_b200_ctx *ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFTFE_B200_H */

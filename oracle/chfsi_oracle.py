@@ -1,0 +1,537 @@
+"""CPU oracle for DFT-FE's Chebyshev-filtered subspace iteration (ChFSI) hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``dftfe_b200/`` may import this module;
+only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s CPU-baseline /
+``--impl reference`` legs use it, and only as the checker / the timed baseline.
+
+PARITY UNPINNED at kernel granularity: the reference (DFT-FE 1.1.0-pre) ships no
+golden vector, known-answer test or fixture for HX, X^T X, the index map or the
+constraint application in isolation (only end-to-end SCF
+energies are pinned, and the reference cannot be built here - deal.II, p4est,
+MPI, ScaLAPACK, ELPA are absent).  This file is therefore a line-by-line
+restatement of the reference's own *CPU twin* of the device path, pinned only by
+(i) analytic known answers (plane-wave eigenvalues of -1/2 Laplacian on a periodic
+box, harmonic oscillator levels, scalar Chebyshev recurrence on an exact
+eigenvector, X^T X = I after orthonormalisation, <Cx,y> = <x,C^T y> adjointness of
+the constraint pair) and (ii) cross-checks between the CPU statement of the
+filter (linearAlgebraOperationsOpt.cc:276-352) and the device statement with its
+pre-scaled state (linearAlgebraOperationsDevice.cc:531-727), which must agree.
+
+All ``file:line`` citations are relative to the reference tree (dftfeDevelopers/dftfe).
+
+Multi-rank runs are emulated in one process: ``ranks`` is a list of
+``RankProblem`` (dftfe_b200.femesh) and every distributed multivector is a list
+of per-rank arrays of shape ``(M_r + G_r, B)`` - row-major, wavefunction index
+fastest, ghosts after the owned rows (include/MultiVector.h:41-75).
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Sequence
+
+import numpy as np
+
+# --------------------------------------------------------------------------
+# integer maps (bit-exact rows of SURVEY section 8: a9)
+# --------------------------------------------------------------------------
+
+def compute_cell_local_index_set_map(cell_global_dofs: np.ndarray, owned_start: int, owned_end: int,
+                                     ghost_sorted: np.ndarray, block_size: int) -> np.ndarray:
+    """utils/vectorTools/vectorUtilities.cc:473-502.
+
+    ``map[c*n+i] = globalToLocal(cell_dof_indices[i]) * blockSize`` (64-bit), owned
+    cells in begin_active order; globalToLocal = g - ownedStart for owned DoFs,
+    M + position in the sorted ghost list otherwise (utils/MPIPatternP2P.t.cc).
+    """
+    M = owned_end - owned_start
+    out = np.empty(cell_global_dofs.size, dtype=np.uint64)
+    flat = cell_global_dofs.ravel()
+    for k in range(flat.size):  # deliberately scalar: independent restatement
+        g = int(flat[k])
+        if owned_start <= g < owned_end:
+            loc = g - owned_start
+        else:
+            lo, hi = 0, len(ghost_sorted)
+            while lo < hi:
+                mid = (lo + hi) // 2
+                if ghost_sorted[mid] < g:
+                    lo = mid + 1
+                else:
+                    hi = mid
+            assert ghost_sorted[lo] == g, "global index is neither owned nor ghost"
+            loc = M + lo
+        out[k] = loc * block_size
+    return out
+
+
+def proc_boundary_flags(ranks, r: int) -> np.ndarray:
+    """kohnShamDFTOperatorDevice.cc:555-581: flag owned DoFs that appear in the
+    partitioner's import_indices (= are ghosts of some other rank)."""
+    rp = ranks[r]
+    flags = np.zeros(rp.M, dtype=np.uint32)
+    for s, other in enumerate(ranks):
+        if s == r:
+            continue
+        g = other.ghostGlobal
+        mine = g[(g >= rp.ownedStart) & (g < rp.ownedEnd)]
+        flags[mine - rp.ownedStart] = 1
+    return flags
+
+
+# --------------------------------------------------------------------------
+# distributed multivector semantics (a8)
+# --------------------------------------------------------------------------
+
+def update_ghost_values(ranks, vecs):
+    """utils/MPICommunicatorP2P.cc:103-250: ghost rows <- owner's rows."""
+    for r, rp in enumerate(ranks):
+        if rp.G == 0:
+            continue
+        owner = np.searchsorted([q.ownedStart for q in ranks], rp.ghostGlobal, side="right") - 1
+        for s in np.unique(owner):
+            sel = np.nonzero(owner == s)[0]
+            vecs[r][rp.M + sel] = vecs[s][rp.ghostGlobal[sel] - ranks[s].ownedStart]
+
+
+def accumulate_add_locally_owned(ranks, vecs):
+    """utils/MPICommunicatorP2P.cc:263-418: owner rows += every rank's ghost copy.
+    (The ghost rows themselves are left untouched, as in the reference.)"""
+    for r, rp in enumerate(ranks):
+        if rp.G == 0:
+            continue
+        owner = np.searchsorted([q.ownedStart for q in ranks], rp.ghostGlobal, side="right") - 1
+        for s in np.unique(owner):
+            sel = np.nonzero(owner == s)[0]
+            np.add.at(vecs[s], rp.ghostGlobal[sel] - ranks[s].ownedStart, vecs[r][rp.M + sel])
+
+
+def zero_out_ghosts(ranks, vecs):
+    """src/linAlg/MultiVector.t.cc:527-533."""
+    for rp, v in zip(ranks, vecs):
+        v[rp.M:] = 0
+
+
+# --------------------------------------------------------------------------
+# constraints (a7) - utils/constraintMatrixInfo.cc
+# --------------------------------------------------------------------------
+
+def distribute(rp, x: np.ndarray):
+    """utils/constraintMatrixInfo.cc:247-293: x[row] = inhom + sum_j w_j x[col_j]."""
+    for i in range(rp.rowIdsLocal.size):
+        new = np.full(x.shape[1], rp.inhomogeneities[i], dtype=x.dtype)
+        s = int(rp.rowStarts[i])
+        for j in range(int(rp.rowSizes[i])):
+            new += rp.colValues[s + j] * x[rp.colIdsLocal[s + j]]
+        x[rp.rowIdsLocal[i]] = new
+
+
+def distribute_slave_to_master(rp, x: np.ndarray):
+    """utils/constraintMatrixInfo.cc:338-375: x[col_j] += w_j x[row]; x[row] = 0."""
+    for i in range(rp.rowIdsLocal.size):
+        row = rp.rowIdsLocal[i]
+        s = int(rp.rowStarts[i])
+        for j in range(int(rp.rowSizes[i])):
+            x[rp.colIdsLocal[s + j]] += rp.colValues[s + j] * x[row]
+        x[row] = 0
+
+
+def set_zero(rp, x: np.ndarray):
+    """utils/constraintMatrixInfo.cc:393-411."""
+    x[rp.rowIdsLocal] = 0
+
+
+# --------------------------------------------------------------------------
+# operator (a3-a5) - CPU twin
+# --------------------------------------------------------------------------
+
+def compute_local_hamiltonian_times_x(rp, src: np.ndarray, dst: np.ndarray, scalar: float = 1.0):
+    """src/dftOperator/matrixVectorProductImplementations.cc:97-169 (real) /
+    :27-95 (complex, transB='T'): per cell dcopy -> dgemm('N','N',B,n,n) -> daxpy.
+
+    Column-major ``cellY(B x n) = scalar * cellX(B x n) . H_c(n x n)`` with
+    H_c(k,i) = mem[k + i*n] means, row-wise, ``Y[i,:] = scalar * sum_k mem[i*n+k] X[k,:]``
+    for the real build; the complex build multiplies by H_c^T instead."""
+    H = rp.H
+    ids = rp.cellLocalDofs
+    cplx = np.iscomplexobj(src)
+    for c in range(rp.nCells):
+        Xc = src[ids[c]]
+        Hc = H[c].T if cplx else H[c]
+        Yc = scalar * (Hc @ Xc)
+        np.add.at(dst, ids[c], Yc)  # ids within a cell are unique; in order like daxpy
+
+
+def HX(ranks, src, dst, scale_flag: bool, scalar: float, do_unscaling_src: bool = True):
+    """src/dftOperator/kohnShamDFTOperator.cc:950-1044 (CPU) with the device
+    variant's ``doUnscalingSrc`` switch and ``scalar`` placement
+    (src/dftOperator/kohnShamDFTOperatorDevice.cc:3765-3860: src *= scalar*M^-1/2).
+
+    dst (+)= M^-1/2 H M^-1/2 (scalar*src); on exit src has its ghosts zeroed and is
+    rescaled back when do_unscaling_src."""
+    for rp, s, d in zip(ranks, src, dst):
+        M = rp.M
+        s[:M] *= (scalar * rp.invSqrtMass[:M])[:, None]
+        if scale_flag:
+            d[:M] *= rp.sqrtMass[:M][:, None]
+    update_ghost_values(ranks, src)
+    for rp, s, d in zip(ranks, src, dst):
+        distribute(rp, s)
+        compute_local_hamiltonian_times_x(rp, s, d, 1.0)
+        distribute_slave_to_master(rp, d)
+    zero_out_ghosts(ranks, src)
+    accumulate_add_locally_owned(ranks, dst)
+    zero_out_ghosts(ranks, dst)
+    for rp, s, d in zip(ranks, src, dst):
+        M = rp.M
+        d[:M] *= rp.invSqrtMass[:M][:, None]
+        if do_unscaling_src:
+            s[:M] *= (rp.sqrtMass[:M] / scalar)[:, None]
+
+
+def HXCheby(ranks, src, dst):
+    """src/dftOperator/kohnShamDFTOperatorDevice.cc:3874-3997 (FP64, no overlap
+    split): bare dst += H src with ghost update, distribute, slave->master and
+    accumulate; no mass scalings inside."""
+    update_ghost_values(ranks, src)
+    for rp, s, d in zip(ranks, src, dst):
+        distribute(rp, s)
+        compute_local_hamiltonian_times_x(rp, s, d, 1.0)
+        distribute_slave_to_master(rp, d)
+    zero_out_ghosts(ranks, src)
+    accumulate_add_locally_owned(ranks, dst)
+    zero_out_ghosts(ranks, dst)
+
+
+# --------------------------------------------------------------------------
+# Chebyshev filter (a2)
+# --------------------------------------------------------------------------
+
+def chebyshev_filter(ranks, X, m: int, a: float, b: float, a0: float):
+    """src/linAlg/linearAlgebraOperationsOpt.cc:276-352 (CPU statement).
+    In place on X (list of (M+G) x B arrays in the Loewdin basis)."""
+    e = (b - a) / 2.0
+    c = (b + a) / 2.0
+    sigma = e / (a0 - c)
+    sigma1 = sigma
+    gamma = 2.0 / sigma1
+    Y = [np.zeros_like(x) for x in X]
+    HX(ranks, X, Y, False, 1.0)
+    alpha1, alpha2 = sigma1 / e, -c
+    for x, y in zip(X, Y):
+        y[:] = alpha1 * (y + alpha2 * x)          # addAndScale
+    for _degree in range(2, m + 1):
+        sigma2 = 1.0 / (gamma - sigma)
+        alpha1, alpha2 = 2.0 * sigma2 / e, -(sigma * sigma2)
+        for x, y in zip(X, Y):
+            x[:] = alpha2 * x + (-c * alpha1) * y  # scaleAndAdd
+        HX(ranks, Y, X, True, alpha1)
+        X, Y = Y, X
+        sigma = sigma2
+    return Y  # 'copy back YArray to XArray' (:350): the newest iterate is the array now called Y
+
+
+def chebyshev_filter_inplace(ranks, X, m, a, b, a0):
+    """Wrapper that leaves the filtered block in the caller's arrays."""
+    work = [x.copy() for x in X]
+    out = chebyshev_filter(ranks, work, m, a, b, a0)
+    for x, o in zip(X, out):
+        x[:] = o
+
+
+def chebyshev_filter_device_state(ranks, X, m: int, a: float, b: float, a0: float):
+    """src/linAlg/linearAlgebraOperationsDevice.cc:531-727 - the device statement
+    with its pre-scaled (alpha1*M^-1/2 / M^1/2) state and the fused
+    ``combinedDeviceKernel`` (:37-64).  Must agree with ``chebyshev_filter``."""
+    e = (b - a) / 2.0
+    c = (b + a) / 2.0
+    sigma = e / (a0 - c)
+    sigma1 = sigma
+    gamma = 2.0 / sigma1
+    X = [x.copy() for x in X]
+    Y = [np.zeros_like(x) for x in X]
+    HX(ranks, X, Y, False, 1.0)
+    alpha1, alpha2 = sigma1 / e, -c
+    alpha1_old = alpha1
+    for rp, x, y in zip(ranks, X, Y):
+        M = rp.M
+        y[:M] = alpha2 * x[:M] + y[:M]
+        y[:M] *= alpha1
+    for degree in range(2, m + 1):
+        sigma2 = 1.0 / (gamma - sigma)
+        alpha1, alpha2 = 2.0 * sigma2 / e, -(sigma * sigma2)
+        coeff = -c * alpha1
+        if degree == 2:
+            for rp, x, y in zip(ranks, X, Y):
+                M = rp.M
+                x[:M] = coeff * y[:M] + alpha2 * x[:M]
+                y[:M] *= (alpha1 * rp.invSqrtMass[:M])[:, None]
+                x[:M] *= rp.sqrtMass[:M][:, None]
+            HXCheby(ranks, Y, X)
+        elif degree == m:
+            for rp, x, y in zip(ranks, X, Y):
+                M = rp.M
+                x[:M] *= (rp.sqrtMass[:M] / alpha1_old)[:, None]
+                y[:M] *= rp.invSqrtMass[:M][:, None]
+                x[:M] = coeff * y[:M] + alpha2 * x[:M]
+            HX(ranks, Y, X, True, alpha1)
+        else:
+            for rp, x, y in zip(ranks, X, Y):
+                M = rp.M
+                sq, isq = rp.sqrtMass[:M][:, None], rp.invSqrtMass[:M][:, None]
+                # combinedDeviceKernel(x:=YArray, y:=XArray): linearAlgebraOperationsDevice.cc:37-64
+                x[:M] *= sq / alpha1_old
+                y[:M] *= isq
+                x[:M] = coeff * y[:M] + alpha2 * x[:M]
+                y[:M] *= isq * alpha1
+                x[:M] *= sq
+            HXCheby(ranks, Y, X)
+        X, Y = Y, X
+        sigma = sigma2
+        alpha1_old = alpha1
+    return Y  # linearAlgebraOperationsDevice.cc:723-726
+
+
+def chebyshev_scalar(lam: float, m: int, a: float, b: float, a0: float) -> float:
+    """Scalar value of the scaled degree-m polynomial at eigenvalue ``lam`` (closed
+    form of the recurrence at linearAlgebraOperationsOpt.cc:289-348)."""
+    e = (b - a) / 2.0
+    c = (b + a) / 2.0
+    sigma = e / (a0 - c)
+    sigma1 = sigma
+    gamma = 2.0 / sigma1
+    x = 1.0
+    y = (sigma1 / e) * (lam - c) * x
+    for _ in range(2, m + 1):
+        sigma2 = 1.0 / (gamma - sigma)
+        alpha1, alpha2 = 2.0 * sigma2 / e, -(sigma * sigma2)
+        x, y = y, alpha1 * (lam - c) * y + alpha2 * x
+        sigma = sigma2
+    return y
+
+
+# --------------------------------------------------------------------------
+# projections, rotation, RR-GEP, residual, Lanczos (a10-a15)
+# --------------------------------------------------------------------------
+
+def _owned(ranks, X):
+    return [x[:rp.M] for rp, x in zip(ranks, X)]
+
+
+def xtx(ranks, X) -> np.ndarray:
+    """S = X^H X summed over ranks (fillParallelOverlapMatScalapack,
+    src/linAlg/linearAlgebraOperationsDevice.cc:3078-3240); full N x N returned,
+    the reference stores the lower triangle."""
+    S = 0
+    for x in _owned(ranks, X):
+        S = S + x.conj().T @ x
+    return S
+
+
+def apply_HX_blocked(ranks, X, block: int):
+    """H~ X for a full N-column X by blocks of ``block`` columns, as XtHX does
+    (src/dftOperator/kohnShamDFTOperatorDevice.cc:4051-4090)."""
+    N = X[0].shape[1]
+    HXf = [np.zeros_like(x) for x in X]
+    for j in range(0, N, block):
+        Xb = [x[:, j:j + block].copy() for x in X]
+        zero_out_ghosts(ranks, Xb)
+        Yb = [np.zeros_like(x) for x in Xb]
+        HX(ranks, Xb, Yb, False, 1.0, do_unscaling_src=False)
+        for h, y in zip(HXf, Yb):
+            h[:, j:j + block] = y
+    return HXf
+
+
+def xthx(ranks, X, block: int) -> np.ndarray:
+    """Hp = X^H H~ X (kohnShamDFTOperatorDevice.cc:4001-4157)."""
+    HXf = apply_HX_blocked(ranks, X, block)
+    Hp = 0
+    for x, h in zip(_owned(ranks, X), _owned(ranks, HXf)):
+        Hp = Hp + x.conj().T @ h
+    return Hp
+
+
+def rayleigh_ritz_gep(ranks, X, block: int):
+    """src/linAlg/rayleighRitzDevice.cc:355-819 (CPU twin
+    linearAlgebraOperationsOpt.cc:613-969): S = X^H X = L L^H; Hp = X^H H~ X;
+    Hs = L^-1 Hp L^-H = Q D Q^H; X <- X L^-H Q.  Returns eigenvalues (ascending)."""
+    S = xtx(ranks, X)
+    L = np.linalg.cholesky(S)
+    Linv = np.linalg.inv(L)
+    Hp = xthx(ranks, X, block)
+    Hp = 0.5 * (Hp + Hp.conj().T)
+    Hs = Linv @ Hp @ Linv.conj().T
+    evals, Q = np.linalg.eigh(Hs)
+    R = Linv.conj().T @ Q
+    for rp, x in zip(ranks, X):
+        x[:rp.M] = x[:rp.M] @ R
+    return evals
+
+
+def cholesky_gram_schmidt(ranks, X):
+    """src/linAlg/pseudoGSDevice.cc:81-463: X <- X L^-H with X^H X = L L^H."""
+    S = xtx(ranks, X)
+    L = np.linalg.cholesky(S)
+    Linv = np.linalg.inv(L)
+    for rp, x in zip(ranks, X):
+        x[:rp.M] = x[:rp.M] @ Linv.conj().T
+
+
+def rayleigh_ritz(ranks, X, block: int):
+    """src/linAlg/rayleighRitzDevice.cc:81-353: Hp = X^H H~ X = Q D Q^H; X <- X Q."""
+    Hp = xthx(ranks, X, block)
+    Hp = 0.5 * (Hp + Hp.conj().T)
+    evals, Q = np.linalg.eigh(Hp)
+    for rp, x in zip(ranks, X):
+        x[:rp.M] = x[:rp.M] @ Q
+    return evals
+
+
+def eigen_residual_norm(ranks, X, evals, block: int) -> np.ndarray:
+    """src/linAlg/linearAlgebraOperationsDevice.cc:4610-4766."""
+    HXf = apply_HX_blocked(ranks, X, block)
+    r2 = 0
+    for x, h in zip(_owned(ranks, X), _owned(ranks, HXf)):
+        d = h - x * evals[None, :]
+        r2 = r2 + np.sum(np.abs(d) ** 2, axis=0)
+    return np.sqrt(r2)
+
+
+class GlibcRand:
+    """glibc ``srand``/``rand`` (TYPE_3 additive feedback generator, r[i] =
+    r[i-3] + r[i-31]) - the reference seeds Lanczos with ``std::srand(rank)``;
+    ``rand()/RAND_MAX`` (linearAlgebraOperationsDevice.cc:368-372)."""
+
+    RAND_MAX = 2147483647
+
+    def __init__(self, seed: int):
+        seed = seed & 0xFFFFFFFF
+        if seed == 0:
+            seed = 1
+        r = [0] * 34
+        r[0] = seed
+        for i in range(1, 31):
+            # 16807 * r[i-1] % 2147483647 computed as glibc does (signed hi/lo split)
+            hi, lo = divmod(self._s32(r[i - 1]), 127773)
+            word = 16807 * lo - 2836 * hi
+            if word < 0:
+                word += 2147483647
+            r[i] = word
+        for i in range(31, 34):
+            r[i] = r[i - 31]
+        self.state = [x & 0xFFFFFFFF for x in r]
+        self.out = []
+        for _ in range(310):
+            self._next_raw()
+
+    @staticmethod
+    def _s32(x):
+        x &= 0xFFFFFFFF
+        return x - (1 << 32) if x & 0x80000000 else x
+
+    def _next_raw(self):
+        s = self.state
+        val = (s[-31] + s[-3]) & 0xFFFFFFFF
+        s.append(val)
+        if len(s) > 64:
+            del s[0:len(s) - 34]
+        return val
+
+    def rand(self) -> int:
+        return self._next_raw() >> 1
+
+
+def lanczos_bounds(ranks, block: int = 1, iterations: int = 20, reproducible: bool = False):
+    """src/linAlg/linearAlgebraOperationsDevice.cc:340-527: 20-step Lanczos with a
+    ``rand()`` start vector per rank, constrained rows zeroed, returns
+    (floor(lambda_min), ceil(lambda_max + |f|/10))."""
+    if reproducible:
+        iterations = 40
+    v = []
+    for r, rp in enumerate(ranks):
+        g = GlibcRand(r)
+        x = np.zeros((rp.M + rp.G, 1))
+        x[:rp.M, 0] = [g.rand() / GlibcRand.RAND_MAX for _ in range(rp.M)]
+        set_zero(rp, x)
+        x[rp.M:] = 0
+        v.append(x)
+    nrm = math.sqrt(sum(float(np.sum(x[:rp.M] ** 2)) for rp, x in zip(ranks, v)))
+    for x in v:
+        x /= nrm
+
+    def apply(vv):
+        src = [x.copy() for x in vv]
+        dst = [np.zeros_like(x) for x in vv]
+        HX(ranks, src, dst, False, 1.0)
+        return dst
+
+    def dot(a, b):
+        return sum(float(np.sum(x[:rp.M] * y[:rp.M])) for rp, x, y in zip(ranks, a, b))
+
+    f = apply(v)
+    alpha = dot(f, v)
+    for x, y in zip(f, v):
+        x -= alpha * y
+    T = np.zeros((iterations, iterations))
+    T[0, 0] = alpha
+    for j in range(1, iterations):
+        beta = math.sqrt(dot(f, f))
+        v0 = v
+        v = [x / beta for x in f]
+        f = apply(v)
+        for x, y in zip(f, v0):
+            x -= beta * y
+        alpha = dot(f, v)
+        for x, y in zip(f, v):
+            x -= alpha * y
+        T[j, j - 1] = beta
+        T[j - 1, j] = beta
+        T[j, j] = alpha
+    ev = np.linalg.eigvalsh(T)
+    fnorm = math.sqrt(dot(f, f))
+    lower = math.floor(ev[0])
+    upper = math.ceil(ev[-1] + (fnorm if reproducible else fnorm / 10.0))
+    return lower, upper
+
+
+ORDER_LOOKUP = [(500, 24), (750, 30), (1000, 39), (1500, 50), (2000, 53), (3000, 57), (4000, 62),
+                (5000, 69), (9000, 77), (14000, 104), (20000, 119), (30000, 162), (50000, 300),
+                (80000, 450), (100000, 550), (200000, 700), (500000, 1000)]
+
+
+def set_chebyshev_order(upper_bound: float) -> int:
+    """chebyshevOrthogonalizedSubspaceIterationSolverDevice.cc:29-46,60-75."""
+    for ub, order in ORDER_LOOKUP:
+        if upper_bound <= ub:
+            return order
+    return 1250
+
+
+def solve(ranks, X, block: int, cheb_order: int, bounds, use_gep: bool = True,
+          compute_residual: bool = True):
+    """chebyshevOrthogonalizedSubspaceIterationSolverDevice::solve
+    (src/solvers/eigenSolvers/chebyshevOrthogonalizedSubspaceIterationSolverDevice.cc:155-736),
+    one band group, no spectrum splitting.
+
+    X: list of (M+G) x N arrays holding the wavefunctions in the usual FE basis
+    (owned rows meaningful).  bounds = (a0, bLow, bUp).  Returns (eigenvalues,
+    residual norms); X is overwritten with the rotated, M^-1/2-scaled vectors."""
+    a0, blow, bup = bounds
+    N = X[0].shape[1]
+    for rp, x in zip(ranks, X):
+        x[:rp.M] *= rp.sqrtMass[:rp.M][:, None]           # :358-363
+    for j in range(0, N, block):
+        Xb = [x[:, j:j + block].copy() for x in X]
+        zero_out_ghosts(ranks, Xb)
+        chebyshev_filter_inplace(ranks, Xb, cheb_order, blow, bup, a0)
+        for x, xb in zip(X, Xb):
+            x[:, j:j + block] = xb
+    if use_gep:
+        evals = rayleigh_ritz_gep(ranks, X, block)
+    else:
+        cholesky_gram_schmidt(ranks, X)
+        evals = rayleigh_ritz(ranks, X, block)
+    res = eigen_residual_norm(ranks, X, evals, block) if compute_residual else None
+    for rp, x in zip(ranks, X):
+        x[:rp.M] *= rp.invSqrtMass[:rp.M][:, None]        # :719-733
+    return evals, res

@@ -1,0 +1,58 @@
+"""Shared helpers for the parity tests (oracle side lives in oracle/)."""
+import numpy as np
+
+from dftfe_b200.femesh import build_mesh, gaussian_wells_potential
+
+
+def make_problem(p, ncells, h=1.0, periodic=(True, True, True), nranks=1, vquad="gauss", potential=True,
+                 extra_constraints=None, rank_grid=None):
+    mesh = build_mesh(p, ncells, h, periodic=periodic, nranks=nranks, extra_constraints=extra_constraints,
+                      rank_grid=rank_grid)
+    pot = gaussian_wells_potential(mesh.box, periodic=periodic) if potential else None
+    ranks = [mesh.rank_problem(r, potential=pot, vquad=vquad) for r in range(nranks)]
+    return mesh, ranks
+
+
+def random_global(mesh, ncols, seed=0):
+    rng = np.random.default_rng(seed)
+    return rng.uniform(-1.0, 1.0, size=(mesh.nNodes, ncols))
+
+
+def scatter_to_ranks(ranks, Xg, loewdin=False, zero_constrained=True):
+    """global (by global DoF id) -> per-rank (M+G) x ncols arrays, ghosts zero."""
+    out = []
+    for rp in ranks:
+        x = np.zeros((rp.M + rp.G, Xg.shape[1]))
+        x[:rp.M] = Xg[rp.ownedStart:rp.ownedEnd]
+        if loewdin:
+            x[:rp.M] *= rp.sqrtMass[:rp.M, None]
+        if zero_constrained:
+            x[rp.rowIdsLocal[rp.rowIdsLocal < rp.M]] = 0.0
+        out.append(x)
+    return out
+
+
+def hanging_like_constraints(nrows=6, seed=3):
+    """Inject multi-column constraint rows (weights like hanging-node interpolation)
+    on interior nodes of a structured mesh, to exercise general CSR rows."""
+
+    def fn(mesh):
+        rng = np.random.default_rng(seed)
+        NX, NY, NZ = mesh.node_dims
+        out = []
+        used = set()
+        tries = 0
+        while len(out) < nrows and tries < 1000:
+            tries += 1
+            ix, iy, iz = (int(rng.integers(2, d - 2)) for d in (NX, NY, NZ))
+            row = ix + NX * (iy + NY * iz)
+            nb = [row - 1, row + 1, row - NX, row + NX]
+            if row in used or any(b in used for b in nb):
+                continue
+            used.add(row)
+            used.update(nb)
+            w = rng.uniform(0.1, 0.6, size=4)
+            out.append((row, list(zip(nb, w)), 0.0))
+        return out
+
+    return fn
