@@ -1,0 +1,345 @@
+#!/usr/bin/env python
+"""Headline benchmark: Chebyshev-filter wavefunction-DoF applies per second.
+
+Workload (BASELINE.json configs[1]): FE order 6,
+17^3 periodic cells per GPU (102^3 = 1 061 208 free DoFs; 103^3 grid nodes with the
+periodic images kept as constrained DoFs, as deal.II does), N = 2048
+wavefunctions, Chebyshev block B = 256, degree m = 20.  One "step" = the blocked
+filter loop of solve() over all N columns (8 blocks x 20 fused operator applies).
+
+    value  = M_free_global * N * m / t_step   (inputs resident in HBM)
+    e2e    = same through dftfe_b200_cheb_filter_all_host with X in pinned HOST memory
+             (block H2D / D2H copies inside the timed region)
+
+`--impl reference` times the CPU restatement of the reference's own CPU path
+(oracle/chfsi_oracle.c, OpenMP over all host cores, OpenBLAS dgemm per cell) on a
+bounded sample of the same workload; the reference itself cannot be built in this
+image (deal.II, p4est, MPI, ScaLAPACK, ELPA absent - SURVEY.md section 8c).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+P_ORDER = 6
+CELLS_PER_GPU = 17
+N_WFC = 2048
+BLOCK = 256
+DEGREE = 20
+A0, A_LOW = -3.0, 2.0  # wanted-spectrum lower bound / filter lower edge
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--cells", type=int, default=CELLS_PER_GPU, help="cells per axis per GPU (debug)")
+    ap.add_argument("--nwfc", type=int, default=N_WFC)
+    ap.add_argument("--degree", type=int, default=DEGREE)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def rank_grid_for(n):
+    return {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}.get(n) or (n, 1, 1)
+
+
+def build_rank_problem(args, rank, nranks, build_H_host=False):
+    from dftfe_b200.femesh import build_mesh, gaussian_wells_potential
+
+    grid = rank_grid_for(nranks)
+    ncells = tuple(args.cells * g for g in grid)
+    mesh = build_mesh(P_ORDER, ncells, 1.0, periodic=(True, True, True), nranks=nranks, rank_grid=grid)
+    pot = gaussian_wells_potential(mesh.box, nwells=8, seed=1234)
+    rp = mesh.rank_problem(rank, potential=pot, vquad="gll", build_H=build_H_host, with_xyz=False)
+    return mesh, rp, pot
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index=0):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                          "-i", str(self.index), "-lms", "200"], stdout=subprocess.PIPE, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def fp64_peak_tflops():
+    """FP64 tensor (DMMA) peak measured on this pool's B200 by tools/microbench_fp64
+    (MEASURED_PEAKS.json only carries bf16 / HBM figures)."""
+    path = os.path.join(ROOT, "profiles", "r01_fp64_peaks.jsonl")
+    best = None
+    try:
+        for ln in open(path):
+            d = json.loads(ln)
+            if d.get("probe") == "dmma_8x8x4":
+                best = max(best or 0.0, d["tflops"])
+    except Exception:
+        pass
+    return (best, "profiles/r01_fp64_peaks.jsonl raw DMMA.8x8x4 issue rate, measured") if best else \
+        (37.0, "fallback: 64 FP64 FMA/clk/SM x 148 SMs x 1.965 GHz")
+
+
+# ---------------------------------------------------------------------------
+def cpu_reference_run(args, steps, warmup, degree_sample):
+    """C oracle (port of the reference CPU path) on all host cores: one block of BLOCK
+    wavefunctions, `degree_sample` degrees, full single-GPU mesh."""
+    from oracle.c_oracle import COracle, greedy_colouring
+
+    mesh, rp, pot = build_rank_problem(args, 0, 1, build_H_host=True)
+    col = greedy_colouring(np.ascontiguousarray(rp.cellLocalDofs), rp.M + rp.G)
+    B = min(BLOCK, args.nwfc)
+    co = COracle(rp, B, colouring=col)
+    rng = np.random.default_rng(42)
+    X = rng.uniform(-1.0, 1.0, size=(rp.M + rp.G, B))
+    X[rp.rowIdsLocal] = 0.0
+    Y = np.empty_like(X)
+    b_up = 40.0  # any upper bound: the arithmetic per apply does not depend on it
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        co.cheb_filter(X, degree_sample, A_LOW, b_up, A0, Y)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    t = float(np.mean(times))
+    applies = mesh.nFreeDofs * B * degree_sample
+    return {"value": applies / t, "ms_per_step": t * 1e3, "cores": co.threads, "blas": co.lib.blas,
+            "sample": f"1 block of {B} of {args.nwfc} wavefunctions x degree {degree_sample} of {args.degree}, "
+                      f"full {args.cells}^3-cell order-{P_ORDER} mesh ({mesh.nFreeDofs} DoFs)",
+            "mesh": mesh}
+
+
+def main_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    r = cpu_reference_run(args, args.steps, args.warmup, degree_sample=min(8, args.degree))
+    line = {
+        "impl": "reference", "metric": "cheb_filter_wfc_dof_applies_per_s", "value": r["value"], "unit": "applies/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": r["ms_per_step"],
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, args.gpus),
+        "cpu_baseline": {"value": r["value"], "unit": "applies/s", "cores": r["cores"], "kind": "port",
+                         "sample": r["sample"], "blas": r["blas"]},
+        "e2e": {"value": r["value"], "unit": "applies/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(args, nranks):
+    return {"workload": f"synthetic ChFSI microbench: FE order {P_ORDER}, {args.cells}^3 periodic cells per GPU "
+                        f"({(args.cells * P_ORDER) ** 3} free DoFs per GPU), N={args.nwfc} wavefunctions, "
+                        f"block {min(BLOCK, args.nwfc)}, Chebyshev degree {args.degree}",
+            "fe_order": P_ORDER, "cells_per_gpu": args.cells ** 3, "n_wavefunctions": args.nwfc,
+            "cheby_block": min(BLOCK, args.nwfc), "degree": args.degree, "partition": f"brick {rank_grid_for(nranks)}",
+            "l2_policy": "inputs larger than L2 (X block 2.2 GB, cell H 4.6 GB per pass)"}
+
+
+# ---------------------------------------------------------------------------
+def main_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from dftfe_b200 import build, capi
+
+    if rank == 0:
+        build.build()
+    if world > 1:
+        dist.barrier()
+
+    mesh, rp, pot = build_rank_problem(args, rank, world)
+    B = min(BLOCK, args.nwfc)
+    N = args.nwfc
+    stream = torch.cuda.Stream(device=dev)
+    with torch.cuda.stream(stream):
+        op = capi.Operator(rp, B, device=local_rank)
+        if world > 1:
+            ids = [capi.nccl_unique_id() if rank == 0 else None]
+            dist.broadcast_object_list(ids, src=0)
+            op.comm_init(ids[0], rank, world)
+        # cell Hamiltonians built on the device: H_c = 1/2 K + diag(v(x_i) w_i)  (GLL-quadrature potential)
+        ref = mesh.ref
+        K3 = torch.from_numpy(0.5 * ref.K3).to(dev)
+        H = K3.unsqueeze(0).repeat(rp.nCells, 1, 1)
+        nx, ny, nz = mesh.ncells
+        c = rp.cellIds
+        origin = np.stack([c % nx, (c // nx) % ny, c // (nx * ny)], axis=1) * mesh.h
+        vd = pot(origin[:, None, :] + ref.node_xyz[None, :, :]) * ref.mass_gll[None, :]
+        H.diagonal(dim1=1, dim2=2).add_(torch.from_numpy(vd).to(dev))
+        op.set_cell_hamiltonian(H)
+        del H, K3
+        torch.cuda.empty_cache()
+        g = torch.Generator(device=dev)
+        g.manual_seed(42 + rank)
+        X = torch.rand((rp.M, N), dtype=torch.float64, device=dev, generator=g) * 2.0 - 1.0
+        con_owned = torch.from_numpy(rp.rowIdsLocal[rp.rowIdsLocal < rp.M].astype(np.int64)).to(dev)
+        X[con_owned] = 0.0
+        lo, up = op.lanczosLowerUpperBoundEigenSpectrum()
+        m = args.degree
+
+        def step():
+            op.chebyshevFilterAll(X, m, A_LOW, up, A0)
+
+        def sync_all():
+            stream.synchronize()
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        for _ in range(args.warmup):
+            step()
+        sync_all()
+        op.profile_reset()
+        op.profile_enable(True)
+        launches0 = op.launch_count()
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            step()
+        e1.record(stream)
+        sync_all()
+        clocks = sampler.stop() if rank == 0 else None
+        ms_total = e0.elapsed_time(e1)
+        launches = op.launch_count() - launches0
+        op.profile_enable(False)
+        k_ms, k_launches = op.profile_get("cell_matvec")
+        finite = bool(torch.isfinite(X).all().item())
+
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step = float(t.item()) / args.steps
+        applies_per_step = (args.cells * P_ORDER) ** 3 * world * N * m
+        value = applies_per_step / (ms_step * 1e-3)
+
+        # ---- roofline of the dominant kernel (fused cell matvec), timed live with CUDA events
+        ncol, _ = op.colouring()
+        flops_per_launch = 2.0 * rp.n * rp.n * B * rp.nCells / ncol
+        avg_launch_s = (k_ms * 1e-3) / max(k_launches, 1)
+        achieved = flops_per_launch / avg_launch_s / 1e12
+        peak, peak_src = fp64_peak_tflops()
+        roofline = {"bound": "tensor", "kernel": "cell_matvec_kernel<343> (FP64 DMMA.8x8x4)", "achieved": achieved,
+                    "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                    "peak_source": peak_src, "launches_timed": int(k_launches),
+                    "avg_launch_ms": avg_launch_s * 1e3, "kernel_share_of_step": k_ms / ms_total,
+                    "flops_per_launch": flops_per_launch}
+
+        # ---- end to end: X in pinned host memory, copies inside the timed region
+        e2e = None
+        if not args.no_e2e:
+            Xh = torch.empty((rp.M, N), dtype=torch.float64, pin_memory=True)
+            Xh.copy_(X)
+            del X
+            torch.cuda.empty_cache()
+            n_e2e = max(1, min(args.steps, 3))
+            op.chebyshevFilterAllHost(Xh, m, A_LOW, up, A0)  # warm-up (stream / buffer creation)
+            sync_all()
+            t0 = time.perf_counter()
+            for _ in range(n_e2e):
+                op.chebyshevFilterAllHost(Xh, m, A_LOW, up, A0)
+            sync_all()
+            dt = time.perf_counter() - t0
+            tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            e2e_val = applies_per_step * n_e2e / float(tt.item())
+            nbytes = rp.M * N * 8
+            e2e = {"value": e2e_val, "unit": "applies/s", "h2d_bytes_per_step": int(nbytes),
+                   "d2h_bytes_per_step": int(nbytes), "steps": n_e2e,
+                   "api": "dftfe_b200_cheb_filter_all_host (pinned host X, pipelined block copies)"}
+            finite = finite and bool(torch.isfinite(Xh[:: max(1, rp.M // 1000)]).all().item())
+        op.close()
+
+    line = None
+    if rank == 0:
+        line = {
+            "metric": "cheb_filter_wfc_dof_applies_per_s", "value": value, "unit": "applies/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
+            "roofline": roofline, "finite": finite, "spectrum_bounds": [A0, A_LOW, up],
+            "tflops_fp64_filter": 2.0 * rp.n ** 2 * B * rp.nCells * (N // B) * m * world / (ms_step * 1e-3) / 1e12,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            r = cpu_reference_run(args, steps=1, warmup=0, degree_sample=args.degree)
+            line["cpu_baseline"] = {"value": r["value"], "unit": "applies/s", "cores": r["cores"], "kind": "port",
+                                    "sample": r["sample"], "blas": r["blas"]}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    a = parse_args()
+    sys.exit(main_reference(a) if a.impl == "reference" else main_ours(a))

@@ -52,7 +52,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
         raise RuntimeError("nvcc compilation failed")
     if force or procs or _stale(LIB, objs):
         cmd = [NVCC, "-shared", "-o", str(LIB), *map(str, objs), "-L/usr/local/cuda/lib64", "-lcublas",
-               "-lcusolver", "-lnccl", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
+               "-lcusolver", "-ldl", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)

@@ -67,9 +67,10 @@ EXPORTED_SYMBOLS = [
     "dftfe_b200_update_ghost_values", "dftfe_b200_accumulate_add_locally_owned", "dftfe_b200_zero_out_ghosts",
     "dftfe_b200_constraints_distribute", "dftfe_b200_constraints_distribute_slave_to_master",
     "dftfe_b200_constraints_set_zero", "dftfe_b200_hx", "dftfe_b200_hx_cheby", "dftfe_b200_cheb_filter",
+    "dftfe_b200_cheb_filter_all", "dftfe_b200_cheb_filter_all_host",
     "dftfe_b200_xtx", "dftfe_b200_xthx", "dftfe_b200_rotate", "dftfe_b200_lanczos_bounds",
     "dftfe_b200_residual_norms", "dftfe_b200_reinit_spectrum_bounds", "dftfe_b200_solve",
-    "dftfe_b200_get_spectrum_bounds", "dftfe_b200_get_colouring", "dftfe_b200_profile_enable",
+    "dftfe_b200_get_spectrum_bounds", "dftfe_b200_get_colouring", "dftfe_b200_set_option", "dftfe_b200_profile_enable",
     "dftfe_b200_profile_get", "dftfe_b200_profile_reset", "dftfe_b200_launch_count",
 ]
 
@@ -83,6 +84,10 @@ def load() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
+    try:  # let a co-resident PyTorch bring in ITS cuBLAS/cuSOLVER/NCCL first (same SONAMEs)
+        import torch  # noqa: F401
+    except Exception:
+        pass
     if not _LIB_PATH.exists():
         raise DftfeB200Error(-2, f"{_LIB_PATH} is missing: run `python -m dftfe_b200.build` (there is no CPU fallback)")
     lib = C.CDLL(str(_LIB_PATH), mode=C.RTLD_GLOBAL)
@@ -246,6 +251,22 @@ class Operator:
         _check(self.lib.dftfe_b200_cheb_filter(self.h, _dptr(X), _dptr(Y), C.c_int32(X.shape[1]), C.c_int32(m),
                                                C.c_double(a), C.c_double(b), C.c_double(a0)))
 
+    def chebyshevFilterAll(self, X, m: int, a: float, b: float, a0: float):
+        """solver .cc:376-526: blocked filter loop over the full device-resident X [M, N]."""
+        _check(self.lib.dftfe_b200_cheb_filter_all(self.h, _dptr(X), C.c_int32(X.shape[1]), C.c_int32(m),
+                                                   C.c_double(a), C.c_double(b), C.c_double(a0)))
+
+    def chebyshevFilterAllHost(self, X_host, m: int, a: float, b: float, a0: float):
+        """Same with X in host memory (torch CPU tensor, pinned preferred, or numpy): copies pipelined."""
+        if isinstance(X_host, np.ndarray):
+            assert X_host.dtype == np.float64 and X_host.flags.c_contiguous
+            ptr, N = X_host.ctypes.data, X_host.shape[1]
+        else:
+            assert (not X_host.is_cuda) and X_host.is_contiguous()
+            ptr, N = X_host.data_ptr(), X_host.shape[1]
+        _check(self.lib.dftfe_b200_cheb_filter_all_host(self.h, C.c_void_p(ptr), C.c_int32(N), C.c_int32(m),
+                                                        C.c_double(a), C.c_double(b), C.c_double(a0)))
+
     def XtX(self, X, S):
         _check(self.lib.dftfe_b200_xtx(self.h, _dptr(X), C.c_int32(X.shape[1]), _dptr(S)))
 
@@ -274,6 +295,9 @@ class Operator:
         col = np.empty(self.prob.nCells, dtype=np.int32)
         _check(self.lib.dftfe_b200_get_colouring(self.h, C.byref(nc), _ptr(col)))
         return nc.value, col
+
+    def set_option(self, name: str, value: int):
+        _check(self.lib.dftfe_b200_set_option(self.h, name.encode(), C.c_int32(value)))
 
     def profile_enable(self, on: bool = True):
         _check(self.lib.dftfe_b200_profile_enable(self.h, C.c_int32(int(on))))

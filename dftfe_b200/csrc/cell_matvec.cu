@@ -57,8 +57,13 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
 
 // H_c (row-major n x n as stored by the reference) -> fragment-major:
 // Ht[cell][ks][mt][lane] = Hm[mt*8 + lane/4][ks*4 + lane%4], zero padded.
+// The mass scalings of H~ = M^-1/2 H M^-1/2 are folded in here, once per
+// set_cell_hamiltonian: Ht holds rowOut[row(c,i)] * H_c[i][k] * rowIn[row(c,k)], so the
+// per-degree kernels gather raw rows (pure copies - TMA-able) and scale nothing.
 template <int NODES>
-__global__ void retile_H_kernel(const double *__restrict__ H, double *__restrict__ Ht, int64_t nCells) {
+__global__ void retile_H_kernel(const double *__restrict__ H, double *__restrict__ Ht, int64_t nCells,
+                                const uint32_t *__restrict__ cellRows, const double *__restrict__ rowIn,
+                                const double *__restrict__ rowOut) {
   using C = CellCfg<NODES>;
   const int64_t total = nCells * (int64_t)C::HT_PER_CELL;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
@@ -72,7 +77,11 @@ __global__ void retile_H_kernel(const double *__restrict__ H, double *__restrict
     const int i = mt * 8 + lane / 4;
     const int k = ks * 4 + lane % 4;
     double v = 0.0;
-    if (i < NODES && k < NODES) v = H[cell * (int64_t)NODES * NODES + (int64_t)i * NODES + k];
+    if (i < NODES && k < NODES) {
+      v = H[cell * (int64_t)NODES * NODES + (int64_t)i * NODES + k];
+      const uint32_t ri = cellRows[cell * NODES + i] & 0x7fffffffu, rk = cellRows[cell * NODES + k] & 0x7fffffffu;
+      v = rowOut[ri] * v * rowIn[rk];
+    }
     Ht[idx] = v;
   }
 }
@@ -212,6 +221,224 @@ cell_matvec_kernel(const double *__restrict__ Ht, const uint32_t *__restrict__ c
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// Fast path: persistent, warp-specialised version of the kernel above.
+//   * one CTA per SM loops over the (cell, column-tile) items of a colour;
+//   * a producer warp gathers the NEXT item's X tile with 1-D TMA bulk copies
+//     (cp.async.bulk, one 256-byte row segment each, completion on an mbarrier)
+//     into the other half of a double-buffered shared-memory tile while
+//   * twelve MMA warps run the DMMA k-loop of the current item with a 4-deep
+//     register prefetch of their A fragments and then do the recurrence /
+//     assembly epilogue straight from registers.
+// No CTA-wide barrier inside the loop: warps drift, so one warp's epilogue
+// overlaps its SMSP neighbours' DMMAs.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+template <int NODES>
+struct PersistCfg {
+  using C = CellCfg<NODES>;
+  static constexpr int MMA_WARPS = C::WARPS;
+  static constexpr int THREADS = (MMA_WARPS + 1) * 32;  // + one producer warp
+  static constexpr size_t XBUF = (size_t)C::KPAD * LDS;  // doubles per buffer
+  static constexpr size_t SMEM = 2 * XBUF * sizeof(double) + 2 * NODES * sizeof(uint32_t) + 4 * sizeof(uint64_t);
+  static constexpr int APF = 4;  // A-fragment prefetch depth in k-steps
+};
+
+template <int NODES>
+__global__ void __launch_bounds__(PersistCfg<NODES>::THREADS, 1)
+cell_matvec_persistent_kernel(const double *__restrict__ Ht, const uint32_t *__restrict__ cellRows,
+                              const int32_t *__restrict__ cells, int nItems, const double *__restrict__ src,
+                              double *__restrict__ dst, int ldx, int nColTiles, EpilogueParams ep) {
+  using C = CellCfg<NODES>;
+  using P = PersistCfg<NODES>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *Xs = reinterpret_cast<double *>(smem_raw);                                  // [2][KPAD][LDS]
+  uint32_t *rowsS = reinterpret_cast<uint32_t *>(smem_raw + 2 * P::XBUF * sizeof(double));  // [2][NODES]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + 2 * P::XBUF * sizeof(double) +
+                                                ((2 * NODES * sizeof(uint32_t) + 7) / 8) * 8);
+  uint64_t *full = bars, *empty = bars + 2;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5;
+  const int lane = tid & 31;
+
+  // zero both tiles once (pad rows k >= NODES and pad columns stay zero forever)
+  for (int i = tid; i < (int)(2 * P::XBUF); i += P::THREADS) Xs[i] = 0.0;
+  if (tid == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    mbar_init(&empty[0], P::MMA_WARPS);
+    mbar_init(&empty[1], P::MMA_WARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  // generic-proxy zero fill must be ordered before the async-proxy (TMA) writes
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+
+  if (warp == P::MMA_WARPS) {
+    // ===== producer warp: gather rows of the next item through the index map =====
+    int it = 0;
+    for (int item = blockIdx.x; item < nItems; item += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      mbar_wait(&empty[buf], ph ^ 1);
+      const int cell = cells[item / nColTiles];
+      const int col0 = (item % nColTiles) * BT;
+      uint32_t *rs = rowsS + buf * NODES;
+      double *xs = Xs + buf * P::XBUF;
+      const uint32_t *cr = cellRows + (size_t)cell * NODES;
+      for (int i = lane; i < NODES; i += 32) rs[i] = cr[i];
+      __syncwarp();
+      if (lane == 0) mbar_arrive_expect_tx(&full[buf], (uint32_t)(NODES * BT * sizeof(double)));
+      __syncwarp();
+      for (int k = lane; k < NODES; k += 32) {
+        const uint32_t r = rs[k] & 0x7fffffffu;
+        tma_bulk_g2s(xs + k * LDS, src + (size_t)r * ldx + col0, BT * sizeof(double), &full[buf]);
+      }
+    }
+  } else {
+    // ===== MMA warps =====
+    const double *xb0 = Xs + (lane & 3) * LDS + (lane >> 2);
+    int it = 0;
+    for (int item = blockIdx.x; item < nItems; item += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const uint32_t ph = (it >> 1) & 1;
+      const int cell = cells[item / nColTiles];
+      const int col0 = (item % nColTiles) * BT;
+      const double *Hc = Ht + (size_t)cell * C::HT_PER_CELL + lane;
+      const double *xb = xb0 + buf * P::XBUF;
+
+      double acc[C::TPW][NT][2];
+#pragma unroll
+      for (int t = 0; t < C::TPW; ++t)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) acc[t][nt][0] = acc[t][nt][1] = 0.0;
+
+      // A prefetch ring (does not depend on the gathered tile: issue before waiting)
+      double a[P::APF][C::TPW];
+#pragma unroll
+      for (int s = 0; s < P::APF; ++s)
+#pragma unroll
+        for (int t = 0; t < C::TPW; ++t) {
+          const int mt = warp + t * C::WARPS;
+          a[s][t] = (mt < C::MT && s < C::KS) ? __ldg(Hc + (size_t)(s * C::MT + mt) * 32) : 0.0;
+        }
+
+      mbar_wait(&full[buf], ph);
+
+      int ks = 0;
+      for (; ks + P::APF <= C::KS; ks += P::APF) {
+#pragma unroll
+        for (int s = 0; s < P::APF; ++s) {
+          double b[NT];
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) b[nt] = xb[((ks + s) * 4) * LDS + nt * 8];
+#pragma unroll
+          for (int t = 0; t < C::TPW; ++t) {
+            if (warp + t * C::WARPS < C::MT) {
+#pragma unroll
+              for (int nt = 0; nt < NT; ++nt) dmma884(acc[t][nt][0], acc[t][nt][1], a[s][t], b[nt]);
+            }
+          }
+#pragma unroll
+          for (int t = 0; t < C::TPW; ++t) {
+            const int mt = warp + t * C::WARPS;
+            if (mt < C::MT && ks + s + P::APF < C::KS)
+              a[s][t] = __ldg(Hc + (size_t)((ks + s + P::APF) * C::MT + mt) * 32);
+          }
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < C::KS % P::APF; ++s) {
+        double b[NT];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) b[nt] = xb[((ks + s) * 4) * LDS + nt * 8];
+#pragma unroll
+        for (int t = 0; t < C::TPW; ++t) {
+          if (warp + t * C::WARPS < C::MT) {
+#pragma unroll
+            for (int nt = 0; nt < NT; ++nt) dmma884(acc[t][nt][0], acc[t][nt][1], a[s][t], b[nt]);
+          }
+        }
+      }
+
+      // rows of this warp's tiles, then release the buffer to the producer
+      uint32_t fr[C::TPW];
+#pragma unroll
+      for (int t = 0; t < C::TPW; ++t) {
+        const int i = (warp + t * C::WARPS) * 8 + (lane >> 2);
+        fr[t] = (i < NODES) ? rowsS[buf * NODES + i] : 0u;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[buf]);
+
+      // ---- epilogue (full tiles, even ldx: guaranteed by the launcher)
+#pragma unroll
+      for (int t = 0; t < C::TPW; ++t) {
+        const int mt = warp + t * C::WARPS;
+        const int i = mt * 8 + (lane >> 2);
+        if (mt < C::MT && i < NODES) {
+          const uint32_t r = fr[t] & 0x7fffffffu;
+          const bool first = (fr[t] >> 31) != 0;
+          const double so = ep.s * (ep.rowOut ? __ldg(ep.rowOut + r) : 1.0);
+          double ca = 0.0, cb = 1.0;
+          if (first) {
+            ca = ep.a * (ep.rowA ? __ldg(ep.rowA + r) : 1.0);
+            cb = ep.b * (ep.rowB ? __ldg(ep.rowB + r) : 1.0);
+          }
+          double *drow = dst + (size_t)r * ldx + col0 + (lane & 3) * 2;
+          const double *srow = src + (size_t)r * ldx + col0 + (lane & 3) * 2;
+          double2 d[NT], sv[NT];
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) {
+            d[nt] = (cb != 0.0) ? *reinterpret_cast<const double2 *>(drow + nt * 8) : make_double2(0.0, 0.0);
+            sv[nt] = (ca != 0.0) ? *reinterpret_cast<const double2 *>(srow + nt * 8) : make_double2(0.0, 0.0);
+          }
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) {
+            double2 o;
+            o.x = so * acc[t][nt][0] + ca * sv[nt].x + cb * d[nt].x;
+            o.y = so * acc[t][nt][1] + ca * sv[nt].y + cb * d[nt].y;
+            *reinterpret_cast<double2 *>(drow + nt * 8) = o;
+          }
+        }
+      }
+    }
+  }
+}
+
 // rows that no owned cell touches still need the first-touch formula (contrib = 0)
 __global__ void orphan_first_touch_kernel(const uint32_t *__restrict__ rows, int64_t nRows,
                                           const double *__restrict__ src, double *__restrict__ dst, int ncols,
@@ -241,13 +468,32 @@ int launch_impl(dftfe_b200_ctx *ctx, const double *src, double *dst, int ncols, 
     attr_set = true;
   }
   const int nColTiles = (ncols + BT - 1) / BT;
+  using P = PersistCfg<NODES>;
+  static bool attr2_set = false;
+  if (!attr2_set && P::SMEM <= 227 * 1024) {
+    DB_CUDA(cudaFuncSetAttribute(cell_matvec_persistent_kernel<NODES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)P::SMEM));
+    attr2_set = true;
+  }
+  // fast path needs full 32-column tiles, 16-byte aligned row segments and no extra gather scale
+  const bool fast = (P::SMEM <= 227 * 1024) && (ncols % BT == 0) && (ldx % 2 == 0) && ep.rowIn == nullptr &&
+                    ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
+                    !ctx->force_generic_cell_kernel;
   for (int k = 0; k < ctx->nColours; ++k) {
     const int nCellsK = ctx->colourStart_h[k + 1] - ctx->colourStart_h[k];
     if (nCellsK == 0) continue;
     ProfScope ps(ctx, "cell_matvec");
-    cell_matvec_kernel<NODES><<<nCellsK * nColTiles, C::THREADS, C::SMEM, ctx->stream>>>(
-        ctx->Htiled.p, ctx->cellRowsFlagged.p, ctx->colourCells.p + ctx->colourStart_h[k], src, dst, ncols, ldx,
-        nColTiles, ep);
+    const int nItems = nCellsK * nColTiles;
+    if (fast) {
+      const int grid = std::min(nItems, ctx->num_sms);
+      cell_matvec_persistent_kernel<NODES><<<grid, P::THREADS, P::SMEM, ctx->stream>>>(
+          ctx->Htiled.p, ctx->cellRowsFlagged.p, ctx->colourCells.p + ctx->colourStart_h[k], nItems, src, dst, ldx,
+          nColTiles, ep);
+    } else {
+      cell_matvec_kernel<NODES><<<nItems, C::THREADS, C::SMEM, ctx->stream>>>(
+          ctx->Htiled.p, ctx->cellRowsFlagged.p, ctx->colourCells.p + ctx->colourStart_h[k], src, dst, ncols, ldx,
+          nColTiles, ep);
+    }
   }
   DB_CUDA(cudaGetLastError());
   return 0;
@@ -258,7 +504,9 @@ int retile_impl(dftfe_b200_ctx *ctx, const double *H_d) {
   using C = CellCfg<NODES>;
   DB_TRY(ctx->Htiled.alloc((size_t)ctx->nC * C::HT_PER_CELL));
   ctx->launches += 1;
-  retile_H_kernel<NODES><<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(H_d, ctx->Htiled.p, ctx->nC);
+  retile_H_kernel<NODES><<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(H_d, ctx->Htiled.p, ctx->nC,
+                                                                    ctx->cellRowsFlagged.p, ctx->rowIn.p,
+                                                                    ctx->rowOut.p);
   DB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -284,6 +532,9 @@ int cell_kernel_supported(int n) {
 }
 
 int retile_cell_hamiltonian(dftfe_b200_ctx *ctx, const double *H_d) {
+  DB_CHECK(ctx->have_map && ctx->have_mass,
+           "set_cell_hamiltonian needs set_index_map, set_constraints and set_mass first (the M^-1/2 scalings are "
+           "folded into the re-tiled cell matrices)");
   DB_DISPATCH_NODES(ctx->n, retile_impl, ctx, H_d);
 }
 

@@ -12,6 +12,8 @@
 // device-to-device copies between two process-wide barriers.  It exists so that
 // the multi-rank path (pack -> exchange -> unpack-add, all-reduce) can be
 // parity-tested on a single B200.
+#include <dlfcn.h>
+
 #include <condition_variable>
 #include <cstring>
 #include <memory>
@@ -27,6 +29,36 @@ int launch_copy_rows(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx, int64_t
                      int toBuf);
 int launch_unpack_add(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx, const double *buf,
                       const double *rowScale);
+
+const NcclApi *nccl_api() {
+  static NcclApi api;
+  static int state = 0;  // 0 = untried, 1 = ok, -1 = failed
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  if (state == 0) {
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    state = -1;
+    if (h) {
+#define DB_SYM(field, name) *(void **)(&api.field) = dlsym(h, name)
+      DB_SYM(GetUniqueId, "ncclGetUniqueId");
+      DB_SYM(CommInitRank, "ncclCommInitRank");
+      DB_SYM(CommDestroy, "ncclCommDestroy");
+      DB_SYM(Send, "ncclSend");
+      DB_SYM(Recv, "ncclRecv");
+      DB_SYM(AllReduce, "ncclAllReduce");
+      DB_SYM(GroupStart, "ncclGroupStart");
+      DB_SYM(GroupEnd, "ncclGroupEnd");
+      DB_SYM(GetErrorString, "ncclGetErrorString");
+#undef DB_SYM
+      if (api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.Send && api.Recv && api.AllReduce &&
+          api.GroupStart && api.GroupEnd && api.GetErrorString)
+        state = 1;
+    }
+    if (state != 1) set_error("libnccl.so.2 could not be loaded: %s", h ? "missing symbols" : dlerror());
+  }
+  return state == 1 ? &api : nullptr;
+}
 
 struct LoopbackGroup {
   int nranks = 0;
@@ -98,17 +130,17 @@ int ghost_update(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx) {
   const bool direct = (ldx == ncols);
   double *ghostBase = direct ? x + (size_t)ctx->M * ldx : ctx->recvBuf.p;
   if (ctx->nccl) {
-    DB_NCCL(ncclGroupStart());
+    DB_NCCL(nccl_api()->GroupStart());
     for (size_t t = 0; t < ctx->targetProcs_h.size(); ++t)
-      DB_NCCL(ncclSend(ctx->sendBuf.p + (size_t)ctx->targetOffsets_h[t] * ncols,
+      DB_NCCL(nccl_api()->Send(ctx->sendBuf.p + (size_t)ctx->targetOffsets_h[t] * ncols,
                        (size_t)ctx->nOwnedForTargets_h[t] * ncols, ncclDouble, ctx->targetProcs_h[t], ctx->nccl,
                        ctx->stream));
     for (size_t g = 0; g < ctx->ghostProcs_h.size(); ++g) {
       const int64_t s = ctx->ghostRanges_h[2 * g], e = ctx->ghostRanges_h[2 * g + 1];
-      DB_NCCL(ncclRecv(ghostBase + (size_t)s * ncols, (size_t)(e - s) * ncols, ncclDouble, ctx->ghostProcs_h[g],
+      DB_NCCL(nccl_api()->Recv(ghostBase + (size_t)s * ncols, (size_t)(e - s) * ncols, ncclDouble, ctx->ghostProcs_h[g],
                        ctx->nccl, ctx->stream));
     }
-    DB_NCCL(ncclGroupEnd());
+    DB_NCCL(nccl_api()->GroupEnd());
   } else {
     LoopbackGroup *grp = loopback_of(ctx);
     DB_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -138,17 +170,17 @@ int ghost_accumulate(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx, const d
   double *ghostBase = direct ? x + (size_t)ctx->M * ldx : ctx->sendBuf.p;
   if (!direct) DB_TRY(launch_copy_rows(ctx, x, ncols, ldx, ctx->M, ctx->G, ctx->sendBuf.p, 1));
   if (ctx->nccl) {
-    DB_NCCL(ncclGroupStart());
+    DB_NCCL(nccl_api()->GroupStart());
     for (size_t g = 0; g < ctx->ghostProcs_h.size(); ++g) {
       const int64_t s = ctx->ghostRanges_h[2 * g], e = ctx->ghostRanges_h[2 * g + 1];
-      DB_NCCL(ncclSend(ghostBase + (size_t)s * ncols, (size_t)(e - s) * ncols, ncclDouble, ctx->ghostProcs_h[g],
+      DB_NCCL(nccl_api()->Send(ghostBase + (size_t)s * ncols, (size_t)(e - s) * ncols, ncclDouble, ctx->ghostProcs_h[g],
                        ctx->nccl, ctx->stream));
     }
     for (size_t t = 0; t < ctx->targetProcs_h.size(); ++t)
-      DB_NCCL(ncclRecv(ctx->recvBuf.p + (size_t)ctx->targetOffsets_h[t] * ncols,
+      DB_NCCL(nccl_api()->Recv(ctx->recvBuf.p + (size_t)ctx->targetOffsets_h[t] * ncols,
                        (size_t)ctx->nOwnedForTargets_h[t] * ncols, ncclDouble, ctx->targetProcs_h[t], ctx->nccl,
                        ctx->stream));
-    DB_NCCL(ncclGroupEnd());
+    DB_NCCL(nccl_api()->GroupEnd());
   } else {
     LoopbackGroup *grp = loopback_of(ctx);
     // publish where my ghost payload lives
@@ -191,7 +223,7 @@ int ghost_zero(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx) {
 int allreduce_sum(dftfe_b200_ctx *ctx, double *buf, size_t count) {
   if (ctx->nranks == 1) return 0;
   if (ctx->nccl) {
-    DB_NCCL(ncclAllReduce(buf, buf, count, ncclDouble, ncclSum, ctx->nccl, ctx->stream));
+    DB_NCCL(nccl_api()->AllReduce(buf, buf, count, ncclDouble, ncclSum, ctx->nccl, ctx->stream));
     return 0;
   }
   LoopbackGroup *grp = loopback_of(ctx);

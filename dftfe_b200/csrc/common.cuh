@@ -49,12 +49,29 @@ void set_error(const char *fmt, ...);
     }                                                                                      \
   } while (0)
 
+// NCCL is bound at run time (dlopen of libnccl.so.2 on first use) so that a process
+// that also hosts PyTorch ends up with ONE libnccl - whichever was loaded first -
+// instead of this library pinning the system copy before torch asks for its own.
+struct NcclApi {
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *);
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+  ncclResult_t (*CommDestroy)(ncclComm_t);
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+  ncclResult_t (*GroupStart)();
+  ncclResult_t (*GroupEnd)();
+  const char *(*GetErrorString)(ncclResult_t);
+};
+const NcclApi *nccl_api();  // nullptr (with the error set) when libnccl cannot be loaded
+
 #define DB_NCCL(call)                                                                      \
   do {                                                                                     \
     ncclResult_t r__ = (call);                                                             \
     if (r__ != ncclSuccess) {                                                              \
-      ::dftfe_b200::set_error("NCCL error '%s' at %s:%d (%s)", ncclGetErrorString(r__),    \
-                              __FILE__, __LINE__, #call);                                  \
+      ::dftfe_b200::set_error("NCCL error '%s' at %s:%d (%s)",                             \
+                              ::dftfe_b200::nccl_api()->GetErrorString(r__), __FILE__,     \
+                              __LINE__, #call);                                            \
       return DFTFE_B200_ERR_NCCL;                                                          \
     }                                                                                      \
   } while (0)
@@ -171,7 +188,7 @@ struct dftfe_b200_ctx {
   dftfe_b200::DevBuf<double> rowOut;     // invSqrtM on owned free rows, 1 elsewhere
   dftfe_b200::DevBuf<double> rowLive;    // 1 on owned free rows, 0 elsewhere
   dftfe_b200::DevBuf<double> rowLiveInvSqrtM;  // invSqrtM on owned free rows, 0 elsewhere
-  dftfe_b200::DevBuf<double> rowOutRaw;  // 1 everywhere (owned) - used by bare HXCheby paths
+  dftfe_b200::DevBuf<double> rowInInv, rowOutInv;  // reciprocals: undo the scales folded into Htiled (bare HXCheby)
 
   // --- ghost pattern / NCCL
   int rank = 0, nranks = 1;
@@ -188,11 +205,14 @@ struct dftfe_b200_ctx {
 
   // --- cell Hamiltonian (fragment-major)
   bool have_H = false;
+  bool force_generic_cell_kernel = false;  // test hook: run the non-persistent kernel
   dftfe_b200::DevBuf<double> Htiled;
   dftfe_b200::DevBuf<double> Hstage;   // staging for host uploads
 
   // --- solver state / scratch
   dftfe_b200::DevBuf<double> blockX, blockY;      // (M+G)*B
+  dftfe_b200::DevBuf<double> blockX2;             // second block buffer of the host-pipelined filter
+  cudaStream_t copyIn = nullptr, copyOut = nullptr;
   dftfe_b200::DevBuf<double> HXfull;              // M*Bw
   dftfe_b200::DevBuf<double> denseA, denseB, denseC, denseW;  // N*N scratch
   dftfe_b200::DevBuf<double> eigDev, resDev;

@@ -25,18 +25,23 @@ static int rebuild_row_vectors(dftfe_b200_ctx *ctx, const double *sqrtM_h, const
   const int64_t R = ctx->M + ctx->G;
   std::vector<char> con(R, 0);
   for (uint32_t r : ctx->conRows_h) con[r] = 1;
-  std::vector<double> rowIn(R), rowOut(R), rowLive(R), rowLiveInv(R);
+  std::vector<double> rowIn(R), rowOut(R), rowLive(R), rowLiveInv(R), rowInInv(R), rowOutInv(R);
   for (int64_t r = 0; r < R; ++r) {
     const bool owned = r < ctx->M;
     rowIn[r] = con[r] ? 1.0 : invSqrtM_h[r];
     rowOut[r] = (owned && !con[r]) ? invSqrtM_h[r] : 1.0;
     rowLive[r] = (owned && !con[r]) ? 1.0 : 0.0;
     rowLiveInv[r] = (owned && !con[r]) ? invSqrtM_h[r] : 0.0;
+    rowInInv[r] = rowIn[r] != 0.0 ? 1.0 / rowIn[r] : 0.0;
+    rowOutInv[r] = rowOut[r] != 0.0 ? 1.0 / rowOut[r] : 0.0;
   }
   DB_TRY(ctx->rowIn.upload(rowIn.data(), R, ctx->stream));
   DB_TRY(ctx->rowOut.upload(rowOut.data(), R, ctx->stream));
   DB_TRY(ctx->rowLive.upload(rowLive.data(), R, ctx->stream));
   DB_TRY(ctx->rowLiveInvSqrtM.upload(rowLiveInv.data(), R, ctx->stream));
+  DB_TRY(ctx->rowInInv.upload(rowInInv.data(), R, ctx->stream));
+  DB_TRY(ctx->rowOutInv.upload(rowOutInv.data(), R, ctx->stream));
+  ctx->have_H = false;  // scales are folded into the tiled H: it must be set again
   (void)sqrtM_h;
   return 0;
 }
@@ -120,7 +125,9 @@ void dftfe_b200_destroy(dftfe_b200_ctx *ctx) {
       cudaEventDestroy(pr.first);
       cudaEventDestroy(pr.second);
     }
-  if (ctx->nccl) ncclCommDestroy(ctx->nccl);
+  if (ctx->copyIn) cudaStreamDestroy(ctx->copyIn);
+  if (ctx->copyOut) cudaStreamDestroy(ctx->copyOut);
+  if (ctx->nccl && nccl_api()) nccl_api()->CommDestroy(ctx->nccl);
   if (ctx->cusolver) cusolverDnDestroy(ctx->cusolver);
   if (ctx->cublas) cublasDestroy(ctx->cublas);
   if (ctx->owned_stream) cudaStreamDestroy(ctx->owned_stream);
@@ -370,7 +377,8 @@ int dftfe_b200_set_ghost_pattern(dftfe_b200_ctx *ctx, int32_t rank, int32_t nran
 int dftfe_b200_nccl_unique_id(uint8_t id_out_h[128]) {
   static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is expected to be 128 bytes");
   ncclUniqueId id;
-  DB_NCCL(ncclGetUniqueId(&id));
+  if (!nccl_api()) return DFTFE_B200_ERR_NCCL;
+  DB_NCCL(nccl_api()->GetUniqueId(&id));
   std::memcpy(id_out_h, &id, 128);
   return 0;
 }
@@ -380,7 +388,8 @@ int dftfe_b200_comm_init(dftfe_b200_ctx *ctx, const uint8_t id_h[128], int32_t r
   DB_CHECK(!ctx->nccl, "comm_init: communicator already initialised");
   ncclUniqueId id;
   std::memcpy(&id, id_h, 128);
-  DB_NCCL(ncclCommInitRank(&ctx->nccl, nranks, id, rank));
+  if (!nccl_api()) return DFTFE_B200_ERR_NCCL;
+  DB_NCCL(nccl_api()->CommInitRank(&ctx->nccl, nranks, id, rank));
   ctx->rank = rank;
   ctx->nranks = nranks;
   return 0;
@@ -443,6 +452,17 @@ int dftfe_b200_get_colouring(dftfe_b200_ctx *ctx, int32_t *n_colours_out, int32_
   if (n_colours_out) *n_colours_out = ctx->nColours;
   if (cell_colour_out_h) std::memcpy(cell_colour_out_h, ctx->cellColour_h.data(), ctx->nC * sizeof(int32_t));
   return 0;
+}
+
+int dftfe_b200_set_option(dftfe_b200_ctx *ctx, const char *name, int32_t value) {
+  DB_CTX(ctx);
+  DB_CHECK(name, "set_option: null name");
+  if (std::strcmp(name, "generic_cell_kernel") == 0) {
+    ctx->force_generic_cell_kernel = value != 0;
+    return 0;
+  }
+  set_error("set_option: unknown option '%s'", name);
+  return DFTFE_B200_ERR_INVALID;
 }
 
 int dftfe_b200_profile_enable(dftfe_b200_ctx *ctx, int32_t enable) {

@@ -25,8 +25,9 @@ static int fused_apply_impl(dftfe_b200_ctx *ctx, double *src, double *dst, int n
   ep.a = a;
   ep.b = b;
   ep.s = s;
-  ep.rowIn = ctx->rowIn.p;
-  ep.rowOut = ctx->rowOut.p;
+  // rowIn / rowOut (M^-1/2 on free rows) are folded into the tiled cell matrices
+  ep.rowIn = nullptr;
+  ep.rowOut = nullptr;
   ep.rowA = ctx->rowLive.p;
   ep.rowB = rowB;
   DB_TRY(launch_cell_matvec(ctx, src, dst, ncols, ldx, ep));
@@ -63,7 +64,9 @@ int op_hx_cheby(dftfe_b200_ctx *ctx, double *src, double *dst, int ncols) {
   const int ldx = ncols;
   DB_TRY(ghost_update(ctx, src, ncols, ldx));
   DB_TRY(launch_distribute(ctx, src, ncols, ldx, nullptr));
-  EpilogueParams ep;  // a=0, b=1, s=1, no row scalings: pure accumulate
+  EpilogueParams ep;  // a=0, b=1, s=1: pure accumulate; undo the scales folded into the tiled H
+  ep.rowIn = ctx->rowInInv.p;
+  ep.rowOut = ctx->rowOutInv.p;
   DB_TRY(launch_cell_matvec(ctx, src, dst, ncols, ldx, ep));
   DB_TRY(launch_slave_to_master(ctx, dst, ncols, ldx, nullptr));
   DB_TRY(ghost_zero(ctx, src, ncols, ldx));
@@ -491,6 +494,82 @@ static int cgs_rr(dftfe_b200_ctx *ctx, double *X, int N, double *eig_h) {
   return 0;
 }
 
+// HOT LOOP 1 of solve() (solver .cc:376-526) on a device-resident X (M x N):
+// slice block -> filter -> write back, for every block of B columns.
+static int filter_all_impl(dftfe_b200_ctx *ctx, double *X, int N, int m, double a, double b, double a0,
+                           const double *inScale) {
+  const int B = std::min(ctx->B, N);
+  DB_CHECK(N % B == 0, "number of wavefunctions (%d) must be a multiple of the Chebyshev block size (%d)", N, B);
+  DB_TRY(ensure_block_scratch(ctx));
+  for (int j = 0; j < N; j += B) {
+    DB_TRY(launch_block_copy_from_full(ctx, X, N, j, ctx->blockX.p, B, ctx->M, inScale));
+    DB_TRY(ghost_zero(ctx, ctx->blockX.p, B, B));
+    DB_TRY(cheb_filter_impl(ctx, ctx->blockX.p, ctx->blockY.p, B, m, a, b, a0));
+    DB_TRY(launch_block_copy_to_full(ctx, X, N, j, ctx->blockX.p, B, ctx->M, nullptr));
+  }
+  return 0;
+}
+
+// Same loop for a HOST-resident X (pinned memory recommended): block i+1 is copied
+// in and block i-1 copied out on two copy streams while block i is filtered on the
+// context stream, so PCIe traffic hides behind the cell kernels.
+static int filter_all_host_impl(dftfe_b200_ctx *ctx, double *X_h, int N, int m, double a, double b, double a0) {
+  const int B = std::min(ctx->B, N);
+  DB_CHECK(N % B == 0, "number of wavefunctions (%d) must be a multiple of the Chebyshev block size (%d)", N, B);
+  const size_t blk = (size_t)(ctx->M + ctx->G) * B;
+  DB_TRY(ctx->blockX.alloc(blk));
+  DB_TRY(ctx->blockX2.alloc(blk));
+  DB_TRY(ctx->blockY.alloc(blk));
+  if (!ctx->copyIn) {
+    DB_CUDA(cudaStreamCreateWithFlags(&ctx->copyIn, cudaStreamNonBlocking));
+    DB_CUDA(cudaStreamCreateWithFlags(&ctx->copyOut, cudaStreamNonBlocking));
+  }
+  const int nb = N / B;
+  std::vector<cudaEvent_t> evIn(nb), evComp(nb), evOut(nb);
+  for (int i = 0; i < nb; ++i) {
+    DB_CUDA(cudaEventCreateWithFlags(&evIn[i], cudaEventDisableTiming));
+    DB_CUDA(cudaEventCreateWithFlags(&evComp[i], cudaEventDisableTiming));
+    DB_CUDA(cudaEventCreateWithFlags(&evOut[i], cudaEventDisableTiming));
+  }
+  // the copy streams must not start before earlier work on the context stream is done
+  cudaEvent_t evStart;
+  DB_CUDA(cudaEventCreateWithFlags(&evStart, cudaEventDisableTiming));
+  DB_CUDA(cudaEventRecord(evStart, ctx->stream));
+  DB_CUDA(cudaStreamWaitEvent(ctx->copyIn, evStart, 0));
+  int rc = 0;
+  auto body = [&]() -> int {
+    for (int i = 0; i < nb; ++i) {
+      double *buf = (i & 1) ? ctx->blockX2.p : ctx->blockX.p;
+      if (i >= 2) DB_CUDA(cudaStreamWaitEvent(ctx->copyIn, evOut[i - 2], 0));  // buffer free again
+      DB_CUDA(cudaMemcpy2DAsync(buf, (size_t)B * sizeof(double), X_h + (size_t)i * B, (size_t)N * sizeof(double),
+                                (size_t)B * sizeof(double), (size_t)ctx->M, cudaMemcpyHostToDevice, ctx->copyIn));
+      DB_CUDA(cudaEventRecord(evIn[i], ctx->copyIn));
+      DB_CUDA(cudaStreamWaitEvent(ctx->stream, evIn[i], 0));
+      DB_TRY(ghost_zero(ctx, buf, B, B));
+      DB_TRY(cheb_filter_impl(ctx, buf, ctx->blockY.p, B, m, a, b, a0));
+      DB_CUDA(cudaEventRecord(evComp[i], ctx->stream));
+      DB_CUDA(cudaStreamWaitEvent(ctx->copyOut, evComp[i], 0));
+      DB_CUDA(cudaMemcpy2DAsync(X_h + (size_t)i * B, (size_t)N * sizeof(double), buf, (size_t)B * sizeof(double),
+                                (size_t)B * sizeof(double), (size_t)ctx->M, cudaMemcpyDeviceToHost, ctx->copyOut));
+      DB_CUDA(cudaEventRecord(evOut[i], ctx->copyOut));
+    }
+    // the call returns with the result visible to work queued on the context stream
+    DB_CUDA(cudaStreamWaitEvent(ctx->stream, evOut[nb - 1], 0));
+    if (nb >= 2) DB_CUDA(cudaStreamWaitEvent(ctx->stream, evOut[nb - 2], 0));
+    DB_CUDA(cudaStreamSynchronize(ctx->stream));
+    return 0;
+  };
+  rc = body();
+  if (rc != 0) cudaDeviceSynchronize();
+  for (int i = 0; i < nb; ++i) {
+    cudaEventDestroy(evIn[i]);
+    cudaEventDestroy(evComp[i]);
+    cudaEventDestroy(evOut[i]);
+  }
+  cudaEventDestroy(evStart);
+  return rc;
+}
+
 static const unsigned int order_lookup[][2] = {{500, 24},     {750, 30},     {1000, 39},    {1500, 50},
                                                {2000, 53},    {3000, 57},    {4000, 62},    {5000, 69},
                                                {9000, 77},    {14000, 104},  {20000, 119},  {30000, 162},
@@ -534,12 +613,7 @@ static int solve_impl(dftfe_b200_ctx *ctx, double *X, int N, const dftfe_b200_so
   if (order < 1) order = 1;
 
   // X <- M^1/2 X (solver .cc:358-363) fused into the block copy; filter; copy back (:376-526)
-  for (int j = 0; j < N; j += B) {
-    DB_TRY(launch_block_copy_from_full(ctx, X, N, j, ctx->blockX.p, B, ctx->M, ctx->sqrtM.p));
-    DB_TRY(ghost_zero(ctx, ctx->blockX.p, B, B));
-    DB_TRY(cheb_filter_impl(ctx, ctx->blockX.p, ctx->blockY.p, B, (int)order, ctx->bLow, ctx->bUp, ctx->a0));
-    DB_TRY(launch_block_copy_to_full(ctx, X, N, j, ctx->blockX.p, B, ctx->M, nullptr));
-  }
+  DB_TRY(filter_all_impl(ctx, X, N, (int)order, ctx->bLow, ctx->bUp, ctx->a0, ctx->sqrtM.p));
   if (p->use_cgs_rr)
     DB_TRY(cgs_rr(ctx, X, N, eig_h));
   else
@@ -598,6 +672,19 @@ int dftfe_b200_cheb_filter(dftfe_b200_ctx *ctx, double *x_d, double *y_d, int32_
   DB_CTX(ctx);
   DB_TRY(check_cols(ctx, ncols));
   return cheb_filter_impl(ctx, x_d, y_d, ncols, m, a, b, a0);
+}
+
+int dftfe_b200_cheb_filter_all(dftfe_b200_ctx *ctx, double *X_d, int32_t N, int32_t m, double a, double b,
+                               double a0) {
+  DB_CTX(ctx);
+  return filter_all_impl(ctx, X_d, N, m, a, b, a0, nullptr);
+}
+
+int dftfe_b200_cheb_filter_all_host(dftfe_b200_ctx *ctx, double *X_h, int32_t N, int32_t m, double a, double b,
+                                    double a0) {
+  DB_CTX(ctx);
+  DB_CHECK(X_h, "cheb_filter_all_host: null host pointer");
+  return filter_all_host_impl(ctx, X_h, N, m, a, b, a0);
 }
 
 int dftfe_b200_xtx(dftfe_b200_ctx *ctx, const double *X_d, int32_t N, double *S_d) {

@@ -168,6 +168,17 @@ int dftfe_b200_hx_cheby(dftfe_b200_ctx *ctx, double *src_d, double *dst_d, int32
 int dftfe_b200_cheb_filter(dftfe_b200_ctx *ctx, double *x_d, double *y_d, int32_t ncols, int32_t m, double a,
                            double b, double a0);
 
+/* The blocked filter loop of solve() (solver .cc:376-526) over a device-resident X
+ * (row-major M x N, Loewdin basis, N a multiple of B): every block of B columns is
+ * sliced out, filtered and written back. */
+int dftfe_b200_cheb_filter_all(dftfe_b200_ctx *ctx, double *X_d, int32_t N, int32_t m, double a, double b,
+                               double a0);
+/* Same for a HOST-resident X (pinned memory recommended).  Host->device and
+ * device->host block copies run on two copy streams and overlap the filtering of
+ * the neighbouring blocks.  Synchronous: X_h holds the result on return. */
+int dftfe_b200_cheb_filter_all_host(dftfe_b200_ctx *ctx, double *X_h, int32_t N, int32_t m, double a, double b,
+                                    double a0);
+
 /* ---- subspace projections / rotation ------------------------------------- */
 /* S = X^T X, all-reduced; full symmetric N x N written to S_d (row-major)
  * (fillParallelOverlapMatScalapack, linearAlgebraOperationsDevice.cc:3078-3240). */
@@ -198,6 +209,9 @@ int dftfe_b200_solve(dftfe_b200_ctx *ctx, double *X_d, int32_t N, const dftfe_b2
 int dftfe_b200_get_spectrum_bounds(dftfe_b200_ctx *ctx, double out_h[3]);
 
 /* ---- introspection / measurement ----------------------------------------- */
+/* Options: "generic_cell_kernel" = 1 forces the non-persistent cell kernel (the path
+ * taken anyway for ragged column counts, odd leading dimensions and FE order 7). */
+int dftfe_b200_set_option(dftfe_b200_ctx *ctx, const char *name, int32_t value);
 /* Number of cell colours, and per-colour cell counts (n_out entries filled). */
 int dftfe_b200_get_colouring(dftfe_b200_ctx *ctx, int32_t *n_colours_out, int32_t *cell_colour_out_h);
 /* Per-kernel CUDA-event timing on the context stream.  names: "cell_matvec",

@@ -40,12 +40,14 @@ def capi(lib_built):
     (6, (2, 2, 2), (True, True, True), 32),
     (7, (2, 2, 2), (False, True, True), 8),
 ])
-def test_hx_and_hxcheby_single_rank(capi, p, ncells, periodic, B):
+@pytest.mark.parametrize("generic", [0, 1])
+def test_hx_and_hxcheby_single_rank(capi, p, ncells, periodic, B, generic):
     from oracle import chfsi_oracle as O
 
     mesh, ranks = make_problem(p, ncells, 1.1, periodic)
     rp = ranks[0]
     op = capi.Operator(rp, B)
+    op.set_option("generic_cell_kernel", generic)
     op.set_cell_hamiltonian(rp.H)
     X = scatter_to_ranks(ranks, random_global(mesh, B, seed=p), loewdin=True)
     Y0 = scatter_to_ranks(ranks, random_global(mesh, B, seed=p + 100), loewdin=True)
