@@ -1,0 +1,92 @@
+"""CPU suite: the C-ABI library loads, exports every symbol the header declares, its
+host-only entry points are bit-exact against the oracle, and compute entry points fail
+loudly (no CPU fallback) when there is no GPU."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle import chfsi_oracle as O
+from tests.helpers import make_problem
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def capi(lib_built):
+    from dftfe_b200 import capi
+
+    capi.load()
+    return capi
+
+
+def _header_symbols():
+    text = open(os.path.join(ROOT, "include", "dftfe_b200.h")).read()
+    return sorted(set(re.findall(r"\b(dftfe_b200_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(capi):
+    lib = capi.load()
+    syms = _header_symbols()
+    assert len(syms) >= 40
+    for s in syms:
+        assert hasattr(lib, s), f"{s} declared in include/dftfe_b200.h but not exported"
+    assert sorted(capi.EXPORTED_SYMBOLS) == syms
+    assert b"sm_100a" in lib.dftfe_b200_version()
+
+
+def test_library_has_no_hard_nccl_or_torch_dependency(capi):
+    import subprocess
+
+    out = subprocess.run(["ldd", str(capi.lib_path())], capture_output=True, text=True).stdout
+    assert "libnccl" not in out and "libtorch" not in out and "libc10" not in out
+
+
+def test_index_map_builder_bit_exact(capi):
+    mesh, ranks = make_problem(2, (4, 3, 3), 1.0, (True, False, True), nranks=4, potential=False)
+    for rp in ranks:
+        for B in (1, 7, 256):
+            ref = O.compute_cell_local_index_set_map(rp.cellGlobalDofs, rp.ownedStart, rp.ownedEnd, rp.ghostGlobal, B)
+            got = capi.build_index_map(rp.cellGlobalDofs, rp.ownedStart, rp.ownedEnd, rp.ghostGlobal, B)
+            assert got.dtype == np.uint64 and np.array_equal(got, ref)
+            assert np.array_equal(got, rp.index_map(B))
+        flags = O.proc_boundary_flags(ranks, rp.rank)
+        assert np.array_equal(flags, rp.procBoundaryFlags)
+
+
+def test_index_map_builder_rejects_unknown_dof(capi):
+    mesh, ranks = make_problem(1, (2, 2, 2), 1.0, (False, False, False), nranks=2, potential=False)
+    rp = ranks[1]
+    bad = rp.cellGlobalDofs.copy()
+    bad[0, 0] = mesh.nNodes + 5
+    with pytest.raises(capi.DftfeB200Error) as e:
+        capi.build_index_map(bad, rp.ownedStart, rp.ownedEnd, rp.ghostGlobal, 4)
+    assert "neither owned nor ghost" in str(e.value)
+
+
+def test_no_cpu_fallback(capi):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    mesh, ranks = make_problem(1, (2, 2, 2), 1.0, (True, True, True), potential=False)
+    with pytest.raises(capi.DftfeB200Error) as e:
+        capi.Operator(ranks[0], 8)
+    assert e.value.code == -2 and "no CPU fallback" in str(e.value)
+
+
+def test_create_rejects_unsupported_element(capi):
+    lib = capi.load()
+    desc = capi.ProblemDesc(nodes_per_cell=100, cheby_block=8, n_cells=1, n_owned=10, n_ghost=0, n_global_dofs=10,
+                            device=0, reserved=0)
+    h = C.c_void_p()
+    rc = lib.dftfe_b200_create(C.byref(desc), C.byref(h))
+    assert rc == -4 and b"nodes per cell" in lib.dftfe_b200_last_error()
+
+
+def test_c_structs_match_header_layout(capi):
+    # int32,int32,int64 x4,int32,int32 and 10 x int32 + double
+    assert C.sizeof(capi.ProblemDesc) == 48
+    assert C.sizeof(capi.SolveParams) == 48

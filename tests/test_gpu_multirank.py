@@ -1,0 +1,122 @@
+"""-m gpu: the multi-rank path (ghost pack -> exchange -> unpack-add, all-reduce) on ONE GPU through
+the library's in-process loopback transport: one context per rank, one host thread per rank."""
+import threading
+
+import numpy as np
+import pytest
+
+from tests.helpers import hanging_like_constraints, make_problem, random_global, scatter_to_ranks
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _run_ranks(nranks, fn):
+    out, errs = [None] * nranks, []
+
+    def tgt(r):
+        try:
+            out[r] = fn(r)
+        except Exception as e:  # noqa: BLE001
+            errs.append((r, repr(e)))
+
+    th = [threading.Thread(target=tgt, args=(r,)) for r in range(nranks)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=600)
+    assert not errs, errs
+    return out
+
+
+@pytest.mark.parametrize("nranks,rank_grid,group", [(2, None, 11), (4, (2, 2, 1), 12), (8, (2, 2, 2), 13)])
+def test_loopback_multirank_filter_and_projections(lib_built, nranks, rank_grid, group):
+    assert torch.cuda.is_available()
+    from dftfe_b200 import capi
+    from oracle import chfsi_oracle as O
+
+    p, B, N = 2, 32, 64
+    mesh, ranks = make_problem(p, (4, 4, 4), 1.1, (True, True, False), nranks=nranks, rank_grid=rank_grid,
+                               extra_constraints=hanging_like_constraints(5))
+    Xg = random_global(mesh, N, seed=21)
+    X = scatter_to_ranks(ranks, Xg, loewdin=True)
+    lo, up = O.lanczos_bounds(ranks)
+    a, a0, m = lo + 0.3 * (up - lo), lo - 0.2, 9
+    # oracle
+    ref_blk = [x[:, :B].copy() for x in X]
+    O.chebyshev_filter_inplace(ranks, ref_blk, m, a, up, a0)
+    S_ref = O.xtx(ranks, X)
+    H_ref = O.xthx(ranks, [x.copy() for x in X], B)
+
+    def rank_fn(r):
+        rp = ranks[r]
+        op = capi.Operator(rp, B, use_torch_stream=False)
+        op.comm_init_loopback(group, r, nranks)
+        op.set_cell_hamiltonian(rp.H)
+        x_d = _dev(X[r][:, :B])
+        y_d = torch.empty_like(x_d)
+        op.chebyshevFilter(x_d, y_d, m, a, up, a0)
+        op.sync()
+        filt = x_d.cpu().numpy()
+        Xf = _dev(X[r][:rp.M])
+        S = torch.empty(N, N, dtype=torch.float64, device="cuda")
+        op.XtX(Xf, S)
+        op.sync()
+        S_h = S.cpu().numpy()
+        op.XtHX(Xf, S)
+        op.sync()
+        H_h = S.cpu().numpy()
+        bounds = op.lanczosLowerUpperBoundEigenSpectrum()
+        op.close()
+        return filt, S_h, H_h, bounds
+
+    res = _run_ranks(nranks, rank_fn)
+    scale = max(np.abs(b).max() for b in ref_blk)
+    for r, (filt, S_h, H_h, bounds) in enumerate(res):
+        rp = ranks[r]
+        assert np.abs(filt[:rp.M] - ref_blk[r][:rp.M]).max() < m * 1e-12 * scale
+        assert np.all(filt[rp.M:] == 0)
+        assert np.abs(S_h - S_ref).max() < 1e-12 * np.abs(S_ref).max()
+        assert np.abs(H_h - H_ref).max() < 1e-11 * np.abs(H_ref).max()
+        assert bounds == (lo, up)
+
+
+def test_loopback_multirank_solve(lib_built):
+    from dftfe_b200 import capi
+    from oracle import chfsi_oracle as O
+
+    nranks, B, N = 2, 16, 16
+    mesh, ranks = make_problem(3, (4, 2, 2), 1.5, (True, True, True), nranks=nranks)
+    Xg = random_global(mesh, N, seed=5)
+    Xo = scatter_to_ranks(ranks, Xg, zero_constrained=False)
+    lo, up = O.lanczos_bounds(ranks)
+    blow0 = lo + (up - lo) * N / mesh.nNodes * 200.0
+    ev_ref = None
+    a0, blow = lo, blow0
+    for _ in range(3):
+        ev_ref, res_ref = O.solve(ranks, Xo, B, 16, (a0, blow, up))
+        a0, blow = ev_ref[0], ev_ref[-1]
+
+    def rank_fn(r):
+        rp = ranks[r]
+        op = capi.Operator(rp, B, use_torch_stream=False)
+        op.comm_init_loopback(21, r, nranks)
+        op.set_cell_hamiltonian(rp.H)
+        solver = capi.ChebyshevSolver(op)
+        Xd = _dev(scatter_to_ranks(ranks, Xg, zero_constrained=False)[r][:rp.M])
+        first = True
+        for _ in range(3):
+            eig, res, ub = solver.solve(Xd, isFirstFilteringCall=first, chebyshevOrder=16, reuseLanczos=True)
+            solver.reinitSpectrumBounds(eig[0], eig[-1])
+            first = False
+        op.close()
+        return eig, res
+
+    out = _run_ranks(nranks, rank_fn)
+    for eig, res in out:
+        assert np.abs(eig - ev_ref).max() < 1e-8
+        assert np.abs(res - res_ref).max() < 1e-6

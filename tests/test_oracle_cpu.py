@@ -1,0 +1,224 @@
+"""CPU suite: pins the oracle (analytic known answers, cross-statement agreement,
+golden fixtures) and the host logic.  No GPU needed."""
+import ctypes
+import os
+
+import numpy as np
+import pytest
+
+from dftfe_b200.femesh import ReferenceCell, build_mesh, gll_points_weights
+from oracle import chfsi_oracle as O
+from tests.helpers import hanging_like_constraints, make_problem, random_global, scatter_to_ranks
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def test_gll_nodes_and_weights():
+    x, w = gll_points_weights(7)
+    assert np.allclose(x[[1, 2]], [-0.830223896278567, -0.468848793470714], atol=1e-14)
+    assert np.allclose(w[[0, 3]], [1.0 / 21.0, 0.487619047619048], atol=1e-13)
+    for n in range(2, 10):
+        x, w = gll_points_weights(n)
+        assert abs(w.sum() - 2.0) < 1e-13 and abs(x[0] + 1) < 1e-15 and abs(x[-1] - 1) < 1e-15
+        # GLL with n points integrates degree 2n-3 exactly
+        k = 2 * n - 3
+        assert abs((w * x ** (k - 1)).sum() - (2.0 / k if (k - 1) % 2 == 0 else 0.0)) < 1e-13
+
+
+def test_reference_cell_operators():
+    ref = ReferenceCell(4, 1.7)
+    assert abs(ref.M1.sum() - 1.7) < 1e-13
+    assert np.abs(ref.K1.sum(axis=1)).max() < 1e-12          # constants are in the kernel of the stiffness
+    assert abs(ref.mass_gll.sum() - 1.7 ** 3) < 1e-12
+    assert np.abs(ref.K3 - ref.K3.T).max() < 1e-12
+
+
+def _dense_operator(rp):
+    nn = rp.M
+    Hf = np.zeros((nn, nn))
+    for c in range(rp.nCells):
+        ids = rp.cellLocalDofs[c]
+        Hf[np.ix_(ids, ids)] += rp.H[c]
+    C = np.eye(nn)
+    for i, row in enumerate(rp.rowIdsLocal):
+        C[row, :] = 0
+        s = rp.rowStarts[i]
+        for j in range(rp.rowSizes[i]):
+            C[row, rp.colIdsLocal[s + j]] = rp.colValues[s + j]
+    D = rp.invSqrtMass[:nn]
+    A = D[:, None] * (C.T @ Hf @ C) * D[None, :]
+    return A, D > 0
+
+
+def test_plane_wave_eigenvalues_periodic_box():
+    """-1/2 Laplacian on a periodic cube: eigenvalues 1/2 |2 pi k / L|^2 (known answer i)."""
+    mesh, ranks = make_problem(5, (3, 3, 3), 2.0, (True, True, True), potential=False)
+    A, free = _dense_operator(ranks[0])
+    ev = np.linalg.eigvalsh(A[np.ix_(free, free)])
+    L = 6.0
+    exact = 0.5 * (2 * np.pi / L) ** 2
+    assert abs(ev[0]) < 1e-10
+    assert np.abs(ev[1:7] - exact).max() < 1e-6
+    assert np.abs(ev[7:19] - 2 * exact).max() < 1e-5
+    # the operator the oracle applies is exactly this matrix
+    X = np.eye(ranks[0].M)[:, :6].copy()
+    dst = [np.zeros_like(X)]
+    O.HX(ranks, [X.copy()], dst, False, 1.0)
+    assert np.abs(dst[0] - A[:, :6]).max() < 1e-12
+
+
+def test_harmonic_oscillator_levels():
+    """v = 1/2 r^2 in a large Dirichlet box: levels n + 3/2 (known answer ii)."""
+    from dftfe_b200.femesh import build_mesh
+
+    mesh = build_mesh(6, (2, 2, 2), 6.0, periodic=(False, False, False))
+    c = np.array(mesh.box) / 2.0
+    rp = mesh.rank_problem(0, potential=lambda xyz: 0.5 * np.sum((xyz - c) ** 2, axis=-1), vquad="gauss")
+    A, free = _dense_operator(rp)
+    ev = np.linalg.eigvalsh(A[np.ix_(free, free)])
+    assert abs(ev[0] - 1.5) < 5e-3 and np.abs(ev[1:4] - 2.5).max() < 5e-2
+
+
+@pytest.mark.parametrize("nranks", [1, 2, 4])
+def test_filter_of_exact_eigenvector_is_scalar(nranks):
+    """Known answer iii: filtering the constant mode (eigenvalue 0 of -1/2 Laplacian) scales it by
+    the closed-form Chebyshev value; also multi-rank emulation == single rank."""
+    mesh, ranks = make_problem(3, (4, 2, 2), 2.0, (True, True, True), nranks=nranks, potential=False)
+    X = []
+    for rp in ranks:
+        x = np.zeros((rp.M + rp.G, 1))
+        x[:rp.M, 0] = rp.sqrtMass[:rp.M]
+        X.append(x)
+    for m in (1, 2, 7, 12):
+        Y = [x.copy() for x in X]
+        O.chebyshev_filter_inplace(ranks, Y, m, 3.0, 40.0, -1.0)
+        sc = O.chebyshev_scalar(0.0, m, 3.0, 40.0, -1.0)
+        for rp, x, y in zip(ranks, X, Y):
+            free = rp.sqrtMass[:rp.M] > 0
+            assert np.abs(y[:rp.M, 0][free] / x[:rp.M, 0][free] - sc).max() < 1e-13
+
+
+def test_cpu_and_device_statements_of_the_filter_agree():
+    mesh, ranks = make_problem(3, (3, 3, 2), 1.3, (True, True, False), nranks=2,
+                               extra_constraints=hanging_like_constraints(5))
+    X = scatter_to_ranks(ranks, random_global(mesh, 4, 1), loewdin=True)
+    A = [x.copy() for x in X]
+    O.chebyshev_filter_inplace(ranks, A, 9, 2.0, 60.0, -2.1)
+    Bv = O.chebyshev_filter_device_state(ranks, X, 9, 2.0, 60.0, -2.1)
+    for rp, a, b in zip(ranks, A, Bv):
+        assert np.abs(a[:rp.M] - b[:rp.M]).max() <= 1e-14 * np.abs(a).max()
+
+
+def test_constraint_pair_is_adjoint():
+    """Known answer v: <C x, y> = <x, C^T y> for homogeneous constraints."""
+    mesh, ranks = make_problem(2, (3, 3, 3), 1.0, (True, False, True), potential=False,
+                               extra_constraints=hanging_like_constraints(6))
+    rp = ranks[0]
+    rng = np.random.default_rng(2)
+    x = rng.normal(size=(rp.M, 3))
+    y = rng.normal(size=(rp.M, 3))
+    x[rp.rowIdsLocal] = 0
+    Cx = x.copy()
+    O.distribute(rp, Cx)
+    Cty = y.copy()
+    O.distribute_slave_to_master(rp, Cty)
+    assert abs(np.sum(Cx * y) - np.sum(x * Cty)) < 1e-12
+    z = y.copy()
+    O.set_zero(rp, z)
+    assert np.all(z[rp.rowIdsLocal] == 0) and np.array_equal(np.delete(z, rp.rowIdsLocal, 0), np.delete(y, rp.rowIdsLocal, 0))
+
+
+@pytest.mark.parametrize("nranks,rank_grid", [(2, None), (4, (2, 2, 1)), (8, (2, 2, 2))])
+def test_multirank_emulation_matches_single_rank(nranks, rank_grid):
+    p, nc = 2, (4, 4, 4)
+    mesh1, r1 = make_problem(p, nc, 1.0, (True, True, False))
+    meshN, rN = make_problem(p, nc, 1.0, (True, True, False), nranks=nranks, rank_grid=rank_grid)
+    # same physical vector: index by natural node id
+    rng = np.random.default_rng(3)
+    Xnat = rng.uniform(-1, 1, size=(mesh1.nNodes, 5))
+    X1 = scatter_to_ranks(r1, Xnat[mesh1.natural_of_gid], loewdin=True)
+    XN = scatter_to_ranks(rN, Xnat[meshN.natural_of_gid], loewdin=True)
+    O.chebyshev_filter_inplace(r1, X1, 6, 5.0, 50.0, -1.0)
+    O.chebyshev_filter_inplace(rN, XN, 6, 5.0, 50.0, -1.0)
+    ref_nat = np.empty_like(Xnat)
+    ref_nat[mesh1.natural_of_gid[:r1[0].M]] = X1[0][:r1[0].M]
+    for rp, x in zip(rN, XN):
+        nat = meshN.natural_of_gid[rp.ownedStart:rp.ownedEnd]
+        assert np.abs(x[:rp.M] - ref_nat[nat]).max() < 1e-12 * np.abs(ref_nat).max()
+    assert sum(rp.M for rp in rN) == mesh1.nNodes
+
+
+def test_solve_converges_and_orthonormalises():
+    mesh, ranks = make_problem(4, (3, 3, 3), 2.0, (True, True, True), nranks=2, potential=False)
+    N = 12
+    X = scatter_to_ranks(ranks, random_global(mesh, N, 0), zero_constrained=False)
+    lo, up = O.lanczos_bounds(ranks)
+    a0, blow = lo, 3.0
+    for _ in range(5):
+        ev, res = O.solve(ranks, X, N, 30, (a0, blow, up))
+        a0, blow = ev[0], ev[-1]
+    exact = 0.5 * (2 * np.pi / 6.0) ** 2
+    assert abs(ev[0]) < 1e-10 and np.abs(ev[1:7] - exact).max() < 1e-4
+    # known answer iv: X^T M X = I after the Rayleigh-Ritz step
+    S = 0
+    for rp, x in zip(ranks, X):
+        xl = x[:rp.M] * rp.sqrtMass[:rp.M, None]
+        S = S + xl.T @ xl
+    assert np.abs(S - np.eye(N)).max() < 1e-12
+    # CGS + RR gives the same Ritz values
+    X2 = scatter_to_ranks(ranks, random_global(mesh, N, 0), zero_constrained=False)
+    a0, blow = lo, 3.0
+    for _ in range(5):
+        ev2, _ = O.solve(ranks, X2, N, 30, (a0, blow, up), use_gep=False)
+        a0, blow = ev2[0], ev2[-1]
+    assert np.abs(ev2[:7] - ev[:7]).max() < 1e-9
+
+
+def test_c_oracle_matches_numpy_oracle():
+    from oracle.c_oracle import COracle
+
+    mesh, ranks = make_problem(3, (3, 3, 4), 1.2, (True, False, True), extra_constraints=hanging_like_constraints(4))
+    rp = ranks[0]
+    B = 16
+    co = COracle(rp, B)
+    X = scatter_to_ranks(ranks, random_global(mesh, B, 1), loewdin=True)
+    ref = [X[0].copy()]
+    O.chebyshev_filter_inplace(ranks, ref, 9, 5.0, 60.0, -1.0)
+    xc = X[0].copy()
+    co.cheb_filter(xc, 9, 5.0, 60.0, -1.0)
+    assert np.abs(xc[:rp.M] - ref[0][:rp.M]).max() < 1e-13 * np.abs(ref[0]).max()
+    # HX alone
+    src, dst = [X[0].copy()], [np.zeros_like(X[0])]
+    O.HX(ranks, src, dst, False, 1.0)
+    s2, d2 = X[0].copy(), np.zeros_like(X[0])
+    co.hx(s2, d2, False, 1.0)
+    assert np.abs(d2 - dst[0]).max() < 1e-13 * np.abs(dst[0]).max()
+
+
+def test_glibc_rand_restatement():
+    libc = ctypes.CDLL("libc.so.6")
+    for seed in (0, 1, 2, 7):
+        libc.srand(seed)
+        ref = [libc.rand() for _ in range(50)]
+        g = O.GlibcRand(seed)
+        assert [g.rand() for _ in range(50)] == ref
+
+
+def test_chebyshev_order_table():
+    assert [O.set_chebyshev_order(u) for u in (10, 500, 501, 1129, 9000, 600000)] == [24, 24, 30, 50, 77, 1250]
+
+
+def test_golden_fixture():
+    """tests/golden/chfsi_small.npz was written by tests/golden/make_golden.py from the oracle; it
+    freezes the oracle's own answers (the reference has no kernel-level golden vectors)."""
+    from tests.golden.make_golden import build_case
+
+    g = np.load(os.path.join(HERE, "golden", "chfsi_small.npz"))
+    mesh, ranks, X = build_case()
+    assert np.array_equal(g["index_map_rank1"], ranks[1].index_map(8))
+    assert np.array_equal(g["rowIdsLocal_rank1"], ranks[1].rowIdsLocal)
+    Y = [x.copy() for x in X]
+    O.chebyshev_filter_inplace(ranks, Y, 8, float(g["a"]), float(g["b"]), float(g["a0"]))
+    for r, (rp, y) in enumerate(zip(ranks, Y)):
+        assert np.abs(y[:rp.M] - g[f"filtered_rank{r}"]).max() < 1e-13
+    assert np.abs(O.xtx(ranks, X) - g["xtx"]).max() < 1e-12
