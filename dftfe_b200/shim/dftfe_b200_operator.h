@@ -1,0 +1,202 @@
+// Header-only C++ adapter over the C ABI (include/dftfe_b200.h) that keeps the
+// reference's method names, argument order and semantics for the ChFSI hot path,
+// so a DFT-FE build can route its device path through libdftfe_b200.so:
+//
+//   dftfe::operatorDFTDeviceClass::{HX, HXCheby, XtHX}          include/operatorDevice.h:43-420
+//   dftfe::chebyshevOrthogonalizedSubspaceIterationSolverDevice  include/chebyshevOrthogonalizedSubspaceIterationSolverDevice.h:48-124
+//   dftfe::linearAlgebraOperationsDevice::{chebyshevFilter, ...} include/linearAlgebraOperationsDevice.h:75-387
+//
+// The classes are templates over the vector / matrix types so that they compile
+// against DFT-FE's own distributedDeviceVec<double> (needs .begin()) and
+// dftfe::ScaLAPACKMatrix<double> (needs local_m/local_n/global_row/global_column/local_el)
+// without including deal.II here, and against the plain stand-ins used by this
+// repository's tests.  Arguments that only exist to carry library handles in the
+// reference (cublas handle, process grid, CCL wrapper, MPI communicators, FP32
+// scratch vector, projector-ket vector) are accepted and ignored: the context owns
+// its handles and scratch.  Errors surface as std::runtime_error (the reference
+// exit()s, include/DeviceExceptions.cu.h:21-47).
+#pragma once
+#include <cuda_runtime.h>
+
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/dftfe_b200.h"
+
+namespace dftfe_b200_shim {
+
+inline void check(int rc, const char *what) {
+  if (rc != 0) throw std::runtime_error(std::string(what) + ": " + dftfe_b200_last_error());
+}
+
+// Arrays DFT-FE already has at the end of kohnShamDFTOperatorDeviceClass::reinit
+// (src/dftOperator/kohnShamDFTOperatorDevice.cc:492-933) and computeMassVector (:938-1031).
+struct ReinitData {
+  dftfe_b200_problem_desc desc{};
+  const uint64_t *flattenedArrayCellLocalProcIndexIdMap = nullptr;  // nC*n, pre-multiplied by B (:583-596)
+  // constraintMatrixInfoDevice (utils/constraintMatrixInfoDevice.cc:446-542)
+  int64_t numConstraints = 0;
+  const uint32_t *rowIdsLocal = nullptr, *rowSizes = nullptr, *rowSizesAccumulated = nullptr,
+                 *columnIdsLocal = nullptr;
+  const double *columnValues = nullptr, *inhomogenities = nullptr;
+  const double *sqrtMassVec = nullptr, *invSqrtMassVec = nullptr;  // M+G each
+  // MPIPatternP2P (utils/MPIPatternP2P.t.cc)
+  int rank = 0, nranks = 1;
+  std::vector<int32_t> ghostProcIds, ghostLocalIndicesRanges, targetProcIds, numOwnedIndicesForTargetProcs;
+  const uint32_t *flattenedLocalTargetIndices = nullptr;
+};
+
+class operatorDFTDeviceClass {
+ public:
+  explicit operatorDFTDeviceClass(const ReinitData &d) : d_M(d.desc.n_owned), d_B(d.desc.cheby_block) {
+    check(dftfe_b200_create(&d.desc, &d_ctx), "dftfe_b200_create");
+    check(dftfe_b200_set_index_map(d_ctx, d.flattenedArrayCellLocalProcIndexIdMap), "set_index_map");
+    check(dftfe_b200_set_constraints(d_ctx, d.numConstraints, d.rowIdsLocal, d.rowSizes, d.rowSizesAccumulated,
+                                     d.columnIdsLocal, d.columnValues, d.inhomogenities),
+          "set_constraints");
+    check(dftfe_b200_set_mass(d_ctx, d.sqrtMassVec, d.invSqrtMassVec), "set_mass");
+    check(dftfe_b200_set_ghost_pattern(d_ctx, d.rank, d.nranks, (int32_t)d.ghostProcIds.size(), d.ghostProcIds.data(),
+                                       d.ghostLocalIndicesRanges.data(), (int32_t)d.targetProcIds.size(),
+                                       d.targetProcIds.data(), d.numOwnedIndicesForTargetProcs.data(),
+                                       d.flattenedLocalTargetIndices),
+          "set_ghost_pattern");
+  }
+  ~operatorDFTDeviceClass() { dftfe_b200_destroy(d_ctx); }
+  operatorDFTDeviceClass(const operatorDFTDeviceClass &) = delete;
+  operatorDFTDeviceClass &operator=(const operatorDFTDeviceClass &) = delete;
+
+  dftfe_b200_ctx *context() { return d_ctx; }
+  void setStream(cudaStream_t s) { check(dftfe_b200_set_stream(d_ctx, (void *)s), "set_stream"); }
+  // DeviceCCLWrapper::init equivalent: id produced by dftfe_b200_nccl_unique_id on rank 0 and MPI_Bcast by the caller
+  void initComm(const uint8_t id[128], int rank, int nranks) { check(dftfe_b200_comm_init(d_ctx, id, rank, nranks), "comm_init"); }
+
+  // computeHamiltonianMatricesAllkpt output for the active (k, spin): d_cellHamiltonianMatrixFlattenedDevice
+  void reinitkPointSpinIndex(const double *cellHamiltonianMatrixFlattenedDevice) {
+    check(dftfe_b200_set_cell_hamiltonian(d_ctx, cellHamiltonianMatrixFlattenedDevice), "set_cell_hamiltonian");
+  }
+
+  // kohnShamDFTOperatorDevice.cc:3765-3860
+  template <class Vec>
+  void HX(Vec &src, Vec & /*projectorKetTimesVector*/, const unsigned int /*localVectorSize*/,
+          const unsigned int numberComponents, const bool scaleFlag, const double scalar, Vec &dst,
+          const bool doUnscalingX = true, const bool onlyHPrimePartForFirstOrderDensityMatResponse = false) {
+    if (onlyHPrimePartForFirstOrderDensityMatResponse)
+      throw std::runtime_error("HX: onlyHPrime is outside the ChFSI hot path and not provided");
+    check(dftfe_b200_hx(d_ctx, src.begin(), dst.begin(), (int32_t)numberComponents, scaleFlag ? 1 : 0, scalar,
+                        doUnscalingX ? 1 : 0),
+          "HX");
+  }
+
+  // kohnShamDFTOperatorDevice.cc:3874-3997 (FP64; the compute/communication split flags are an
+  // implementation detail of the reference's 2-block overlap schedule and are rejected)
+  template <class Vec, class VecFP32>
+  void HXCheby(Vec &X, VecFP32 & /*XTempFP32*/, Vec & /*projectorKetTimesVector*/, const unsigned int /*localVectorSize*/,
+               const unsigned int numberComponents, Vec &Y, bool mixPrecFlag = false,
+               bool returnBeforeCompressSkipUpdateSkipNonLocal = false,
+               bool returnBeforeCompressSkipUpdateSkipLocal = false) {
+    if (mixPrecFlag || returnBeforeCompressSkipUpdateSkipNonLocal || returnBeforeCompressSkipUpdateSkipLocal)
+      throw std::runtime_error("HXCheby: mixed precision / split-phase flags are not provided (FP64, fused)");
+    check(dftfe_b200_hx_cheby(d_ctx, X.begin(), Y.begin(), (int32_t)numberComponents), "HXCheby");
+  }
+
+  // kohnShamDFTOperatorDevice.cc:4001-4157.  projHamPar receives the lower triangle exactly as the
+  // reference fills it (:4128-4145); Matrix needs local_m(), local_n(), global_row(i), global_column(j), local_el(i,j).
+  template <class Vec, class Matrix, class... Ignored>
+  void XtHX(const double *X, Vec & /*Xb*/, Vec & /*HXb*/, Vec & /*projectorKetTimesVector*/, const unsigned int /*M*/,
+            const unsigned int N, Matrix &projHamPar, Ignored &&...) {
+    std::vector<double> host((size_t)N * N);
+    double *dev = nullptr;
+    if (cudaMalloc(&dev, host.size() * sizeof(double)) != cudaSuccess) throw std::runtime_error("XtHX: cudaMalloc");
+    int rc = dftfe_b200_xthx(d_ctx, X, (int32_t)N, dev);
+    if (rc == 0) rc = dftfe_b200_sync(d_ctx);
+    cudaMemcpy(host.data(), dev, host.size() * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(dev);
+    check(rc, "XtHX");
+    fillLowerTriangle(host, N, projHamPar);
+  }
+
+  // fillParallelOverlapMatScalapack (linearAlgebraOperationsDevice.cc:3078-3240)
+  template <class Matrix>
+  void fillParallelOverlapMat(const double *X, const unsigned int N, Matrix &overlapMatPar) {
+    std::vector<double> host((size_t)N * N);
+    double *dev = nullptr;
+    if (cudaMalloc(&dev, host.size() * sizeof(double)) != cudaSuccess) throw std::runtime_error("XtX: cudaMalloc");
+    int rc = dftfe_b200_xtx(d_ctx, X, (int32_t)N, dev);
+    if (rc == 0) rc = dftfe_b200_sync(d_ctx);
+    cudaMemcpy(host.data(), dev, host.size() * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(dev);
+    check(rc, "XtX");
+    fillLowerTriangle(host, N, overlapMatPar);
+  }
+
+  // linearAlgebraOperationsDevice::chebyshevFilter (linearAlgebraOperationsDevice.cc:531-727)
+  template <class Vec>
+  void chebyshevFilter(Vec &XArray, Vec &YArray, const unsigned int numberVectors, const unsigned int m, const double a,
+                       const double b, const double a0) {
+    check(dftfe_b200_cheb_filter(d_ctx, XArray.begin(), YArray.begin(), (int32_t)numberVectors, (int32_t)m, a, b, a0),
+          "chebyshevFilter");
+  }
+
+ private:
+  template <class Matrix>
+  static void fillLowerTriangle(const std::vector<double> &full, unsigned int N, Matrix &mat) {
+    for (unsigned int jl = 0; jl < mat.local_n(); ++jl) {
+      const unsigned int j = mat.global_column(jl);
+      for (unsigned int il = 0; il < mat.local_m(); ++il) {
+        const unsigned int i = mat.global_row(il);
+        if (i >= j) mat.local_el(il, jl) = full[(size_t)i + (size_t)j * N];
+      }
+    }
+  }
+  dftfe_b200_ctx *d_ctx = nullptr;
+  int64_t d_M;
+  int d_B;
+};
+
+// chebyshevOrthogonalizedSubspaceIterationSolverDevice
+// (src/solvers/eigenSolvers/chebyshevOrthogonalizedSubspaceIterationSolverDevice.cc:95-736)
+class chebyshevOrthogonalizedSubspaceIterationSolverDevice {
+ public:
+  chebyshevOrthogonalizedSubspaceIterationSolverDevice(double lowerBoundWantedSpectrum, double lowerBoundUnWantedSpectrum,
+                                                       double upperBoundUnWantedSpectrum,
+                                                       const dftfe_b200_solve_params &dftParams)
+      : d_lowerWanted(lowerBoundWantedSpectrum), d_lowerUnwanted(lowerBoundUnWantedSpectrum),
+        d_upperUnwanted(upperBoundUnWantedSpectrum), d_params(dftParams) {}
+
+  void reinitSpectrumBounds(double lowerBoundWantedSpectrum, double lowerBoundUnWantedSpectrum) {
+    d_lowerWanted = lowerBoundWantedSpectrum;
+    d_lowerUnwanted = lowerBoundUnWantedSpectrum;
+  }
+
+  // solve(operatorMatrix, BLASWrapperPtr, elpaScala, eigenVectorsFlattenedDevice, eigenVectorsRotFracDensityFlattenedDevice,
+  //       flattenedSize, totalNumberWaveFunctions, eigenValues, residuals, devicecclMpiCommDomain, interBandGroupComm,
+  //       isFirstFilteringCall, computeResidual, useMixedPrecOverall, isFirstScf) -> upper bound  (:155-736)
+  double solve(operatorDFTDeviceClass &operatorMatrix, double *eigenVectorsFlattenedDevice,
+               double * /*eigenVectorsRotFracDensityFlattenedDevice*/, const unsigned int flattenedSize,
+               const unsigned int totalNumberWaveFunctions, std::vector<double> &eigenValues,
+               std::vector<double> &residuals, const bool isFirstFilteringCall, const bool computeResidual,
+               const bool useMixedPrecOverall = false, const bool isFirstScf = false) {
+    (void)flattenedSize;
+    if (useMixedPrecOverall) throw std::runtime_error("solve: mixed precision is not provided yet (FP64 only)");
+    if (eigenValues.size() != totalNumberWaveFunctions)
+      throw std::runtime_error("solve: spectrum splitting (eigenValues.size() != N) is not provided yet");
+    dftfe_b200_solve_params p = d_params;
+    p.is_first_filtering_call = isFirstFilteringCall ? 1 : 0;
+    p.compute_residual = computeResidual ? 1 : 0;
+    p.is_first_scf = isFirstScf ? 1 : 0;
+    if (!isFirstFilteringCall)
+      check(dftfe_b200_reinit_spectrum_bounds(operatorMatrix.context(), d_lowerWanted, d_lowerUnwanted), "reinitSpectrumBounds");
+    residuals.resize(totalNumberWaveFunctions);
+    check(dftfe_b200_solve(operatorMatrix.context(), eigenVectorsFlattenedDevice, (int32_t)totalNumberWaveFunctions, &p,
+                           eigenValues.data(), residuals.data(), &d_upperUnwanted),
+          "solve");
+    return d_upperUnwanted;
+  }
+
+ private:
+  double d_lowerWanted, d_lowerUnwanted, d_upperUnwanted;
+  dftfe_b200_solve_params d_params;
+};
+
+}  // namespace dftfe_b200_shim

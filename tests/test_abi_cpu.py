@@ -90,3 +90,18 @@ def test_c_structs_match_header_layout(capi):
     # int32,int32,int64 x4,int32,int32 and 10 x int32 + double
     assert C.sizeof(capi.ProblemDesc) == 48
     assert C.sizeof(capi.SolveParams) == 48
+
+
+def test_cpp_adapter_compiles_and_links(capi, tmp_path):
+    """dftfe_b200/shim: the C++ classes with the reference's method names build against
+    stand-in vector/matrix types and link with the C-ABI library."""
+    import subprocess
+
+    exe = tmp_path / "shim_check"
+    libdir = os.path.dirname(str(capi.lib_path()))
+    cmd = ["g++", "-std=c++17", "-I/usr/local/cuda/include", os.path.join(ROOT, "tests", "shim_compile_check.cc"),
+           "-o", str(exe), f"-L{libdir}", "-ldftfe_b200", "-L/usr/local/cuda/lib64", "-lcudart",
+           f"-Wl,-rpath,{libdir}", "-Wl,-rpath,/usr/local/cuda/lib64"]
+    subprocess.check_call(cmd)
+    out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
+    assert "dftfe_b200" in out
