@@ -209,7 +209,7 @@ def main_ours(args):
     from dftfe_b200 import build, capi
 
     if rank == 0:
-        build.build()
+        build.build() if not os.environ.get("DFTFE_B200_LIB") else None
     if world > 1:
         dist.barrier()
 

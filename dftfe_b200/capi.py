@@ -18,7 +18,7 @@ from typing import Optional, Sequence
 
 import numpy as np
 
-_LIB_PATH = Path(__file__).resolve().parent / "lib" / "libdftfe_b200.so"
+_LIB_PATH = Path(os.environ.get("DFTFE_B200_LIB") or (Path(__file__).resolve().parent / "lib" / "libdftfe_b200.so"))
 _lib = None
 
 

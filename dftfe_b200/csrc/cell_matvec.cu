@@ -36,6 +36,21 @@ namespace {
 constexpr int BT = 32;       // wavefunction columns per CTA tile
 constexpr int NT = BT / 8;   // n8 tiles per warp
 constexpr int LDS = BT + 4;  // shared-memory row pitch in doubles ( = 4 mod 16 )
+// row word of the flagged index map: bits 0..29 local row, bit 30 = live (owned and
+// unconstrained), bit 31 = first touch (this cell is the first, in colour order, to write the row)
+constexpr uint32_t ROW_MASK = 0x3fffffffu, LIVE_BIT = 0x40000000u, FIRST_BIT = 0x80000000u;
+
+// first touch: dst = ca*src + cb*dst + s*acc ; later touches: dst += s*acc
+__device__ __forceinline__ void epilogue_coeffs(uint32_t word, const EpilogueParams &ep, double &ca, double &cb) {
+  const uint32_t r = word & ROW_MASK;
+  const bool live = (word & LIVE_BIT) != 0 || ep.allLive;
+  ca = 0.0;
+  cb = 1.0;
+  if (word & FIRST_BIT) {
+    ca = live ? ep.a * (ep.rowA ? __ldg(ep.rowA + r) : 1.0) : 0.0;
+    cb = live ? ep.b * (ep.rowB ? __ldg(ep.rowB + r) : 1.0) : 0.0;
+  }
+}
 
 template <int NODES>
 struct CellCfg {
@@ -79,7 +94,7 @@ __global__ void retile_H_kernel(const double *__restrict__ H, double *__restrict
     double v = 0.0;
     if (i < NODES && k < NODES) {
       v = H[cell * (int64_t)NODES * NODES + (int64_t)i * NODES + k];
-      const uint32_t ri = cellRows[cell * NODES + i] & 0x7fffffffu, rk = cellRows[cell * NODES + k] & 0x7fffffffu;
+      const uint32_t ri = cellRows[cell * NODES + i] & ROW_MASK, rk = cellRows[cell * NODES + k] & ROW_MASK;
       v = rowOut[ri] * v * rowIn[rk];
     }
     Ht[idx] = v;
@@ -111,7 +126,7 @@ cell_matvec_kernel(const double *__restrict__ Ht, const uint32_t *__restrict__ c
   for (int k = warp; k < C::KPAD; k += C::WARPS) {
     double v = 0.0;
     if (k < NODES && colOk) {
-      const uint32_t r = rowsS[k] & 0x7fffffffu;
+      const uint32_t r = rowsS[k] & ROW_MASK;
       v = __ldg(src + (size_t)r * ldx + col0 + lane);
       if (ep.rowIn) v *= __ldg(ep.rowIn + r);
     }
@@ -179,14 +194,10 @@ cell_matvec_kernel(const double *__restrict__ Ht, const uint32_t *__restrict__ c
     const int i = mt * 8 + (lane >> 2);
     if (mt < C::MT && i < NODES) {
       const uint32_t fr = rowsS[i];
-      const uint32_t r = fr & 0x7fffffffu;
-      const bool first = (fr >> 31) != 0;
+      const uint32_t r = fr & ROW_MASK;
       const double so = ep.s * (ep.rowOut ? __ldg(ep.rowOut + r) : 1.0);
-      double ca = 0.0, cb = 1.0;
-      if (first) {
-        ca = ep.a * (ep.rowA ? __ldg(ep.rowA + r) : 1.0);
-        cb = ep.b * (ep.rowB ? __ldg(ep.rowB + r) : 1.0);
-      }
+      double ca, cb;
+      epilogue_coeffs(fr, ep, ca, cb);
       double *drow = dst + (size_t)r * ldx + col0 + (lane & 3) * 2;
       const double *srow = src + (size_t)r * ldx + col0 + (lane & 3) * 2;
       if (vec2) {
@@ -273,8 +284,133 @@ struct PersistCfg {
   static constexpr int THREADS = (MMA_WARPS + 1) * 32;  // + one producer warp
   static constexpr size_t XBUF = (size_t)C::KPAD * LDS;  // doubles per buffer
   static constexpr size_t SMEM = 2 * XBUF * sizeof(double) + 2 * NODES * sizeof(uint32_t) + 4 * sizeof(uint64_t);
-  static constexpr int APF = 4;  // A-fragment prefetch depth in k-steps
+#ifndef DB_DIAG
+#define DB_DIAG 0
+#endif
+#ifndef DB_APF
+#define DB_APF 4
+#endif
+  static constexpr int APF = DB_APF;  // A-fragment prefetch depth in k-steps
 };
+
+
+template <int NODES, int NTILE>
+__device__ __forceinline__ void mma_warp_items(const double *__restrict__ Ht, const int32_t *__restrict__ cells,
+                                               int nItems, const double *__restrict__ src,
+                                               double *__restrict__ dst, int ldx, int nColTiles,
+                                               const EpilogueParams &ep, const double *Xs, const uint32_t *rowsS,
+                                               uint64_t *full, uint64_t *empty, int warp, int lane) {
+  using C = CellCfg<NODES>;
+  using P = PersistCfg<NODES>;
+  const double *xb0 = Xs + (lane & 3) * LDS + (lane >> 2);
+  // A prefetch ring; primed for the first item here, re-primed for the next item before each epilogue
+  double a[P::APF][NTILE];
+  auto prime = [&](int item) {
+    const int cell = cells[item / nColTiles];
+    const double *Hc = Ht + (size_t)cell * C::HT_PER_CELL + lane;
+#pragma unroll
+    for (int s = 0; s < P::APF; ++s)
+#pragma unroll
+      for (int t = 0; t < NTILE; ++t)
+        a[s][t] = (s < C::KS) ? __ldg(Hc + (size_t)(s * C::MT + warp + t * C::WARPS) * 32) : 0.0;
+  };
+  if ((int)blockIdx.x < nItems) prime(blockIdx.x);
+  int it = 0;
+  for (int item = blockIdx.x; item < nItems; item += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const uint32_t ph = (it >> 1) & 1;
+    const int cell = cells[item / nColTiles];
+    const int col0 = (item % nColTiles) * BT;
+    const double *Hc = Ht + (size_t)cell * C::HT_PER_CELL + lane;
+    const double *xb = xb0 + buf * P::XBUF;
+
+    double acc[NTILE][NT][2];
+#pragma unroll
+    for (int t = 0; t < NTILE; ++t)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) acc[t][nt][0] = acc[t][nt][1] = 0.0;
+
+    mbar_wait(&full[buf], ph);
+
+    int ks = 0;
+    for (; ks + P::APF <= C::KS; ks += P::APF) {
+#pragma unroll
+      for (int s = 0; s < P::APF; ++s) {
+        double b[NT];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) b[nt] = xb[((ks + s) * 4) * LDS + nt * 8];
+#pragma unroll
+        for (int t = 0; t < NTILE; ++t)
+#pragma unroll
+          for (int nt = 0; nt < NT; ++nt) dmma884(acc[t][nt][0], acc[t][nt][1], a[s][t], b[nt]);
+#if DB_DIAG != 1 && DB_DIAG != 4
+        if (ks + s + P::APF < C::KS) {
+#pragma unroll
+          for (int t = 0; t < NTILE; ++t)
+            a[s][t] = __ldg(Hc + (size_t)((ks + s + P::APF) * C::MT + warp + t * C::WARPS) * 32);
+        }
+#endif
+      }
+    }
+#pragma unroll
+    for (int s = 0; s < C::KS % P::APF; ++s) {
+      double b[NT];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) b[nt] = xb[((ks + s) * 4) * LDS + nt * 8];
+#pragma unroll
+      for (int t = 0; t < NTILE; ++t)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) dmma884(acc[t][nt][0], acc[t][nt][1], a[s][t], b[nt]);
+    }
+
+    // rows of this warp's tiles, then release the buffer to the producer
+    uint32_t fr[NTILE];
+#pragma unroll
+    for (int t = 0; t < NTILE; ++t) {
+      const int i = (warp + t * C::WARPS) * 8 + (lane >> 2);
+      fr[t] = (i < NODES) ? rowsS[buf * NODES + i] : 0u;
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[buf]);
+
+    // next item's first A fragments fly while this item's epilogue runs
+    if (item + (int)gridDim.x < nItems) prime(item + gridDim.x);
+
+    // ---- epilogue (full tiles, even ldx: guaranteed by the launcher)
+#pragma unroll
+    for (int t = 0; t < NTILE; ++t) {
+      const int i = (warp + t * C::WARPS) * 8 + (lane >> 2);
+      if (i < NODES) {
+        const uint32_t r = fr[t] & ROW_MASK;
+        const double so = ep.s * (ep.rowOut ? __ldg(ep.rowOut + r) : 1.0);
+        double ca, cb;
+        epilogue_coeffs(fr[t], ep, ca, cb);
+        double *drow = dst + (size_t)r * ldx + col0 + (lane & 3) * 2;
+        const double *srow = src + (size_t)r * ldx + col0 + (lane & 3) * 2;
+#if DB_DIAG == 2 || DB_DIAG == 4
+        double sum = 0.0;
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) sum += acc[t][nt][0] + acc[t][nt][1];
+        if (sum == 1.2345e300) drow[0] = so * sum + ca + cb + srow[0];
+#else
+        double2 d[NT], sv[NT];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          d[nt] = (cb != 0.0) ? *reinterpret_cast<const double2 *>(drow + nt * 8) : make_double2(0.0, 0.0);
+          sv[nt] = (ca != 0.0) ? *reinterpret_cast<const double2 *>(srow + nt * 8) : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          double2 o;
+          o.x = so * acc[t][nt][0] + ca * sv[nt].x + cb * d[nt].x;
+          o.y = so * acc[t][nt][1] + ca * sv[nt].y + cb * d[nt].y;
+          *reinterpret_cast<double2 *>(drow + nt * 8) = o;
+        }
+#endif
+      }
+    }
+  }
+}
 
 template <int NODES>
 __global__ void __launch_bounds__(PersistCfg<NODES>::THREADS, 1)
@@ -291,8 +427,11 @@ cell_matvec_persistent_kernel(const double *__restrict__ Ht, const uint32_t *__r
   uint64_t *full = bars, *empty = bars + 2;
 
   const int tid = threadIdx.x;
-  const int warp = tid >> 5;
   const int lane = tid & 31;
+  // physical warp 0 is the producer; MMA warp ids 0..11 sit on physical warps 1..12, which puts the
+  // three lightest MMA warps (ids 3, 7, 11: 4+3+3 row tiles) on the producer's scheduler (SMSP 0)
+  const int pwarp = tid >> 5;
+  const int warp = pwarp - 1;
 
   // zero both tiles once (pad rows k >= NODES and pad columns stay zero forever)
   for (int i = tid; i < (int)(2 * P::XBUF); i += P::THREADS) Xs[i] = 0.0;
@@ -307,135 +446,55 @@ cell_matvec_persistent_kernel(const double *__restrict__ Ht, const uint32_t *__r
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   __syncthreads();
 
-  if (warp == P::MMA_WARPS) {
+  if (pwarp == 0) {
     // ===== producer warp: gather rows of the next item through the index map =====
     int it = 0;
     for (int item = blockIdx.x; item < nItems; item += gridDim.x, ++it) {
       const int buf = it & 1;
       const uint32_t ph = (it >> 1) & 1;
-      mbar_wait(&empty[buf], ph ^ 1);
       const int cell = cells[item / nColTiles];
       const int col0 = (item % nColTiles) * BT;
+      const uint32_t *cr = cellRows + (size_t)cell * NODES;
+      // row words first (global latency overlaps the wait for the buffer)
+      uint32_t myRows[(NODES + 31) / 32];
+#pragma unroll
+      for (int j = 0; j < (NODES + 31) / 32; ++j) {
+        const int k = lane + 32 * j;
+        myRows[j] = (k < NODES) ? __ldg(cr + k) : 0u;
+      }
+      mbar_wait(&empty[buf], ph ^ 1);
       uint32_t *rs = rowsS + buf * NODES;
       double *xs = Xs + buf * P::XBUF;
-      const uint32_t *cr = cellRows + (size_t)cell * NODES;
-      for (int i = lane; i < NODES; i += 32) rs[i] = cr[i];
+#pragma unroll
+      for (int j = 0; j < (NODES + 31) / 32; ++j) {
+        const int k = lane + 32 * j;
+        if (k < NODES) rs[k] = myRows[j];
+      }
       __syncwarp();
+#if DB_DIAG == 3 || DB_DIAG == 4
+      if (lane == 0) mbar_arrive(&full[buf]);
+      continue;
+#endif
       if (lane == 0) mbar_arrive_expect_tx(&full[buf], (uint32_t)(NODES * BT * sizeof(double)));
       __syncwarp();
-      for (int k = lane; k < NODES; k += 32) {
-        const uint32_t r = rs[k] & 0x7fffffffu;
-        tma_bulk_g2s(xs + k * LDS, src + (size_t)r * ldx + col0, BT * sizeof(double), &full[buf]);
+#pragma unroll
+      for (int j = 0; j < (NODES + 31) / 32; ++j) {
+        const int k = lane + 32 * j;
+        if (k < NODES)
+          tma_bulk_g2s(xs + k * LDS, src + (size_t)(myRows[j] & ROW_MASK) * ldx + col0, BT * sizeof(double),
+                       &full[buf]);
       }
     }
   } else {
-    // ===== MMA warps =====
-    const double *xb0 = Xs + (lane & 3) * LDS + (lane >> 2);
-    int it = 0;
-    for (int item = blockIdx.x; item < nItems; item += gridDim.x, ++it) {
-      const int buf = it & 1;
-      const uint32_t ph = (it >> 1) & 1;
-      const int cell = cells[item / nColTiles];
-      const int col0 = (item % nColTiles) * BT;
-      const double *Hc = Ht + (size_t)cell * C::HT_PER_CELL + lane;
-      const double *xb = xb0 + buf * P::XBUF;
-
-      double acc[C::TPW][NT][2];
-#pragma unroll
-      for (int t = 0; t < C::TPW; ++t)
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) acc[t][nt][0] = acc[t][nt][1] = 0.0;
-
-      // A prefetch ring (does not depend on the gathered tile: issue before waiting)
-      double a[P::APF][C::TPW];
-#pragma unroll
-      for (int s = 0; s < P::APF; ++s)
-#pragma unroll
-        for (int t = 0; t < C::TPW; ++t) {
-          const int mt = warp + t * C::WARPS;
-          a[s][t] = (mt < C::MT && s < C::KS) ? __ldg(Hc + (size_t)(s * C::MT + mt) * 32) : 0.0;
-        }
-
-      mbar_wait(&full[buf], ph);
-
-      int ks = 0;
-      for (; ks + P::APF <= C::KS; ks += P::APF) {
-#pragma unroll
-        for (int s = 0; s < P::APF; ++s) {
-          double b[NT];
-#pragma unroll
-          for (int nt = 0; nt < NT; ++nt) b[nt] = xb[((ks + s) * 4) * LDS + nt * 8];
-#pragma unroll
-          for (int t = 0; t < C::TPW; ++t) {
-            if (warp + t * C::WARPS < C::MT) {
-#pragma unroll
-              for (int nt = 0; nt < NT; ++nt) dmma884(acc[t][nt][0], acc[t][nt][1], a[s][t], b[nt]);
-            }
-          }
-#pragma unroll
-          for (int t = 0; t < C::TPW; ++t) {
-            const int mt = warp + t * C::WARPS;
-            if (mt < C::MT && ks + s + P::APF < C::KS)
-              a[s][t] = __ldg(Hc + (size_t)((ks + s + P::APF) * C::MT + mt) * 32);
-          }
-        }
-      }
-#pragma unroll
-      for (int s = 0; s < C::KS % P::APF; ++s) {
-        double b[NT];
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) b[nt] = xb[((ks + s) * 4) * LDS + nt * 8];
-#pragma unroll
-        for (int t = 0; t < C::TPW; ++t) {
-          if (warp + t * C::WARPS < C::MT) {
-#pragma unroll
-            for (int nt = 0; nt < NT; ++nt) dmma884(acc[t][nt][0], acc[t][nt][1], a[s][t], b[nt]);
-          }
-        }
-      }
-
-      // rows of this warp's tiles, then release the buffer to the producer
-      uint32_t fr[C::TPW];
-#pragma unroll
-      for (int t = 0; t < C::TPW; ++t) {
-        const int i = (warp + t * C::WARPS) * 8 + (lane >> 2);
-        fr[t] = (i < NODES) ? rowsS[buf * NODES + i] : 0u;
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&empty[buf]);
-
-      // ---- epilogue (full tiles, even ldx: guaranteed by the launcher)
-#pragma unroll
-      for (int t = 0; t < C::TPW; ++t) {
-        const int mt = warp + t * C::WARPS;
-        const int i = mt * 8 + (lane >> 2);
-        if (mt < C::MT && i < NODES) {
-          const uint32_t r = fr[t] & 0x7fffffffu;
-          const bool first = (fr[t] >> 31) != 0;
-          const double so = ep.s * (ep.rowOut ? __ldg(ep.rowOut + r) : 1.0);
-          double ca = 0.0, cb = 1.0;
-          if (first) {
-            ca = ep.a * (ep.rowA ? __ldg(ep.rowA + r) : 1.0);
-            cb = ep.b * (ep.rowB ? __ldg(ep.rowB + r) : 1.0);
-          }
-          double *drow = dst + (size_t)r * ldx + col0 + (lane & 3) * 2;
-          const double *srow = src + (size_t)r * ldx + col0 + (lane & 3) * 2;
-          double2 d[NT], sv[NT];
-#pragma unroll
-          for (int nt = 0; nt < NT; ++nt) {
-            d[nt] = (cb != 0.0) ? *reinterpret_cast<const double2 *>(drow + nt * 8) : make_double2(0.0, 0.0);
-            sv[nt] = (ca != 0.0) ? *reinterpret_cast<const double2 *>(srow + nt * 8) : make_double2(0.0, 0.0);
-          }
-#pragma unroll
-          for (int nt = 0; nt < NT; ++nt) {
-            double2 o;
-            o.x = so * acc[t][nt][0] + ca * sv[nt].x + cb * d[nt].x;
-            o.y = so * acc[t][nt][1] + ca * sv[nt].y + cb * d[nt].y;
-            *reinterpret_cast<double2 *>(drow + nt * 8) = o;
-          }
-        }
-      }
-    }
+    // ===== MMA warps: the row-tile count (TPW or TPW-1) is a compile-time constant per branch,
+    // because a predicated-off DMMA still occupies its tensor-pipe slot =====
+    constexpr int FULL_WARPS = C::MT - (C::TPW - 1) * C::WARPS;  // warps that own TPW tiles
+    if (warp < FULL_WARPS)
+      mma_warp_items<NODES, C::TPW>(Ht, cells, nItems, src, dst, ldx, nColTiles, ep, Xs, rowsS, full, empty, warp,
+                                    lane);
+    else if (C::TPW > 1)
+      mma_warp_items<NODES, (C::TPW > 1 ? C::TPW - 1 : 1)>(Ht, cells, nItems, src, dst, ldx, nColTiles, ep, Xs, rowsS,
+                                                          full, empty, warp, lane);
   }
 }
 
@@ -446,10 +505,11 @@ __global__ void orphan_first_touch_kernel(const uint32_t *__restrict__ rows, int
   const int64_t total = nRows * ncols;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
-    const uint32_t r = rows[idx / ncols];
+    const uint32_t w = rows[idx / ncols] | FIRST_BIT;
+    const uint32_t r = w & ROW_MASK;
     const int col = idx % ncols;
-    const double ca = ep.a * (ep.rowA ? ep.rowA[r] : 1.0);
-    const double cb = ep.b * (ep.rowB ? ep.rowB[r] : 1.0);
+    double ca, cb;
+    epilogue_coeffs(w, ep, ca, cb);
     double o = 0.0;
     if (ca != 0.0) o += ca * src[(size_t)r * ldx + col];
     if (cb != 0.0) o += cb * dst[(size_t)r * ldx + col];

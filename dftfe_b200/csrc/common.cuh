@@ -140,8 +140,9 @@ struct EpilogueParams {
   double s = 1.0;
   const double *rowIn = nullptr;   // gather scale per local row (nullptr -> 1)
   const double *rowOut = nullptr;  // output scale per local row (nullptr -> 1)
-  const double *rowA = nullptr;    // multiplies a*src on first touch (nullptr -> 1)
-  const double *rowB = nullptr;    // multiplies b*dst on first touch (nullptr -> 1)
+  const double *rowA = nullptr;    // extra factor on a*src at first touch (nullptr -> 1)
+  const double *rowB = nullptr;    // extra factor on b*dst at first touch (nullptr -> 1)
+  int allLive = 0;                 // 1: ignore the live bit (bare dst += H src on every row)
 };
 
 }  // namespace dftfe_b200
@@ -165,7 +166,9 @@ struct dftfe_b200_ctx {
   std::vector<int32_t> cellColour_h;     // nC
   int nColours = 0;
   std::vector<int32_t> colourStart_h;    // nColours+1
-  dftfe_b200::DevBuf<uint32_t> cellRowsFlagged;  // nC*n: bit31 = first touch, bits 0..30 = row
+  std::vector<uint32_t> firstTouch_h;            // nC*n 0/1
+  std::vector<uint32_t> orphanRows_h;
+  dftfe_b200::DevBuf<uint32_t> cellRowsFlagged;  // nC*n: bit31 = first touch, bit30 = live, bits 0..29 = row
   dftfe_b200::DevBuf<int32_t> colourCells;       // nC cell ids grouped by colour
   dftfe_b200::DevBuf<uint32_t> orphanRows;       // rows no owned cell touches
   int64_t nOrphan = 0;

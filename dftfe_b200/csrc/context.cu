@@ -20,6 +20,25 @@ void set_error(const char *fmt, ...) {
 int loopback_join(dftfe_b200_ctx *ctx, int group_id, int rank, int nranks);
 void loopback_forget(dftfe_b200_ctx *ctx);
 
+// row words of the flagged index map: row | live<<30 | first<<31 (see cell_matvec.cu)
+static int rebuild_row_words(dftfe_b200_ctx *ctx) {
+  if (!ctx->have_map) return 0;
+  const int64_t R = ctx->M + ctx->G;
+  std::vector<char> live(R, 0);
+  for (int64_t r = 0; r < ctx->M; ++r) live[r] = 1;
+  for (uint32_t r : ctx->conRows_h) live[r] = 0;
+  std::vector<uint32_t> words(ctx->cellRows_h.size());
+  for (size_t k = 0; k < words.size(); ++k) {
+    const uint32_t r = ctx->cellRows_h[k];
+    words[k] = r | (live[r] ? 0x40000000u : 0u) | (ctx->firstTouch_h[k] ? 0x80000000u : 0u);
+  }
+  std::vector<uint32_t> orph(ctx->orphanRows_h.size());
+  for (size_t k = 0; k < orph.size(); ++k) orph[k] = ctx->orphanRows_h[k] | (live[ctx->orphanRows_h[k]] ? 0x40000000u : 0u);
+  DB_TRY(ctx->cellRowsFlagged.upload(words.data(), words.size(), ctx->stream));
+  DB_TRY(ctx->orphanRows.upload(orph.data(), orph.size(), ctx->stream));
+  return 0;
+}
+
 // derived per-row scale vectors (see solver.cu: fused_apply_impl)
 static int rebuild_row_vectors(dftfe_b200_ctx *ctx, const double *sqrtM_h, const double *invSqrtM_h) {
   const int64_t R = ctx->M + ctx->G;
@@ -72,7 +91,7 @@ int dftfe_b200_create(const dftfe_b200_problem_desc *desc, dftfe_b200_ctx **out)
   DB_CHECK(desc && out, "create: null argument");
   DB_CHECK(desc->n_cells >= 0 && desc->n_owned >= 0 && desc->n_ghost >= 0, "create: negative size");
   DB_CHECK(desc->cheby_block >= 1, "create: cheby_block must be >= 1");
-  DB_CHECK((desc->n_owned + desc->n_ghost) < (int64_t)0x7fffffff, "create: more than 2^31-1 local rows");
+  DB_CHECK((desc->n_owned + desc->n_ghost) < (int64_t)0x3fffffff, "create: more than 2^30-1 local rows");
   if (!cell_kernel_supported(desc->nodes_per_cell)) {
     set_error("create: no sm_100a cell kernel for %d nodes per cell (supported FE orders 1..7)",
               desc->nodes_per_cell);
@@ -233,7 +252,7 @@ int dftfe_b200_set_index_map(dftfe_b200_ctx *ctx, const uint64_t *map_h) {
     for (int64_t c = 0; c < nC; ++c) colourCells[fill[ctx->cellColour_h[c]]++] = (int32_t)c;
   }
   // first-touch flags in colour processing order
-  std::vector<uint32_t> flagged(ctx->cellRows_h);
+  ctx->firstTouch_h.assign(total, 0);
   std::vector<char> touched(R, 0);
   for (int64_t q = 0; q < nC; ++q) {
     const int64_t c = colourCells[q];
@@ -241,19 +260,17 @@ int dftfe_b200_set_index_map(dftfe_b200_ctx *ctx, const uint64_t *map_h) {
       const uint32_t r = ctx->cellRows_h[c * n + i];
       if (!touched[r]) {
         touched[r] = 1;
-        flagged[c * n + i] |= 0x80000000u;
+        ctx->firstTouch_h[c * n + i] = 1;
       }
     }
   }
-  std::vector<uint32_t> orphans;
+  ctx->orphanRows_h.clear();
   for (int64_t r = 0; r < R; ++r)
-    if (!touched[r]) orphans.push_back((uint32_t)r);
-  ctx->nOrphan = (int64_t)orphans.size();
-  DB_TRY(ctx->cellRowsFlagged.upload(flagged.data(), flagged.size(), ctx->stream));
+    if (!touched[r]) ctx->orphanRows_h.push_back((uint32_t)r);
+  ctx->nOrphan = (int64_t)ctx->orphanRows_h.size();
   DB_TRY(ctx->colourCells.upload(colourCells.data(), colourCells.size(), ctx->stream));
-  DB_TRY(ctx->orphanRows.upload(orphans.data(), orphans.size(), ctx->stream));
   ctx->have_map = true;
-  return 0;
+  return rebuild_row_words(ctx);
 }
 
 int dftfe_b200_set_constraints(dftfe_b200_ctx *ctx, int64_t nCon, const uint32_t *rows_h, const uint32_t *sizes_h,
@@ -312,7 +329,8 @@ int dftfe_b200_set_constraints(dftfe_b200_ctx *ctx, int64_t nCon, const uint32_t
   DB_TRY(ctx->masterSlaves.upload(slaves.data(), slaves.size(), ctx->stream));
   DB_TRY(ctx->masterVals.upload(mvals.data(), mvals.size(), ctx->stream));
   if (ctx->have_mass) DB_TRY(rebuild_row_vectors(ctx, ctx->sqrtM_h.data(), ctx->invSqrtM_h.data()));
-  return 0;
+  ctx->have_H = false;
+  return rebuild_row_words(ctx);
 }
 
 int dftfe_b200_set_mass(dftfe_b200_ctx *ctx, const double *sqrt_mass_h, const double *inv_sqrt_mass_h) {

@@ -28,7 +28,7 @@ static int fused_apply_impl(dftfe_b200_ctx *ctx, double *src, double *dst, int n
   // rowIn / rowOut (M^-1/2 on free rows) are folded into the tiled cell matrices
   ep.rowIn = nullptr;
   ep.rowOut = nullptr;
-  ep.rowA = ctx->rowLive.p;
+  ep.rowA = nullptr;  // liveness travels in the row words of the index map
   ep.rowB = rowB;
   DB_TRY(launch_cell_matvec(ctx, src, dst, ncols, ldx, ep));
   DB_TRY(launch_orphan_first_touch(ctx, src, dst, ncols, ldx, ep));
@@ -40,14 +40,14 @@ static int fused_apply_impl(dftfe_b200_ctx *ctx, double *src, double *dst, int n
 }
 
 int op_fused_apply(dftfe_b200_ctx *ctx, double *src, double *dst, int ncols, double a, double b, double s) {
-  return fused_apply_impl(ctx, src, dst, ncols, a, b, s, ctx->rowLive.p);
+  return fused_apply_impl(ctx, src, dst, ncols, a, b, s, nullptr);
 }
 
 // operatorDFTDeviceClass::HX net effect (kohnShamDFTOperatorDevice.cc:3765-3860)
 int op_hx(dftfe_b200_ctx *ctx, double *src, double *dst, int ncols, int scaleFlag, double scalar, int doUnscale) {
   // dst <- (scaleFlag ? dst : M^-1/2 dst) + scalar * H~ src on owned free rows, 0 on constrained rows
   DB_TRY(fused_apply_impl(ctx, src, dst, ncols, 0.0, 1.0, scalar,
-                          scaleFlag ? ctx->rowLive.p : ctx->rowLiveInvSqrtM.p));
+                          scaleFlag ? nullptr : ctx->invSqrtM.p));
   // src side effects of the reference: constrained rows end at 0 (x M^1/2 = 0), ghosts zeroed;
   // without unscaling the caller sees scalar * M^-1/2 * src.
   if (doUnscale) {
@@ -67,6 +67,7 @@ int op_hx_cheby(dftfe_b200_ctx *ctx, double *src, double *dst, int ncols) {
   EpilogueParams ep;  // a=0, b=1, s=1: pure accumulate; undo the scales folded into the tiled H
   ep.rowIn = ctx->rowInInv.p;
   ep.rowOut = ctx->rowOutInv.p;
+  ep.allLive = 1;
   DB_TRY(launch_cell_matvec(ctx, src, dst, ncols, ldx, ep));
   DB_TRY(launch_slave_to_master(ctx, dst, ncols, ldx, nullptr));
   DB_TRY(ghost_zero(ctx, src, ncols, ldx));
