@@ -61,8 +61,29 @@ struct CellCfg {
   static constexpr int TPW = (MT + WARPS - 1) / WARPS;  // row tiles per warp (max)
   static constexpr int THREADS = WARPS * 32;
   static constexpr size_t SMEM = (size_t)KPAD * LDS * sizeof(double);
-  static constexpr size_t HT_PER_CELL = (size_t)KS * MT * 32;  // doubles
+  // per-lane fragment vector (padded so that it is loadable with 16/32-byte vector loads)
+  static constexpr int TPWP = TPW <= 1 ? 1 : (TPW <= 2 ? 2 : (TPW <= 4 ? 4 : 8));
+  static constexpr size_t HT_PER_WARP = (size_t)KS * 32 * TPWP;   // doubles
+  static constexpr size_t HT_PER_CELL = (size_t)WARPS * HT_PER_WARP;  // doubles
 };
+
+// one k-step of A fragments for a warp: TPWP consecutive doubles per lane
+template <int N>
+__device__ __forceinline__ void load_frags(const double *p, double (&a)[N]) {
+  if constexpr (N == 1) {
+    a[0] = __ldg(p);
+  } else if constexpr (N == 2) {
+    asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(a[0]), "=d"(a[1]) : "l"(p));
+  } else if constexpr (N == 4) {
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a[0]), "=d"(a[1]), "=d"(a[2]), "=d"(a[3]) : "l"(p));
+  } else {
+    static_assert(N == 8, "unsupported fragment vector");
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(a[0]), "=d"(a[1]), "=d"(a[2]), "=d"(a[3]) : "l"(p));
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];"
+                 : "=d"(a[4]), "=d"(a[5]), "=d"(a[6]), "=d"(a[7])
+                 : "l"(p + 4));
+  }
+}
 
 __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
@@ -70,8 +91,10 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
                : "d"(a), "d"(b));
 }
 
-// H_c (row-major n x n as stored by the reference) -> fragment-major:
-// Ht[cell][ks][mt][lane] = Hm[mt*8 + lane/4][ks*4 + lane%4], zero padded.
+// H_c (row-major n x n as stored by the reference) -> fragment-major, grouped per MMA warp:
+// Ht[cell][warp][ks][lane][t] = Hm[(warp + t*WARPS)*8 + lane/4][ks*4 + lane%4], zero padded, so a
+// lane fetches the A fragments of all its row tiles for one k-step with ONE 32-byte load
+// (LDG.E.256) and a warp's stream for a cell is one contiguous run.
 // The mass scalings of H~ = M^-1/2 H M^-1/2 are folded in here, once per
 // set_cell_hamiltonian: Ht holds rowOut[row(c,i)] * H_c[i][k] * rowIn[row(c,k)], so the
 // per-degree kernels gather raw rows (pure copies - TMA-able) and scale nothing.
@@ -83,13 +106,17 @@ __global__ void retile_H_kernel(const double *__restrict__ H, double *__restrict
   const int64_t total = nCells * (int64_t)C::HT_PER_CELL;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
-    const int lane = idx % 32;
-    int64_t r = idx / 32;
-    const int mt = r % C::MT;
-    r /= C::MT;
+    int64_t r = idx;
+    const int t = r % C::TPWP;
+    r /= C::TPWP;
+    const int lane = r % 32;
+    r /= 32;
     const int ks = r % C::KS;
-    const int64_t cell = r / C::KS;
-    const int i = mt * 8 + lane / 4;
+    r /= C::KS;
+    const int w = r % C::WARPS;
+    const int64_t cell = r / C::WARPS;
+    const int mt = w + t * C::WARPS;
+    const int i = (t < C::TPW && mt < C::MT) ? mt * 8 + lane / 4 : NODES;
     const int k = ks * 4 + lane % 4;
     double v = 0.0;
     if (i < NODES && k < NODES) {
@@ -141,26 +168,18 @@ cell_matvec_kernel(const double *__restrict__ Ht, const uint32_t *__restrict__ c
 #pragma unroll
     for (int nt = 0; nt < NT; ++nt) acc[t][nt][0] = acc[t][nt][1] = 0.0;
 
-  const double *Hc = Ht + (size_t)cell * C::HT_PER_CELL + lane;
+  const double *Hc = Ht + (size_t)cell * C::HT_PER_CELL + (size_t)warp * C::HT_PER_WARP + lane * C::TPWP;
   const double *xb = Xs + (lane & 3) * LDS + (lane >> 2);
 
-  double a0[C::TPW], a1[C::TPW];
-#pragma unroll
-  for (int t = 0; t < C::TPW; ++t) {
-    const int mt = warp + t * C::WARPS;
-    a0[t] = (mt < C::MT) ? __ldg(Hc + (size_t)(0 * C::MT + mt) * 32) : 0.0;
-    a1[t] = (mt < C::MT && C::KS > 1) ? __ldg(Hc + (size_t)(1 * C::MT + mt) * 32) : 0.0;
-  }
+  double a0[C::TPWP], a1[C::TPWP];
+  load_frags<C::TPWP>(Hc, a0);
+  load_frags<C::TPWP>(Hc + (C::KS > 1 ? 32 * C::TPWP : 0), a1);
 
   for (int ks = 0; ks < C::KS; ks += 2) {
-    // prefetch A for ks+2, ks+3
-    double n0[C::TPW], n1[C::TPW];
-#pragma unroll
-    for (int t = 0; t < C::TPW; ++t) {
-      const int mt = warp + t * C::WARPS;
-      n0[t] = (mt < C::MT && ks + 2 < C::KS) ? __ldg(Hc + (size_t)((ks + 2) * C::MT + mt) * 32) : 0.0;
-      n1[t] = (mt < C::MT && ks + 3 < C::KS) ? __ldg(Hc + (size_t)((ks + 3) * C::MT + mt) * 32) : 0.0;
-    }
+    // prefetch A for ks+2, ks+3 (clamped re-reads at the end are harmless)
+    double n0[C::TPWP], n1[C::TPWP];
+    load_frags<C::TPWP>(Hc + (size_t)min(ks + 2, C::KS - 1) * 32 * C::TPWP, n0);
+    load_frags<C::TPWP>(Hc + (size_t)min(ks + 3, C::KS - 1) * 32 * C::TPWP, n1);
     {
       double b[NT];
 #pragma unroll
@@ -180,7 +199,7 @@ cell_matvec_kernel(const double *__restrict__ Ht, const uint32_t *__restrict__ c
         for (int nt = 0; nt < NT; ++nt) dmma884(acc[t][nt][0], acc[t][nt][1], a1[t], b[nt]);
     }
 #pragma unroll
-    for (int t = 0; t < C::TPW; ++t) {
+    for (int t = 0; t < C::TPWP; ++t) {
       a0[t] = n0[t];
       a1[t] = n1[t];
     }
@@ -304,15 +323,12 @@ __device__ __forceinline__ void mma_warp_items(const double *__restrict__ Ht, co
   using P = PersistCfg<NODES>;
   const double *xb0 = Xs + (lane & 3) * LDS + (lane >> 2);
   // A prefetch ring; primed for the first item here, re-primed for the next item before each epilogue
-  double a[P::APF][NTILE];
+  double a[P::APF][C::TPWP];
   auto prime = [&](int item) {
     const int cell = cells[item / nColTiles];
-    const double *Hc = Ht + (size_t)cell * C::HT_PER_CELL + lane;
+    const double *Hc = Ht + (size_t)cell * C::HT_PER_CELL + (size_t)warp * C::HT_PER_WARP + lane * C::TPWP;
 #pragma unroll
-    for (int s = 0; s < P::APF; ++s)
-#pragma unroll
-      for (int t = 0; t < NTILE; ++t)
-        a[s][t] = (s < C::KS) ? __ldg(Hc + (size_t)(s * C::MT + warp + t * C::WARPS) * 32) : 0.0;
+    for (int s = 0; s < P::APF; ++s) load_frags<C::TPWP>(Hc + (size_t)min(s, C::KS - 1) * 32 * C::TPWP, a[s]);
   };
   if ((int)blockIdx.x < nItems) prime(blockIdx.x);
   int it = 0;
@@ -321,7 +337,7 @@ __device__ __forceinline__ void mma_warp_items(const double *__restrict__ Ht, co
     const uint32_t ph = (it >> 1) & 1;
     const int cell = cells[item / nColTiles];
     const int col0 = (item % nColTiles) * BT;
-    const double *Hc = Ht + (size_t)cell * C::HT_PER_CELL + lane;
+    const double *Hc = Ht + (size_t)cell * C::HT_PER_CELL + (size_t)warp * C::HT_PER_WARP + lane * C::TPWP;
     const double *xb = xb0 + buf * P::XBUF;
 
     double acc[NTILE][NT][2];
@@ -344,11 +360,7 @@ __device__ __forceinline__ void mma_warp_items(const double *__restrict__ Ht, co
 #pragma unroll
           for (int nt = 0; nt < NT; ++nt) dmma884(acc[t][nt][0], acc[t][nt][1], a[s][t], b[nt]);
 #if DB_DIAG != 1 && DB_DIAG != 4
-        if (ks + s + P::APF < C::KS) {
-#pragma unroll
-          for (int t = 0; t < NTILE; ++t)
-            a[s][t] = __ldg(Hc + (size_t)((ks + s + P::APF) * C::MT + warp + t * C::WARPS) * 32);
-        }
+        if (ks + s + P::APF < C::KS) load_frags<C::TPWP>(Hc + (size_t)(ks + s + P::APF) * 32 * C::TPWP, a[s]);
 #endif
       }
     }
