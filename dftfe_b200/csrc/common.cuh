@@ -222,6 +222,9 @@ struct dftfe_b200_ctx {
   dftfe_b200::DevBuf<double> partials;            // split-K / reduction workspace
   dftfe_b200::DevBuf<double> arTmp;               // loopback all-reduce scratch
   dftfe_b200::DevBuf<double> rotScratch;
+  dftfe_b200::DevBuf<int32_t> projTiles;          // tile list of the DMMA projection kernel
+  dftfe_b200::DevBuf<double> projWs;              // its split-m partial tiles
+  bool use_cublas_dense = false;                  // option "cublas_projections": A/B against cuBLAS Dgemm
   dftfe_b200::DevBuf<int> devInfo;
   dftfe_b200::DevBuf<double> cusolverWork;
   double a0 = 0, bLow = 0, bUp = 0;
@@ -283,6 +286,15 @@ int launch_orphan_first_touch(dftfe_b200_ctx *ctx, const double *src, double *ds
                               const EpilogueParams &ep);
 
 int allreduce_sum(dftfe_b200_ctx *ctx, double *buf, size_t count);
+
+// projection.cu
+bool dmma_projection_usable(const dftfe_b200_ctx *ctx, int N, int lda, int ldb, int i0, int j0, int nRowsC,
+                            int nColsC);
+int launch_xty(dftfe_b200_ctx *ctx, const double *A, int lda, int iOff, const double *B, int ldb, int jOff,
+               int nRowsC, int nColsC, int iGlobal, int jGlobal, bool lowerOnly, double *C, int ldc);
+bool dmma_rotation_usable(int N);
+int launch_xq(dftfe_b200_ctx *ctx, const double *X, int N, int64_t rows, const double *Qrm, double *Out);
+int launch_transpose_square(dftfe_b200_ctx *ctx, const double *in, double *out, int N);
 
 // high-level pieces (solver.cu)
 int op_hx(dftfe_b200_ctx *ctx, double *src, double *dst, int ncols, int scaleFlag, double scalar,

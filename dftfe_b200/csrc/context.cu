@@ -479,6 +479,10 @@ int dftfe_b200_set_option(dftfe_b200_ctx *ctx, const char *name, int32_t value) 
     ctx->force_generic_cell_kernel = value != 0;
     return 0;
   }
+  if (std::strcmp(name, "cublas_projections") == 0) {
+    ctx->use_cublas_dense = value != 0;
+    return 0;
+  }
   set_error("set_option: unknown option '%s'", name);
   return DFTFE_B200_ERR_INVALID;
 }

@@ -195,7 +195,10 @@ static int xtx_impl(dftfe_b200_ctx *ctx, const double *X, int N, double *S) {
   const double one = 1.0, zero = 0.0;
   DB_CUBLAS(cublasSetStream(ctx->cublas, ctx->stream));
   DB_CUDA(cudaMemsetAsync(S, 0, (size_t)N * N * sizeof(double), ctx->stream));
-  if (ctx->M > 0) {
+  if (ctx->M > 0 && !ctx->use_cublas_dense && dmma_projection_usable(ctx, N, N, N, 0, 0, N, N)) {
+    // hand-written DMMA kernel, lower-triangular 128x128 tiles of the whole N x N matrix in one pass
+    DB_TRY(launch_xty(ctx, X, N, 0, X, N, 0, N, N, 0, 0, true, S, N));
+  } else if (ctx->M > 0) {
     for (int j = 0; j < N; j += Bw) {
       const int Bc = std::min(Bw, N - j), D = N - j;
       ProfScope ps(ctx, "projection");
@@ -229,7 +232,9 @@ static int xthx_impl(dftfe_b200_ctx *ctx, const double *X, int N, double *Hp) {
   for (int j = 0; j < N; j += Bc0) {
     const int Bc = std::min(Bc0, N - j), D = N - j;
     DB_TRY(apply_H_to_columns(ctx, X, N, j, Bc));
-    if (ctx->M > 0) {
+    if (ctx->M > 0 && !ctx->use_cublas_dense && dmma_projection_usable(ctx, N, N, Bc, j, 0, D, Bc)) {
+      DB_TRY(launch_xty(ctx, X, N, j, ctx->blockY.p, Bc, 0, D, Bc, j, j, true, Hp + j + (size_t)j * N, N));
+    } else if (ctx->M > 0) {
       ProfScope ps(ctx, "projection");
       // block(D x Bc) = X_cm[j:, :] (D x M) * HXb_cm (Bc x M)^T
       DB_CUBLAS(cublasDgemm(ctx->cublas, CUBLAS_OP_N, CUBLAS_OP_T, D, Bc, (int)ctx->M, &one, X + j, N,
@@ -246,12 +251,26 @@ static int xthx_impl(dftfe_b200_ctx *ctx, const double *X, int N, double *Hp) {
 // X <- X * Q.  qColMajor: Q memory holds Q(i,j) at i + j*N (cuSOLVER output), else row-major.
 static int rotate_impl(dftfe_b200_ctx *ctx, double *X, int N, const double *Q, bool qColMajor) {
   if (ctx->M == 0) return 0;
-  const int64_t chunk = std::min<int64_t>(ctx->M, 16384);
+  const int64_t chunk = std::min<int64_t>(ctx->M, 148 * 128);
   DB_TRY(ctx->rotScratch.alloc((size_t)chunk * N));
   const double one = 1.0, zero = 0.0;
   DB_CUBLAS(cublasSetStream(ctx->cublas, ctx->stream));
+  const bool dmma = !ctx->use_cublas_dense && dmma_rotation_usable(N);
+  const double *Qrm = Q;
+  if (dmma && qColMajor) {  // the kernel wants Q(k, j) with j fastest
+    DB_TRY(ctx->denseC.alloc((size_t)N * N));
+    DB_TRY(launch_transpose_square(ctx, Q, ctx->denseC.p, N));
+    Qrm = ctx->denseC.p;
+  }
   for (int64_t r0 = 0; r0 < ctx->M; r0 += chunk) {
     const int mc = (int)std::min<int64_t>(chunk, ctx->M - r0);
+    if (dmma) {
+      DB_TRY(launch_xq(ctx, X + (size_t)r0 * N, N, mc, Qrm, ctx->rotScratch.p));
+      ctx->launches += 1;
+      DB_CUDA(cudaMemcpyAsync(X + (size_t)r0 * N, ctx->rotScratch.p, (size_t)mc * N * sizeof(double),
+                              cudaMemcpyDeviceToDevice, ctx->stream));
+      continue;
+    }
     ProfScope ps(ctx, "rotation", 2);
     // Xnew_cm (N x mc) = Q^T_(math) * X_cm ; row-major Q memory is col-major Q^T
     DB_CUBLAS(cublasDgemm(ctx->cublas, qColMajor ? CUBLAS_OP_T : CUBLAS_OP_N, CUBLAS_OP_N, N, mc, N, &one, Q, N,

@@ -192,3 +192,43 @@ def test_projections_rotation_and_solve(capi):
     # known answer: lowest eigenvalues are converged and match a dense solve of the same discretisation
     assert res[:4].max() < 1e-6
     op.close()
+
+
+@pytest.mark.parametrize("N,B", [(128, 128), (256, 128), (384, 128)])
+def test_dmma_projection_and_rotation_kernels(capi, N, B):
+    """Hand-written DMMA GEMMs (128-wide tiles, split-m partials, ragged last chunk) against the oracle
+    and against the cuBLAS path of the same entry points."""
+    from oracle import chfsi_oracle as O
+
+    mesh, ranks = make_problem(2, (5, 4, 3), 1.3, (True, False, True))
+    rp = ranks[0]
+    assert rp.M % 16 != 0  # exercises the ragged last chunk
+    op = capi.Operator(rp, B)
+    op.set_cell_hamiltonian(rp.H)
+    X = scatter_to_ranks(ranks, random_global(mesh, N, seed=3), loewdin=True)
+    X_d = _dev(X[0][:rp.M])
+    S_ref = O.xtx(ranks, X)
+    H_ref = O.xthx(ranks, [x.copy() for x in X], B)
+    Q = np.linalg.qr(np.random.default_rng(1).normal(size=(N, N)))[0]
+    R_ref = X[0][:rp.M] @ Q
+    for use_cublas in (0, 1):
+        op.set_option("cublas_projections", use_cublas)
+        S_d = torch.full((N, N), float("nan"), dtype=torch.float64, device="cuda")
+        op.XtX(X_d, S_d)
+        assert _relerr(S_d.cpu().numpy(), S_ref) < 1e-13, use_cublas
+        op.XtHX(X_d, S_d)
+        assert _relerr(S_d.cpu().numpy(), H_ref) < 1e-12, use_cublas
+        Xr = X_d.clone()
+        op.subspaceRotation(Xr, _dev(Q))
+        assert _relerr(Xr.cpu().numpy(), R_ref) < 1e-13, use_cublas
+    # solve() end to end with the DMMA kernels (N multiple of 128)
+    op.set_option("cublas_projections", 0)
+    solver = capi.ChebyshevSolver(op)
+    Xo = scatter_to_ranks(ranks, random_global(mesh, N, seed=8), zero_constrained=False)
+    Xd = _dev(Xo[0][:rp.M])
+    lo, up = O.lanczos_bounds(ranks)
+    eig, res, ub = solver.solve(Xd, isFirstFilteringCall=True, chebyshevOrder=10, reuseLanczos=True)
+    a0, blow, bup = solver.spectrumBounds()
+    ev_ref, res_ref = O.solve(ranks, Xo, B, 10, (a0, blow, bup))
+    assert np.abs(eig - ev_ref).max() < 1e-8
+    op.close()
