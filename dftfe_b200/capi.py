@@ -63,7 +63,7 @@ EXPORTED_SYMBOLS = [
     "dftfe_b200_set_stream", "dftfe_b200_sync", "dftfe_b200_build_index_map", "dftfe_b200_set_index_map",
     "dftfe_b200_set_constraints", "dftfe_b200_set_mass", "dftfe_b200_set_ghost_pattern",
     "dftfe_b200_nccl_unique_id", "dftfe_b200_comm_init", "dftfe_b200_comm_init_loopback",
-    "dftfe_b200_set_cell_hamiltonian", "dftfe_b200_set_cell_hamiltonian_host",
+    "dftfe_b200_set_nonlocal", "dftfe_b200_set_cell_hamiltonian", "dftfe_b200_set_cell_hamiltonian_host",
     "dftfe_b200_update_ghost_values", "dftfe_b200_accumulate_add_locally_owned", "dftfe_b200_zero_out_ghosts",
     "dftfe_b200_constraints_distribute", "dftfe_b200_constraints_distribute_slave_to_master",
     "dftfe_b200_constraints_set_zero", "dftfe_b200_hx", "dftfe_b200_hx_cheby", "dftfe_b200_cheb_filter",
@@ -179,6 +179,17 @@ class Operator:
         _check(self.lib.dftfe_b200_set_ghost_pattern(self.h, C.c_int32(prob.rank), C.c_int32(prob.nranks),
                                                      C.c_int32(gp.size), _ptr(gp), _ptr(gr), C.c_int32(tp.size),
                                                      _ptr(tp), _ptr(tc), _ptr(ti)))
+
+        nl = getattr(prob, "nonlocal_data", None)
+        if nl is not None:
+            self.set_nonlocal(nl)
+
+    def set_nonlocal(self, nl):
+        """NonLocalData (dftfe_b200.femesh) -> dftfe_b200_set_nonlocal."""
+        npj, V = _np(nl.nProjPerAtom, np.int32), _np(nl.V, np.float64)
+        ec, ea, Cm = _np(nl.entryCell, np.int32), _np(nl.entryAtom, np.int32), _np(nl.C, np.float64)
+        _check(self.lib.dftfe_b200_set_nonlocal(self.h, C.c_int32(nl.nAtoms), _ptr(npj), _ptr(V), C.c_int64(ec.size),
+                                                _ptr(ec), _ptr(ea), _ptr(Cm), C.c_int32(nl.pMax)))
 
     # ---- lifetime -------------------------------------------------------
     def close(self):

@@ -212,6 +212,15 @@ struct dftfe_b200_ctx {
   dftfe_b200::DevBuf<double> Htiled;
   dftfe_b200::DevBuf<double> Hstage;   // staging for host uploads
 
+  // --- non-local projectors (nonlocal.cu)
+  bool have_nonlocal = false;
+  int nlAtoms = 0, nlTotalProj = 0;
+  int64_t nlRows = 0;
+  dftfe_b200::DevBuf<int32_t> nlProjOffset, nlAtomRowStart, nlEntProj;
+  dftfe_b200::DevBuf<int64_t> nlAtomValStart, nlRowStart;
+  dftfe_b200::DevBuf<uint32_t> nlAtomRows, nlRowList;
+  dftfe_b200::DevBuf<double> nlV, nlVals, nlEntVal, nlProj;
+
   // --- solver state / scratch
   dftfe_b200::DevBuf<double> blockX, blockY;      // (M+G)*B
   dftfe_b200::DevBuf<double> blockX2;             // second block buffer of the host-pipelined filter
@@ -286,6 +295,12 @@ int launch_orphan_first_touch(dftfe_b200_ctx *ctx, const double *src, double *ds
                               const EpilogueParams &ep);
 
 int allreduce_sum(dftfe_b200_ctx *ctx, double *buf, size_t count);
+
+// nonlocal.cu
+int nonlocal_setup(dftfe_b200_ctx *ctx, int32_t nAtoms, const int32_t *nProj, const double *V, int64_t nEntries,
+                   const int32_t *entryCell, const int32_t *entryAtom, const double *C, int32_t pMax);
+int nonlocal_project(dftfe_b200_ctx *ctx, const double *x, int ncols, int ldx, const double *rowScaleIn);
+int nonlocal_apply(dftfe_b200_ctx *ctx, double *y, int ncols, int ldx, const double *rowScaleOut, double s);
 
 // projection.cu
 bool dmma_projection_usable(const dftfe_b200_ctx *ctx, int N, int lda, int ldb, int i0, int j0, int nRowsC,

@@ -421,6 +421,14 @@ int dftfe_b200_comm_init_loopback(dftfe_b200_ctx *ctx, int32_t group_id, int32_t
   return loopback_join(ctx, group_id, rank, nranks);
 }
 
+int dftfe_b200_set_nonlocal(dftfe_b200_ctx *ctx, int32_t n_atoms, const int32_t *n_proj_per_atom_h, const double *V_h,
+                            int64_t n_entries, const int32_t *entry_cell_h, const int32_t *entry_atom_h,
+                            const double *C_h, int32_t p_max) {
+  DB_CTX(ctx);
+  DB_CHECK(n_atoms >= 0 && n_entries >= 0 && p_max >= 0, "set_nonlocal: negative size");
+  return nonlocal_setup(ctx, n_atoms, n_proj_per_atom_h, V_h, n_entries, entry_cell_h, entry_atom_h, C_h, p_max);
+}
+
 int dftfe_b200_set_cell_hamiltonian(dftfe_b200_ctx *ctx, const double *H_d) {
   DB_CTX(ctx);
   DB_CHECK(H_d || ctx->nC == 0, "set_cell_hamiltonian: null pointer");

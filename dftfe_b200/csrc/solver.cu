@@ -30,8 +30,10 @@ static int fused_apply_impl(dftfe_b200_ctx *ctx, double *src, double *dst, int n
   ep.rowOut = nullptr;
   ep.rowA = nullptr;  // liveness travels in the row words of the index map
   ep.rowB = rowB;
+  DB_TRY(nonlocal_project(ctx, src, ncols, ldx, ctx->rowIn.p));  // C^T (M^-1/2 x), all-reduced
   DB_TRY(launch_cell_matvec(ctx, src, dst, ncols, ldx, ep));
   DB_TRY(launch_orphan_first_touch(ctx, src, dst, ncols, ldx, ep));
+  DB_TRY(nonlocal_apply(ctx, dst, ncols, ldx, ctx->rowOut.p, s));  // += s M^-1/2 C V (C^T ...)
   DB_TRY(launch_slave_to_master(ctx, dst, ncols, ldx, ctx->rowOut.p));
   DB_TRY(ghost_accumulate(ctx, dst, ncols, ldx, ctx->rowOut.p));
   DB_TRY(ghost_zero(ctx, dst, ncols, ldx));
@@ -68,7 +70,9 @@ int op_hx_cheby(dftfe_b200_ctx *ctx, double *src, double *dst, int ncols) {
   ep.rowIn = ctx->rowInInv.p;
   ep.rowOut = ctx->rowOutInv.p;
   ep.allLive = 1;
+  DB_TRY(nonlocal_project(ctx, src, ncols, ldx, nullptr));
   DB_TRY(launch_cell_matvec(ctx, src, dst, ncols, ldx, ep));
+  DB_TRY(nonlocal_apply(ctx, dst, ncols, ldx, nullptr, 1.0));
   DB_TRY(launch_slave_to_master(ctx, dst, ncols, ldx, nullptr));
   DB_TRY(ghost_zero(ctx, src, ncols, ldx));
   DB_TRY(ghost_accumulate(ctx, dst, ncols, ldx, nullptr));

@@ -169,6 +169,23 @@ def gaussian_wells_potential(box: Sequence[float], nwells: int = 8, seed: int = 
 # mesh / partition
 # --------------------------------------------------------------------------
 @dataclass
+class NonLocalData:
+    """Separable (Kleinman-Bylander-like) non-local pseudopotential data of one rank, in the spirit of
+    the arrays kohnShamDFTOperatorDeviceClass::reinit packs
+    (src/dftOperator/kohnShamDFTOperatorDevice.cc:626-927): for every (owned cell, atom) pair whose
+    projector support touches the cell an n x Pmax block C[e][i][p] = int N_i phi_{a,p}, the coupling
+    constants V[a][p] and the projector count per atom."""
+
+    nAtoms: int                    # global number of non-local atoms
+    nProjPerAtom: np.ndarray       # int32[nAtoms]
+    V: np.ndarray                  # float64[sum nProjPerAtom], atom-major
+    entryCell: np.ndarray          # int32[nEntries] local (owned) cell index
+    entryAtom: np.ndarray          # int32[nEntries] global atom id
+    C: np.ndarray                  # float64[nEntries, n, Pmax] (zero padded beyond nProjPerAtom[atom])
+    pMax: int
+
+
+@dataclass
 class RankProblem:
     """Everything one rank hands to the C ABI (plain arrays)."""
 
@@ -204,6 +221,7 @@ class RankProblem:
     procBoundaryFlags: np.ndarray       # uint32[M]  (locallyOwnedProcBoundaryNodes)
     nodeXYZ: Optional[np.ndarray] = None  # float64[M+G, 3] physical coordinates of local rows
     H: Optional[np.ndarray] = None      # float64[nCells, n, n]; mem[c,I,J] = H_c(I,J)
+    nonlocal_data: Optional["NonLocalData"] = None
 
     def index_map(self, B: int) -> np.ndarray:
         """flattenedArrayCellLocalProcIndexIdMap: local id pre-multiplied by B
@@ -405,6 +423,49 @@ class GlobalMesh:
             ownedLocalIdxForTargets=(np.concatenate(tidx) if tidx else np.zeros(0, np.uint32)),
             procBoundaryFlags=flags, nodeXYZ=xyz, H=H,
         )
+
+    def nonlocal_data(self, rank: int, atoms_xyz: np.ndarray, n_proj: Sequence[int], rc: float = 2.0,
+                      seed: int = 77) -> NonLocalData:
+        """Synthetic separable projectors: atom a carries n_proj[a] functions
+        phi_p(r) = poly_p(r - R_a) * exp(-|r - R_a|^2 / (2 s^2)) cut off at rc (minimum image on periodic
+        axes); C_c[i,p] = phi_p(x_i) * w_i (GLL quadrature, like the mass vector); couplings V in
+        [-1.5, 1.5] seeded."""
+        ref = self.ref
+        cells = self.owned_cells(rank)
+        nx, ny, nz = self.ncells
+        origin = np.stack([(cells % nx), (cells // nx) % ny, cells // (nx * ny)], axis=1) * self.h
+        xyz = origin[:, None, :] + ref.node_xyz[None, :, :]             # (nc, n, 3)
+        box = np.asarray(self.box)
+        per = np.asarray(self.periodic)
+        n_proj = np.asarray(n_proj, dtype=np.int32)
+        pmax = int(n_proj.max())
+        rng = np.random.default_rng(seed)
+        V = rng.uniform(-1.5, 1.5, size=int(n_proj.sum()))
+        sig = 0.45 * rc
+        eCell, eAtom, Cs = [], [], []
+        for a, R in enumerate(np.asarray(atoms_xyz, dtype=np.float64)):
+            d = xyz - R
+            d = np.where(per, d - box * np.round(d / box), d)
+            r2 = np.sum(d * d, axis=-1)
+            inside = r2 < rc * rc
+            hit = np.nonzero(inside.any(axis=1))[0]
+            if hit.size == 0:
+                continue
+            g = np.exp(-r2[hit] / (2 * sig * sig)) * inside[hit] * ref.mass_gll[None, :]
+            dd = d[hit]
+            polys = [np.ones_like(g), dd[..., 0], dd[..., 1], dd[..., 2], dd[..., 0] * dd[..., 1],
+                     dd[..., 1] * dd[..., 2], dd[..., 0] * dd[..., 2], r2[hit] - 1.0]
+            blk = np.zeros((hit.size, ref.n, pmax))
+            for p in range(int(n_proj[a])):
+                blk[:, :, p] = polys[p % len(polys)] * g * (1.0 + 0.25 * (p // len(polys)))
+            eCell.append(hit.astype(np.int32))
+            eAtom.append(np.full(hit.size, a, dtype=np.int32))
+            Cs.append(blk)
+        if eCell:
+            return NonLocalData(len(atoms_xyz), n_proj, V, np.concatenate(eCell), np.concatenate(eAtom),
+                                np.concatenate(Cs), pmax)
+        return NonLocalData(len(atoms_xyz), n_proj, V, np.zeros(0, np.int32), np.zeros(0, np.int32),
+                            np.zeros((0, ref.n, pmax)), pmax)
 
     def cell_hamiltonians(self, cells: np.ndarray, potential: Optional[Callable],
                           vquad: str = "gauss", out: Optional[np.ndarray] = None) -> np.ndarray:

@@ -131,6 +131,16 @@ int dftfe_b200_comm_init(dftfe_b200_ctx *ctx, const uint8_t id_h[128], int32_t r
  * Test facility for the multi-rank path; production uses dftfe_b200_comm_init. */
 int dftfe_b200_comm_init_loopback(dftfe_b200_ctx *ctx, int32_t group_id, int32_t rank, int32_t nranks);
 
+/* Non-local (separable pseudopotential) projectors, the data reinit() packs at
+ * kohnShamDFTOperatorDevice.cc:626-927: for each (owned cell, atom) pair in the compact support an
+ * n x p_max block C[e][i][p] = <N_i | phi_{atom,p}> (zero padded), the coupling constants V (atom-major)
+ * and the projector count per (global) atom.  HX / HXCheby then add C V C^T x
+ * (computeNonLocalHamiltonianTimesXMemoryOptBatchGEMMDevice.cc:27-283); the projector vector is summed
+ * over ranks with an all-reduce.  At most 32 projectors per atom. */
+int dftfe_b200_set_nonlocal(dftfe_b200_ctx *ctx, int32_t n_atoms, const int32_t *n_proj_per_atom_h, const double *V_h,
+                            int64_t n_entries, const int32_t *entry_cell_h, const int32_t *entry_atom_h,
+                            const double *C_h, int32_t p_max);
+
 /* Cell Hamiltonian for the active (k-point, spin): nC * n * n doubles,
  * mem[c*n*n + I*n + J] = H_c(I,J) as d_cellHamiltonianMatrixFlattenedDevice
  * (kohnShamDFTOperatorDevice.cc:602-606; hamiltonianMatrixCalculatorFlattenedDevice.cc:23-60).

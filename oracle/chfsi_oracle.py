@@ -161,6 +161,35 @@ def compute_local_hamiltonian_times_x(rp, src: np.ndarray, dst: np.ndarray, scal
         np.add.at(dst, ids[c], Yc)  # ids within a cell are unique; in order like daxpy
 
 
+def compute_nonlocal_hamiltonian_times_x(ranks, src, dst, scalar: float = 1.0):
+    """src/dftOperator/computeNonLocalHamiltonianTimesXMemoryOpt.cc:266-505 (real): per owned cell and
+    atom, projKet[a] += C_c^T X_c (dgemm); the projector vector is summed over ranks
+    (accumulateAddLocallyOwned + updateGhostValues on d_projectorKetTimesVectorParFlattened); scaled
+    by the coupling constants V; then per cell Y_c = C_c (V projKet[a]) is added into dst through the
+    index map.  No-op when the ranks carry no non-local data."""
+    if getattr(ranks[0], "nonlocal_data", None) is None:
+        return
+    nl0 = ranks[0].nonlocal_data
+    off = np.concatenate(([0], np.cumsum(nl0.nProjPerAtom)))
+    B = src[0].shape[1]
+    proj = np.zeros((int(off[-1]), B), dtype=src[0].dtype)
+    for rp, s in zip(ranks, src):
+        nl = rp.nonlocal_data
+        for e in range(nl.entryCell.size):
+            a = nl.entryAtom[e]
+            P = nl.nProjPerAtom[a]
+            Xc = s[rp.cellLocalDofs[nl.entryCell[e]]]
+            proj[off[a]:off[a] + P] += nl.C[e][:, :P].T @ Xc
+    proj *= nl0.V[:, None]
+    for rp, d in zip(ranks, dst):
+        nl = rp.nonlocal_data
+        for e in range(nl.entryCell.size):
+            a = nl.entryAtom[e]
+            P = nl.nProjPerAtom[a]
+            Yc = scalar * (nl.C[e][:, :P] @ proj[off[a]:off[a] + P])
+            np.add.at(d, rp.cellLocalDofs[nl.entryCell[e]], Yc)
+
+
 def HX(ranks, src, dst, scale_flag: bool, scalar: float, do_unscaling_src: bool = True):
     """src/dftOperator/kohnShamDFTOperator.cc:950-1044 (CPU) with the device
     variant's ``doUnscalingSrc`` switch and ``scalar`` placement
@@ -177,6 +206,8 @@ def HX(ranks, src, dst, scale_flag: bool, scalar: float, do_unscaling_src: bool 
     for rp, s, d in zip(ranks, src, dst):
         distribute(rp, s)
         compute_local_hamiltonian_times_x(rp, s, d, 1.0)
+    compute_nonlocal_hamiltonian_times_x(ranks, src, dst, 1.0)
+    for rp, d in zip(ranks, dst):
         distribute_slave_to_master(rp, d)
     zero_out_ghosts(ranks, src)
     accumulate_add_locally_owned(ranks, dst)
@@ -196,6 +227,8 @@ def HXCheby(ranks, src, dst):
     for rp, s, d in zip(ranks, src, dst):
         distribute(rp, s)
         compute_local_hamiltonian_times_x(rp, s, d, 1.0)
+    compute_nonlocal_hamiltonian_times_x(ranks, src, dst, 1.0)
+    for rp, d in zip(ranks, dst):
         distribute_slave_to_master(rp, d)
     zero_out_ghosts(ranks, src)
     accumulate_add_locally_owned(ranks, dst)

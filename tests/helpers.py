@@ -5,11 +5,17 @@ from dftfe_b200.femesh import build_mesh, gaussian_wells_potential
 
 
 def make_problem(p, ncells, h=1.0, periodic=(True, True, True), nranks=1, vquad="gauss", potential=True,
-                 extra_constraints=None, rank_grid=None):
+                 extra_constraints=None, rank_grid=None, n_atoms=0, n_proj=4, rc=1.6):
     mesh = build_mesh(p, ncells, h, periodic=periodic, nranks=nranks, extra_constraints=extra_constraints,
                       rank_grid=rank_grid)
     pot = gaussian_wells_potential(mesh.box, periodic=periodic) if potential else None
     ranks = [mesh.rank_problem(r, potential=pot, vquad=vquad) for r in range(nranks)]
+    if n_atoms:
+        rng = np.random.default_rng(123)
+        atoms = rng.uniform(0.2, 0.8, size=(n_atoms, 3)) * np.asarray(mesh.box)
+        nproj = [n_proj + (a % 3) for a in range(n_atoms)]
+        for r, rp in enumerate(ranks):
+            rp.nonlocal_data = mesh.nonlocal_data(r, atoms, nproj, rc=rc)
     return mesh, ranks
 
 

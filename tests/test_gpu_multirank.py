@@ -41,7 +41,7 @@ def test_loopback_multirank_filter_and_projections(lib_built, nranks, rank_grid,
 
     p, B, N = 2, 32, 64
     mesh, ranks = make_problem(p, (4, 4, 4), 1.1, (True, True, False), nranks=nranks, rank_grid=rank_grid,
-                               extra_constraints=hanging_like_constraints(5))
+                               extra_constraints=hanging_like_constraints(5), n_atoms=2)
     Xg = random_global(mesh, N, seed=21)
     X = scatter_to_ranks(ranks, Xg, loewdin=True)
     lo, up = O.lanczos_bounds(ranks)

@@ -232,3 +232,39 @@ def test_dmma_projection_and_rotation_kernels(capi, N, B):
     ev_ref, res_ref = O.solve(ranks, Xo, B, 10, (a0, blow, bup))
     assert np.abs(eig - ev_ref).max() < 1e-8
     op.close()
+
+
+@pytest.mark.parametrize("p,ncells,periodic,B,generic", [
+    (3, (4, 3, 3), (True, True, False), 32, 0),
+    (2, (4, 4, 4), (True, True, True), 40, 1),
+    (6, (2, 2, 2), (True, True, True), 32, 0),
+])
+def test_nonlocal_projectors(capi, p, ncells, periodic, B, generic):
+    """HX / HXCheby / filter with the separable non-local term C V C^T (a6)."""
+    from oracle import chfsi_oracle as O
+
+    mesh, ranks = make_problem(p, ncells, 1.2, periodic, n_atoms=3, extra_constraints=hanging_like_constraints(3))
+    rp = ranks[0]
+    assert rp.nonlocal_data.entryCell.size > 0
+    op = capi.Operator(rp, B)
+    op.set_option("generic_cell_kernel", generic)
+    op.set_cell_hamiltonian(rp.H)
+    X = scatter_to_ranks(ranks, random_global(mesh, B, seed=1), loewdin=True)
+    Y0 = scatter_to_ranks(ranks, random_global(mesh, B, seed=2), loewdin=True)
+    src, dst = [X[0].copy()], [Y0[0].copy()]
+    O.HX(ranks, src, dst, True, 0.7)
+    s_d, d_d = _dev(X[0]), _dev(Y0[0])
+    op.HX(s_d, d_d, True, 0.7)
+    assert _relerr(d_d.cpu().numpy(), dst[0]) < RTOL
+    src, dst = [X[0].copy()], [Y0[0].copy()]
+    O.HXCheby(ranks, src, dst)
+    s_d, d_d = _dev(X[0]), _dev(Y0[0])
+    op.HXCheby(s_d, d_d)
+    assert _relerr(d_d.cpu().numpy(), dst[0]) < RTOL
+    lo, up = O.lanczos_bounds(ranks)
+    ref = [X[0].copy()]
+    O.chebyshev_filter_inplace(ranks, ref, 9, lo + 0.3 * (up - lo), up, lo - 0.3)
+    x_d, y_d = _dev(X[0]), torch.empty_like(_dev(X[0]))
+    op.chebyshevFilter(x_d, y_d, 9, lo + 0.3 * (up - lo), up, lo - 0.3)
+    assert _relerr(x_d.cpu().numpy()[:rp.M], ref[0][:rp.M]) < 9 * RTOL
+    op.close()
