@@ -37,8 +37,11 @@ class ProblemDesc(C.Structure):
         ("n_ghost", C.c_int64),
         ("n_global_dofs", C.c_int64),
         ("device", C.c_int32),
-        ("reserved", C.c_int32),
+        ("flags", C.c_int32),
     ]
+
+
+FLAG_COMPLEX = 1
 
 
 class SolveParams(C.Structure):
@@ -118,8 +121,8 @@ def _dptr(t) -> C.c_void_p:
     """device pointer of a torch CUDA tensor (float64, contiguous)."""
     import torch
 
-    assert isinstance(t, torch.Tensor) and t.is_cuda and t.dtype == torch.float64 and t.is_contiguous(), \
-        "expected a contiguous float64 CUDA tensor"
+    assert isinstance(t, torch.Tensor) and t.is_cuda and t.dtype in (torch.float64, torch.complex128) and \
+        t.is_contiguous(), "expected a contiguous float64 / complex128 CUDA tensor"
     return C.c_void_p(t.data_ptr())
 
 
@@ -147,7 +150,7 @@ class Operator:
     """One rank's ChFSI context.  Mirrors ``kohnShamDFTOperatorDeviceClass`` for the
     hot path: ``reinit`` == constructor, then HX / HXCheby / XtHX / overlap."""
 
-    def __init__(self, prob, block: int, device: int = 0, use_torch_stream: bool = True):
+    def __init__(self, prob, block: int, device: int = 0, use_torch_stream: bool = True, complex: bool = False):
         import torch
 
         self.lib = load()
@@ -156,7 +159,9 @@ class Operator:
         self.M, self.G, self.n = int(prob.M), int(prob.G), int(prob.n)
         self.device = device
         desc = ProblemDesc(nodes_per_cell=prob.n, cheby_block=block, n_cells=prob.nCells, n_owned=prob.M,
-                           n_ghost=prob.G, n_global_dofs=prob.nGlobalDofs, device=device, reserved=0)
+                           n_ghost=prob.G, n_global_dofs=prob.nGlobalDofs, device=device,
+                           flags=FLAG_COMPLEX if complex else 0)
+        self.complex = bool(complex)
         h = C.c_void_p()
         _check(self.lib.dftfe_b200_create(C.byref(desc), C.byref(h)))
         self.h = h
@@ -223,7 +228,8 @@ class Operator:
     def set_cell_hamiltonian(self, H):
         """H: torch CUDA tensor or numpy array [nCells, n, n] (mem[c,I,J] = H_c(I,J))."""
         if isinstance(H, np.ndarray):
-            Hc = _np(H, np.float64)
+            assert np.iscomplexobj(H) == self.complex, "cell Hamiltonian dtype does not match the context"
+            Hc = _np(H, np.complex128 if self.complex else np.float64)
             _check(self.lib.dftfe_b200_set_cell_hamiltonian_host(self.h, _ptr(Hc)))
         else:
             _check(self.lib.dftfe_b200_set_cell_hamiltonian(self.h, _dptr(H)))

@@ -7,10 +7,11 @@
 //   K5 stridedBlockScale x4            (src/dftOperator/kohnShamDFTOperatorDevice.cc:3790-3859)
 //   K7 combinedDeviceKernel            (src/linAlg/linearAlgebraOperationsDevice.cc:37-64)
 // i.e. for every owned cell c and wavefunction column tile:
-//   Xc[k,:]   = rowIn[row(c,k)] * src[row(c,k), tile]            (gather through the index map)
-//   Yc        = Hm_c * Xc            with Hm_c[i][k] = mem[c*n*n + i*n + k]      (FP64 DMMA)
-//   dst[row(c,i), tile] (first touch) = a*rowA*src + b*rowB*dst + s*rowOut*Yc[i,:]
-//                        (otherwise) += s*rowOut*Yc[i,:]
+//   Xc[k,:]   = src[row(c,k), tile]                               (gather through the index map)
+//   Yc        = A_c * Xc       A_c[i][k] = rowOut*H_c(i,k)*rowIn   (real: dgemm 'N','N' of the reference)
+//                              A_c[i][k] = rowOut*H_c(k,i)*rowIn   (complex: zgemm 'N','T', i.e. H^T)
+//   dst[row(c,i), tile] (first touch) = ca*src + cb*dst + s*Yc[i,:]
+//                        (otherwise) += s*Yc[i,:]
 // Cells of one colour share no row, so the read-modify-write needs no atomics and
 // the summation order is fixed (deterministic, unlike the reference's atomicAdd).
 //
@@ -27,13 +28,21 @@
 // so staging it through shared memory buys nothing); the gathered X tile lives
 // in shared memory with a row pitch of 36 doubles (conflict-free B-fragment
 // reads).
+//
+// Complex (k-point) build: vectors are interleaved (re, im), so a tile of 32 real
+// columns holds 16 complex ones and  Y = (Ar + i Ai) X  is computed with real DMMAs as
+// Y = Ar * X + Ai * X',  X'[k, 2j] = -X[k, 2j+1],  X'[k, 2j+1] = X[k, 2j]:
+// the k loop runs over 2*KS "virtual" k-steps, even ones take Ar and the B fragment as
+// stored, odd ones take Ai and the partner column with the sign of the real part flipped
+// (one integer XOR per fragment).  No split re/im temporaries (the reference needs them
+// around its atomics, matrixVectorProductImplementationsDevice.cc:86-108).
 #include "common.cuh"
 
 namespace dftfe_b200 {
 
 namespace {
 
-constexpr int BT = 32;       // wavefunction columns per CTA tile
+constexpr int BT = 32;       // real wavefunction columns per CTA tile
 constexpr int NT = BT / 8;   // n8 tiles per warp
 constexpr int LDS = BT + 4;  // shared-memory row pitch in doubles ( = 4 mod 16 )
 // row word of the flagged index map: bits 0..29 local row, bit 30 = live (owned and
@@ -52,10 +61,11 @@ __device__ __forceinline__ void epilogue_coeffs(uint32_t word, const EpiloguePar
   }
 }
 
-template <int NODES>
+template <int NODES, bool CPLX = false>
 struct CellCfg {
   static constexpr int MT = (NODES + 7) / 8;  // m8 row tiles
   static constexpr int KS = (NODES + 3) / 4;  // k4 steps
+  static constexpr int KSV = CPLX ? 2 * KS : KS;  // virtual k-steps (complex: Ar / Ai interleaved)
   static constexpr int KPAD = KS * 4;
   static constexpr int WARPS = MT >= 12 ? 12 : (MT >= 8 ? 8 : 4);
   static constexpr int TPW = (MT + WARPS - 1) / WARPS;  // row tiles per warp (max)
@@ -63,7 +73,7 @@ struct CellCfg {
   static constexpr size_t SMEM = (size_t)KPAD * LDS * sizeof(double);
   // per-lane fragment vector (padded so that it is loadable with 16/32-byte vector loads)
   static constexpr int TPWP = TPW <= 1 ? 1 : (TPW <= 2 ? 2 : (TPW <= 4 ? 4 : 8));
-  static constexpr size_t HT_PER_WARP = (size_t)KS * 32 * TPWP;   // doubles
+  static constexpr size_t HT_PER_WARP = (size_t)KSV * 32 * TPWP;      // doubles
   static constexpr size_t HT_PER_CELL = (size_t)WARPS * HT_PER_WARP;  // doubles
 };
 
@@ -91,18 +101,29 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
                : "d"(a), "d"(b));
 }
 
-// H_c (row-major n x n as stored by the reference) -> fragment-major, grouped per MMA warp:
-// Ht[cell][warp][ks][lane][t] = Hm[(warp + t*WARPS)*8 + lane/4][ks*4 + lane%4], zero padded, so a
-// lane fetches the A fragments of all its row tiles for one k-step with ONE 32-byte load
-// (LDG.E.256) and a warp's stream for a cell is one contiguous run.
-// The mass scalings of H~ = M^-1/2 H M^-1/2 are folded in here, once per
-// set_cell_hamiltonian: Ht holds rowOut[row(c,i)] * H_c[i][k] * rowIn[row(c,k)], so the
-// per-degree kernels gather raw rows (pure copies - TMA-able) and scale nothing.
-template <int NODES>
+// B fragments of k-step `ks` for the NT column tiles of a warp.
+//   PARTNER = false: xb = tile + (lane&3)*LDS + (lane>>2), as stored
+//   PARTNER = true : xb = tile + (lane&3)*LDS + ((lane>>2)^1), the other half of the complex pair, with the
+//                    sign bit flipped on lanes that hold a real-part column (sgn mask)
+template <bool PARTNER>
+__device__ __forceinline__ void load_b(const double *xb, unsigned long long sgn, int ks, double (&b)[NT]) {
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt) {
+    const double v = xb[(ks * 4) * LDS + nt * 8];
+    b[nt] = PARTNER ? __longlong_as_double(__double_as_longlong(v) ^ (long long)sgn) : v;
+  }
+}
+
+// H_c (as stored by the reference: mem[c][I][J] = H_c(I,J), complex interleaved for CPLX) -> fragment-major,
+// grouped per MMA warp:  Ht[cell][warp][ksv][lane][t] = A_c[(warp + t*WARPS)*8 + lane/4][k*4 + lane%4],
+// zero padded, so a lane fetches the A fragments of all its row tiles for one k-step with ONE 32-byte load
+// (LDG.E.256) and a warp's stream for a cell is one contiguous run.  The mass scalings of
+// H~ = M^-1/2 H M^-1/2 are folded in here, once per set_cell_hamiltonian.
+template <int NODES, bool CPLX>
 __global__ void retile_H_kernel(const double *__restrict__ H, double *__restrict__ Ht, int64_t nCells,
                                 const uint32_t *__restrict__ cellRows, const double *__restrict__ rowIn,
                                 const double *__restrict__ rowOut) {
-  using C = CellCfg<NODES>;
+  using C = CellCfg<NODES, CPLX>;
   const int64_t total = nCells * (int64_t)C::HT_PER_CELL;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
@@ -111,16 +132,20 @@ __global__ void retile_H_kernel(const double *__restrict__ H, double *__restrict
     r /= C::TPWP;
     const int lane = r % 32;
     r /= 32;
-    const int ks = r % C::KS;
-    r /= C::KS;
+    const int ksv = r % C::KSV;
+    r /= C::KSV;
     const int w = r % C::WARPS;
     const int64_t cell = r / C::WARPS;
+    const int ks = CPLX ? (ksv >> 1) : ksv;
     const int mt = w + t * C::WARPS;
     const int i = (t < C::TPW && mt < C::MT) ? mt * 8 + lane / 4 : NODES;
     const int k = ks * 4 + lane % 4;
     double v = 0.0;
     if (i < NODES && k < NODES) {
-      v = H[cell * (int64_t)NODES * NODES + (int64_t)i * NODES + k];
+      if (CPLX)  // A(i,k) = H_c(k,i): the reference's zgemm uses transB = 'T'
+        v = H[(cell * (int64_t)NODES * NODES + (int64_t)k * NODES + i) * 2 + (ksv & 1)];
+      else
+        v = H[cell * (int64_t)NODES * NODES + (int64_t)i * NODES + k];
       const uint32_t ri = cellRows[cell * NODES + i] & ROW_MASK, rk = cellRows[cell * NODES + k] & ROW_MASK;
       v = rowOut[ri] * v * rowIn[rk];
     }
@@ -128,12 +153,16 @@ __global__ void retile_H_kernel(const double *__restrict__ H, double *__restrict
   }
 }
 
-template <int NODES>
-__global__ void __launch_bounds__(CellCfg<NODES>::THREADS, 1)
+// ---------------------------------------------------------------------------
+// Generic kernel: one CTA per (cell, column tile); any column count / leading dimension;
+// optional extra gather / output scales (the bare HXCheby entry point undoes the folded ones).
+// ---------------------------------------------------------------------------
+template <int NODES, bool CPLX>
+__global__ void __launch_bounds__(CellCfg<NODES, CPLX>::THREADS, 1)
 cell_matvec_kernel(const double *__restrict__ Ht, const uint32_t *__restrict__ cellRows,
                    const int32_t *__restrict__ cells, const double *__restrict__ src,
                    double *__restrict__ dst, int ncols, int ldx, int nColTiles, EpilogueParams ep) {
-  using C = CellCfg<NODES>;
+  using C = CellCfg<NODES, CPLX>;
   extern __shared__ __align__(16) double Xs[];  // [KPAD][LDS]
   __shared__ uint32_t rowsS[NODES];
 
@@ -161,7 +190,7 @@ cell_matvec_kernel(const double *__restrict__ Ht, const uint32_t *__restrict__ c
   }
   __syncthreads();
 
-  // ---- DMMA main loop
+  // ---- DMMA main loop over pairs of (virtual) k-steps
   double acc[C::TPW][NT][2];
 #pragma unroll
   for (int t = 0; t < C::TPW; ++t)
@@ -170,33 +199,40 @@ cell_matvec_kernel(const double *__restrict__ Ht, const uint32_t *__restrict__ c
 
   const double *Hc = Ht + (size_t)cell * C::HT_PER_CELL + (size_t)warp * C::HT_PER_WARP + lane * C::TPWP;
   const double *xb = Xs + (lane & 3) * LDS + (lane >> 2);
+  const double *xbp = Xs + (lane & 3) * LDS + ((lane >> 2) ^ 1);
+  const unsigned long long sgn = ((lane >> 2) & 1) ? 0ull : 0x8000000000000000ull;
 
   double a0[C::TPWP], a1[C::TPWP];
   load_frags<C::TPWP>(Hc, a0);
-  load_frags<C::TPWP>(Hc + (C::KS > 1 ? 32 * C::TPWP : 0), a1);
+  load_frags<C::TPWP>(Hc + (C::KSV > 1 ? 32 * C::TPWP : 0), a1);
 
-  for (int ks = 0; ks < C::KS; ks += 2) {
+  for (int ks = 0; ks < C::KSV; ks += 2) {
     // prefetch A for ks+2, ks+3 (clamped re-reads at the end are harmless)
     double n0[C::TPWP], n1[C::TPWP];
-    load_frags<C::TPWP>(Hc + (size_t)min(ks + 2, C::KS - 1) * 32 * C::TPWP, n0);
-    load_frags<C::TPWP>(Hc + (size_t)min(ks + 3, C::KS - 1) * 32 * C::TPWP, n1);
+    load_frags<C::TPWP>(Hc + (size_t)min(ks + 2, C::KSV - 1) * 32 * C::TPWP, n0);
+    load_frags<C::TPWP>(Hc + (size_t)min(ks + 3, C::KSV - 1) * 32 * C::TPWP, n1);
     {
       double b[NT];
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt) b[nt] = xb[(ks * 4) * LDS + nt * 8];
+      load_b<false>(xb, sgn, CPLX ? (ks >> 1) : ks, b);  // even virtual step: Ar (or real A), B as stored
 #pragma unroll
       for (int t = 0; t < C::TPW; ++t)
+        if (warp + t * C::WARPS < C::MT) {
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) dmma884(acc[t][nt][0], acc[t][nt][1], a0[t], b[nt]);
+          for (int nt = 0; nt < NT; ++nt) dmma884(acc[t][nt][0], acc[t][nt][1], a0[t], b[nt]);
+        }
     }
-    if (ks + 1 < C::KS) {
+    if (ks + 1 < C::KSV) {
       double b[NT];
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt) b[nt] = xb[((ks + 1) * 4) * LDS + nt * 8];
+      if (CPLX)
+        load_b<true>(xbp, sgn, ks >> 1, b);  // odd virtual step: Ai with the partner column
+      else
+        load_b<false>(xb, sgn, ks + 1, b);
 #pragma unroll
       for (int t = 0; t < C::TPW; ++t)
+        if (warp + t * C::WARPS < C::MT) {
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) dmma884(acc[t][nt][0], acc[t][nt][1], a1[t], b[nt]);
+          for (int nt = 0; nt < NT; ++nt) dmma884(acc[t][nt][0], acc[t][nt][1], a1[t], b[nt]);
+        }
     }
 #pragma unroll
     for (int t = 0; t < C::TPWP; ++t) {
@@ -251,7 +287,6 @@ cell_matvec_kernel(const double *__restrict__ Ht, const uint32_t *__restrict__ c
   }
 }
 
-
 // ---------------------------------------------------------------------------
 // Fast path: persistent, warp-specialised version of the kernel above.
 //   * one CTA per SM loops over the (cell, column-tile) items of a colour;
@@ -259,8 +294,8 @@ cell_matvec_kernel(const double *__restrict__ Ht, const uint32_t *__restrict__ c
 //     (cp.async.bulk, one 256-byte row segment each, completion on an mbarrier)
 //     into the other half of a double-buffered shared-memory tile while
 //   * twelve MMA warps run the DMMA k-loop of the current item with a 4-deep
-//     register prefetch of their A fragments and then do the recurrence /
-//     assembly epilogue straight from registers.
+//     register prefetch of their A fragments (one LDG.E.256 per k-step) and then do
+//     the recurrence / assembly epilogue straight from registers.
 // No CTA-wide barrier inside the loop: warps drift, so one warp's epilogue
 // overlaps its SMSP neighbours' DMMAs.
 // ---------------------------------------------------------------------------
@@ -296,39 +331,37 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst, const void *src, uint32_
                : "memory");
 }
 
-template <int NODES>
+template <int NODES, bool CPLX>
 struct PersistCfg {
-  using C = CellCfg<NODES>;
+  using C = CellCfg<NODES, CPLX>;
   static constexpr int MMA_WARPS = C::WARPS;
   static constexpr int THREADS = (MMA_WARPS + 1) * 32;  // + one producer warp
   static constexpr size_t XBUF = (size_t)C::KPAD * LDS;  // doubles per buffer
   static constexpr size_t SMEM = 2 * XBUF * sizeof(double) + 2 * NODES * sizeof(uint32_t) + 4 * sizeof(uint64_t);
-#ifndef DB_DIAG
-#define DB_DIAG 0
-#endif
-#ifndef DB_APF
-#define DB_APF 4
-#endif
-  static constexpr int APF = DB_APF;  // A-fragment prefetch depth in k-steps
+  static constexpr int APF = 4;  // A-fragment prefetch depth in (virtual) k-steps
 };
 
-
-template <int NODES, int NTILE>
+// The row-tile count NTILE (TPW or TPW-1) is a compile-time constant per instantiation because a
+// predicated-off DMMA still occupies its tensor-pipe slot.
+template <int NODES, bool CPLX, int NTILE>
 __device__ __forceinline__ void mma_warp_items(const double *__restrict__ Ht, const int32_t *__restrict__ cells,
                                                int nItems, const double *__restrict__ src,
                                                double *__restrict__ dst, int ldx, int nColTiles,
                                                const EpilogueParams &ep, const double *Xs, const uint32_t *rowsS,
                                                uint64_t *full, uint64_t *empty, int warp, int lane) {
-  using C = CellCfg<NODES>;
-  using P = PersistCfg<NODES>;
+  using C = CellCfg<NODES, CPLX>;
+  using P = PersistCfg<NODES, CPLX>;
+  static_assert(P::APF % 2 == 0, "the parity of a virtual k-step must be that of its ring slot");
   const double *xb0 = Xs + (lane & 3) * LDS + (lane >> 2);
+  const double *xbp0 = Xs + (lane & 3) * LDS + ((lane >> 2) ^ 1);
+  const unsigned long long sgn = ((lane >> 2) & 1) ? 0ull : 0x8000000000000000ull;
   // A prefetch ring; primed for the first item here, re-primed for the next item before each epilogue
   double a[P::APF][C::TPWP];
   auto prime = [&](int item) {
     const int cell = cells[item / nColTiles];
     const double *Hc = Ht + (size_t)cell * C::HT_PER_CELL + (size_t)warp * C::HT_PER_WARP + lane * C::TPWP;
 #pragma unroll
-    for (int s = 0; s < P::APF; ++s) load_frags<C::TPWP>(Hc + (size_t)min(s, C::KS - 1) * 32 * C::TPWP, a[s]);
+    for (int s = 0; s < P::APF; ++s) load_frags<C::TPWP>(Hc + (size_t)min(s, C::KSV - 1) * 32 * C::TPWP, a[s]);
   };
   if ((int)blockIdx.x < nItems) prime(blockIdx.x);
   int it = 0;
@@ -339,6 +372,7 @@ __device__ __forceinline__ void mma_warp_items(const double *__restrict__ Ht, co
     const int col0 = (item % nColTiles) * BT;
     const double *Hc = Ht + (size_t)cell * C::HT_PER_CELL + (size_t)warp * C::HT_PER_WARP + lane * C::TPWP;
     const double *xb = xb0 + buf * P::XBUF;
+    const double *xbp = xbp0 + buf * P::XBUF;
 
     double acc[NTILE][NT][2];
 #pragma unroll
@@ -348,27 +382,29 @@ __device__ __forceinline__ void mma_warp_items(const double *__restrict__ Ht, co
 
     mbar_wait(&full[buf], ph);
 
-    int ks = 0;
-    for (; ks + P::APF <= C::KS; ks += P::APF) {
+    int ks = 0;  // virtual k-step; advances by APF (even), so the parity of ks+s is that of s
+    for (; ks + P::APF <= C::KSV; ks += P::APF) {
 #pragma unroll
       for (int s = 0; s < P::APF; ++s) {
         double b[NT];
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) b[nt] = xb[((ks + s) * 4) * LDS + nt * 8];
+        if (CPLX && (s & 1))
+          load_b<true>(xbp, sgn, (ks + s) >> 1, b);
+        else
+          load_b<false>(xb, sgn, CPLX ? ((ks + s) >> 1) : (ks + s), b);
 #pragma unroll
         for (int t = 0; t < NTILE; ++t)
 #pragma unroll
           for (int nt = 0; nt < NT; ++nt) dmma884(acc[t][nt][0], acc[t][nt][1], a[s][t], b[nt]);
-#if DB_DIAG != 1 && DB_DIAG != 4
-        if (ks + s + P::APF < C::KS) load_frags<C::TPWP>(Hc + (size_t)(ks + s + P::APF) * 32 * C::TPWP, a[s]);
-#endif
+        if (ks + s + P::APF < C::KSV) load_frags<C::TPWP>(Hc + (size_t)(ks + s + P::APF) * 32 * C::TPWP, a[s]);
       }
     }
 #pragma unroll
-    for (int s = 0; s < C::KS % P::APF; ++s) {
+    for (int s = 0; s < C::KSV % P::APF; ++s) {
       double b[NT];
-#pragma unroll
-      for (int nt = 0; nt < NT; ++nt) b[nt] = xb[((ks + s) * 4) * LDS + nt * 8];
+      if (CPLX && (s & 1))
+        load_b<true>(xbp, sgn, (ks + s) >> 1, b);
+      else
+        load_b<false>(xb, sgn, CPLX ? ((ks + s) >> 1) : (ks + s), b);
 #pragma unroll
       for (int t = 0; t < NTILE; ++t)
 #pragma unroll
@@ -399,12 +435,6 @@ __device__ __forceinline__ void mma_warp_items(const double *__restrict__ Ht, co
         epilogue_coeffs(fr[t], ep, ca, cb);
         double *drow = dst + (size_t)r * ldx + col0 + (lane & 3) * 2;
         const double *srow = src + (size_t)r * ldx + col0 + (lane & 3) * 2;
-#if DB_DIAG == 2 || DB_DIAG == 4
-        double sum = 0.0;
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) sum += acc[t][nt][0] + acc[t][nt][1];
-        if (sum == 1.2345e300) drow[0] = so * sum + ca + cb + srow[0];
-#else
         double2 d[NT], sv[NT];
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
@@ -418,19 +448,18 @@ __device__ __forceinline__ void mma_warp_items(const double *__restrict__ Ht, co
           o.y = so * acc[t][nt][1] + ca * sv[nt].y + cb * d[nt].y;
           *reinterpret_cast<double2 *>(drow + nt * 8) = o;
         }
-#endif
       }
     }
   }
 }
 
-template <int NODES>
-__global__ void __launch_bounds__(PersistCfg<NODES>::THREADS, 1)
+template <int NODES, bool CPLX>
+__global__ void __launch_bounds__(PersistCfg<NODES, CPLX>::THREADS, 1)
 cell_matvec_persistent_kernel(const double *__restrict__ Ht, const uint32_t *__restrict__ cellRows,
                               const int32_t *__restrict__ cells, int nItems, const double *__restrict__ src,
                               double *__restrict__ dst, int ldx, int nColTiles, EpilogueParams ep) {
-  using C = CellCfg<NODES>;
-  using P = PersistCfg<NODES>;
+  using C = CellCfg<NODES, CPLX>;
+  using P = PersistCfg<NODES, CPLX>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *Xs = reinterpret_cast<double *>(smem_raw);                                  // [2][KPAD][LDS]
   uint32_t *rowsS = reinterpret_cast<uint32_t *>(smem_raw + 2 * P::XBUF * sizeof(double));  // [2][NODES]
@@ -483,10 +512,6 @@ cell_matvec_persistent_kernel(const double *__restrict__ Ht, const uint32_t *__r
         if (k < NODES) rs[k] = myRows[j];
       }
       __syncwarp();
-#if DB_DIAG == 3 || DB_DIAG == 4
-      if (lane == 0) mbar_arrive(&full[buf]);
-      continue;
-#endif
       if (lane == 0) mbar_arrive_expect_tx(&full[buf], (uint32_t)(NODES * BT * sizeof(double)));
       __syncwarp();
 #pragma unroll
@@ -498,15 +523,13 @@ cell_matvec_persistent_kernel(const double *__restrict__ Ht, const uint32_t *__r
       }
     }
   } else {
-    // ===== MMA warps: the row-tile count (TPW or TPW-1) is a compile-time constant per branch,
-    // because a predicated-off DMMA still occupies its tensor-pipe slot =====
     constexpr int FULL_WARPS = C::MT - (C::TPW - 1) * C::WARPS;  // warps that own TPW tiles
     if (warp < FULL_WARPS)
-      mma_warp_items<NODES, C::TPW>(Ht, cells, nItems, src, dst, ldx, nColTiles, ep, Xs, rowsS, full, empty, warp,
-                                    lane);
+      mma_warp_items<NODES, CPLX, C::TPW>(Ht, cells, nItems, src, dst, ldx, nColTiles, ep, Xs, rowsS, full, empty,
+                                          warp, lane);
     else if (C::TPW > 1)
-      mma_warp_items<NODES, (C::TPW > 1 ? C::TPW - 1 : 1)>(Ht, cells, nItems, src, dst, ldx, nColTiles, ep, Xs, rowsS,
-                                                          full, empty, warp, lane);
+      mma_warp_items<NODES, CPLX, (C::TPW > 1 ? C::TPW - 1 : 1)>(Ht, cells, nItems, src, dst, ldx, nColTiles, ep,
+                                                                 Xs, rowsS, full, empty, warp, lane);
   }
 }
 
@@ -529,24 +552,21 @@ __global__ void orphan_first_touch_kernel(const uint32_t *__restrict__ rows, int
   }
 }
 
-template <int NODES>
-int launch_impl(dftfe_b200_ctx *ctx, const double *src, double *dst, int ncols, int ldx,
-                const EpilogueParams &ep) {
-  using C = CellCfg<NODES>;
+template <int NODES, bool CPLX>
+int launch_impl2(dftfe_b200_ctx *ctx, const double *src, double *dst, int ncols, int ldx,
+                 const EpilogueParams &ep) {
+  using C = CellCfg<NODES, CPLX>;
+  using P = PersistCfg<NODES, CPLX>;
   static bool attr_set = false;
   if (!attr_set) {
-    DB_CUDA(cudaFuncSetAttribute(cell_matvec_kernel<NODES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    DB_CUDA(cudaFuncSetAttribute(cell_matvec_kernel<NODES, CPLX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)C::SMEM));
+    if (P::SMEM <= 227 * 1024)
+      DB_CUDA(cudaFuncSetAttribute(cell_matvec_persistent_kernel<NODES, CPLX>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::SMEM));
     attr_set = true;
   }
   const int nColTiles = (ncols + BT - 1) / BT;
-  using P = PersistCfg<NODES>;
-  static bool attr2_set = false;
-  if (!attr2_set && P::SMEM <= 227 * 1024) {
-    DB_CUDA(cudaFuncSetAttribute(cell_matvec_persistent_kernel<NODES>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)P::SMEM));
-    attr2_set = true;
-  }
   // fast path needs full 32-column tiles, 16-byte aligned row segments and no extra gather scale
   const bool fast = (P::SMEM <= 227 * 1024) && (ncols % BT == 0) && (ldx % 2 == 0) && ep.rowIn == nullptr &&
                     ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
@@ -558,11 +578,11 @@ int launch_impl(dftfe_b200_ctx *ctx, const double *src, double *dst, int ncols, 
     const int nItems = nCellsK * nColTiles;
     if (fast) {
       const int grid = std::min(nItems, ctx->num_sms);
-      cell_matvec_persistent_kernel<NODES><<<grid, P::THREADS, P::SMEM, ctx->stream>>>(
+      cell_matvec_persistent_kernel<NODES, CPLX><<<grid, P::THREADS, P::SMEM, ctx->stream>>>(
           ctx->Htiled.p, ctx->cellRowsFlagged.p, ctx->colourCells.p + ctx->colourStart_h[k], nItems, src, dst, ldx,
           nColTiles, ep);
     } else {
-      cell_matvec_kernel<NODES><<<nItems, C::THREADS, C::SMEM, ctx->stream>>>(
+      cell_matvec_kernel<NODES, CPLX><<<nItems, C::THREADS, C::SMEM, ctx->stream>>>(
           ctx->Htiled.p, ctx->cellRowsFlagged.p, ctx->colourCells.p + ctx->colourStart_h[k], src, dst, ncols, ldx,
           nColTiles, ep);
     }
@@ -572,13 +592,23 @@ int launch_impl(dftfe_b200_ctx *ctx, const double *src, double *dst, int ncols, 
 }
 
 template <int NODES>
+int launch_impl(dftfe_b200_ctx *ctx, const double *src, double *dst, int ncols, int ldx,
+                const EpilogueParams &ep) {
+  return ctx->cplx ? launch_impl2<NODES, true>(ctx, src, dst, ncols, ldx, ep)
+                   : launch_impl2<NODES, false>(ctx, src, dst, ncols, ldx, ep);
+}
+
+template <int NODES>
 int retile_impl(dftfe_b200_ctx *ctx, const double *H_d) {
-  using C = CellCfg<NODES>;
-  DB_TRY(ctx->Htiled.alloc((size_t)ctx->nC * C::HT_PER_CELL));
+  const size_t perCell = ctx->cplx ? CellCfg<NODES, true>::HT_PER_CELL : CellCfg<NODES, false>::HT_PER_CELL;
+  DB_TRY(ctx->Htiled.alloc((size_t)ctx->nC * perCell));
   ctx->launches += 1;
-  retile_H_kernel<NODES><<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(H_d, ctx->Htiled.p, ctx->nC,
-                                                                    ctx->cellRowsFlagged.p, ctx->rowIn.p,
-                                                                    ctx->rowOut.p);
+  if (ctx->cplx)
+    retile_H_kernel<NODES, true><<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(
+        H_d, ctx->Htiled.p, ctx->nC, ctx->cellRowsFlagged.p, ctx->rowIn.p, ctx->rowOut.p);
+  else
+    retile_H_kernel<NODES, false><<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(
+        H_d, ctx->Htiled.p, ctx->nC, ctx->cellRowsFlagged.p, ctx->rowIn.p, ctx->rowOut.p);
   DB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -603,6 +633,7 @@ int cell_kernel_supported(int n) {
   return n == 8 || n == 27 || n == 64 || n == 125 || n == 216 || n == 343 || n == 512;
 }
 
+// H_d: real n x n doubles per cell, or complex interleaved (2 n x n doubles) for a complex context
 int retile_cell_hamiltonian(dftfe_b200_ctx *ctx, const double *H_d) {
   DB_CHECK(ctx->have_map && ctx->have_mass,
            "set_cell_hamiltonian needs set_index_map, set_constraints and set_mass first (the M^-1/2 scalings are "
@@ -610,6 +641,7 @@ int retile_cell_hamiltonian(dftfe_b200_ctx *ctx, const double *H_d) {
   DB_DISPATCH_NODES(ctx->n, retile_impl, ctx, H_d);
 }
 
+// ncols / ldx in REAL columns (a complex context passes 2 x its complex column count)
 int launch_cell_matvec(dftfe_b200_ctx *ctx, const double *src, double *dst, int ncols, int ldx,
                        const EpilogueParams &ep) {
   DB_CHECK(ctx->have_map && ctx->have_H, "cell matvec needs set_index_map and set_cell_hamiltonian first");

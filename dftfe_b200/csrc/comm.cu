@@ -124,8 +124,8 @@ static int64_t target_offset(const dftfe_b200_ctx *c, int targetRank) {
 int ghost_update(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx) {
   if (ctx->nranks == 1) return 0;
   DB_CHECK(ctx->nccl || loopback_of(ctx), "ghost exchange needs comm_init (NCCL) or a loopback group");
-  DB_TRY(ctx->sendBuf.alloc((size_t)ctx->nSend * ctx->B));
-  DB_TRY(ctx->recvBuf.alloc((size_t)std::max<int64_t>(ctx->G, ctx->nSend) * ctx->B));
+  DB_TRY(ctx->sendBuf.alloc((size_t)ctx->nSend * ctx->B * ctx->cm));
+  DB_TRY(ctx->recvBuf.alloc((size_t)std::max<int64_t>(ctx->G, ctx->nSend) * ctx->B * ctx->cm));
   DB_TRY(launch_pack_rows(ctx, x, ncols, ldx, ctx->nSend, ctx->sendRows.p, ctx->sendBuf.p));
   const bool direct = (ldx == ncols);
   double *ghostBase = direct ? x + (size_t)ctx->M * ldx : ctx->recvBuf.p;
@@ -164,8 +164,8 @@ int ghost_update(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx) {
 int ghost_accumulate(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx, const double *rowScale) {
   if (ctx->nranks == 1) return 0;
   DB_CHECK(ctx->nccl || loopback_of(ctx), "ghost exchange needs comm_init (NCCL) or a loopback group");
-  DB_TRY(ctx->sendBuf.alloc((size_t)std::max<int64_t>(ctx->G, ctx->nSend) * ctx->B));
-  DB_TRY(ctx->recvBuf.alloc((size_t)std::max<int64_t>(ctx->G, ctx->nSend) * ctx->B));
+  DB_TRY(ctx->sendBuf.alloc((size_t)std::max<int64_t>(ctx->G, ctx->nSend) * ctx->B * ctx->cm));
+  DB_TRY(ctx->recvBuf.alloc((size_t)std::max<int64_t>(ctx->G, ctx->nSend) * ctx->B * ctx->cm));
   const bool direct = (ldx == ncols);
   double *ghostBase = direct ? x + (size_t)ctx->M * ldx : ctx->sendBuf.p;
   if (!direct) DB_TRY(launch_copy_rows(ctx, x, ncols, ldx, ctx->M, ctx->G, ctx->sendBuf.p, 1));

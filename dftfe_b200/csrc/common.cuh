@@ -150,6 +150,8 @@ struct EpilogueParams {
 struct dftfe_b200_ctx {
   dftfe_b200_problem_desc desc{};
   int n = 0;          // nodes per cell
+  bool cplx = false;  // T = complex<double> (k-point build): vectors are interleaved (re, im)
+  int cm = 1;         // real columns per wavefunction column (1 real, 2 complex)
   int B = 0;          // cheby block
   int64_t nC = 0, M = 0, G = 0;
   cudaStream_t stream = nullptr;

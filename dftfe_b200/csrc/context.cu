@@ -120,6 +120,8 @@ int dftfe_b200_create(const dftfe_b200_problem_desc *desc, dftfe_b200_ctx **out)
   ctx->nC = desc->n_cells;
   ctx->M = desc->n_owned;
   ctx->G = desc->n_ghost;
+  ctx->cplx = (desc->flags & DFTFE_B200_FLAG_COMPLEX) != 0;
+  ctx->cm = ctx->cplx ? 2 : 1;
   ctx->num_sms = prop.multiProcessorCount;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cublasCreate(&ctx->cublas) != CUBLAS_STATUS_SUCCESS ||
@@ -426,6 +428,10 @@ int dftfe_b200_set_nonlocal(dftfe_b200_ctx *ctx, int32_t n_atoms, const int32_t 
                             const double *C_h, int32_t p_max) {
   DB_CTX(ctx);
   DB_CHECK(n_atoms >= 0 && n_entries >= 0 && p_max >= 0, "set_nonlocal: negative size");
+  if (ctx->cplx) {
+    set_error("set_nonlocal: complex (k-point dependent) projectors are not provided yet");
+    return DFTFE_B200_ERR_UNSUPPORTED;
+  }
   return nonlocal_setup(ctx, n_atoms, n_proj_per_atom_h, V_h, n_entries, entry_cell_h, entry_atom_h, C_h, p_max);
 }
 
@@ -440,7 +446,7 @@ int dftfe_b200_set_cell_hamiltonian(dftfe_b200_ctx *ctx, const double *H_d) {
 
 int dftfe_b200_set_cell_hamiltonian_host(dftfe_b200_ctx *ctx, const double *H_h) {
   DB_CTX(ctx);
-  const size_t count = (size_t)ctx->nC * ctx->n * ctx->n;
+  const size_t count = (size_t)ctx->nC * ctx->n * ctx->n * ctx->cm;
   DB_TRY(ctx->Hstage.upload(H_h, count, ctx->stream));
   int rc = dftfe_b200_set_cell_hamiltonian(ctx, ctx->Hstage.p);
   ctx->Hstage.release();
@@ -449,27 +455,27 @@ int dftfe_b200_set_cell_hamiltonian_host(dftfe_b200_ctx *ctx, const double *H_h)
 
 int dftfe_b200_update_ghost_values(dftfe_b200_ctx *ctx, double *x_d, int32_t ncols) {
   DB_CTX(ctx);
-  return ghost_update(ctx, x_d, ncols, ncols);
+  return ghost_update(ctx, x_d, ncols * ctx->cm, ncols * ctx->cm);
 }
 int dftfe_b200_accumulate_add_locally_owned(dftfe_b200_ctx *ctx, double *x_d, int32_t ncols) {
   DB_CTX(ctx);
-  return ghost_accumulate(ctx, x_d, ncols, ncols, nullptr);
+  return ghost_accumulate(ctx, x_d, ncols * ctx->cm, ncols * ctx->cm, nullptr);
 }
 int dftfe_b200_zero_out_ghosts(dftfe_b200_ctx *ctx, double *x_d, int32_t ncols) {
   DB_CTX(ctx);
-  return ghost_zero(ctx, x_d, ncols, ncols);
+  return ghost_zero(ctx, x_d, ncols * ctx->cm, ncols * ctx->cm);
 }
 int dftfe_b200_constraints_distribute(dftfe_b200_ctx *ctx, double *x_d, int32_t ncols) {
   DB_CTX(ctx);
-  return launch_distribute(ctx, x_d, ncols, ncols, nullptr);
+  return launch_distribute(ctx, x_d, ncols * ctx->cm, ncols * ctx->cm, nullptr);
 }
 int dftfe_b200_constraints_distribute_slave_to_master(dftfe_b200_ctx *ctx, double *x_d, int32_t ncols) {
   DB_CTX(ctx);
-  return launch_slave_to_master(ctx, x_d, ncols, ncols, nullptr);
+  return launch_slave_to_master(ctx, x_d, ncols * ctx->cm, ncols * ctx->cm, nullptr);
 }
 int dftfe_b200_constraints_set_zero(dftfe_b200_ctx *ctx, double *x_d, int32_t ncols) {
   DB_CTX(ctx);
-  return launch_set_zero_rows(ctx, x_d, ncols, ncols);
+  return launch_set_zero_rows(ctx, x_d, ncols * ctx->cm, ncols * ctx->cm);
 }
 
 int dftfe_b200_get_colouring(dftfe_b200_ctx *ctx, int32_t *n_colours_out, int32_t *cell_colour_out_h) {

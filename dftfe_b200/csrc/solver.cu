@@ -18,6 +18,7 @@ namespace dftfe_b200 {
 static int fused_apply_impl(dftfe_b200_ctx *ctx, double *src, double *dst, int ncols, double a, double b,
                             double s, const double *rowB) {
   DB_CHECK(ctx->have_mass, "set_mass must be called before applying the operator");
+  ncols *= ctx->cm;  // real columns from here on (complex vectors are interleaved re/im)
   const int ldx = ncols;
   DB_TRY(ghost_update(ctx, src, ncols, ldx));
   DB_TRY(launch_distribute(ctx, src, ncols, ldx, ctx->invSqrtM.p));
@@ -52,17 +53,19 @@ int op_hx(dftfe_b200_ctx *ctx, double *src, double *dst, int ncols, int scaleFla
                           scaleFlag ? nullptr : ctx->invSqrtM.p));
   // src side effects of the reference: constrained rows end at 0 (x M^1/2 = 0), ghosts zeroed;
   // without unscaling the caller sees scalar * M^-1/2 * src.
+  const int nr = ncols * ctx->cm;
   if (doUnscale) {
-    DB_TRY(launch_set_zero_rows(ctx, src, ncols, ncols));
+    DB_TRY(launch_set_zero_rows(ctx, src, nr, nr));
   } else {
     // (constrained rows keep the distributed, scaled values exactly as the reference leaves them)
-    DB_TRY(launch_row_scale(ctx, src, ctx->M, ncols, ncols, scalar, ctx->rowIn.p));
+    DB_TRY(launch_row_scale(ctx, src, ctx->M, nr, nr, scalar, ctx->rowIn.p));
   }
   return 0;
 }
 
 // operatorDFTDeviceClass::HXCheby, FP64 (kohnShamDFTOperatorDevice.cc:3874-3997): dst += H src
 int op_hx_cheby(dftfe_b200_ctx *ctx, double *src, double *dst, int ncols) {
+  ncols *= ctx->cm;
   const int ldx = ncols;
   DB_TRY(ghost_update(ctx, src, ncols, ldx));
   DB_TRY(launch_distribute(ctx, src, ncols, ldx, nullptr));
@@ -105,8 +108,8 @@ static int cheb_filter_impl(dftfe_b200_ctx *ctx, double *x_d, double *y_d, int n
   }
   if (Y != x_d) {
     ctx->launches += 1;
-    DB_CUDA(cudaMemcpyAsync(x_d, Y, (size_t)(ctx->M + ctx->G) * ncols * sizeof(double), cudaMemcpyDeviceToDevice,
-                            ctx->stream));
+    DB_CUDA(cudaMemcpyAsync(x_d, Y, (size_t)(ctx->M + ctx->G) * ncols * ctx->cm * sizeof(double),
+                            cudaMemcpyDeviceToDevice, ctx->stream));
   }
   return 0;
 }
@@ -188,8 +191,8 @@ __global__ void scale_copy_kernel(double *__restrict__ y, const double *__restri
 }  // namespace
 
 static int ensure_block_scratch(dftfe_b200_ctx *ctx) {
-  DB_TRY(ctx->blockX.alloc((size_t)(ctx->M + ctx->G) * ctx->B));
-  DB_TRY(ctx->blockY.alloc((size_t)(ctx->M + ctx->G) * ctx->B));
+  DB_TRY(ctx->blockX.alloc((size_t)(ctx->M + ctx->G) * ctx->B * ctx->cm));
+  DB_TRY(ctx->blockY.alloc((size_t)(ctx->M + ctx->G) * ctx->B * ctx->cm));
   return 0;
 }
 
@@ -525,11 +528,12 @@ static int filter_all_impl(dftfe_b200_ctx *ctx, double *X, int N, int m, double 
   const int B = std::min(ctx->B, N);
   DB_CHECK(N % B == 0, "number of wavefunctions (%d) must be a multiple of the Chebyshev block size (%d)", N, B);
   DB_TRY(ensure_block_scratch(ctx));
+  const int cm = ctx->cm;
   for (int j = 0; j < N; j += B) {
-    DB_TRY(launch_block_copy_from_full(ctx, X, N, j, ctx->blockX.p, B, ctx->M, inScale));
-    DB_TRY(ghost_zero(ctx, ctx->blockX.p, B, B));
+    DB_TRY(launch_block_copy_from_full(ctx, X, N * cm, j * cm, ctx->blockX.p, B * cm, ctx->M, inScale));
+    DB_TRY(ghost_zero(ctx, ctx->blockX.p, B * cm, B * cm));
     DB_TRY(cheb_filter_impl(ctx, ctx->blockX.p, ctx->blockY.p, B, m, a, b, a0));
-    DB_TRY(launch_block_copy_to_full(ctx, X, N, j, ctx->blockX.p, B, ctx->M, nullptr));
+    DB_TRY(launch_block_copy_to_full(ctx, X, N * cm, j * cm, ctx->blockX.p, B * cm, ctx->M, nullptr));
   }
   return 0;
 }
@@ -540,7 +544,8 @@ static int filter_all_impl(dftfe_b200_ctx *ctx, double *X, int N, int m, double 
 static int filter_all_host_impl(dftfe_b200_ctx *ctx, double *X_h, int N, int m, double a, double b, double a0) {
   const int B = std::min(ctx->B, N);
   DB_CHECK(N % B == 0, "number of wavefunctions (%d) must be a multiple of the Chebyshev block size (%d)", N, B);
-  const size_t blk = (size_t)(ctx->M + ctx->G) * B;
+  const int cm = ctx->cm;
+  const size_t blk = (size_t)(ctx->M + ctx->G) * B * cm;
   DB_TRY(ctx->blockX.alloc(blk));
   DB_TRY(ctx->blockX2.alloc(blk));
   DB_TRY(ctx->blockY.alloc(blk));
@@ -565,16 +570,18 @@ static int filter_all_host_impl(dftfe_b200_ctx *ctx, double *X_h, int N, int m, 
     for (int i = 0; i < nb; ++i) {
       double *buf = (i & 1) ? ctx->blockX2.p : ctx->blockX.p;
       if (i >= 2) DB_CUDA(cudaStreamWaitEvent(ctx->copyIn, evOut[i - 2], 0));  // buffer free again
-      DB_CUDA(cudaMemcpy2DAsync(buf, (size_t)B * sizeof(double), X_h + (size_t)i * B, (size_t)N * sizeof(double),
-                                (size_t)B * sizeof(double), (size_t)ctx->M, cudaMemcpyHostToDevice, ctx->copyIn));
+      DB_CUDA(cudaMemcpy2DAsync(buf, (size_t)B * cm * sizeof(double), X_h + (size_t)i * B * cm,
+                                (size_t)N * cm * sizeof(double), (size_t)B * cm * sizeof(double), (size_t)ctx->M,
+                                cudaMemcpyHostToDevice, ctx->copyIn));
       DB_CUDA(cudaEventRecord(evIn[i], ctx->copyIn));
       DB_CUDA(cudaStreamWaitEvent(ctx->stream, evIn[i], 0));
-      DB_TRY(ghost_zero(ctx, buf, B, B));
+      DB_TRY(ghost_zero(ctx, buf, B * cm, B * cm));
       DB_TRY(cheb_filter_impl(ctx, buf, ctx->blockY.p, B, m, a, b, a0));
       DB_CUDA(cudaEventRecord(evComp[i], ctx->stream));
       DB_CUDA(cudaStreamWaitEvent(ctx->copyOut, evComp[i], 0));
-      DB_CUDA(cudaMemcpy2DAsync(X_h + (size_t)i * B, (size_t)N * sizeof(double), buf, (size_t)B * sizeof(double),
-                                (size_t)B * sizeof(double), (size_t)ctx->M, cudaMemcpyDeviceToHost, ctx->copyOut));
+      DB_CUDA(cudaMemcpy2DAsync(X_h + (size_t)i * B * cm, (size_t)N * cm * sizeof(double), buf,
+                                (size_t)B * cm * sizeof(double), (size_t)B * cm * sizeof(double), (size_t)ctx->M,
+                                cudaMemcpyDeviceToHost, ctx->copyOut));
       DB_CUDA(cudaEventRecord(evOut[i], ctx->copyOut));
     }
     // the call returns with the result visible to work queued on the context stream

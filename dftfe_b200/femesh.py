@@ -117,6 +117,12 @@ class ReferenceCell:
             + np.kron(M1, np.kron(K1, M1))
             + np.kron(K1, np.kron(M1, M1))
         )
+        # consistent mass and first-derivative matrices for the k-point terms
+        # (hamiltonianMatrixCalculatorFlattenedDevice.cc:259-278): G_d[I,J] = int dN_I/dx_d N_J
+        self.D1 = (dphi.T * self.wq) @ phi
+        D1 = self.D1
+        self.M3c = np.kron(M1, np.kron(M1, M1))
+        self.G3 = [np.kron(M1, np.kron(M1, D1)), np.kron(M1, np.kron(D1, M1)), np.kron(D1, np.kron(M1, M1))]
         wl = self.wgll * (h / 2.0)
         self.mass_gll = np.kron(wl, np.kron(wl, wl))  # diagonal GLL mass per node
         # node offsets inside the cell (physical units), lexicographic
@@ -466,6 +472,17 @@ class GlobalMesh:
                                 np.concatenate(Cs), pmax)
         return NonLocalData(len(atoms_xyz), n_proj, V, np.zeros(0, np.int32), np.zeros(0, np.int32),
                             np.zeros((0, ref.n, pmax)), pmax)
+
+    def cell_hamiltonians_kpoint(self, cells: np.ndarray, potential: Optional[Callable], kpoint,
+                                 vquad: str = "gauss") -> np.ndarray:
+        """Complex cell matrices of a k-point (hamiltonianMatrixCalculatorFlattenedDevice.cc:259-278):
+        H_c(I,J) = 1/2 K + V + 1/2 |k|^2 int N_I N_J  -  i sum_d k_d int dN_I/dx_d N_J , complex128[nc, n, n]."""
+        ref = self.ref
+        k = np.asarray(kpoint, dtype=np.float64)
+        Hr = self.cell_hamiltonians(cells, potential, vquad)
+        Hr += 0.5 * float(k @ k) * ref.M3c
+        Hi = -(k[0] * ref.G3[0] + k[1] * ref.G3[1] + k[2] * ref.G3[2])
+        return Hr + 1j * Hi[None, :, :]
 
     def cell_hamiltonians(self, cells: np.ndarray, potential: Optional[Callable],
                           vquad: str = "gauss", out: Optional[np.ndarray] = None) -> np.ndarray:

@@ -61,8 +61,14 @@ typedef struct {
   int64_t n_ghost;         /* G: ghost DoFs                                     */
   int64_t n_global_dofs;   /* size of the global vector (Lanczos bLow heuristic) */
   int32_t device;          /* CUDA device ordinal                               */
-  int32_t reserved;
+  int32_t flags;           /* DFTFE_B200_FLAG_* bits                            */
 } dftfe_b200_problem_desc;
+
+/* T = std::complex<double> (the reference's USE_COMPLEX build, include/dftfeDataTypes.h:38-48): every
+ * multivector / X / H / S / Q pointer then addresses interleaved (re, im) pairs and column counts are
+ * complex columns.  The operator applied is the reference's conjugate convention (zgemm with transB = 'T',
+ * matrixVectorProductImplementationsDevice.cc:60-62). */
+#define DFTFE_B200_FLAG_COMPLEX 1
 
 /* Knobs of solve(); restates the dftParameters members the hot path reads
  * (utils/dftParameters.cc). */

@@ -474,7 +474,7 @@ class GlibcRand:
         return self._next_raw() >> 1
 
 
-def lanczos_bounds(ranks, block: int = 1, iterations: int = 20, reproducible: bool = False):
+def lanczos_bounds(ranks, block: int = 1, iterations: int = 20, reproducible: bool = False, dtype=np.float64):
     """src/linAlg/linearAlgebraOperationsDevice.cc:340-527: 20-step Lanczos with a
     ``rand()`` start vector per rank, constrained rows zeroed, returns
     (floor(lambda_min), ceil(lambda_max + |f|/10))."""
@@ -483,12 +483,12 @@ def lanczos_bounds(ranks, block: int = 1, iterations: int = 20, reproducible: bo
     v = []
     for r, rp in enumerate(ranks):
         g = GlibcRand(r)
-        x = np.zeros((rp.M + rp.G, 1))
+        x = np.zeros((rp.M + rp.G, 1), dtype=dtype)
         x[:rp.M, 0] = [g.rand() / GlibcRand.RAND_MAX for _ in range(rp.M)]
         set_zero(rp, x)
         x[rp.M:] = 0
         v.append(x)
-    nrm = math.sqrt(sum(float(np.sum(x[:rp.M] ** 2)) for rp, x in zip(ranks, v)))
+    nrm = math.sqrt(sum(float(np.sum(np.abs(x[:rp.M]) ** 2)) for rp, x in zip(ranks, v)))
     for x in v:
         x /= nrm
 
@@ -498,8 +498,8 @@ def lanczos_bounds(ranks, block: int = 1, iterations: int = 20, reproducible: bo
         HX(ranks, src, dst, False, 1.0)
         return dst
 
-    def dot(a, b):
-        return sum(float(np.sum(x[:rp.M] * y[:rp.M])) for rp, x, y in zip(ranks, a, b))
+    def dot(a, b):  # <b, a>; real part (H~ is Hermitian so the imaginary part is rounding noise)
+        return sum(float(np.sum((x[:rp.M] * np.conj(y[:rp.M])).real)) for rp, x, y in zip(ranks, a, b))
 
     f = apply(v)
     alpha = dot(f, v)

@@ -5,11 +5,14 @@ from dftfe_b200.femesh import build_mesh, gaussian_wells_potential
 
 
 def make_problem(p, ncells, h=1.0, periodic=(True, True, True), nranks=1, vquad="gauss", potential=True,
-                 extra_constraints=None, rank_grid=None, n_atoms=0, n_proj=4, rc=1.6):
+                 extra_constraints=None, rank_grid=None, n_atoms=0, n_proj=4, rc=1.6, kpoint=None):
     mesh = build_mesh(p, ncells, h, periodic=periodic, nranks=nranks, extra_constraints=extra_constraints,
                       rank_grid=rank_grid)
     pot = gaussian_wells_potential(mesh.box, periodic=periodic) if potential else None
     ranks = [mesh.rank_problem(r, potential=pot, vquad=vquad) for r in range(nranks)]
+    if kpoint is not None:
+        for r, rp in enumerate(ranks):
+            rp.H = mesh.cell_hamiltonians_kpoint(mesh.owned_cells(r), pot, kpoint, vquad)
     if n_atoms:
         rng = np.random.default_rng(123)
         atoms = rng.uniform(0.2, 0.8, size=(n_atoms, 3)) * np.asarray(mesh.box)
@@ -19,16 +22,19 @@ def make_problem(p, ncells, h=1.0, periodic=(True, True, True), nranks=1, vquad=
     return mesh, ranks
 
 
-def random_global(mesh, ncols, seed=0):
+def random_global(mesh, ncols, seed=0, cplx=False):
     rng = np.random.default_rng(seed)
-    return rng.uniform(-1.0, 1.0, size=(mesh.nNodes, ncols))
+    x = rng.uniform(-1.0, 1.0, size=(mesh.nNodes, ncols))
+    if cplx:
+        x = x + 1j * rng.uniform(-1.0, 1.0, size=(mesh.nNodes, ncols))
+    return x
 
 
 def scatter_to_ranks(ranks, Xg, loewdin=False, zero_constrained=True):
     """global (by global DoF id) -> per-rank (M+G) x ncols arrays, ghosts zero."""
     out = []
     for rp in ranks:
-        x = np.zeros((rp.M + rp.G, Xg.shape[1]))
+        x = np.zeros((rp.M + rp.G, Xg.shape[1]), dtype=Xg.dtype)
         x[:rp.M] = Xg[rp.ownedStart:rp.ownedEnd]
         if loewdin:
             x[:rp.M] *= rp.sqrtMass[:rp.M, None]

@@ -80,7 +80,7 @@ def test_no_cpu_fallback(capi):
 def test_create_rejects_unsupported_element(capi):
     lib = capi.load()
     desc = capi.ProblemDesc(nodes_per_cell=100, cheby_block=8, n_cells=1, n_owned=10, n_ghost=0, n_global_dofs=10,
-                            device=0, reserved=0)
+                            device=0, flags=0)
     h = C.c_void_p()
     rc = lib.dftfe_b200_create(C.byref(desc), C.byref(h))
     assert rc == -4 and b"nodes per cell" in lib.dftfe_b200_last_error()

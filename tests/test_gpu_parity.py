@@ -268,3 +268,42 @@ def test_nonlocal_projectors(capi, p, ncells, periodic, B, generic):
     op.chebyshevFilter(x_d, y_d, 9, lo + 0.3 * (up - lo), up, lo - 0.3)
     assert _relerr(x_d.cpu().numpy()[:rp.M], ref[0][:rp.M]) < 9 * RTOL
     op.close()
+
+
+@pytest.mark.parametrize("p,ncells,periodic,B,generic", [
+    (2, (3, 3, 3), (True, True, True), 16, 0),
+    (3, (3, 2, 3), (True, True, False), 24, 1),
+    (6, (2, 2, 2), (True, True, True), 16, 0),
+    (4, (2, 3, 2), (True, True, True), 20, 0),
+])
+def test_complex_kpoint_operator_and_filter(capi, p, ncells, periodic, B, generic):
+    """T = complex<double> (k-point) build: HX / HXCheby / filter against the oracle (zgemm 'N','T' convention)."""
+    from oracle import chfsi_oracle as O
+
+    mesh, ranks = make_problem(p, ncells, 1.2, periodic, kpoint=(0.21, -0.13, 0.34),
+                               extra_constraints=hanging_like_constraints(3))
+    rp = ranks[0]
+    assert np.iscomplexobj(rp.H)
+    op = capi.Operator(rp, B, complex=True)
+    op.set_option("generic_cell_kernel", generic)
+    op.set_cell_hamiltonian(rp.H)
+    X = scatter_to_ranks(ranks, random_global(mesh, B, seed=1, cplx=True), loewdin=True)
+    Y0 = scatter_to_ranks(ranks, random_global(mesh, B, seed=2, cplx=True), loewdin=True)
+    src, dst = [X[0].copy()], [Y0[0].copy()]
+    O.HX(ranks, src, dst, True, 0.6)
+    s_d, d_d = _dev(X[0]), _dev(Y0[0])
+    op.HX(s_d, d_d, True, 0.6)
+    assert _relerr(d_d.cpu().numpy(), dst[0]) < RTOL
+    assert _relerr(s_d.cpu().numpy(), src[0]) < RTOL
+    src, dst = [X[0].copy()], [Y0[0].copy()]
+    O.HXCheby(ranks, src, dst)
+    s_d, d_d = _dev(X[0]), _dev(Y0[0])
+    op.HXCheby(s_d, d_d)
+    assert _relerr(d_d.cpu().numpy(), dst[0]) < RTOL
+    lo, up = O.lanczos_bounds(ranks, dtype=np.complex128)
+    ref = [X[0].copy()]
+    O.chebyshev_filter_inplace(ranks, ref, 8, lo + 0.3 * (up - lo), up, lo - 0.3)
+    x_d, y_d = _dev(X[0]), torch.empty_like(_dev(X[0]))
+    op.chebyshevFilter(x_d, y_d, 8, lo + 0.3 * (up - lo), up, lo - 0.3)
+    assert _relerr(x_d.cpu().numpy()[:rp.M], ref[0][:rp.M]) < 8 * RTOL
+    op.close()
