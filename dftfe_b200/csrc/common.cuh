@@ -229,6 +229,7 @@ struct dftfe_b200_ctx {
   cudaStream_t copyIn = nullptr, copyOut = nullptr;
   dftfe_b200::DevBuf<double> HXfull;              // M*Bw
   dftfe_b200::DevBuf<double> denseA, denseB, denseC, denseW;  // N*N scratch
+  dftfe_b200::DevBuf<double> denseG;              // (2N)^2 real embedding scratch of the complex build
   dftfe_b200::DevBuf<double> eigDev, resDev;
   dftfe_b200::DevBuf<double> partials;            // split-K / reduction workspace
   dftfe_b200::DevBuf<double> arTmp;               // loopback all-reduce scratch

@@ -131,13 +131,13 @@ __global__ void symmetrise_from_lower_kernel(double *S, int N) {
 
 // partial[blockIdx.x][col] = sum over this block's rows of (hx - lambda*x)^2
 __global__ void residual_partial_kernel(const double *__restrict__ X, int N, int j0, const double *__restrict__ HXb,
-                                        int ncols, int64_t rows, const double *__restrict__ eig,
+                                        int ncols, int64_t rows, const double *__restrict__ eig, int colsPerEig,
                                         double *__restrict__ partial) {
   __shared__ double red[8][33];
   const int col = blockIdx.y * 32 + threadIdx.x;
   double acc = 0.0;
   if (col < ncols) {
-    const double lam = eig[j0 + col];
+    const double lam = eig[(j0 + col) / colsPerEig];
     for (int64_t r = blockIdx.x * 8 + threadIdx.y; r < rows; r += (int64_t)gridDim.x * 8) {
       const double d = HXb[(size_t)r * ncols + col] - lam * X[(size_t)r * N + j0 + col];
       acc += d * d;
@@ -178,6 +178,62 @@ __global__ void column_dot_partial_kernel(const double *__restrict__ x, const do
   if (threadIdx.x == 0) partial[blockIdx.x] = red[0];
 }
 
+// complex N x N (column-major, interleaved) from the real 2N x 2N embedding G(a,b) = sum_m Xr[m,a] Yr[m,b]:
+//   S(i,j) = sum_m conj(x_i) y_j = (G(2i,2j) + G(2i+1,2j+1)) + i (G(2i,2j+1) - G(2i+1,2j))
+// lowerOnly: only i >= j is formed from G's lower tiles, the rest by Hermitian symmetry.
+__global__ void cplx_combine_kernel(const double *__restrict__ G, int N, double *__restrict__ S, int lowerOnly) {
+  const int64_t total = (int64_t)N * N;
+  const int64_t ld = 2 * (int64_t)N;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    int i = idx % N, j = idx / N;
+    const bool flip = lowerOnly && i < j;
+    if (flip) {
+      const int t = i;
+      i = j;
+      j = t;
+    }
+    const double re = G[2 * i + (2 * j) * ld] + G[2 * i + 1 + (2 * j + 1) * ld];
+    const double im = G[2 * i + (2 * j + 1) * ld] - G[2 * i + 1 + (2 * j) * ld];
+    S[2 * idx] = re;
+    S[2 * idx + 1] = flip ? -im : im;
+  }
+}
+
+// real row-major 2N x 2N embedding of a complex N x N matrix R for X <- X R on interleaved storage:
+//   Rt[2k][2j] = Re R(k,j), Rt[2k][2j+1] = Im R(k,j), Rt[2k+1][2j] = -Im R(k,j), Rt[2k+1][2j+1] = Re R(k,j)
+__global__ void cplx_embed_kernel(const double *__restrict__ R, int N, int colMajor, double *__restrict__ Rt) {
+  const int64_t total = (int64_t)N * N;
+  const int64_t ld = 2 * (int64_t)N;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int k = idx / N, j = idx % N;
+    const int64_t src = colMajor ? ((int64_t)k + (int64_t)j * N) : idx;
+    const double re = R[2 * src], im = R[2 * src + 1];
+    Rt[(2 * k) * ld + 2 * j] = re;
+    Rt[(2 * k) * ld + 2 * j + 1] = im;
+    Rt[(2 * k + 1) * ld + 2 * j] = -im;
+    Rt[(2 * k + 1) * ld + 2 * j + 1] = re;
+  }
+}
+
+// out(row-major complex) <- in(column-major complex)
+__global__ void cplx_transpose_kernel(const double *__restrict__ in, double *__restrict__ out, int N) {
+  const int64_t total = (int64_t)N * N;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int i = idx / N, j = idx % N;  // out[i][j] = in(i,j)
+    const int64_t src = (int64_t)i + (int64_t)j * N;
+    out[2 * idx] = in[2 * src];
+    out[2 * idx + 1] = in[2 * src + 1];
+  }
+}
+
+__global__ void pair_sum_kernel(const double *__restrict__ in, double *__restrict__ out, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = in[2 * i] + in[2 * i + 1];
+}
+
 __global__ void axpy_kernel(double *__restrict__ y, const double *__restrict__ x, double alpha, int64_t n) {
   for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
     y[i] += alpha * x[i];
@@ -196,67 +252,91 @@ static int ensure_block_scratch(dftfe_b200_ctx *ctx) {
   return 0;
 }
 
-// S (col-major == row-major after symmetrisation) = X^T X, lower blocks then mirror
+// Gram matrix of the local rows: real: S = X^T X (N x N, symmetric, column- == row-major);
+// complex: S(i,j) = sum_m conj(X[m,i]) X[m,j], column-major interleaved, via the real 2N x 2N embedding.
+// Lower-triangular tiles/blocks only, mirrored afterwards; all-reduced over the ranks.
 static int xtx_impl(dftfe_b200_ctx *ctx, const double *X, int N, double *S) {
-  const int Bw = std::min(ctx->B, N);
+  const int cm = ctx->cm, Nr = N * cm;
+  const int Bw = std::min(ctx->B, N) * cm;
   const double one = 1.0, zero = 0.0;
+  double *G = S;
+  if (ctx->cplx) {
+    DB_TRY(ctx->denseG.alloc((size_t)Nr * Nr));
+    G = ctx->denseG.p;
+  }
   DB_CUBLAS(cublasSetStream(ctx->cublas, ctx->stream));
-  DB_CUDA(cudaMemsetAsync(S, 0, (size_t)N * N * sizeof(double), ctx->stream));
-  if (ctx->M > 0 && !ctx->use_cublas_dense && dmma_projection_usable(ctx, N, N, N, 0, 0, N, N)) {
-    // hand-written DMMA kernel, lower-triangular 128x128 tiles of the whole N x N matrix in one pass
-    DB_TRY(launch_xty(ctx, X, N, 0, X, N, 0, N, N, 0, 0, true, S, N));
+  DB_CUDA(cudaMemsetAsync(G, 0, (size_t)Nr * Nr * sizeof(double), ctx->stream));
+  if (ctx->M > 0 && !ctx->use_cublas_dense && dmma_projection_usable(ctx, Nr, Nr, Nr, 0, 0, Nr, Nr)) {
+    // hand-written DMMA kernel, lower-triangular 128x128 tiles of the whole matrix in one pass
+    DB_TRY(launch_xty(ctx, X, Nr, 0, X, Nr, 0, Nr, Nr, 0, 0, true, G, Nr));
   } else if (ctx->M > 0) {
-    for (int j = 0; j < N; j += Bw) {
-      const int Bc = std::min(Bw, N - j), D = N - j;
+    for (int j = 0; j < Nr; j += Bw) {
+      const int Bc = std::min(Bw, Nr - j), D = Nr - j;
       ProfScope ps(ctx, "projection");
       // block(D x Bc) = X_cm[j:, :] (D x M) * X_cm[j:j+Bc, :]^T
-      DB_CUBLAS(cublasDgemm(ctx->cublas, CUBLAS_OP_N, CUBLAS_OP_T, D, Bc, (int)ctx->M, &one, X + j, N, X + j, N,
-                            &zero, S + j + (size_t)j * N, N));
+      DB_CUBLAS(cublasDgemm(ctx->cublas, CUBLAS_OP_N, CUBLAS_OP_T, D, Bc, (int)ctx->M, &one, X + j, Nr, X + j, Nr,
+                            &zero, G + j + (size_t)j * Nr, Nr));
     }
   }
   ctx->launches += 1;
-  symmetrise_from_lower_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(S, N);
+  symmetrise_from_lower_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(G, Nr);
+  if (ctx->cplx) {
+    ctx->launches += 1;
+    cplx_combine_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(G, N, S, 0);
+  }
   DB_CUDA(cudaGetLastError());
-  DB_TRY(allreduce_sum(ctx, S, (size_t)N * N));
+  DB_TRY(allreduce_sum(ctx, S, (size_t)N * N * cm));
   return 0;
 }
 
 // HXb(M x ncols, dense) = H~ * X[:, j0:j0+ncols]
 static int apply_H_to_columns(dftfe_b200_ctx *ctx, const double *X, int N, int j0, int ncols) {
+  const int cm = ctx->cm;
   DB_TRY(ensure_block_scratch(ctx));
-  DB_TRY(launch_block_copy_from_full(ctx, X, N, j0, ctx->blockX.p, ncols, ctx->M, nullptr));
-  DB_TRY(ghost_zero(ctx, ctx->blockX.p, ncols, ncols));
+  DB_TRY(launch_block_copy_from_full(ctx, X, N * cm, j0 * cm, ctx->blockX.p, ncols * cm, ctx->M, nullptr));
+  DB_TRY(ghost_zero(ctx, ctx->blockX.p, ncols * cm, ncols * cm));
   // dst = H~ src (b = 0: dst is never read)
   DB_TRY(op_fused_apply(ctx, ctx->blockX.p, ctx->blockY.p, ncols, 0.0, 0.0, 1.0));
   return 0;
 }
 
+// Hp = X^H (H~ X), same storage conventions as xtx_impl
 static int xthx_impl(dftfe_b200_ctx *ctx, const double *X, int N, double *Hp) {
+  const int cm = ctx->cm, Nr = N * cm;
   const int Bc0 = std::min(ctx->B, N);
   const double one = 1.0, zero = 0.0;
+  double *G = Hp;
+  if (ctx->cplx) {
+    DB_TRY(ctx->denseG.alloc((size_t)Nr * Nr));
+    G = ctx->denseG.p;
+  }
   DB_CUBLAS(cublasSetStream(ctx->cublas, ctx->stream));
-  DB_CUDA(cudaMemsetAsync(Hp, 0, (size_t)N * N * sizeof(double), ctx->stream));
+  DB_CUDA(cudaMemsetAsync(G, 0, (size_t)Nr * Nr * sizeof(double), ctx->stream));
   for (int j = 0; j < N; j += Bc0) {
-    const int Bc = std::min(Bc0, N - j), D = N - j;
+    const int Bc = std::min(Bc0, N - j);
+    const int jr = j * cm, Bcr = Bc * cm, D = Nr - jr;
     DB_TRY(apply_H_to_columns(ctx, X, N, j, Bc));
-    if (ctx->M > 0 && !ctx->use_cublas_dense && dmma_projection_usable(ctx, N, N, Bc, j, 0, D, Bc)) {
-      DB_TRY(launch_xty(ctx, X, N, j, ctx->blockY.p, Bc, 0, D, Bc, j, j, true, Hp + j + (size_t)j * N, N));
+    if (ctx->M > 0 && !ctx->use_cublas_dense && dmma_projection_usable(ctx, Nr, Nr, Bcr, jr, 0, D, Bcr)) {
+      DB_TRY(launch_xty(ctx, X, Nr, jr, ctx->blockY.p, Bcr, 0, D, Bcr, jr, jr, true, G + jr + (size_t)jr * Nr, Nr));
     } else if (ctx->M > 0) {
       ProfScope ps(ctx, "projection");
       // block(D x Bc) = X_cm[j:, :] (D x M) * HXb_cm (Bc x M)^T
-      DB_CUBLAS(cublasDgemm(ctx->cublas, CUBLAS_OP_N, CUBLAS_OP_T, D, Bc, (int)ctx->M, &one, X + j, N,
-                            ctx->blockY.p, Bc, &zero, Hp + j + (size_t)j * N, N));
+      DB_CUBLAS(cublasDgemm(ctx->cublas, CUBLAS_OP_N, CUBLAS_OP_T, D, Bcr, (int)ctx->M, &one, X + jr, Nr,
+                            ctx->blockY.p, Bcr, &zero, G + jr + (size_t)jr * Nr, Nr));
     }
   }
   ctx->launches += 1;
-  symmetrise_from_lower_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(Hp, N);
+  if (ctx->cplx)
+    cplx_combine_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(G, N, Hp, 1);
+  else
+    symmetrise_from_lower_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(G, Nr);
   DB_CUDA(cudaGetLastError());
-  DB_TRY(allreduce_sum(ctx, Hp, (size_t)N * N));
+  DB_TRY(allreduce_sum(ctx, Hp, (size_t)N * N * cm));
   return 0;
 }
 
-// X <- X * Q.  qColMajor: Q memory holds Q(i,j) at i + j*N (cuSOLVER output), else row-major.
-static int rotate_impl(dftfe_b200_ctx *ctx, double *X, int N, const double *Q, bool qColMajor) {
+// X(M x Nr real) <- X * Q.  qColMajor: Q memory holds Q(i,j) at i + j*Nr (cuSOLVER output), else row-major.
+static int rotate_real(dftfe_b200_ctx *ctx, double *X, int N, const double *Q, bool qColMajor) {
   if (ctx->M == 0) return 0;
   const int64_t chunk = std::min<int64_t>(ctx->M, 148 * 128);
   DB_TRY(ctx->rotScratch.alloc((size_t)chunk * N));
@@ -288,26 +368,46 @@ static int rotate_impl(dftfe_b200_ctx *ctx, double *X, int N, const double *Q, b
   return 0;
 }
 
+// X <- X * Q for N wavefunction columns (complex: through the real 2N x 2N embedding of Q)
+static int rotate_impl(dftfe_b200_ctx *ctx, double *X, int N, const double *Q, bool qColMajor) {
+  if (!ctx->cplx) return rotate_real(ctx, X, N, Q, qColMajor);
+  const int Nr = 2 * N;
+  DB_TRY(ctx->denseG.alloc((size_t)Nr * Nr));
+  ctx->launches += 1;
+  cplx_embed_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(Q, N, qColMajor ? 1 : 0, ctx->denseG.p);
+  DB_CUDA(cudaGetLastError());
+  return rotate_real(ctx, X, Nr, ctx->denseG.p, false);
+}
+
 static int residual_impl(dftfe_b200_ctx *ctx, const double *X, int N, const double *eig_h, double *res_h) {
+  const int cm = ctx->cm;
   DB_TRY(ctx->eigDev.alloc(N));
-  DB_TRY(ctx->resDev.alloc(N));
+  DB_TRY(ctx->resDev.alloc((size_t)N * cm + N));
   DB_CUDA(cudaMemcpyAsync(ctx->eigDev.p, eig_h, N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   const int Bc0 = std::min(ctx->B, N);
   const int nParts = ctx->num_sms * 2;
-  DB_TRY(ctx->partials.alloc((size_t)nParts * Bc0));
+  DB_TRY(ctx->partials.alloc((size_t)nParts * Bc0 * cm));
+  double *perCol = ctx->resDev.p;              // N*cm per-real-column sums
+  double *perState = ctx->resDev.p + (size_t)N * cm;
   for (int j = 0; j < N; j += Bc0) {
-    const int Bc = std::min(Bc0, N - j);
+    const int Bc = std::min(Bc0, N - j), Bcr = Bc * cm;
     DB_TRY(apply_H_to_columns(ctx, X, N, j, Bc));
     ProfScope ps(ctx, "residual", 2);
-    dim3 grid(nParts, (Bc + 31) / 32), block(32, 8);
-    residual_partial_kernel<<<grid, block, 0, ctx->stream>>>(X, N, j, ctx->blockY.p, Bc, ctx->M, ctx->eigDev.p,
-                                                             ctx->partials.p);
-    residual_final_kernel<<<(Bc + 127) / 128, 128, 0, ctx->stream>>>(ctx->partials.p, nParts, Bc,
-                                                                     ctx->resDev.p + j);
+    dim3 grid(nParts, (Bcr + 31) / 32), block(32, 8);
+    residual_partial_kernel<<<grid, block, 0, ctx->stream>>>(X, N * cm, j * cm, ctx->blockY.p, Bcr, ctx->M,
+                                                             ctx->eigDev.p, cm, ctx->partials.p);
+    residual_final_kernel<<<(Bcr + 127) / 128, 128, 0, ctx->stream>>>(ctx->partials.p, nParts, Bcr,
+                                                                      perCol + (size_t)j * cm);
     DB_CUDA(cudaGetLastError());
   }
-  DB_TRY(allreduce_sum(ctx, ctx->resDev.p, N));
-  DB_CUDA(cudaMemcpyAsync(res_h, ctx->resDev.p, N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  if (ctx->cplx) {
+    ctx->launches += 1;
+    pair_sum_kernel<<<(N + 127) / 128, 128, 0, ctx->stream>>>(perCol, perState, N);
+  } else {
+    perState = perCol;
+  }
+  DB_TRY(allreduce_sum(ctx, perState, N));
+  DB_CUDA(cudaMemcpyAsync(res_h, perState, N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   DB_CUDA(cudaStreamSynchronize(ctx->stream));
   for (int i = 0; i < N; ++i) res_h[i] = std::sqrt(res_h[i]);
   return 0;
@@ -320,7 +420,7 @@ static int global_dot(dftfe_b200_ctx *ctx, const double *x, const double *y, dou
   const int nParts = 256;
   DB_TRY(ctx->partials.alloc(nParts + 8));
   ctx->launches += 2;
-  column_dot_partial_kernel<<<nParts, 256, 0, ctx->stream>>>(x, y, ctx->M, ctx->partials.p);
+  column_dot_partial_kernel<<<nParts, 256, 0, ctx->stream>>>(x, y, ctx->M * ctx->cm, ctx->partials.p);
   residual_final_kernel<<<1, 32, 0, ctx->stream>>>(ctx->partials.p, nParts, 1, ctx->partials.p + nParts);
   DB_CUDA(cudaGetLastError());
   DB_TRY(allreduce_sum(ctx, ctx->partials.p + nParts, 1));
@@ -362,18 +462,19 @@ static void jacobi_eigenvalues(std::vector<double> &A, int n, std::vector<double
 
 static int lanczos_impl(dftfe_b200_ctx *ctx, int reproducible, double out[2]) {
   const int iters = reproducible ? 40 : 20;
-  const int64_t rows = ctx->M + ctx->G;
+  // single-column vectors; complex build: (re, im) pairs, so every length below is in doubles and the
+  // real dot products over 2M doubles are Re<x,y> (H~ is Hermitian: alpha is real up to rounding)
+  const int cm = ctx->cm;
+  const int64_t rows = (ctx->M + ctx->G) * cm;
+  const int64_t owned = ctx->M * cm;
   DB_TRY(ensure_block_scratch(ctx));
-  DB_CHECK(ctx->B >= 4 || rows == 0 || true, "unreachable");
-  // three single-column vectors carved out of blockX/blockY scratch would alias the
-  // operator scratch, so use a dedicated buffer
   DB_TRY(ctx->HXfull.alloc((size_t)rows * 4));
   double *v = ctx->HXfull.p, *f = v + rows, *v0 = f + rows, *src = v0 + rows;
   std::vector<double> hv(rows, 0.0);
   std::srand(ctx->rank);
-  for (int64_t i = 0; i < ctx->M; ++i) hv[i] = ((double)std::rand()) / ((double)RAND_MAX);
+  for (int64_t i = 0; i < ctx->M; ++i) hv[i * cm] = ((double)std::rand()) / ((double)RAND_MAX);
   for (uint32_t r : ctx->conRows_h)
-    if (r < ctx->M) hv[r] = 0.0;
+    if (r < ctx->M) hv[(int64_t)r * cm] = 0.0;
   DB_CUDA(cudaMemcpyAsync(v, hv.data(), rows * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   double nrm2 = 0;
   DB_TRY(global_dot(ctx, v, v, &nrm2));
@@ -391,7 +492,7 @@ static int lanczos_impl(dftfe_b200_ctx *ctx, int reproducible, double out[2]) {
   DB_TRY(applyH(v, f));
   DB_TRY(global_dot(ctx, f, v, &alpha));
   ctx->launches += 1;
-  axpy_kernel<<<g, 256, 0, ctx->stream>>>(f, v, -alpha, ctx->M);
+  axpy_kernel<<<g, 256, 0, ctx->stream>>>(f, v, -alpha, owned);
   T[0] = alpha;
   for (int j = 1; j < iters; ++j) {
     double ff = 0;
@@ -399,12 +500,12 @@ static int lanczos_impl(dftfe_b200_ctx *ctx, int reproducible, double out[2]) {
     beta = std::sqrt(ff);
     ctx->launches += 3;
     DB_CUDA(cudaMemcpyAsync(v0, v, rows * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
-    scale_copy_kernel<<<g, 256, 0, ctx->stream>>>(v, f, 1.0 / beta, ctx->M);
+    scale_copy_kernel<<<g, 256, 0, ctx->stream>>>(v, f, 1.0 / beta, owned);
     DB_TRY(applyH(v, f));
-    axpy_kernel<<<g, 256, 0, ctx->stream>>>(f, v0, -beta, ctx->M);
+    axpy_kernel<<<g, 256, 0, ctx->stream>>>(f, v0, -beta, owned);
     DB_TRY(global_dot(ctx, f, v, &alpha));
     ctx->launches += 1;
-    axpy_kernel<<<g, 256, 0, ctx->stream>>>(f, v, -alpha, ctx->M);
+    axpy_kernel<<<g, 256, 0, ctx->stream>>>(f, v, -alpha, owned);
     T[(size_t)j * iters + j - 1] = beta;
     T[(size_t)(j - 1) * iters + j] = beta;
     T[(size_t)j * iters + j] = alpha;
@@ -460,8 +561,79 @@ static int dense_eigh(dftfe_b200_ctx *ctx, double *A, int N, double *W) {
   return dense_check_info(ctx, "eigendecomposition of the projected Hamiltonian (cusolverDnDsyevd)");
 }
 
+static int dense_cholesky_cplx(dftfe_b200_ctx *ctx, double *S, int N) {
+  DB_CUSOLVER(cusolverDnSetStream(ctx->cusolver, ctx->stream));
+  DB_TRY(ctx->devInfo.alloc(1));
+  int lwork = 0;
+  cuDoubleComplex *Sz = reinterpret_cast<cuDoubleComplex *>(S);
+  DB_CUSOLVER(cusolverDnZpotrf_bufferSize(ctx->cusolver, CUBLAS_FILL_MODE_LOWER, N, Sz, N, &lwork));
+  DB_TRY(ctx->cusolverWork.alloc((size_t)lwork * 2));
+  ctx->launches += 1;
+  DB_CUSOLVER(cusolverDnZpotrf(ctx->cusolver, CUBLAS_FILL_MODE_LOWER, N, Sz, N,
+                               reinterpret_cast<cuDoubleComplex *>(ctx->cusolverWork.p), lwork, ctx->devInfo.p));
+  return dense_check_info(ctx, "Cholesky factorisation of X^H X (cusolverDnZpotrf)");
+}
+
+static int dense_eigh_cplx(dftfe_b200_ctx *ctx, double *A, int N, double *W) {
+  DB_CUSOLVER(cusolverDnSetStream(ctx->cusolver, ctx->stream));
+  DB_TRY(ctx->devInfo.alloc(1));
+  int lwork = 0;
+  cuDoubleComplex *Az = reinterpret_cast<cuDoubleComplex *>(A);
+  DB_CUSOLVER(cusolverDnZheevd_bufferSize(ctx->cusolver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, N, Az, N,
+                                          W, &lwork));
+  DB_TRY(ctx->cusolverWork.alloc((size_t)lwork * 2));
+  ctx->launches += 1;
+  DB_CUSOLVER(cusolverDnZheevd(ctx->cusolver, CUSOLVER_EIG_MODE_VECTOR, CUBLAS_FILL_MODE_LOWER, N, Az, N, W,
+                               reinterpret_cast<cuDoubleComplex *>(ctx->cusolverWork.p), lwork, ctx->devInfo.p));
+  return dense_check_info(ctx, "eigendecomposition of the projected Hamiltonian (cusolverDnZheevd)");
+}
+
+// complex build of rayleighRitzGEP / CGS+RR: S = X^H X = L L^H, Hs = L^-1 Hp L^-H = Q' D Q'^H, X <- X L^-H Q'
+static int rr_cplx(dftfe_b200_ctx *ctx, double *X, int N, double *eig_h, bool cgsFirst) {
+  const size_t nn = (size_t)N * N * 2;
+  DB_TRY(ctx->denseA.alloc(nn));
+  DB_TRY(ctx->denseB.alloc(nn));
+  DB_TRY(ctx->eigDev.alloc(N));
+  double *S = ctx->denseA.p, *Hp = ctx->denseB.p;
+  cuDoubleComplex *Sz = reinterpret_cast<cuDoubleComplex *>(S), *Hz = reinterpret_cast<cuDoubleComplex *>(Hp);
+  const cuDoubleComplex one = make_cuDoubleComplex(1.0, 0.0);
+  DB_TRY(xtx_impl(ctx, X, N, S));
+  DB_TRY(dense_cholesky_cplx(ctx, S, N));
+  DB_CUBLAS(cublasSetStream(ctx->cublas, ctx->stream));
+  if (cgsFirst) {
+    // X <- X L^-H, then plain RR
+    std::vector<double> eye(nn, 0.0);
+    for (int i = 0; i < N; ++i) eye[((size_t)i * N + i) * 2] = 1.0;
+    DB_CUDA(cudaMemcpyAsync(Hp, eye.data(), nn * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    DB_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->launches += 1;
+    DB_CUBLAS(cublasZtrsm(ctx->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_C, CUBLAS_DIAG_NON_UNIT, N,
+                          N, &one, Sz, N, Hz, N));
+    DB_TRY(rotate_impl(ctx, X, N, Hp, true));
+    DB_TRY(xthx_impl(ctx, X, N, Hp));
+    DB_TRY(dense_eigh_cplx(ctx, Hp, N, ctx->eigDev.p));
+    DB_TRY(rotate_impl(ctx, X, N, Hp, true));
+  } else {
+    DB_TRY(xthx_impl(ctx, X, N, Hp));
+    DB_CUBLAS(cublasSetStream(ctx->cublas, ctx->stream));
+    ctx->launches += 3;
+    DB_CUBLAS(cublasZtrsm(ctx->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, N,
+                          N, &one, Sz, N, Hz, N));
+    DB_CUBLAS(cublasZtrsm(ctx->cublas, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_C, CUBLAS_DIAG_NON_UNIT,
+                          N, N, &one, Sz, N, Hz, N));
+    DB_TRY(dense_eigh_cplx(ctx, Hp, N, ctx->eigDev.p));
+    DB_CUBLAS(cublasZtrsm(ctx->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_C, CUBLAS_DIAG_NON_UNIT, N,
+                          N, &one, Sz, N, Hz, N));
+    DB_TRY(rotate_impl(ctx, X, N, Hp, true));
+  }
+  DB_CUDA(cudaMemcpyAsync(eig_h, ctx->eigDev.p, N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  DB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
 // rayleighRitzGEP (src/linAlg/rayleighRitzDevice.cc:355-819)
 static int rr_gep(dftfe_b200_ctx *ctx, double *X, int N, double *eig_h) {
+  if (ctx->cplx) return rr_cplx(ctx, X, N, eig_h, false);
   const size_t nn = (size_t)N * N;
   DB_TRY(ctx->denseA.alloc(nn));
   DB_TRY(ctx->denseB.alloc(nn));
@@ -492,6 +664,7 @@ static int rr_gep(dftfe_b200_ctx *ctx, double *X, int N, double *eig_h) {
 // pseudoGramSchmidtOrthogonalization + rayleighRitz
 // (src/linAlg/pseudoGSDevice.cc:81-463, src/linAlg/rayleighRitzDevice.cc:81-353)
 static int cgs_rr(dftfe_b200_ctx *ctx, double *X, int N, double *eig_h) {
+  if (ctx->cplx) return rr_cplx(ctx, X, N, eig_h, true);
   const size_t nn = (size_t)N * N;
   DB_TRY(ctx->denseA.alloc(nn));
   DB_TRY(ctx->denseB.alloc(nn));
@@ -651,7 +824,7 @@ static int solve_impl(dftfe_b200_ctx *ctx, double *X, int N, const dftfe_b200_so
     DB_TRY(rr_gep(ctx, X, N, eig_h));
   if (p->compute_residual && res_h) DB_TRY(residual_impl(ctx, X, N, eig_h, res_h));
   // X <- M^-1/2 X (solver .cc:719-733)
-  DB_TRY(launch_row_scale(ctx, X, ctx->M, N, N, 1.0, ctx->invSqrtM.p));
+  DB_TRY(launch_row_scale(ctx, X, ctx->M, N * ctx->cm, N * ctx->cm, 1.0, ctx->invSqrtM.p));
   if (upper_h) *upper_h = ctx->bUp;
   DB_CUDA(cudaStreamSynchronize(ctx->stream));
   return 0;
@@ -718,14 +891,26 @@ int dftfe_b200_cheb_filter_all_host(dftfe_b200_ctx *ctx, double *X_h, int32_t N,
   return filter_all_host_impl(ctx, X_h, N, m, a, b, a0);
 }
 
+static int to_row_major_cplx(dftfe_b200_ctx *ctx, double *S_d, int N) {
+  DB_TRY(ctx->denseW.alloc((size_t)N * N * 2));
+  ctx->launches += 2;
+  cplx_transpose_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(S_d, ctx->denseW.p, N);
+  DB_CUDA(cudaGetLastError());
+  DB_CUDA(cudaMemcpyAsync(S_d, ctx->denseW.p, (size_t)N * N * 2 * sizeof(double), cudaMemcpyDeviceToDevice,
+                          ctx->stream));
+  return 0;
+}
+
 int dftfe_b200_xtx(dftfe_b200_ctx *ctx, const double *X_d, int32_t N, double *S_d) {
   DB_CTX(ctx);
-  return xtx_impl(ctx, X_d, N, S_d);
+  DB_TRY(xtx_impl(ctx, X_d, N, S_d));
+  return ctx->cplx ? to_row_major_cplx(ctx, S_d, N) : 0;
 }
 
 int dftfe_b200_xthx(dftfe_b200_ctx *ctx, const double *X_d, int32_t N, double *Hp_d) {
   DB_CTX(ctx);
-  return xthx_impl(ctx, X_d, N, Hp_d);
+  DB_TRY(xthx_impl(ctx, X_d, N, Hp_d));
+  return ctx->cplx ? to_row_major_cplx(ctx, Hp_d, N) : 0;
 }
 
 int dftfe_b200_rotate(dftfe_b200_ctx *ctx, double *X_d, int32_t N, const double *Q_d) {

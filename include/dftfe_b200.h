@@ -196,7 +196,8 @@ int dftfe_b200_cheb_filter_all_host(dftfe_b200_ctx *ctx, double *X_h, int32_t N,
                                     double a0);
 
 /* ---- subspace projections / rotation ------------------------------------- */
-/* S = X^T X, all-reduced; full symmetric N x N written to S_d (row-major)
+/* S = X^H X, all-reduced; full symmetric / Hermitian N x N written to S_d (row-major; complex: S[i][j] =
+ * sum_m conj(X[m,i]) X[m,j], interleaved)
  * (fillParallelOverlapMatScalapack, linearAlgebraOperationsDevice.cc:3078-3240). */
 int dftfe_b200_xtx(dftfe_b200_ctx *ctx, const double *X_d, int32_t N, double *S_d);
 /* Hp = X^T (M^-1/2 H M^-1/2) X, all-reduced, full symmetric N x N

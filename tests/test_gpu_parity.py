@@ -307,3 +307,47 @@ def test_complex_kpoint_operator_and_filter(capi, p, ncells, periodic, B, generi
     op.chebyshevFilter(x_d, y_d, 8, lo + 0.3 * (up - lo), up, lo - 0.3)
     assert _relerr(x_d.cpu().numpy()[:rp.M], ref[0][:rp.M]) < 8 * RTOL
     op.close()
+
+
+@pytest.mark.parametrize("N,B", [(64, 32), (24, 8)])
+def test_complex_projections_and_solve(capi, N, B):
+    """complex build: X^H X, X^H H~ X, rotation, Lanczos and solve() (N=64: DMMA kernels on the real
+    2N-column embedding; N=24: cuBLAS fallback for ragged tiles)."""
+    from oracle import chfsi_oracle as O
+
+    mesh, ranks = make_problem(3, (3, 3, 2), 1.4, (True, True, True), kpoint=(0.15, 0.05, -0.2))
+    rp = ranks[0]
+    op = capi.Operator(rp, B, complex=True)
+    op.set_cell_hamiltonian(rp.H)
+    Xg = random_global(mesh, N, seed=4, cplx=True)
+    X = scatter_to_ranks(ranks, Xg, loewdin=True)
+    X_d = _dev(X[0][:rp.M])
+    S_d = torch.empty(N, N, dtype=torch.complex128, device="cuda")
+    op.XtX(X_d, S_d)
+    assert _relerr(S_d.cpu().numpy(), O.xtx(ranks, X)) < 1e-13
+    op.XtHX(X_d, S_d)
+    assert _relerr(S_d.cpu().numpy(), O.xthx(ranks, [x.copy() for x in X], B)) < 1e-12
+    rng = np.random.default_rng(0)
+    Q = np.linalg.qr(rng.normal(size=(N, N)) + 1j * rng.normal(size=(N, N)))[0]
+    Xr = X_d.clone()
+    op.subspaceRotation(Xr, _dev(Q))
+    assert _relerr(Xr.cpu().numpy(), X[0][:rp.M] @ Q) < 1e-13
+    lo, up = O.lanczos_bounds(ranks, dtype=np.complex128)
+    assert op.lanczosLowerUpperBoundEigenSpectrum() == (lo, up)
+    solver = capi.ChebyshevSolver(op)
+    Xo = scatter_to_ranks(ranks, Xg, zero_constrained=False)
+    Xd = _dev(Xo[0][:rp.M])
+    first = True
+    a0 = blow = None
+    for it in range(3):
+        if not first:
+            solver.reinitSpectrumBounds(a0, blow)
+        eig, res, ub = solver.solve(Xd, isFirstFilteringCall=first, chebyshevOrder=14, reuseLanczos=True)
+        if first:
+            a0, blow, _ = solver.spectrumBounds()
+        ev_ref, res_ref = O.solve(ranks, Xo, B, 14, (a0, blow, up))
+        first = False
+        a0, blow = ev_ref[0], ev_ref[-1]
+        assert np.abs(eig - ev_ref).max() < 1e-8, it
+        assert np.abs(res - res_ref).max() < 1e-7
+    op.close()
