@@ -160,14 +160,300 @@ __global__ void block_to_full_kernel(double *__restrict__ X, int N, int j0, cons
   }
 }
 
+
+// ---------------------------------------------------------------------------
+// Vector path (the one that runs for every even column count / leading dimension):
+// one warp per row, 16-byte (double2) accesses, four independent row segments in
+// flight per lane, no integer division.  A 256-column row is 2 KB = four 512-byte
+// warp requests.  Arithmetic (and its order) is identical to the scalar kernels
+// above, so the results are bit-identical between the two paths.
+// ---------------------------------------------------------------------------
+constexpr int VU = 4;  // double2 chunks in flight per lane
+
+struct WarpRows {
+  int lane;
+  int64_t first, step;
+  __device__ WarpRows() {
+    lane = threadIdx.x & 31;
+    first = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5;
+    step = (gridDim.x * (int64_t)blockDim.x) >> 5;
+  }
+};
+
+__device__ __forceinline__ double2 ld2(const double *p) { return *reinterpret_cast<const double2 *>(p); }
+__device__ __forceinline__ void st2(double *p, double2 v) { *reinterpret_cast<double2 *>(p) = v; }
+// streaming variants for data that is touched once per pass
+__device__ __forceinline__ double2 ld2_stream(const double *p) {
+  double2 v;
+  asm volatile("ld.global.cs.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ void st2_stream(double *p, double2 v) {
+  asm volatile("st.global.cs.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
+}
+
+__global__ void __launch_bounds__(256)
+distribute_vec_kernel(double *__restrict__ x, int ncols, int ldx, int64_t nCon, const uint32_t *__restrict__ rows,
+                      const uint32_t *__restrict__ sizes, const uint32_t *__restrict__ starts,
+                      const uint32_t *__restrict__ cols, const double *__restrict__ vals,
+                      const double *__restrict__ inhom, const double *__restrict__ colScale) {
+  const WarpRows w;
+  for (int64_t i = w.first; i < nCon; i += w.step) {
+    const uint32_t s = starts[i], nz = sizes[i];
+    const double ih = inhom[i];
+    double *out = x + (size_t)rows[i] * ldx;
+    for (int c0 = w.lane * 2; c0 < ncols; c0 += 64 * VU) {
+      double2 v[VU];
+#pragma unroll
+      for (int u = 0; u < VU; ++u) v[u] = make_double2(ih, ih);
+      for (uint32_t j = 0; j < nz; ++j) {
+        const uint32_t cj = cols[s + j];
+        const double wj = vals[s + j];
+        const double sc = colScale ? colScale[cj] : 1.0;
+        const double *in = x + (size_t)cj * ldx + c0;
+        double2 xv[VU];
+#pragma unroll
+        for (int u = 0; u < VU; ++u) xv[u] = (c0 + 64 * u < ncols) ? ld2(in + 64 * u) : make_double2(0.0, 0.0);
+#pragma unroll
+        for (int u = 0; u < VU; ++u) {
+          if (colScale) {
+            xv[u].x = __dmul_rn(xv[u].x, sc);
+            xv[u].y = __dmul_rn(xv[u].y, sc);
+          }
+          v[u].x = __dadd_rn(v[u].x, __dmul_rn(wj, xv[u].x));
+          v[u].y = __dadd_rn(v[u].y, __dmul_rn(wj, xv[u].y));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < VU; ++u)
+        if (c0 + 64 * u < ncols) st2(out + c0 + 64 * u, v[u]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+slave_to_master_vec_kernel(double *__restrict__ x, int ncols, int ldx, int64_t nMasters,
+                           const uint32_t *__restrict__ masters, const uint32_t *__restrict__ mstarts,
+                           const uint32_t *__restrict__ slaves, const double *__restrict__ vals,
+                           const double *__restrict__ masterScale) {
+  const WarpRows w;
+  for (int64_t i = w.first; i < nMasters; i += w.step) {
+    const uint32_t m = masters[i];
+    const double sc = masterScale ? masterScale[m] : 1.0;
+    const uint32_t j0 = mstarts[i], j1 = mstarts[i + 1];
+    double *row = x + (size_t)m * ldx;
+    for (int c0 = w.lane * 2; c0 < ncols; c0 += 64 * VU) {
+      double2 v[VU];
+#pragma unroll
+      for (int u = 0; u < VU; ++u) v[u] = (c0 + 64 * u < ncols) ? ld2(row + c0 + 64 * u) : make_double2(0.0, 0.0);
+      for (uint32_t j = j0; j < j1; ++j) {
+        const double wj = vals[j];
+        const double *in = x + (size_t)slaves[j] * ldx + c0;
+        double2 t[VU];
+#pragma unroll
+        for (int u = 0; u < VU; ++u) t[u] = (c0 + 64 * u < ncols) ? ld2(in + 64 * u) : make_double2(0.0, 0.0);
+#pragma unroll
+        for (int u = 0; u < VU; ++u) {
+          t[u].x = __dmul_rn(wj, t[u].x);
+          t[u].y = __dmul_rn(wj, t[u].y);
+          if (masterScale) {
+            t[u].x = __dmul_rn(t[u].x, sc);
+            t[u].y = __dmul_rn(t[u].y, sc);
+          }
+          v[u].x = __dadd_rn(v[u].x, t[u].x);
+          v[u].y = __dadd_rn(v[u].y, t[u].y);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < VU; ++u)
+        if (c0 + 64 * u < ncols) st2(row + c0 + 64 * u, v[u]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+zero_rows_vec_kernel(double *__restrict__ x, int ncols, int ldx, int64_t nRows, const uint32_t *__restrict__ rows) {
+  const WarpRows w;
+  for (int64_t i = w.first; i < nRows; i += w.step) {
+    double *row = x + (size_t)rows[i] * ldx;
+    for (int c = w.lane * 2; c < ncols; c += 64) st2(row + c, make_double2(0.0, 0.0));
+  }
+}
+
+// send[k,:] = x[rows[k],:]   (TOUT = double, or float for the FP32 payload of the mixed-precision filter)
+template <typename TOUT>
+__global__ void __launch_bounds__(256)
+pack_rows_vec_kernel(const double *__restrict__ x, int ncols, int ldx, int64_t nRows,
+                     const uint32_t *__restrict__ rows, int64_t row0, TOUT *__restrict__ buf) {
+  const WarpRows w;
+  for (int64_t i = w.first; i < nRows; i += w.step) {
+    const double *in = x + (size_t)(rows ? (int64_t)rows[i] : row0 + i) * ldx;
+    TOUT *out = buf + (size_t)i * ncols;
+    for (int c0 = w.lane * 2; c0 < ncols; c0 += 64 * VU) {
+      double2 v[VU];
+#pragma unroll
+      for (int u = 0; u < VU; ++u) v[u] = (c0 + 64 * u < ncols) ? ld2(in + c0 + 64 * u) : make_double2(0.0, 0.0);
+#pragma unroll
+      for (int u = 0; u < VU; ++u)
+        if (c0 + 64 * u < ncols) {
+          if constexpr (sizeof(TOUT) == 8)
+            st2(reinterpret_cast<double *>(out) + c0 + 64 * u, v[u]);
+          else
+            *reinterpret_cast<float2 *>(out + c0 + 64 * u) = make_float2((float)v[u].x, (float)v[u].y);
+        }
+    }
+  }
+}
+
+// contiguous rows [row0, row0+nRows) of x <- dense buffer (ghost segment fill)
+template <typename TIN>
+__global__ void __launch_bounds__(256)
+unpack_rows_vec_kernel(double *__restrict__ x, int ncols, int ldx, int64_t row0, int64_t nRows,
+                       const TIN *__restrict__ buf) {
+  const WarpRows w;
+  for (int64_t i = w.first; i < nRows; i += w.step) {
+    double *out = x + (size_t)(row0 + i) * ldx;
+    const TIN *in = buf + (size_t)i * ncols;
+    for (int c = w.lane * 2; c < ncols; c += 64) {
+      if constexpr (sizeof(TIN) == 8) {
+        st2(out + c, ld2(reinterpret_cast<const double *>(in) + c));
+      } else {
+        const float2 f = *reinterpret_cast<const float2 *>(in + c);
+        st2(out + c, make_double2((double)f.x, (double)f.y));
+      }
+    }
+  }
+}
+
+// FP64 payload: x[r,:] += scale[r] * slot_k, slots in ascending order.
+// FP32 payload (reference: the whole accumulate runs on a float copy of dst and the processor-boundary rows
+// are copied back as doubles, kohnShamDFTOperatorDevice.cc:3953-3990):
+//   x[r,:] = double( float(x[r,:]) +f float(scale[r]*slot_1) +f float(scale[r]*slot_2) ... )   (FP32 adds)
+template <typename TIN>
+__global__ void __launch_bounds__(256)
+unpack_add_vec_kernel(double *__restrict__ x, int ncols, int ldx, int64_t nRows, const uint32_t *__restrict__ rows,
+                      const uint32_t *__restrict__ starts, const uint32_t *__restrict__ slots,
+                      const TIN *__restrict__ buf, const double *__restrict__ rowScale) {
+  const WarpRows w;
+  for (int64_t i = w.first; i < nRows; i += w.step) {
+    const uint32_t r = rows[i];
+    const double sc = rowScale ? rowScale[r] : 1.0;
+    const uint32_t j0 = starts[i], j1 = starts[i + 1];
+    double *row = x + (size_t)r * ldx;
+    for (int c0 = w.lane * 2; c0 < ncols; c0 += 64 * VU) {
+      double2 v[VU];
+#pragma unroll
+      for (int u = 0; u < VU; ++u) v[u] = (c0 + 64 * u < ncols) ? ld2(row + c0 + 64 * u) : make_double2(0.0, 0.0);
+      if constexpr (sizeof(TIN) == 8) {
+        for (uint32_t j = j0; j < j1; ++j) {
+          const double *in = reinterpret_cast<const double *>(buf) + (size_t)slots[j] * ncols + c0;
+#pragma unroll
+          for (int u = 0; u < VU; ++u)
+            if (c0 + 64 * u < ncols) {
+              double2 t = ld2(in + 64 * u);
+              if (rowScale) {
+                t.x *= sc;
+                t.y *= sc;
+              }
+              v[u].x += t.x;
+              v[u].y += t.y;
+            }
+        }
+      } else {
+        float2 f[VU];
+#pragma unroll
+        for (int u = 0; u < VU; ++u) f[u] = make_float2((float)v[u].x, (float)v[u].y);
+        for (uint32_t j = j0; j < j1; ++j) {
+          const float *in = reinterpret_cast<const float *>(buf) + (size_t)slots[j] * ncols + c0;
+#pragma unroll
+          for (int u = 0; u < VU; ++u)
+            if (c0 + 64 * u < ncols) {
+              const float2 t = *reinterpret_cast<const float2 *>(in + 64 * u);
+              f[u].x = __fadd_rn(f[u].x, rowScale ? (float)((double)t.x * sc) : t.x);
+              f[u].y = __fadd_rn(f[u].y, rowScale ? (float)((double)t.y * sc) : t.y);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < VU; ++u) v[u] = make_double2((double)f[u].x, (double)f[u].y);
+      }
+#pragma unroll
+      for (int u = 0; u < VU; ++u)
+        if (c0 + 64 * u < ncols) st2(row + c0 + 64 * u, v[u]);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+row_scale_vec_kernel(double *__restrict__ x, int64_t rows, int ncols, int ldx, double alpha,
+                     const double *__restrict__ s) {
+  const WarpRows w;
+  for (int64_t r = w.first; r < rows; r += w.step) {
+    const double f = s ? alpha * s[r] : alpha;
+    double *row = x + (size_t)r * ldx;
+    for (int c0 = w.lane * 2; c0 < ncols; c0 += 64 * VU) {
+      double2 v[VU];
+#pragma unroll
+      for (int u = 0; u < VU; ++u) v[u] = (c0 + 64 * u < ncols) ? ld2(row + c0 + 64 * u) : make_double2(0.0, 0.0);
+#pragma unroll
+      for (int u = 0; u < VU; ++u)
+        if (c0 + 64 * u < ncols) st2(row + c0 + 64 * u, make_double2(v[u].x * f, v[u].y * f));
+    }
+  }
+}
+
+// dst[r, 0:ncols] = s[r] * src[r, 0:ncols] with independent leading dimensions: the block slice out of /
+// back into the full wavefunction matrix (K8).  Both sides are touched once -> streaming loads / stores.
+__global__ void __launch_bounds__(256)
+strided_copy_vec_kernel(const double *__restrict__ src, int lds, double *__restrict__ dst, int ldd, int ncols,
+                        int64_t rows, const double *__restrict__ s) {
+  const WarpRows w;
+  for (int64_t r = w.first; r < rows; r += w.step) {
+    const double f = s ? s[r] : 1.0;
+    const double *in = src + (size_t)r * lds;
+    double *out = dst + (size_t)r * ldd;
+    for (int c0 = w.lane * 2; c0 < ncols; c0 += 64 * VU) {
+      double2 v[VU];
+#pragma unroll
+      for (int u = 0; u < VU; ++u) v[u] = (c0 + 64 * u < ncols) ? ld2_stream(in + c0 + 64 * u) : make_double2(0.0, 0.0);
+#pragma unroll
+      for (int u = 0; u < VU; ++u)
+        if (c0 + 64 * u < ncols) {
+          if (s) {
+            v[u].x *= f;
+            v[u].y *= f;
+          }
+          st2_stream(out + c0 + 64 * u, v[u]);
+        }
+    }
+  }
+}
+
+inline bool vec_ok(const void *p, int ncols, int ldx) {
+  return (ncols % 2 == 0) && (ldx % 2 == 0) && ((reinterpret_cast<uintptr_t>(p) & 15) == 0);
+}
+
+// one warp per row, 8 warps per CTA, at most 8 CTAs per SM's worth of grid
+inline int grid_rows(const dftfe_b200_ctx *ctx, int64_t nRows) {
+  int64_t g = (nRows + 7) / 8;
+  const int64_t cap = (int64_t)ctx->num_sms * 8;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
 }  // namespace
 
 int launch_distribute(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx, const double *colScale) {
   if (ctx->nCon == 0) return 0;
   ProfScope ps(ctx, "distribute");
-  distribute_kernel<<<grid_for(ctx, ctx->nCon * ncols), 256, 0, ctx->stream>>>(
-      x, ncols, ldx, ctx->nCon, ctx->conRows.p, ctx->conSizes.p, ctx->conStarts.p, ctx->conCols.p, ctx->conVals.p,
-      ctx->conInhom.p, colScale);
+  if (vec_ok(x, ncols, ldx) && !ctx->force_scalar_row_kernels)
+    distribute_vec_kernel<<<grid_rows(ctx, ctx->nCon), 256, 0, ctx->stream>>>(
+        x, ncols, ldx, ctx->nCon, ctx->conRows.p, ctx->conSizes.p, ctx->conStarts.p, ctx->conCols.p,
+        ctx->conVals.p, ctx->conInhom.p, colScale);
+  else
+    distribute_kernel<<<grid_for(ctx, ctx->nCon * ncols), 256, 0, ctx->stream>>>(
+        x, ncols, ldx, ctx->nCon, ctx->conRows.p, ctx->conSizes.p, ctx->conStarts.p, ctx->conCols.p,
+        ctx->conVals.p, ctx->conInhom.p, colScale);
   DB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -175,12 +461,22 @@ int launch_distribute(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx, const 
 int launch_slave_to_master(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx, const double *masterScale) {
   if (ctx->nCon == 0) return 0;
   ProfScope ps(ctx, "slave_to_master", 2);
-  if (ctx->nMasters > 0)
-    slave_to_master_kernel<<<grid_for(ctx, ctx->nMasters * ncols), 256, 0, ctx->stream>>>(
-        x, ncols, ldx, ctx->nMasters, ctx->masterRows.p, ctx->masterStarts.p, ctx->masterSlaves.p,
-        ctx->masterVals.p, masterScale);
-  zero_rows_kernel<<<grid_for(ctx, ctx->nCon * ncols), 256, 0, ctx->stream>>>(x, ncols, ldx, ctx->nCon,
-                                                                             ctx->conRows.p);
+  const bool vec = vec_ok(x, ncols, ldx) && !ctx->force_scalar_row_kernels;
+  if (ctx->nMasters > 0) {
+    if (vec)
+      slave_to_master_vec_kernel<<<grid_rows(ctx, ctx->nMasters), 256, 0, ctx->stream>>>(
+          x, ncols, ldx, ctx->nMasters, ctx->masterRows.p, ctx->masterStarts.p, ctx->masterSlaves.p,
+          ctx->masterVals.p, masterScale);
+    else
+      slave_to_master_kernel<<<grid_for(ctx, ctx->nMasters * ncols), 256, 0, ctx->stream>>>(
+          x, ncols, ldx, ctx->nMasters, ctx->masterRows.p, ctx->masterStarts.p, ctx->masterSlaves.p,
+          ctx->masterVals.p, masterScale);
+  }
+  if (vec)
+    zero_rows_vec_kernel<<<grid_rows(ctx, ctx->nCon), 256, 0, ctx->stream>>>(x, ncols, ldx, ctx->nCon, ctx->conRows.p);
+  else
+    zero_rows_kernel<<<grid_for(ctx, ctx->nCon * ncols), 256, 0, ctx->stream>>>(x, ncols, ldx, ctx->nCon,
+                                                                               ctx->conRows.p);
   DB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -188,8 +484,11 @@ int launch_slave_to_master(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx, c
 int launch_set_zero_rows(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx) {
   if (ctx->nCon == 0) return 0;
   ProfScope ps(ctx, "set_zero");
-  zero_rows_kernel<<<grid_for(ctx, ctx->nCon * ncols), 256, 0, ctx->stream>>>(x, ncols, ldx, ctx->nCon,
-                                                                             ctx->conRows.p);
+  if (vec_ok(x, ncols, ldx) && !ctx->force_scalar_row_kernels)
+    zero_rows_vec_kernel<<<grid_rows(ctx, ctx->nCon), 256, 0, ctx->stream>>>(x, ncols, ldx, ctx->nCon, ctx->conRows.p);
+  else
+    zero_rows_kernel<<<grid_for(ctx, ctx->nCon * ncols), 256, 0, ctx->stream>>>(x, ncols, ldx, ctx->nCon,
+                                                                               ctx->conRows.p);
   DB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -198,43 +497,87 @@ int launch_row_scale(dftfe_b200_ctx *ctx, double *x, int64_t rows, int ncols, in
                      const double *rowScale) {
   if (rows == 0) return 0;
   ProfScope ps(ctx, "row_scale");
-  row_scale_kernel<<<grid_for(ctx, rows * ncols), 256, 0, ctx->stream>>>(x, rows, ncols, ldx, alpha, rowScale);
+  if (vec_ok(x, ncols, ldx) && !ctx->force_scalar_row_kernels)
+    row_scale_vec_kernel<<<grid_rows(ctx, rows), 256, 0, ctx->stream>>>(x, rows, ncols, ldx, alpha, rowScale);
+  else
+    row_scale_kernel<<<grid_for(ctx, rows * ncols), 256, 0, ctx->stream>>>(x, rows, ncols, ldx, alpha, rowScale);
   DB_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_block_copy_from_full(dftfe_b200_ctx *ctx, const double *X, int N, int j0, double *blk, int ncols,
                                 int64_t rows, const double *rowScale) {
+  if (rows == 0) return 0;
   ProfScope ps(ctx, "block_copy");
-  block_from_full_kernel<<<grid_for(ctx, rows * ncols), 256, 0, ctx->stream>>>(X, N, j0, blk, ncols, rows,
-                                                                              rowScale);
+  if (vec_ok(X + j0, ncols, N) && vec_ok(blk, ncols, ncols) && !ctx->force_scalar_row_kernels)
+    strided_copy_vec_kernel<<<grid_rows(ctx, rows), 256, 0, ctx->stream>>>(X + j0, N, blk, ncols, ncols, rows,
+                                                                          rowScale);
+  else
+    block_from_full_kernel<<<grid_for(ctx, rows * ncols), 256, 0, ctx->stream>>>(X, N, j0, blk, ncols, rows,
+                                                                                rowScale);
   DB_CUDA(cudaGetLastError());
   return 0;
 }
 
 int launch_block_copy_to_full(dftfe_b200_ctx *ctx, double *X, int N, int j0, const double *blk, int ncols,
                               int64_t rows, const double *rowScale) {
+  if (rows == 0) return 0;
   ProfScope ps(ctx, "block_copy");
-  block_to_full_kernel<<<grid_for(ctx, rows * ncols), 256, 0, ctx->stream>>>(X, N, j0, blk, ncols, rows, rowScale);
+  if (vec_ok(X + j0, ncols, N) && vec_ok(blk, ncols, ncols) && !ctx->force_scalar_row_kernels)
+    strided_copy_vec_kernel<<<grid_rows(ctx, rows), 256, 0, ctx->stream>>>(blk, ncols, X + j0, N, ncols, rows,
+                                                                          rowScale);
+  else
+    block_to_full_kernel<<<grid_for(ctx, rows * ncols), 256, 0, ctx->stream>>>(X, N, j0, blk, ncols, rows, rowScale);
   DB_CUDA(cudaGetLastError());
   return 0;
 }
 
 // ---- kernels used by comm.cu ------------------------------------------------
+// rows == nullptr: contiguous rows [row0, row0 + nRows)
 int launch_pack_rows(dftfe_b200_ctx *ctx, const double *x, int ncols, int ldx, int64_t nRows, const uint32_t *rows,
-                     double *buf) {
+                     int64_t row0, double *buf) {
   if (nRows == 0) return 0;
   ProfScope ps(ctx, "ghost_pack");
-  pack_rows_kernel<<<grid_for(ctx, nRows * ncols), 256, 0, ctx->stream>>>(x, ncols, ldx, nRows, rows, buf);
+  if (vec_ok(x, ncols, ldx) && vec_ok(buf, ncols, ncols) && !ctx->force_scalar_row_kernels)
+    pack_rows_vec_kernel<double><<<grid_rows(ctx, nRows), 256, 0, ctx->stream>>>(x, ncols, ldx, nRows, rows, row0, buf);
+  else if (rows)
+    pack_rows_kernel<<<grid_for(ctx, nRows * ncols), 256, 0, ctx->stream>>>(x, ncols, ldx, nRows, rows, buf);
+  else
+    copy_rows_kernel<<<grid_for(ctx, nRows * ncols), 256, 0, ctx->stream>>>(const_cast<double *>(x), ncols, ldx, row0,
+                                                                           nRows, buf, 1);
   DB_CUDA(cudaGetLastError());
   return 0;
 }
 
-int launch_copy_rows(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx, int64_t row0, int64_t nRows, double *buf,
-                     int toBuf) {
+// FP32 payload of the mixed-precision filter (HXCheby with chebMixedPrec, kohnShamDFTOperatorDevice.cc:3899-3915)
+int launch_pack_rows_f32(dftfe_b200_ctx *ctx, const double *x, int ncols, int ldx, int64_t nRows,
+                         const uint32_t *rows, int64_t row0, float *buf) {
   if (nRows == 0) return 0;
-  ProfScope ps(ctx, toBuf ? "ghost_pack" : "ghost_unpack");
-  copy_rows_kernel<<<grid_for(ctx, nRows * ncols), 256, 0, ctx->stream>>>(x, ncols, ldx, row0, nRows, buf, toBuf);
+  DB_CHECK(vec_ok(x, ncols, ldx), "FP32 ghost payload needs an even column count and 16-byte aligned rows");
+  ProfScope ps(ctx, "ghost_pack");
+  pack_rows_vec_kernel<float><<<grid_rows(ctx, nRows), 256, 0, ctx->stream>>>(x, ncols, ldx, nRows, rows, row0, buf);
+  DB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_unpack_rows(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx, int64_t row0, int64_t nRows,
+                       const double *buf) {
+  if (nRows == 0) return 0;
+  ProfScope ps(ctx, "ghost_unpack");
+  if (vec_ok(x, ncols, ldx) && vec_ok(buf, ncols, ncols) && !ctx->force_scalar_row_kernels)
+    unpack_rows_vec_kernel<double><<<grid_rows(ctx, nRows), 256, 0, ctx->stream>>>(x, ncols, ldx, row0, nRows, buf);
+  else
+    copy_rows_kernel<<<grid_for(ctx, nRows * ncols), 256, 0, ctx->stream>>>(x, ncols, ldx, row0, nRows,
+                                                                           const_cast<double *>(buf), 0);
+  DB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_unpack_rows_f32(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx, int64_t row0, int64_t nRows,
+                           const float *buf) {
+  if (nRows == 0) return 0;
+  ProfScope ps(ctx, "ghost_unpack");
+  unpack_rows_vec_kernel<float><<<grid_rows(ctx, nRows), 256, 0, ctx->stream>>>(x, ncols, ldx, row0, nRows, buf);
   DB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -243,7 +586,21 @@ int launch_unpack_add(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx, const 
                       const double *rowScale) {
   if (ctx->nBoundaryRows == 0) return 0;
   ProfScope ps(ctx, "ghost_unpack");
-  unpack_add_kernel<<<grid_for(ctx, ctx->nBoundaryRows * ncols), 256, 0, ctx->stream>>>(
+  if (vec_ok(x, ncols, ldx) && vec_ok(buf, ncols, ncols) && !ctx->force_scalar_row_kernels)
+    unpack_add_vec_kernel<double><<<grid_rows(ctx, ctx->nBoundaryRows), 256, 0, ctx->stream>>>(
+        x, ncols, ldx, ctx->nBoundaryRows, ctx->bndRows.p, ctx->bndStarts.p, ctx->bndSlots.p, buf, rowScale);
+  else
+    unpack_add_kernel<<<grid_for(ctx, ctx->nBoundaryRows * ncols), 256, 0, ctx->stream>>>(
+        x, ncols, ldx, ctx->nBoundaryRows, ctx->bndRows.p, ctx->bndStarts.p, ctx->bndSlots.p, buf, rowScale);
+  DB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_unpack_add_f32(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx, const float *buf,
+                          const double *rowScale) {
+  if (ctx->nBoundaryRows == 0) return 0;
+  ProfScope ps(ctx, "ghost_unpack");
+  unpack_add_vec_kernel<float><<<grid_rows(ctx, ctx->nBoundaryRows), 256, 0, ctx->stream>>>(
       x, ncols, ldx, ctx->nBoundaryRows, ctx->bndRows.p, ctx->bndStarts.p, ctx->bndSlots.p, buf, rowScale);
   DB_CUDA(cudaGetLastError());
   return 0;
