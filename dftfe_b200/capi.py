@@ -55,6 +55,14 @@ class SolveParams(C.Structure):
         ("compute_residual", C.c_int32),
         ("use_cgs_rr", C.c_int32),
         ("reproducible_output", C.c_int32),
+        ("use_mixed_prec_overall", C.c_int32),
+        ("use_mixed_prec_cheby", C.c_int32),
+        ("use_mixed_prec_cgs_o", C.c_int32),
+        ("use_mixed_prec_cgs_sr", C.c_int32),
+        ("use_mixed_prec_xthx_spectrum_split", C.c_int32),
+        ("use_mixed_prec_subspace_rot_rr", C.c_int32),
+        ("num_core_wfc_xthx", C.c_int32),
+        ("n_core_states", C.c_int32),
         ("reserved", C.c_int32),
         ("first_scf_scaling", C.c_double),
     ]
@@ -67,6 +75,8 @@ EXPORTED_SYMBOLS = [
     "dftfe_b200_set_constraints", "dftfe_b200_set_mass", "dftfe_b200_set_ghost_pattern",
     "dftfe_b200_nccl_unique_id", "dftfe_b200_comm_init", "dftfe_b200_comm_init_loopback",
     "dftfe_b200_set_nonlocal", "dftfe_b200_set_cell_hamiltonian", "dftfe_b200_set_cell_hamiltonian_host",
+    "dftfe_b200_strided_copy_to_block", "dftfe_b200_strided_copy_from_block", "dftfe_b200_strided_block_scale",
+    "dftfe_b200_set_cell_hamiltonian_kpt", "dftfe_b200_reinit_kpoint_spin_index", "dftfe_b200_rotate_spectrum_split",
     "dftfe_b200_update_ghost_values", "dftfe_b200_accumulate_add_locally_owned", "dftfe_b200_zero_out_ghosts",
     "dftfe_b200_constraints_distribute", "dftfe_b200_constraints_distribute_slave_to_master",
     "dftfe_b200_constraints_set_zero", "dftfe_b200_hx", "dftfe_b200_hx_cheby", "dftfe_b200_cheb_filter",
@@ -225,14 +235,23 @@ class Operator:
         _check(self.lib.dftfe_b200_comm_init_loopback(self.h, C.c_int32(group_id), C.c_int32(rank), C.c_int32(nranks)))
 
     # ---- Hamiltonian ------------------------------------------------------
-    def set_cell_hamiltonian(self, H):
-        """H: torch CUDA tensor or numpy array [nCells, n, n] (mem[c,I,J] = H_c(I,J))."""
+    def set_cell_hamiltonian(self, H, kptSpinIndex: int = 0):
+        """H: torch CUDA tensor or numpy array [nCells, n, n] (mem[c,I,J] = H_c(I,J)); stored as the
+        (k-point, spin) set ``kptSpinIndex`` and made active."""
         if isinstance(H, np.ndarray):
+            import torch
+
             assert np.iscomplexobj(H) == self.complex, "cell Hamiltonian dtype does not match the context"
             Hc = _np(H, np.complex128 if self.complex else np.float64)
-            _check(self.lib.dftfe_b200_set_cell_hamiltonian_host(self.h, _ptr(Hc)))
-        else:
-            _check(self.lib.dftfe_b200_set_cell_hamiltonian(self.h, _dptr(H)))
+            if kptSpinIndex == 0:
+                _check(self.lib.dftfe_b200_set_cell_hamiltonian_host(self.h, _ptr(Hc)))
+                return
+            H = torch.from_numpy(Hc).cuda(self.device)
+        _check(self.lib.dftfe_b200_set_cell_hamiltonian_kpt(self.h, C.c_int32(kptSpinIndex), _dptr(H)))
+
+    def reinitkPointSpinIndex(self, kptSpinIndex: int):
+        """kohnShamDFTOperatorDevice.cc:1033-1058: switch to a stored (k-point, spin) Hamiltonian set."""
+        _check(self.lib.dftfe_b200_reinit_kpoint_spin_index(self.h, C.c_int32(kptSpinIndex)))
 
     # ---- MultiVector / constraints ---------------------------------------
     def update_ghost_values(self, x):
@@ -253,27 +272,44 @@ class Operator:
     def set_zero(self, x):
         _check(self.lib.dftfe_b200_constraints_set_zero(self.h, _dptr(x), C.c_int32(x.shape[1])))
 
+    # ---- deviceKernelsGeneric (utils/DeviceKernelsGeneric.cc:156-209, 257-278) ----
+    def stridedCopyToBlock(self, X, j0: int, block):
+        _check(self.lib.dftfe_b200_strided_copy_to_block(self.h, _dptr(X), C.c_int32(X.shape[1]), C.c_int32(j0),
+                                                         _dptr(block), C.c_int32(block.shape[1])))
+
+    def stridedCopyFromBlock(self, X, j0: int, block):
+        _check(self.lib.dftfe_b200_strided_copy_from_block(self.h, _dptr(X), C.c_int32(X.shape[1]), C.c_int32(j0),
+                                                           _dptr(block), C.c_int32(block.shape[1])))
+
+    def stridedBlockScale(self, x, alpha: float, which: int):
+        """which: 0 none, 1 M^1/2, 2 M^-1/2."""
+        _check(self.lib.dftfe_b200_strided_block_scale(self.h, _dptr(x), C.c_int32(x.shape[1]), C.c_double(alpha),
+                                                       C.c_int32(which)))
+
     # ---- operatorDFTDeviceClass -------------------------------------------
     def HX(self, src, dst, scaleFlag: bool, scalar: float, doUnscalingSrc: bool = True):
         """kohnShamDFTOperatorDevice.cc:3765-3860."""
         _check(self.lib.dftfe_b200_hx(self.h, _dptr(src), _dptr(dst), C.c_int32(src.shape[1]), C.c_int32(int(scaleFlag)),
                                       C.c_double(scalar), C.c_int32(int(doUnscalingSrc))))
 
-    def HXCheby(self, src, dst):
-        """kohnShamDFTOperatorDevice.cc:3874-3997 (FP64)."""
-        _check(self.lib.dftfe_b200_hx_cheby(self.h, _dptr(src), _dptr(dst), C.c_int32(src.shape[1])))
+    def HXCheby(self, src, dst, mixPrecFlag: bool = False):
+        """kohnShamDFTOperatorDevice.cc:3874-3997; mixPrecFlag: FP32 ghost payloads."""
+        _check(self.lib.dftfe_b200_hx_cheby(self.h, _dptr(src), _dptr(dst), C.c_int32(src.shape[1]),
+                                            C.c_int32(int(mixPrecFlag))))
 
-    def chebyshevFilter(self, X, Y, m: int, a: float, b: float, a0: float):
+    def chebyshevFilter(self, X, Y, m: int, a: float, b: float, a0: float, mixedPrec: bool = False):
         """linearAlgebraOperationsDevice.cc:531-727; X in/out (Loewdin basis), Y scratch."""
         _check(self.lib.dftfe_b200_cheb_filter(self.h, _dptr(X), _dptr(Y), C.c_int32(X.shape[1]), C.c_int32(m),
-                                               C.c_double(a), C.c_double(b), C.c_double(a0)))
+                                               C.c_double(a), C.c_double(b), C.c_double(a0),
+                                               C.c_int32(int(mixedPrec))))
 
-    def chebyshevFilterAll(self, X, m: int, a: float, b: float, a0: float):
+    def chebyshevFilterAll(self, X, m: int, a: float, b: float, a0: float, mixedPrec: bool = False):
         """solver .cc:376-526: blocked filter loop over the full device-resident X [M, N]."""
         _check(self.lib.dftfe_b200_cheb_filter_all(self.h, _dptr(X), C.c_int32(X.shape[1]), C.c_int32(m),
-                                                   C.c_double(a), C.c_double(b), C.c_double(a0)))
+                                                   C.c_double(a), C.c_double(b), C.c_double(a0),
+                                                   C.c_int32(int(mixedPrec))))
 
-    def chebyshevFilterAllHost(self, X_host, m: int, a: float, b: float, a0: float):
+    def chebyshevFilterAllHost(self, X_host, m: int, a: float, b: float, a0: float, mixedPrec: bool = False):
         """Same with X in host memory (torch CPU tensor, pinned preferred, or numpy): copies pipelined."""
         if isinstance(X_host, np.ndarray):
             assert X_host.dtype == np.float64 and X_host.flags.c_contiguous
@@ -282,17 +318,26 @@ class Operator:
             assert (not X_host.is_cuda) and X_host.is_contiguous()
             ptr, N = X_host.data_ptr(), X_host.shape[1]
         _check(self.lib.dftfe_b200_cheb_filter_all_host(self.h, C.c_void_p(ptr), C.c_int32(N), C.c_int32(m),
-                                                        C.c_double(a), C.c_double(b), C.c_double(a0)))
+                                                        C.c_double(a), C.c_double(b), C.c_double(a0),
+                                                        C.c_int32(int(mixedPrec))))
 
-    def XtX(self, X, S):
-        _check(self.lib.dftfe_b200_xtx(self.h, _dptr(X), C.c_int32(X.shape[1]), _dptr(S)))
+    def XtX(self, X, S, mixedPrec: bool = False):
+        """fillParallelOverlapMat[MixedPrec]Scalapack (linearAlgebraOperationsDevice.cc:3078-3240, 3543-3798)."""
+        _check(self.lib.dftfe_b200_xtx(self.h, _dptr(X), C.c_int32(X.shape[1]), _dptr(S), C.c_int32(int(mixedPrec))))
 
-    def XtHX(self, X, Hp):
-        """kohnShamDFTOperatorDevice.cc:4001-4157."""
-        _check(self.lib.dftfe_b200_xthx(self.h, _dptr(X), C.c_int32(X.shape[1]), _dptr(Hp)))
+    def XtHX(self, X, Hp, Noc: int = 0, mixedPrec: bool = False):
+        """kohnShamDFTOperatorDevice.cc:4001-4157; mixedPrec + Noc: XtHXMixedPrecOverlapComputeCommun (:4550-5080)."""
+        _check(self.lib.dftfe_b200_xthx(self.h, _dptr(X), C.c_int32(X.shape[1]), C.c_int32(Noc), _dptr(Hp),
+                                        C.c_int32(int(mixedPrec))))
 
-    def subspaceRotation(self, X, Q):
-        _check(self.lib.dftfe_b200_rotate(self.h, _dptr(X), C.c_int32(X.shape[1]), _dptr(Q)))
+    def subspaceRotation(self, X, Q, mixedMode: int = 0):
+        """X <- X Q.  mixedMode 1 / 2: subspaceRotationCGSMixedPrec / RRMixedPrec."""
+        _check(self.lib.dftfe_b200_rotate(self.h, _dptr(X), C.c_int32(X.shape[1]), _dptr(Q), C.c_int32(mixedMode)))
+
+    def subspaceRotationSpectrumSplit(self, X, Q, XFrac):
+        """XFrac = X Q[:, N-Nfr:] (linearAlgebraOperationsDevice.cc:1446-1830)."""
+        _check(self.lib.dftfe_b200_rotate_spectrum_split(self.h, _dptr(X), C.c_int32(X.shape[1]), _dptr(Q),
+                                                         C.c_int32(XFrac.shape[1]), _dptr(XFrac)))
 
     def lanczosLowerUpperBoundEigenSpectrum(self, reproducible: bool = False):
         out = (C.c_double * 2)()
@@ -347,18 +392,30 @@ class ChebyshevSolver:
 
     def solve(self, X, isFirstFilteringCall: bool, computeResidual: bool = True, chebyshevOrder: int = 0,
               isFirstScf: bool = False, isPseudopotential: bool = True, useCgsRR: bool = False,
-              reuseLanczos: bool = False, reproducible: bool = False, firstScfScaling: float = 1.34):
-        """X: torch CUDA [M, N] float64, in/out.  Returns (eigenvalues, residuals, upper bound)."""
+              reuseLanczos: bool = False, reproducible: bool = False, firstScfScaling: float = 1.34,
+              useMixedPrecOverall: bool = False, mixedPrec: Sequence[str] = (), numCoreWfcXtHX: int = 0,
+              XFrac=None):
+        """X: torch CUDA [M, N] float64 / complex128, in/out.  Returns (eigenvalues, residuals, upper bound).
+        mixedPrec: subset of {"cheby", "cgs_o", "cgs_sr", "xthx", "rot_rr"} (dftParameters::useMixedPrec*), active
+        when useMixedPrecOverall.  XFrac [M, Nfr]: spectrum splitting (eigenValues.size() = Nfr < N)."""
         N = X.shape[1]
+        ncore = 0 if XFrac is None else N - XFrac.shape[1]
+        mp = set(mixedPrec)
+        assert mp <= {"cheby", "cgs_o", "cgs_sr", "xthx", "rot_rr"}
         p = SolveParams(chebyshev_order=chebyshevOrder, wfc_block=0,
                         is_first_filtering_call=int(isFirstFilteringCall),
                         reuse_lanczos_upper_bound=int(reuseLanczos), is_first_scf=int(isFirstScf),
                         is_pseudopotential=int(isPseudopotential), compute_residual=int(computeResidual),
-                        use_cgs_rr=int(useCgsRR), reproducible_output=int(reproducible), reserved=0,
-                        first_scf_scaling=firstScfScaling)
-        eig = np.empty(N)
-        res = np.empty(N)
+                        use_cgs_rr=int(useCgsRR), reproducible_output=int(reproducible),
+                        use_mixed_prec_overall=int(useMixedPrecOverall), use_mixed_prec_cheby=int("cheby" in mp),
+                        use_mixed_prec_cgs_o=int("cgs_o" in mp), use_mixed_prec_cgs_sr=int("cgs_sr" in mp),
+                        use_mixed_prec_xthx_spectrum_split=int("xthx" in mp),
+                        use_mixed_prec_subspace_rot_rr=int("rot_rr" in mp), num_core_wfc_xthx=numCoreWfcXtHX,
+                        n_core_states=ncore, reserved=0, first_scf_scaling=firstScfScaling)
+        nev = N - ncore
+        eig = np.empty(nev)
+        res = np.empty(nev)
         ub = C.c_double()
-        _check(self.op.lib.dftfe_b200_solve(self.op.h, _dptr(X), C.c_int32(N), C.byref(p), _ptr(eig), _ptr(res),
-                                            C.byref(ub)))
+        _check(self.op.lib.dftfe_b200_solve(self.op.h, _dptr(X), _dptr(XFrac) if XFrac is not None else None,
+                                            C.c_int32(N), C.byref(p), _ptr(eig), _ptr(res), C.byref(ub)))
         return eig, (res if computeResidual else None), ub.value

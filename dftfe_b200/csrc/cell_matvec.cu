@@ -579,11 +579,11 @@ int launch_impl2(dftfe_b200_ctx *ctx, const double *src, double *dst, int ncols,
     if (fast) {
       const int grid = std::min(nItems, ctx->num_sms);
       cell_matvec_persistent_kernel<NODES, CPLX><<<grid, P::THREADS, P::SMEM, ctx->stream>>>(
-          ctx->Htiled.p, ctx->cellRowsFlagged.p, ctx->colourCells.p + ctx->colourStart_h[k], nItems, src, dst, ldx,
+          ctx->Hactive, ctx->cellRowsFlagged.p, ctx->colourCells.p + ctx->colourStart_h[k], nItems, src, dst, ldx,
           nColTiles, ep);
     } else {
       cell_matvec_kernel<NODES, CPLX><<<nItems, C::THREADS, C::SMEM, ctx->stream>>>(
-          ctx->Htiled.p, ctx->cellRowsFlagged.p, ctx->colourCells.p + ctx->colourStart_h[k], src, dst, ncols, ldx,
+          ctx->Hactive, ctx->cellRowsFlagged.p, ctx->colourCells.p + ctx->colourStart_h[k], src, dst, ncols, ldx,
           nColTiles, ep);
     }
   }
@@ -601,14 +601,16 @@ int launch_impl(dftfe_b200_ctx *ctx, const double *src, double *dst, int ncols, 
 template <int NODES>
 int retile_impl(dftfe_b200_ctx *ctx, const double *H_d) {
   const size_t perCell = ctx->cplx ? CellCfg<NODES, true>::HT_PER_CELL : CellCfg<NODES, false>::HT_PER_CELL;
-  DB_TRY(ctx->Htiled.alloc((size_t)ctx->nC * perCell));
+  dftfe_b200::DevBuf<double> &Ht = ctx->Hsets[ctx->activeK];
+  DB_TRY(Ht.alloc((size_t)ctx->nC * perCell));
+  ctx->Hactive = Ht.p;
   ctx->launches += 1;
   if (ctx->cplx)
     retile_H_kernel<NODES, true><<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(
-        H_d, ctx->Htiled.p, ctx->nC, ctx->cellRowsFlagged.p, ctx->rowIn.p, ctx->rowOut.p);
+        H_d, Ht.p, ctx->nC, ctx->cellRowsFlagged.p, ctx->rowIn.p, ctx->rowOut.p);
   else
     retile_H_kernel<NODES, false><<<ctx->num_sms * 8, 256, 0, ctx->stream>>>(
-        H_d, ctx->Htiled.p, ctx->nC, ctx->cellRowsFlagged.p, ctx->rowIn.p, ctx->rowOut.p);
+        H_d, Ht.p, ctx->nC, ctx->cellRowsFlagged.p, ctx->rowIn.p, ctx->rowOut.p);
   DB_CUDA(cudaGetLastError());
   return 0;
 }

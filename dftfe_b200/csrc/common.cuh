@@ -201,7 +201,16 @@ struct dftfe_b200_ctx {
   std::vector<int64_t> targetOffsets_h;
   int64_t nSend = 0;
   dftfe_b200::DevBuf<uint32_t> sendRows;         // ownedLocalIndicesForTargetProcs
-  dftfe_b200::DevBuf<double> sendBuf, recvBuf;   // nSend*B each
+  // Two "lanes" (stream + block scratch + exchange payload buffers each): the blocked filter loop keeps two
+  // wavefunction blocks in flight so that one block's ghost exchange overlaps the other block's cell kernels
+  // (the reference's two-block chebyshevFilter, linearAlgebraOperationsDevice.cc:734-1443).  `lane` selects
+  // the buffers; `stream` is re-pointed at the lane's stream while its work is enqueued.
+  int lane = 0;
+  dftfe_b200::DevBuf<double> sendB[2], recvB[2];  // max(nSend, G)*B each
+  cudaStream_t laneStream[2] = {nullptr, nullptr};
+  cudaEvent_t laneEvent[2] = {nullptr, nullptr};
+  cudaEvent_t forkEvent = nullptr;
+  int overlap_lanes = -1;  // option "overlap_lanes": -1 auto (on when nranks > 1), 0 off, 1 on
   // transposed unpack map: boundary row -> positions in recvBuf
   int64_t nBoundaryRows = 0;
   dftfe_b200::DevBuf<uint32_t> bndRows, bndStarts, bndSlots;
@@ -211,7 +220,11 @@ struct dftfe_b200_ctx {
   // --- cell Hamiltonian (fragment-major)
   bool have_H = false;
   bool force_generic_cell_kernel = false;  // test hook: run the non-persistent kernel
-  dftfe_b200::DevBuf<double> Htiled;
+  bool force_scalar_row_kernels = false;   // test hook: scalar fallbacks of the HBM-bound row kernels
+  // one re-tiled set per (k-point, spin) index (reinitkPointSpinIndex, kohnShamDFTOperatorDevice.cc:1033-1058)
+  std::map<int, dftfe_b200::DevBuf<double>> Hsets;
+  int activeK = 0;
+  double *Hactive = nullptr;
   dftfe_b200::DevBuf<double> Hstage;   // staging for host uploads
 
   // --- non-local projectors (nonlocal.cu)
@@ -225,7 +238,8 @@ struct dftfe_b200_ctx {
 
   // --- solver state / scratch
   dftfe_b200::DevBuf<double> blockX, blockY;      // (M+G)*B
-  dftfe_b200::DevBuf<double> blockX2;             // second block buffer of the host-pipelined filter
+  dftfe_b200::DevBuf<double> blockX2;             // second block buffer (host-pipelined filter; lane 1)
+  dftfe_b200::DevBuf<double> blockY2;             // lane 1 scratch
   cudaStream_t copyIn = nullptr, copyOut = nullptr;
   dftfe_b200::DevBuf<double> HXfull;              // M*Bw
   dftfe_b200::DevBuf<double> denseA, denseB, denseC, denseW;  // N*N scratch
@@ -237,6 +251,10 @@ struct dftfe_b200_ctx {
   dftfe_b200::DevBuf<int32_t> projTiles;          // tile list of the DMMA projection kernel
   dftfe_b200::DevBuf<double> projWs;              // its split-m partial tiles
   bool use_cublas_dense = false;                  // option "cublas_projections": A/B against cuBLAS Dgemm
+  // mixed-precision projections / rotations (mixed_precision.cu)
+  dftfe_b200::DevBuf<float> mpXsp, mpSp, mpBlockSp;
+  dftfe_b200::DevBuf<double> mpDp;
+  dftfe_b200::DevBuf<float> arTmpF;
   dftfe_b200::DevBuf<int> devInfo;
   dftfe_b200::DevBuf<double> cusolverWork;
   double a0 = 0, bLow = 0, bUp = 0;
@@ -284,8 +302,8 @@ int launch_distribute(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx, const 
 int launch_slave_to_master(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx, const double *masterScale);
 int launch_set_zero_rows(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx);
 
-int ghost_update(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx);
-int ghost_accumulate(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx, const double *rowScale);
+int ghost_update(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx, bool fp32 = false);
+int ghost_accumulate(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx, const double *rowScale, bool fp32 = false);
 int ghost_zero(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx);
 
 int launch_row_scale(dftfe_b200_ctx *ctx, double *x, int64_t rows, int ncols, int ldx, double alpha,
@@ -298,6 +316,7 @@ int launch_orphan_first_touch(dftfe_b200_ctx *ctx, const double *src, double *ds
                               const EpilogueParams &ep);
 
 int allreduce_sum(dftfe_b200_ctx *ctx, double *buf, size_t count);
+int allreduce_sum_f32(dftfe_b200_ctx *ctx, float *buf, size_t count);
 
 // nonlocal.cu
 int nonlocal_setup(dftfe_b200_ctx *ctx, int32_t nAtoms, const int32_t *nProj, const double *V, int64_t nEntries,
@@ -310,14 +329,22 @@ bool dmma_projection_usable(const dftfe_b200_ctx *ctx, int N, int lda, int ldb, 
                             int nColsC);
 int launch_xty(dftfe_b200_ctx *ctx, const double *A, int lda, int iOff, const double *B, int ldb, int jOff,
                int nRowsC, int nColsC, int iGlobal, int jGlobal, bool lowerOnly, double *C, int ldc);
-bool dmma_rotation_usable(int N);
-int launch_xq(dftfe_b200_ctx *ctx, const double *X, int N, int64_t rows, const double *Qrm, double *Out);
+bool dmma_rotation_usable(int N, int Nout, int ldq, int ldo);
+int launch_xq(dftfe_b200_ctx *ctx, const double *X, int N, int64_t rows, const double *Qrm, int ldq, int Nout,
+              double *Out, int ldo);
 int launch_transpose_square(dftfe_b200_ctx *ctx, const double *in, double *out, int N);
 
+// mixed_precision.cu
+int xtx_mixed_impl(dftfe_b200_ctx *ctx, const double *X, int N, double *S);
+int xthx_mixed_impl(dftfe_b200_ctx *ctx, const double *X, int N, int Noc, double *Hp);
+int rotate_mixed_impl(dftfe_b200_ctx *ctx, double *X, int N, const double *Q, bool qColMajor, int mode);
+
 // high-level pieces (solver.cu)
+int apply_H_to_columns(dftfe_b200_ctx *ctx, const double *X, int N, int j0, int ncols);
 int op_hx(dftfe_b200_ctx *ctx, double *src, double *dst, int ncols, int scaleFlag, double scalar,
           int doUnscale);
-int op_hx_cheby(dftfe_b200_ctx *ctx, double *src, double *dst, int ncols);
-int op_fused_apply(dftfe_b200_ctx *ctx, double *src, double *dst, int ncols, double a, double b, double s);
+int op_hx_cheby(dftfe_b200_ctx *ctx, double *src, double *dst, int ncols, bool mixedPrec = false);
+int op_fused_apply(dftfe_b200_ctx *ctx, double *src, double *dst, int ncols, double a, double b, double s,
+                   bool fp32Comm = false);
 
 }  // namespace dftfe_b200

@@ -146,6 +146,11 @@ void dftfe_b200_destroy(dftfe_b200_ctx *ctx) {
       cudaEventDestroy(pr.first);
       cudaEventDestroy(pr.second);
     }
+  for (int l = 0; l < 2; ++l) {
+    if (ctx->laneStream[l]) cudaStreamDestroy(ctx->laneStream[l]);
+    if (ctx->laneEvent[l]) cudaEventDestroy(ctx->laneEvent[l]);
+  }
+  if (ctx->forkEvent) cudaEventDestroy(ctx->forkEvent);
   if (ctx->copyIn) cudaStreamDestroy(ctx->copyIn);
   if (ctx->copyOut) cudaStreamDestroy(ctx->copyOut);
   if (ctx->nccl && nccl_api()) nccl_api()->CommDestroy(ctx->nccl);
@@ -435,12 +440,29 @@ int dftfe_b200_set_nonlocal(dftfe_b200_ctx *ctx, int32_t n_atoms, const int32_t 
   return nonlocal_setup(ctx, n_atoms, n_proj_per_atom_h, V_h, n_entries, entry_cell_h, entry_atom_h, C_h, p_max);
 }
 
-int dftfe_b200_set_cell_hamiltonian(dftfe_b200_ctx *ctx, const double *H_d) {
+int dftfe_b200_set_cell_hamiltonian_kpt(dftfe_b200_ctx *ctx, int32_t kpt_spin_index, const double *H_d) {
   DB_CTX(ctx);
   DB_CHECK(H_d || ctx->nC == 0, "set_cell_hamiltonian: null pointer");
+  DB_CHECK(kpt_spin_index >= 0, "set_cell_hamiltonian: negative (k-point, spin) index");
+  if (!ctx->have_H) ctx->Hsets.clear();  // constraints / mass changed: every stored set is stale
+  ctx->activeK = kpt_spin_index;
   if (ctx->nC > 0) DB_TRY(retile_cell_hamiltonian(ctx, H_d));
   DB_CUDA(cudaStreamSynchronize(ctx->stream));  // caller's buffer is free after return
   ctx->have_H = true;
+  return 0;
+}
+
+int dftfe_b200_set_cell_hamiltonian(dftfe_b200_ctx *ctx, const double *H_d) {
+  return dftfe_b200_set_cell_hamiltonian_kpt(ctx, 0, H_d);
+}
+
+int dftfe_b200_reinit_kpoint_spin_index(dftfe_b200_ctx *ctx, int32_t kpt_spin_index) {
+  DB_CTX(ctx);
+  auto it = ctx->Hsets.find(kpt_spin_index);
+  DB_CHECK(ctx->have_H && it != ctx->Hsets.end() && (it->second.p || ctx->nC == 0),
+           "reinit_kpoint_spin_index: no cell Hamiltonian stored for index %d", kpt_spin_index);
+  ctx->activeK = kpt_spin_index;
+  ctx->Hactive = it->second.p;
   return 0;
 }
 
@@ -478,6 +500,32 @@ int dftfe_b200_constraints_set_zero(dftfe_b200_ctx *ctx, double *x_d, int32_t nc
   return launch_set_zero_rows(ctx, x_d, ncols * ctx->cm, ncols * ctx->cm);
 }
 
+int dftfe_b200_strided_copy_to_block(dftfe_b200_ctx *ctx, const double *X_d, int32_t N, int32_t j0, double *block_d,
+                                     int32_t ncols) {
+  DB_CTX(ctx);
+  DB_CHECK(j0 >= 0 && ncols >= 1 && j0 + ncols <= N, "strided_copy_to_block: columns [%d, %d) outside [0, %d)", j0,
+           j0 + ncols, N);
+  const int cm = ctx->cm;
+  return launch_block_copy_from_full(ctx, X_d, N * cm, j0 * cm, block_d, ncols * cm, ctx->M, nullptr);
+}
+
+int dftfe_b200_strided_copy_from_block(dftfe_b200_ctx *ctx, double *X_d, int32_t N, int32_t j0, const double *block_d,
+                                       int32_t ncols) {
+  DB_CTX(ctx);
+  DB_CHECK(j0 >= 0 && ncols >= 1 && j0 + ncols <= N, "strided_copy_from_block: columns [%d, %d) outside [0, %d)", j0,
+           j0 + ncols, N);
+  const int cm = ctx->cm;
+  return launch_block_copy_to_full(ctx, X_d, N * cm, j0 * cm, block_d, ncols * cm, ctx->M, nullptr);
+}
+
+int dftfe_b200_strided_block_scale(dftfe_b200_ctx *ctx, double *x_d, int32_t ncols, double alpha, int32_t which) {
+  DB_CTX(ctx);
+  DB_CHECK(ctx->have_mass || which == 0, "strided_block_scale: set_mass first");
+  const double *s = which == 1 ? ctx->sqrtM.p : (which == 2 ? ctx->invSqrtM.p : nullptr);
+  DB_CHECK(which >= 0 && which <= 2, "strided_block_scale: which must be 0 (none), 1 (M^1/2) or 2 (M^-1/2)");
+  return launch_row_scale(ctx, x_d, ctx->M, ncols * ctx->cm, ncols * ctx->cm, alpha, s);
+}
+
 int dftfe_b200_get_colouring(dftfe_b200_ctx *ctx, int32_t *n_colours_out, int32_t *cell_colour_out_h) {
   DB_CTX(ctx);
   DB_CHECK(ctx->have_map, "get_colouring: set_index_map first");
@@ -491,6 +539,14 @@ int dftfe_b200_set_option(dftfe_b200_ctx *ctx, const char *name, int32_t value) 
   DB_CHECK(name, "set_option: null name");
   if (std::strcmp(name, "generic_cell_kernel") == 0) {
     ctx->force_generic_cell_kernel = value != 0;
+    return 0;
+  }
+  if (std::strcmp(name, "scalar_row_kernels") == 0) {
+    ctx->force_scalar_row_kernels = value != 0;
+    return 0;
+  }
+  if (std::strcmp(name, "overlap_lanes") == 0) {
+    ctx->overlap_lanes = value;
     return 0;
   }
   if (std::strcmp(name, "cublas_projections") == 0) {

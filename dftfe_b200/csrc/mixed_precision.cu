@@ -1,0 +1,251 @@
+// Mixed-precision variants of the subspace projections and rotations (real build).
+//
+// Reference (all under src/linAlg/linearAlgebraOperationsDevice.cc unless stated):
+//   fillParallelOverlapMatMixedPrecScalapack      :3543-3798  S = X^T X, diagonal Bw x Bw blocks FP64, the blocks
+//                                                             below them FP32 from an FP32 copy of X, FP32 all-reduce
+//   XtHXMixedPrecOverlapComputeCommun (kohnShamDFTOperatorDevice.cc:4550-5080)
+//                                                             Hp = X^T H~ X, column blocks that end inside the
+//                                                             first Noc states entirely FP32, the rest FP64
+//   subspaceRotationCGSMixedPrecScalapack         :2243-2658  X <- X U (U = L^-T): diagonal blocks FP64,
+//                                                             off-diagonal FP32
+//   subspaceRotationRRMixedPrecScalapack          :2660-3076  X <- X diag(Q) (FP64) + X_sp (Q - diag Q)_sp (FP32)
+// The reference issues cuBLAS Sgemm for every FP32 block; so does this file (plain library GEMMs - the FP64
+// diagonal blocks go through the hand-written DMMA kernel of projection.cu).  The FP32 partial sums are
+// all-reduced as floats, like DeviceCCLWrapper::deviceDirectAllReduceMixedPrecGroupWrapper
+// (utils/DeviceDirectCCLWrapper.cc:196-261).
+#include <algorithm>
+
+#include "common.cuh"
+
+namespace dftfe_b200 {
+
+namespace {
+
+__global__ void to_float_rows_kernel(const double *__restrict__ in, int64_t ldi, float *__restrict__ out, int64_t ldo,
+                                     int ncols, int64_t rows) {
+  // one warp per row, float2/double2 when the shapes allow
+  const int lane = threadIdx.x & 31;
+  const int64_t w0 = (blockIdx.x * (int64_t)blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * (int64_t)blockDim.x) >> 5;
+  const bool vec = (ncols % 2 == 0) && (ldi % 2 == 0) && (ldo % 2 == 0) &&
+                   ((reinterpret_cast<uintptr_t>(in) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 7) == 0);
+  for (int64_t r = w0; r < rows; r += nw) {
+    const double *pi = in + r * ldi;
+    float *po = out + r * ldo;
+    if (vec) {
+      for (int c = lane * 2; c < ncols; c += 64) {
+        const double2 v = *reinterpret_cast<const double2 *>(pi + c);
+        *reinterpret_cast<float2 *>(po + c) = make_float2((float)v.x, (float)v.y);
+      }
+    } else {
+      for (int c = lane; c < ncols; c += 32) po[c] = (float)pi[c];
+    }
+  }
+}
+
+// Qsp (row-major N x N float) = off-diagonal part of Q; mode 1: the Bw x Bw diagonal blocks are dropped,
+// mode 2: only the diagonal entries.  qColMajor: Q(k,j) at k + j*N, else k*N + j.
+__global__ void split_rotation_kernel(const double *__restrict__ Q, int N, int qColMajor, int mode, int Bw,
+                                      float *__restrict__ Qsp, double *__restrict__ diag) {
+  const int64_t total = (int64_t)N * N;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int k = idx / N, j = idx % N;
+    const double v = Q[qColMajor ? ((int64_t)k + (int64_t)j * N) : idx];
+    const bool onDiag = mode == 1 ? (k / Bw == j / Bw) : (k == j);
+    Qsp[idx] = onDiag ? 0.0f : (float)v;
+    if (mode == 2 && k == j) diag[k] = v;
+  }
+}
+
+// X[r, :] = X[r, :] * diag[:] + T[r, :]
+__global__ void combine_diag_kernel(double *__restrict__ X, int N, int64_t rows, const double *__restrict__ diag,
+                                    const float *__restrict__ T) {
+  const int64_t total = rows * N;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x)
+    X[idx] = X[idx] * diag[idx % N] + (double)T[idx];
+}
+
+// X[r, :] = D[r, :] + T[r, :]
+__global__ void combine_block_kernel(double *__restrict__ X, const double *__restrict__ D,
+                                     const float *__restrict__ T, int64_t total) {
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x)
+    X[idx] = D[idx] + (double)T[idx];
+}
+
+// full symmetric S (column- == row-major, double) from FP64 diagonal blocks (dp: Bw x N, block of column j at
+// dp[r + j*Bw]) and the FP32 strictly-lower blocks (sp: column-major N x N)
+__global__ void merge_overlap_kernel(const double *__restrict__ dp, const float *__restrict__ sp, int N, int Bw,
+                                     double *__restrict__ S) {
+  const int64_t total = (int64_t)N * N;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int a = idx % N, b = idx / N;
+    const int i = max(a, b), j = min(a, b);  // lower-triangular source element
+    const int bj = j / Bw;
+    S[idx] = (i / Bw == bj) ? dp[(i - bj * Bw) + (int64_t)j * Bw] : (double)sp[(int64_t)i + (int64_t)j * N];
+  }
+}
+
+// full symmetric Hp from the FP64 lower blocks (G, column-major N x N) and the FP32 column blocks (sp) that end
+// inside the first Noc states
+__global__ void merge_projham_kernel(const double *__restrict__ G, const float *__restrict__ sp, int N, int Bw,
+                                     int Noc, double *__restrict__ Hp) {
+  const int64_t total = (int64_t)N * N;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int a = idx % N, b = idx / N;
+    const int i = max(a, b), j = min(a, b);
+    const int j0 = (j / Bw) * Bw;
+    const bool single = (j0 + min(Bw, N - j0)) <= Noc;
+    const int64_t src = (int64_t)i + (int64_t)j * N;
+    Hp[idx] = single ? (double)sp[src] : G[src];
+  }
+}
+
+inline int grid_for(const dftfe_b200_ctx *ctx, int64_t work) {
+  return (int)std::max<int64_t>(1, std::min<int64_t>((work + 255) / 256, (int64_t)ctx->num_sms * 8));
+}
+
+int to_float(dftfe_b200_ctx *ctx, const double *in, int64_t ldi, float *out, int64_t ldo, int ncols, int64_t rows) {
+  if (rows == 0) return 0;
+  ctx->launches += 1;
+  to_float_rows_kernel<<<grid_for(ctx, rows * 32), 256, 0, ctx->stream>>>(in, ldi, out, ldo, ncols, rows);
+  DB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+// S = X^T X with FP64 diagonal blocks and FP32 off-diagonal blocks; full symmetric result, all-reduced
+int xtx_mixed_impl(dftfe_b200_ctx *ctx, const double *X, int N, double *S) {
+  const int Bw = std::min(ctx->B, N);
+  const int64_t M = ctx->M;
+  DB_TRY(ctx->mpXsp.alloc((size_t)std::max<int64_t>(M, 1) * N));
+  DB_TRY(ctx->mpSp.alloc((size_t)N * N));
+  DB_TRY(ctx->mpDp.alloc((size_t)N * Bw));
+  DB_CUBLAS(cublasSetStream(ctx->cublas, ctx->stream));
+  DB_CUDA(cudaMemsetAsync(ctx->mpSp.p, 0, (size_t)N * N * sizeof(float), ctx->stream));
+  DB_CUDA(cudaMemsetAsync(ctx->mpDp.p, 0, (size_t)N * Bw * sizeof(double), ctx->stream));
+  DB_TRY(to_float(ctx, X, N, ctx->mpXsp.p, N, N, M));
+  const double one = 1.0, zero = 0.0;
+  const float onef = 1.0f, zerof = 0.0f;
+  for (int j = 0; j < N && M > 0; j += Bw) {
+    const int Bc = std::min(Bw, N - j), DRem = N - j - Bc;
+    double *Cd = ctx->mpDp.p + (size_t)j * Bw;
+    if (!ctx->use_cublas_dense && dmma_projection_usable(ctx, N, N, N, j, j, Bc, Bc)) {
+      DB_TRY(launch_xty(ctx, X, N, j, X, N, j, Bc, Bc, j, j, true, Cd, Bw));
+    } else {
+      ProfScope ps(ctx, "projection");
+      DB_CUBLAS(cublasDgemm(ctx->cublas, CUBLAS_OP_N, CUBLAS_OP_T, Bc, Bc, (int)M, &one, X + j, N, X + j, N, &zero, Cd,
+                            Bw));
+    }
+    if (DRem > 0) {
+      ProfScope ps(ctx, "projection_fp32");
+      DB_CUBLAS(cublasSgemm(ctx->cublas, CUBLAS_OP_N, CUBLAS_OP_T, DRem, Bc, (int)M, &onef, ctx->mpXsp.p + j + Bc, N,
+                            ctx->mpXsp.p + j, N, &zerof, ctx->mpSp.p + (j + Bc) + (size_t)j * N, N));
+    }
+  }
+  DB_TRY(allreduce_sum(ctx, ctx->mpDp.p, (size_t)N * Bw));
+  DB_TRY(allreduce_sum_f32(ctx, ctx->mpSp.p, (size_t)N * N));
+  ctx->launches += 1;
+  merge_overlap_kernel<<<grid_for(ctx, (int64_t)N * N), 256, 0, ctx->stream>>>(ctx->mpDp.p, ctx->mpSp.p, N, Bw, S);
+  DB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// Hp = X^T (H~ X): column blocks [j, j+Bc) with j + Bc <= Noc entirely in FP32, the others FP64
+int xthx_mixed_impl(dftfe_b200_ctx *ctx, const double *X, int N, int Noc, double *Hp) {
+  const int Bw = std::min(ctx->B, N);
+  const int64_t M = ctx->M;
+  DB_TRY(ctx->mpXsp.alloc((size_t)std::max<int64_t>(M, 1) * N));
+  DB_TRY(ctx->mpSp.alloc((size_t)N * N));
+  DB_TRY(ctx->mpBlockSp.alloc((size_t)std::max<int64_t>(M, 1) * Bw));
+  DB_TRY(ctx->denseW.alloc((size_t)N * N));
+  double *G = ctx->denseW.p;
+  DB_CUDA(cudaMemsetAsync(ctx->mpSp.p, 0, (size_t)N * N * sizeof(float), ctx->stream));
+  DB_CUDA(cudaMemsetAsync(G, 0, (size_t)N * N * sizeof(double), ctx->stream));
+  DB_TRY(to_float(ctx, X, N, ctx->mpXsp.p, N, N, M));
+  const double one = 1.0, zero = 0.0;
+  const float onef = 1.0f, zerof = 0.0f;
+  for (int j = 0; j < N; j += Bw) {
+    const int Bc = std::min(Bw, N - j), D = N - j;
+    DB_TRY(apply_H_to_columns(ctx, X, N, j, Bc));  // blockY = H~ X[:, j:j+Bc]  (M x Bc)
+    if (M == 0) continue;
+    DB_CUBLAS(cublasSetStream(ctx->cublas, ctx->stream));
+    if (j + Bc <= Noc) {
+      DB_TRY(to_float(ctx, ctx->blockY.p, Bc, ctx->mpBlockSp.p, Bc, Bc, M));
+      ProfScope ps(ctx, "projection_fp32");
+      DB_CUBLAS(cublasSgemm(ctx->cublas, CUBLAS_OP_N, CUBLAS_OP_T, D, Bc, (int)M, &onef, ctx->mpXsp.p + j, N,
+                            ctx->mpBlockSp.p, Bc, &zerof, ctx->mpSp.p + j + (size_t)j * N, N));
+    } else if (!ctx->use_cublas_dense && dmma_projection_usable(ctx, N, N, Bc, j, 0, D, Bc)) {
+      DB_TRY(launch_xty(ctx, X, N, j, ctx->blockY.p, Bc, 0, D, Bc, j, j, true, G + j + (size_t)j * N, N));
+    } else {
+      ProfScope ps(ctx, "projection");
+      DB_CUBLAS(cublasDgemm(ctx->cublas, CUBLAS_OP_N, CUBLAS_OP_T, D, Bc, (int)M, &one, X + j, N, ctx->blockY.p, Bc,
+                            &zero, G + j + (size_t)j * N, N));
+    }
+  }
+  DB_TRY(allreduce_sum(ctx, G, (size_t)N * N));
+  DB_TRY(allreduce_sum_f32(ctx, ctx->mpSp.p, (size_t)N * N));
+  ctx->launches += 1;
+  merge_projham_kernel<<<grid_for(ctx, (int64_t)N * N), 256, 0, ctx->stream>>>(G, ctx->mpSp.p, N, Bw, Noc, Hp);
+  DB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// X <- X Q in mixed precision.  mode 1 (CGS): FP64 diagonal Bw x Bw blocks + FP32 off-diagonal;
+// mode 2 (RR): FP64 diag(Q) + FP32 (Q - diag Q).  Row chunks, in place.
+int rotate_mixed_impl(dftfe_b200_ctx *ctx, double *X, int N, const double *Q, bool qColMajor, int mode) {
+  DB_CHECK(mode == 1 || mode == 2, "rotate: unknown mixed-precision mode %d", mode);
+  const int64_t M = ctx->M;
+  if (M == 0) return 0;
+  const int Bw = std::min(ctx->B, N);
+  const int64_t chunk = std::min<int64_t>(M, 148 * 128);
+  DB_TRY(ctx->mpSp.alloc((size_t)N * N));            // Q off-diagonal part, FP32 row-major
+  DB_TRY(ctx->mpDp.alloc((size_t)N * std::max(Bw, 1)));  // diag(Q) (mode 2)
+  DB_TRY(ctx->mpXsp.alloc((size_t)chunk * N * 2));   // [chunk x N] FP32 copy of X, then the FP32 product
+  float *Xsp = ctx->mpXsp.p, *Tsp = ctx->mpXsp.p + (size_t)chunk * N;
+  if (mode == 1) DB_TRY(ctx->rotScratch.alloc((size_t)chunk * N));
+  ctx->launches += 1;
+  split_rotation_kernel<<<grid_for(ctx, (int64_t)N * N), 256, 0, ctx->stream>>>(Q, N, qColMajor ? 1 : 0, mode, Bw,
+                                                                               ctx->mpSp.p, ctx->mpDp.p);
+  DB_CUDA(cudaGetLastError());
+  DB_CUBLAS(cublasSetStream(ctx->cublas, ctx->stream));
+  const float onef = 1.0f, zerof = 0.0f;
+  const double one = 1.0, zero = 0.0;
+  for (int64_t r0 = 0; r0 < M; r0 += chunk) {
+    const int mc = (int)std::min<int64_t>(chunk, M - r0);
+    double *Xc = X + (size_t)r0 * N;
+    DB_TRY(to_float(ctx, Xc, N, Xsp, N, N, mc));
+    {
+      ProfScope ps(ctx, "rotation_fp32");
+      // T (row-major mc x N) = Xsp * Qsp  <=>  T_cm (N x mc) = Qsp_rm-as-cm (N x N) * Xsp_cm (N x mc)
+      DB_CUBLAS(cublasSgemm(ctx->cublas, CUBLAS_OP_N, CUBLAS_OP_N, N, mc, N, &onef, ctx->mpSp.p, N, Xsp, N, &zerof,
+                            Tsp, N));
+    }
+    if (mode == 2) {
+      ctx->launches += 1;
+      combine_diag_kernel<<<grid_for(ctx, (int64_t)mc * N), 256, 0, ctx->stream>>>(Xc, N, mc, ctx->mpDp.p, Tsp);
+    } else {
+      ProfScope ps(ctx, "rotation", N / Bw + 1);
+      for (int j = 0; j < N; j += Bw) {
+        const int Bc = std::min(Bw, N - j);
+        // D[:, j:j+Bc] (row-major) = Xc[:, j:j+Bc] * Q[j:j+Bc, j:j+Bc]
+        if (qColMajor)
+          DB_CUBLAS(cublasDgemm(ctx->cublas, CUBLAS_OP_T, CUBLAS_OP_N, Bc, mc, Bc, &one, Q + j + (size_t)j * N, N,
+                                Xc + j, N, &zero, ctx->rotScratch.p + j, N));
+        else
+          DB_CUBLAS(cublasDgemm(ctx->cublas, CUBLAS_OP_N, CUBLAS_OP_N, Bc, mc, Bc, &one, Q + j + (size_t)j * N, N,
+                                Xc + j, N, &zero, ctx->rotScratch.p + j, N));
+      }
+      combine_block_kernel<<<grid_for(ctx, (int64_t)mc * N), 256, 0, ctx->stream>>>(Xc, ctx->rotScratch.p, Tsp,
+                                                                                   (int64_t)mc * N);
+    }
+    DB_CUDA(cudaGetLastError());
+  }
+  return 0;
+}
+
+}  // namespace dftfe_b200

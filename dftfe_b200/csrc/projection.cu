@@ -200,13 +200,14 @@ constexpr size_t XQ_STAGE_DOUBLES = (size_t)TM * XQ_PA + (size_t)XQ_KC * PITCH;
 constexpr size_t XQ_SMEM = XQ_STAGES * XQ_STAGE_DOUBLES * sizeof(double) + 2 * XQ_STAGES * sizeof(uint64_t);
 
 __global__ void __launch_bounds__(THREADS, 1)
-xq_kernel(const double *__restrict__ X, int N, int64_t rows, const double *__restrict__ Q, double *__restrict__ Out) {
+xq_kernel(const double *__restrict__ X, int N, int64_t rows, const double *__restrict__ Q, int ldq, int Nout,
+          double *__restrict__ Out, int ldo) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *st = reinterpret_cast<double *>(smem_raw);
   uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + XQ_STAGES * XQ_STAGE_DOUBLES * sizeof(double));
   uint64_t *empty = full + XQ_STAGES;
   const int tid = threadIdx.x, lane = tid & 31, pwarp = tid >> 5;
-  const int nColTiles = N / TN;
+  const int nColTiles = Nout / TN;
   const int64_t nRowBlocks = (rows + TM - 1) / TM;
   const int64_t nItems = nRowBlocks * nColTiles;
   const int nK = N / XQ_KC;
@@ -244,7 +245,7 @@ xq_kernel(const double *__restrict__ X, int N, int64_t rows, const double *__res
         __syncwarp();
         for (int r = lane; r < vrows; r += 32)
           tma_bulk_g2s(sA + r * XQ_PA, X + (size_t)(m0 + r) * N + kc * XQ_KC, XQ_KC * sizeof(double), &full[s]);
-        tma_bulk_g2s(sB + lane * PITCH, Q + (size_t)(kc * XQ_KC + lane) * N + j0, TN * sizeof(double), &full[s]);
+        tma_bulk_g2s(sB + lane * PITCH, Q + (size_t)(kc * XQ_KC + lane) * ldq + j0, TN * sizeof(double), &full[s]);
       }
     }
   } else {
@@ -288,7 +289,7 @@ xq_kernel(const double *__restrict__ X, int N, int64_t rows, const double *__res
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int col = j0 + wn * 32 + j * 8 + (lane & 3) * 2;
-            *reinterpret_cast<double2 *>(Out + (size_t)r * N + col) = make_double2(acc[i][j][0], acc[i][j][1]);
+            *reinterpret_cast<double2 *>(Out + (size_t)r * ldo + col) = make_double2(acc[i][j][0], acc[i][j][1]);
           }
         }
       }
@@ -369,9 +370,13 @@ int launch_xty(dftfe_b200_ctx *ctx, const double *A, int lda, int iOff, const do
   return 0;
 }
 
-bool dmma_rotation_usable(int N) { return N % TN == 0 && N % XQ_KC == 0; }
+bool dmma_rotation_usable(int N, int Nout, int ldq, int ldo) {
+  return N % XQ_KC == 0 && Nout % TN == 0 && Nout > 0 && N % 2 == 0 && ldq % 2 == 0 && ldo % 2 == 0;
+}
 
-int launch_xq(dftfe_b200_ctx *ctx, const double *X, int N, int64_t rows, const double *Qrm, double *Out) {
+// Out[rows x Nout] (ld ldo) = X[rows x N] (ld N) * Q[N x Nout] (row-major, ld ldq)
+int launch_xq(dftfe_b200_ctx *ctx, const double *X, int N, int64_t rows, const double *Qrm, int ldq, int Nout,
+              double *Out, int ldo) {
   static bool attr = false;
   if (!attr) {
     DB_CUDA(cudaFuncSetAttribute(xq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XQ_SMEM));
@@ -379,9 +384,9 @@ int launch_xq(dftfe_b200_ctx *ctx, const double *X, int N, int64_t rows, const d
   }
   if (rows == 0) return 0;
   ProfScope ps(ctx, "rotation");
-  const int64_t items = ((rows + TM - 1) / TM) * (N / TN);
+  const int64_t items = ((rows + TM - 1) / TM) * (Nout / TN);
   const int grid = (int)std::min<int64_t>(items, ctx->num_sms);
-  xq_kernel<<<grid, THREADS, XQ_SMEM, ctx->stream>>>(X, N, rows, Qrm, Out);
+  xq_kernel<<<grid, THREADS, XQ_SMEM, ctx->stream>>>(X, N, rows, Qrm, ldq, Nout, Out, ldo);
   DB_CUDA(cudaGetLastError());
   return 0;
 }

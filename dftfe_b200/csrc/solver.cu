@@ -16,11 +16,12 @@ namespace dftfe_b200 {
 // One pass: ghost update -> distribute -> coloured fused cell kernel -> slave->master
 // -> ghost accumulate.  Constrained and ghost rows of dst end at 0.
 static int fused_apply_impl(dftfe_b200_ctx *ctx, double *src, double *dst, int ncols, double a, double b,
-                            double s, const double *rowB) {
+                            double s, const double *rowB, bool fp32Comm = false) {
   DB_CHECK(ctx->have_mass, "set_mass must be called before applying the operator");
   ncols *= ctx->cm;  // real columns from here on (complex vectors are interleaved re/im)
   const int ldx = ncols;
-  DB_TRY(ghost_update(ctx, src, ncols, ldx));
+  fp32Comm = fp32Comm && (ncols % 2 == 0);
+  DB_TRY(ghost_update(ctx, src, ncols, ldx, fp32Comm));
   DB_TRY(launch_distribute(ctx, src, ncols, ldx, ctx->invSqrtM.p));
   EpilogueParams ep;
   ep.a = a;
@@ -36,14 +37,15 @@ static int fused_apply_impl(dftfe_b200_ctx *ctx, double *src, double *dst, int n
   DB_TRY(launch_orphan_first_touch(ctx, src, dst, ncols, ldx, ep));
   DB_TRY(nonlocal_apply(ctx, dst, ncols, ldx, ctx->rowOut.p, s));  // += s M^-1/2 C V (C^T ...)
   DB_TRY(launch_slave_to_master(ctx, dst, ncols, ldx, ctx->rowOut.p));
-  DB_TRY(ghost_accumulate(ctx, dst, ncols, ldx, ctx->rowOut.p));
+  DB_TRY(ghost_accumulate(ctx, dst, ncols, ldx, ctx->rowOut.p, fp32Comm));
   DB_TRY(ghost_zero(ctx, dst, ncols, ldx));
   DB_TRY(ghost_zero(ctx, src, ncols, ldx));
   return 0;
 }
 
-int op_fused_apply(dftfe_b200_ctx *ctx, double *src, double *dst, int ncols, double a, double b, double s) {
-  return fused_apply_impl(ctx, src, dst, ncols, a, b, s, nullptr);
+int op_fused_apply(dftfe_b200_ctx *ctx, double *src, double *dst, int ncols, double a, double b, double s,
+                   bool fp32Comm) {
+  return fused_apply_impl(ctx, src, dst, ncols, a, b, s, nullptr, fp32Comm);
 }
 
 // operatorDFTDeviceClass::HX net effect (kohnShamDFTOperatorDevice.cc:3765-3860)
@@ -64,10 +66,11 @@ int op_hx(dftfe_b200_ctx *ctx, double *src, double *dst, int ncols, int scaleFla
 }
 
 // operatorDFTDeviceClass::HXCheby, FP64 (kohnShamDFTOperatorDevice.cc:3874-3997): dst += H src
-int op_hx_cheby(dftfe_b200_ctx *ctx, double *src, double *dst, int ncols) {
+int op_hx_cheby(dftfe_b200_ctx *ctx, double *src, double *dst, int ncols, bool mixedPrec) {
   ncols *= ctx->cm;
   const int ldx = ncols;
-  DB_TRY(ghost_update(ctx, src, ncols, ldx));
+  mixedPrec = mixedPrec && (ncols % 2 == 0);
+  DB_TRY(ghost_update(ctx, src, ncols, ldx, mixedPrec));
   DB_TRY(launch_distribute(ctx, src, ncols, ldx, nullptr));
   EpilogueParams ep;  // a=0, b=1, s=1: pure accumulate; undo the scales folded into the tiled H
   ep.rowIn = ctx->rowInInv.p;
@@ -78,7 +81,7 @@ int op_hx_cheby(dftfe_b200_ctx *ctx, double *src, double *dst, int ncols) {
   DB_TRY(nonlocal_apply(ctx, dst, ncols, ldx, nullptr, 1.0));
   DB_TRY(launch_slave_to_master(ctx, dst, ncols, ldx, nullptr));
   DB_TRY(ghost_zero(ctx, src, ncols, ldx));
-  DB_TRY(ghost_accumulate(ctx, dst, ncols, ldx, nullptr));
+  DB_TRY(ghost_accumulate(ctx, dst, ncols, ldx, nullptr, mixedPrec));
   DB_TRY(ghost_zero(ctx, dst, ncols, ldx));
   return 0;
 }
@@ -87,31 +90,58 @@ int op_hx_cheby(dftfe_b200_ctx *ctx, double *src, double *dst, int ncols) {
 // Chebyshev filter (linearAlgebraOperationsDevice.cc:531-727), Loewdin basis,
 // recurrence fused into the cell kernel epilogue: one HBM pass per degree.
 // ---------------------------------------------------------------------------
-static int cheb_filter_impl(dftfe_b200_ctx *ctx, double *x_d, double *y_d, int ncols, int m, double a, double b,
-                            double a0) {
-  DB_CHECK(m >= 1, "Chebyshev degree must be >= 1");
-  const double e = (b - a) / 2.0;
-  const double c = (b + a) / 2.0;
-  double sigma = e / (a0 - c);
-  const double sigma1 = sigma;
-  const double gamma = 2.0 / sigma1;
-  double *X = x_d, *Y = y_d;
-  // degree 1: Y = (sigma1/e) (H~ X - c X)
-  DB_TRY(op_fused_apply(ctx, X, Y, ncols, -c * sigma1 / e, 0.0, sigma1 / e));
-  for (int degree = 2; degree <= m; ++degree) {
-    const double sigma2 = 1.0 / (gamma - sigma);
-    const double alpha1 = 2.0 * sigma2 / e, alpha2 = -(sigma * sigma2);
-    // X <- alpha1 (H~ - c) Y + alpha2 X
-    DB_TRY(op_fused_apply(ctx, Y, X, ncols, -c * alpha1, alpha2, alpha1));
-    std::swap(X, Y);
-    sigma = sigma2;
+// The recurrence state of one block: which of (x, y) holds the newest iterate, and the running sigma.
+struct ChebState {
+  double *X, *Y;  // Y = newest after step 1
+  double e, c, sigma, sigma1, gamma;
+  int degree = 0;
+};
+
+static void cheb_begin(ChebState &st, double *x_d, double *y_d, double a, double b, double a0) {
+  st.e = (b - a) / 2.0;
+  st.c = (b + a) / 2.0;
+  st.sigma = st.e / (a0 - st.c);
+  st.sigma1 = st.sigma;
+  st.gamma = 2.0 / st.sigma1;
+  st.X = x_d;
+  st.Y = y_d;
+  st.degree = 0;
+}
+
+// one more degree (1-based).  mixedPrec: FP32 ghost payloads for degrees 2..m-1, exactly where the reference
+// passes mixedPrecOverall && useMixedPrecCheby to HXCheby (linearAlgebraOperationsDevice.cc:612-622, 700-708);
+// degrees 1 and m go through the FP64 HX (:560-566, 650-656).
+static int cheb_step(dftfe_b200_ctx *ctx, ChebState &st, int ncols, int m, bool mixedPrec) {
+  const int degree = ++st.degree;
+  if (degree == 1) {
+    // Y = (sigma1/e) (H~ X - c X)
+    return op_fused_apply(ctx, st.X, st.Y, ncols, -st.c * st.sigma1 / st.e, 0.0, st.sigma1 / st.e, false);
   }
-  if (Y != x_d) {
+  const double sigma2 = 1.0 / (st.gamma - st.sigma);
+  const double alpha1 = 2.0 * sigma2 / st.e, alpha2 = -(st.sigma * sigma2);
+  // X <- alpha1 (H~ - c) Y + alpha2 X
+  DB_TRY(op_fused_apply(ctx, st.Y, st.X, ncols, -st.c * alpha1, alpha2, alpha1, mixedPrec && degree < m));
+  std::swap(st.X, st.Y);
+  st.sigma = sigma2;
+  return 0;
+}
+
+static int cheb_end(dftfe_b200_ctx *ctx, ChebState &st, double *x_d, int ncols) {
+  if (st.Y != x_d) {
     ctx->launches += 1;
-    DB_CUDA(cudaMemcpyAsync(x_d, Y, (size_t)(ctx->M + ctx->G) * ncols * ctx->cm * sizeof(double),
+    DB_CUDA(cudaMemcpyAsync(x_d, st.Y, (size_t)(ctx->M + ctx->G) * ncols * ctx->cm * sizeof(double),
                             cudaMemcpyDeviceToDevice, ctx->stream));
   }
   return 0;
+}
+
+static int cheb_filter_impl(dftfe_b200_ctx *ctx, double *x_d, double *y_d, int ncols, int m, double a, double b,
+                            double a0, bool mixedPrec = false) {
+  DB_CHECK(m >= 1, "Chebyshev degree must be >= 1");
+  ChebState st;
+  cheb_begin(st, x_d, y_d, a, b, a0);
+  for (int degree = 1; degree <= m; ++degree) DB_TRY(cheb_step(ctx, st, ncols, m, mixedPrec));
+  return cheb_end(ctx, st, x_d, ncols);
 }
 
 // ---------------------------------------------------------------------------
@@ -290,7 +320,7 @@ static int xtx_impl(dftfe_b200_ctx *ctx, const double *X, int N, double *S) {
 }
 
 // HXb(M x ncols, dense) = H~ * X[:, j0:j0+ncols]
-static int apply_H_to_columns(dftfe_b200_ctx *ctx, const double *X, int N, int j0, int ncols) {
+int apply_H_to_columns(dftfe_b200_ctx *ctx, const double *X, int N, int j0, int ncols) {
   const int cm = ctx->cm;
   DB_TRY(ensure_block_scratch(ctx));
   DB_TRY(launch_block_copy_from_full(ctx, X, N * cm, j0 * cm, ctx->blockX.p, ncols * cm, ctx->M, nullptr));
@@ -335,14 +365,20 @@ static int xthx_impl(dftfe_b200_ctx *ctx, const double *X, int N, double *Hp) {
   return 0;
 }
 
-// X(M x Nr real) <- X * Q.  qColMajor: Q memory holds Q(i,j) at i + j*Nr (cuSOLVER output), else row-major.
-static int rotate_real(dftfe_b200_ctx *ctx, double *X, int N, const double *Q, bool qColMajor) {
+// Out(M x Nout, ld ldo) = X(M x Nr real) * Q[:, c0:c0+Nout].  Out == nullptr: in place (c0 = 0, Nout = Nr) through a
+// row-chunk scratch.  qColMajor: Q memory holds Q(i,j) at i + j*Nr (cuSOLVER output), else row-major.
+static int rotate_real(dftfe_b200_ctx *ctx, double *X, int N, const double *Q, bool qColMajor, int c0 = 0,
+                       int Nout = -1, double *Out = nullptr, int ldo = 0) {
   if (ctx->M == 0) return 0;
+  if (Nout < 0) Nout = N;
+  const bool inPlace = Out == nullptr;
+  DB_CHECK(!inPlace || (c0 == 0 && Nout == N), "rotate: an in-place rotation needs the full square Q");
+  if (inPlace) ldo = N;
   const int64_t chunk = std::min<int64_t>(ctx->M, 148 * 128);
-  DB_TRY(ctx->rotScratch.alloc((size_t)chunk * N));
+  if (inPlace) DB_TRY(ctx->rotScratch.alloc((size_t)chunk * N));
   const double one = 1.0, zero = 0.0;
   DB_CUBLAS(cublasSetStream(ctx->cublas, ctx->stream));
-  const bool dmma = !ctx->use_cublas_dense && dmma_rotation_usable(N);
+  const bool dmma = !ctx->use_cublas_dense && dmma_rotation_usable(N, Nout, N, ldo) && (c0 % 2 == 0);
   const double *Qrm = Q;
   if (dmma && qColMajor) {  // the kernel wants Q(k, j) with j fastest
     DB_TRY(ctx->denseC.alloc((size_t)N * N));
@@ -351,32 +387,53 @@ static int rotate_real(dftfe_b200_ctx *ctx, double *X, int N, const double *Q, b
   }
   for (int64_t r0 = 0; r0 < ctx->M; r0 += chunk) {
     const int mc = (int)std::min<int64_t>(chunk, ctx->M - r0);
+    double *dst = inPlace ? ctx->rotScratch.p : Out + (size_t)r0 * ldo;
     if (dmma) {
-      DB_TRY(launch_xq(ctx, X + (size_t)r0 * N, N, mc, Qrm, ctx->rotScratch.p));
+      DB_TRY(launch_xq(ctx, X + (size_t)r0 * N, N, mc, Qrm + c0, N, Nout, dst, ldo));
+    } else {
+      ProfScope ps(ctx, "rotation");
+      // dst_cm (Nout x mc) = Qsub^T * X_cm ; row-major Q memory is col-major Q^T
+      if (qColMajor)
+        DB_CUBLAS(cublasDgemm(ctx->cublas, CUBLAS_OP_T, CUBLAS_OP_N, Nout, mc, N, &one, Q + (size_t)c0 * N, N,
+                              X + (size_t)r0 * N, N, &zero, dst, ldo));
+      else
+        DB_CUBLAS(cublasDgemm(ctx->cublas, CUBLAS_OP_N, CUBLAS_OP_N, Nout, mc, N, &one, Q + c0, N, X + (size_t)r0 * N,
+                              N, &zero, dst, ldo));
+    }
+    if (inPlace) {
       ctx->launches += 1;
       DB_CUDA(cudaMemcpyAsync(X + (size_t)r0 * N, ctx->rotScratch.p, (size_t)mc * N * sizeof(double),
                               cudaMemcpyDeviceToDevice, ctx->stream));
-      continue;
     }
-    ProfScope ps(ctx, "rotation", 2);
-    // Xnew_cm (N x mc) = Q^T_(math) * X_cm ; row-major Q memory is col-major Q^T
-    DB_CUBLAS(cublasDgemm(ctx->cublas, qColMajor ? CUBLAS_OP_T : CUBLAS_OP_N, CUBLAS_OP_N, N, mc, N, &one, Q, N,
-                          X + (size_t)r0 * N, N, &zero, ctx->rotScratch.p, N));
-    DB_CUDA(cudaMemcpyAsync(X + (size_t)r0 * N, ctx->rotScratch.p, (size_t)mc * N * sizeof(double),
-                            cudaMemcpyDeviceToDevice, ctx->stream));
   }
   return 0;
 }
 
-// X <- X * Q for N wavefunction columns (complex: through the real 2N x 2N embedding of Q)
-static int rotate_impl(dftfe_b200_ctx *ctx, double *X, int N, const double *Q, bool qColMajor) {
-  if (!ctx->cplx) return rotate_real(ctx, X, N, Q, qColMajor);
+// X <- X * Q for N wavefunction columns (complex: through the real 2N x 2N embedding of Q).
+// mixedMode 0: FP64; 1 / 2: the reference's CGS / RR mixed-precision rotations (real build only).
+static int rotate_impl(dftfe_b200_ctx *ctx, double *X, int N, const double *Q, bool qColMajor, int mixedMode = 0) {
+  if (!ctx->cplx) {
+    if (mixedMode != 0) return rotate_mixed_impl(ctx, X, N, Q, qColMajor, mixedMode);
+    return rotate_real(ctx, X, N, Q, qColMajor);
+  }
   const int Nr = 2 * N;
   DB_TRY(ctx->denseG.alloc((size_t)Nr * Nr));
   ctx->launches += 1;
   cplx_embed_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(Q, N, qColMajor ? 1 : 0, ctx->denseG.p);
   DB_CUDA(cudaGetLastError());
   return rotate_real(ctx, X, Nr, ctx->denseG.p, false);
+}
+
+// XFrac(M x Nfr) = X * Q[:, c0:c0+Nfr]  (subspaceRotationSpectrumSplitScalapack, linearAlgebraOperationsDevice.cc:1446-1830)
+static int rotate_into(dftfe_b200_ctx *ctx, double *X, int N, const double *Qcm, int c0, int Nfr, double *XFrac) {
+  if (!ctx->cplx) return rotate_real(ctx, X, N, Qcm, true, c0, Nfr, XFrac, Nfr);
+  // complex: embed the N x Nfr column slice of Q as real 2N x 2Nfr (row-major, ld 2N of the full embedding)
+  const int Nr = 2 * N;
+  DB_TRY(ctx->denseG.alloc((size_t)Nr * Nr));
+  ctx->launches += 1;
+  cplx_embed_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(Qcm, N, 1, ctx->denseG.p);
+  DB_CUDA(cudaGetLastError());
+  return rotate_real(ctx, X, Nr, ctx->denseG.p, false, 2 * c0, 2 * Nfr, XFrac, 2 * Nfr);
 }
 
 static int residual_impl(dftfe_b200_ctx *ctx, const double *X, int N, const double *eig_h, double *res_h) {
@@ -631,8 +688,34 @@ static int rr_cplx(dftfe_b200_ctx *ctx, double *X, int N, double *eig_h, bool cg
   return 0;
 }
 
+// Which pieces run in mixed precision (dftParameters::useMixedPrec*, all gated by useMixedPrecOverall) and the
+// number of "core" states whose XtHX blocks may be FP32 (numCoreWfcXtHX / Noc).
+struct RRFlags {
+  bool mpOverlap = false;   // useMixedPrecCGS_O
+  bool mpCgsRot = false;    // useMixedPrecCGS_SR
+  bool mpXtHX = false;      // useMixedPrecXTHXSpectrumSplit
+  bool mpRRRot = false;     // useMixedPrecSubspaceRotRR
+  int nCore = 0;
+};
+
+static int overlap_any(dftfe_b200_ctx *ctx, const double *X, int N, double *S, bool mixed) {
+  return (mixed && !ctx->cplx) ? xtx_mixed_impl(ctx, X, N, S) : xtx_impl(ctx, X, N, S);
+}
+static int projham_any(dftfe_b200_ctx *ctx, const double *X, int N, double *Hp, bool mixed, int nCore) {
+  return (mixed && !ctx->cplx && nCore > 0) ? xthx_mixed_impl(ctx, X, N, nCore, Hp) : xthx_impl(ctx, X, N, Hp);
+}
+
+static int identity_to(dftfe_b200_ctx *ctx, double *A, int N) {
+  std::vector<double> eye((size_t)N * N, 0.0);
+  for (int i = 0; i < N; ++i) eye[(size_t)i * N + i] = 1.0;
+  ctx->launches += 1;
+  DB_CUDA(cudaMemcpyAsync(A, eye.data(), eye.size() * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  DB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
 // rayleighRitzGEP (src/linAlg/rayleighRitzDevice.cc:355-819)
-static int rr_gep(dftfe_b200_ctx *ctx, double *X, int N, double *eig_h) {
+static int rr_gep(dftfe_b200_ctx *ctx, double *X, int N, double *eig_h, const RRFlags &f = RRFlags()) {
   if (ctx->cplx) return rr_cplx(ctx, X, N, eig_h, false);
   const size_t nn = (size_t)N * N;
   DB_TRY(ctx->denseA.alloc(nn));
@@ -640,7 +723,7 @@ static int rr_gep(dftfe_b200_ctx *ctx, double *X, int N, double *eig_h) {
   DB_TRY(ctx->eigDev.alloc(N));
   double *S = ctx->denseA.p, *Hp = ctx->denseB.p;
   const double one = 1.0;
-  DB_TRY(xtx_impl(ctx, X, N, S));
+  DB_TRY(overlap_any(ctx, X, N, S, f.mpOverlap));
   DB_TRY(dense_cholesky(ctx, S, N));  // S lower <- L
   DB_TRY(xthx_impl(ctx, X, N, Hp));
   DB_CUBLAS(cublasSetStream(ctx->cublas, ctx->stream));
@@ -655,58 +738,163 @@ static int rr_gep(dftfe_b200_ctx *ctx, double *X, int N, double *eig_h) {
   ctx->launches += 1;
   DB_CUBLAS(cublasDtrsm(ctx->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, N,
                         N, &one, S, N, Hp, N));
-  DB_TRY(rotate_impl(ctx, X, N, Hp, true));
+  DB_TRY(rotate_impl(ctx, X, N, Hp, true, f.mpRRRot ? 2 : 0));
   DB_CUDA(cudaMemcpyAsync(eig_h, ctx->eigDev.p, N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   DB_CUDA(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
 
-// pseudoGramSchmidtOrthogonalization + rayleighRitz
-// (src/linAlg/pseudoGSDevice.cc:81-463, src/linAlg/rayleighRitzDevice.cc:81-353)
-static int cgs_rr(dftfe_b200_ctx *ctx, double *X, int N, double *eig_h) {
-  if (ctx->cplx) return rr_cplx(ctx, X, N, eig_h, true);
+// pseudoGramSchmidtOrthogonalization (src/linAlg/pseudoGSDevice.cc:81-463): X <- X L^-T with S = X^T X = L L^T
+static int cgs_orthogonalise(dftfe_b200_ctx *ctx, double *X, int N, const RRFlags &f) {
   const size_t nn = (size_t)N * N;
   DB_TRY(ctx->denseA.alloc(nn));
   DB_TRY(ctx->denseB.alloc(nn));
-  DB_TRY(ctx->eigDev.alloc(N));
-  double *S = ctx->denseA.p, *Hp = ctx->denseB.p;
+  double *S = ctx->denseA.p, *U = ctx->denseB.p;
   const double one = 1.0;
-  DB_TRY(xtx_impl(ctx, X, N, S));
+  DB_TRY(overlap_any(ctx, X, N, S, f.mpOverlap));
   DB_TRY(dense_cholesky(ctx, S, N));
-  // Linv^T as a column-major matrix: solve L^T Z = I
-  ctx->launches += 2;
-  DB_CUDA(cudaMemsetAsync(Hp, 0, nn * sizeof(double), ctx->stream));
-  {
+  DB_TRY(identity_to(ctx, U, N));  // L^-T as a column-major matrix: solve L^T U = I
+  DB_CUBLAS(cublasSetStream(ctx->cublas, ctx->stream));
+  ctx->launches += 1;
+  DB_CUBLAS(cublasDtrsm(ctx->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, N,
+                        N, &one, S, N, U, N));
+  return rotate_impl(ctx, X, N, U, true, f.mpCgsRot ? 1 : 0);
+}
+
+// pseudoGramSchmidtOrthogonalization + rayleighRitz
+// (src/linAlg/pseudoGSDevice.cc:81-463, src/linAlg/rayleighRitzDevice.cc:81-353)
+static int cgs_rr(dftfe_b200_ctx *ctx, double *X, int N, double *eig_h, const RRFlags &f = RRFlags()) {
+  if (ctx->cplx) return rr_cplx(ctx, X, N, eig_h, true);
+  DB_TRY(ctx->eigDev.alloc(N));
+  DB_TRY(cgs_orthogonalise(ctx, X, N, f));
+  double *Hp = ctx->denseB.p;
+  DB_TRY(projham_any(ctx, X, N, Hp, f.mpXtHX, f.nCore));
+  DB_TRY(dense_eigh(ctx, Hp, N, ctx->eigDev.p));
+  DB_TRY(rotate_impl(ctx, X, N, Hp, true, f.mpRRRot ? 2 : 0));
+  DB_CUDA(cudaMemcpyAsync(eig_h, ctx->eigDev.p, N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  DB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// rayleighRitzGEPSpectrumSplitDirect (src/linAlg/rayleighRitzDevice.cc:821-1454): X is orthonormalised
+// (X <- X L^-T) but NOT rotated; only the top Nfr = N - Noc eigenpairs of the projected Hamiltonian are kept and
+// XFrac (M x Nfr) = X Q[:, Noc:N] receives the rotated fractionally-occupied states.  eig_h: Nfr values.
+static int rr_spectrum_split(dftfe_b200_ctx *ctx, double *X, double *XFrac, int N, int Noc, double *eig_h,
+                             const RRFlags &f) {
+  DB_CHECK(Noc > 0 && Noc < N && XFrac, "spectrum split needs 0 < n_core_states < N and an XFrac buffer");
+  DB_TRY(ctx->eigDev.alloc(N));
+  double *Hp = nullptr;
+  if (ctx->cplx) {
+    const size_t nn = (size_t)N * N * 2;
+    DB_TRY(ctx->denseA.alloc(nn));
+    DB_TRY(ctx->denseB.alloc(nn));
+    double *S = ctx->denseA.p;
+    Hp = ctx->denseB.p;
+    cuDoubleComplex *Sz = reinterpret_cast<cuDoubleComplex *>(S), *Hz = reinterpret_cast<cuDoubleComplex *>(Hp);
+    const cuDoubleComplex one = make_cuDoubleComplex(1.0, 0.0);
+    DB_TRY(xtx_impl(ctx, X, N, S));
+    DB_TRY(dense_cholesky_cplx(ctx, S, N));
     std::vector<double> eye(nn, 0.0);
-    for (int i = 0; i < N; ++i) eye[(size_t)i * N + i] = 1.0;
+    for (int i = 0; i < N; ++i) eye[((size_t)i * N + i) * 2] = 1.0;
     DB_CUDA(cudaMemcpyAsync(Hp, eye.data(), nn * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
     DB_CUDA(cudaStreamSynchronize(ctx->stream));
+    DB_CUBLAS(cublasSetStream(ctx->cublas, ctx->stream));
+    ctx->launches += 1;
+    DB_CUBLAS(cublasZtrsm(ctx->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_C, CUBLAS_DIAG_NON_UNIT, N,
+                          N, &one, Sz, N, Hz, N));
+    DB_TRY(rotate_impl(ctx, X, N, Hp, true));
+    DB_TRY(xthx_impl(ctx, X, N, Hp));
+    DB_TRY(dense_eigh_cplx(ctx, Hp, N, ctx->eigDev.p));
+  } else {
+    DB_TRY(cgs_orthogonalise(ctx, X, N, f));
+    Hp = ctx->denseB.p;
+    DB_TRY(projham_any(ctx, X, N, Hp, f.mpXtHX, Noc));
+    DB_TRY(dense_eigh(ctx, Hp, N, ctx->eigDev.p));
   }
-  DB_CUBLAS(cublasSetStream(ctx->cublas, ctx->stream));
-  DB_CUBLAS(cublasDtrsm(ctx->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_T, CUBLAS_DIAG_NON_UNIT, N,
-                        N, &one, S, N, Hp, N));
-  DB_TRY(rotate_impl(ctx, X, N, Hp, true));  // X <- X L^-T
-  DB_TRY(xthx_impl(ctx, X, N, Hp));
-  DB_TRY(dense_eigh(ctx, Hp, N, ctx->eigDev.p));
-  DB_TRY(rotate_impl(ctx, X, N, Hp, true));
-  DB_CUDA(cudaMemcpyAsync(eig_h, ctx->eigDev.p, N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  DB_TRY(rotate_into(ctx, X, N, Hp, Noc, N - Noc, XFrac));
+  DB_CUDA(cudaMemcpyAsync(eig_h, ctx->eigDev.p + Noc, (N - Noc) * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   DB_CUDA(cudaStreamSynchronize(ctx->stream));
   return 0;
 }
 
 // HOT LOOP 1 of solve() (solver .cc:376-526) on a device-resident X (M x N):
 // slice block -> filter -> write back, for every block of B columns.
+//
+// With more than one rank (or option "overlap_lanes" = 1) two blocks are kept in flight on two lanes
+// (stream + scratch + exchange buffers each), their degrees enqueued alternately: while one block's cell
+// kernels own the SMs the other block's pack / NCCL send-recv / unpack run beside them, which is the
+// reference's overlapComputeCommunCheby two-block schedule (linearAlgebraOperationsDevice.cc:734-1443)
+// expressed with streams instead of a hand-interleaved 20-step sequence.  The arithmetic per block is
+// unchanged, so results are bit-identical to the single-lane loop.
+static int ensure_lanes(dftfe_b200_ctx *ctx) {
+  for (int l = 0; l < 2; ++l) {
+    if (!ctx->laneStream[l]) DB_CUDA(cudaStreamCreateWithFlags(&ctx->laneStream[l], cudaStreamNonBlocking));
+    if (!ctx->laneEvent[l]) DB_CUDA(cudaEventCreateWithFlags(&ctx->laneEvent[l], cudaEventDisableTiming));
+  }
+  if (!ctx->forkEvent) DB_CUDA(cudaEventCreateWithFlags(&ctx->forkEvent, cudaEventDisableTiming));
+  const size_t blk = (size_t)(ctx->M + ctx->G) * ctx->B * ctx->cm;
+  DB_TRY(ctx->blockX2.alloc(blk));
+  DB_TRY(ctx->blockY2.alloc(blk));
+  return 0;
+}
+
 static int filter_all_impl(dftfe_b200_ctx *ctx, double *X, int N, int m, double a, double b, double a0,
-                           const double *inScale) {
+                           const double *inScale, bool mixedPrec = false) {
   const int B = std::min(ctx->B, N);
   DB_CHECK(N % B == 0, "number of wavefunctions (%d) must be a multiple of the Chebyshev block size (%d)", N, B);
+  DB_CHECK(m >= 1, "Chebyshev degree must be >= 1");
   DB_TRY(ensure_block_scratch(ctx));
   const int cm = ctx->cm;
-  for (int j = 0; j < N; j += B) {
-    DB_TRY(launch_block_copy_from_full(ctx, X, N * cm, j * cm, ctx->blockX.p, B * cm, ctx->M, inScale));
-    DB_TRY(ghost_zero(ctx, ctx->blockX.p, B * cm, B * cm));
-    DB_TRY(cheb_filter_impl(ctx, ctx->blockX.p, ctx->blockY.p, B, m, a, b, a0));
-    DB_TRY(launch_block_copy_to_full(ctx, X, N * cm, j * cm, ctx->blockX.p, B * cm, ctx->M, nullptr));
+  const bool lanes = (ctx->overlap_lanes == 1 || (ctx->overlap_lanes < 0 && ctx->nranks > 1)) && N / B >= 2;
+  if (!lanes) {
+    for (int j = 0; j < N; j += B) {
+      DB_TRY(launch_block_copy_from_full(ctx, X, N * cm, j * cm, ctx->blockX.p, B * cm, ctx->M, inScale));
+      DB_TRY(ghost_zero(ctx, ctx->blockX.p, B * cm, B * cm));
+      DB_TRY(cheb_filter_impl(ctx, ctx->blockX.p, ctx->blockY.p, B, m, a, b, a0, mixedPrec));
+      DB_TRY(launch_block_copy_to_full(ctx, X, N * cm, j * cm, ctx->blockX.p, B * cm, ctx->M, nullptr));
+    }
+    return 0;
+  }
+  DB_TRY(ensure_lanes(ctx));
+  cudaStream_t mainStream = ctx->stream;
+  double *bx[2] = {ctx->blockX.p, ctx->blockX2.p}, *by[2] = {ctx->blockY.p, ctx->blockY2.p};
+  DB_CUDA(cudaEventRecord(ctx->forkEvent, mainStream));
+  for (int l = 0; l < 2; ++l) DB_CUDA(cudaStreamWaitEvent(ctx->laneStream[l], ctx->forkEvent, 0));
+  int rc = 0;
+  auto on_lane = [&](int l) {
+    ctx->lane = l;
+    ctx->stream = ctx->laneStream[l];
+  };
+  auto body = [&]() -> int {
+    for (int j = 0; j < N; j += 2 * B) {
+      const int nl = (j + B < N) ? 2 : 1;
+      ChebState st[2];
+      for (int l = 0; l < nl; ++l) {
+        on_lane(l);
+        DB_TRY(launch_block_copy_from_full(ctx, X, N * cm, (j + l * B) * cm, bx[l], B * cm, ctx->M, inScale));
+        DB_TRY(ghost_zero(ctx, bx[l], B * cm, B * cm));
+        cheb_begin(st[l], bx[l], by[l], a, b, a0);
+      }
+      for (int degree = 1; degree <= m; ++degree)
+        for (int l = 0; l < nl; ++l) {
+          on_lane(l);
+          DB_TRY(cheb_step(ctx, st[l], B, m, mixedPrec));
+        }
+      for (int l = 0; l < nl; ++l) {
+        on_lane(l);
+        DB_TRY(cheb_end(ctx, st[l], bx[l], B));
+        DB_TRY(launch_block_copy_to_full(ctx, X, N * cm, (j + l * B) * cm, bx[l], B * cm, ctx->M, nullptr));
+      }
+    }
+    return 0;
+  };
+  rc = body();
+  ctx->lane = 0;
+  ctx->stream = mainStream;
+  if (rc != 0) return rc;
+  for (int l = 0; l < 2; ++l) {
+    DB_CUDA(cudaEventRecord(ctx->laneEvent[l], ctx->laneStream[l]));
+    DB_CUDA(cudaStreamWaitEvent(mainStream, ctx->laneEvent[l], 0));
   }
   return 0;
 }
@@ -714,7 +902,8 @@ static int filter_all_impl(dftfe_b200_ctx *ctx, double *X, int N, int m, double 
 // Same loop for a HOST-resident X (pinned memory recommended): block i+1 is copied
 // in and block i-1 copied out on two copy streams while block i is filtered on the
 // context stream, so PCIe traffic hides behind the cell kernels.
-static int filter_all_host_impl(dftfe_b200_ctx *ctx, double *X_h, int N, int m, double a, double b, double a0) {
+static int filter_all_host_impl(dftfe_b200_ctx *ctx, double *X_h, int N, int m, double a, double b, double a0,
+                                bool mixedPrec) {
   const int B = std::min(ctx->B, N);
   DB_CHECK(N % B == 0, "number of wavefunctions (%d) must be a multiple of the Chebyshev block size (%d)", N, B);
   const int cm = ctx->cm;
@@ -749,7 +938,7 @@ static int filter_all_host_impl(dftfe_b200_ctx *ctx, double *X_h, int N, int m, 
       DB_CUDA(cudaEventRecord(evIn[i], ctx->copyIn));
       DB_CUDA(cudaStreamWaitEvent(ctx->stream, evIn[i], 0));
       DB_TRY(ghost_zero(ctx, buf, B * cm, B * cm));
-      DB_TRY(cheb_filter_impl(ctx, buf, ctx->blockY.p, B, m, a, b, a0));
+      DB_TRY(cheb_filter_impl(ctx, buf, ctx->blockY.p, B, m, a, b, a0, mixedPrec));
       DB_CUDA(cudaEventRecord(evComp[i], ctx->stream));
       DB_CUDA(cudaStreamWaitEvent(ctx->copyOut, evComp[i], 0));
       DB_CUDA(cudaMemcpy2DAsync(X_h + (size_t)i * B * cm, (size_t)N * cm * sizeof(double), buf,
@@ -786,10 +975,13 @@ static unsigned int set_chebyshev_order(double upperBound) {
   return 1250;
 }
 
-static int solve_impl(dftfe_b200_ctx *ctx, double *X, int N, const dftfe_b200_solve_params *p, double *eig_h,
-                      double *res_h, double *upper_h) {
+static int solve_impl(dftfe_b200_ctx *ctx, double *X, double *XFrac, int N, const dftfe_b200_solve_params *p,
+                      double *eig_h, double *res_h, double *upper_h) {
   const int B = std::min(ctx->B, N);
   DB_CHECK(N % B == 0, "number of wavefunctions (%d) must be a multiple of the Chebyshev block size (%d)", N, B);
+  const int Noc = p->n_core_states;
+  DB_CHECK(Noc >= 0 && Noc < N, "solve: n_core_states (%d) must be in [0, N)", Noc);
+  DB_CHECK(Noc == 0 || XFrac, "solve: spectrum splitting (n_core_states > 0) needs the X_frac_d buffer");
   DB_TRY(ensure_block_scratch(ctx));
   // spectrum bounds (solver .cc:241-297)
   if (p->is_first_filtering_call || !ctx->bounds_valid) {
@@ -816,15 +1008,29 @@ static int solve_impl(dftfe_b200_ctx *ctx, double *X, int N, const dftfe_b200_so
   if (p->is_first_scf && p->is_pseudopotential) order = (unsigned int)(order * p->first_scf_scaling);
   if (order < 1) order = 1;
 
+  const bool mp = p->use_mixed_prec_overall != 0;
+  RRFlags f;
+  f.mpOverlap = mp && p->use_mixed_prec_cgs_o;
+  f.mpCgsRot = mp && p->use_mixed_prec_cgs_sr;
+  f.mpXtHX = mp && p->use_mixed_prec_xthx_spectrum_split;
+  f.mpRRRot = mp && p->use_mixed_prec_subspace_rot_rr;
+  f.nCore = p->num_core_wfc_xthx;
+
   // X <- M^1/2 X (solver .cc:358-363) fused into the block copy; filter; copy back (:376-526)
-  DB_TRY(filter_all_impl(ctx, X, N, (int)order, ctx->bLow, ctx->bUp, ctx->a0, ctx->sqrtM.p));
-  if (p->use_cgs_rr)
-    DB_TRY(cgs_rr(ctx, X, N, eig_h));
-  else
-    DB_TRY(rr_gep(ctx, X, N, eig_h));
-  if (p->compute_residual && res_h) DB_TRY(residual_impl(ctx, X, N, eig_h, res_h));
+  DB_TRY(filter_all_impl(ctx, X, N, (int)order, ctx->bLow, ctx->bUp, ctx->a0, ctx->sqrtM.p,
+                         mp && p->use_mixed_prec_cheby));
+  const int Nev = N - Noc;  // eigenValues.size() of the reference
+  if (Noc > 0) {
+    DB_TRY(rr_spectrum_split(ctx, X, XFrac, N, Noc, eig_h, f));  // solver .cc:553-575
+  } else if (p->use_cgs_rr) {
+    DB_TRY(cgs_rr(ctx, X, N, eig_h, f));
+  } else {
+    DB_TRY(rr_gep(ctx, X, N, eig_h, f));
+  }
+  if (p->compute_residual && res_h) DB_TRY(residual_impl(ctx, Noc > 0 ? XFrac : X, Nev, eig_h, res_h));
   // X <- M^-1/2 X (solver .cc:719-733)
   DB_TRY(launch_row_scale(ctx, X, ctx->M, N * ctx->cm, N * ctx->cm, 1.0, ctx->invSqrtM.p));
+  if (Noc > 0) DB_TRY(launch_row_scale(ctx, XFrac, ctx->M, Nev * ctx->cm, Nev * ctx->cm, 1.0, ctx->invSqrtM.p));
   if (upper_h) *upper_h = ctx->bUp;
   DB_CUDA(cudaStreamSynchronize(ctx->stream));
   return 0;
@@ -865,30 +1071,30 @@ int dftfe_b200_hx(dftfe_b200_ctx *ctx, double *src_d, double *dst_d, int32_t nco
   return op_hx(ctx, src_d, dst_d, ncols, scale_flag, scalar, do_unscaling_src);
 }
 
-int dftfe_b200_hx_cheby(dftfe_b200_ctx *ctx, double *src_d, double *dst_d, int32_t ncols) {
+int dftfe_b200_hx_cheby(dftfe_b200_ctx *ctx, double *src_d, double *dst_d, int32_t ncols, int32_t mixed_prec) {
   DB_CTX(ctx);
   DB_TRY(check_cols(ctx, ncols));
-  return op_hx_cheby(ctx, src_d, dst_d, ncols);
+  return op_hx_cheby(ctx, src_d, dst_d, ncols, mixed_prec != 0);
 }
 
 int dftfe_b200_cheb_filter(dftfe_b200_ctx *ctx, double *x_d, double *y_d, int32_t ncols, int32_t m, double a,
-                           double b, double a0) {
+                           double b, double a0, int32_t mixed_prec) {
   DB_CTX(ctx);
   DB_TRY(check_cols(ctx, ncols));
-  return cheb_filter_impl(ctx, x_d, y_d, ncols, m, a, b, a0);
+  return cheb_filter_impl(ctx, x_d, y_d, ncols, m, a, b, a0, mixed_prec != 0);
 }
 
 int dftfe_b200_cheb_filter_all(dftfe_b200_ctx *ctx, double *X_d, int32_t N, int32_t m, double a, double b,
-                               double a0) {
+                               double a0, int32_t mixed_prec) {
   DB_CTX(ctx);
-  return filter_all_impl(ctx, X_d, N, m, a, b, a0, nullptr);
+  return filter_all_impl(ctx, X_d, N, m, a, b, a0, nullptr, mixed_prec != 0);
 }
 
 int dftfe_b200_cheb_filter_all_host(dftfe_b200_ctx *ctx, double *X_h, int32_t N, int32_t m, double a, double b,
-                                    double a0) {
+                                    double a0, int32_t mixed_prec) {
   DB_CTX(ctx);
   DB_CHECK(X_h, "cheb_filter_all_host: null host pointer");
-  return filter_all_host_impl(ctx, X_h, N, m, a, b, a0);
+  return filter_all_host_impl(ctx, X_h, N, m, a, b, a0, mixed_prec != 0);
 }
 
 static int to_row_major_cplx(dftfe_b200_ctx *ctx, double *S_d, int N) {
@@ -901,21 +1107,38 @@ static int to_row_major_cplx(dftfe_b200_ctx *ctx, double *S_d, int N) {
   return 0;
 }
 
-int dftfe_b200_xtx(dftfe_b200_ctx *ctx, const double *X_d, int32_t N, double *S_d) {
+int dftfe_b200_xtx(dftfe_b200_ctx *ctx, const double *X_d, int32_t N, double *S_d, int32_t mixed_prec) {
   DB_CTX(ctx);
-  DB_TRY(xtx_impl(ctx, X_d, N, S_d));
+  DB_TRY(overlap_any(ctx, X_d, N, S_d, mixed_prec != 0));
   return ctx->cplx ? to_row_major_cplx(ctx, S_d, N) : 0;
 }
 
-int dftfe_b200_xthx(dftfe_b200_ctx *ctx, const double *X_d, int32_t N, double *Hp_d) {
+int dftfe_b200_xthx(dftfe_b200_ctx *ctx, const double *X_d, int32_t N, int32_t n_core, double *Hp_d,
+                    int32_t mixed_prec) {
   DB_CTX(ctx);
-  DB_TRY(xthx_impl(ctx, X_d, N, Hp_d));
+  DB_CHECK(n_core >= 0 && n_core <= N, "xthx: n_core (%d) must be in [0, N]", n_core);
+  DB_TRY(projham_any(ctx, X_d, N, Hp_d, mixed_prec != 0, n_core));
   return ctx->cplx ? to_row_major_cplx(ctx, Hp_d, N) : 0;
 }
 
-int dftfe_b200_rotate(dftfe_b200_ctx *ctx, double *X_d, int32_t N, const double *Q_d) {
+int dftfe_b200_rotate(dftfe_b200_ctx *ctx, double *X_d, int32_t N, const double *Q_d, int32_t mixed_mode) {
   DB_CTX(ctx);
-  return rotate_impl(ctx, X_d, N, Q_d, false);
+  DB_CHECK(mixed_mode >= 0 && mixed_mode <= 2, "rotate: mixed_mode must be 0, 1 or 2");
+  return rotate_impl(ctx, X_d, N, Q_d, false, mixed_mode);
+}
+
+int dftfe_b200_rotate_spectrum_split(dftfe_b200_ctx *ctx, double *X_d, int32_t N, const double *Q_d,
+                                     int32_t n_frac, double *X_frac_d) {
+  DB_CTX(ctx);
+  DB_CHECK(n_frac > 0 && n_frac <= N && X_frac_d, "rotate_spectrum_split: bad n_frac / null output");
+  // Q_d row-major N x N: the kernels want exactly that, so go straight to rotate_real on the column slice
+  if (!ctx->cplx) return rotate_real(ctx, X_d, N, Q_d, false, N - n_frac, n_frac, X_frac_d, n_frac);
+  const int Nr = 2 * N;
+  DB_TRY(ctx->denseG.alloc((size_t)Nr * Nr));
+  ctx->launches += 1;
+  cplx_embed_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(Q_d, N, 0, ctx->denseG.p);
+  DB_CUDA(cudaGetLastError());
+  return rotate_real(ctx, X_d, Nr, ctx->denseG.p, false, 2 * (N - n_frac), 2 * n_frac, X_frac_d, 2 * n_frac);
 }
 
 int dftfe_b200_lanczos_bounds(dftfe_b200_ctx *ctx, int32_t reproducible, double bounds_out_h[2]) {
@@ -944,11 +1167,12 @@ int dftfe_b200_get_spectrum_bounds(dftfe_b200_ctx *ctx, double out_h[3]) {
   return 0;
 }
 
-int dftfe_b200_solve(dftfe_b200_ctx *ctx, double *X_d, int32_t N, const dftfe_b200_solve_params *params,
-                     double *eig_out_h, double *res_out_h, double *upper_bound_out_h) {
+int dftfe_b200_solve(dftfe_b200_ctx *ctx, double *X_d, double *X_frac_d, int32_t N,
+                     const dftfe_b200_solve_params *params, double *eig_out_h, double *res_out_h,
+                     double *upper_bound_out_h) {
   DB_CTX(ctx);
   DB_CHECK(params && eig_out_h, "solve: params and eig_out_h are required");
-  return solve_impl(ctx, X_d, N, params, eig_out_h, res_out_h, upper_bound_out_h);
+  return solve_impl(ctx, X_d, X_frac_d, N, params, eig_out_h, res_out_h, upper_bound_out_h);
 }
 
 }  // extern "C"

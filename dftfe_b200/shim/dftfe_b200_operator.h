@@ -71,9 +71,18 @@ class operatorDFTDeviceClass {
   // DeviceCCLWrapper::init equivalent: id produced by dftfe_b200_nccl_unique_id on rank 0 and MPI_Bcast by the caller
   void initComm(const uint8_t id[128], int rank, int nranks) { check(dftfe_b200_comm_init(d_ctx, id, rank, nranks), "comm_init"); }
 
-  // computeHamiltonianMatricesAllkpt output for the active (k, spin): d_cellHamiltonianMatrixFlattenedDevice
-  void reinitkPointSpinIndex(const double *cellHamiltonianMatrixFlattenedDevice) {
-    check(dftfe_b200_set_cell_hamiltonian(d_ctx, cellHamiltonianMatrixFlattenedDevice), "set_cell_hamiltonian");
+  // computeHamiltonianMatricesAllkpt output (kohnShamDFTOperatorDevice.cc:1060-3606): the flattened
+  // d_cellHamiltonianMatrixFlattenedDevice holds nKptSpin sets of nC*n*n entries; hand each one over once per SCF
+  void setCellHamiltonian(const unsigned int kPointSpinIndex, const double *cellHamiltonianMatrixFlattenedDevice) {
+    check(dftfe_b200_set_cell_hamiltonian_kpt(d_ctx, (int32_t)kPointSpinIndex, cellHamiltonianMatrixFlattenedDevice),
+          "set_cell_hamiltonian_kpt");
+  }
+  // kohnShamDFTOperatorDevice.cc:1033-1058; the flat index is (1 + spinPolarized) * kPointIndex + spinIndex,
+  // the one the reference uses to address d_cellHamiltonianMatrixFlattenedDevice
+  void reinitkPointSpinIndex(const unsigned int kPointIndex, const unsigned int spinIndex,
+                             const unsigned int spinPolarized = 0) {
+    check(dftfe_b200_reinit_kpoint_spin_index(d_ctx, (int32_t)((1 + spinPolarized) * kPointIndex + spinIndex)),
+          "reinit_kpoint_spin_index");
   }
 
   // kohnShamDFTOperatorDevice.cc:3765-3860
@@ -88,16 +97,17 @@ class operatorDFTDeviceClass {
           "HX");
   }
 
-  // kohnShamDFTOperatorDevice.cc:3874-3997 (FP64; the compute/communication split flags are an
-  // implementation detail of the reference's 2-block overlap schedule and are rejected)
+  // kohnShamDFTOperatorDevice.cc:3874-3997.  mixPrecFlag: FP32 ghost payloads (the FP32 scratch vector is owned
+  // by the context).  The computePart1/2 split flags exist for the reference's hand-interleaved two-block
+  // schedule; here the overlap lives inside dftfe_b200_cheb_filter_all (two stream lanes), so they are rejected.
   template <class Vec, class VecFP32>
   void HXCheby(Vec &X, VecFP32 & /*XTempFP32*/, Vec & /*projectorKetTimesVector*/, const unsigned int /*localVectorSize*/,
                const unsigned int numberComponents, Vec &Y, bool mixPrecFlag = false,
                bool returnBeforeCompressSkipUpdateSkipNonLocal = false,
                bool returnBeforeCompressSkipUpdateSkipLocal = false) {
-    if (mixPrecFlag || returnBeforeCompressSkipUpdateSkipNonLocal || returnBeforeCompressSkipUpdateSkipLocal)
-      throw std::runtime_error("HXCheby: mixed precision / split-phase flags are not provided (FP64, fused)");
-    check(dftfe_b200_hx_cheby(d_ctx, X.begin(), Y.begin(), (int32_t)numberComponents), "HXCheby");
+    if (returnBeforeCompressSkipUpdateSkipNonLocal || returnBeforeCompressSkipUpdateSkipLocal)
+      throw std::runtime_error("HXCheby: split-phase flags are not provided (the overlap is internal to the filter loop)");
+    check(dftfe_b200_hx_cheby(d_ctx, X.begin(), Y.begin(), (int32_t)numberComponents, mixPrecFlag ? 1 : 0), "HXCheby");
   }
 
   // kohnShamDFTOperatorDevice.cc:4001-4157.  projHamPar receives the lower triangle exactly as the
@@ -108,21 +118,44 @@ class operatorDFTDeviceClass {
     std::vector<double> host((size_t)N * N);
     double *dev = nullptr;
     if (cudaMalloc(&dev, host.size() * sizeof(double)) != cudaSuccess) throw std::runtime_error("XtHX: cudaMalloc");
-    int rc = dftfe_b200_xthx(d_ctx, X, (int32_t)N, dev);
+    int rc = dftfe_b200_xthx(d_ctx, X, (int32_t)N, 0, dev, 0);
     if (rc == 0) rc = dftfe_b200_sync(d_ctx);
     cudaMemcpy(host.data(), dev, host.size() * sizeof(double), cudaMemcpyDeviceToHost);
     cudaFree(dev);
     check(rc, "XtHX");
     fillLowerTriangle(host, N, projHamPar);
   }
+  // XtHXOverlapComputeCommun (:4161-4519): same result; compute/communication overlap is the library's business
+  template <class Vec, class Matrix, class... Ignored>
+  void XtHXOverlapComputeCommun(const double *X, Vec &Xb, Vec &HXb, Vec &projectorKetTimesVector, const unsigned int M,
+                                const unsigned int N, Matrix &projHamPar, Ignored &&...rest) {
+    XtHX(X, Xb, HXb, projectorKetTimesVector, M, N, projHamPar, rest...);
+  }
+  // XtHXMixedPrecOverlapComputeCommun (:4550-5080): column blocks inside the first Noc states in FP32
+  template <class Vec, class VecFP32, class Matrix, class... Ignored>
+  void XtHXMixedPrecOverlapComputeCommun(const double *X, Vec & /*Xb*/, VecFP32 & /*floatXb*/, Vec & /*HXb*/,
+                                         Vec & /*projectorKetTimesVector*/, const unsigned int /*M*/,
+                                         const unsigned int N, const unsigned int Noc, Matrix &projHamPar,
+                                         Ignored &&...) {
+    std::vector<double> host((size_t)N * N);
+    double *dev = nullptr;
+    if (cudaMalloc(&dev, host.size() * sizeof(double)) != cudaSuccess) throw std::runtime_error("XtHX: cudaMalloc");
+    int rc = dftfe_b200_xthx(d_ctx, X, (int32_t)N, (int32_t)Noc, dev, 1);
+    if (rc == 0) rc = dftfe_b200_sync(d_ctx);
+    cudaMemcpy(host.data(), dev, host.size() * sizeof(double), cudaMemcpyDeviceToHost);
+    cudaFree(dev);
+    check(rc, "XtHXMixedPrecOverlapComputeCommun");
+    fillLowerTriangle(host, N, projHamPar);
+  }
 
   // fillParallelOverlapMatScalapack (linearAlgebraOperationsDevice.cc:3078-3240)
+  // mixedPrec: fillParallelOverlapMatMixedPrecScalapack (:3543-3798)
   template <class Matrix>
-  void fillParallelOverlapMat(const double *X, const unsigned int N, Matrix &overlapMatPar) {
+  void fillParallelOverlapMat(const double *X, const unsigned int N, Matrix &overlapMatPar, bool mixedPrec = false) {
     std::vector<double> host((size_t)N * N);
     double *dev = nullptr;
     if (cudaMalloc(&dev, host.size() * sizeof(double)) != cudaSuccess) throw std::runtime_error("XtX: cudaMalloc");
-    int rc = dftfe_b200_xtx(d_ctx, X, (int32_t)N, dev);
+    int rc = dftfe_b200_xtx(d_ctx, X, (int32_t)N, dev, mixedPrec ? 1 : 0);
     if (rc == 0) rc = dftfe_b200_sync(d_ctx);
     cudaMemcpy(host.data(), dev, host.size() * sizeof(double), cudaMemcpyDeviceToHost);
     cudaFree(dev);
@@ -133,8 +166,9 @@ class operatorDFTDeviceClass {
   // linearAlgebraOperationsDevice::chebyshevFilter (linearAlgebraOperationsDevice.cc:531-727)
   template <class Vec>
   void chebyshevFilter(Vec &XArray, Vec &YArray, const unsigned int numberVectors, const unsigned int m, const double a,
-                       const double b, const double a0) {
-    check(dftfe_b200_cheb_filter(d_ctx, XArray.begin(), YArray.begin(), (int32_t)numberVectors, (int32_t)m, a, b, a0),
+                       const double b, const double a0, const bool mixedPrecOverall = false) {
+    check(dftfe_b200_cheb_filter(d_ctx, XArray.begin(), YArray.begin(), (int32_t)numberVectors, (int32_t)m, a, b, a0,
+                                 mixedPrecOverall ? 1 : 0),
           "chebyshevFilter");
   }
 
@@ -172,24 +206,28 @@ class chebyshevOrthogonalizedSubspaceIterationSolverDevice {
   // solve(operatorMatrix, BLASWrapperPtr, elpaScala, eigenVectorsFlattenedDevice, eigenVectorsRotFracDensityFlattenedDevice,
   //       flattenedSize, totalNumberWaveFunctions, eigenValues, residuals, devicecclMpiCommDomain, interBandGroupComm,
   //       isFirstFilteringCall, computeResidual, useMixedPrecOverall, isFirstScf) -> upper bound  (:155-736)
+  // eigenValues.size() < N selects spectrum splitting exactly as in the reference (:553-575): only the top
+  // eigenValues.size() states are returned, rotated into eigenVectorsRotFracDensityFlattenedDevice.
   double solve(operatorDFTDeviceClass &operatorMatrix, double *eigenVectorsFlattenedDevice,
-               double * /*eigenVectorsRotFracDensityFlattenedDevice*/, const unsigned int flattenedSize,
+               double *eigenVectorsRotFracDensityFlattenedDevice, const unsigned int flattenedSize,
                const unsigned int totalNumberWaveFunctions, std::vector<double> &eigenValues,
                std::vector<double> &residuals, const bool isFirstFilteringCall, const bool computeResidual,
                const bool useMixedPrecOverall = false, const bool isFirstScf = false) {
     (void)flattenedSize;
-    if (useMixedPrecOverall) throw std::runtime_error("solve: mixed precision is not provided yet (FP64 only)");
-    if (eigenValues.size() != totalNumberWaveFunctions)
-      throw std::runtime_error("solve: spectrum splitting (eigenValues.size() != N) is not provided yet");
+    if (eigenValues.empty() || eigenValues.size() > totalNumberWaveFunctions)
+      throw std::runtime_error("solve: eigenValues.size() must be in [1, N]");
     dftfe_b200_solve_params p = d_params;
     p.is_first_filtering_call = isFirstFilteringCall ? 1 : 0;
     p.compute_residual = computeResidual ? 1 : 0;
     p.is_first_scf = isFirstScf ? 1 : 0;
+    p.use_mixed_prec_overall = useMixedPrecOverall ? 1 : 0;
+    p.n_core_states = (int32_t)(totalNumberWaveFunctions - eigenValues.size());
     if (!isFirstFilteringCall)
       check(dftfe_b200_reinit_spectrum_bounds(operatorMatrix.context(), d_lowerWanted, d_lowerUnwanted), "reinitSpectrumBounds");
-    residuals.resize(totalNumberWaveFunctions);
-    check(dftfe_b200_solve(operatorMatrix.context(), eigenVectorsFlattenedDevice, (int32_t)totalNumberWaveFunctions, &p,
-                           eigenValues.data(), residuals.data(), &d_upperUnwanted),
+    residuals.resize(eigenValues.size());
+    check(dftfe_b200_solve(operatorMatrix.context(), eigenVectorsFlattenedDevice,
+                           p.n_core_states > 0 ? eigenVectorsRotFracDensityFlattenedDevice : nullptr,
+                           (int32_t)totalNumberWaveFunctions, &p, eigenValues.data(), residuals.data(), &d_upperUnwanted),
           "solve");
     return d_upperUnwanted;
   }

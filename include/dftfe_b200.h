@@ -82,6 +82,19 @@ typedef struct {
   int32_t compute_residual;
   int32_t use_cgs_rr;            /* 1: CGS + RR (useSubspaceProjectedSHEPGPU), 0: RR-GEP    */
   int32_t reproducible_output;   /* 40 Lanczos steps, |f| instead of |f|/10                */
+  /* mixed precision (real build; the complex build runs these pieces in FP64): every flag below is
+   * gated by use_mixed_prec_overall, the useMixedPrecOverall argument of solve() */
+  int32_t use_mixed_prec_overall;
+  int32_t use_mixed_prec_cheby;               /* FP32 ghost payloads in the filter (useMixedPrecCheby)      */
+  int32_t use_mixed_prec_cgs_o;               /* FP32 off-diagonal blocks of X^T X (useMixedPrecCGS_O)      */
+  int32_t use_mixed_prec_cgs_sr;              /* FP32 off-diagonal part of X L^-T (useMixedPrecCGS_SR)      */
+  int32_t use_mixed_prec_xthx_spectrum_split; /* FP32 X^T H X blocks inside the core states                 */
+  int32_t use_mixed_prec_subspace_rot_rr;     /* FP32 off-diagonal part of X Q (useMixedPrecSubspaceRotRR)  */
+  int32_t num_core_wfc_xthx;     /* numCoreWfcXtHX: core states for the mixed X^T H X of CGS + RR          */
+  /* spectrum splitting (rayleighRitzGEPSpectrumSplitDirect): N - eigenValues.size() of the reference.
+   * > 0: only the top N - n_core_states eigenpairs are returned, X_frac_d receives the rotated states and
+   * X_d is left orthonormalised but unrotated */
+  int32_t n_core_states;
   int32_t reserved;
   double first_scf_scaling;      /* chebyshevFilterPolyDegreeFirstScfScalingFactor (1.34)  */
 } dftfe_b200_solve_params;
@@ -154,6 +167,14 @@ int dftfe_b200_set_nonlocal(dftfe_b200_ctx *ctx, int32_t n_atoms, const int32_t 
  * buffer is not referenced after the call returns. */
 int dftfe_b200_set_cell_hamiltonian(dftfe_b200_ctx *ctx, const double *H_d);
 int dftfe_b200_set_cell_hamiltonian_host(dftfe_b200_ctx *ctx, const double *H_h);
+/* Several (k-point, spin) sets, the reference's [nSpinKpt][nC][n][n] storage
+ * (computeHamiltonianMatricesAllkpt, kohnShamDFTOperatorDevice.cc:1060-3606): store the set `kpt_spin_index`
+ * (and make it active); dftfe_b200_set_cell_hamiltonian == index 0.  Stored sets stay valid until
+ * set_constraints / set_mass is called again. */
+int dftfe_b200_set_cell_hamiltonian_kpt(dftfe_b200_ctx *ctx, int32_t kpt_spin_index, const double *H_d);
+/* operatorDFTDeviceClass::reinitkPointSpinIndex (kohnShamDFTOperatorDevice.cc:1033-1058): switch the
+ * operator to a stored set; no data moves. */
+int dftfe_b200_reinit_kpoint_spin_index(dftfe_b200_ctx *ctx, int32_t kpt_spin_index);
 
 /* ---- distributed-vector primitives (MultiVector / MPICommunicatorP2P) ---- */
 int dftfe_b200_update_ghost_values(dftfe_b200_ctx *ctx, double *x_d, int32_t ncols);
@@ -165,6 +186,17 @@ int dftfe_b200_constraints_distribute(dftfe_b200_ctx *ctx, double *x_d, int32_t 
 int dftfe_b200_constraints_distribute_slave_to_master(dftfe_b200_ctx *ctx, double *x_d, int32_t ncols);
 int dftfe_b200_constraints_set_zero(dftfe_b200_ctx *ctx, double *x_d, int32_t ncols);
 
+/* ---- block slices and scalings (utils/DeviceKernelsGeneric.cc) ------------ */
+/* stridedCopyToBlockConstantStride / stridedCopyFromBlockConstantStride (:156-209): block[r, 0:ncols] <->
+ * X[r, j0:j0+ncols] over the M owned rows (X row-major M x N, block row-major with ld = ncols). */
+int dftfe_b200_strided_copy_to_block(dftfe_b200_ctx *ctx, const double *X_d, int32_t N, int32_t j0, double *block_d,
+                                     int32_t ncols);
+int dftfe_b200_strided_copy_from_block(dftfe_b200_ctx *ctx, double *X_d, int32_t N, int32_t j0, const double *block_d,
+                                       int32_t ncols);
+/* stridedBlockScale (:257-278): x[r, :] *= alpha * s[r] over the M owned rows; which = 0: s = 1,
+ * 1: s = M^1/2 (getSqrtMassVec), 2: s = M^-1/2 (getInvSqrtMassVec). */
+int dftfe_b200_strided_block_scale(dftfe_b200_ctx *ctx, double *x_d, int32_t ncols, double alpha, int32_t which);
+
 /* ---- operator ------------------------------------------------------------ */
 /* operatorDFTDeviceClass::HX (kohnShamDFTOperatorDevice.cc:3765-3860):
  *   dst = (scale_flag ? dst : M^-1/2 dst) + scalar * M^-1/2 H M^-1/2 src
@@ -172,40 +204,55 @@ int dftfe_b200_constraints_set_zero(dftfe_b200_ctx *ctx, double *x_d, int32_t nc
  * src is left unscaled (do_unscaling_src != 0) or scaled by scalar*M^-1/2. */
 int dftfe_b200_hx(dftfe_b200_ctx *ctx, double *src_d, double *dst_d, int32_t ncols, int32_t scale_flag,
                   double scalar, int32_t do_unscaling_src);
-/* operatorDFTDeviceClass::HXCheby (kohnShamDFTOperatorDevice.cc:3874-3997),
- * FP64, no compute/communication split: dst += H src (no mass scalings). */
-int dftfe_b200_hx_cheby(dftfe_b200_ctx *ctx, double *src_d, double *dst_d, int32_t ncols);
+/* operatorDFTDeviceClass::HXCheby (kohnShamDFTOperatorDevice.cc:3874-3997), no compute/communication
+ * split: dst += H src (no mass scalings).  mixed_prec = the reference's chebMixedPrec flag: ghost values
+ * travel as FP32 in both exchange directions (:3899-3915, 3953-3990); all arithmetic stays FP64. */
+int dftfe_b200_hx_cheby(dftfe_b200_ctx *ctx, double *src_d, double *dst_d, int32_t ncols, int32_t mixed_prec);
 
 /* linearAlgebraOperationsDevice::chebyshevFilter
  * (src/linAlg/linearAlgebraOperationsDevice.cc:531-727): degree-m scaled Chebyshev
  * polynomial of M^-1/2 H M^-1/2 applied in place to one (M+G) x B block held in
  * the Loewdin basis.  y_d is the caller's scratch block of the same shape.
- * One fused HBM pass per degree. */
+ * One fused HBM pass per degree.  mixed_prec = mixedPrecOverall && useMixedPrecCheby: FP32 ghost payloads
+ * for degrees 2..m-1 (the HXCheby calls, :612-622 and :700-708); degrees 1 and m stay FP64 (HX). */
 int dftfe_b200_cheb_filter(dftfe_b200_ctx *ctx, double *x_d, double *y_d, int32_t ncols, int32_t m, double a,
-                           double b, double a0);
+                           double b, double a0, int32_t mixed_prec);
 
 /* The blocked filter loop of solve() (solver .cc:376-526) over a device-resident X
  * (row-major M x N, Loewdin basis, N a multiple of B): every block of B columns is
- * sliced out, filtered and written back. */
+ * sliced out, filtered and written back.  With more than one rank two blocks are in flight on two
+ * streams so that one block's ghost exchange overlaps the other's cell kernels (the reference's
+ * overlapComputeCommunCheby two-block filter, linearAlgebraOperationsDevice.cc:734-1443). */
 int dftfe_b200_cheb_filter_all(dftfe_b200_ctx *ctx, double *X_d, int32_t N, int32_t m, double a, double b,
-                               double a0);
+                               double a0, int32_t mixed_prec);
 /* Same for a HOST-resident X (pinned memory recommended).  Host->device and
  * device->host block copies run on two copy streams and overlap the filtering of
  * the neighbouring blocks.  Synchronous: X_h holds the result on return. */
 int dftfe_b200_cheb_filter_all_host(dftfe_b200_ctx *ctx, double *X_h, int32_t N, int32_t m, double a, double b,
-                                    double a0);
+                                    double a0, int32_t mixed_prec);
 
 /* ---- subspace projections / rotation ------------------------------------- */
 /* S = X^H X, all-reduced; full symmetric / Hermitian N x N written to S_d (row-major; complex: S[i][j] =
  * sum_m conj(X[m,i]) X[m,j], interleaved)
- * (fillParallelOverlapMatScalapack, linearAlgebraOperationsDevice.cc:3078-3240). */
-int dftfe_b200_xtx(dftfe_b200_ctx *ctx, const double *X_d, int32_t N, double *S_d);
+ * (fillParallelOverlapMatScalapack, linearAlgebraOperationsDevice.cc:3078-3240).
+ * mixed_prec (real build): diagonal B x B blocks FP64, the blocks below them FP32 with an FP32 all-reduce
+ * (fillParallelOverlapMatMixedPrecScalapack, :3543-3798). */
+int dftfe_b200_xtx(dftfe_b200_ctx *ctx, const double *X_d, int32_t N, double *S_d, int32_t mixed_prec);
 /* Hp = X^T (M^-1/2 H M^-1/2) X, all-reduced, full symmetric N x N
- * (operatorDFTDeviceClass::XtHX, kohnShamDFTOperatorDevice.cc:4001-4157). */
-int dftfe_b200_xthx(dftfe_b200_ctx *ctx, const double *X_d, int32_t N, double *Hp_d);
+ * (operatorDFTDeviceClass::XtHX, kohnShamDFTOperatorDevice.cc:4001-4157).
+ * mixed_prec with n_core = Noc > 0 (real build): column blocks ending inside the first Noc states are
+ * computed and all-reduced in FP32 (XtHXMixedPrecOverlapComputeCommun, :4550-5080). */
+int dftfe_b200_xthx(dftfe_b200_ctx *ctx, const double *X_d, int32_t N, int32_t n_core, double *Hp_d,
+                    int32_t mixed_prec);
 /* X <- X Q with Q row-major N x N on device (subspaceRotationScalapack,
- * linearAlgebraOperationsDevice.cc:1832-2241). */
-int dftfe_b200_rotate(dftfe_b200_ctx *ctx, double *X_d, int32_t N, const double *Q_d);
+ * linearAlgebraOperationsDevice.cc:1832-2241).  mixed_mode (real build): 0 FP64; 1 FP64 diagonal B x B blocks +
+ * FP32 off-diagonal (subspaceRotationCGSMixedPrecScalapack, :2243-2658); 2 FP64 diag(Q) + FP32 (Q - diag Q)
+ * (subspaceRotationRRMixedPrecScalapack, :2660-3076). */
+int dftfe_b200_rotate(dftfe_b200_ctx *ctx, double *X_d, int32_t N, const double *Q_d, int32_t mixed_mode);
+/* X_frac (M x n_frac) = X Q[:, N-n_frac : N], X untouched (subspaceRotationSpectrumSplitScalapack,
+ * linearAlgebraOperationsDevice.cc:1446-1830). */
+int dftfe_b200_rotate_spectrum_split(dftfe_b200_ctx *ctx, double *X_d, int32_t N, const double *Q_d,
+                                     int32_t n_frac, double *X_frac_d);
 
 /* ---- eigensolver --------------------------------------------------------- */
 /* lanczosLowerUpperBoundEigenSpectrum (linearAlgebraOperationsDevice.cc:340-527):
@@ -218,16 +265,22 @@ int dftfe_b200_residual_norms(dftfe_b200_ctx *ctx, const double *X_d, int32_t N,
 int dftfe_b200_reinit_spectrum_bounds(dftfe_b200_ctx *ctx, double lower_wanted, double lower_unwanted);
 /* chebyshevOrthogonalizedSubspaceIterationSolverDevice::solve
  * (src/solvers/eigenSolvers/chebyshevOrthogonalizedSubspaceIterationSolverDevice.cc:155-736).
- * X_d: M x N, in/out.  eig_out_h[N], res_out_h[N] (may be NULL).  Returns the
- * upper bound of the unwanted spectrum through upper_bound_out_h. */
-int dftfe_b200_solve(dftfe_b200_ctx *ctx, double *X_d, int32_t N, const dftfe_b200_solve_params *params,
-                     double *eig_out_h, double *res_out_h, double *upper_bound_out_h);
+ * X_d: M x N, in/out (eigenVectorsFlattenedDevice).  X_frac_d: M x (N - n_core_states), out
+ * (eigenVectorsRotFracDensityFlattenedDevice), only with spectrum splitting, else may be NULL.
+ * eig_out_h / res_out_h: N - n_core_states values (res may be NULL).  Returns the upper bound of the
+ * unwanted spectrum through upper_bound_out_h. */
+int dftfe_b200_solve(dftfe_b200_ctx *ctx, double *X_d, double *X_frac_d, int32_t N,
+                     const dftfe_b200_solve_params *params, double *eig_out_h, double *res_out_h,
+                     double *upper_bound_out_h);
 /* bounds currently held by the solver object: {a0, bLow, bUp}. */
 int dftfe_b200_get_spectrum_bounds(dftfe_b200_ctx *ctx, double out_h[3]);
 
 /* ---- introspection / measurement ----------------------------------------- */
 /* Options: "generic_cell_kernel" = 1 forces the non-persistent cell kernel (the path
- * taken anyway for ragged column counts, odd leading dimensions and FE order 7). */
+ * taken anyway for ragged column counts, odd leading dimensions and FE order 7);
+ * "scalar_row_kernels" = 1 forces the scalar fallbacks of the HBM-bound row kernels (odd column counts);
+ * "overlap_lanes" = 0 / 1 / -1: two-block overlapped filter loop off / on / auto (on when nranks > 1);
+ * "cublas_projections" = 1: cuBLAS Dgemm instead of the DMMA projection / rotation kernels (A/B). */
 int dftfe_b200_set_option(dftfe_b200_ctx *ctx, const char *name, int32_t value);
 /* Number of cell colours, and per-colour cell counts (n_out entries filled). */
 int dftfe_b200_get_colouring(dftfe_b200_ctx *ctx, int32_t *n_colours_out, int32_t *cell_colour_out_h);

@@ -219,11 +219,31 @@ def HX(ranks, src, dst, scale_flag: bool, scalar: float, do_unscaling_src: bool 
             s[:M] *= (rp.sqrtMass[:M] / scalar)[:, None]
 
 
-def HXCheby(ranks, src, dst):
-    """src/dftOperator/kohnShamDFTOperatorDevice.cc:3874-3997 (FP64, no overlap
-    split): bare dst += H src with ghost update, distribute, slave->master and
-    accumulate; no mass scalings inside."""
-    update_ghost_values(ranks, src)
+def update_ghost_values_fp32(ranks, vecs):
+    """chebMixedPrec forward exchange (kohnShamDFTOperatorDevice.cc:3899-3915): the owned part is copied to a
+    float vector, exchanged, and only the ghost rows are copied back -> ghosts = double(float(owner value))."""
+    tmp = [v.astype(np.float32 if v.dtype == np.float64 else np.complex64) for v in vecs]
+    update_ghost_values(ranks, tmp)
+    for rp, v, t in zip(ranks, vecs, tmp):
+        v[rp.M:] = t[rp.M:]
+
+
+def accumulate_add_locally_owned_fp32(ranks, vecs):
+    """chebMixedPrec reverse exchange (kohnShamDFTOperatorDevice.cc:3953-3990): the whole vector is copied to
+    floats, accumulated in FP32, and the processor-boundary owned rows are copied back as doubles."""
+    f32 = np.float32 if vecs[0].dtype == np.float64 else np.complex64
+    tmp = [v.astype(f32) for v in vecs]
+    accumulate_add_locally_owned(ranks, tmp)
+    for r, (rp, v, t) in enumerate(zip(ranks, vecs, tmp)):
+        bnd = np.nonzero(proc_boundary_flags(ranks, r))[0]
+        v[bnd] = t[bnd]
+
+
+def HXCheby(ranks, src, dst, mixed_prec: bool = False):
+    """src/dftOperator/kohnShamDFTOperatorDevice.cc:3874-3997 (no overlap split): bare dst += H src with
+    ghost update, distribute, slave->master and accumulate; no mass scalings inside.  mixed_prec =
+    chebMixedPrec: both exchanges carry FP32 payloads."""
+    (update_ghost_values_fp32 if mixed_prec else update_ghost_values)(ranks, src)
     for rp, s, d in zip(ranks, src, dst):
         distribute(rp, s)
         compute_local_hamiltonian_times_x(rp, s, d, 1.0)
@@ -231,7 +251,7 @@ def HXCheby(ranks, src, dst):
     for rp, d in zip(ranks, dst):
         distribute_slave_to_master(rp, d)
     zero_out_ghosts(ranks, src)
-    accumulate_add_locally_owned(ranks, dst)
+    (accumulate_add_locally_owned_fp32 if mixed_prec else accumulate_add_locally_owned)(ranks, dst)
     zero_out_ghosts(ranks, dst)
 
 
@@ -271,10 +291,12 @@ def chebyshev_filter_inplace(ranks, X, m, a, b, a0):
         x[:] = o
 
 
-def chebyshev_filter_device_state(ranks, X, m: int, a: float, b: float, a0: float):
+def chebyshev_filter_device_state(ranks, X, m: int, a: float, b: float, a0: float, mixed_prec: bool = False):
     """src/linAlg/linearAlgebraOperationsDevice.cc:531-727 - the device statement
     with its pre-scaled (alpha1*M^-1/2 / M^1/2) state and the fused
-    ``combinedDeviceKernel`` (:37-64).  Must agree with ``chebyshev_filter``."""
+    ``combinedDeviceKernel`` (:37-64).  Must agree with ``chebyshev_filter``.
+    mixed_prec = mixedPrecOverall && useMixedPrecCheby: the HXCheby calls (degrees 2..m-1) exchange FP32
+    ghost payloads (:612-622, 700-708)."""
     e = (b - a) / 2.0
     c = (b + a) / 2.0
     sigma = e / (a0 - c)
@@ -299,7 +321,7 @@ def chebyshev_filter_device_state(ranks, X, m: int, a: float, b: float, a0: floa
                 x[:M] = coeff * y[:M] + alpha2 * x[:M]
                 y[:M] *= (alpha1 * rp.invSqrtMass[:M])[:, None]
                 x[:M] *= rp.sqrtMass[:M][:, None]
-            HXCheby(ranks, Y, X)
+            HXCheby(ranks, Y, X, mixed_prec)
         elif degree == m:
             for rp, x, y in zip(ranks, X, Y):
                 M = rp.M
@@ -317,7 +339,7 @@ def chebyshev_filter_device_state(ranks, X, m: int, a: float, b: float, a0: floa
                 x[:M] = coeff * y[:M] + alpha2 * x[:M]
                 y[:M] *= isq * alpha1
                 x[:M] *= sq
-            HXCheby(ranks, Y, X)
+            HXCheby(ranks, Y, X, mixed_prec)
         X, Y = Y, X
         sigma = sigma2
         alpha1_old = alpha1
@@ -418,6 +440,101 @@ def rayleigh_ritz(ranks, X, block: int):
     for rp, x in zip(ranks, X):
         x[:rp.M] = x[:rp.M] @ Q
     return evals
+
+
+# --------------------------------------------------------------------------
+# mixed-precision projections / rotations and spectrum splitting (real build)
+# --------------------------------------------------------------------------
+
+def xtx_mixed(ranks, X, block: int) -> np.ndarray:
+    """fillParallelOverlapMatMixedPrecScalapack (linearAlgebraOperationsDevice.cc:3543-3798): per column block
+    the diagonal ``block x block`` part in FP64, the rows below it as an FP32 GEMM on an FP32 copy of X
+    (:3641-3675) and an FP32 sum over ranks; only the lower triangle is filled, mirrored here."""
+    N = X[0].shape[1]
+    S = np.zeros((N, N))
+    Xo = _owned(ranks, X)
+    Xs = [x.astype(np.float32) for x in Xo]
+    for j in range(0, N, block):
+        B = min(block, N - j)
+        dp = 0
+        sp = np.zeros((N - j - B, B), dtype=np.float32)
+        for x, xs in zip(Xo, Xs):
+            dp = dp + x[:, j:j + B].T @ x[:, j:j + B]
+            if N - j - B > 0:
+                sp = sp + xs[:, j + B:].T @ xs[:, j:j + B]
+        S[j:j + B, j:j + B] = dp
+        S[j + B:, j:j + B] = sp
+    return np.tril(S) + np.tril(S, -1).T
+
+
+def xthx_mixed(ranks, X, block: int, n_core: int) -> np.ndarray:
+    """XtHXMixedPrecOverlapComputeCommun (kohnShamDFTOperatorDevice.cc:4550-5080): column blocks that end inside
+    the first ``n_core`` states are computed entirely in FP32 (FP32 copy of X times the FP32-rounded H~X block,
+    FP32 sum over ranks), the others in FP64."""
+    N = X[0].shape[1]
+    HXf = apply_HX_blocked(ranks, X, block)
+    Hp = np.zeros((N, N))
+    Xo, Ho = _owned(ranks, X), _owned(ranks, HXf)
+    for j in range(0, N, block):
+        B = min(block, N - j)
+        if j + B <= n_core:
+            acc = np.zeros((N - j, B), dtype=np.float32)
+            for x, h in zip(Xo, Ho):
+                acc = acc + x[:, j:].astype(np.float32).T @ h[:, j:j + B].astype(np.float32)
+        else:
+            acc = 0
+            for x, h in zip(Xo, Ho):
+                acc = acc + x[:, j:].T @ h[:, j:j + B]
+        Hp[j:, j:j + B] = acc
+    return np.tril(Hp) + np.tril(Hp, -1).T
+
+
+def subspace_rotation_cgs_mixed(ranks, X, U: np.ndarray, block: int):
+    """subspaceRotationCGSMixedPrecScalapack (linearAlgebraOperationsDevice.cc:2243-2658): X <- X U with the
+    diagonal ``block x block`` blocks of U applied in FP64 and the off-diagonal part as an FP32 GEMM."""
+    N = U.shape[0]
+    blk = np.arange(N) // block
+    on = blk[:, None] == blk[None, :]
+    Ud = np.where(on, U, 0.0)
+    Us = np.where(on, 0.0, U).astype(np.float32)
+    for rp, x in zip(ranks, X):
+        xo = x[:rp.M]
+        x[:rp.M] = xo @ Ud + (xo.astype(np.float32) @ Us).astype(np.float64)
+
+
+def subspace_rotation_rr_mixed(ranks, X, Q: np.ndarray):
+    """subspaceRotationRRMixedPrecScalapack (linearAlgebraOperationsDevice.cc:2660-3076):
+    X <- X diag(Q) (FP64, computeDiagQTimesXKernel) + X_fp32 (Q - diag Q)_fp32."""
+    d = np.diag(Q).copy()
+    Qs = (Q - np.diag(d)).astype(np.float32)
+    for rp, x in zip(ranks, X):
+        xo = x[:rp.M]
+        x[:rp.M] = xo * d[None, :] + (xo.astype(np.float32) @ Qs).astype(np.float64)
+
+
+def rayleigh_ritz_gep_spectrum_split(ranks, X, block: int, n_core: int, mixed=()):
+    """rayleighRitzGEPSpectrumSplitDirect (src/linAlg/rayleighRitzDevice.cc:821-1454): S = X^H X = L L^H,
+    X <- X L^-H (kept, NOT rotated), Hp = X^H H~ X, only eigenpairs n_core..N-1 of Hp are computed,
+    XFrac = X Q[:, n_core:].  Returns (eigenvalues[N - n_core], XFrac list).  ``mixed``: subset of
+    {"cgs_o", "cgs_sr", "xthx"} (real build)."""
+    mixed = set(mixed)
+    S = xtx_mixed(ranks, X, block) if "cgs_o" in mixed else xtx(ranks, X)
+    L = np.linalg.cholesky(S)
+    U = np.linalg.inv(L).conj().T
+    if "cgs_sr" in mixed:
+        subspace_rotation_cgs_mixed(ranks, X, U, block)
+    else:
+        for rp, x in zip(ranks, X):
+            x[:rp.M] = x[:rp.M] @ U
+    Hp = xthx_mixed(ranks, X, block, n_core) if "xthx" in mixed else xthx(ranks, X, block)
+    Hp = 0.5 * (Hp + Hp.conj().T)
+    evals, Q = np.linalg.eigh(Hp)
+    XFrac = []
+    for rp, x in zip(ranks, X):
+        xf = np.zeros((x.shape[0], Q.shape[0] - n_core), dtype=x.dtype)
+        xf[:rp.M] = x[:rp.M] @ Q[:, n_core:]
+        XFrac.append(xf)
+    return evals[n_core:], XFrac
 
 
 def eigen_residual_norm(ranks, X, evals, block: int) -> np.ndarray:
@@ -541,14 +658,18 @@ def set_chebyshev_order(upper_bound: float) -> int:
 
 
 def solve(ranks, X, block: int, cheb_order: int, bounds, use_gep: bool = True,
-          compute_residual: bool = True):
+          compute_residual: bool = True, n_core: int = 0, mixed=()):
     """chebyshevOrthogonalizedSubspaceIterationSolverDevice::solve
     (src/solvers/eigenSolvers/chebyshevOrthogonalizedSubspaceIterationSolverDevice.cc:155-736),
-    one band group, no spectrum splitting.
+    one band group.
 
     X: list of (M+G) x N arrays holding the wavefunctions in the usual FE basis
     (owned rows meaningful).  bounds = (a0, bLow, bUp).  Returns (eigenvalues,
-    residual norms); X is overwritten with the rotated, M^-1/2-scaled vectors."""
+    residual norms); X is overwritten with the rotated, M^-1/2-scaled vectors.
+    n_core > 0: spectrum splitting (:553-575) - returns (eigenvalues[N-n_core], residuals, XFrac).
+    mixed: subset of {"cheby", "cgs_o", "cgs_sr", "xthx", "rot_rr"} (useMixedPrecOverall and the matching
+    dftParameters flag on); "xthx" without spectrum splitting uses n_core_xthx = block (numCoreWfcXtHX)."""
+    mixed = set(mixed)
     a0, blow, bup = bounds
     N = X[0].shape[1]
     for rp, x in zip(ranks, X):
@@ -556,15 +677,42 @@ def solve(ranks, X, block: int, cheb_order: int, bounds, use_gep: bool = True,
     for j in range(0, N, block):
         Xb = [x[:, j:j + block].copy() for x in X]
         zero_out_ghosts(ranks, Xb)
-        chebyshev_filter_inplace(ranks, Xb, cheb_order, blow, bup, a0)
+        if "cheby" in mixed:
+            out = chebyshev_filter_device_state(ranks, Xb, cheb_order, blow, bup, a0, mixed_prec=True)
+            for xb, o in zip(Xb, out):
+                xb[:] = o
+        else:
+            chebyshev_filter_inplace(ranks, Xb, cheb_order, blow, bup, a0)
         for x, xb in zip(X, Xb):
             x[:, j:j + block] = xb
-    if use_gep:
-        evals = rayleigh_ritz_gep(ranks, X, block)
+    XFrac = None
+    if n_core > 0:
+        evals, XFrac = rayleigh_ritz_gep_spectrum_split(ranks, X, block, n_core, mixed)
+    elif use_gep:
+        if mixed & {"cgs_o", "rot_rr"}:
+            S = xtx_mixed(ranks, X, block) if "cgs_o" in mixed else xtx(ranks, X)
+            L = np.linalg.cholesky(S)
+            Linv = np.linalg.inv(L)
+            Hp = xthx(ranks, X, block)
+            Hp = 0.5 * (Hp + Hp.conj().T)
+            evals, Q = np.linalg.eigh(Linv @ Hp @ Linv.conj().T)
+            R = Linv.conj().T @ Q
+            if "rot_rr" in mixed:
+                subspace_rotation_rr_mixed(ranks, X, R)
+            else:
+                for rp, x in zip(ranks, X):
+                    x[:rp.M] = x[:rp.M] @ R
+        else:
+            evals = rayleigh_ritz_gep(ranks, X, block)
     else:
         cholesky_gram_schmidt(ranks, X)
         evals = rayleigh_ritz(ranks, X, block)
-    res = eigen_residual_norm(ranks, X, evals, block) if compute_residual else None
+    tgt = XFrac if n_core > 0 else X
+    res = eigen_residual_norm(ranks, tgt, evals, block) if compute_residual else None
     for rp, x in zip(ranks, X):
         x[:rp.M] *= rp.invSqrtMass[:rp.M][:, None]        # :719-733
+    if n_core > 0:
+        for rp, x in zip(ranks, XFrac):
+            x[:rp.M] *= rp.invSqrtMass[:rp.M][:, None]
+        return evals, res, XFrac
     return evals, res

@@ -33,13 +33,22 @@ int main(int argc, char **) {
     Mat m(4);
     op.HX(a, pk, 0u, 4u, false, 1.0, b);
     op.HXCheby(a, f, pk, 0u, 4u, b);
+    op.HXCheby(a, f, pk, 0u, 4u, b, true);
     op.XtHX(nullptr, a, b, pk, 0u, 4u, m, nullptr, nullptr);
+    op.XtHXOverlapComputeCommun(nullptr, a, b, pk, 0u, 4u, m, nullptr, nullptr);
+    op.XtHXMixedPrecOverlapComputeCommun(nullptr, a, f, b, pk, 0u, 4u, 2u, m, nullptr, nullptr);
     op.fillParallelOverlapMat(nullptr, 4u, m);
+    op.fillParallelOverlapMat(nullptr, 4u, m, true);
     op.chebyshevFilter(a, b, 4u, 10u, 1.0, 2.0, 0.0);
+    op.chebyshevFilter(a, b, 4u, 10u, 1.0, 2.0, 0.0, true);
+    op.setCellHamiltonian(1u, nullptr);
+    op.reinitkPointSpinIndex(1u, 0u);
     dftfe_b200_solve_params p{};
     chebyshevOrthogonalizedSubspaceIterationSolverDevice s(0, 0, 0, p);
     std::vector<double> ev(4), res;
     s.solve(op, nullptr, nullptr, 0u, 4u, ev, res, true, true);
+    std::vector<double> evFrac(2);
+    s.solve(op, nullptr, nullptr, 0u, 4u, evFrac, res, false, true, true);  // spectrum splitting + mixed precision
   }
   std::printf("%s\n", dftfe_b200_version());
   return 0;

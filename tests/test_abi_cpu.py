@@ -4,6 +4,7 @@ loudly (no CPU fallback) when there is no GPU."""
 import ctypes as C
 import os
 import re
+import subprocess
 
 import numpy as np
 import pytest
@@ -86,10 +87,20 @@ def test_create_rejects_unsupported_element(capi):
     assert rc == -4 and b"nodes per cell" in lib.dftfe_b200_last_error()
 
 
-def test_c_structs_match_header_layout(capi):
-    # int32,int32,int64 x4,int32,int32 and 10 x int32 + double
-    assert C.sizeof(capi.ProblemDesc) == 48
-    assert C.sizeof(capi.SolveParams) == 48
+def test_c_structs_match_header_layout(capi, tmp_path):
+    """sizeof / offsetof as the C compiler sees include/dftfe_b200.h == the ctypes mirrors."""
+    src = tmp_path / "layout.c"
+    fields = [f for f, _ in capi.SolveParams._fields_]
+    prints = "".join(f'printf("%zu\\n", offsetof(dftfe_b200_solve_params, {f}));' for f in fields)
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "dftfe_b200.h"\nint main(void){'
+                   'printf("%zu\\n%zu\\n", sizeof(dftfe_b200_problem_desc), sizeof(dftfe_b200_solve_params));'
+                   + prints + "return 0;}")
+    exe = tmp_path / "layout"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    out = [int(x) for x in subprocess.check_output([str(exe)], text=True).split()]
+    assert out[0] == C.sizeof(capi.ProblemDesc)
+    assert out[1] == C.sizeof(capi.SolveParams)
+    assert out[2:] == [getattr(capi.SolveParams, f).offset for f in fields]
 
 
 def test_cpp_adapter_compiles_and_links(capi, tmp_path):
