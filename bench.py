@@ -51,7 +51,8 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-scf", action="store_true", help="skip the full solve() (wall s per SCF iteration) section")
-    ap.add_argument("--lanes", type=int, default=-1, help="overlap_lanes option: -1 auto (on for N>1), 0 off, 1 on")
+    ap.add_argument("--lanes", type=int, default=1, help="overlap_lanes option: 1 two blocks in flight (default), 0 one")
+    ap.add_argument("--reserved-sms", type=int, default=0, help="SMs the cell kernel leaves free for NCCL kernels")
     ap.add_argument("--mixed", action="store_true", help="useMixedPrecCheby: FP32 ghost payloads in the filter")
     return ap.parse_args()
 
@@ -193,7 +194,7 @@ def workload_config(args, nranks):
             "fe_order": P_ORDER, "cells_per_gpu": args.cells ** 3, "n_wavefunctions": args.nwfc,
             "cheby_block": min(BLOCK, args.nwfc), "degree": args.degree, "partition": f"brick {rank_grid_for(nranks)}",
             "l2_policy": "inputs larger than L2 (X block 2.2 GB, cell H 4.6 GB per pass)",
-            "overlap_lanes": "on" if (args.lanes == 1 or (args.lanes < 0 and nranks > 1)) else "off",
+            "overlap_lanes": "on" if args.lanes != 0 else "off",
             "mixed_prec_cheby": bool(args.mixed)}
 
 
@@ -249,7 +250,8 @@ def main_ours(args):
         m = args.degree
 
         op.set_option("overlap_lanes", args.lanes)
-        lanes_on = args.lanes == 1 or (args.lanes < 0 and world > 1)
+        op.set_option("reserved_sms", args.reserved_sms)
+        lanes_on = args.lanes != 0
 
         def step():
             op.chebyshevFilterAll(X, m, A_LOW, up, A0, mixedPrec=args.mixed)
@@ -380,7 +382,7 @@ def main_ours(args):
             nbytes = rp.M * N * 8
             e2e = {"value": e2e_val, "unit": "applies/s", "h2d_bytes_per_step": int(nbytes),
                    "d2h_bytes_per_step": int(nbytes), "steps": n_e2e,
-                   "api": "dftfe_b200_cheb_filter_all_host (pinned host X, pipelined block copies)"}
+                   "api": "dftfe_b200_cheb_filter_all_host (pinned host X, block copies pipelined under two filter lanes)"}
             finite = finite and bool(torch.isfinite(Xh[:: max(1, rp.M // 1000)]).all().item())
         op.close()
 

@@ -338,7 +338,13 @@ struct PersistCfg {
   static constexpr int THREADS = (MMA_WARPS + 1) * 32;  // + one producer warp
   static constexpr size_t XBUF = (size_t)C::KPAD * LDS;  // doubles per buffer
   static constexpr size_t SMEM = 2 * XBUF * sizeof(double) + 2 * NODES * sizeof(uint32_t) + 4 * sizeof(uint64_t);
-  static constexpr int APF = 4;  // A-fragment prefetch depth in (virtual) k-steps
+#ifndef DB_APF
+#define DB_APF 4
+#endif
+#ifndef DB_L2_PREFETCH
+#define DB_L2_PREFETCH 0
+#endif
+  static constexpr int APF = DB_APF;  // A-fragment prefetch depth in (virtual) k-steps
 };
 
 // The row-tile count NTILE (TPW or TPW-1) is a compile-time constant per instantiation because a
@@ -453,8 +459,19 @@ __device__ __forceinline__ void mma_warp_items(const double *__restrict__ Ht, co
   }
 }
 
+#ifndef DB_MAXNREG
+#define DB_MAXNREG 0
+#endif
+// 13 warps x 152 registers x 32 lanes = 63232 <= 65536: the register file allows 152 per thread, but
+// __launch_bounds__(416, 1) makes ptxas budget for 512 threads (128 registers, with spills); __maxnreg__ states
+// the real limit.
 template <int NODES, bool CPLX>
-__global__ void __launch_bounds__(PersistCfg<NODES, CPLX>::THREADS, 1)
+__global__ void
+#if DB_MAXNREG
+__maxnreg__(DB_MAXNREG)
+#else
+__launch_bounds__(PersistCfg<NODES, CPLX>::THREADS, 1)
+#endif
 cell_matvec_persistent_kernel(const double *__restrict__ Ht, const uint32_t *__restrict__ cellRows,
                               const int32_t *__restrict__ cells, int nItems, const double *__restrict__ src,
                               double *__restrict__ dst, int ldx, int nColTiles, EpilogueParams ep) {
@@ -521,6 +538,23 @@ cell_matvec_persistent_kernel(const double *__restrict__ Ht, const uint32_t *__r
           tma_bulk_g2s(xs + k * LDS, src + (size_t)(myRows[j] & ROW_MASK) * ldx + col0, BT * sizeof(double),
                        &full[buf]);
       }
+#if DB_L2_PREFETCH
+      // pull the tiled H of the cell this CTA works on next-but-one into L2 (one CTA per cell does it: the
+      // one with column tile 0); the MMA warps then find their A fragments in L2 instead of HBM
+      {
+        const int nitem = item + 2 * (int)gridDim.x;
+        if (nitem < nItems && (nitem % nColTiles) == 0) {
+          const int ncell = cells[nitem / nColTiles];
+          const char *base = reinterpret_cast<const char *>(Ht + (size_t)ncell * C::HT_PER_CELL);
+          constexpr size_t total = C::HT_PER_CELL * sizeof(double);
+          constexpr size_t chunk = 16384;
+          for (size_t off = (size_t)lane * chunk; off < total; off += 32 * chunk) {
+            const uint32_t bytes = (uint32_t)((total - off) < chunk ? (total - off) : chunk);
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + off), "r"(bytes) : "memory");
+          }
+        }
+      }
+#endif
     }
   } else {
     constexpr int FULL_WARPS = C::MT - (C::TPW - 1) * C::WARPS;  // warps that own TPW tiles
@@ -577,7 +611,7 @@ int launch_impl2(dftfe_b200_ctx *ctx, const double *src, double *dst, int ncols,
     ProfScope ps(ctx, "cell_matvec");
     const int nItems = nCellsK * nColTiles;
     if (fast) {
-      const int grid = std::min(nItems, ctx->num_sms);
+      const int grid = std::min(nItems, std::max(1, ctx->num_sms - ctx->reserved_sms));
       cell_matvec_persistent_kernel<NODES, CPLX><<<grid, P::THREADS, P::SMEM, ctx->stream>>>(
           ctx->Hactive, ctx->cellRowsFlagged.p, ctx->colourCells.p + ctx->colourStart_h[k], nItems, src, dst, ldx,
           nColTiles, ep);

@@ -210,7 +210,7 @@ struct dftfe_b200_ctx {
   cudaStream_t laneStream[2] = {nullptr, nullptr};
   cudaEvent_t laneEvent[2] = {nullptr, nullptr};
   cudaEvent_t forkEvent = nullptr;
-  int overlap_lanes = -1;  // option "overlap_lanes": -1 auto (on when nranks > 1), 0 off, 1 on
+  int overlap_lanes = 1;   // option "overlap_lanes": 0 = one block in flight, otherwise two
   // transposed unpack map: boundary row -> positions in recvBuf
   int64_t nBoundaryRows = 0;
   dftfe_b200::DevBuf<uint32_t> bndRows, bndStarts, bndSlots;
@@ -220,7 +220,9 @@ struct dftfe_b200_ctx {
   // --- cell Hamiltonian (fragment-major)
   bool have_H = false;
   bool force_generic_cell_kernel = false;  // test hook: run the non-persistent kernel
+  int reserved_sms = 0;  // option "reserved_sms": SMs the persistent cell kernel leaves free (for NCCL's kernels)
   bool force_scalar_row_kernels = false;   // test hook: scalar fallbacks of the HBM-bound row kernels
+  std::map<const void *, int> rowKernelCtasPerSm;  // resident CTAs per SM of each row kernel (occupancy API)
   // one re-tiled set per (k-point, spin) index (reinitkPointSpinIndex, kohnShamDFTOperatorDevice.cc:1033-1058)
   std::map<int, dftfe_b200::DevBuf<double>> Hsets;
   int activeK = 0;
@@ -240,6 +242,7 @@ struct dftfe_b200_ctx {
   dftfe_b200::DevBuf<double> blockX, blockY;      // (M+G)*B
   dftfe_b200::DevBuf<double> blockX2;             // second block buffer (host-pipelined filter; lane 1)
   dftfe_b200::DevBuf<double> blockY2;             // lane 1 scratch
+  dftfe_b200::DevBuf<double> blockX3, blockX4;    // second buffer set of the host-resident filter loop
   cudaStream_t copyIn = nullptr, copyOut = nullptr;
   dftfe_b200::DevBuf<double> HXfull;              // M*Bw
   dftfe_b200::DevBuf<double> denseA, denseB, denseC, denseW;  // N*N scratch

@@ -545,6 +545,11 @@ int dftfe_b200_set_option(dftfe_b200_ctx *ctx, const char *name, int32_t value) 
     ctx->force_scalar_row_kernels = value != 0;
     return 0;
   }
+  if (std::strcmp(name, "reserved_sms") == 0) {
+    DB_CHECK(value >= 0 && value < ctx->num_sms, "set_option: reserved_sms out of range");
+    ctx->reserved_sms = value;
+    return 0;
+  }
   if (std::strcmp(name, "overlap_lanes") == 0) {
     ctx->overlap_lanes = value;
     return 0;

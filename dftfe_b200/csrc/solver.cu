@@ -817,16 +817,18 @@ static int rr_spectrum_split(dftfe_b200_ctx *ctx, double *X, double *XFrac, int 
   return 0;
 }
 
-// HOT LOOP 1 of solve() (solver .cc:376-526) on a device-resident X (M x N):
-// slice block -> filter -> write back, for every block of B columns.
+// HOT LOOP 1 of solve() (solver .cc:376-526): slice block -> filter -> write back, for every block of B
+// columns of X (row-major M x N), X resident in HBM (Xd) or in host memory (Xh, pinned recommended).
 //
-// With more than one rank (or option "overlap_lanes" = 1) two blocks are kept in flight on two lanes
-// (stream + scratch + exchange buffers each), their degrees enqueued alternately: while one block's cell
-// kernels own the SMs the other block's pack / NCCL send-recv / unpack run beside them, which is the
-// reference's overlapComputeCommunCheby two-block schedule (linearAlgebraOperationsDevice.cc:734-1443)
-// expressed with streams instead of a hand-interleaved 20-step sequence.  The arithmetic per block is
-// unchanged, so results are bit-identical to the single-lane loop.
-static int ensure_lanes(dftfe_b200_ctx *ctx) {
+// Two blocks are kept in flight on two lanes (stream + scratch + exchange buffers each), their degrees
+// enqueued alternately: while one block's cell kernels own the SMs the other block's pack / NCCL send-recv /
+// unpack run beside them - the reference's overlapComputeCommunCheby two-block schedule
+// (linearAlgebraOperationsDevice.cc:734-1443) expressed with streams instead of a hand-interleaved 20-step
+// sequence - and the tail of every colour launch (SMs idle while the last items finish) is filled by the other
+// lane's kernel, which is worth 2.6 % even on one GPU.  The arithmetic per block is unchanged, so results are
+// bit-identical to the single-lane loop.  Host-resident X: the next pair's H2D copies and the previous pair's
+// D2H copies run on two copy streams under the current pair's kernels (two sets of lane buffers).
+static int ensure_lanes(dftfe_b200_ctx *ctx, bool hostSets) {
   for (int l = 0; l < 2; ++l) {
     if (!ctx->laneStream[l]) DB_CUDA(cudaStreamCreateWithFlags(&ctx->laneStream[l], cudaStreamNonBlocking));
     if (!ctx->laneEvent[l]) DB_CUDA(cudaEventCreateWithFlags(&ctx->laneEvent[l], cudaEventDisableTiming));
@@ -835,132 +837,129 @@ static int ensure_lanes(dftfe_b200_ctx *ctx) {
   const size_t blk = (size_t)(ctx->M + ctx->G) * ctx->B * ctx->cm;
   DB_TRY(ctx->blockX2.alloc(blk));
   DB_TRY(ctx->blockY2.alloc(blk));
+  if (hostSets) {
+    DB_TRY(ctx->blockX3.alloc(blk));
+    DB_TRY(ctx->blockX4.alloc(blk));
+    if (!ctx->copyIn) {
+      DB_CUDA(cudaStreamCreateWithFlags(&ctx->copyIn, cudaStreamNonBlocking));
+      DB_CUDA(cudaStreamCreateWithFlags(&ctx->copyOut, cudaStreamNonBlocking));
+    }
+  }
   return 0;
 }
 
-static int filter_all_impl(dftfe_b200_ctx *ctx, double *X, int N, int m, double a, double b, double a0,
-                           const double *inScale, bool mixedPrec = false) {
+static int filter_blocks_impl(dftfe_b200_ctx *ctx, double *Xd, double *Xh, int N, int m, double a, double b,
+                              double a0, const double *inScale, bool mixedPrec) {
   const int B = std::min(ctx->B, N);
   DB_CHECK(N % B == 0, "number of wavefunctions (%d) must be a multiple of the Chebyshev block size (%d)", N, B);
   DB_CHECK(m >= 1, "Chebyshev degree must be >= 1");
   DB_TRY(ensure_block_scratch(ctx));
-  const int cm = ctx->cm;
-  const bool lanes = (ctx->overlap_lanes == 1 || (ctx->overlap_lanes < 0 && ctx->nranks > 1)) && N / B >= 2;
-  if (!lanes) {
-    for (int j = 0; j < N; j += B) {
-      DB_TRY(launch_block_copy_from_full(ctx, X, N * cm, j * cm, ctx->blockX.p, B * cm, ctx->M, inScale));
-      DB_TRY(ghost_zero(ctx, ctx->blockX.p, B * cm, B * cm));
-      DB_TRY(cheb_filter_impl(ctx, ctx->blockX.p, ctx->blockY.p, B, m, a, b, a0, mixedPrec));
-      DB_TRY(launch_block_copy_to_full(ctx, X, N * cm, j * cm, ctx->blockX.p, B * cm, ctx->M, nullptr));
-    }
-    return 0;
-  }
-  DB_TRY(ensure_lanes(ctx));
+  const int cm = ctx->cm, nb = N / B;
+  const bool host = Xh != nullptr;
+  const bool lanes = ctx->overlap_lanes != 0 && nb >= 2;
+  const int nl = lanes ? 2 : 1;
+  DB_TRY(ensure_lanes(ctx, host));
   cudaStream_t mainStream = ctx->stream;
-  double *bx[2] = {ctx->blockX.p, ctx->blockX2.p}, *by[2] = {ctx->blockY.p, ctx->blockY2.p};
+  // lane buffers: [set][lane]; the device-resident loop needs one set only
+  double *bx[2][2] = {{ctx->blockX.p, ctx->blockX2.p}, {ctx->blockX3.p, ctx->blockX4.p}};
+  double *by[2] = {ctx->blockY.p, ctx->blockY2.p};
+  const size_t rowBytes = (size_t)B * cm * sizeof(double), pitchBytes = (size_t)N * cm * sizeof(double);
+  const int nGroups = (nb + nl - 1) / nl;
+  std::vector<cudaEvent_t> evIn, evComp, evOut;
+  if (host) {
+    evIn.resize(nb);
+    evComp.resize(nb);
+    evOut.resize(nb);
+    for (int i = 0; i < nb; ++i) {
+      DB_CUDA(cudaEventCreateWithFlags(&evIn[i], cudaEventDisableTiming));
+      DB_CUDA(cudaEventCreateWithFlags(&evComp[i], cudaEventDisableTiming));
+      DB_CUDA(cudaEventCreateWithFlags(&evOut[i], cudaEventDisableTiming));
+    }
+  }
   DB_CUDA(cudaEventRecord(ctx->forkEvent, mainStream));
-  for (int l = 0; l < 2; ++l) DB_CUDA(cudaStreamWaitEvent(ctx->laneStream[l], ctx->forkEvent, 0));
-  int rc = 0;
+  for (int l = 0; l < nl; ++l) DB_CUDA(cudaStreamWaitEvent(ctx->laneStream[l], ctx->forkEvent, 0));
+  if (host) DB_CUDA(cudaStreamWaitEvent(ctx->copyIn, ctx->forkEvent, 0));
   auto on_lane = [&](int l) {
     ctx->lane = l;
     ctx->stream = ctx->laneStream[l];
   };
   auto body = [&]() -> int {
-    for (int j = 0; j < N; j += 2 * B) {
-      const int nl = (j + B < N) ? 2 : 1;
+    for (int g = 0; g < nGroups; ++g) {
+      const int set = host ? (g & 1) : 0;
+      const int nCur = std::min(nl, nb - g * nl);
       ChebState st[2];
-      for (int l = 0; l < nl; ++l) {
+      for (int l = 0; l < nCur; ++l) {
+        const int blkIdx = g * nl + l;
+        double *buf = bx[set][l];
         on_lane(l);
-        DB_TRY(launch_block_copy_from_full(ctx, X, N * cm, (j + l * B) * cm, bx[l], B * cm, ctx->M, inScale));
-        DB_TRY(ghost_zero(ctx, bx[l], B * cm, B * cm));
-        cheb_begin(st[l], bx[l], by[l], a, b, a0);
+        if (host) {
+          // the buffer is free once the block that used it two groups ago has been copied out
+          if (g >= 2) DB_CUDA(cudaStreamWaitEvent(ctx->copyIn, evOut[(g - 2) * nl + l], 0));
+          DB_CUDA(cudaMemcpy2DAsync(buf, rowBytes, Xh + (size_t)blkIdx * B * cm, pitchBytes, rowBytes, (size_t)ctx->M,
+                                    cudaMemcpyHostToDevice, ctx->copyIn));
+          DB_CUDA(cudaEventRecord(evIn[blkIdx], ctx->copyIn));
+          DB_CUDA(cudaStreamWaitEvent(ctx->stream, evIn[blkIdx], 0));
+          if (inScale) DB_TRY(launch_row_scale(ctx, buf, ctx->M, B * cm, B * cm, 1.0, inScale));
+        } else {
+          DB_TRY(launch_block_copy_from_full(ctx, Xd, N * cm, blkIdx * B * cm, buf, B * cm, ctx->M, inScale));
+        }
+        DB_TRY(ghost_zero(ctx, buf, B * cm, B * cm));
+        cheb_begin(st[l], buf, by[l], a, b, a0);
       }
       for (int degree = 1; degree <= m; ++degree)
-        for (int l = 0; l < nl; ++l) {
+        for (int l = 0; l < nCur; ++l) {
           on_lane(l);
           DB_TRY(cheb_step(ctx, st[l], B, m, mixedPrec));
         }
-      for (int l = 0; l < nl; ++l) {
+      for (int l = 0; l < nCur; ++l) {
+        const int blkIdx = g * nl + l;
+        double *buf = bx[set][l];
         on_lane(l);
-        DB_TRY(cheb_end(ctx, st[l], bx[l], B));
-        DB_TRY(launch_block_copy_to_full(ctx, X, N * cm, (j + l * B) * cm, bx[l], B * cm, ctx->M, nullptr));
+        DB_TRY(cheb_end(ctx, st[l], buf, B));
+        if (host) {
+          DB_CUDA(cudaEventRecord(evComp[blkIdx], ctx->stream));
+          DB_CUDA(cudaStreamWaitEvent(ctx->copyOut, evComp[blkIdx], 0));
+          DB_CUDA(cudaMemcpy2DAsync(Xh + (size_t)blkIdx * B * cm, pitchBytes, buf, rowBytes, rowBytes, (size_t)ctx->M,
+                                    cudaMemcpyDeviceToHost, ctx->copyOut));
+          DB_CUDA(cudaEventRecord(evOut[blkIdx], ctx->copyOut));
+        } else {
+          DB_TRY(launch_block_copy_to_full(ctx, Xd, N * cm, blkIdx * B * cm, buf, B * cm, ctx->M, nullptr));
+        }
       }
     }
     return 0;
   };
-  rc = body();
+  int rc = body();
   ctx->lane = 0;
   ctx->stream = mainStream;
-  if (rc != 0) return rc;
-  for (int l = 0; l < 2; ++l) {
-    DB_CUDA(cudaEventRecord(ctx->laneEvent[l], ctx->laneStream[l]));
-    DB_CUDA(cudaStreamWaitEvent(mainStream, ctx->laneEvent[l], 0));
+  if (rc == 0) {
+    for (int l = 0; l < nl && rc == 0; ++l) {
+      if (cudaEventRecord(ctx->laneEvent[l], ctx->laneStream[l]) != cudaSuccess ||
+          cudaStreamWaitEvent(mainStream, ctx->laneEvent[l], 0) != cudaSuccess)
+        rc = DFTFE_B200_ERR_CUDA;
+    }
+    if (host) {
+      // the call returns with the result in X_h: wait for every copy-out
+      for (int i = std::max(0, nb - 2 * nl); i < nb; ++i) cudaStreamWaitEvent(mainStream, evOut[i], 0);
+      if (cudaStreamSynchronize(mainStream) != cudaSuccess) rc = DFTFE_B200_ERR_CUDA;
+      if (rc == DFTFE_B200_ERR_CUDA) set_error("host-resident filter loop: stream synchronisation failed");
+    }
+  } else {
+    cudaDeviceSynchronize();
   }
-  return 0;
+  for (auto &v : {&evIn, &evComp, &evOut})
+    for (cudaEvent_t e : *v) cudaEventDestroy(e);
+  return rc;
 }
 
-// Same loop for a HOST-resident X (pinned memory recommended): block i+1 is copied
-// in and block i-1 copied out on two copy streams while block i is filtered on the
-// context stream, so PCIe traffic hides behind the cell kernels.
+static int filter_all_impl(dftfe_b200_ctx *ctx, double *X, int N, int m, double a, double b, double a0,
+                           const double *inScale, bool mixedPrec = false) {
+  return filter_blocks_impl(ctx, X, nullptr, N, m, a, b, a0, inScale, mixedPrec);
+}
+
 static int filter_all_host_impl(dftfe_b200_ctx *ctx, double *X_h, int N, int m, double a, double b, double a0,
                                 bool mixedPrec) {
-  const int B = std::min(ctx->B, N);
-  DB_CHECK(N % B == 0, "number of wavefunctions (%d) must be a multiple of the Chebyshev block size (%d)", N, B);
-  const int cm = ctx->cm;
-  const size_t blk = (size_t)(ctx->M + ctx->G) * B * cm;
-  DB_TRY(ctx->blockX.alloc(blk));
-  DB_TRY(ctx->blockX2.alloc(blk));
-  DB_TRY(ctx->blockY.alloc(blk));
-  if (!ctx->copyIn) {
-    DB_CUDA(cudaStreamCreateWithFlags(&ctx->copyIn, cudaStreamNonBlocking));
-    DB_CUDA(cudaStreamCreateWithFlags(&ctx->copyOut, cudaStreamNonBlocking));
-  }
-  const int nb = N / B;
-  std::vector<cudaEvent_t> evIn(nb), evComp(nb), evOut(nb);
-  for (int i = 0; i < nb; ++i) {
-    DB_CUDA(cudaEventCreateWithFlags(&evIn[i], cudaEventDisableTiming));
-    DB_CUDA(cudaEventCreateWithFlags(&evComp[i], cudaEventDisableTiming));
-    DB_CUDA(cudaEventCreateWithFlags(&evOut[i], cudaEventDisableTiming));
-  }
-  // the copy streams must not start before earlier work on the context stream is done
-  cudaEvent_t evStart;
-  DB_CUDA(cudaEventCreateWithFlags(&evStart, cudaEventDisableTiming));
-  DB_CUDA(cudaEventRecord(evStart, ctx->stream));
-  DB_CUDA(cudaStreamWaitEvent(ctx->copyIn, evStart, 0));
-  int rc = 0;
-  auto body = [&]() -> int {
-    for (int i = 0; i < nb; ++i) {
-      double *buf = (i & 1) ? ctx->blockX2.p : ctx->blockX.p;
-      if (i >= 2) DB_CUDA(cudaStreamWaitEvent(ctx->copyIn, evOut[i - 2], 0));  // buffer free again
-      DB_CUDA(cudaMemcpy2DAsync(buf, (size_t)B * cm * sizeof(double), X_h + (size_t)i * B * cm,
-                                (size_t)N * cm * sizeof(double), (size_t)B * cm * sizeof(double), (size_t)ctx->M,
-                                cudaMemcpyHostToDevice, ctx->copyIn));
-      DB_CUDA(cudaEventRecord(evIn[i], ctx->copyIn));
-      DB_CUDA(cudaStreamWaitEvent(ctx->stream, evIn[i], 0));
-      DB_TRY(ghost_zero(ctx, buf, B * cm, B * cm));
-      DB_TRY(cheb_filter_impl(ctx, buf, ctx->blockY.p, B, m, a, b, a0, mixedPrec));
-      DB_CUDA(cudaEventRecord(evComp[i], ctx->stream));
-      DB_CUDA(cudaStreamWaitEvent(ctx->copyOut, evComp[i], 0));
-      DB_CUDA(cudaMemcpy2DAsync(X_h + (size_t)i * B * cm, (size_t)N * cm * sizeof(double), buf,
-                                (size_t)B * cm * sizeof(double), (size_t)B * cm * sizeof(double), (size_t)ctx->M,
-                                cudaMemcpyDeviceToHost, ctx->copyOut));
-      DB_CUDA(cudaEventRecord(evOut[i], ctx->copyOut));
-    }
-    // the call returns with the result visible to work queued on the context stream
-    DB_CUDA(cudaStreamWaitEvent(ctx->stream, evOut[nb - 1], 0));
-    if (nb >= 2) DB_CUDA(cudaStreamWaitEvent(ctx->stream, evOut[nb - 2], 0));
-    DB_CUDA(cudaStreamSynchronize(ctx->stream));
-    return 0;
-  };
-  rc = body();
-  if (rc != 0) cudaDeviceSynchronize();
-  for (int i = 0; i < nb; ++i) {
-    cudaEventDestroy(evIn[i]);
-    cudaEventDestroy(evComp[i]);
-    cudaEventDestroy(evOut[i]);
-  }
-  cudaEventDestroy(evStart);
-  return rc;
+  return filter_blocks_impl(ctx, nullptr, X_h, N, m, a, b, a0, nullptr, mixedPrec);
 }
 
 static const unsigned int order_lookup[][2] = {{500, 24},     {750, 30},     {1000, 39},    {1500, 50},

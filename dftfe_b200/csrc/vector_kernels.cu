@@ -428,17 +428,95 @@ strided_copy_vec_kernel(const double *__restrict__ src, int lds, double *__restr
   }
 }
 
+// Streaming row mover, software pipelined: dst[r, :] = f(r) * src[map(r), :] for r < rows, one warp per row.
+// The next row's NCH 16-byte loads per lane are issued BEFORE the current row is stored, so a warp always has
+// a full row (ncols * 8 bytes) of loads in flight; a pure load-then-store loop leaves the memory system idle
+// during each warp's store phase and measured 3.4 TB/s, about half of the copy bandwidth.
+// Covers the block slices (K8), stridedBlockScale (K5, src == dst), the ghost pack (K14, row map) and the
+// ghost-segment fill.  NCH = ceil(ncols / 64) <= 8.
+template <int NCH>
+__global__ void __launch_bounds__(256)
+stream_rows_kernel(const double *src, int64_t lds, const uint32_t *__restrict__ srcRows, double *dst, int64_t ldd,
+                   int ncols, int64_t rows, const double *__restrict__ s, double alpha, int streaming) {
+  const WarpRows w;
+  const int c = w.lane * 2;
+  int64_t r = w.first;
+  if (r >= rows) return;
+  double2 v[NCH];
+  double f;
+  auto load = [&](int64_t row, double2(&out)[NCH], double &fac) {
+    const double *in = src + (srcRows ? (int64_t)srcRows[row] : row) * lds + c;
+#pragma unroll
+    for (int u = 0; u < NCH; ++u)
+      out[u] = (c + 64 * u < ncols) ? (streaming ? ld2_stream(in + 64 * u) : ld2(in + 64 * u)) : make_double2(0.0, 0.0);
+    fac = s ? alpha * s[row] : alpha;
+  };
+  load(r, v, f);
+  while (true) {
+    const int64_t rn = r + w.step;
+    double2 vn[NCH];
+    double fn = 1.0;
+    if (rn < rows) load(rn, vn, fn);
+    double *out = dst + r * ldd + c;
+#pragma unroll
+    for (int u = 0; u < NCH; ++u)
+      if (c + 64 * u < ncols) {
+        const double2 o = make_double2(v[u].x * f, v[u].y * f);
+        if (streaming)
+          st2_stream(out + 64 * u, o);
+        else
+          st2(out + 64 * u, o);
+      }
+    if (rn >= rows) break;
+#pragma unroll
+    for (int u = 0; u < NCH; ++u) v[u] = vn[u];
+    f = fn;
+    r = rn;
+  }
+}
+
 inline bool vec_ok(const void *p, int ncols, int ldx) {
   return (ncols % 2 == 0) && (ldx % 2 == 0) && ((reinterpret_cast<uintptr_t>(p) & 15) == 0);
 }
 
-// one warp per row, 8 warps per CTA, at most 8 CTAs per SM's worth of grid
-inline int grid_rows(const dftfe_b200_ctx *ctx, int64_t nRows) {
+// one warp per row, 8 warps per CTA; the grid is exactly one resident wave (SM count x the CTAs of THIS kernel
+// that fit on an SM), so that no CTA queues behind a full machine and leaves a half-empty second wave
+template <typename K>
+inline int grid_rows(dftfe_b200_ctx *ctx, K kernel, int64_t nRows) {
+  int &perSm = ctx->rowKernelCtasPerSm[reinterpret_cast<const void *>(kernel)];
+  if (perSm == 0) {
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, kernel, 256, 0) != cudaSuccess || perSm < 1) perSm = 4;
+  }
   int64_t g = (nRows + 7) / 8;
-  const int64_t cap = (int64_t)ctx->num_sms * 8;
+  const int64_t cap = (int64_t)ctx->num_sms * perSm;
   if (g > cap) g = cap;
   if (g < 1) g = 1;
   return (int)g;
+}
+
+// dst[r, 0:ncols] = alpha * s[r] * src[map(r), 0:ncols]; returns false when the shape needs the fallback kernels
+inline bool launch_stream_rows(dftfe_b200_ctx *ctx, const double *src, int64_t lds, const uint32_t *srcRows,
+                               double *dst, int64_t ldd, int ncols, int64_t rows, const double *s, double alpha,
+                               bool streaming) {
+  if (ctx->force_scalar_row_kernels || ncols > 512 || ncols % 2 || lds % 2 || ldd % 2 ||
+      (reinterpret_cast<uintptr_t>(src) & 15) || (reinterpret_cast<uintptr_t>(dst) & 15))
+    return false;
+  const int nch = (ncols + 63) / 64;
+  const int st = streaming ? 1 : 0;
+#define DB_STREAM(N)                                                                                      \
+  stream_rows_kernel<N><<<grid_rows(ctx, stream_rows_kernel<N>, rows), 256, 0, ctx->stream>>>(src, lds, srcRows, dst, \
+                                                                                             ldd, ncols, rows, s,   \
+                                                                                             alpha, st)
+  if (nch <= 1)
+    DB_STREAM(1);
+  else if (nch <= 2)
+    DB_STREAM(2);
+  else if (nch <= 4)
+    DB_STREAM(4);
+  else
+    DB_STREAM(8);
+#undef DB_STREAM
+  return true;
 }
 
 }  // namespace
@@ -447,7 +525,7 @@ int launch_distribute(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx, const 
   if (ctx->nCon == 0) return 0;
   ProfScope ps(ctx, "distribute");
   if (vec_ok(x, ncols, ldx) && !ctx->force_scalar_row_kernels)
-    distribute_vec_kernel<<<grid_rows(ctx, ctx->nCon), 256, 0, ctx->stream>>>(
+    distribute_vec_kernel<<<grid_rows(ctx, distribute_vec_kernel, ctx->nCon), 256, 0, ctx->stream>>>(
         x, ncols, ldx, ctx->nCon, ctx->conRows.p, ctx->conSizes.p, ctx->conStarts.p, ctx->conCols.p,
         ctx->conVals.p, ctx->conInhom.p, colScale);
   else
@@ -464,7 +542,7 @@ int launch_slave_to_master(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx, c
   const bool vec = vec_ok(x, ncols, ldx) && !ctx->force_scalar_row_kernels;
   if (ctx->nMasters > 0) {
     if (vec)
-      slave_to_master_vec_kernel<<<grid_rows(ctx, ctx->nMasters), 256, 0, ctx->stream>>>(
+      slave_to_master_vec_kernel<<<grid_rows(ctx, slave_to_master_vec_kernel, ctx->nMasters), 256, 0, ctx->stream>>>(
           x, ncols, ldx, ctx->nMasters, ctx->masterRows.p, ctx->masterStarts.p, ctx->masterSlaves.p,
           ctx->masterVals.p, masterScale);
     else
@@ -473,7 +551,7 @@ int launch_slave_to_master(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx, c
           ctx->masterVals.p, masterScale);
   }
   if (vec)
-    zero_rows_vec_kernel<<<grid_rows(ctx, ctx->nCon), 256, 0, ctx->stream>>>(x, ncols, ldx, ctx->nCon, ctx->conRows.p);
+    zero_rows_vec_kernel<<<grid_rows(ctx, zero_rows_vec_kernel, ctx->nCon), 256, 0, ctx->stream>>>(x, ncols, ldx, ctx->nCon, ctx->conRows.p);
   else
     zero_rows_kernel<<<grid_for(ctx, ctx->nCon * ncols), 256, 0, ctx->stream>>>(x, ncols, ldx, ctx->nCon,
                                                                                ctx->conRows.p);
@@ -485,7 +563,7 @@ int launch_set_zero_rows(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx) {
   if (ctx->nCon == 0) return 0;
   ProfScope ps(ctx, "set_zero");
   if (vec_ok(x, ncols, ldx) && !ctx->force_scalar_row_kernels)
-    zero_rows_vec_kernel<<<grid_rows(ctx, ctx->nCon), 256, 0, ctx->stream>>>(x, ncols, ldx, ctx->nCon, ctx->conRows.p);
+    zero_rows_vec_kernel<<<grid_rows(ctx, zero_rows_vec_kernel, ctx->nCon), 256, 0, ctx->stream>>>(x, ncols, ldx, ctx->nCon, ctx->conRows.p);
   else
     zero_rows_kernel<<<grid_for(ctx, ctx->nCon * ncols), 256, 0, ctx->stream>>>(x, ncols, ldx, ctx->nCon,
                                                                                ctx->conRows.p);
@@ -497,8 +575,9 @@ int launch_row_scale(dftfe_b200_ctx *ctx, double *x, int64_t rows, int ncols, in
                      const double *rowScale) {
   if (rows == 0) return 0;
   ProfScope ps(ctx, "row_scale");
-  if (vec_ok(x, ncols, ldx) && !ctx->force_scalar_row_kernels)
-    row_scale_vec_kernel<<<grid_rows(ctx, rows), 256, 0, ctx->stream>>>(x, rows, ncols, ldx, alpha, rowScale);
+  if (launch_stream_rows(ctx, x, ldx, nullptr, x, ldx, ncols, rows, rowScale, alpha, false)) {
+  } else if (vec_ok(x, ncols, ldx) && !ctx->force_scalar_row_kernels)
+    row_scale_vec_kernel<<<grid_rows(ctx, row_scale_vec_kernel, rows), 256, 0, ctx->stream>>>(x, rows, ncols, ldx, alpha, rowScale);
   else
     row_scale_kernel<<<grid_for(ctx, rows * ncols), 256, 0, ctx->stream>>>(x, rows, ncols, ldx, alpha, rowScale);
   DB_CUDA(cudaGetLastError());
@@ -509,8 +588,9 @@ int launch_block_copy_from_full(dftfe_b200_ctx *ctx, const double *X, int N, int
                                 int64_t rows, const double *rowScale) {
   if (rows == 0) return 0;
   ProfScope ps(ctx, "block_copy");
-  if (vec_ok(X + j0, ncols, N) && vec_ok(blk, ncols, ncols) && !ctx->force_scalar_row_kernels)
-    strided_copy_vec_kernel<<<grid_rows(ctx, rows), 256, 0, ctx->stream>>>(X + j0, N, blk, ncols, ncols, rows,
+  if (launch_stream_rows(ctx, X + j0, N, nullptr, blk, ncols, ncols, rows, rowScale, 1.0, true)) {
+  } else if (vec_ok(X + j0, ncols, N) && vec_ok(blk, ncols, ncols) && !ctx->force_scalar_row_kernels)
+    strided_copy_vec_kernel<<<grid_rows(ctx, strided_copy_vec_kernel, rows), 256, 0, ctx->stream>>>(X + j0, N, blk, ncols, ncols, rows,
                                                                           rowScale);
   else
     block_from_full_kernel<<<grid_for(ctx, rows * ncols), 256, 0, ctx->stream>>>(X, N, j0, blk, ncols, rows,
@@ -523,8 +603,9 @@ int launch_block_copy_to_full(dftfe_b200_ctx *ctx, double *X, int N, int j0, con
                               int64_t rows, const double *rowScale) {
   if (rows == 0) return 0;
   ProfScope ps(ctx, "block_copy");
-  if (vec_ok(X + j0, ncols, N) && vec_ok(blk, ncols, ncols) && !ctx->force_scalar_row_kernels)
-    strided_copy_vec_kernel<<<grid_rows(ctx, rows), 256, 0, ctx->stream>>>(blk, ncols, X + j0, N, ncols, rows,
+  if (launch_stream_rows(ctx, blk, ncols, nullptr, X + j0, N, ncols, rows, rowScale, 1.0, true)) {
+  } else if (vec_ok(X + j0, ncols, N) && vec_ok(blk, ncols, ncols) && !ctx->force_scalar_row_kernels)
+    strided_copy_vec_kernel<<<grid_rows(ctx, strided_copy_vec_kernel, rows), 256, 0, ctx->stream>>>(blk, ncols, X + j0, N, ncols, rows,
                                                                           rowScale);
   else
     block_to_full_kernel<<<grid_for(ctx, rows * ncols), 256, 0, ctx->stream>>>(X, N, j0, blk, ncols, rows, rowScale);
@@ -538,8 +619,10 @@ int launch_pack_rows(dftfe_b200_ctx *ctx, const double *x, int ncols, int ldx, i
                      int64_t row0, double *buf) {
   if (nRows == 0) return 0;
   ProfScope ps(ctx, "ghost_pack");
-  if (vec_ok(x, ncols, ldx) && vec_ok(buf, ncols, ncols) && !ctx->force_scalar_row_kernels)
-    pack_rows_vec_kernel<double><<<grid_rows(ctx, nRows), 256, 0, ctx->stream>>>(x, ncols, ldx, nRows, rows, row0, buf);
+  if (launch_stream_rows(ctx, rows ? x : x + (size_t)row0 * ldx, ldx, rows, buf, ncols, ncols, nRows, nullptr, 1.0,
+                         false)) {
+  } else if (vec_ok(x, ncols, ldx) && vec_ok(buf, ncols, ncols) && !ctx->force_scalar_row_kernels)
+    pack_rows_vec_kernel<double><<<grid_rows(ctx, pack_rows_vec_kernel<double>, nRows), 256, 0, ctx->stream>>>(x, ncols, ldx, nRows, rows, row0, buf);
   else if (rows)
     pack_rows_kernel<<<grid_for(ctx, nRows * ncols), 256, 0, ctx->stream>>>(x, ncols, ldx, nRows, rows, buf);
   else
@@ -555,7 +638,7 @@ int launch_pack_rows_f32(dftfe_b200_ctx *ctx, const double *x, int ncols, int ld
   if (nRows == 0) return 0;
   DB_CHECK(vec_ok(x, ncols, ldx), "FP32 ghost payload needs an even column count and 16-byte aligned rows");
   ProfScope ps(ctx, "ghost_pack");
-  pack_rows_vec_kernel<float><<<grid_rows(ctx, nRows), 256, 0, ctx->stream>>>(x, ncols, ldx, nRows, rows, row0, buf);
+  pack_rows_vec_kernel<float><<<grid_rows(ctx, pack_rows_vec_kernel<float>, nRows), 256, 0, ctx->stream>>>(x, ncols, ldx, nRows, rows, row0, buf);
   DB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -564,8 +647,9 @@ int launch_unpack_rows(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx, int64
                        const double *buf) {
   if (nRows == 0) return 0;
   ProfScope ps(ctx, "ghost_unpack");
-  if (vec_ok(x, ncols, ldx) && vec_ok(buf, ncols, ncols) && !ctx->force_scalar_row_kernels)
-    unpack_rows_vec_kernel<double><<<grid_rows(ctx, nRows), 256, 0, ctx->stream>>>(x, ncols, ldx, row0, nRows, buf);
+  if (launch_stream_rows(ctx, buf, ncols, nullptr, x + (size_t)row0 * ldx, ldx, ncols, nRows, nullptr, 1.0, false)) {
+  } else if (vec_ok(x, ncols, ldx) && vec_ok(buf, ncols, ncols) && !ctx->force_scalar_row_kernels)
+    unpack_rows_vec_kernel<double><<<grid_rows(ctx, unpack_rows_vec_kernel<double>, nRows), 256, 0, ctx->stream>>>(x, ncols, ldx, row0, nRows, buf);
   else
     copy_rows_kernel<<<grid_for(ctx, nRows * ncols), 256, 0, ctx->stream>>>(x, ncols, ldx, row0, nRows,
                                                                            const_cast<double *>(buf), 0);
@@ -577,7 +661,7 @@ int launch_unpack_rows_f32(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx, i
                            const float *buf) {
   if (nRows == 0) return 0;
   ProfScope ps(ctx, "ghost_unpack");
-  unpack_rows_vec_kernel<float><<<grid_rows(ctx, nRows), 256, 0, ctx->stream>>>(x, ncols, ldx, row0, nRows, buf);
+  unpack_rows_vec_kernel<float><<<grid_rows(ctx, unpack_rows_vec_kernel<float>, nRows), 256, 0, ctx->stream>>>(x, ncols, ldx, row0, nRows, buf);
   DB_CUDA(cudaGetLastError());
   return 0;
 }
@@ -587,7 +671,7 @@ int launch_unpack_add(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx, const 
   if (ctx->nBoundaryRows == 0) return 0;
   ProfScope ps(ctx, "ghost_unpack");
   if (vec_ok(x, ncols, ldx) && vec_ok(buf, ncols, ncols) && !ctx->force_scalar_row_kernels)
-    unpack_add_vec_kernel<double><<<grid_rows(ctx, ctx->nBoundaryRows), 256, 0, ctx->stream>>>(
+    unpack_add_vec_kernel<double><<<grid_rows(ctx, unpack_add_vec_kernel<double>, ctx->nBoundaryRows), 256, 0, ctx->stream>>>(
         x, ncols, ldx, ctx->nBoundaryRows, ctx->bndRows.p, ctx->bndStarts.p, ctx->bndSlots.p, buf, rowScale);
   else
     unpack_add_kernel<<<grid_for(ctx, ctx->nBoundaryRows * ncols), 256, 0, ctx->stream>>>(
@@ -600,7 +684,7 @@ int launch_unpack_add_f32(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx, co
                           const double *rowScale) {
   if (ctx->nBoundaryRows == 0) return 0;
   ProfScope ps(ctx, "ghost_unpack");
-  unpack_add_vec_kernel<float><<<grid_rows(ctx, ctx->nBoundaryRows), 256, 0, ctx->stream>>>(
+  unpack_add_vec_kernel<float><<<grid_rows(ctx, unpack_add_vec_kernel<float>, ctx->nBoundaryRows), 256, 0, ctx->stream>>>(
       x, ncols, ldx, ctx->nBoundaryRows, ctx->bndRows.p, ctx->bndStarts.p, ctx->bndSlots.p, buf, rowScale);
   DB_CUDA(cudaGetLastError());
   return 0;

@@ -220,14 +220,14 @@ int dftfe_b200_cheb_filter(dftfe_b200_ctx *ctx, double *x_d, double *y_d, int32_
 
 /* The blocked filter loop of solve() (solver .cc:376-526) over a device-resident X
  * (row-major M x N, Loewdin basis, N a multiple of B): every block of B columns is
- * sliced out, filtered and written back.  With more than one rank two blocks are in flight on two
- * streams so that one block's ghost exchange overlaps the other's cell kernels (the reference's
- * overlapComputeCommunCheby two-block filter, linearAlgebraOperationsDevice.cc:734-1443). */
+ * sliced out, filtered and written back.  Two blocks are in flight on two streams so that one block's
+ * ghost exchange (and the tail of each of its kernel launches) overlaps the other's cell kernels - the
+ * reference's overlapComputeCommunCheby two-block filter, linearAlgebraOperationsDevice.cc:734-1443. */
 int dftfe_b200_cheb_filter_all(dftfe_b200_ctx *ctx, double *X_d, int32_t N, int32_t m, double a, double b,
                                double a0, int32_t mixed_prec);
 /* Same for a HOST-resident X (pinned memory recommended).  Host->device and
- * device->host block copies run on two copy streams and overlap the filtering of
- * the neighbouring blocks.  Synchronous: X_h holds the result on return. */
+ * device->host block copies run on two copy streams under the kernels of the
+ * neighbouring block pairs.  Synchronous: X_h holds the result on return. */
 int dftfe_b200_cheb_filter_all_host(dftfe_b200_ctx *ctx, double *X_h, int32_t N, int32_t m, double a, double b,
                                     double a0, int32_t mixed_prec);
 
@@ -279,7 +279,7 @@ int dftfe_b200_get_spectrum_bounds(dftfe_b200_ctx *ctx, double out_h[3]);
 /* Options: "generic_cell_kernel" = 1 forces the non-persistent cell kernel (the path
  * taken anyway for ragged column counts, odd leading dimensions and FE order 7);
  * "scalar_row_kernels" = 1 forces the scalar fallbacks of the HBM-bound row kernels (odd column counts);
- * "overlap_lanes" = 0 / 1 / -1: two-block overlapped filter loop off / on / auto (on when nranks > 1);
+ * "overlap_lanes" = 0 / 1: one / two (default) wavefunction blocks in flight in the blocked filter loop;
  * "cublas_projections" = 1: cuBLAS Dgemm instead of the DMMA projection / rotation kernels (A/B). */
 int dftfe_b200_set_option(dftfe_b200_ctx *ctx, const char *name, int32_t value);
 /* Number of cell colours, and per-colour cell counts (n_out entries filled). */

@@ -227,6 +227,12 @@ def test_overlap_lanes_bit_identical(capi):
         op.sync()
         outs.append(Xd.cpu().numpy())
     assert np.array_equal(outs[0], outs[1])
+    # host-resident X: same arithmetic again, block copies pipelined under the lanes
+    for lanes in (0, 1):
+        op.set_option("overlap_lanes", lanes)
+        Xh = torch.from_numpy(X0.copy()).pin_memory()
+        op.chebyshevFilterAllHost(Xh, m, 5.0, 60.0, -2.0)
+        assert np.array_equal(Xh.numpy(), outs[0]), lanes
     op.close()
 
     nranks = 2

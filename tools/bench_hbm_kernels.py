@@ -25,8 +25,8 @@ def many_constraints(nrows, ncolsper=8, seed=5):
     def fn(mesh):
         rng = np.random.default_rng(seed)
         NX, NY, NZ = mesh.node_dims
-        # constrained rows on a sub-lattice (every 3rd interior node per axis), columns = nearby unconstrained nodes
-        ix, iy, iz = np.meshgrid(np.arange(3, NX - 3, 3), np.arange(3, NY - 3, 3), np.arange(3, NZ - 3, 3), indexing="ij")
+        # constrained rows on a sub-lattice (every 2nd interior node per axis), columns = nearby unconstrained nodes
+        ix, iy, iz = np.meshgrid(np.arange(4, NX - 4, 2), np.arange(4, NY - 4, 2), np.arange(4, NZ - 4, 2), indexing="ij")
         rows = (ix + NX * (iy + NY * iz)).ravel()
         rng.shuffle(rows)
         rows = rows[:nrows]
@@ -43,7 +43,7 @@ def many_constraints(nrows, ncolsper=8, seed=5):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cells", type=int, default=12)
-    ap.add_argument("--rows", type=int, default=12000)
+    ap.add_argument("--rows", type=int, default=36000)
     ap.add_argument("--block", type=int, default=256)
     ap.add_argument("--reps", type=int, default=20)
     args = ap.parse_args()
@@ -65,6 +65,7 @@ def main():
                       extra_constraints=many_constraints(args.rows))
     ranks = [mesh.rank_problem(r, potential=None, build_H=False, with_xyz=False) for r in range(nranks)]
     results = [None] * nranks
+    turn = threading.Barrier(nranks)
 
     def rank_fn(r):
         rp = ranks[r]
@@ -79,7 +80,21 @@ def main():
         nBnd = int(np.unique(rp.ownedLocalIdxForTargets).size)
         out = {}
 
-        def timed(name, slot, fn, nbytes, launches_per_call=1):
+        def timed(name, slot, fn, nbytes, launches_per_call=1, collective=False):
+            # rank-local kernels are measured one rank at a time (the ranks share ONE GPU here, concurrent
+            # launches would split the HBM bandwidth between them); collectives need every rank inside
+            if not collective:
+                for who in range(nranks):
+                    turn.wait()
+                    if who == r:
+                        _timed(name, slot, fn, nbytes, launches_per_call)
+                    torch.cuda.synchronize()
+                turn.wait()
+            else:
+                turn.wait()
+                _timed(name, slot, fn, nbytes, launches_per_call)
+
+        def _timed(name, slot, fn, nbytes, launches_per_call=1):
             for _ in range(3):
                 fn()
             op.sync()
@@ -97,8 +112,9 @@ def main():
         timed("slave_to_master+zero", "slave_to_master", lambda: op.distribute_slave_to_master(x),
               8.0 * B * (nnz + 2 * nMasters + nCon))
         timed("set_zero", "set_zero", lambda: op.set_zero(x), 8.0 * B * nCon)
-        timed("ghost_pack", "ghost_pack", lambda: op.update_ghost_values(x), 16.0 * B * nSend)
-        timed("ghost_unpack_add", "ghost_unpack", lambda: op.accumulate_add_locally_owned(x), 8.0 * B * (nSend + 2 * nBnd))
+        timed("ghost_pack", "ghost_pack", lambda: op.update_ghost_values(x), 16.0 * B * nSend, collective=True)
+        timed("ghost_unpack_add", "ghost_unpack", lambda: op.accumulate_add_locally_owned(x),
+              8.0 * B * (nSend + 2 * nBnd), collective=True)
         # block slice in / out of the full wavefunction matrix (K8) and the M^1/2 scaling (K5)
         N = 4 * B
         X = torch.rand((rp.M, N), dtype=torch.float64, device="cuda", generator=g)
@@ -106,6 +122,24 @@ def main():
         timed("strided_copy_to_block", "block_copy", lambda: op.stridedCopyToBlock(X, B, blk), 16.0 * B * rp.M)
         timed("strided_copy_from_block", "block_copy", lambda: op.stridedCopyFromBlock(X, 2 * B, blk), 16.0 * B * rp.M)
         timed("strided_block_scale", "row_scale", lambda: op.stridedBlockScale(blk, 1.0, 1), 16.0 * B * rp.M)
+        # calibration: the same 2 x 404 MB moved by torch's own copy kernel, timed the same way
+        turn.wait()
+        if r == 0:
+            dst = torch.empty_like(blk)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for _ in range(3):
+                dst.copy_(blk)
+            torch.cuda.synchronize()
+            e0.record()
+            for _ in range(args.reps):
+                dst.copy_(blk)
+            e1.record()
+            torch.cuda.synchronize()
+            per = e0.elapsed_time(e1) / args.reps
+            out["torch_copy_same_size"] = {"kernel": "torch_copy_same_size (calibration, not ours)", "ms": per,
+                                           "bytes": 16.0 * B * rp.M, "GBps": 16.0 * B * rp.M / (per * 1e-3) / 1e9}
+        torch.cuda.synchronize()
+        turn.wait()
         sz = {"nCon": nCon, "nnz": nnz, "nMasters": nMasters, "nSend": nSend, "nBoundaryRows": nBnd, "M": int(rp.M),
               "G": G}
         op.close()
