@@ -76,7 +76,7 @@ EXPORTED_SYMBOLS = [
     "dftfe_b200_nccl_unique_id", "dftfe_b200_comm_init", "dftfe_b200_comm_init_loopback",
     "dftfe_b200_set_nonlocal", "dftfe_b200_set_cell_hamiltonian", "dftfe_b200_set_cell_hamiltonian_host",
     "dftfe_b200_strided_copy_to_block", "dftfe_b200_strided_copy_from_block", "dftfe_b200_strided_block_scale",
-    "dftfe_b200_set_cell_hamiltonian_kpt", "dftfe_b200_reinit_kpoint_spin_index", "dftfe_b200_rotate_spectrum_split",
+    "dftfe_b200_set_cell_hamiltonian_kpt", "dftfe_b200_set_nonlocal_kpt", "dftfe_b200_reinit_kpoint_spin_index", "dftfe_b200_rotate_spectrum_split",
     "dftfe_b200_update_ghost_values", "dftfe_b200_accumulate_add_locally_owned", "dftfe_b200_zero_out_ghosts",
     "dftfe_b200_constraints_distribute", "dftfe_b200_constraints_distribute_slave_to_master",
     "dftfe_b200_constraints_set_zero", "dftfe_b200_hx", "dftfe_b200_hx_cheby", "dftfe_b200_cheb_filter",
@@ -199,12 +199,15 @@ class Operator:
         if nl is not None:
             self.set_nonlocal(nl)
 
-    def set_nonlocal(self, nl):
-        """NonLocalData (dftfe_b200.femesh) -> dftfe_b200_set_nonlocal."""
+    def set_nonlocal(self, nl, kPointIndex: int = 0):
+        """NonLocalData (dftfe_b200.femesh) -> dftfe_b200_set_nonlocal_kpt (complex C for a complex context)."""
         npj, V = _np(nl.nProjPerAtom, np.int32), _np(nl.V, np.float64)
-        ec, ea, Cm = _np(nl.entryCell, np.int32), _np(nl.entryAtom, np.int32), _np(nl.C, np.float64)
-        _check(self.lib.dftfe_b200_set_nonlocal(self.h, C.c_int32(nl.nAtoms), _ptr(npj), _ptr(V), C.c_int64(ec.size),
-                                                _ptr(ec), _ptr(ea), _ptr(Cm), C.c_int32(nl.pMax)))
+        assert np.iscomplexobj(nl.C) == self.complex, "projector dtype does not match the context"
+        ec, ea = _np(nl.entryCell, np.int32), _np(nl.entryAtom, np.int32)
+        Cm = _np(nl.C, np.complex128 if self.complex else np.float64)
+        _check(self.lib.dftfe_b200_set_nonlocal_kpt(self.h, C.c_int32(kPointIndex), C.c_int32(nl.nAtoms), _ptr(npj),
+                                                    _ptr(V), C.c_int64(ec.size), _ptr(ec), _ptr(ea), _ptr(Cm),
+                                                    C.c_int32(nl.pMax)))
 
     # ---- lifetime -------------------------------------------------------
     def close(self):
@@ -235,23 +238,25 @@ class Operator:
         _check(self.lib.dftfe_b200_comm_init_loopback(self.h, C.c_int32(group_id), C.c_int32(rank), C.c_int32(nranks)))
 
     # ---- Hamiltonian ------------------------------------------------------
-    def set_cell_hamiltonian(self, H, kptSpinIndex: int = 0):
+    def set_cell_hamiltonian(self, H, kPointIndex: int = 0, spinIndex: int = 0):
         """H: torch CUDA tensor or numpy array [nCells, n, n] (mem[c,I,J] = H_c(I,J)); stored as the
-        (k-point, spin) set ``kptSpinIndex`` and made active."""
+        (k-point, spin) set and made active."""
         if isinstance(H, np.ndarray):
             import torch
 
             assert np.iscomplexobj(H) == self.complex, "cell Hamiltonian dtype does not match the context"
             Hc = _np(H, np.complex128 if self.complex else np.float64)
-            if kptSpinIndex == 0:
+            if kPointIndex == 0 and spinIndex == 0:
                 _check(self.lib.dftfe_b200_set_cell_hamiltonian_host(self.h, _ptr(Hc)))
                 return
             H = torch.from_numpy(Hc).cuda(self.device)
-        _check(self.lib.dftfe_b200_set_cell_hamiltonian_kpt(self.h, C.c_int32(kptSpinIndex), _dptr(H)))
+        _check(self.lib.dftfe_b200_set_cell_hamiltonian_kpt(self.h, C.c_int32(kPointIndex), C.c_int32(spinIndex),
+                                                            _dptr(H)))
 
-    def reinitkPointSpinIndex(self, kptSpinIndex: int):
-        """kohnShamDFTOperatorDevice.cc:1033-1058: switch to a stored (k-point, spin) Hamiltonian set."""
-        _check(self.lib.dftfe_b200_reinit_kpoint_spin_index(self.h, C.c_int32(kptSpinIndex)))
+    def reinitkPointSpinIndex(self, kPointIndex: int, spinIndex: int = 0):
+        """kohnShamDFTOperatorDevice.cc:1033-1058: switch to a stored (k-point, spin) Hamiltonian set and to the
+        non-local projector set of that k-point."""
+        _check(self.lib.dftfe_b200_reinit_kpoint_spin_index(self.h, C.c_int32(kPointIndex), C.c_int32(spinIndex)))
 
     # ---- MultiVector / constraints ---------------------------------------
     def update_ghost_values(self, x):

@@ -229,15 +229,18 @@ struct dftfe_b200_ctx {
   double *Hactive = nullptr;
   dftfe_b200::DevBuf<double> Hstage;   // staging for host uploads
 
-  // --- non-local projectors (nonlocal.cu)
-  bool have_nonlocal = false;
-  int nlAtoms = 0, nlTotalProj = 0;
-  int64_t nlRows = 0;
-  dftfe_b200::DevBuf<int32_t> nlProjOffset, nlAtomRowStart, nlEntProj;
-  dftfe_b200::DevBuf<int64_t> nlAtomValStart, nlRowStart;
-  dftfe_b200::DevBuf<uint32_t> nlAtomRows, nlRowList;
-  dftfe_b200::DevBuf<double> nlV, nlVals, nlEntVal, nlProj;
-
+  // --- non-local projectors (nonlocal.cu): one set per k-point (the projector matrices carry the Bloch phase)
+  struct NonlocalSet {
+    int nAtoms = 0, totalProj = 0;
+    int64_t nRows = 0;
+    dftfe_b200::DevBuf<int32_t> projOffset, atomRowStart, entProj;
+    dftfe_b200::DevBuf<int64_t> atomValStart, rowStart;
+    dftfe_b200::DevBuf<uint32_t> atomRows, rowList;
+    dftfe_b200::DevBuf<double> V, vals, entVal;  // vals / entVal: (re, im) pairs in the complex build
+  };
+  std::map<int, NonlocalSet> nlSets;
+  NonlocalSet *nl = nullptr;  // active set (nullptr: no non-local term)
+  dftfe_b200::DevBuf<double> nlProj;  // projector block: totalProj x B (x 2 complex), all-reduced
   // --- solver state / scratch
   dftfe_b200::DevBuf<double> blockX, blockY;      // (M+G)*B
   dftfe_b200::DevBuf<double> blockX2;             // second block buffer (host-pipelined filter; lane 1)
@@ -322,8 +325,8 @@ int allreduce_sum(dftfe_b200_ctx *ctx, double *buf, size_t count);
 int allreduce_sum_f32(dftfe_b200_ctx *ctx, float *buf, size_t count);
 
 // nonlocal.cu
-int nonlocal_setup(dftfe_b200_ctx *ctx, int32_t nAtoms, const int32_t *nProj, const double *V, int64_t nEntries,
-                   const int32_t *entryCell, const int32_t *entryAtom, const double *C, int32_t pMax);
+int nonlocal_setup(dftfe_b200_ctx *ctx, int kpt, int32_t nAtoms, const int32_t *nProj, const double *V,
+                   int64_t nEntries, const int32_t *entryCell, const int32_t *entryAtom, const double *C, int32_t pMax);
 int nonlocal_project(dftfe_b200_ctx *ctx, const double *x, int ncols, int ldx, const double *rowScaleIn);
 int nonlocal_apply(dftfe_b200_ctx *ctx, double *y, int ncols, int ldx, const double *rowScaleOut, double s);
 

@@ -428,41 +428,61 @@ int dftfe_b200_comm_init_loopback(dftfe_b200_ctx *ctx, int32_t group_id, int32_t
   return loopback_join(ctx, group_id, rank, nranks);
 }
 
+int dftfe_b200_set_nonlocal_kpt(dftfe_b200_ctx *ctx, int32_t kpoint_index, int32_t n_atoms,
+                                const int32_t *n_proj_per_atom_h, const double *V_h, int64_t n_entries,
+                                const int32_t *entry_cell_h, const int32_t *entry_atom_h, const double *C_h,
+                                int32_t p_max) {
+  DB_CTX(ctx);
+  DB_CHECK(n_atoms >= 0 && n_entries >= 0 && p_max >= 0 && kpoint_index >= 0, "set_nonlocal: negative size / index");
+  return nonlocal_setup(ctx, kpoint_index, n_atoms, n_proj_per_atom_h, V_h, n_entries, entry_cell_h, entry_atom_h, C_h,
+                        p_max);
+}
+
 int dftfe_b200_set_nonlocal(dftfe_b200_ctx *ctx, int32_t n_atoms, const int32_t *n_proj_per_atom_h, const double *V_h,
                             int64_t n_entries, const int32_t *entry_cell_h, const int32_t *entry_atom_h,
                             const double *C_h, int32_t p_max) {
-  DB_CTX(ctx);
-  DB_CHECK(n_atoms >= 0 && n_entries >= 0 && p_max >= 0, "set_nonlocal: negative size");
-  if (ctx->cplx) {
-    set_error("set_nonlocal: complex (k-point dependent) projectors are not provided yet");
-    return DFTFE_B200_ERR_UNSUPPORTED;
-  }
-  return nonlocal_setup(ctx, n_atoms, n_proj_per_atom_h, V_h, n_entries, entry_cell_h, entry_atom_h, C_h, p_max);
+  return dftfe_b200_set_nonlocal_kpt(ctx, 0, n_atoms, n_proj_per_atom_h, V_h, n_entries, entry_cell_h, entry_atom_h,
+                                     C_h, p_max);
 }
 
-int dftfe_b200_set_cell_hamiltonian_kpt(dftfe_b200_ctx *ctx, int32_t kpt_spin_index, const double *H_d) {
+// flat key of a (k-point, spin) cell-Hamiltonian set
+static inline int hkey(int kpt, int spin) { return 2 * kpt + spin; }
+
+int dftfe_b200_set_cell_hamiltonian_kpt(dftfe_b200_ctx *ctx, int32_t kpoint_index, int32_t spin_index,
+                                        const double *H_d) {
   DB_CTX(ctx);
   DB_CHECK(H_d || ctx->nC == 0, "set_cell_hamiltonian: null pointer");
-  DB_CHECK(kpt_spin_index >= 0, "set_cell_hamiltonian: negative (k-point, spin) index");
+  DB_CHECK(kpoint_index >= 0 && (spin_index == 0 || spin_index == 1),
+           "set_cell_hamiltonian: bad (k-point, spin) index (%d, %d)", kpoint_index, spin_index);
   if (!ctx->have_H) ctx->Hsets.clear();  // constraints / mass changed: every stored set is stale
-  ctx->activeK = kpt_spin_index;
+  ctx->activeK = hkey(kpoint_index, spin_index);
   if (ctx->nC > 0) DB_TRY(retile_cell_hamiltonian(ctx, H_d));
   DB_CUDA(cudaStreamSynchronize(ctx->stream));  // caller's buffer is free after return
   ctx->have_H = true;
+  auto nl = ctx->nlSets.find(kpoint_index);
+  if (nl != ctx->nlSets.end()) ctx->nl = nl->second.totalProj > 0 ? &nl->second : nullptr;
   return 0;
 }
 
 int dftfe_b200_set_cell_hamiltonian(dftfe_b200_ctx *ctx, const double *H_d) {
-  return dftfe_b200_set_cell_hamiltonian_kpt(ctx, 0, H_d);
+  return dftfe_b200_set_cell_hamiltonian_kpt(ctx, 0, 0, H_d);
 }
 
-int dftfe_b200_reinit_kpoint_spin_index(dftfe_b200_ctx *ctx, int32_t kpt_spin_index) {
+int dftfe_b200_reinit_kpoint_spin_index(dftfe_b200_ctx *ctx, int32_t kpoint_index, int32_t spin_index) {
   DB_CTX(ctx);
-  auto it = ctx->Hsets.find(kpt_spin_index);
+  auto it = ctx->Hsets.find(hkey(kpoint_index, spin_index));
   DB_CHECK(ctx->have_H && it != ctx->Hsets.end() && (it->second.p || ctx->nC == 0),
-           "reinit_kpoint_spin_index: no cell Hamiltonian stored for index %d", kpt_spin_index);
-  ctx->activeK = kpt_spin_index;
+           "reinit_kpoint_spin_index: no cell Hamiltonian stored for (k-point %d, spin %d)", kpoint_index, spin_index);
+  ctx->activeK = it->first;
   ctx->Hactive = it->second.p;
+  // the projector matrices depend on the k-point only (h_d_B / h_d_C re-pointing, kohnShamDFTOperatorDevice.cc:1043-1056)
+  auto nl = ctx->nlSets.find(kpoint_index);
+  if (nl != ctx->nlSets.end())
+    ctx->nl = nl->second.totalProj > 0 ? &nl->second : nullptr;
+  else
+    DB_CHECK(ctx->nlSets.empty() || !ctx->cplx,
+             "reinit_kpoint_spin_index: non-local projectors were set for other k-points but not for k-point %d",
+             kpoint_index);
   return 0;
 }
 

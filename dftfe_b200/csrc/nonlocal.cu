@@ -16,6 +16,12 @@
 //   3. nl_apply_kernel   : y[row, :] += s * out(row) * sum_e Chat[row,e] V[e] proj[e, :]           (row-parallel)
 // Both are coalesced along the wavefunction index, atomics-free and deterministic; the projector block
 // (totalProj x B doubles) stays L2 resident between 1 and 3.
+//
+// Complex (k-point) build: C carries the Bloch phase, one set per k-point; vectors are interleaved (re, im) and
+//   proj = Chat^H x  (zgemm with d_nonLocalProjectorElementMatricesConjugate, ...MemoryOpt.cc:98-112),
+//   y   += Chat V proj  (zgemm with ...MatricesTranspose, :230-246),
+// computed on the interleaved real columns: a lane that holds the real (imaginary) part of a column also reads
+// its partner lane's value of the same row - the same 16-byte segment, so no extra memory traffic.
 #include <map>
 
 #include "common.cuh"
@@ -28,6 +34,9 @@ constexpr int NL_MAXP = 32;   // projectors per atom held in registers
 constexpr int NL_COLS = 64;   // columns per CTA
 constexpr int NL_RG = 2;      // row groups per CTA (static smem: RG*32*65*8 B)
 
+// cm = 1: vals[r][p] real.  cm = 2: vals[r][p] = (re, im); column `col` is the real part of a complex column when
+// even and the imaginary part when odd:  (conj(c) x)_re = cr xr + ci xi,  (conj(c) x)_im = cr xi - ci xr.
+template <int CM>
 __global__ void __launch_bounds__(NL_COLS *NL_RG)
 nl_project_kernel(const double *__restrict__ x, int ncols, int ldx, const int32_t *__restrict__ atomRowStart,
                   const uint32_t *__restrict__ atomRows, const int64_t *__restrict__ atomValStart,
@@ -39,7 +48,8 @@ nl_project_kernel(const double *__restrict__ x, int ncols, int ldx, const int32_
   const int rg = threadIdx.y;
   const int P = projOffset[a + 1] - projOffset[a];
   const int r0 = atomRowStart[a], r1 = atomRowStart[a + 1];
-  const double *va = vals + atomValStart[a];
+  const double *va = vals + atomValStart[a] * CM;
+  const double sgn = (col & 1) ? -1.0 : 1.0;
   double acc[NL_MAXP];
 #pragma unroll
   for (int p = 0; p < NL_MAXP; ++p) acc[p] = 0.0;
@@ -47,11 +57,21 @@ nl_project_kernel(const double *__restrict__ x, int ncols, int ldx, const int32_
     for (int r = r0 + rg; r < r1; r += NL_RG) {
       const uint32_t row = atomRows[r];
       double xv = x[(size_t)row * ldx + col];
-      if (rowScale) xv *= rowScale[row];
-      const double *v = va + (size_t)(r - r0) * P;
+      double xp = CM == 2 ? x[(size_t)row * ldx + (col ^ 1)] : 0.0;
+      if (rowScale) {
+        const double sc = rowScale[row];
+        xv *= sc;
+        xp *= sc;
+      }
+      const double *v = va + (size_t)(r - r0) * P * CM;
 #pragma unroll
       for (int p = 0; p < NL_MAXP; ++p)
-        if (p < P) acc[p] += v[p] * xv;
+        if (p < P) {
+          if (CM == 2)
+            acc[p] += v[2 * p] * xv + sgn * v[2 * p + 1] * xp;
+          else
+            acc[p] += v[p] * xv;
+        }
     }
   }
 #pragma unroll
@@ -67,6 +87,8 @@ nl_project_kernel(const double *__restrict__ x, int ncols, int ldx, const int32_
     }
 }
 
+// (c q)_re = cr qr - ci qi,  (c q)_im = cr qi + ci qr
+template <int CM>
 __global__ void nl_apply_kernel(double *__restrict__ y, int ncols, int ldx, int64_t nRows,
                                 const uint32_t *__restrict__ rows, const int64_t *__restrict__ rowStart,
                                 const int32_t *__restrict__ entProj, const double *__restrict__ entVal,
@@ -78,10 +100,15 @@ __global__ void nl_apply_kernel(double *__restrict__ y, int ncols, int ldx, int6
     const int64_t i = idx / ncols;
     const int c = idx % ncols;
     const uint32_t row = rows[i];
+    const double sgn = (c & 1) ? 1.0 : -1.0;
     double sum = 0.0;
     for (int64_t e = rowStart[i]; e < rowStart[i + 1]; ++e) {
       const int id = entProj[e];
-      sum += entVal[e] * V[id] * proj[(size_t)id * ncols + c];
+      if (CM == 2)
+        sum += V[id] * (entVal[2 * e] * proj[(size_t)id * ncols + c] +
+                        sgn * entVal[2 * e + 1] * proj[(size_t)id * ncols + (c ^ 1)]);
+      else
+        sum += entVal[e] * V[id] * proj[(size_t)id * ncols + c];
     }
     const double f = rowScale ? s * rowScale[row] : s;
     y[(size_t)row * ldx + c] += f * sum;
@@ -90,10 +117,11 @@ __global__ void nl_apply_kernel(double *__restrict__ y, int ncols, int ldx, int6
 
 }  // namespace
 
-int nonlocal_setup(dftfe_b200_ctx *ctx, int32_t nAtoms, const int32_t *nProj, const double *V, int64_t nEntries,
-                   const int32_t *entryCell, const int32_t *entryAtom, const double *C, int32_t pMax) {
+// C: [nEntries][n][pMax] doubles (real build) or (re, im) pairs (complex build)
+int nonlocal_setup(dftfe_b200_ctx *ctx, int kpt, int32_t nAtoms, const int32_t *nProj, const double *V,
+                   int64_t nEntries, const int32_t *entryCell, const int32_t *entryAtom, const double *C, int32_t pMax) {
   DB_CHECK(ctx->have_map, "set_nonlocal: set_index_map first");
-  const int n = ctx->n;
+  const int n = ctx->n, cm = ctx->cm;
   std::vector<int32_t> off(nAtoms + 1, 0);
   for (int a = 0; a < nAtoms; ++a) {
     DB_CHECK(nProj[a] >= 0 && nProj[a] <= NL_MAXP && nProj[a] <= pMax,
@@ -101,7 +129,7 @@ int nonlocal_setup(dftfe_b200_ctx *ctx, int32_t nAtoms, const int32_t *nProj, co
     off[a + 1] = off[a] + nProj[a];
   }
   const int totalProj = off[nAtoms];
-  // assemble Chat per atom: row -> P values
+  // assemble Chat per atom: row -> P (complex) values
   std::vector<std::map<uint32_t, std::vector<double>>> perAtom(nAtoms);
   for (int64_t e = 0; e < nEntries; ++e) {
     const int a = entryAtom[e];
@@ -111,16 +139,16 @@ int nonlocal_setup(dftfe_b200_ctx *ctx, int32_t nAtoms, const int32_t *nProj, co
     for (int i = 0; i < n; ++i) {
       const uint32_t row = ctx->cellRows_h[c * n + i];
       auto &v = perAtom[a][row];
-      if (v.empty()) v.assign(P, 0.0);
-      const double *src = C + ((size_t)e * n + i) * pMax;
-      for (int p = 0; p < P; ++p) v[p] += src[p];
+      if (v.empty()) v.assign((size_t)P * cm, 0.0);
+      const double *src = C + ((size_t)e * n + i) * pMax * cm;
+      for (int p = 0; p < P * cm; ++p) v[p] += src[p];
     }
   }
   std::vector<int32_t> atomRowStart(nAtoms + 1, 0);
   std::vector<int64_t> atomValStart(nAtoms + 1, 0);
   std::vector<uint32_t> atomRows;
   std::vector<double> vals;
-  std::map<uint32_t, std::vector<std::pair<int32_t, double>>> byRow;
+  std::map<uint32_t, std::vector<std::pair<int32_t, std::pair<double, double>>>> byRow;
   for (int a = 0; a < nAtoms; ++a) {
     const int P = nProj[a];
     for (auto &kv : perAtom[a]) {
@@ -129,11 +157,13 @@ int nonlocal_setup(dftfe_b200_ctx *ctx, int32_t nAtoms, const int32_t *nProj, co
       if (!nz) continue;
       atomRows.push_back(kv.first);
       vals.insert(vals.end(), kv.second.begin(), kv.second.end());
-      for (int p = 0; p < P; ++p)
-        if (kv.second[p] != 0.0) byRow[kv.first].push_back({off[a] + p, kv.second[p]});
+      for (int p = 0; p < P; ++p) {
+        const double re = kv.second[(size_t)p * cm], im = cm == 2 ? kv.second[(size_t)p * cm + 1] : 0.0;
+        if (re != 0.0 || im != 0.0) byRow[kv.first].push_back({off[a] + p, {re, im}});
+      }
     }
     atomRowStart[a + 1] = (int32_t)atomRows.size();
-    atomValStart[a + 1] = (int64_t)vals.size();
+    atomValStart[a + 1] = (int64_t)vals.size() / cm;
   }
   std::vector<uint32_t> rows;
   std::vector<int64_t> rowStart(1, 0);
@@ -143,51 +173,63 @@ int nonlocal_setup(dftfe_b200_ctx *ctx, int32_t nAtoms, const int32_t *nProj, co
     rows.push_back(kv.first);
     for (auto &pr : kv.second) {
       entProj.push_back(pr.first);
-      entVal.push_back(pr.second);
+      entVal.push_back(pr.second.first);
+      if (cm == 2) entVal.push_back(pr.second.second);
     }
     rowStart.push_back((int64_t)entProj.size());
   }
-  ctx->nlAtoms = nAtoms;
-  ctx->nlTotalProj = totalProj;
-  ctx->nlRows = (int64_t)rows.size();
-  DB_TRY(ctx->nlProjOffset.upload(off.data(), off.size(), ctx->stream));
-  DB_TRY(ctx->nlV.upload(V, totalProj, ctx->stream));
-  DB_TRY(ctx->nlAtomRowStart.upload(atomRowStart.data(), atomRowStart.size(), ctx->stream));
-  DB_TRY(ctx->nlAtomValStart.upload(atomValStart.data(), atomValStart.size(), ctx->stream));
-  DB_TRY(ctx->nlAtomRows.upload(atomRows.data(), atomRows.size(), ctx->stream));
-  DB_TRY(ctx->nlVals.upload(vals.data(), vals.size(), ctx->stream));
-  DB_TRY(ctx->nlRowList.upload(rows.data(), rows.size(), ctx->stream));
-  DB_TRY(ctx->nlRowStart.upload(rowStart.data(), rowStart.size(), ctx->stream));
-  DB_TRY(ctx->nlEntProj.upload(entProj.data(), entProj.size(), ctx->stream));
-  DB_TRY(ctx->nlEntVal.upload(entVal.data(), entVal.size(), ctx->stream));
-  DB_TRY(ctx->nlProj.alloc((size_t)std::max(totalProj, 1) * ctx->B));
-  ctx->have_nonlocal = totalProj > 0;
+  dftfe_b200_ctx::NonlocalSet &ns = ctx->nlSets[kpt];
+  ns.nAtoms = nAtoms;
+  ns.totalProj = totalProj;
+  ns.nRows = (int64_t)rows.size();
+  DB_TRY(ns.projOffset.upload(off.data(), off.size(), ctx->stream));
+  DB_TRY(ns.V.upload(V, totalProj, ctx->stream));
+  DB_TRY(ns.atomRowStart.upload(atomRowStart.data(), atomRowStart.size(), ctx->stream));
+  DB_TRY(ns.atomValStart.upload(atomValStart.data(), atomValStart.size(), ctx->stream));
+  DB_TRY(ns.atomRows.upload(atomRows.data(), atomRows.size(), ctx->stream));
+  DB_TRY(ns.vals.upload(vals.data(), vals.size(), ctx->stream));
+  DB_TRY(ns.rowList.upload(rows.data(), rows.size(), ctx->stream));
+  DB_TRY(ns.rowStart.upload(rowStart.data(), rowStart.size(), ctx->stream));
+  DB_TRY(ns.entProj.upload(entProj.data(), entProj.size(), ctx->stream));
+  DB_TRY(ns.entVal.upload(entVal.data(), entVal.size(), ctx->stream));
+  DB_TRY(ctx->nlProj.alloc((size_t)std::max(totalProj, 1) * ctx->B * cm));
+  ctx->nl = totalProj > 0 ? &ns : nullptr;
   return 0;
 }
 
-// proj = Chat^T (in o x), all-reduced over ranks
+// proj = Chat^H (in o x), all-reduced over ranks
 int nonlocal_project(dftfe_b200_ctx *ctx, const double *x, int ncols, int ldx, const double *rowScaleIn) {
-  if (!ctx->have_nonlocal) return 0;
+  if (!ctx->nl) return 0;
+  const dftfe_b200_ctx::NonlocalSet &ns = *ctx->nl;
   {
     ProfScope ps(ctx, "nonlocal");
-    dim3 grid(ctx->nlAtoms, (ncols + NL_COLS - 1) / NL_COLS), block(NL_COLS, NL_RG);
-    nl_project_kernel<<<grid, block, 0, ctx->stream>>>(x, ncols, ldx, ctx->nlAtomRowStart.p, ctx->nlAtomRows.p,
-                                                       ctx->nlAtomValStart.p, ctx->nlVals.p, ctx->nlProjOffset.p,
-                                                       rowScaleIn, ctx->nlProj.p);
+    dim3 grid(ns.nAtoms, (ncols + NL_COLS - 1) / NL_COLS), block(NL_COLS, NL_RG);
+    if (ctx->cplx)
+      nl_project_kernel<2><<<grid, block, 0, ctx->stream>>>(x, ncols, ldx, ns.atomRowStart.p, ns.atomRows.p,
+                                                            ns.atomValStart.p, ns.vals.p, ns.projOffset.p,
+                                                            rowScaleIn, ctx->nlProj.p);
+    else
+      nl_project_kernel<1><<<grid, block, 0, ctx->stream>>>(x, ncols, ldx, ns.atomRowStart.p, ns.atomRows.p,
+                                                            ns.atomValStart.p, ns.vals.p, ns.projOffset.p,
+                                                            rowScaleIn, ctx->nlProj.p);
     DB_CUDA(cudaGetLastError());
   }
-  return allreduce_sum(ctx, ctx->nlProj.p, (size_t)ctx->nlTotalProj * ncols);
+  return allreduce_sum(ctx, ctx->nlProj.p, (size_t)ns.totalProj * ncols);
 }
 
 // y += s * (out o Chat) V proj
 int nonlocal_apply(dftfe_b200_ctx *ctx, double *y, int ncols, int ldx, const double *rowScaleOut, double s) {
-  if (!ctx->have_nonlocal || ctx->nlRows == 0) return 0;
+  if (!ctx->nl || ctx->nl->nRows == 0) return 0;
+  const dftfe_b200_ctx::NonlocalSet &ns = *ctx->nl;
   ProfScope ps(ctx, "nonlocal");
-  const int64_t total = ctx->nlRows * ncols;
+  const int64_t total = ns.nRows * ncols;
   const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)ctx->num_sms * 16);
-  nl_apply_kernel<<<grid, 256, 0, ctx->stream>>>(y, ncols, ldx, ctx->nlRows, ctx->nlRowList.p, ctx->nlRowStart.p,
-                                                 ctx->nlEntProj.p, ctx->nlEntVal.p, ctx->nlV.p, ctx->nlProj.p,
-                                                 rowScaleOut, s);
+  if (ctx->cplx)
+    nl_apply_kernel<2><<<grid, 256, 0, ctx->stream>>>(y, ncols, ldx, ns.nRows, ns.rowList.p, ns.rowStart.p,
+                                                      ns.entProj.p, ns.entVal.p, ns.V.p, ctx->nlProj.p, rowScaleOut, s);
+  else
+    nl_apply_kernel<1><<<grid, 256, 0, ctx->stream>>>(y, ncols, ldx, ns.nRows, ns.rowList.p, ns.rowStart.p,
+                                                      ns.entProj.p, ns.entVal.p, ns.V.p, ctx->nlProj.p, rowScaleOut, s);
   DB_CUDA(cudaGetLastError());
   return 0;
 }

@@ -431,11 +431,13 @@ class GlobalMesh:
         )
 
     def nonlocal_data(self, rank: int, atoms_xyz: np.ndarray, n_proj: Sequence[int], rc: float = 2.0,
-                      seed: int = 77) -> NonLocalData:
+                      seed: int = 77, kpoint=None) -> NonLocalData:
         """Synthetic separable projectors: atom a carries n_proj[a] functions
         phi_p(r) = poly_p(r - R_a) * exp(-|r - R_a|^2 / (2 s^2)) cut off at rc (minimum image on periodic
         axes); C_c[i,p] = phi_p(x_i) * w_i (GLL quadrature, like the mass vector); couplings V in
-        [-1.5, 1.5] seeded."""
+        [-1.5, 1.5] seeded.  ``kpoint`` (complex build): every block carries the Bloch phase
+        exp(-i k.(x_i - R_a)) the reference folds into its k-point dependent projector matrices
+        (src/dft/initPseudo-OV.cc:560-700), C becomes complex128."""
         ref = self.ref
         cells = self.owned_cells(rank)
         nx, ny, nz = self.ncells
@@ -461,9 +463,11 @@ class GlobalMesh:
             dd = d[hit]
             polys = [np.ones_like(g), dd[..., 0], dd[..., 1], dd[..., 2], dd[..., 0] * dd[..., 1],
                      dd[..., 1] * dd[..., 2], dd[..., 0] * dd[..., 2], r2[hit] - 1.0]
-            blk = np.zeros((hit.size, ref.n, pmax))
+            blk = np.zeros((hit.size, ref.n, pmax), dtype=np.complex128 if kpoint is not None else np.float64)
             for p in range(int(n_proj[a])):
                 blk[:, :, p] = polys[p % len(polys)] * g * (1.0 + 0.25 * (p // len(polys)))
+            if kpoint is not None:
+                blk *= np.exp(-1j * (dd @ np.asarray(kpoint, dtype=np.float64)))[:, :, None]
             eCell.append(hit.astype(np.int32))
             eAtom.append(np.full(hit.size, a, dtype=np.int32))
             Cs.append(blk)
@@ -471,7 +475,7 @@ class GlobalMesh:
             return NonLocalData(len(atoms_xyz), n_proj, V, np.concatenate(eCell), np.concatenate(eAtom),
                                 np.concatenate(Cs), pmax)
         return NonLocalData(len(atoms_xyz), n_proj, V, np.zeros(0, np.int32), np.zeros(0, np.int32),
-                            np.zeros((0, ref.n, pmax)), pmax)
+                            np.zeros((0, ref.n, pmax), dtype=np.complex128 if kpoint is not None else np.float64), pmax)
 
     def cell_hamiltonians_kpoint(self, cells: np.ndarray, potential: Optional[Callable], kpoint,
                                  vquad: str = "gauss") -> np.ndarray:

@@ -73,16 +73,15 @@ class operatorDFTDeviceClass {
 
   // computeHamiltonianMatricesAllkpt output (kohnShamDFTOperatorDevice.cc:1060-3606): the flattened
   // d_cellHamiltonianMatrixFlattenedDevice holds nKptSpin sets of nC*n*n entries; hand each one over once per SCF
-  void setCellHamiltonian(const unsigned int kPointSpinIndex, const double *cellHamiltonianMatrixFlattenedDevice) {
-    check(dftfe_b200_set_cell_hamiltonian_kpt(d_ctx, (int32_t)kPointSpinIndex, cellHamiltonianMatrixFlattenedDevice),
+  void setCellHamiltonian(const unsigned int kPointIndex, const unsigned int spinIndex,
+                          const double *cellHamiltonianMatrixFlattenedDevice) {
+    check(dftfe_b200_set_cell_hamiltonian_kpt(d_ctx, (int32_t)kPointIndex, (int32_t)spinIndex,
+                                              cellHamiltonianMatrixFlattenedDevice),
           "set_cell_hamiltonian_kpt");
   }
-  // kohnShamDFTOperatorDevice.cc:1033-1058; the flat index is (1 + spinPolarized) * kPointIndex + spinIndex,
-  // the one the reference uses to address d_cellHamiltonianMatrixFlattenedDevice
-  void reinitkPointSpinIndex(const unsigned int kPointIndex, const unsigned int spinIndex,
-                             const unsigned int spinPolarized = 0) {
-    check(dftfe_b200_reinit_kpoint_spin_index(d_ctx, (int32_t)((1 + spinPolarized) * kPointIndex + spinIndex)),
-          "reinit_kpoint_spin_index");
+  // kohnShamDFTOperatorDevice.cc:1033-1058
+  void reinitkPointSpinIndex(const unsigned int kPointIndex, const unsigned int spinIndex) {
+    check(dftfe_b200_reinit_kpoint_spin_index(d_ctx, (int32_t)kPointIndex, (int32_t)spinIndex), "reinit_kpoint_spin_index");
   }
 
   // kohnShamDFTOperatorDevice.cc:3765-3860

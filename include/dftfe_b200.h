@@ -155,10 +155,18 @@ int dftfe_b200_comm_init_loopback(dftfe_b200_ctx *ctx, int32_t group_id, int32_t
  * n x p_max block C[e][i][p] = <N_i | phi_{atom,p}> (zero padded), the coupling constants V (atom-major)
  * and the projector count per (global) atom.  HX / HXCheby then add C V C^T x
  * (computeNonLocalHamiltonianTimesXMemoryOptBatchGEMMDevice.cc:27-283); the projector vector is summed
- * over ranks with an all-reduce.  At most 32 projectors per atom. */
+ * over ranks with an all-reduce.  At most 32 projectors per atom.
+ * Complex build: C_h holds (re, im) pairs and carries the Bloch phase of ONE k-point; HX adds C V C^H x
+ * (zgemm with the Conjugate / Transpose copies, computeNonLocalHamiltonianTimesXMemoryOpt.cc:98-112, 230-246).
+ * _kpt stores the set of k-point `kpoint_index` (reinit_kpoint_spin_index selects it); the plain call is
+ * k-point 0. */
 int dftfe_b200_set_nonlocal(dftfe_b200_ctx *ctx, int32_t n_atoms, const int32_t *n_proj_per_atom_h, const double *V_h,
                             int64_t n_entries, const int32_t *entry_cell_h, const int32_t *entry_atom_h,
                             const double *C_h, int32_t p_max);
+int dftfe_b200_set_nonlocal_kpt(dftfe_b200_ctx *ctx, int32_t kpoint_index, int32_t n_atoms,
+                                const int32_t *n_proj_per_atom_h, const double *V_h, int64_t n_entries,
+                                const int32_t *entry_cell_h, const int32_t *entry_atom_h, const double *C_h,
+                                int32_t p_max);
 
 /* Cell Hamiltonian for the active (k-point, spin): nC * n * n doubles,
  * mem[c*n*n + I*n + J] = H_c(I,J) as d_cellHamiltonianMatrixFlattenedDevice
@@ -168,13 +176,14 @@ int dftfe_b200_set_nonlocal(dftfe_b200_ctx *ctx, int32_t n_atoms, const int32_t 
 int dftfe_b200_set_cell_hamiltonian(dftfe_b200_ctx *ctx, const double *H_d);
 int dftfe_b200_set_cell_hamiltonian_host(dftfe_b200_ctx *ctx, const double *H_h);
 /* Several (k-point, spin) sets, the reference's [nSpinKpt][nC][n][n] storage
- * (computeHamiltonianMatricesAllkpt, kohnShamDFTOperatorDevice.cc:1060-3606): store the set `kpt_spin_index`
- * (and make it active); dftfe_b200_set_cell_hamiltonian == index 0.  Stored sets stay valid until
- * set_constraints / set_mass is called again. */
-int dftfe_b200_set_cell_hamiltonian_kpt(dftfe_b200_ctx *ctx, int32_t kpt_spin_index, const double *H_d);
-/* operatorDFTDeviceClass::reinitkPointSpinIndex (kohnShamDFTOperatorDevice.cc:1033-1058): switch the
- * operator to a stored set; no data moves. */
-int dftfe_b200_reinit_kpoint_spin_index(dftfe_b200_ctx *ctx, int32_t kpt_spin_index);
+ * (computeHamiltonianMatricesAllkpt, kohnShamDFTOperatorDevice.cc:1060-3606): store the set of
+ * (kpoint_index, spin_index in {0,1}) and make it active; dftfe_b200_set_cell_hamiltonian == (0, 0).
+ * Stored sets stay valid until set_constraints / set_mass is called again. */
+int dftfe_b200_set_cell_hamiltonian_kpt(dftfe_b200_ctx *ctx, int32_t kpoint_index, int32_t spin_index,
+                                        const double *H_d);
+/* operatorDFTDeviceClass::reinitkPointSpinIndex(kPointIndex, spinIndex) (kohnShamDFTOperatorDevice.cc:1033-1058):
+ * switch the operator to a stored Hamiltonian set and to the projector set of that k-point; no data moves. */
+int dftfe_b200_reinit_kpoint_spin_index(dftfe_b200_ctx *ctx, int32_t kpoint_index, int32_t spin_index);
 
 /* ---- distributed-vector primitives (MultiVector / MPICommunicatorP2P) ---- */
 int dftfe_b200_update_ghost_values(dftfe_b200_ctx *ctx, double *x_d, int32_t ncols);

@@ -162,11 +162,13 @@ def compute_local_hamiltonian_times_x(rp, src: np.ndarray, dst: np.ndarray, scal
 
 
 def compute_nonlocal_hamiltonian_times_x(ranks, src, dst, scalar: float = 1.0):
-    """src/dftOperator/computeNonLocalHamiltonianTimesXMemoryOpt.cc:266-505 (real): per owned cell and
-    atom, projKet[a] += C_c^T X_c (dgemm); the projector vector is summed over ranks
+    """src/dftOperator/computeNonLocalHamiltonianTimesXMemoryOpt.cc:266-505 (real) / :27-264 (complex): per
+    owned cell and atom, projKet[a] += C_c^H X_c (dgemm; complex: zgemm with
+    d_nonLocalProjectorElementMatricesConjugate, :98-112); the projector vector is summed over ranks
     (accumulateAddLocallyOwned + updateGhostValues on d_projectorKetTimesVectorParFlattened); scaled
-    by the coupling constants V; then per cell Y_c = C_c (V projKet[a]) is added into dst through the
-    index map.  No-op when the ranks carry no non-local data."""
+    by the coupling constants V; then per cell Y_c = C_c (V projKet[a]) (complex: zgemm with
+    ...MatricesTranspose, :230-246) is added into dst through the index map.  No-op when the ranks carry no
+    non-local data."""
     if getattr(ranks[0], "nonlocal_data", None) is None:
         return
     nl0 = ranks[0].nonlocal_data
@@ -179,7 +181,7 @@ def compute_nonlocal_hamiltonian_times_x(ranks, src, dst, scalar: float = 1.0):
             a = nl.entryAtom[e]
             P = nl.nProjPerAtom[a]
             Xc = s[rp.cellLocalDofs[nl.entryCell[e]]]
-            proj[off[a]:off[a] + P] += nl.C[e][:, :P].T @ Xc
+            proj[off[a]:off[a] + P] += nl.C[e][:, :P].conj().T @ Xc
     proj *= nl0.V[:, None]
     for rp, d in zip(ranks, dst):
         nl = rp.nonlocal_data

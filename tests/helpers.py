@@ -18,7 +18,7 @@ def make_problem(p, ncells, h=1.0, periodic=(True, True, True), nranks=1, vquad=
         atoms = rng.uniform(0.2, 0.8, size=(n_atoms, 3)) * np.asarray(mesh.box)
         nproj = [n_proj + (a % 3) for a in range(n_atoms)]
         for r, rp in enumerate(ranks):
-            rp.nonlocal_data = mesh.nonlocal_data(r, atoms, nproj, rc=rc)
+            rp.nonlocal_data = mesh.nonlocal_data(r, atoms, nproj, rc=rc, kpoint=kpoint)
     return mesh, ranks
 
 

@@ -41,7 +41,7 @@ int main(int argc, char **) {
     op.fillParallelOverlapMat(nullptr, 4u, m, true);
     op.chebyshevFilter(a, b, 4u, 10u, 1.0, 2.0, 0.0);
     op.chebyshevFilter(a, b, 4u, 10u, 1.0, 2.0, 0.0, true);
-    op.setCellHamiltonian(1u, nullptr);
+    op.setCellHamiltonian(1u, 0u, nullptr);
     op.reinitkPointSpinIndex(1u, 0u);
     dftfe_b200_solve_params p{};
     chebyshevOrthogonalizedSubspaceIterationSolverDevice s(0, 0, 0, p);

@@ -192,11 +192,11 @@ def test_kpoint_spin_hamiltonian_sets(capi):
     H0 = rp.H
     H1 = rp.H * 0.5 + 0.25 * np.transpose(rp.H, (0, 2, 1))  # a second, different symmetric set
     op = capi.Operator(rp, B)
-    op.set_cell_hamiltonian(H0, kptSpinIndex=0)
-    op.set_cell_hamiltonian(H1, kptSpinIndex=1)
+    op.set_cell_hamiltonian(H0, kPointIndex=0, spinIndex=0)
+    op.set_cell_hamiltonian(H1, kPointIndex=0, spinIndex=1)
     X = scatter_to_ranks(ranks, random_global(mesh, B, seed=2), loewdin=True)
     for idx, H in ((1, H1), (0, H0), (1, H1)):
-        op.reinitkPointSpinIndex(idx)
+        op.reinitkPointSpinIndex(0, idx)
         rp.H = H
         src = [x.copy() for x in X]
         dst = [np.zeros_like(x) for x in X]
@@ -206,7 +206,7 @@ def test_kpoint_spin_hamiltonian_sets(capi):
         assert _relerr(d_d.cpu().numpy()[:rp.M], dst[0][:rp.M]) < 1e-12, idx
     rp.H = H0
     with pytest.raises(capi.DftfeB200Error):
-        op.reinitkPointSpinIndex(7)
+        op.reinitkPointSpinIndex(7, 0)
     op.close()
 
 
@@ -300,3 +300,90 @@ def test_row_kernels_vector_and_scalar_paths_bit_identical(capi):
         assert np.array_equal(a_v, a_s) and np.array_equal(b_v, b_s)
         assert np.array_equal(a_v, ref[r])            # distribute: bit-exact against the oracle
         assert _relerr(b_v[:ranks[r].M], ref2[r][:ranks[r].M]) < 1e-14
+
+
+def test_complex_nonlocal_kpoints_and_spin_sets(capi):
+    """BASELINE config 5 in miniature: complex build, separable projectors with Bloch phases (C V C^H), two
+    k-points x two spins of cell Hamiltonians, switched with reinitkPointSpinIndex; multi-rank loopback."""
+    from oracle import chfsi_oracle as O
+
+    p, B, nranks = 3, 16, 2
+    kpts = [(0.21, -0.13, 0.34), (-0.4, 0.25, 0.1)]
+    probs = []
+    for k in kpts:
+        mesh, ranks = make_problem(p, (4, 2, 3), 1.2, (True, True, True), nranks=nranks, kpoint=k, n_atoms=3, rc=1.7)
+        probs.append((mesh, ranks))
+    mesh = probs[0][0]
+    assert np.iscomplexobj(probs[0][1][0].nonlocal_data.C)
+    Xg = random_global(mesh, B, seed=6, cplx=True)
+    # spin-down Hamiltonians: a different (still Hermitian) potential shift per cell
+    def spin_down(H):
+        return H + 0.05 * np.eye(H.shape[1])[None, :, :] * (1.0 + np.arange(H.shape[0]) % 3)[:, None, None]
+
+    refs = {}
+    for ik, (_, ranks) in enumerate(probs):
+        for spin in (0, 1):
+            Hs = [rp.H for rp in ranks]
+            if spin:
+                for rp in ranks:
+                    rp.H = spin_down(rp.H)
+            X = scatter_to_ranks(ranks, Xg, loewdin=True)
+            src = [x.copy() for x in X]
+            dst = [np.zeros_like(x) for x in X]
+            O.HX(ranks, src, dst, False, 1.0)
+            refs[(ik, spin)] = dst
+            for rp, h in zip(ranks, Hs):
+                rp.H = h
+
+    def rank_fn(r):
+        rp0 = probs[0][1][r]
+        op = capi.Operator(rp0, B, use_torch_stream=False, complex=True)   # registers k-point 0's projectors
+        op.comm_init_loopback(61, r, nranks)
+        op.set_nonlocal(probs[1][1][r].nonlocal_data, kPointIndex=1)
+        for ik, (_, ranks) in enumerate(probs):
+            op.set_cell_hamiltonian(ranks[r].H, kPointIndex=ik, spinIndex=0)
+            op.set_cell_hamiltonian(spin_down(ranks[r].H), kPointIndex=ik, spinIndex=1)
+        X = scatter_to_ranks(probs[0][1], Xg, loewdin=True)
+        errs = {}
+        for ik, spin in ((1, 0), (0, 1), (1, 1), (0, 0)):
+            op.reinitkPointSpinIndex(ik, spin)
+            s_d = _dev(X[r])
+            d_d = torch.zeros(rp0.M + rp0.G, B, dtype=torch.complex128, device="cuda")
+            op.HX(s_d, d_d, False, 1.0)
+            op.sync()
+            errs[(ik, spin)] = _relerr(d_d.cpu().numpy()[:rp0.M], refs[(ik, spin)][r][:rp0.M])
+        op.close()
+        return errs
+
+    for errs in _run_ranks(nranks, rank_fn):
+        for key, e in errs.items():
+            assert e < 1e-12, (key, e)
+    # the four operators really differ
+    a, b = refs[(0, 0)][0], refs[(1, 0)][0]
+    assert _relerr(a, b) > 1e-3
+
+
+def test_complex_spectrum_split(capi):
+    from oracle import chfsi_oracle as O
+
+    p, B, N, Noc = 2, 8, 24, 8
+    mesh, ranks = make_problem(p, (3, 3, 2), 1.3, (True, True, True), kpoint=(0.1, 0.2, -0.15))
+    rp = ranks[0]
+    op = capi.Operator(rp, B, complex=True)
+    op.set_cell_hamiltonian(rp.H)
+    solver = capi.ChebyshevSolver(op)
+    Xg = random_global(mesh, N, seed=3, cplx=True)
+    Xo = scatter_to_ranks(ranks, Xg, zero_constrained=False)
+    Xd = _dev(Xo[0][:rp.M])
+    XF = torch.zeros((rp.M, N - Noc), dtype=torch.complex128, device="cuda")
+    eig, res, ub = solver.solve(Xd, isFirstFilteringCall=True, chebyshevOrder=10, reuseLanczos=True, XFrac=XF)
+    a0, blow, bup = solver.spectrumBounds()
+    ev_ref, res_ref, XF_ref = O.solve(ranks, Xo, B, 10, (a0, blow, bup), n_core=Noc)
+    assert np.abs(eig - ev_ref).max() < 1e-8
+    assert np.abs(res - res_ref).max() < 1e-7
+    Xn = Xd.cpu().numpy() * rp.sqrtMass[:rp.M, None]
+    assert np.abs(Xn.conj().T @ Xn - np.eye(N)).max() < 1e-10
+    # XFrac spans the same subspace as the oracle's: projector difference
+    F, Fr = XF.cpu().numpy() * rp.sqrtMass[:rp.M, None], XF_ref[0][:rp.M] * rp.sqrtMass[:rp.M, None]
+    assert np.abs(F @ F.conj().T - Fr @ Fr.conj().T).max() < 1e-7
+    op.close()
