@@ -83,7 +83,7 @@ EXPORTED_SYMBOLS = [
     "dftfe_b200_cheb_filter_all", "dftfe_b200_cheb_filter_all_host",
     "dftfe_b200_xtx", "dftfe_b200_xthx", "dftfe_b200_rotate", "dftfe_b200_lanczos_bounds",
     "dftfe_b200_residual_norms", "dftfe_b200_reinit_spectrum_bounds", "dftfe_b200_solve",
-    "dftfe_b200_get_spectrum_bounds", "dftfe_b200_get_colouring", "dftfe_b200_set_option", "dftfe_b200_profile_enable",
+    "dftfe_b200_get_spectrum_bounds", "dftfe_b200_solve_no_rr", "dftfe_b200_get_colouring", "dftfe_b200_set_option", "dftfe_b200_profile_enable",
     "dftfe_b200_profile_get", "dftfe_b200_profile_reset", "dftfe_b200_launch_count",
 ]
 
@@ -394,6 +394,20 @@ class ChebyshevSolver:
         out = (C.c_double * 3)()
         _check(self.op.lib.dftfe_b200_get_spectrum_bounds(self.op.h, out))
         return out[0], out[1], out[2]
+
+    def solveNoRR(self, X, numberPasses: int, chebyshevOrder: int = 0, isPseudopotential: bool = True,
+                  reuseLanczos: bool = True, firstScfScaling: float = 1.34, useMixedPrecOverall: bool = False,
+                  mixedPrec: Sequence[str] = ()):
+        """solver .cc:742-1071: numberPasses x (filter + CGS).  Returns the upper bound used."""
+        mp = set(mixedPrec)
+        p = SolveParams(chebyshev_order=chebyshevOrder, reuse_lanczos_upper_bound=int(reuseLanczos),
+                        is_pseudopotential=int(isPseudopotential), use_mixed_prec_overall=int(useMixedPrecOverall),
+                        use_mixed_prec_cheby=int("cheby" in mp), use_mixed_prec_cgs_o=int("cgs_o" in mp),
+                        use_mixed_prec_cgs_sr=int("cgs_sr" in mp), first_scf_scaling=firstScfScaling)
+        ub = C.c_double()
+        _check(self.op.lib.dftfe_b200_solve_no_rr(self.op.h, _dptr(X), C.c_int32(X.shape[1]), C.byref(p),
+                                                  C.c_int32(numberPasses), C.byref(ub)))
+        return ub.value
 
     def solve(self, X, isFirstFilteringCall: bool, computeResidual: bool = True, chebyshevOrder: int = 0,
               isFirstScf: bool = False, isPseudopotential: bool = True, useCgsRR: bool = False,

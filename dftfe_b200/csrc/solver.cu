@@ -1035,6 +1035,61 @@ static int solve_impl(dftfe_b200_ctx *ctx, double *X, double *XFrac, int N, cons
   return 0;
 }
 
+// chebyshevOrthogonalizedSubspaceIterationSolverDevice::solveNoRR (solver .cc:742-1071): numberPasses x
+// (filter every block, Cholesky-Gram-Schmidt), no Rayleigh-Ritz step, no eigenvalues.
+static int solve_no_rr_impl(dftfe_b200_ctx *ctx, double *X, int N, const dftfe_b200_solve_params *p, int numberPasses,
+                            double *upper_h) {
+  const int B = std::min(ctx->B, N);
+  DB_CHECK(N % B == 0, "number of wavefunctions (%d) must be a multiple of the Chebyshev block size (%d)", N, B);
+  DB_CHECK(numberPasses >= 1, "solveNoRR: numberPasses must be >= 1");
+  DB_CHECK(ctx->bounds_valid, "solveNoRR: spectrum bounds are not set (call solve() with is_first_filtering_call "
+                              "or reinit_spectrum_bounds + lanczos first)");
+  DB_TRY(ensure_block_scratch(ctx));
+  if (!p->reuse_lanczos_upper_bound) {  // :813-826
+    double bounds[2];
+    DB_TRY(lanczos_impl(ctx, p->reproducible_output, bounds));
+    ctx->bUp = bounds[1];
+  }
+  unsigned int order = p->chebyshev_order;
+  if (order == 0) order = set_chebyshev_order(ctx->bUp);
+  if (p->is_pseudopotential) order = (unsigned int)(order * p->first_scf_scaling);  // :836-840, unconditional here
+  if (order < 1) order = 1;
+  const bool mp = p->use_mixed_prec_overall != 0;
+  RRFlags f;
+  f.mpOverlap = mp && p->use_mixed_prec_cgs_o;
+  f.mpCgsRot = mp && p->use_mixed_prec_cgs_sr;
+  DB_TRY(launch_row_scale(ctx, X, ctx->M, N * ctx->cm, N * ctx->cm, 1.0, ctx->sqrtM.p));
+  for (int ipass = 0; ipass < numberPasses; ++ipass) {
+    DB_TRY(filter_all_impl(ctx, X, N, (int)order, ctx->bLow, ctx->bUp, ctx->a0, nullptr, mp && p->use_mixed_prec_cheby));
+    if (ctx->cplx) {
+      // complex CGS: S = X^H X = L L^H, X <- X L^-H
+      const size_t nn = (size_t)N * N * 2;
+      DB_TRY(ctx->denseA.alloc(nn));
+      DB_TRY(ctx->denseB.alloc(nn));
+      cuDoubleComplex *Sz = reinterpret_cast<cuDoubleComplex *>(ctx->denseA.p);
+      cuDoubleComplex *Uz = reinterpret_cast<cuDoubleComplex *>(ctx->denseB.p);
+      const cuDoubleComplex one = make_cuDoubleComplex(1.0, 0.0);
+      DB_TRY(xtx_impl(ctx, X, N, ctx->denseA.p));
+      DB_TRY(dense_cholesky_cplx(ctx, ctx->denseA.p, N));
+      std::vector<double> eye(nn, 0.0);
+      for (int i = 0; i < N; ++i) eye[((size_t)i * N + i) * 2] = 1.0;
+      DB_CUDA(cudaMemcpyAsync(ctx->denseB.p, eye.data(), nn * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+      DB_CUDA(cudaStreamSynchronize(ctx->stream));
+      DB_CUBLAS(cublasSetStream(ctx->cublas, ctx->stream));
+      ctx->launches += 1;
+      DB_CUBLAS(cublasZtrsm(ctx->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_C, CUBLAS_DIAG_NON_UNIT, N,
+                            N, &one, Sz, N, Uz, N));
+      DB_TRY(rotate_impl(ctx, X, N, ctx->denseB.p, true));
+    } else {
+      DB_TRY(cgs_orthogonalise(ctx, X, N, f));
+    }
+  }
+  DB_TRY(launch_row_scale(ctx, X, ctx->M, N * ctx->cm, N * ctx->cm, 1.0, ctx->invSqrtM.p));
+  if (upper_h) *upper_h = ctx->bUp;
+  DB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
 }  // namespace dftfe_b200
 
 // ===========================================================================
@@ -1155,7 +1210,14 @@ int dftfe_b200_reinit_spectrum_bounds(dftfe_b200_ctx *ctx, double lower_wanted, 
   DB_CTX(ctx);
   ctx->a0 = lower_wanted;
   ctx->bLow = lower_unwanted;
-  return 0;
+  return 0;  // bounds_valid still needs an upper bound: the first solve() / lanczos call provides it
+}
+
+int dftfe_b200_solve_no_rr(dftfe_b200_ctx *ctx, double *X_d, int32_t N, const dftfe_b200_solve_params *params,
+                           int32_t number_passes, double *upper_bound_out_h) {
+  DB_CTX(ctx);
+  DB_CHECK(params, "solve_no_rr: params are required");
+  return solve_no_rr_impl(ctx, X_d, N, params, number_passes, upper_bound_out_h);
 }
 
 int dftfe_b200_get_spectrum_bounds(dftfe_b200_ctx *ctx, double out_h[3]) {

@@ -231,6 +231,20 @@ class chebyshevOrthogonalizedSubspaceIterationSolverDevice {
     return d_upperUnwanted;
   }
 
+  // solveNoRR(operatorMatrix, BLASWrapperPtr, elpaScala, eigenVectorsFlattenedDevice, flattenedSize,
+  //           totalNumberWaveFunctions, eigenValues, devicecclMpiCommDomain, interBandGroupComm, numberPasses,
+  //           useMixedPrecOverall)  (:742-1071)
+  void solveNoRR(operatorDFTDeviceClass &operatorMatrix, double *eigenVectorsFlattenedDevice,
+                 const unsigned int /*flattenedSize*/, const unsigned int totalNumberWaveFunctions,
+                 std::vector<double> & /*eigenValues*/, const unsigned int numberPasses,
+                 const bool useMixedPrecOverall) {
+    dftfe_b200_solve_params p = d_params;
+    p.use_mixed_prec_overall = useMixedPrecOverall ? 1 : 0;
+    check(dftfe_b200_solve_no_rr(operatorMatrix.context(), eigenVectorsFlattenedDevice, (int32_t)totalNumberWaveFunctions,
+                                 &p, (int32_t)numberPasses, &d_upperUnwanted),
+          "solveNoRR");
+  }
+
  private:
   double d_lowerWanted, d_lowerUnwanted, d_upperUnwanted;
   dftfe_b200_solve_params d_params;

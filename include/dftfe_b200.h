@@ -281,6 +281,11 @@ int dftfe_b200_reinit_spectrum_bounds(dftfe_b200_ctx *ctx, double lower_wanted, 
 int dftfe_b200_solve(dftfe_b200_ctx *ctx, double *X_d, double *X_frac_d, int32_t N,
                      const dftfe_b200_solve_params *params, double *eig_out_h, double *res_out_h,
                      double *upper_bound_out_h);
+/* chebyshevOrthogonalizedSubspaceIterationSolverDevice::solveNoRR (solver .cc:742-1071): number_passes x
+ * (filter every block, Cholesky-Gram-Schmidt orthonormalisation); no Rayleigh-Ritz, no eigenvalues.  Needs the
+ * bounds of an earlier solve() (the reference calls it after the first SCF's solve). */
+int dftfe_b200_solve_no_rr(dftfe_b200_ctx *ctx, double *X_d, int32_t N, const dftfe_b200_solve_params *params,
+                           int32_t number_passes, double *upper_bound_out_h);
 /* bounds currently held by the solver object: {a0, bLow, bUp}. */
 int dftfe_b200_get_spectrum_bounds(dftfe_b200_ctx *ctx, double out_h[3]);
 

@@ -718,3 +718,23 @@ def solve(ranks, X, block: int, cheb_order: int, bounds, use_gep: bool = True,
             x[:rp.M] *= rp.invSqrtMass[:rp.M][:, None]
         return evals, res, XFrac
     return evals, res
+
+
+def solve_no_rr(ranks, X, block: int, cheb_order: int, bounds, number_passes: int):
+    """chebyshevOrthogonalizedSubspaceIterationSolverDevice::solveNoRR
+    (src/solvers/eigenSolvers/chebyshevOrthogonalizedSubspaceIterationSolverDevice.cc:742-1071):
+    X <- M^1/2 X; number_passes x (filter every block; pseudoGramSchmidtOrthogonalization); X <- M^-1/2 X."""
+    a0, blow, bup = bounds
+    N = X[0].shape[1]
+    for rp, x in zip(ranks, X):
+        x[:rp.M] *= rp.sqrtMass[:rp.M][:, None]
+    for _ in range(number_passes):
+        for j in range(0, N, block):
+            Xb = [x[:, j:j + block].copy() for x in X]
+            zero_out_ghosts(ranks, Xb)
+            chebyshev_filter_inplace(ranks, Xb, cheb_order, blow, bup, a0)
+            for x, xb in zip(X, Xb):
+                x[:, j:j + block] = xb
+        cholesky_gram_schmidt(ranks, X)
+    for rp, x in zip(ranks, X):
+        x[:rp.M] *= rp.invSqrtMass[:rp.M][:, None]

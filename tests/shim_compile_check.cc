@@ -47,6 +47,7 @@ int main(int argc, char **) {
     chebyshevOrthogonalizedSubspaceIterationSolverDevice s(0, 0, 0, p);
     std::vector<double> ev(4), res;
     s.solve(op, nullptr, nullptr, 0u, 4u, ev, res, true, true);
+    s.solveNoRR(op, nullptr, 0u, 4u, ev, 2u, false);
     std::vector<double> evFrac(2);
     s.solve(op, nullptr, nullptr, 0u, 4u, evFrac, res, false, true, true);  // spectrum splitting + mixed precision
   }

@@ -387,3 +387,30 @@ def test_complex_spectrum_split(capi):
     F, Fr = XF.cpu().numpy() * rp.sqrtMass[:rp.M, None], XF_ref[0][:rp.M] * rp.sqrtMass[:rp.M, None]
     assert np.abs(F @ F.conj().T - Fr @ Fr.conj().T).max() < 1e-7
     op.close()
+
+
+def test_solve_no_rr(capi):
+    """solveNoRR: two passes of filter + Cholesky-Gram-Schmidt; the result is a deterministic function of the
+    input (triangular orthonormalisation), so the vectors themselves are compared."""
+    from oracle import chfsi_oracle as O
+
+    p, B, N = 3, 16, 32
+    mesh, ranks = make_problem(p, (3, 3, 3), 1.5, (True, True, True))
+    rp = ranks[0]
+    op = capi.Operator(rp, B)
+    op.set_cell_hamiltonian(rp.H)
+    solver = capi.ChebyshevSolver(op)
+    Xg = random_global(mesh, N, seed=7)
+    Xo = scatter_to_ranks(ranks, Xg, zero_constrained=False)
+    Xd = _dev(Xo[0][:rp.M])
+    eig, res, ub = solver.solve(Xd, isFirstFilteringCall=True, chebyshevOrder=8, reuseLanczos=True)
+    bounds = solver.spectrumBounds()
+    O.solve(ranks, Xo, B, 8, bounds)
+    solver.solveNoRR(Xd, 2, chebyshevOrder=6, isPseudopotential=False)
+    O.solve_no_rr(ranks, Xo, B, 6, bounds, 2)
+    got, ref = Xd.cpu().numpy(), Xo[0][:rp.M]
+    Xn = got * rp.sqrtMass[:rp.M, None]
+    assert np.abs(Xn.T @ Xn - np.eye(N)).max() < 1e-11
+    # same subspace, same vectors up to the conditioning of the Gram matrix
+    assert np.abs(got @ (got.T * rp.sqrtMass[:rp.M] ** 2) - ref @ (ref.T * rp.sqrtMass[:rp.M] ** 2)).max() < 1e-7
+    op.close()
