@@ -309,6 +309,14 @@ class GlobalMesh:
                + NX * (iy[:, None, :, None] + NY * iz[:, :, None, None]))
         return nat.reshape(len(cells), n1 ** 3)
 
+    def cell_origin_scale(self, cells: np.ndarray):
+        """(origin[nc, 3], scale[nc]) of the given cells: physical corner and edge length relative to ``ref.h``
+        (1 on the structured mesh; the adaptive mesh of femesh_adaptive.py overrides this)."""
+        nx, ny, nz = self.ncells
+        cells = np.asarray(cells, dtype=np.int64)
+        origin = np.stack([(cells % nx), (cells // nx) % ny, cells // (nx * ny)], axis=1) * self.h
+        return origin.astype(np.float64), np.ones(cells.size)
+
     # ---- partition helpers ------------------------------------------------
     def _con_lookup(self, gset: np.ndarray) -> np.ndarray:
         """positions in conRows of those members of gset that are constrained."""
@@ -440,9 +448,9 @@ class GlobalMesh:
         (src/dft/initPseudo-OV.cc:560-700), C becomes complex128."""
         ref = self.ref
         cells = self.owned_cells(rank)
-        nx, ny, nz = self.ncells
-        origin = np.stack([(cells % nx), (cells // nx) % ny, cells // (nx * ny)], axis=1) * self.h
-        xyz = origin[:, None, :] + ref.node_xyz[None, :, :]             # (nc, n, 3)
+        origin, scale = self.cell_origin_scale(cells)
+        xyz = origin[:, None, :] + scale[:, None, None] * ref.node_xyz[None, :, :]   # (nc, n, 3)
+        wnode = (scale ** 3)[:, None] * ref.mass_gll[None, :]                        # GLL weights per cell
         box = np.asarray(self.box)
         per = np.asarray(self.periodic)
         n_proj = np.asarray(n_proj, dtype=np.int32)
@@ -459,7 +467,7 @@ class GlobalMesh:
             hit = np.nonzero(inside.any(axis=1))[0]
             if hit.size == 0:
                 continue
-            g = np.exp(-r2[hit] / (2 * sig * sig)) * inside[hit] * ref.mass_gll[None, :]
+            g = np.exp(-r2[hit] / (2 * sig * sig)) * inside[hit] * wnode[hit]
             dd = d[hit]
             polys = [np.ones_like(g), dd[..., 0], dd[..., 1], dd[..., 2], dd[..., 0] * dd[..., 1],
                      dd[..., 1] * dd[..., 2], dd[..., 0] * dd[..., 2], r2[hit] - 1.0]
@@ -483,26 +491,28 @@ class GlobalMesh:
         H_c(I,J) = 1/2 K + V + 1/2 |k|^2 int N_I N_J  -  i sum_d k_d int dN_I/dx_d N_J , complex128[nc, n, n]."""
         ref = self.ref
         k = np.asarray(kpoint, dtype=np.float64)
+        _, scale = self.cell_origin_scale(cells)
         Hr = self.cell_hamiltonians(cells, potential, vquad)
-        Hr += 0.5 * float(k @ k) * ref.M3c
+        Hr += 0.5 * float(k @ k) * (scale ** 3)[:, None, None] * ref.M3c[None, :, :]
         Hi = -(k[0] * ref.G3[0] + k[1] * ref.G3[1] + k[2] * ref.G3[2])
-        return Hr + 1j * Hi[None, :, :]
+        return Hr + 1j * (scale ** 2)[:, None, None] * Hi[None, :, :]
 
     def cell_hamiltonians(self, cells: np.ndarray, potential: Optional[Callable],
                           vquad: str = "gauss", out: Optional[np.ndarray] = None) -> np.ndarray:
         """H_c = 1/2 K_c + V_c for the given natural cell ids, float64[nc, n, n]."""
         ref = self.ref
         n = ref.n
-        nx, ny, nz = self.ncells
         cells = np.asarray(cells, dtype=np.int64)
+        origin, scale = self.cell_origin_scale(cells)
         H = out if out is not None else np.empty((cells.size, n, n))
-        H[:] = 0.5 * ref.K3
+        # stiffness of a cube of edge s*h: K = s * K(h); volume weights scale with s^3
+        H[:] = 0.5 * scale[:, None, None] * ref.K3[None, :, :]
         if potential is None:
             return H
-        origin = np.stack([(cells % nx), (cells // nx) % ny, cells // (nx * ny)], axis=1) * self.h
+        vol = scale ** 3
         if vquad == "gll":
-            xyz = origin[:, None, :] + ref.node_xyz[None, :, :]
-            vd = potential(xyz) * ref.mass_gll[None, :]
+            xyz = origin[:, None, :] + scale[:, None, None] * ref.node_xyz[None, :, :]
+            vd = potential(xyz) * ref.mass_gll[None, :] * vol[:, None]
             idx = np.arange(n)
             H[:, idx, idx] += vd
         elif vquad == "gauss":
@@ -510,8 +520,8 @@ class GlobalMesh:
             chunk = max(1, int(2.0e8 // (phi.size + n * n)))
             for s in range(0, cells.size, chunk):
                 e = min(cells.size, s + chunk)
-                xyz = origin[s:e, None, :] + ref.quad_xyz[None, :, :]
-                vw = potential(xyz) * ref.quad_w[None, :]          # (nc, nq3)
+                xyz = origin[s:e, None, :] + scale[s:e, None, None] * ref.quad_xyz[None, :, :]
+                vw = potential(xyz) * ref.quad_w[None, :] * vol[s:e, None]   # (nc, nq3)
                 H[s:e] += np.einsum("cq,qi,qj->cij", vw, phi, phi, optimize=True)
         else:
             raise ValueError(vquad)
@@ -620,6 +630,19 @@ def build_mesh(p: int, ncells: Sequence[int], h: float = 1.0,
         if g in entries:
             continue
         entries[g] = ([int(gid_of_natural[c]) for c, _ in cw], [float(w) for _, w in cw], float(inh))
+    _close_constraints_and_assemble_mass(tmp, entries)
+    return tmp
+
+
+def _close_constraints_and_assemble_mass(tmp: GlobalMesh, entries: dict) -> None:
+    """entries: {row_gid: ([col_gid...], [weight...], inhomogeneity)} -> closed, sorted global CSR on ``tmp`` and
+    the diagonal GLL mass with distribute_local_to_global semantics
+    (src/dftOperator/kohnShamDFTOperator.cc:453-524)."""
+    ref = tmp.ref
+    nNodes = tmp.nNodes
+    gid_of_natural = tmp.gid_of_natural
+    cid = np.arange(tmp.cellRank.size, dtype=np.int64)
+    chunk = 1 << 14
     # resolve chains (columns must be unconstrained, as after AffineConstraints::close())
     changed = True
     while changed:
@@ -669,7 +692,8 @@ def build_mesh(p: int, ncells: Sequence[int], h: float = 1.0,
     for s in range(0, cid.size, chunk):
         e = min(cid.size, s + chunk)
         g = gid_of_natural[tmp.cell_natural_nodes(cid[s:e])].ravel()
-        w = np.tile(ref.mass_gll, e - s)
+        _, scale = tmp.cell_origin_scale(cid[s:e])
+        w = ((scale ** 3)[:, None] * ref.mass_gll[None, :]).ravel()
         con = isCon[g]
         np.add.at(mass, g[~con], w[~con])
         if con.any():
@@ -681,4 +705,4 @@ def build_mesh(p: int, ncells: Sequence[int], h: float = 1.0,
                 idx = base + off
                 np.add.at(mass, tmp.conCols[idx], tmp.conVals[idx] * np.repeat(w[con], cnt))
     tmp.massGlobal = mass
-    return tmp
+

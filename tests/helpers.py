@@ -68,3 +68,39 @@ def hanging_like_constraints(nrows=6, seed=3):
         return out
 
     return fn
+
+
+def make_adaptive_problem(p, ncoarse=(3, 3, 3), H=1.4, nranks=1, radius=0.8, n_atoms=0, n_proj=4, rc=1.2, vquad="gauss",
+                          half=False):
+    """One level of 2:1 refinement around the box centre (real hanging nodes), non-periodic, Dirichlet - the mesh
+    class of BASELINE configs[0] / configs[3]."""
+    from dftfe_b200.femesh_adaptive import build_adaptive_mesh
+
+    box = np.array(ncoarse) * H
+
+    def refine(centres):
+        if half:   # refine the x < L/2 half: one planar coarse / fine interface
+            return centres[:, 0] < box[0] / 2.0
+        return np.linalg.norm(centres - box / 2.0, axis=1) < radius * H
+
+    mesh = build_adaptive_mesh(p, ncoarse, H, refine, nranks=nranks)
+    pot = gaussian_wells_potential(mesh.box, periodic=(False, False, False))
+    ranks = [mesh.rank_problem(r, potential=pot, vquad=vquad) for r in range(nranks)]
+    if n_atoms:
+        rng = np.random.default_rng(321)
+        atoms = (0.5 + rng.uniform(-0.25, 0.25, size=(n_atoms, 3))) * box   # near the refined region, as in a molecule
+        nproj = [n_proj + (a % 3) for a in range(n_atoms)]
+        for r, rp in enumerate(ranks):
+            rp.nonlocal_data = mesh.nonlocal_data(r, atoms, nproj, rc=rc)
+    return mesh, ranks
+
+
+def field_on_nodes(rp, ncols, seed=0):
+    """A smooth-plus-noise field defined by node coordinates, so that different partitions of the same mesh see
+    the same global vector."""
+    xyz = rp.nodeXYZ
+    cols = []
+    for k in range(ncols):
+        a, b, c = 0.9 + 0.13 * k + seed, 0.4 + 0.07 * k, 0.21 * (k + 1)
+        cols.append(np.sin(a * xyz[:, 0] + k) * np.cos(b * xyz[:, 1] - k) + c * np.sin(3.1 * xyz[:, 2] + seed))
+    return np.stack(cols, axis=1)

@@ -1,0 +1,117 @@
+"""-m gpu: meshes with real hanging nodes (one level of 2:1 refinement, non-periodic) - the mesh class of
+BASELINE configs[0] (demo/ex1: adaptive, pseudopotential, 15 states -> ragged block) and configs[3]."""
+import threading
+
+import numpy as np
+import pytest
+
+from tests.helpers import field_on_nodes, make_adaptive_problem
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _relerr(a, b):
+    return np.abs(a - b).max() / max(np.abs(b).max(), 1e-300)
+
+
+@pytest.fixture(scope="module")
+def capi(lib_built):
+    assert torch.cuda.is_available()
+    from dftfe_b200 import capi
+
+    return capi
+
+
+@pytest.mark.parametrize("p,B,n_atoms", [(3, 15, 2), (6, 32, 0), (4, 32, 2)])
+def test_adaptive_operator_constraints_and_filter(capi, p, B, n_atoms):
+    from oracle import chfsi_oracle as O
+
+    mesh, ranks = make_adaptive_problem(p, (3, 3, 3) if p < 6 else (2, 2, 2), 1.4, half=(p == 6), n_atoms=n_atoms)
+    rp = ranks[0]
+    assert mesh.nHanging > 0 and rp.rowSizes.max() > p + 1   # face-hanging rows with up to (p+1)^2 columns
+    op = capi.Operator(rp, B)
+    op.set_cell_hamiltonian(rp.H)
+    ncol, colours = op.colouring()
+    assert ncol >= 8   # irregular adjacency needs at least the structured 8 colours
+    X = [field_on_nodes(rp, B) * rp.sqrtMass[:, None]]
+    # constraints on real hanging rows: bit-exact
+    xr = np.random.default_rng(1).uniform(-1, 1, size=(rp.M + rp.G, B))
+    ref = xr.copy()
+    O.distribute(rp, ref)
+    x_d = _dev(xr)
+    op.distribute(x_d)
+    assert np.array_equal(x_d.cpu().numpy(), ref)
+    ref2 = ref.copy()
+    O.distribute_slave_to_master(rp, ref2)
+    op.distribute_slave_to_master(x_d)
+    assert _relerr(x_d.cpu().numpy(), ref2) < 1e-15
+    # operator
+    src, dst = [X[0].copy()], [np.zeros_like(X[0])]
+    O.HX(ranks, src, dst, False, 1.0)
+    s_d, d_d = _dev(X[0]), torch.zeros(rp.M + rp.G, B, dtype=torch.float64, device="cuda")
+    op.HX(s_d, d_d, False, 1.0)
+    assert _relerr(d_d.cpu().numpy()[:rp.M], dst[0][:rp.M]) < 1e-12
+    # filter
+    lo, up = O.lanczos_bounds(ranks)
+    refb = [X[0].copy()]
+    O.chebyshev_filter_inplace(ranks, refb, 8, lo + 0.3 * (up - lo), up, lo - 0.2)
+    x_d, y_d = _dev(X[0]), torch.zeros(rp.M + rp.G, B, dtype=torch.float64, device="cuda")
+    op.chebyshevFilter(x_d, y_d, 8, lo + 0.3 * (up - lo), up, lo - 0.2)
+    assert _relerr(x_d.cpu().numpy()[:rp.M], refb[0][:rp.M]) < 1e-11
+    op.close()
+
+
+def test_adaptive_multirank_solve_ex1_like(capi):
+    """demo/ex1 in miniature: adaptive non-periodic mesh, non-local projectors, 15 states in ONE ragged block,
+    CGS + RR as the device path runs it, three ranks through the loopback transport."""
+    from oracle import chfsi_oracle as O
+
+    nranks, p, N = 3, 3, 15
+    mesh, ranks = make_adaptive_problem(p, (3, 3, 3), 1.4, nranks=nranks, n_atoms=2)
+    Xo = [field_on_nodes(rp, N, seed=1) for rp in ranks]
+    for rp, x in zip(ranks, Xo):
+        x[rp.M:] = 0
+    lo, up = O.lanczos_bounds(ranks)
+    out = [None] * nranks
+    errs = []
+
+    def rank_fn(r):
+        try:
+            rp = ranks[r]
+            op = capi.Operator(rp, N, use_torch_stream=False)
+            op.comm_init_loopback(71, r, nranks)
+            op.set_cell_hamiltonian(rp.H)
+            solver = capi.ChebyshevSolver(op)
+            Xd = _dev(Xo[r][:rp.M])
+            first, hist = True, []
+            for _ in range(3):
+                eig, res, ub = solver.solve(Xd, isFirstFilteringCall=first, chebyshevOrder=12, reuseLanczos=True,
+                                            useCgsRR=True)
+                hist.append((eig.copy(), solver.spectrumBounds()))
+                solver.reinitSpectrumBounds(eig[0], eig[-1])
+                first = False
+            op.close()
+            out[r] = (hist, res)
+        except Exception as e:  # noqa: BLE001
+            errs.append((r, repr(e)))
+
+    th = [threading.Thread(target=rank_fn, args=(r,)) for r in range(nranks)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join(timeout=600)
+    assert not errs, errs
+    Xr = [x.copy() for x in Xo]
+    for it in range(3):
+        bounds = out[0][0][it][1]
+        ev_ref, res_ref = O.solve(ranks, Xr, N, 12, bounds, use_gep=False)
+        for r in range(nranks):
+            assert np.abs(out[r][0][it][0] - ev_ref).max() < 1e-8, (it, r)
+    # total band energy of the 15 states (the reference's 1e-6 Ha/atom energy criterion, 2 atoms here)
+    assert abs(out[0][0][2][0].sum() - ev_ref.sum()) / 2 < 1e-6
+    assert np.abs(out[0][1] - res_ref).max() < 1e-6

@@ -222,3 +222,76 @@ def test_golden_fixture():
     for r, (rp, y) in enumerate(zip(ranks, Y)):
         assert np.abs(y[:rp.M] - g[f"filtered_rank{r}"]).max() < 1e-13
     assert np.abs(O.xtx(ranks, X) - g["xtx"]).max() < 1e-12
+
+
+def _adaptive(p=3, nranks=1, ncoarse=(3, 3, 3), H=1.4, potential=True):
+    from dftfe_b200.femesh import gaussian_wells_potential
+    from dftfe_b200.femesh_adaptive import build_adaptive_mesh
+
+    box = np.array(ncoarse) * H
+
+    def refine(centres):   # the coarse cells around the box centre
+        return np.linalg.norm(centres - box / 2.0, axis=1) < 0.8 * H
+
+    mesh = build_adaptive_mesh(p, ncoarse, H, refine, nranks=nranks)
+    pot = gaussian_wells_potential(mesh.box, periodic=(False, False, False)) if potential else None
+    ranks = [mesh.rank_problem(r, potential=pot) for r in range(nranks)]
+    return mesh, ranks
+
+
+def test_adaptive_mesh_hanging_node_constraints():
+    """One level of 2:1 refinement: hanging-node rows are partitions of unity with at most (p+1)^2 columns, the
+    constrained operator is symmetric and reproduces the particle-in-a-box levels."""
+    p = 4
+    mesh, ranks = _adaptive(p=p, potential=False)
+    rp = ranks[0]
+    assert mesh.nHanging > 0
+    sizes = rp.rowSizes
+    multi = sizes > 1
+    assert multi.sum() > 0 and sizes.max() <= (p + 1) ** 2
+    # closed constraints: no column is itself constrained; interior hanging rows interpolate constants exactly
+    assert not np.isin(rp.colIdsLocal, rp.rowIdsLocal).any()
+    xyz = rp.nodeXYZ
+    L = np.array(mesh.box)
+    for i in np.nonzero(multi)[0]:
+        s = rp.rowStarts[i]
+        cols, w = rp.colIdsLocal[s:s + sizes[i]], rp.colValues[s:s + sizes[i]]
+        # columns dropped by the Dirichlet closure only reduce the sum; rows away from the boundary sum to 1 and
+        # reproduce the coordinates of the hanging node (linear completeness of the coarse trace)
+        x = xyz[rp.rowIdsLocal[i]]
+        if np.all((x > 1.45) & (x < L - 1.45)):
+            assert abs(w.sum() - 1.0) < 1e-12
+            assert np.abs(w @ xyz[cols] - x).max() < 1e-12
+    A, free = _dense_operator(rp)
+    assert np.abs(A - A.T).max() < 1e-12
+    ev = np.linalg.eigvalsh(A[np.ix_(free, free)])
+    exact = 0.5 * np.pi ** 2 * np.array([3.0, 6.0, 6.0, 6.0, 9.0]) / L[0] ** 2
+    assert np.abs(ev[:5] - exact).max() < 2e-4
+    # total mass = volume of the interior of the box (mass of constrained rows is redistributed or dropped at the
+    # Dirichlet boundary only)
+    assert rp.sqrtMass[:rp.M].max() > 0
+
+
+@pytest.mark.parametrize("nranks", [2, 3])
+def test_adaptive_mesh_multirank_matches_single_rank(nranks):
+    mesh1, r1 = _adaptive(p=3)
+    meshn, rn = _adaptive(p=3, nranks=nranks)
+    B = 5
+    rng = np.random.default_rng(0)
+    # the same field by coordinates on both partitions
+    f = lambda xyz: np.stack([np.sin(1.3 * xyz[:, 0] + k) * np.cos(0.7 * xyz[:, 1] - k) + 0.1 * k * xyz[:, 2]
+                              for k in range(B)], axis=1)
+    X1 = [f(r1[0].nodeXYZ) * r1[0].sqrtMass[:, None]]
+    Xn = [f(rp.nodeXYZ) * rp.sqrtMass[:, None] for rp in rn]
+    for rp, x in zip(rn, Xn):
+        x[rp.M:] = 0
+    lo, up = O.lanczos_bounds(r1)
+    O.chebyshev_filter_inplace(r1, X1, 6, lo + 0.3 * (up - lo), up, lo - 0.1)
+    O.chebyshev_filter_inplace(rn, Xn, 6, lo + 0.3 * (up - lo), up, lo - 0.1)
+    # compare by coordinates
+    key = lambda xyz: [tuple(np.round(v, 8)) for v in xyz]
+    ref = {k: v for k, v in zip(key(r1[0].nodeXYZ[:r1[0].M]), X1[0][:r1[0].M])}
+    scale = np.abs(X1[0]).max()
+    for rp, x in zip(rn, Xn):
+        for k, v in zip(key(rp.nodeXYZ[:rp.M]), x[:rp.M]):
+            assert np.abs(ref[k] - v).max() < 1e-11 * scale
