@@ -48,6 +48,7 @@ def parse_args():
     ap.add_argument("--cells", type=int, default=CELLS_PER_GPU, help="cells per axis per GPU (debug)")
     ap.add_argument("--nwfc", type=int, default=N_WFC)
     ap.add_argument("--degree", type=int, default=DEGREE)
+    ap.add_argument("--block", type=int, default=BLOCK, help="Chebyshev block size (debug; headline = 256)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-scf", action="store_true", help="skip the full solve() (wall s per SCF iteration) section")
@@ -146,7 +147,7 @@ def cpu_reference_run(args, steps, warmup, degree_sample):
 
     mesh, rp, pot = build_rank_problem(args, 0, 1, build_H_host=True)
     col = greedy_colouring(np.ascontiguousarray(rp.cellLocalDofs), rp.M + rp.G)
-    B = min(BLOCK, args.nwfc)
+    B = min(args.block, args.nwfc)
     co = COracle(rp, B, colouring=col)
     rng = np.random.default_rng(42)
     X = rng.uniform(-1.0, 1.0, size=(rp.M + rp.G, B))
@@ -190,9 +191,9 @@ def main_reference(args):
 def workload_config(args, nranks):
     return {"workload": f"synthetic ChFSI microbench: FE order {P_ORDER}, {args.cells}^3 periodic cells per GPU "
                         f"({(args.cells * P_ORDER) ** 3} free DoFs per GPU), N={args.nwfc} wavefunctions, "
-                        f"block {min(BLOCK, args.nwfc)}, Chebyshev degree {args.degree}",
+                        f"block {min(args.block, args.nwfc)}, Chebyshev degree {args.degree}",
             "fe_order": P_ORDER, "cells_per_gpu": args.cells ** 3, "n_wavefunctions": args.nwfc,
-            "cheby_block": min(BLOCK, args.nwfc), "degree": args.degree, "partition": f"brick {rank_grid_for(nranks)}",
+            "cheby_block": min(args.block, args.nwfc), "degree": args.degree, "partition": f"brick {rank_grid_for(nranks)}",
             "l2_policy": "inputs larger than L2 (X block 2.2 GB, cell H 4.6 GB per pass)",
             "overlap_lanes": "on" if args.lanes != 0 else "off",
             "mixed_prec_cheby": bool(args.mixed)}
@@ -220,7 +221,7 @@ def main_ours(args):
         dist.barrier()
 
     mesh, rp, pot = build_rank_problem(args, rank, world)
-    B = min(BLOCK, args.nwfc)
+    B = min(args.block, args.nwfc)
     N = args.nwfc
     stream = torch.cuda.Stream(device=dev)
     with torch.cuda.stream(stream):

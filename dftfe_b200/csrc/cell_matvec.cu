@@ -105,10 +105,10 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
 //   PARTNER = false: xb = tile + (lane&3)*LDS + (lane>>2), as stored
 //   PARTNER = true : xb = tile + (lane&3)*LDS + ((lane>>2)^1), the other half of the complex pair, with the
 //                    sign bit flipped on lanes that hold a real-part column (sgn mask)
-template <bool PARTNER>
-__device__ __forceinline__ void load_b(const double *xb, unsigned long long sgn, int ks, double (&b)[NT]) {
+template <bool PARTNER, int NTL = NT>
+__device__ __forceinline__ void load_b(const double *xb, unsigned long long sgn, int ks, double (&b)[NTL]) {
 #pragma unroll
-  for (int nt = 0; nt < NT; ++nt) {
+  for (int nt = 0; nt < NTL; ++nt) {
     const double v = xb[(ks * 4) * LDS + nt * 8];
     b[nt] = PARTNER ? __longlong_as_double(__double_as_longlong(v) ^ (long long)sgn) : v;
   }
@@ -347,10 +347,12 @@ struct PersistCfg {
   static constexpr int APF = DB_APF;  // A-fragment prefetch depth in (virtual) k-steps
 };
 
-// The row-tile count NTILE (TPW or TPW-1) is a compile-time constant per instantiation because a
-// predicated-off DMMA still occupies its tensor-pipe slot.
+// Item loop of an MMA warp for blocks whose column count is a multiple of 32 (every tile full): kept as ONE
+// function - splitting it into per-item pieces as the ragged variant below does costs registers (64 B of spills,
+// -5 % on the headline configuration).  The row-tile count NTILE (TPW or TPW-1) is a compile-time constant per
+// instantiation because a predicated-off DMMA still occupies its tensor-pipe slot.
 template <int NODES, bool CPLX, int NTILE>
-__device__ __forceinline__ void mma_warp_items(const double *__restrict__ Ht, const int32_t *__restrict__ cells,
+__device__ __forceinline__ void mma_warp_items_full(const double *__restrict__ Ht, const int32_t *__restrict__ cells,
                                                int nItems, const double *__restrict__ src,
                                                double *__restrict__ dst, int ldx, int nColTiles,
                                                const EpilogueParams &ep, const double *Xs, const uint32_t *rowsS,
@@ -459,22 +461,175 @@ __device__ __forceinline__ void mma_warp_items(const double *__restrict__ Ht, co
   }
 }
 
-#ifndef DB_MAXNREG
-#define DB_MAXNREG 0
-#endif
-// 13 warps x 152 registers x 32 lanes = 63232 <= 65536: the register file allows 152 per thread, but
-// __launch_bounds__(416, 1) makes ptxas budget for 512 threads (128 registers, with spills); __maxnreg__ states
-// the real limit.
-template <int NODES, bool CPLX>
-__global__ void
-#if DB_MAXNREG
-__maxnreg__(DB_MAXNREG)
-#else
-__launch_bounds__(PersistCfg<NODES, CPLX>::THREADS, 1)
-#endif
+// One (cell, column tile) item of an MMA warp.  The row-tile count NTILE (TPW or TPW-1) and the number of n8
+// column tiles NTL (4 for a full 32-column tile, fewer for the ragged last tile of a block whose column count is
+// not a multiple of 32 - the reference's AUTO block sizes are 90..130 and 180..220, src/dft/dft.cc:554-690) are
+// compile-time constants per instantiation because a predicated-off DMMA still occupies its tensor-pipe slot.
+template <int NODES, bool CPLX, int NTILE, int NTL, bool RAGGED>
+__device__ __forceinline__ void mma_one_item(const double *__restrict__ Ht, const int32_t *__restrict__ cells,
+                                             int nItems, int item, int it, int col0,
+                                             const double *__restrict__ src,
+                                             double *__restrict__ dst, int ncols, int ldx, int nColTiles,
+                                             const EpilogueParams &ep, const double *Xs, const uint32_t *rowsS,
+                                             uint64_t *full, uint64_t *empty, int warp, int lane,
+                                             double (&a)[PersistCfg<NODES, CPLX>::APF][CellCfg<NODES, CPLX>::TPWP]) {
+  using C = CellCfg<NODES, CPLX>;
+  using P = PersistCfg<NODES, CPLX>;
+  const int buf = it & 1;
+  const uint32_t ph = (it >> 1) & 1;
+  const int cell = cells[item / nColTiles];
+  const double *Hc = Ht + (size_t)cell * C::HT_PER_CELL + (size_t)warp * C::HT_PER_WARP + lane * C::TPWP;
+  const double *xb = Xs + (lane & 3) * LDS + (lane >> 2) + buf * P::XBUF;
+  const double *xbp = Xs + (lane & 3) * LDS + ((lane >> 2) ^ 1) + buf * P::XBUF;
+  const unsigned long long sgn = ((lane >> 2) & 1) ? 0ull : 0x8000000000000000ull;
+
+  double acc[NTILE][NTL][2];
+#pragma unroll
+  for (int t = 0; t < NTILE; ++t)
+#pragma unroll
+    for (int nt = 0; nt < NTL; ++nt) acc[t][nt][0] = acc[t][nt][1] = 0.0;
+
+  mbar_wait(&full[buf], ph);
+
+  int ks = 0;  // virtual k-step; advances by APF (even), so the parity of ks+s is that of s
+  for (; ks + P::APF <= C::KSV; ks += P::APF) {
+#pragma unroll
+    for (int s = 0; s < P::APF; ++s) {
+      double b[NTL];
+      if (CPLX && (s & 1))
+        load_b<true, NTL>(xbp, sgn, (ks + s) >> 1, b);
+      else
+        load_b<false, NTL>(xb, sgn, CPLX ? ((ks + s) >> 1) : (ks + s), b);
+#pragma unroll
+      for (int t = 0; t < NTILE; ++t)
+#pragma unroll
+        for (int nt = 0; nt < NTL; ++nt) dmma884(acc[t][nt][0], acc[t][nt][1], a[s][t], b[nt]);
+      if (ks + s + P::APF < C::KSV) load_frags<C::TPWP>(Hc + (size_t)(ks + s + P::APF) * 32 * C::TPWP, a[s]);
+    }
+  }
+#pragma unroll
+  for (int s = 0; s < C::KSV % P::APF; ++s) {
+    double b[NTL];
+    if (CPLX && (s & 1))
+      load_b<true, NTL>(xbp, sgn, (ks + s) >> 1, b);
+    else
+      load_b<false, NTL>(xb, sgn, CPLX ? ((ks + s) >> 1) : (ks + s), b);
+#pragma unroll
+    for (int t = 0; t < NTILE; ++t)
+#pragma unroll
+      for (int nt = 0; nt < NTL; ++nt) dmma884(acc[t][nt][0], acc[t][nt][1], a[s][t], b[nt]);
+  }
+
+  // rows of this warp's tiles, then release the buffer to the producer
+  uint32_t fr[NTILE];
+#pragma unroll
+  for (int t = 0; t < NTILE; ++t) {
+    const int i = (warp + t * C::WARPS) * 8 + (lane >> 2);
+    fr[t] = (i < NODES) ? rowsS[buf * NODES + i] : 0u;
+  }
+  __syncwarp();
+  if (lane == 0) mbar_arrive(&empty[buf]);
+
+  // next item's first A fragments fly while this item's epilogue runs
+  if (item + (int)gridDim.x < nItems) {
+    const int ncell = cells[(item + gridDim.x) / nColTiles];
+    const double *Hn = Ht + (size_t)ncell * C::HT_PER_CELL + (size_t)warp * C::HT_PER_WARP + lane * C::TPWP;
+#pragma unroll
+    for (int s = 0; s < P::APF; ++s) load_frags<C::TPWP>(Hn + (size_t)min(s, C::KSV - 1) * 32 * C::TPWP, a[s]);
+  }
+
+  // ---- epilogue (even ncols / ldx: guaranteed by the launcher; a ragged tile masks its missing column pairs)
+#pragma unroll
+  for (int t = 0; t < NTILE; ++t) {
+    const int i = (warp + t * C::WARPS) * 8 + (lane >> 2);
+    if (i < NODES) {
+      const uint32_t r = fr[t] & ROW_MASK;
+      const double so = ep.s * (ep.rowOut ? __ldg(ep.rowOut + r) : 1.0);
+      double ca, cb;
+      epilogue_coeffs(fr[t], ep, ca, cb);
+      const int cl = col0 + (lane & 3) * 2;
+      double *drow = dst + (size_t)r * ldx + cl;
+      const double *srow = src + (size_t)r * ldx + cl;
+      double2 d[NTL], sv[NTL];
+#pragma unroll
+      for (int nt = 0; nt < NTL; ++nt) {
+        const bool ok = !RAGGED || (cl + nt * 8 < ncols);
+        d[nt] = (cb != 0.0 && ok) ? *reinterpret_cast<const double2 *>(drow + nt * 8) : make_double2(0.0, 0.0);
+        sv[nt] = (ca != 0.0 && ok) ? *reinterpret_cast<const double2 *>(srow + nt * 8) : make_double2(0.0, 0.0);
+      }
+#pragma unroll
+      for (int nt = 0; nt < NTL; ++nt) {
+        double2 o;
+        o.x = so * acc[t][nt][0] + ca * sv[nt].x + cb * d[nt].x;
+        o.y = so * acc[t][nt][1] + ca * sv[nt].y + cb * d[nt].y;
+        if (!RAGGED || (cl + nt * 8 < ncols)) *reinterpret_cast<double2 *>(drow + nt * 8) = o;
+      }
+    }
+  }
+}
+
+// Column tiling of a block of `ncols` columns: nColTiles = ceil(ncols / 32) tiles; the ceil(ncols / 8) n8 tiles
+// are dealt as evenly as possible (e.g. 100 columns -> 4,3,3,3), because every item streams the whole H_c and a
+// narrow tile would make that stream the bottleneck.
+struct ColTiling {
+  int base, rem;  // tiles [0, rem) hold base+1 n8 tiles, the others base
+  __host__ __device__ ColTiling(int ncols, int nColTiles) {
+    const int total8 = (ncols + 7) >> 3;
+    base = total8 / nColTiles;
+    rem = total8 % nColTiles;
+  }
+  __host__ __device__ int ntl(int tile) const { return base + (tile < rem ? 1 : 0); }
+  __host__ __device__ int col0(int tile) const { return 8 * (tile * base + (tile < rem ? tile : rem)); }
+};
+
+template <int NODES, bool CPLX, int NTILE, bool RAGGED>
+__device__ __forceinline__ void mma_warp_items(const double *__restrict__ Ht, const int32_t *__restrict__ cells,
+                                               int nItems, const double *__restrict__ src,
+                                               double *__restrict__ dst, int ncols, int ldx, int nColTiles,
+                                               const EpilogueParams &ep, const double *Xs, const uint32_t *rowsS,
+                                               uint64_t *full, uint64_t *empty, int warp, int lane) {
+  using C = CellCfg<NODES, CPLX>;
+  using P = PersistCfg<NODES, CPLX>;
+  static_assert(P::APF % 2 == 0, "the parity of a virtual k-step must be that of its ring slot");
+  // A prefetch ring; primed for the first item here, re-primed for the next item before each epilogue
+  double a[P::APF][C::TPWP];
+  if ((int)blockIdx.x < nItems) {
+    const int cell = cells[blockIdx.x / nColTiles];
+    const double *Hc = Ht + (size_t)cell * C::HT_PER_CELL + (size_t)warp * C::HT_PER_WARP + lane * C::TPWP;
+#pragma unroll
+    for (int s = 0; s < P::APF; ++s) load_frags<C::TPWP>(Hc + (size_t)min(s, C::KSV - 1) * 32 * C::TPWP, a[s]);
+  }
+  const ColTiling ct(ncols, nColTiles);
+  int it = 0;
+  for (int item = blockIdx.x; item < nItems; item += gridDim.x, ++it) {
+#define DB_ITEM(NTL, COL0)                                                                                          \
+  mma_one_item<NODES, CPLX, NTILE, NTL, RAGGED>(Ht, cells, nItems, item, it, COL0, src, dst, ncols, ldx, nColTiles, ep, Xs, \
+                                        rowsS, full, empty, warp, lane, a)
+    if (!RAGGED) {
+      DB_ITEM(4, (item % nColTiles) * BT);
+    } else {
+      const int tile = item % nColTiles;
+      const int ntl = ct.ntl(tile), c0 = ct.col0(tile);
+      if (ntl == 4)
+        DB_ITEM(4, c0);
+      else if (ntl == 3)
+        DB_ITEM(3, c0);
+      else if (ntl == 2)
+        DB_ITEM(2, c0);
+      else
+        DB_ITEM(1, c0);
+    }
+#undef DB_ITEM
+  }
+}
+
+// (13 warps: SMSP 0 holds four of them, so the register file allows 16384 / (4 x 32) = 128 registers per thread;
+// __maxnreg__ 144 / 152 compiles without spills but fails to launch.)
+template <int NODES, bool CPLX, bool RAGGED>
+__global__ void __launch_bounds__(PersistCfg<NODES, CPLX>::THREADS, 1)
 cell_matvec_persistent_kernel(const double *__restrict__ Ht, const uint32_t *__restrict__ cellRows,
                               const int32_t *__restrict__ cells, int nItems, const double *__restrict__ src,
-                              double *__restrict__ dst, int ldx, int nColTiles, EpilogueParams ep) {
+                              double *__restrict__ dst, int ncols, int ldx, int nColTiles, EpilogueParams ep) {
   using C = CellCfg<NODES, CPLX>;
   using P = PersistCfg<NODES, CPLX>;
   extern __shared__ __align__(128) unsigned char smem_raw[];
@@ -511,7 +666,10 @@ cell_matvec_persistent_kernel(const double *__restrict__ Ht, const uint32_t *__r
       const int buf = it & 1;
       const uint32_t ph = (it >> 1) & 1;
       const int cell = cells[item / nColTiles];
-      const int col0 = (item % nColTiles) * BT;
+      const ColTiling ct(ncols, nColTiles);
+      const int tile = item % nColTiles;
+      const int col0 = RAGGED ? ct.col0(tile) : tile * BT;
+      const int width = RAGGED ? min(8 * ct.ntl(tile), ncols - col0) : BT;
       const uint32_t *cr = cellRows + (size_t)cell * NODES;
       // row words first (global latency overlaps the wait for the buffer)
       uint32_t myRows[(NODES + 31) / 32];
@@ -529,14 +687,16 @@ cell_matvec_persistent_kernel(const double *__restrict__ Ht, const uint32_t *__r
         if (k < NODES) rs[k] = myRows[j];
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive_expect_tx(&full[buf], (uint32_t)(NODES * BT * sizeof(double)));
+      // a ragged last tile copies only the columns that exist (even count -> multiple of 16 bytes); the
+      // shared-memory columns beyond them keep finite values of earlier tiles and are masked in the epilogue
+      const uint32_t rowBytes = (uint32_t)(width * sizeof(double));
+      if (lane == 0) mbar_arrive_expect_tx(&full[buf], (uint32_t)NODES * rowBytes);
       __syncwarp();
 #pragma unroll
       for (int j = 0; j < (NODES + 31) / 32; ++j) {
         const int k = lane + 32 * j;
         if (k < NODES)
-          tma_bulk_g2s(xs + k * LDS, src + (size_t)(myRows[j] & ROW_MASK) * ldx + col0, BT * sizeof(double),
-                       &full[buf]);
+          tma_bulk_g2s(xs + k * LDS, src + (size_t)(myRows[j] & ROW_MASK) * ldx + col0, rowBytes, &full[buf]);
       }
 #if DB_L2_PREFETCH
       // pull the tiled H of the cell this CTA works on next-but-one into L2 (one CTA per cell does it: the
@@ -558,12 +718,22 @@ cell_matvec_persistent_kernel(const double *__restrict__ Ht, const uint32_t *__r
     }
   } else {
     constexpr int FULL_WARPS = C::MT - (C::TPW - 1) * C::WARPS;  // warps that own TPW tiles
-    if (warp < FULL_WARPS)
-      mma_warp_items<NODES, CPLX, C::TPW>(Ht, cells, nItems, src, dst, ldx, nColTiles, ep, Xs, rowsS, full, empty,
-                                          warp, lane);
-    else if (C::TPW > 1)
-      mma_warp_items<NODES, CPLX, (C::TPW > 1 ? C::TPW - 1 : 1)>(Ht, cells, nItems, src, dst, ldx, nColTiles, ep,
-                                                                 Xs, rowsS, full, empty, warp, lane);
+    if (!RAGGED) {
+      if (warp < FULL_WARPS)
+        mma_warp_items_full<NODES, CPLX, C::TPW>(Ht, cells, nItems, src, dst, ldx, nColTiles, ep, Xs, rowsS, full,
+                                                 empty, warp, lane);
+      else if (C::TPW > 1)
+        mma_warp_items_full<NODES, CPLX, (C::TPW > 1 ? C::TPW - 1 : 1)>(Ht, cells, nItems, src, dst, ldx, nColTiles,
+                                                                        ep, Xs, rowsS, full, empty, warp, lane);
+    } else {
+      if (warp < FULL_WARPS)
+        mma_warp_items<NODES, CPLX, C::TPW, true>(Ht, cells, nItems, src, dst, ncols, ldx, nColTiles, ep, Xs, rowsS,
+                                                  full, empty, warp, lane);
+      else if (C::TPW > 1)
+        mma_warp_items<NODES, CPLX, (C::TPW > 1 ? C::TPW - 1 : 1), true>(Ht, cells, nItems, src, dst, ncols, ldx,
+                                                                         nColTiles, ep, Xs, rowsS, full, empty, warp,
+                                                                         lane);
+    }
   }
 }
 
@@ -595,14 +765,18 @@ int launch_impl2(dftfe_b200_ctx *ctx, const double *src, double *dst, int ncols,
   if (!attr_set) {
     DB_CUDA(cudaFuncSetAttribute(cell_matvec_kernel<NODES, CPLX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)C::SMEM));
-    if (P::SMEM <= 227 * 1024)
-      DB_CUDA(cudaFuncSetAttribute(cell_matvec_persistent_kernel<NODES, CPLX>,
+    if (P::SMEM <= 227 * 1024) {
+      DB_CUDA(cudaFuncSetAttribute(cell_matvec_persistent_kernel<NODES, CPLX, false>,
                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::SMEM));
+      DB_CUDA(cudaFuncSetAttribute(cell_matvec_persistent_kernel<NODES, CPLX, true>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::SMEM));
+    }
     attr_set = true;
   }
   const int nColTiles = (ncols + BT - 1) / BT;
-  // fast path needs full 32-column tiles, 16-byte aligned row segments and no extra gather scale
-  const bool fast = (P::SMEM <= 227 * 1024) && (ncols % BT == 0) && (ldx % 2 == 0) && ep.rowIn == nullptr &&
+  // fast path needs an even column count (16-byte row segments and column pairs), 16-byte aligned rows and no
+  // extra gather scale; the last column tile may be ragged
+  const bool fast = (P::SMEM <= 227 * 1024) && (ncols % 2 == 0) && (ldx % 2 == 0) && ep.rowIn == nullptr &&
                     ((reinterpret_cast<uintptr_t>(src) & 15) == 0) && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) &&
                     !ctx->force_generic_cell_kernel;
   for (int k = 0; k < ctx->nColours; ++k) {
@@ -612,9 +786,14 @@ int launch_impl2(dftfe_b200_ctx *ctx, const double *src, double *dst, int ncols,
     const int nItems = nCellsK * nColTiles;
     if (fast) {
       const int grid = std::min(nItems, std::max(1, ctx->num_sms - ctx->reserved_sms));
-      cell_matvec_persistent_kernel<NODES, CPLX><<<grid, P::THREADS, P::SMEM, ctx->stream>>>(
-          ctx->Hactive, ctx->cellRowsFlagged.p, ctx->colourCells.p + ctx->colourStart_h[k], nItems, src, dst, ldx,
-          nColTiles, ep);
+      if (ncols % BT == 0)
+        cell_matvec_persistent_kernel<NODES, CPLX, false><<<grid, P::THREADS, P::SMEM, ctx->stream>>>(
+            ctx->Hactive, ctx->cellRowsFlagged.p, ctx->colourCells.p + ctx->colourStart_h[k], nItems, src, dst, ncols,
+            ldx, nColTiles, ep);
+      else
+        cell_matvec_persistent_kernel<NODES, CPLX, true><<<grid, P::THREADS, P::SMEM, ctx->stream>>>(
+            ctx->Hactive, ctx->cellRowsFlagged.p, ctx->colourCells.p + ctx->colourStart_h[k], nItems, src, dst, ncols,
+            ldx, nColTiles, ep);
     } else {
       cell_matvec_kernel<NODES, CPLX><<<nItems, C::THREADS, C::SMEM, ctx->stream>>>(
           ctx->Hactive, ctx->cellRowsFlagged.p, ctx->colourCells.p + ctx->colourStart_h[k], src, dst, ncols, ldx,
