@@ -341,8 +341,13 @@ struct PersistCfg {
 #ifndef DB_APF
 #define DB_APF 4
 #endif
-#ifndef DB_L2_PREFETCH
-#define DB_L2_PREFETCH 0
+// what-if switches for profiling (results are wrong when set): skip the A-fragment refills / the epilogue's global
+// traffic to measure what each costs (profiles/r01_cell_kernel_variants.txt)
+#ifndef DB_WHATIF_NOA
+#define DB_WHATIF_NOA 0
+#endif
+#ifndef DB_WHATIF_NOEPI
+#define DB_WHATIF_NOEPI 0
 #endif
   static constexpr int APF = DB_APF;  // A-fragment prefetch depth in (virtual) k-steps
 };
@@ -403,7 +408,9 @@ __device__ __forceinline__ void mma_warp_items_full(const double *__restrict__ H
         for (int t = 0; t < NTILE; ++t)
 #pragma unroll
           for (int nt = 0; nt < NT; ++nt) dmma884(acc[t][nt][0], acc[t][nt][1], a[s][t], b[nt]);
+#if !DB_WHATIF_NOA
         if (ks + s + P::APF < C::KSV) load_frags<C::TPWP>(Hc + (size_t)(ks + s + P::APF) * 32 * C::TPWP, a[s]);
+#endif
       }
     }
 #pragma unroll
@@ -433,6 +440,16 @@ __device__ __forceinline__ void mma_warp_items_full(const double *__restrict__ H
     if (item + (int)gridDim.x < nItems) prime(item + gridDim.x);
 
     // ---- epilogue (full tiles, even ldx: guaranteed by the launcher)
+#if DB_WHATIF_NOEPI
+    {
+      double sacc = 0.0;
+#pragma unroll
+      for (int t = 0; t < NTILE; ++t)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) sacc += acc[t][nt][0] + acc[t][nt][1];
+      if (sacc == 1234.5678) dst[0] = sacc;
+    }
+#else
 #pragma unroll
     for (int t = 0; t < NTILE; ++t) {
       const int i = (warp + t * C::WARPS) * 8 + (lane >> 2);
@@ -458,6 +475,7 @@ __device__ __forceinline__ void mma_warp_items_full(const double *__restrict__ H
         }
       }
     }
+#endif
   }
 }
 
@@ -698,23 +716,6 @@ cell_matvec_persistent_kernel(const double *__restrict__ Ht, const uint32_t *__r
         if (k < NODES)
           tma_bulk_g2s(xs + k * LDS, src + (size_t)(myRows[j] & ROW_MASK) * ldx + col0, rowBytes, &full[buf]);
       }
-#if DB_L2_PREFETCH
-      // pull the tiled H of the cell this CTA works on next-but-one into L2 (one CTA per cell does it: the
-      // one with column tile 0); the MMA warps then find their A fragments in L2 instead of HBM
-      {
-        const int nitem = item + 2 * (int)gridDim.x;
-        if (nitem < nItems && (nitem % nColTiles) == 0) {
-          const int ncell = cells[nitem / nColTiles];
-          const char *base = reinterpret_cast<const char *>(Ht + (size_t)ncell * C::HT_PER_CELL);
-          constexpr size_t total = C::HT_PER_CELL * sizeof(double);
-          constexpr size_t chunk = 16384;
-          for (size_t off = (size_t)lane * chunk; off < total; off += 32 * chunk) {
-            const uint32_t bytes = (uint32_t)((total - off) < chunk ? (total - off) : chunk);
-            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(base + off), "r"(bytes) : "memory");
-          }
-        }
-      }
-#endif
     }
   } else {
     constexpr int FULL_WARPS = C::MT - (C::TPW - 1) * C::WARPS;  // warps that own TPW tiles
