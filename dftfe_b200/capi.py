@@ -76,7 +76,7 @@ EXPORTED_SYMBOLS = [
     "dftfe_b200_nccl_unique_id", "dftfe_b200_comm_init", "dftfe_b200_comm_init_loopback",
     "dftfe_b200_set_nonlocal", "dftfe_b200_set_cell_hamiltonian", "dftfe_b200_set_cell_hamiltonian_host",
     "dftfe_b200_strided_copy_to_block", "dftfe_b200_strided_copy_from_block", "dftfe_b200_strided_block_scale",
-    "dftfe_b200_set_cell_hamiltonian_kpt", "dftfe_b200_set_nonlocal_kpt", "dftfe_b200_reinit_kpoint_spin_index", "dftfe_b200_rotate_spectrum_split",
+    "dftfe_b200_set_cell_hamiltonian_kpt", "dftfe_b200_set_nonlocal_kpt", "dftfe_b200_compute_cell_hamiltonian", "dftfe_b200_reinit_kpoint_spin_index", "dftfe_b200_rotate_spectrum_split",
     "dftfe_b200_update_ghost_values", "dftfe_b200_accumulate_add_locally_owned", "dftfe_b200_zero_out_ghosts",
     "dftfe_b200_constraints_distribute", "dftfe_b200_constraints_distribute_slave_to_master",
     "dftfe_b200_constraints_set_zero", "dftfe_b200_hx", "dftfe_b200_hx_cheby", "dftfe_b200_cheb_filter",
@@ -252,6 +252,22 @@ class Operator:
             H = torch.from_numpy(Hc).cuda(self.device)
         _check(self.lib.dftfe_b200_set_cell_hamiltonian_kpt(self.h, C.c_int32(kPointIndex), C.c_int32(spinIndex),
                                                             _dptr(H)))
+
+    def computeHamiltonianMatrix(self, shapeValues, vEffJxW, gradIntegral, cellKScale=None, extPotCorr=None, out=None):
+        """hamMatrixKernelLDA (hamiltonianMatrixCalculatorFlattenedDevice.cc:63-117) as a DMMA GEMM.
+        shapeValues [n, nq], vEffJxW [nC, nq], gradIntegral [n, n] (shared, scaled by cellKScale [nC]) or [nC, n, n];
+        all torch CUDA float64.  Returns H [nC, n, n] in the reference layout."""
+        import torch
+
+        n, nq = shapeValues.shape
+        nC = vEffJxW.shape[0]
+        per_cell = gradIntegral.dim() == 3
+        H = out if out is not None else torch.empty((nC, n, n), dtype=torch.float64, device=shapeValues.device)
+        _check(self.lib.dftfe_b200_compute_cell_hamiltonian(
+            self.h, C.c_int32(nq), _dptr(shapeValues), _dptr(vEffJxW), _dptr(gradIntegral), C.c_int32(int(per_cell)),
+            _dptr(cellKScale) if cellKScale is not None else None, _dptr(extPotCorr) if extPotCorr is not None else None,
+            _dptr(H)))
+        return H
 
     def reinitkPointSpinIndex(self, kPointIndex: int, spinIndex: int = 0):
         """kohnShamDFTOperatorDevice.cc:1033-1058: switch to a stored (k-point, spin) Hamiltonian set and to the

@@ -261,6 +261,7 @@ struct dftfe_b200_ctx {
   dftfe_b200::DevBuf<float> mpXsp, mpSp, mpBlockSp;
   dftfe_b200::DevBuf<double> mpDp;
   dftfe_b200::DevBuf<float> arTmpF;
+  dftfe_b200::DevBuf<double> hamNt, hamW;         // cell-Hamiltonian assembly: padded N^T and weights
   dftfe_b200::DevBuf<int> devInfo;
   dftfe_b200::DevBuf<double> cusolverWork;
   double a0 = 0, bLow = 0, bUp = 0;
@@ -339,6 +340,11 @@ bool dmma_rotation_usable(int N, int Nout, int ldq, int ldo);
 int launch_xq(dftfe_b200_ctx *ctx, const double *X, int N, int64_t rows, const double *Qrm, int ldq, int Nout,
               double *Out, int ldo);
 int launch_transpose_square(dftfe_b200_ctx *ctx, const double *in, double *out, int N);
+
+// ham_assembly.cu
+int compute_cell_hamiltonian(dftfe_b200_ctx *ctx, int nq, const double *shapeValues, const double *vEffJxW,
+                             const double *gradIntegral, int gradPerCell, const double *cellKScale,
+                             const double *extPotCorr, double *H);
 
 // mixed_precision.cu
 int xtx_mixed_impl(dftfe_b200_ctx *ctx, const double *X, int N, double *S);

@@ -486,6 +486,15 @@ int dftfe_b200_reinit_kpoint_spin_index(dftfe_b200_ctx *ctx, int32_t kpoint_inde
   return 0;
 }
 
+int dftfe_b200_compute_cell_hamiltonian(dftfe_b200_ctx *ctx, int32_t n_quad, const double *shape_values_d,
+                                        const double *veff_jxw_d, const double *grad_integral_d,
+                                        int32_t grad_integral_per_cell, const double *cell_kscale_d,
+                                        const double *ext_pot_corr_d, double *H_out_d) {
+  DB_CTX(ctx);
+  return compute_cell_hamiltonian(ctx, n_quad, shape_values_d, veff_jxw_d, grad_integral_d, grad_integral_per_cell,
+                                  cell_kscale_d, ext_pot_corr_d, H_out_d);
+}
+
 int dftfe_b200_set_cell_hamiltonian_host(dftfe_b200_ctx *ctx, const double *H_h) {
   DB_CTX(ctx);
   const size_t count = (size_t)ctx->nC * ctx->n * ctx->n * ctx->cm;

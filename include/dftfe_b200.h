@@ -185,6 +185,19 @@ int dftfe_b200_set_cell_hamiltonian_kpt(dftfe_b200_ctx *ctx, int32_t kpoint_inde
  * switch the operator to a stored Hamiltonian set and to the projector set of that k-point; no data moves. */
 int dftfe_b200_reinit_kpoint_spin_index(dftfe_b200_ctx *ctx, int32_t kpoint_index, int32_t spin_index);
 
+/* Cell-level Hamiltonian assembly, the step that runs every SCF right before this path
+ * (hamMatrixKernelLDA, src/dftOperator/hamiltonianMatrixCalculatorFlattenedDevice.cc:63-117, called from
+ * computeHamiltonianMatricesAllkpt): H_c(I,J) = 1/2 K_c(I,J) + sum_q vEffJxW[c,q] N_I(q) N_J(q) (+ ext_pot_corr),
+ * as a batched FP64 tensor-core GEMM.  shape_values_d: the reference's shapeFunctionValues, n x n_quad
+ * (mem[I*n_quad + q]); veff_jxw_d: nC x n_quad; grad_integral_d: cellShapeFunctionGradientIntegral, nC x n x n when
+ * grad_integral_per_cell, else ONE n x n matrix scaled per cell by cell_kscale_d[c] (NULL = 1; affine cells of a
+ * uniform or 2:1-refined mesh); ext_pot_corr_d: nC x n x n or NULL.  H_out_d: nC x n x n in the reference layout,
+ * ready for dftfe_b200_set_cell_hamiltonian[_kpt].  Real build, LDA-type local potential (no GGA gradient terms). */
+int dftfe_b200_compute_cell_hamiltonian(dftfe_b200_ctx *ctx, int32_t n_quad, const double *shape_values_d,
+                                        const double *veff_jxw_d, const double *grad_integral_d,
+                                        int32_t grad_integral_per_cell, const double *cell_kscale_d,
+                                        const double *ext_pot_corr_d, double *H_out_d);
+
 /* ---- distributed-vector primitives (MultiVector / MPICommunicatorP2P) ---- */
 int dftfe_b200_update_ghost_values(dftfe_b200_ctx *ctx, double *x_d, int32_t ncols);
 int dftfe_b200_accumulate_add_locally_owned(dftfe_b200_ctx *ctx, double *x_d, int32_t ncols);

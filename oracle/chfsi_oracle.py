@@ -738,3 +738,20 @@ def solve_no_rr(ranks, X, block: int, cheb_order: int, bounds, number_passes: in
         cholesky_gram_schmidt(ranks, X)
     for rp, x in zip(ranks, X):
         x[:rp.M] *= rp.invSqrtMass[:rp.M][:, None]
+
+
+def compute_cell_hamiltonian(shape_values, veff_jxw, grad_integral, cell_kscale=None, ext_pot_corr=None):
+    """hamMatrixKernelLDA (src/dftOperator/hamiltonianMatrixCalculatorFlattenedDevice.cc:63-117):
+    H_c(I,J) = 1/2 K_c(I,J) + sum_q vEffJxW[c,q] N_I(q) N_J(q) (+ correction), q summed in ascending order."""
+    N = np.asarray(shape_values)               # [n, nq]
+    w = np.asarray(veff_jxw)                   # [nC, nq]
+    H = np.einsum("cq,iq,jq->cij", w, N, N, optimize=True)
+    K = np.asarray(grad_integral)
+    if K.ndim == 2:
+        ks = np.ones(w.shape[0]) if cell_kscale is None else np.asarray(cell_kscale)
+        H += 0.5 * ks[:, None, None] * K[None, :, :]
+    else:
+        H += 0.5 * K
+    if ext_pot_corr is not None:
+        H += ext_pot_corr
+    return H

@@ -115,3 +115,46 @@ def test_adaptive_multirank_solve_ex1_like(capi):
     # total band energy of the 15 states (the reference's 1e-6 Ha/atom energy criterion, 2 atoms here)
     assert abs(out[0][0][2][0].sum() - ev_ref.sum()) / 2 < 1e-6
     assert np.abs(out[0][1] - res_ref).max() < 1e-6
+
+
+@pytest.mark.parametrize("p,adaptive", [(6, False), (3, True), (4, True)])
+def test_cell_hamiltonian_assembly(capi, p, adaptive):
+    """H_c = 1/2 K_c + N diag(vEff JxW) N^T as a DMMA GEMM, against the oracle's statement of
+    hamMatrixKernelLDA and against the generator's own cell matrices; then used by the operator."""
+    from oracle import chfsi_oracle as O
+    from tests.helpers import make_problem, random_global, scatter_to_ranks
+
+    if adaptive:
+        mesh, ranks = make_adaptive_problem(p, (3, 3, 3), 1.4)
+    else:
+        mesh, ranks = make_problem(p, (2, 3, 2), 1.2, (True, True, False))
+    rp = ranks[0]
+    ref = mesh.ref
+    from dftfe_b200.femesh import gaussian_wells_potential
+    pot = gaussian_wells_potential(mesh.box, periodic=mesh.periodic)
+    cells = mesh.owned_cells(0)
+    origin, scale = mesh.cell_origin_scale(cells)
+    xyz = origin[:, None, :] + scale[:, None, None] * ref.quad_xyz[None, :, :]
+    vjxw = pot(xyz) * ref.quad_w[None, :] * (scale ** 3)[:, None]          # vEff * JxW, [nC, nq]
+    shape = np.ascontiguousarray(ref.phi3.T)                               # N_I(q), [n, nq]
+    H_ref = O.compute_cell_hamiltonian(shape, vjxw, ref.K3, cell_kscale=scale)
+    assert _relerr(H_ref, rp.H) < 1e-12      # the generator's einsum is the same quantity
+    op = capi.Operator(rp, 32)
+    H_d = op.computeHamiltonianMatrix(_dev(shape), _dev(vjxw), _dev(ref.K3), cellKScale=_dev(scale))
+    got = H_d.cpu().numpy()
+    assert _relerr(got, H_ref) < 1e-13
+    assert np.array_equal(got, np.transpose(got, (0, 2, 1)))   # mirrored tiles: exactly symmetric
+    # per-cell K and a correction matrix
+    Kc = np.ascontiguousarray(scale[:, None, None] * ref.K3[None, :, :])
+    corr = 0.01 * H_ref
+    H2 = op.computeHamiltonianMatrix(_dev(shape), _dev(vjxw), _dev(Kc), extPotCorr=_dev(corr)).cpu().numpy()
+    assert _relerr(H2, 1.01 * H_ref) < 1e-13
+    # feed it to the operator
+    op.set_cell_hamiltonian(H_d)
+    X = [field_on_nodes(rp, 32) * rp.sqrtMass[:, None]]
+    src, dst = [X[0].copy()], [np.zeros_like(X[0])]
+    O.HX(ranks, src, dst, False, 1.0)
+    s_d, d_d = _dev(X[0]), torch.zeros(rp.M + rp.G, 32, dtype=torch.float64, device="cuda")
+    op.HX(s_d, d_d, False, 1.0)
+    assert _relerr(d_d.cpu().numpy()[:rp.M], dst[0][:rp.M]) < 1e-12
+    op.close()
