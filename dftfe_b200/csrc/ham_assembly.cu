@@ -204,12 +204,12 @@ __global__ void __launch_bounds__(THREADS, 1) ham_assemble_kernel(HamArgs g) {
 #pragma unroll
           for (int e = 0; e < 2; ++e) {
             const int J = tj * TN + wn * 32 + j * 8 + (lane & 3) * 2 + e;
-            if (J >= n) continue;
+            if (J >= n || J > I) continue;  // lower triangle only (diagonal tiles included): H_c comes out exactly symmetric
             const size_t ij = (size_t)I * n + J;
             double v = acc[i][j][e] + 0.5 * ks_ * Kc[ij];
             if (Ec) v += Ec[ij];
             Hc[ij] = v;
-            if (ti != tj) Hc[(size_t)J * n + I] = v;  // symmetric: K and the correction matrix are symmetric too
+            if (I != J) Hc[(size_t)J * n + I] = v;  // K and the correction matrix are symmetric too
           }
         }
       }
