@@ -76,7 +76,7 @@ EXPORTED_SYMBOLS = [
     "dftfe_b200_nccl_unique_id", "dftfe_b200_comm_init", "dftfe_b200_comm_init_loopback",
     "dftfe_b200_set_nonlocal", "dftfe_b200_set_cell_hamiltonian", "dftfe_b200_set_cell_hamiltonian_host",
     "dftfe_b200_strided_copy_to_block", "dftfe_b200_strided_copy_from_block", "dftfe_b200_strided_block_scale",
-    "dftfe_b200_set_cell_hamiltonian_kpt", "dftfe_b200_set_nonlocal_kpt", "dftfe_b200_compute_cell_hamiltonian", "dftfe_b200_reinit_kpoint_spin_index", "dftfe_b200_rotate_spectrum_split",
+    "dftfe_b200_set_cell_hamiltonian_kpt", "dftfe_b200_set_nonlocal_kpt", "dftfe_b200_compute_cell_hamiltonian", "dftfe_b200_compute_density", "dftfe_b200_reinit_kpoint_spin_index", "dftfe_b200_rotate_spectrum_split",
     "dftfe_b200_update_ghost_values", "dftfe_b200_accumulate_add_locally_owned", "dftfe_b200_zero_out_ghosts",
     "dftfe_b200_constraints_distribute", "dftfe_b200_constraints_distribute_slave_to_master",
     "dftfe_b200_constraints_set_zero", "dftfe_b200_hx", "dftfe_b200_hx_cheby", "dftfe_b200_cheb_filter",
@@ -268,6 +268,17 @@ class Operator:
             _dptr(cellKScale) if cellKScale is not None else None, _dptr(extPotCorr) if extPotCorr is not None else None,
             _dptr(H)))
         return H
+
+    def computeRhoFromPSI(self, X, occupations, shapeValues):
+        """computeRhoFromPSI (src/dft/densityCalculator.cc:39-560): rho [nC, nq] from X [M, N] (FE basis)."""
+        import torch
+
+        occ = _np(occupations, np.float64)
+        n, nq = shapeValues.shape
+        rho = torch.empty((self.prob.nCells, nq), dtype=torch.float64, device=shapeValues.device)
+        _check(self.lib.dftfe_b200_compute_density(self.h, _dptr(X), C.c_int32(X.shape[1]), _ptr(occ), C.c_int32(nq),
+                                                   _dptr(shapeValues), _dptr(rho)))
+        return rho
 
     def reinitkPointSpinIndex(self, kPointIndex: int, spinIndex: int = 0):
         """kohnShamDFTOperatorDevice.cc:1033-1058: switch to a stored (k-point, spin) Hamiltonian set and to the

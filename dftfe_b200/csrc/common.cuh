@@ -261,7 +261,8 @@ struct dftfe_b200_ctx {
   dftfe_b200::DevBuf<float> mpXsp, mpSp, mpBlockSp;
   dftfe_b200::DevBuf<double> mpDp;
   dftfe_b200::DevBuf<float> arTmpF;
-  dftfe_b200::DevBuf<double> hamNt, hamW;         // cell-Hamiltonian assembly: padded N^T and weights
+  dftfe_b200::DevBuf<double> hamNt, hamW;
+  dftfe_b200::DevBuf<double> denNf, denOcc, denF, denBlock;  // density: tiled shape values, occupancies, block         // cell-Hamiltonian assembly: padded N^T and weights
   dftfe_b200::DevBuf<int> devInfo;
   dftfe_b200::DevBuf<double> cusolverWork;
   double a0 = 0, bLow = 0, bUp = 0;
@@ -316,7 +317,7 @@ int ghost_zero(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx);
 int launch_row_scale(dftfe_b200_ctx *ctx, double *x, int64_t rows, int ncols, int ldx, double alpha,
                      const double *rowScale);
 int launch_block_copy_from_full(dftfe_b200_ctx *ctx, const double *X, int N, int j0, double *blk, int ncols,
-                                int64_t rows, const double *rowScale);
+                                int64_t rows, const double *rowScale, int ldBlk = -1);
 int launch_block_copy_to_full(dftfe_b200_ctx *ctx, double *X, int N, int j0, const double *blk, int ncols,
                               int64_t rows, const double *rowScale);
 int launch_orphan_first_touch(dftfe_b200_ctx *ctx, const double *src, double *dst, int ncols, int ldx,
@@ -345,6 +346,10 @@ int launch_transpose_square(dftfe_b200_ctx *ctx, const double *in, double *out, 
 int compute_cell_hamiltonian(dftfe_b200_ctx *ctx, int nq, const double *shapeValues, const double *vEffJxW,
                              const double *gradIntegral, int gradPerCell, const double *cellKScale,
                              const double *extPotCorr, double *H);
+
+// density.cu
+int compute_density(dftfe_b200_ctx *ctx, const double *X, int N, const double *occ_h, int nq, const double *shapeValues,
+                    double *rho);
 
 // mixed_precision.cu
 int xtx_mixed_impl(dftfe_b200_ctx *ctx, const double *X, int N, double *S);

@@ -585,16 +585,19 @@ int launch_row_scale(dftfe_b200_ctx *ctx, double *x, int64_t rows, int ncols, in
 }
 
 int launch_block_copy_from_full(dftfe_b200_ctx *ctx, const double *X, int N, int j0, double *blk, int ncols,
-                                int64_t rows, const double *rowScale) {
+                                int64_t rows, const double *rowScale, int ldBlk) {
   if (rows == 0) return 0;
+  if (ldBlk <= 0) ldBlk = ncols;
   ProfScope ps(ctx, "block_copy");
-  if (launch_stream_rows(ctx, X + j0, N, nullptr, blk, ncols, ncols, rows, rowScale, 1.0, true)) {
-  } else if (vec_ok(X + j0, ncols, N) && vec_ok(blk, ncols, ncols) && !ctx->force_scalar_row_kernels)
-    strided_copy_vec_kernel<<<grid_rows(ctx, strided_copy_vec_kernel, rows), 256, 0, ctx->stream>>>(X + j0, N, blk, ncols, ncols, rows,
-                                                                          rowScale);
-  else
+  if (launch_stream_rows(ctx, X + j0, N, nullptr, blk, ldBlk, ncols, rows, rowScale, 1.0, true)) {
+  } else if (ldBlk == ncols) {
     block_from_full_kernel<<<grid_for(ctx, rows * ncols), 256, 0, ctx->stream>>>(X, N, j0, blk, ncols, rows,
                                                                                 rowScale);
+  } else {  // odd shapes with a padded block: row by row through the generic 2-D copy
+    DB_CHECK(rowScale == nullptr, "block copy: a row scale needs an even column count when the block is padded");
+    DB_CUDA(cudaMemcpy2DAsync(blk, (size_t)ldBlk * sizeof(double), X + j0, (size_t)N * sizeof(double),
+                              (size_t)ncols * sizeof(double), (size_t)rows, cudaMemcpyDeviceToDevice, ctx->stream));
+  }
   DB_CUDA(cudaGetLastError());
   return 0;
 }

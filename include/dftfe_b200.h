@@ -198,6 +198,16 @@ int dftfe_b200_compute_cell_hamiltonian(dftfe_b200_ctx *ctx, int32_t n_quad, con
                                         int32_t grad_integral_per_cell, const double *cell_kscale_d,
                                         const double *ext_pot_corr_d, double *H_out_d);
 
+/* Electron density from the wavefunctions, the step right after solve() in the SCF (computeRhoFromPSI,
+ * src/dft/densityCalculator.cc:39-560; densityCalculatorDeviceKernels.cc:35-140):
+ *   rho_out_d[c*n_quad + q] = sum_i occupations_h[i] * |sum_I N_I(q) X[row(c,I), i]|^2
+ * over the owned cells, with the ghost update and constraint distribute the reference applies per block.  X_d:
+ * row-major M x N in the FE basis (what solve() returns); occupations_h: N weights (partial occupancy x k-point
+ * weight x spin factor); shape_values_d: n x n_quad as in compute_cell_hamiltonian (n_quad <= 1152).  One fused
+ * kernel per block (gather + FP64 tensor-core GEMM + square + weighted sum); rho only, no grad rho.  FE orders 1-6. */
+int dftfe_b200_compute_density(dftfe_b200_ctx *ctx, const double *X_d, int32_t N, const double *occupations_h,
+                               int32_t n_quad, const double *shape_values_d, double *rho_out_d);
+
 /* ---- distributed-vector primitives (MultiVector / MPICommunicatorP2P) ---- */
 int dftfe_b200_update_ghost_values(dftfe_b200_ctx *ctx, double *x_d, int32_t ncols);
 int dftfe_b200_accumulate_add_locally_owned(dftfe_b200_ctx *ctx, double *x_d, int32_t ncols);

@@ -755,3 +755,20 @@ def compute_cell_hamiltonian(shape_values, veff_jxw, grad_integral, cell_kscale=
     if ext_pot_corr is not None:
         H += ext_pot_corr
     return H
+
+
+def compute_rho_from_psi(ranks, X, occupations, shape_values):
+    """computeRhoFromPSI (src/dft/densityCalculator.cc:39-560): per rank rho[c, q] = sum_i f_i |psi_i(x_q)|^2 with
+    psi_i(x_q) = sum_I N_I(q) x_i[row(c, I)] after updateGhostValues + distribute (:296-303).  X: list of
+    (M+G) x N arrays in the FE basis (ghost / constrained rows are overwritten)."""
+    N = np.asarray(shape_values)                       # [n, nq]
+    f = np.asarray(occupations, dtype=np.float64)
+    X = [x.copy() for x in X]
+    update_ghost_values(ranks, X)
+    out = []
+    for rp, x in zip(ranks, X):
+        distribute(rp, x)
+        Xc = x[rp.cellLocalDofs]                       # [nC, n, Ncols]
+        psi = np.einsum("iq,cik->cqk", N, Xc, optimize=True)
+        out.append(np.einsum("k,cqk->cq", f, np.abs(psi) ** 2, optimize=True))
+    return out

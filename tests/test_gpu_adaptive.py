@@ -158,3 +158,55 @@ def test_cell_hamiltonian_assembly(capi, p, adaptive):
     op.HX(s_d, d_d, False, 1.0)
     assert _relerr(d_d.cpu().numpy()[:rp.M], dst[0][:rp.M]) < 1e-12
     op.close()
+
+
+@pytest.mark.parametrize("p,N,B,cplx,nranks", [(3, 15, 15, False, 1), (6, 64, 32, False, 1), (3, 24, 8, True, 1),
+                                               (4, 48, 32, False, 2)])
+def test_density_from_wavefunctions(capi, p, N, B, cplx, nranks):
+    """rho(q) = sum_i f_i |psi_i(q)|^2, fused gather + DMMA + square + weighted sum, against the
+    oracle's statement of computeRhoFromPSI; ragged blocks, complex vectors and two ranks included."""
+    from oracle import chfsi_oracle as O
+    from tests.helpers import make_problem, random_global, scatter_to_ranks
+
+    if cplx:
+        mesh, ranks = make_problem(p, (3, 2, 2), 1.2, (True, True, True), nranks=nranks, kpoint=(0.2, 0.1, -0.3))
+    elif nranks > 1:
+        mesh, ranks = make_problem(p, (4, 3, 2), 1.2, (True, True, False), nranks=nranks)
+    else:
+        mesh, ranks = make_adaptive_problem(p, (3, 3, 3) if p < 6 else (2, 2, 2), 1.4, half=(p == 6))
+    ref = mesh.ref
+    shape = np.ascontiguousarray(ref.phi3.T)
+    occ = np.linspace(2.0, 0.1, N)
+    if cplx or nranks > 1:
+        X = scatter_to_ranks(ranks, random_global(mesh, N, seed=4, cplx=cplx), zero_constrained=False)
+    else:
+        X = [field_on_nodes(rp, N, seed=2) for rp in ranks]
+        for rp, x in zip(ranks, X):
+            x[rp.M:] = 0
+    rho_ref = O.compute_rho_from_psi(ranks, X, occ, shape)
+
+    def rank_fn(r):
+        rp = ranks[r]
+        op = capi.Operator(rp, B, use_torch_stream=False, complex=cplx)
+        if nranks > 1:
+            op.comm_init_loopback(81, r, nranks)
+        rho = op.computeRhoFromPSI(_dev(X[r][:rp.M]), occ, _dev(shape))
+        op.sync()
+        out = rho.cpu().numpy()
+        op.close()
+        return out
+
+    if nranks == 1:
+        outs = [rank_fn(0)]
+    else:
+        outs = [None] * nranks
+        th = [threading.Thread(target=lambda r=r: outs.__setitem__(r, rank_fn(r))) for r in range(nranks)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join(timeout=300)
+    for r in range(nranks):
+        assert outs[r] is not None
+        assert _relerr(outs[r], rho_ref[r]) < 1e-12
+    # integral of rho = sum of occupations for M-orthonormal vectors is a property of solve(); here just positivity
+    assert outs[0].min() >= 0.0
