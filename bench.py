@@ -351,7 +351,38 @@ def main_ours(args):
                 ntile = N // 128
                 proj_flops = 2.0 * (ntile * (ntile + 1) // 2) * 2 * 128 * 128 * rp.M  # X^T X + X^T H X lower tiles
                 rot_flops = 2.0 * rp.M * N * N
-                scf = {"wall_s": wall, "device_ms": s0.elapsed_time(s1), "n_states": N,
+                # the two steps either side of solve() in the SCF, timed on their own
+                extra = {}
+                try:
+                    shape = torch.from_numpy(np.ascontiguousarray(ref.phi3.T)).to(dev)
+                    vq = pot(origin[:, None, :] + ref.quad_xyz[None, :, :]) * ref.quad_w[None, :]
+                    vq_d = torch.from_numpy(vq).to(dev)
+                    K_d = torch.from_numpy(ref.K3).to(dev)
+                    Hs = torch.empty((rp.nCells, rp.n, rp.n), dtype=torch.float64, device=dev)
+                    op.computeHamiltonianMatrix(shape, vq_d, K_d, out=Hs)
+                    h0, h1, h2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+                    h0.record(stream)
+                    op.computeHamiltonianMatrix(shape, vq_d, K_d, out=Hs)
+                    h1.record(stream)
+                    op.set_cell_hamiltonian(Hs)
+                    h2.record(stream)
+                    sync_all()
+                    del Hs
+                    occ = np.where(np.arange(N) < N // 2, 2.0, 0.0)
+                    rho = op.computeRhoFromPSI(X, occ, shape)
+                    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    d0.record(stream)
+                    rho = op.computeRhoFromPSI(X, occ, shape)
+                    d1.record(stream)
+                    sync_all()
+                    nq = shape.shape[1]
+                    extra = {"ham_assembly_ms": h0.elapsed_time(h1), "ham_retile_ms": h1.elapsed_time(h2),
+                             "density_ms": d0.elapsed_time(d1),
+                             "density_tflops": 2.0 * rp.n * nq * rp.nCells * N / (d0.elapsed_time(d1) * 1e-3) / 1e12,
+                             "n_quad": int(nq), "rho_sum": float(rho.sum().item())}
+                except Exception as e:  # noqa: BLE001
+                    extra = {"extra_error": repr(e)}
+                scf = {"wall_s": wall, "device_ms": s0.elapsed_time(s1), "n_states": N, **extra,
                        "eig_min": float(eig[0]), "eig_max": float(eig[-1]), "residual_max": float(np.max(res)),
                        "cell_matvec_ms": cm_ms, "projection_ms": pj_ms, "rotation_ms": rt_ms,
                        "projection_tflops": proj_flops / (pj_ms * 1e-3) / 1e12 if pj_ms > 0 else None,
