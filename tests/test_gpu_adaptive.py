@@ -210,3 +210,26 @@ def test_density_from_wavefunctions(capi, p, N, B, cplx, nranks):
         assert _relerr(outs[r], rho_ref[r]) < 1e-12
     # integral of rho = sum of occupations for M-orthonormal vectors is a property of solve(); here just positivity
     assert outs[0].min() >= 0.0
+
+
+def test_density_integrates_to_electron_count(capi):
+    """Known answer tying solve() and the density kernel together: for M-orthonormal wavefunctions the density
+    sampled at the GLL nodes and integrated with the GLL weights gives exactly sum_i f_i (the lumped mass matrix IS
+    that quadrature on a periodic structured mesh)."""
+    from oracle import chfsi_oracle as O
+    from tests.helpers import make_problem, random_global, scatter_to_ranks
+
+    p, N, B = 4, 32, 32
+    mesh, ranks = make_problem(p, (3, 3, 2), 1.3, (True, True, True))
+    rp = ranks[0]
+    op = capi.Operator(rp, B)
+    op.set_cell_hamiltonian(rp.H)
+    solver = capi.ChebyshevSolver(op)
+    Xd = _dev(scatter_to_ranks(ranks, random_global(mesh, N, seed=9), zero_constrained=False)[0][:rp.M])
+    solver.solve(Xd, isFirstFilteringCall=True, chebyshevOrder=8, reuseLanczos=True)
+    occ = np.where(np.arange(N) < 10, 2.0, 0.0) + np.where(np.arange(N) == 10, 0.7, 0.0)
+    shape_gll = np.eye(rp.n)                                    # N_I at the GLL nodes
+    rho = op.computeRhoFromPSI(Xd, occ, _dev(shape_gll)).cpu().numpy()
+    total = float((rho * mesh.ref.mass_gll[None, :]).sum())
+    assert abs(total - occ.sum()) < 1e-10 * occ.sum()
+    op.close()
