@@ -396,8 +396,21 @@ def main_ours(args):
         # ---- end to end: X in pinned host memory, copies inside the timed region
         e2e = None
         if not args.no_e2e:
-            Xh = torch.empty((rp.M, N), dtype=torch.float64, pin_memory=True)
-            Xh.copy_(X)
+            # every rank needs M*N*8 bytes of pinned host memory; agree on success before entering the collective path
+            Xh = None
+            try:
+                Xh = torch.empty((rp.M, N), dtype=torch.float64, pin_memory=True)
+                Xh.copy_(X)
+            except Exception as e:  # noqa: BLE001
+                Xh = None
+                e2e = {"error": "pinned host allocation failed: " + repr(e)[:200]}
+            ok = torch.tensor([1 if Xh is not None else 0], dtype=torch.int32, device=dev)
+            if world > 1:
+                dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if int(ok.item()) == 0:
+                Xh = None
+                e2e = e2e or {"error": "pinned host allocation failed on another rank"}
+        if not args.no_e2e and Xh is not None:
             del X
             torch.cuda.empty_cache()
             n_e2e = max(1, min(args.steps, 3))
