@@ -295,3 +295,86 @@ def test_adaptive_mesh_multirank_matches_single_rank(nranks):
     for rp, x in zip(rn, Xn):
         for k, v in zip(key(rp.nodeXYZ[:rp.M]), x[:rp.M]):
             assert np.abs(ref[k] - v).max() < 1e-11 * scale
+
+
+def test_mixed_precision_restatements_are_fp32_perturbations():
+    """The oracle's statements of the reference's mixed-precision routines: FP64-exact where the reference keeps
+    FP64 (diagonal blocks, blocks beyond the core states), FP32-accurate elsewhere."""
+    mesh, ranks = make_problem(2, (4, 4, 4), 1.0, (True, True, False), nranks=2)
+    N, B = 24, 8
+    X = scatter_to_ranks(ranks, random_global(mesh, N, seed=1), loewdin=True)
+    S, Sm = O.xtx(ranks, X), O.xtx_mixed(ranks, X, B)
+    for j in range(0, N, B):
+        assert np.abs(S[j:j + B, j:j + B] - Sm[j:j + B, j:j + B]).max() < 1e-13 * np.abs(S).max()
+    d = np.abs(S - Sm).max() / np.abs(S).max()
+    assert 0.0 < d < 1e-6
+    H = O.xthx(ranks, [x.copy() for x in X], B)
+    Hm = O.xthx_mixed(ranks, [x.copy() for x in X], B, 2 * B)
+    assert np.abs(H[2 * B:, 2 * B:] - Hm[2 * B:, 2 * B:]).max() < 1e-12 * np.abs(H).max()
+    assert 0.0 < np.abs(H - Hm).max() / np.abs(H).max() < 1e-5
+    Q = np.linalg.qr(np.random.default_rng(0).normal(size=(N, N)))[0]
+    Xa, Xb, Xc = ([x.copy() for x in X] for _ in range(3))
+    O.subspace_rotation_rr_mixed(ranks, Xa, Q)
+    O.subspace_rotation_cgs_mixed(ranks, Xb, Q, B)
+    for rp, xa, xb, x in zip(ranks, Xa, Xb, X):
+        exact = x[:rp.M] @ Q
+        for y in (xa, xb):
+            e = np.abs(y[:rp.M] - exact).max() / np.abs(exact).max()
+            assert 0.0 < e < 1e-5
+    # FP32 ghost payloads perturb the filter at FP32 level and only through the ghosts
+    blk = [x[:, :B].copy() for x in X]
+    f64 = O.chebyshev_filter_device_state(ranks, blk, 6, 10.0, 90.0, -2.0)
+    f32 = O.chebyshev_filter_device_state(ranks, blk, 6, 10.0, 90.0, -2.0, mixed_prec=True)
+    e = max(np.abs(a - b)[:rp.M].max() for a, b, rp in zip(f64, f32, ranks)) / max(np.abs(a).max() for a in f64)
+    assert 0.0 < e < 1e-5
+    # single rank: no ghosts, the flag must change nothing
+    mesh1, r1 = make_problem(2, (4, 4, 4), 1.0, (True, True, False))
+    b1 = [scatter_to_ranks(r1, random_global(mesh1, B, seed=1), loewdin=True)[0]]
+    a = O.chebyshev_filter_device_state(r1, b1, 6, 10.0, 90.0, -2.0)
+    b = O.chebyshev_filter_device_state(r1, b1, 6, 10.0, 90.0, -2.0, mixed_prec=True)
+    assert np.array_equal(a[0], b[0])
+
+
+def test_spectrum_split_and_no_rr_statements():
+    mesh, ranks = make_problem(3, (3, 3, 2), 1.4, (True, True, True), nranks=2)
+    N, B, Noc = 16, 8, 8
+    Xg = random_global(mesh, N, seed=4)
+    bounds = (-3.0, 2.0, 70.0)
+    ev_full, res_full = O.solve(ranks, scatter_to_ranks(ranks, Xg, zero_constrained=False), B, 8, bounds)
+    Xs = scatter_to_ranks(ranks, Xg, zero_constrained=False)
+    ev, res, XF = O.solve(ranks, Xs, B, 8, bounds, n_core=Noc)
+    assert np.abs(ev - ev_full[Noc:]).max() < 1e-10 and np.abs(res - res_full[Noc:]).max() < 1e-8
+    # X stays an M-orthonormal basis of the filtered subspace; XFrac are Ritz vectors inside it
+    G = sum((x[:rp.M] * rp.sqrtMass[:rp.M, None]).T @ (x[:rp.M] * rp.sqrtMass[:rp.M, None]) for x, rp in zip(Xs, ranks))
+    assert np.abs(G - np.eye(N)).max() < 1e-10
+    Gf = sum((f[:rp.M] * rp.sqrtMass[:rp.M, None]).T @ (f[:rp.M] * rp.sqrtMass[:rp.M, None]) for f, rp in zip(XF, ranks))
+    assert np.abs(Gf - np.eye(N - Noc)).max() < 1e-10
+    # solveNoRR: orthonormal output, same span as filter + CGS applied twice
+    Xn = scatter_to_ranks(ranks, Xg, zero_constrained=False)
+    O.solve_no_rr(ranks, Xn, B, 6, bounds, 2)
+    Gn = sum((x[:rp.M] * rp.sqrtMass[:rp.M, None]).T @ (x[:rp.M] * rp.sqrtMass[:rp.M, None]) for x, rp in zip(Xn, ranks))
+    assert np.abs(Gn - np.eye(N)).max() < 1e-10
+
+
+def test_cell_hamiltonian_and_density_statements():
+    """hamMatrixKernelLDA / computeRhoFromPSI restatements: the assembled matrices equal the generator's, and the
+    GLL-sampled density of M-orthonormal vectors integrates to the electron count."""
+    from dftfe_b200.femesh import gaussian_wells_potential
+
+    mesh, ranks = make_problem(3, (3, 2, 2), 1.3, (True, True, True), nranks=2)
+    ref = mesh.ref
+    pot = gaussian_wells_potential(mesh.box, periodic=mesh.periodic)
+    for r, rp in enumerate(ranks):
+        cells = mesh.owned_cells(r)
+        origin, scale = mesh.cell_origin_scale(cells)
+        vjxw = pot(origin[:, None, :] + ref.quad_xyz[None, :, :]) * ref.quad_w[None, :]
+        H = O.compute_cell_hamiltonian(np.ascontiguousarray(ref.phi3.T), vjxw, ref.K3)
+        assert np.abs(H - rp.H).max() < 1e-13 * np.abs(rp.H).max()
+    N = 6
+    X = scatter_to_ranks(ranks, random_global(mesh, N, seed=2), loewdin=True)
+    O.cholesky_gram_schmidt(ranks, X)                       # Loewdin basis, orthonormal
+    Xfe = [x * rp.invSqrtMass[:, None] for x, rp in zip(X, ranks)]
+    occ = np.array([2.0, 2.0, 2.0, 1.3, 0.4, 0.0])
+    rho = O.compute_rho_from_psi(ranks, Xfe, occ, np.eye(ref.n))
+    total = sum(float((r_ * ref.mass_gll[None, :]).sum()) for r_ in rho)
+    assert abs(total - occ.sum()) < 1e-11 * occ.sum()
