@@ -21,17 +21,19 @@ def _free_port():
         return s.getsockname()[1]
 
 
-def _exchange_forward(rp, x):
-    """updateGhostValues over torch.distributed using ONLY the pattern arrays."""
+def _exchange_forward(rp, x, payload=np.float64):
+    """updateGhostValues over torch.distributed using ONLY the pattern arrays.  payload=float32: the
+    chebMixedPrec exchange (kohnShamDFTOperatorDevice.cc:3899-3915)."""
     reqs, bufs = [], []
     off = 0
+    tdt = torch.float64 if payload == np.float64 else torch.float32
     for t, cnt in zip(rp.targetProcIds, rp.numOwnedForTargets):
-        send = torch.from_numpy(np.ascontiguousarray(x[rp.ownedLocalIdxForTargets[off:off + cnt]]))
+        send = torch.from_numpy(np.ascontiguousarray(x[rp.ownedLocalIdxForTargets[off:off + cnt]].astype(payload)))
         reqs.append(dist.isend(send, int(t)))
         off += cnt
     for g, p in enumerate(rp.ghostProcIds):
         s, e = rp.ghostLocalRanges[2 * g], rp.ghostLocalRanges[2 * g + 1]
-        buf = torch.empty((e - s, x.shape[1]), dtype=torch.float64)
+        buf = torch.empty((e - s, x.shape[1]), dtype=tdt)
         reqs.append(dist.irecv(buf, int(p)))
         bufs.append((s, e, buf))
     for r in reqs:
@@ -40,22 +42,33 @@ def _exchange_forward(rp, x):
         x[rp.M + s:rp.M + e] = buf.numpy()
 
 
-def _exchange_reverse(rp, x):
-    """accumulateAddLocallyOwned."""
+def _exchange_reverse(rp, x, payload=np.float64):
+    """accumulateAddLocallyOwned.  payload=float32: the boundary rows are accumulated in FP32 on a float copy
+    and copied back (kohnShamDFTOperatorDevice.cc:3953-3990)."""
     reqs, bufs = [], []
+    tdt = torch.float64 if payload == np.float64 else torch.float32
     for g, p in enumerate(rp.ghostProcIds):
         s, e = rp.ghostLocalRanges[2 * g], rp.ghostLocalRanges[2 * g + 1]
-        reqs.append(dist.isend(torch.from_numpy(np.ascontiguousarray(x[rp.M + s:rp.M + e])), int(p)))
+        reqs.append(dist.isend(torch.from_numpy(np.ascontiguousarray(x[rp.M + s:rp.M + e].astype(payload))), int(p)))
     off = 0
     for t, cnt in zip(rp.targetProcIds, rp.numOwnedForTargets):
-        buf = torch.empty((cnt, x.shape[1]), dtype=torch.float64)
+        buf = torch.empty((cnt, x.shape[1]), dtype=tdt)
         reqs.append(dist.irecv(buf, int(t)))
         bufs.append((off, cnt, buf))
         off += cnt
     for r in reqs:
         r.wait()
-    for off, cnt, buf in bufs:
-        np.add.at(x, rp.ownedLocalIdxForTargets[off:off + cnt], buf.numpy())
+    if payload == np.float64:
+        for off, cnt, buf in bufs:
+            np.add.at(x, rp.ownedLocalIdxForTargets[off:off + cnt], buf.numpy())
+    else:
+        bnd = np.unique(rp.ownedLocalIdxForTargets)
+        acc = x[bnd].astype(np.float32)
+        pos = {int(r): i for i, r in enumerate(bnd)}
+        for off, cnt, buf in bufs:
+            idx = np.array([pos[int(r)] for r in rp.ownedLocalIdxForTargets[off:off + cnt]])
+            np.add.at(acc, idx, buf.numpy())
+        x[bnd] = acc
 
 
 def _worker(rank, world, port, q):
@@ -79,7 +92,19 @@ def _worker(rank, world, port, q):
     d[rp.M:] = 0
     d[:rp.M] *= rp.invSqrtMass[:rp.M, None]
     err = float(np.abs(d - dst_ref[rank]).max() / np.abs(dst_ref[rank]).max())
-    q.put((rank, err))
+    # the same bare operator with FP32 payloads both ways against the oracle's chebMixedPrec statement
+    src32 = [x.copy() for x in Xall]
+    dst32 = [np.zeros_like(x) for x in Xall]
+    O.HXCheby(ranks, src32, dst32, mixed_prec=True)
+    s, d = Xall[rank].copy(), np.zeros_like(Xall[rank])
+    _exchange_forward(rp, s, np.float32)
+    O.distribute(rp, s)
+    O.compute_local_hamiltonian_times_x(rp, s, d)
+    O.distribute_slave_to_master(rp, d)
+    _exchange_reverse(rp, d, np.float32)
+    d[rp.M:] = 0
+    err32 = float(np.abs(d - dst32[rank]).max() / np.abs(dst32[rank]).max())
+    q.put((rank, max(err, err32)))
     dist.barrier()
     dist.destroy_process_group()
 
