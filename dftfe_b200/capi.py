@@ -63,7 +63,7 @@ class SolveParams(C.Structure):
         ("use_mixed_prec_subspace_rot_rr", C.c_int32),
         ("num_core_wfc_xthx", C.c_int32),
         ("n_core_states", C.c_int32),
-        ("reserved", C.c_int32),
+        ("use_mixed_prec_commun_only_xthx_cgs_o", C.c_int32),
         ("first_scf_scaling", C.c_double),
     ]
 
@@ -353,11 +353,11 @@ class Operator:
                                                         C.c_double(a), C.c_double(b), C.c_double(a0),
                                                         C.c_int32(int(mixedPrec))))
 
-    def XtX(self, X, S, mixedPrec: bool = False):
+    def XtX(self, X, S, mixedPrec: int = 0):
         """fillParallelOverlapMat[MixedPrec]Scalapack (linearAlgebraOperationsDevice.cc:3078-3240, 3543-3798)."""
         _check(self.lib.dftfe_b200_xtx(self.h, _dptr(X), C.c_int32(X.shape[1]), _dptr(S), C.c_int32(int(mixedPrec))))
 
-    def XtHX(self, X, Hp, Noc: int = 0, mixedPrec: bool = False):
+    def XtHX(self, X, Hp, Noc: int = 0, mixedPrec: int = 0):
         """kohnShamDFTOperatorDevice.cc:4001-4157; mixedPrec + Noc: XtHXMixedPrecOverlapComputeCommun (:4550-5080)."""
         _check(self.lib.dftfe_b200_xthx(self.h, _dptr(X), C.c_int32(X.shape[1]), C.c_int32(Noc), _dptr(Hp),
                                         C.c_int32(int(mixedPrec))))
@@ -447,7 +447,7 @@ class ChebyshevSolver:
         N = X.shape[1]
         ncore = 0 if XFrac is None else N - XFrac.shape[1]
         mp = set(mixedPrec)
-        assert mp <= {"cheby", "cgs_o", "cgs_sr", "xthx", "rot_rr"}
+        assert mp <= {"cheby", "cgs_o", "cgs_sr", "xthx", "rot_rr", "comm_only"}
         p = SolveParams(chebyshev_order=chebyshevOrder, wfc_block=0,
                         is_first_filtering_call=int(isFirstFilteringCall),
                         reuse_lanczos_upper_bound=int(reuseLanczos), is_first_scf=int(isFirstScf),
@@ -457,7 +457,8 @@ class ChebyshevSolver:
                         use_mixed_prec_cgs_o=int("cgs_o" in mp), use_mixed_prec_cgs_sr=int("cgs_sr" in mp),
                         use_mixed_prec_xthx_spectrum_split=int("xthx" in mp),
                         use_mixed_prec_subspace_rot_rr=int("rot_rr" in mp), num_core_wfc_xthx=numCoreWfcXtHX,
-                        n_core_states=ncore, reserved=0, first_scf_scaling=firstScfScaling)
+                        n_core_states=ncore, use_mixed_prec_commun_only_xthx_cgs_o=int("comm_only" in mp),
+                        first_scf_scaling=firstScfScaling)
         nev = N - ncore
         eig = np.empty(nev)
         res = np.empty(nev)

@@ -352,8 +352,8 @@ int compute_density(dftfe_b200_ctx *ctx, const double *X, int N, const double *o
                     double *rho);
 
 // mixed_precision.cu
-int xtx_mixed_impl(dftfe_b200_ctx *ctx, const double *X, int N, double *S);
-int xthx_mixed_impl(dftfe_b200_ctx *ctx, const double *X, int N, int Noc, double *Hp);
+int xtx_mixed_impl(dftfe_b200_ctx *ctx, const double *X, int N, double *S, bool commOnly = false);
+int xthx_mixed_impl(dftfe_b200_ctx *ctx, const double *X, int N, int Noc, double *Hp, bool commOnly = false);
 int rotate_mixed_impl(dftfe_b200_ctx *ctx, double *X, int N, const double *Q, bool qColMajor, int mode);
 
 // high-level pieces (solver.cu)

@@ -104,6 +104,24 @@ __global__ void merge_projham_kernel(const double *__restrict__ G, const float *
   }
 }
 
+// FP64 column block [j, j+Bc) of the lower triangle (G, column-major N x N) -> FP32 copy of its rows below the
+// diagonal block (sp) and the diagonal block itself (dp: Bw x N as in merge_overlap_kernel); skipDiag = 0 sends the
+// whole block to sp (copyFromOverlapMatBlockToDPSPBlocks, linearAlgebraOperationsDevice.cc:4435-4447)
+__global__ void split_dp_sp_kernel(const double *__restrict__ G, int N, int j, int Bc, int Bw, int skipDiag,
+                                   double *__restrict__ dp, float *__restrict__ sp) {
+  const int D = N - j;
+  const int64_t total = (int64_t)D * Bc;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int r = idx % D, c = idx / D;  // row j + r, column j + c
+    const double v = G[(int64_t)(j + r) + (int64_t)(j + c) * N];
+    if (skipDiag && r < Bc)
+      dp[r + (int64_t)(j + c) * Bw] = v;
+    else
+      sp[(int64_t)(j + r) + (int64_t)(j + c) * N] = (float)v;
+  }
+}
+
 inline int grid_for(const dftfe_b200_ctx *ctx, int64_t work) {
   return (int)std::max<int64_t>(1, std::min<int64_t>((work + 255) / 256, (int64_t)ctx->num_sms * 8));
 }
@@ -119,9 +137,47 @@ int to_float(dftfe_b200_ctx *ctx, const double *in, int64_t ldi, float *out, int
 }  // namespace
 
 // S = X^T X with FP64 diagonal blocks and FP32 off-diagonal blocks; full symmetric result, all-reduced
-int xtx_mixed_impl(dftfe_b200_ctx *ctx, const double *X, int N, double *S) {
+int xtx_mixed_impl(dftfe_b200_ctx *ctx, const double *X, int N, double *S, bool commOnly) {
   const int Bw = std::min(ctx->B, N);
   const int64_t M = ctx->M;
+  if (commOnly) {
+    // FP64 arithmetic, FP32 only on the wire (fillParallelOverlapMatMixedPrecCommunScalapackAsyncComputeCommun,
+    // linearAlgebraOperationsDevice.cc:4233-4608): the off-diagonal blocks are rounded to FP32 for the all-reduce
+    DB_TRY(ctx->mpSp.alloc((size_t)N * N));
+    DB_TRY(ctx->mpDp.alloc((size_t)N * Bw));
+    DB_TRY(ctx->denseW.alloc((size_t)N * N));
+    double *G = ctx->denseW.p;
+    DB_CUBLAS(cublasSetStream(ctx->cublas, ctx->stream));
+    DB_CUDA(cudaMemsetAsync(G, 0, (size_t)N * N * sizeof(double), ctx->stream));
+    DB_CUDA(cudaMemsetAsync(ctx->mpSp.p, 0, (size_t)N * N * sizeof(float), ctx->stream));
+    DB_CUDA(cudaMemsetAsync(ctx->mpDp.p, 0, (size_t)N * Bw * sizeof(double), ctx->stream));
+    if (M > 0) {
+      if (!ctx->use_cublas_dense && dmma_projection_usable(ctx, N, N, N, 0, 0, N, N)) {
+        DB_TRY(launch_xty(ctx, X, N, 0, X, N, 0, N, N, 0, 0, true, G, N));
+      } else {
+        const double one = 1.0, zero = 0.0;
+        for (int j = 0; j < N; j += Bw) {
+          const int Bc = std::min(Bw, N - j);
+          ProfScope ps(ctx, "projection");
+          DB_CUBLAS(cublasDgemm(ctx->cublas, CUBLAS_OP_N, CUBLAS_OP_T, N - j, Bc, (int)M, &one, X + j, N, X + j, N,
+                                &zero, G + j + (size_t)j * N, N));
+        }
+      }
+    }
+    for (int j = 0; j < N; j += Bw) {
+      const int Bc = std::min(Bw, N - j);
+      ctx->launches += 1;
+      split_dp_sp_kernel<<<grid_for(ctx, (int64_t)(N - j) * Bc), 256, 0, ctx->stream>>>(G, N, j, Bc, Bw, 1, ctx->mpDp.p,
+                                                                                         ctx->mpSp.p);
+    }
+    DB_CUDA(cudaGetLastError());
+    DB_TRY(allreduce_sum(ctx, ctx->mpDp.p, (size_t)N * Bw));
+    DB_TRY(allreduce_sum_f32(ctx, ctx->mpSp.p, (size_t)N * N));
+    ctx->launches += 1;
+    merge_overlap_kernel<<<grid_for(ctx, (int64_t)N * N), 256, 0, ctx->stream>>>(ctx->mpDp.p, ctx->mpSp.p, N, Bw, S);
+    DB_CUDA(cudaGetLastError());
+    return 0;
+  }
   DB_TRY(ctx->mpXsp.alloc((size_t)std::max<int64_t>(M, 1) * N));
   DB_TRY(ctx->mpSp.alloc((size_t)N * N));
   DB_TRY(ctx->mpDp.alloc((size_t)N * Bw));
@@ -156,17 +212,17 @@ int xtx_mixed_impl(dftfe_b200_ctx *ctx, const double *X, int N, double *S) {
 }
 
 // Hp = X^T (H~ X): column blocks [j, j+Bc) with j + Bc <= Noc entirely in FP32, the others FP64
-int xthx_mixed_impl(dftfe_b200_ctx *ctx, const double *X, int N, int Noc, double *Hp) {
+int xthx_mixed_impl(dftfe_b200_ctx *ctx, const double *X, int N, int Noc, double *Hp, bool commOnly) {
   const int Bw = std::min(ctx->B, N);
   const int64_t M = ctx->M;
-  DB_TRY(ctx->mpXsp.alloc((size_t)std::max<int64_t>(M, 1) * N));
+  DB_TRY(ctx->mpXsp.alloc(commOnly ? 1 : (size_t)std::max<int64_t>(M, 1) * N));
   DB_TRY(ctx->mpSp.alloc((size_t)N * N));
   DB_TRY(ctx->mpBlockSp.alloc((size_t)std::max<int64_t>(M, 1) * Bw));
   DB_TRY(ctx->denseW.alloc((size_t)N * N));
   double *G = ctx->denseW.p;
   DB_CUDA(cudaMemsetAsync(ctx->mpSp.p, 0, (size_t)N * N * sizeof(float), ctx->stream));
   DB_CUDA(cudaMemsetAsync(G, 0, (size_t)N * N * sizeof(double), ctx->stream));
-  DB_TRY(to_float(ctx, X, N, ctx->mpXsp.p, N, N, M));
+  if (!commOnly) DB_TRY(to_float(ctx, X, N, ctx->mpXsp.p, N, N, M));
   const double one = 1.0, zero = 0.0;
   const float onef = 1.0f, zerof = 0.0f;
   for (int j = 0; j < N; j += Bw) {
@@ -174,7 +230,7 @@ int xthx_mixed_impl(dftfe_b200_ctx *ctx, const double *X, int N, int Noc, double
     DB_TRY(apply_H_to_columns(ctx, X, N, j, Bc));  // blockY = H~ X[:, j:j+Bc]  (M x Bc)
     if (M == 0) continue;
     DB_CUBLAS(cublasSetStream(ctx->cublas, ctx->stream));
-    if (j + Bc <= Noc) {
+    if (j + Bc <= Noc && !commOnly) {
       DB_TRY(to_float(ctx, ctx->blockY.p, Bc, ctx->mpBlockSp.p, Bc, Bc, M));
       ProfScope ps(ctx, "projection_fp32");
       DB_CUBLAS(cublasSgemm(ctx->cublas, CUBLAS_OP_N, CUBLAS_OP_T, D, Bc, (int)M, &onef, ctx->mpXsp.p + j, N,
@@ -186,6 +242,20 @@ int xthx_mixed_impl(dftfe_b200_ctx *ctx, const double *X, int N, int Noc, double
       DB_CUBLAS(cublasDgemm(ctx->cublas, CUBLAS_OP_N, CUBLAS_OP_T, D, Bc, (int)M, &one, X + j, N, ctx->blockY.p, Bc,
                             &zero, G + j + (size_t)j * N, N));
     }
+  }
+  if (commOnly) {
+    // FP64 blocks that end inside the core states travel as FP32 (XtHXMixedPrecCommunOverlapComputeCommun,
+    // kohnShamDFTOperatorDevice.cc:5082-5536: copyValueType1ArrToValueType2Arr before the all-reduce)
+    for (int j = 0; j < N; j += Bw) {
+      const int Bc = std::min(Bw, N - j);
+      if (j + Bc > Noc) break;
+      ctx->launches += 2;
+      split_dp_sp_kernel<<<grid_for(ctx, (int64_t)(N - j) * Bc), 256, 0, ctx->stream>>>(G, N, j, Bc, Bw, 0, nullptr,
+                                                                                         ctx->mpSp.p);
+      DB_CUDA(cudaMemset2DAsync(G + j + (size_t)j * N, (size_t)N * sizeof(double), 0, (size_t)(N - j) * sizeof(double),
+                                (size_t)Bc, ctx->stream));
+    }
+    DB_CUDA(cudaGetLastError());
   }
   DB_TRY(allreduce_sum(ctx, G, (size_t)N * N));
   DB_TRY(allreduce_sum_f32(ctx, ctx->mpSp.p, (size_t)N * N));

@@ -691,6 +691,7 @@ static int rr_cplx(dftfe_b200_ctx *ctx, double *X, int N, double *eig_h, bool cg
 // Which pieces run in mixed precision (dftParameters::useMixedPrec*, all gated by useMixedPrecOverall) and the
 // number of "core" states whose XtHX blocks may be FP32 (numCoreWfcXtHX / Noc).
 struct RRFlags {
+  bool commOnly = false;    // useMixedPrecCommunOnlyXTHXCGSO: FP64 arithmetic, FP32 all-reduce payloads
   bool mpOverlap = false;   // useMixedPrecCGS_O
   bool mpCgsRot = false;    // useMixedPrecCGS_SR
   bool mpXtHX = false;      // useMixedPrecXTHXSpectrumSplit
@@ -698,11 +699,13 @@ struct RRFlags {
   int nCore = 0;
 };
 
-static int overlap_any(dftfe_b200_ctx *ctx, const double *X, int N, double *S, bool mixed) {
-  return (mixed && !ctx->cplx) ? xtx_mixed_impl(ctx, X, N, S) : xtx_impl(ctx, X, N, S);
+static int overlap_any(dftfe_b200_ctx *ctx, const double *X, int N, double *S, bool mixed, bool commOnly = false) {
+  return (mixed && !ctx->cplx) ? xtx_mixed_impl(ctx, X, N, S, commOnly) : xtx_impl(ctx, X, N, S);
 }
-static int projham_any(dftfe_b200_ctx *ctx, const double *X, int N, double *Hp, bool mixed, int nCore) {
-  return (mixed && !ctx->cplx && nCore > 0) ? xthx_mixed_impl(ctx, X, N, nCore, Hp) : xthx_impl(ctx, X, N, Hp);
+static int projham_any(dftfe_b200_ctx *ctx, const double *X, int N, double *Hp, bool mixed, int nCore,
+                       bool commOnly = false) {
+  return (mixed && !ctx->cplx && nCore > 0) ? xthx_mixed_impl(ctx, X, N, nCore, Hp, commOnly)
+                                            : xthx_impl(ctx, X, N, Hp);
 }
 
 static int identity_to(dftfe_b200_ctx *ctx, double *A, int N) {
@@ -723,7 +726,7 @@ static int rr_gep(dftfe_b200_ctx *ctx, double *X, int N, double *eig_h, const RR
   DB_TRY(ctx->eigDev.alloc(N));
   double *S = ctx->denseA.p, *Hp = ctx->denseB.p;
   const double one = 1.0;
-  DB_TRY(overlap_any(ctx, X, N, S, f.mpOverlap));
+  DB_TRY(overlap_any(ctx, X, N, S, f.mpOverlap, f.commOnly));
   DB_TRY(dense_cholesky(ctx, S, N));  // S lower <- L
   DB_TRY(xthx_impl(ctx, X, N, Hp));
   DB_CUBLAS(cublasSetStream(ctx->cublas, ctx->stream));
@@ -751,7 +754,7 @@ static int cgs_orthogonalise(dftfe_b200_ctx *ctx, double *X, int N, const RRFlag
   DB_TRY(ctx->denseB.alloc(nn));
   double *S = ctx->denseA.p, *U = ctx->denseB.p;
   const double one = 1.0;
-  DB_TRY(overlap_any(ctx, X, N, S, f.mpOverlap));
+  DB_TRY(overlap_any(ctx, X, N, S, f.mpOverlap, f.commOnly));
   DB_TRY(dense_cholesky(ctx, S, N));
   DB_TRY(identity_to(ctx, U, N));  // L^-T as a column-major matrix: solve L^T U = I
   DB_CUBLAS(cublasSetStream(ctx->cublas, ctx->stream));
@@ -768,7 +771,7 @@ static int cgs_rr(dftfe_b200_ctx *ctx, double *X, int N, double *eig_h, const RR
   DB_TRY(ctx->eigDev.alloc(N));
   DB_TRY(cgs_orthogonalise(ctx, X, N, f));
   double *Hp = ctx->denseB.p;
-  DB_TRY(projham_any(ctx, X, N, Hp, f.mpXtHX, f.nCore));
+  DB_TRY(projham_any(ctx, X, N, Hp, f.mpXtHX, f.nCore, f.commOnly));
   DB_TRY(dense_eigh(ctx, Hp, N, ctx->eigDev.p));
   DB_TRY(rotate_impl(ctx, X, N, Hp, true, f.mpRRRot ? 2 : 0));
   DB_CUDA(cudaMemcpyAsync(eig_h, ctx->eigDev.p, N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
@@ -808,7 +811,7 @@ static int rr_spectrum_split(dftfe_b200_ctx *ctx, double *X, double *XFrac, int 
   } else {
     DB_TRY(cgs_orthogonalise(ctx, X, N, f));
     Hp = ctx->denseB.p;
-    DB_TRY(projham_any(ctx, X, N, Hp, f.mpXtHX, Noc));
+    DB_TRY(projham_any(ctx, X, N, Hp, f.mpXtHX, Noc, f.commOnly));
     DB_TRY(dense_eigh(ctx, Hp, N, ctx->eigDev.p));
   }
   DB_TRY(rotate_into(ctx, X, N, Hp, Noc, N - Noc, XFrac));
@@ -1014,6 +1017,7 @@ static int solve_impl(dftfe_b200_ctx *ctx, double *X, double *XFrac, int N, cons
   f.mpXtHX = mp && p->use_mixed_prec_xthx_spectrum_split;
   f.mpRRRot = mp && p->use_mixed_prec_subspace_rot_rr;
   f.nCore = p->num_core_wfc_xthx;
+  f.commOnly = p->use_mixed_prec_commun_only_xthx_cgs_o != 0;
 
   // X <- M^1/2 X (solver .cc:358-363) fused into the block copy; filter; copy back (:376-526)
   DB_TRY(filter_all_impl(ctx, X, N, (int)order, ctx->bLow, ctx->bUp, ctx->a0, ctx->sqrtM.p,
@@ -1163,7 +1167,8 @@ static int to_row_major_cplx(dftfe_b200_ctx *ctx, double *S_d, int N) {
 
 int dftfe_b200_xtx(dftfe_b200_ctx *ctx, const double *X_d, int32_t N, double *S_d, int32_t mixed_prec) {
   DB_CTX(ctx);
-  DB_TRY(overlap_any(ctx, X_d, N, S_d, mixed_prec != 0));
+  DB_CHECK(mixed_prec >= 0 && mixed_prec <= 2, "xtx: mixed_prec must be 0, 1 or 2");
+  DB_TRY(overlap_any(ctx, X_d, N, S_d, mixed_prec != 0, mixed_prec == 2));
   return ctx->cplx ? to_row_major_cplx(ctx, S_d, N) : 0;
 }
 
@@ -1171,7 +1176,8 @@ int dftfe_b200_xthx(dftfe_b200_ctx *ctx, const double *X_d, int32_t N, int32_t n
                     int32_t mixed_prec) {
   DB_CTX(ctx);
   DB_CHECK(n_core >= 0 && n_core <= N, "xthx: n_core (%d) must be in [0, N]", n_core);
-  DB_TRY(projham_any(ctx, X_d, N, Hp_d, mixed_prec != 0, n_core));
+  DB_CHECK(mixed_prec >= 0 && mixed_prec <= 2, "xthx: mixed_prec must be 0, 1 or 2");
+  DB_TRY(projham_any(ctx, X_d, N, Hp_d, mixed_prec != 0, n_core, mixed_prec == 2));
   return ctx->cplx ? to_row_major_cplx(ctx, Hp_d, N) : 0;
 }
 

@@ -95,7 +95,9 @@ typedef struct {
    * > 0: only the top N - n_core_states eigenpairs are returned, X_frac_d receives the rotated states and
    * X_d is left orthonormalised but unrotated */
   int32_t n_core_states;
-  int32_t reserved;
+  /* useMixedPrecCommunOnlyXTHXCGSO: the mixed X^T X / X^T H X variants keep FP64 arithmetic and use FP32 only
+   * for the all-reduce payloads (fillParallelOverlapMatMixedPrecCommun..., XtHXMixedPrecCommun...) */
+  int32_t use_mixed_prec_commun_only_xthx_cgs_o;
   double first_scf_scaling;      /* chebyshevFilterPolyDegreeFirstScfScalingFactor (1.34)  */
 } dftfe_b200_solve_params;
 
@@ -267,13 +269,16 @@ int dftfe_b200_cheb_filter_all_host(dftfe_b200_ctx *ctx, double *X_h, int32_t N,
 /* S = X^H X, all-reduced; full symmetric / Hermitian N x N written to S_d (row-major; complex: S[i][j] =
  * sum_m conj(X[m,i]) X[m,j], interleaved)
  * (fillParallelOverlapMatScalapack, linearAlgebraOperationsDevice.cc:3078-3240).
- * mixed_prec (real build): diagonal B x B blocks FP64, the blocks below them FP32 with an FP32 all-reduce
- * (fillParallelOverlapMatMixedPrecScalapack, :3543-3798). */
+ * mixed_prec = 1 (real build): diagonal B x B blocks FP64, the blocks below them FP32 with an FP32 all-reduce
+ * (fillParallelOverlapMatMixedPrecScalapack, :3543-3798); mixed_prec = 2: FP64 arithmetic everywhere, FP32 only on
+ * the wire for the off-diagonal blocks (fillParallelOverlapMatMixedPrecCommunScalapackAsyncComputeCommun,
+ * :4233-4608). */
 int dftfe_b200_xtx(dftfe_b200_ctx *ctx, const double *X_d, int32_t N, double *S_d, int32_t mixed_prec);
 /* Hp = X^T (M^-1/2 H M^-1/2) X, all-reduced, full symmetric N x N
  * (operatorDFTDeviceClass::XtHX, kohnShamDFTOperatorDevice.cc:4001-4157).
- * mixed_prec with n_core = Noc > 0 (real build): column blocks ending inside the first Noc states are
- * computed and all-reduced in FP32 (XtHXMixedPrecOverlapComputeCommun, :4550-5080). */
+ * mixed_prec = 1 with n_core = Noc > 0 (real build): column blocks ending inside the first Noc states are
+ * computed and all-reduced in FP32 (XtHXMixedPrecOverlapComputeCommun, :4550-5080); mixed_prec = 2: computed in
+ * FP64, all-reduced in FP32 (XtHXMixedPrecCommunOverlapComputeCommun, :5082-5536). */
 int dftfe_b200_xthx(dftfe_b200_ctx *ctx, const double *X_d, int32_t N, int32_t n_core, double *Hp_d,
                     int32_t mixed_prec);
 /* X <- X Q with Q row-major N x N on device (subspaceRotationScalapack,

@@ -448,10 +448,12 @@ def rayleigh_ritz(ranks, X, block: int):
 # mixed-precision projections / rotations and spectrum splitting (real build)
 # --------------------------------------------------------------------------
 
-def xtx_mixed(ranks, X, block: int) -> np.ndarray:
+def xtx_mixed(ranks, X, block: int, comm_only: bool = False) -> np.ndarray:
     """fillParallelOverlapMatMixedPrecScalapack (linearAlgebraOperationsDevice.cc:3543-3798): per column block
     the diagonal ``block x block`` part in FP64, the rows below it as an FP32 GEMM on an FP32 copy of X
-    (:3641-3675) and an FP32 sum over ranks; only the lower triangle is filled, mirrored here."""
+    (:3641-3675) and an FP32 sum over ranks; only the lower triangle is filled, mirrored here.
+    comm_only = fillParallelOverlapMatMixedPrecCommunScalapackAsyncComputeCommun (:4233-4608): every rank's
+    partial block is computed in FP64 and only rounded to FP32 for the sum over ranks."""
     N = X[0].shape[1]
     S = np.zeros((N, N))
     Xo = _owned(ranks, X)
@@ -463,13 +465,16 @@ def xtx_mixed(ranks, X, block: int) -> np.ndarray:
         for x, xs in zip(Xo, Xs):
             dp = dp + x[:, j:j + B].T @ x[:, j:j + B]
             if N - j - B > 0:
-                sp = sp + xs[:, j + B:].T @ xs[:, j:j + B]
+                if comm_only:
+                    sp = sp + (x[:, j + B:].T @ x[:, j:j + B]).astype(np.float32)
+                else:
+                    sp = sp + xs[:, j + B:].T @ xs[:, j:j + B]
         S[j:j + B, j:j + B] = dp
         S[j + B:, j:j + B] = sp
     return np.tril(S) + np.tril(S, -1).T
 
 
-def xthx_mixed(ranks, X, block: int, n_core: int) -> np.ndarray:
+def xthx_mixed(ranks, X, block: int, n_core: int, comm_only: bool = False) -> np.ndarray:
     """XtHXMixedPrecOverlapComputeCommun (kohnShamDFTOperatorDevice.cc:4550-5080): column blocks that end inside
     the first ``n_core`` states are computed entirely in FP32 (FP32 copy of X times the FP32-rounded H~X block,
     FP32 sum over ranks), the others in FP64."""
@@ -482,7 +487,10 @@ def xthx_mixed(ranks, X, block: int, n_core: int) -> np.ndarray:
         if j + B <= n_core:
             acc = np.zeros((N - j, B), dtype=np.float32)
             for x, h in zip(Xo, Ho):
-                acc = acc + x[:, j:].astype(np.float32).T @ h[:, j:j + B].astype(np.float32)
+                if comm_only:   # XtHXMixedPrecCommunOverlapComputeCommun (:5082-5536): FP64 GEMM, FP32 on the wire
+                    acc = acc + (x[:, j:].T @ h[:, j:j + B]).astype(np.float32)
+                else:
+                    acc = acc + x[:, j:].astype(np.float32).T @ h[:, j:j + B].astype(np.float32)
         else:
             acc = 0
             for x, h in zip(Xo, Ho):

@@ -129,6 +129,19 @@ def test_mixed_precision_projections_and_rotations(capi):
     assert _relerr(H_gpu[Noc:, Noc:], H64[Noc:, Noc:]) < 1e-12      # FP64 blocks beyond the core states
     assert np.abs(H_gpu[:, :Noc] - H64[:, :Noc]).max() > 0.0
 
+    # FP64 arithmetic, FP32 on the wire only (useMixedPrecCommunOnlyXTHXCGSO)
+    op.XtX(X_d, out, mixedPrec=2)
+    S_c = out.cpu().numpy()
+    assert _relerr(S_c, O.xtx_mixed(ranks, X, B, comm_only=True)) < 2e-7
+    for j in range(0, N, B):
+        assert _relerr(S_c[j:j + B, j:j + B], S64[j:j + B, j:j + B]) < 1e-13
+    assert 0.0 < np.abs(S_c - S64).max() / np.abs(S64).max() < 1e-7
+    op.XtHX(X_d, out, Noc=Noc, mixedPrec=2)
+    H_c = out.cpu().numpy()
+    assert _relerr(H_c, O.xthx_mixed(ranks, [x.copy() for x in X], B, Noc, comm_only=True)) < 2e-7
+    assert _relerr(H_c[Noc:, Noc:], H64[Noc:, Noc:]) < 1e-12
+    assert 0.0 < np.abs(H_c - H64).max() / np.abs(H64).max() < 1e-7
+
     rng = np.random.default_rng(1)
     Q = np.linalg.qr(rng.normal(size=(N, N)))[0]
     U = np.triu(rng.normal(size=(N, N))) / np.sqrt(N) + np.eye(N)
