@@ -139,6 +139,27 @@ def fp64_peak_tflops():
         (37.0, "fallback: 64 FP64 FMA/clk/SM x 148 SMs x 1.965 GHz")
 
 
+def ncu_dram_traffic_per_launch():
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the persistent cell kernel, from the committed
+    `ncu --set full` summary of this same workload (profiles/); None when the file is missing."""
+    path = os.path.join(ROOT, "profiles", "r01_cell_matvec_persistent_ncu_summary.csv")
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    try:
+        import csv
+
+        rd = wr = None
+        for row in csv.reader(open(path)):
+            if row and row[0] == "dram__bytes_read.sum":
+                rd = [float(v) * scale[row[1]] for v in row[2:]]
+            if row and row[0] == "dram__bytes_write.sum":
+                wr = [float(v) * scale[row[1]] for v in row[2:]]
+        if rd and wr:
+            return float(np.mean([a + b for a, b in zip(rd, wr)]))
+    except Exception:
+        pass
+    return None
+
+
 # ---------------------------------------------------------------------------
 def cpu_reference_run(args, steps, warmup, degree_sample):
     """C oracle (port of the reference CPU path) on all host cores: one block of BLOCK
@@ -317,7 +338,9 @@ def main_ours(args):
         achieved = flops_per_launch / avg_launch_s / 1e12
         peak, peak_src = fp64_peak_tflops()
         roofline = {"bound": "tensor", "kernel": "cell_matvec_kernel<343> (FP64 DMMA.8x8x4)", "achieved": achieved,
-                    "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                    "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": ncu_dram_traffic_per_launch(),
+                    "traffic_unit": "bytes per launch, ncu dram read+write (profiles/r01_cell_matvec_persistent_ncu_summary.csv)"
+                                    "; algorithmic minimum 1.39e9",
                     "peak_source": peak_src, "launches_timed": int(k_launches),
                     "avg_launch_ms": avg_launch_s * 1e3, "kernel_share_of_step": k_ms / ms_roof,
                     "timed_in": roofline_pass,
