@@ -433,9 +433,6 @@ __device__ __forceinline__ void mma_warp_items_full(const double *__restrict__ H
       const int i = (warp + t * C::WARPS) * 8 + (lane >> 2);
       fr[t] = (i < NODES) ? rowsS[buf * NODES + i] : 0u;
     }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[buf]);
-
     // next item's first A fragments fly while this item's epilogue runs
     if (item + (int)gridDim.x < nItems) prime(item + gridDim.x);
 
@@ -459,7 +456,9 @@ __device__ __forceinline__ void mma_warp_items_full(const double *__restrict__ H
         double ca, cb;
         epilogue_coeffs(fr[t], ep, ca, cb);
         double *drow = dst + (size_t)r * ldx + col0 + (lane & 3) * 2;
-        const double *srow = src + (size_t)r * ldx + col0 + (lane & 3) * 2;
+        // src[row(c,i), tile] is row i of the X tile still sitting in shared memory (the buffer is released
+        // after the epilogue): the a*src term of a first touch costs no global read
+        const double *srow = Xs + buf * P::XBUF + i * LDS + (lane & 3) * 2;
         double2 d[NT], sv[NT];
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
@@ -476,6 +475,9 @@ __device__ __forceinline__ void mma_warp_items_full(const double *__restrict__ H
       }
     }
 #endif
+    // release the X tile to the producer (its rows were the epilogue's src operand)
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[buf]);
   }
 }
 
@@ -545,9 +547,6 @@ __device__ __forceinline__ void mma_one_item(const double *__restrict__ Ht, cons
     const int i = (warp + t * C::WARPS) * 8 + (lane >> 2);
     fr[t] = (i < NODES) ? rowsS[buf * NODES + i] : 0u;
   }
-  __syncwarp();
-  if (lane == 0) mbar_arrive(&empty[buf]);
-
   // next item's first A fragments fly while this item's epilogue runs
   if (item + (int)gridDim.x < nItems) {
     const int ncell = cells[(item + gridDim.x) / nColTiles];
@@ -567,7 +566,7 @@ __device__ __forceinline__ void mma_one_item(const double *__restrict__ Ht, cons
       epilogue_coeffs(fr[t], ep, ca, cb);
       const int cl = col0 + (lane & 3) * 2;
       double *drow = dst + (size_t)r * ldx + cl;
-      const double *srow = src + (size_t)r * ldx + cl;
+      const double *srow = Xs + buf * P::XBUF + i * LDS + (lane & 3) * 2;  // src rows = the X tile (see above)
       double2 d[NTL], sv[NTL];
 #pragma unroll
       for (int nt = 0; nt < NTL; ++nt) {
@@ -584,6 +583,9 @@ __device__ __forceinline__ void mma_one_item(const double *__restrict__ Ht, cons
       }
     }
   }
+  // release the X tile to the producer (its rows were the epilogue's src operand)
+  __syncwarp();
+  if (lane == 0) mbar_arrive(&empty[buf]);
 }
 
 // Column tiling of a block of `ncols` columns: nColTiles = ceil(ncols / 32) tiles; the ceil(ncols / 8) n8 tiles
