@@ -319,10 +319,11 @@ class Operator:
                                                        C.c_int32(which)))
 
     # ---- operatorDFTDeviceClass -------------------------------------------
-    def HX(self, src, dst, scaleFlag: bool, scalar: float, doUnscalingSrc: bool = True):
-        """kohnShamDFTOperatorDevice.cc:3765-3860."""
+    def HX(self, src, dst, scaleFlag: bool, scalar: float, doUnscalingSrc: bool = True, singlePrecCommun: bool = False):
+        """kohnShamDFTOperatorDevice.cc:3765-3860; singlePrecCommun: the FP32-exchange overload (:3609-3761)."""
         _check(self.lib.dftfe_b200_hx(self.h, _dptr(src), _dptr(dst), C.c_int32(src.shape[1]), C.c_int32(int(scaleFlag)),
-                                      C.c_double(scalar), C.c_int32(int(doUnscalingSrc))))
+                                      C.c_double(scalar), C.c_int32(int(doUnscalingSrc)),
+                                      C.c_int32(int(singlePrecCommun))))
 
     def HXCheby(self, src, dst, mixPrecFlag: bool = False):
         """kohnShamDFTOperatorDevice.cc:3874-3997; mixPrecFlag: FP32 ghost payloads."""

@@ -359,7 +359,7 @@ int rotate_mixed_impl(dftfe_b200_ctx *ctx, double *X, int N, const double *Q, bo
 // high-level pieces (solver.cu)
 int apply_H_to_columns(dftfe_b200_ctx *ctx, const double *X, int N, int j0, int ncols);
 int op_hx(dftfe_b200_ctx *ctx, double *src, double *dst, int ncols, int scaleFlag, double scalar,
-          int doUnscale);
+          int doUnscale, bool fp32Comm = false);
 int op_hx_cheby(dftfe_b200_ctx *ctx, double *src, double *dst, int ncols, bool mixedPrec = false);
 int op_fused_apply(dftfe_b200_ctx *ctx, double *src, double *dst, int ncols, double a, double b, double s,
                    bool fp32Comm = false);

@@ -49,10 +49,11 @@ int op_fused_apply(dftfe_b200_ctx *ctx, double *src, double *dst, int ncols, dou
 }
 
 // operatorDFTDeviceClass::HX net effect (kohnShamDFTOperatorDevice.cc:3765-3860)
-int op_hx(dftfe_b200_ctx *ctx, double *src, double *dst, int ncols, int scaleFlag, double scalar, int doUnscale) {
+int op_hx(dftfe_b200_ctx *ctx, double *src, double *dst, int ncols, int scaleFlag, double scalar, int doUnscale,
+          bool fp32Comm) {
   // dst <- (scaleFlag ? dst : M^-1/2 dst) + scalar * H~ src on owned free rows, 0 on constrained rows
   DB_TRY(fused_apply_impl(ctx, src, dst, ncols, 0.0, 1.0, scalar,
-                          scaleFlag ? nullptr : ctx->invSqrtM.p));
+                          scaleFlag ? nullptr : ctx->invSqrtM.p, fp32Comm));
   // src side effects of the reference: constrained rows end at 0 (x M^1/2 = 0), ghosts zeroed;
   // without unscaling the caller sees scalar * M^-1/2 * src.
   const int nr = ncols * ctx->cm;
@@ -1122,11 +1123,11 @@ static int check_cols(dftfe_b200_ctx *ctx, int ncols) {
 extern "C" {
 
 int dftfe_b200_hx(dftfe_b200_ctx *ctx, double *src_d, double *dst_d, int32_t ncols, int32_t scale_flag,
-                  double scalar, int32_t do_unscaling_src) {
+                  double scalar, int32_t do_unscaling_src, int32_t single_prec_commun) {
   DB_CTX(ctx);
   DB_TRY(check_cols(ctx, ncols));
   DB_CHECK(scalar != 0.0, "HX: scalar must be non-zero");
-  return op_hx(ctx, src_d, dst_d, ncols, scale_flag, scalar, do_unscaling_src);
+  return op_hx(ctx, src_d, dst_d, ncols, scale_flag, scalar, do_unscaling_src, single_prec_commun != 0);
 }
 
 int dftfe_b200_hx_cheby(dftfe_b200_ctx *ctx, double *src_d, double *dst_d, int32_t ncols, int32_t mixed_prec) {

@@ -92,7 +92,19 @@ class operatorDFTDeviceClass {
     if (onlyHPrimePartForFirstOrderDensityMatResponse)
       throw std::runtime_error("HX: onlyHPrime is outside the ChFSI hot path and not provided");
     check(dftfe_b200_hx(d_ctx, src.begin(), dst.begin(), (int32_t)numberComponents, scaleFlag ? 1 : 0, scalar,
-                        doUnscalingX ? 1 : 0),
+                        doUnscalingX ? 1 : 0, 0),
+          "HX");
+  }
+  // the overload with the FP32 scratch vector (:3609-3761): singlePrecCommun selects FP32 ghost payloads
+  template <class Vec, class VecFP32>
+  void HX(Vec &src, VecFP32 & /*tempFloatArray*/, Vec & /*projectorKetTimesVector*/, const unsigned int /*localVectorSize*/,
+          const unsigned int numberComponents, const bool scaleFlag, const double scalar, Vec &dst,
+          const bool doUnscalingX = true, const bool singlePrecCommun = false,
+          const bool onlyHPrimePartForFirstOrderDensityMatResponse = false) {
+    if (onlyHPrimePartForFirstOrderDensityMatResponse)
+      throw std::runtime_error("HX: onlyHPrime is outside the ChFSI hot path and not provided");
+    check(dftfe_b200_hx(d_ctx, src.begin(), dst.begin(), (int32_t)numberComponents, scaleFlag ? 1 : 0, scalar,
+                        doUnscalingX ? 1 : 0, singlePrecCommun ? 1 : 0),
           "HX");
   }
 

@@ -235,9 +235,11 @@ int dftfe_b200_strided_block_scale(dftfe_b200_ctx *ctx, double *x_d, int32_t nco
 /* operatorDFTDeviceClass::HX (kohnShamDFTOperatorDevice.cc:3765-3860):
  *   dst = (scale_flag ? dst : M^-1/2 dst) + scalar * M^-1/2 H M^-1/2 src
  * on owned rows; constrained rows of dst end at 0; ghosts of src and dst end at 0;
- * src is left unscaled (do_unscaling_src != 0) or scaled by scalar*M^-1/2. */
+ * src is left unscaled (do_unscaling_src != 0) or scaled by scalar*M^-1/2.
+ * single_prec_commun: the overload with an FP32 scratch vector (:3609-3761) - ghost values travel as FP32 in both
+ * exchange directions, arithmetic stays FP64. */
 int dftfe_b200_hx(dftfe_b200_ctx *ctx, double *src_d, double *dst_d, int32_t ncols, int32_t scale_flag,
-                  double scalar, int32_t do_unscaling_src);
+                  double scalar, int32_t do_unscaling_src, int32_t single_prec_commun);
 /* operatorDFTDeviceClass::HXCheby (kohnShamDFTOperatorDevice.cc:3874-3997), no compute/communication
  * split: dst += H src (no mass scalings).  mixed_prec = the reference's chebMixedPrec flag: ghost values
  * travel as FP32 in both exchange directions (:3899-3915, 3953-3990); all arithmetic stays FP64. */

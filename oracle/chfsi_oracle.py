@@ -192,19 +192,20 @@ def compute_nonlocal_hamiltonian_times_x(ranks, src, dst, scalar: float = 1.0):
             np.add.at(d, rp.cellLocalDofs[nl.entryCell[e]], Yc)
 
 
-def HX(ranks, src, dst, scale_flag: bool, scalar: float, do_unscaling_src: bool = True):
+def HX(ranks, src, dst, scale_flag: bool, scalar: float, do_unscaling_src: bool = True,
+       single_prec_commun: bool = False):
     """src/dftOperator/kohnShamDFTOperator.cc:950-1044 (CPU) with the device
     variant's ``doUnscalingSrc`` switch and ``scalar`` placement
     (src/dftOperator/kohnShamDFTOperatorDevice.cc:3765-3860: src *= scalar*M^-1/2).
 
     dst (+)= M^-1/2 H M^-1/2 (scalar*src); on exit src has its ghosts zeroed and is
-    rescaled back when do_unscaling_src."""
+    rescaled back when do_unscaling_src.  single_prec_commun: the overload at :3609-3761 (FP32 exchanges)."""
     for rp, s, d in zip(ranks, src, dst):
         M = rp.M
         s[:M] *= (scalar * rp.invSqrtMass[:M])[:, None]
         if scale_flag:
             d[:M] *= rp.sqrtMass[:M][:, None]
-    update_ghost_values(ranks, src)
+    (update_ghost_values_fp32 if single_prec_commun else update_ghost_values)(ranks, src)
     for rp, s, d in zip(ranks, src, dst):
         distribute(rp, s)
         compute_local_hamiltonian_times_x(rp, s, d, 1.0)
@@ -212,7 +213,7 @@ def HX(ranks, src, dst, scale_flag: bool, scalar: float, do_unscaling_src: bool 
     for rp, d in zip(ranks, dst):
         distribute_slave_to_master(rp, d)
     zero_out_ghosts(ranks, src)
-    accumulate_add_locally_owned(ranks, dst)
+    (accumulate_add_locally_owned_fp32 if single_prec_commun else accumulate_add_locally_owned)(ranks, dst)
     zero_out_ghosts(ranks, dst)
     for rp, s, d in zip(ranks, src, dst):
         M = rp.M

@@ -32,6 +32,7 @@ int main(int argc, char **) {
     VecF f;
     Mat m(4);
     op.HX(a, pk, 0u, 4u, false, 1.0, b);
+    op.HX(a, f, pk, 0u, 4u, false, 1.0, b, true, true);
     op.HXCheby(a, f, pk, 0u, 4u, b);
     op.HXCheby(a, f, pk, 0u, 4u, b, true);
     op.XtHX(nullptr, a, b, pk, 0u, 4u, m, nullptr, nullptr);

@@ -84,16 +84,25 @@ def test_mixed_precision_filter_fp32_ghost_payload(capi, nranks, rank_grid, grou
         op.HXCheby(s_d, d_d, mixPrecFlag=True)
         op.sync()
         outs.append(d_d.cpu().numpy()[:rp.M])
+        # HX with the FP32-exchange overload
+        s_d, d_d = _dev(X[r]), torch.zeros(rp.M + rp.G, B, dtype=torch.float64, device="cuda")
+        op.HX(s_d, d_d, False, 1.0, singlePrecCommun=True)
+        op.sync()
+        outs.append(d_d.cpu().numpy()[:rp.M])
         op.close()
         return outs
 
     out = _run_ranks(nranks, rank_fn)
     src = [x.copy() for x in X]
+    dst_hx = [np.zeros_like(x) for x in X]
+    O.HX(ranks, src, dst_hx, False, 1.0, single_prec_commun=True)
+    src = [x.copy() for x in X]
     dst = [np.zeros_like(x) for x in X]
     O.HXCheby(ranks, src, dst, mixed_prec=True)
     scale = max(np.abs(r_[:rp.M]).max() for r_, rp in zip(ref64, ranks))
     for r, rp in enumerate(ranks):
-        f64, f32, hx = out[r]
+        f64, f32, hx, hx32 = out[r]
+        assert _relerr(hx32, dst_hx[r][:rp.M]) < TOL_FP32_FILTER
         assert np.abs(f64 - ref64[r][:rp.M]).max() / scale < 1e-11
         assert np.abs(f32 - ref32[r][:rp.M]).max() / scale < TOL_FP32_FILTER
         assert np.abs(f32 - f64).max() > 0.0  # FP32 payloads were used
