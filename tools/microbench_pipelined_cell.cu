@@ -33,7 +33,13 @@ constexpr int BT = 32, NT = 4, LDS = 36;
 constexpr int THREADS = WARPS * 32;
 constexpr size_t XBUF = (size_t)KPAD * LDS;
 constexpr size_t SMEM = 2 * XBUF * sizeof(double) + 4 * sizeof(uint64_t);
-constexpr int APF = 6;  // A prefetch depth (k-steps), 2 doubles per lane per k-step
+#ifndef PROBE_APF
+#define PROBE_APF 6
+#endif
+#ifndef PROBE_NOEPI
+#define PROBE_NOEPI 0  // 1: skip the epilogue's global traffic (ceiling of the two-half k-loop structure; wrong results)
+#endif
+constexpr int APF = PROBE_APF;  // A prefetch depth (k-steps), 2 doubles per lane per k-step
 constexpr size_t H2_PER_HALF = (size_t)KS * 32 * 2;           // doubles
 constexpr size_t H2_PER_CELL = (size_t)WARPS * 2 * H2_PER_HALF;
 
@@ -102,11 +108,16 @@ struct Ep {
 };
 
 // k-loop of one half: NH row tiles (2 or 1) x 4 column tiles
-template <int NH>
-__device__ __forceinline__ void kloop(const double *__restrict__ Ah, const double *xb, double (&acc)[2][NT][2]) {
-  double a[APF][2];
+// the ring must have been primed (prime()) for this half before the call: its first loads are issued as soon as
+// the previous k-loop ends, so they fly under the epilogue work in between
+__device__ __forceinline__ void prime(const double *__restrict__ Ah, double (&a)[APF][2]) {
 #pragma unroll
   for (int s = 0; s < APF; ++s) load2(Ah + (size_t)s * 64, a[s]);
+}
+
+template <int NH>
+__device__ __forceinline__ void kloop(const double *__restrict__ Ah, const double *xb, double (&acc)[2][NT][2],
+                                      double (&a)[APF][2]) {
 #pragma unroll
   for (int t = 0; t < 2; ++t)
 #pragma unroll
@@ -141,6 +152,9 @@ __device__ __forceinline__ void kloop(const double *__restrict__ Ah, const doubl
 template <int NH>
 __device__ __forceinline__ void issue_dst_loads(const double *dst, int ldx, int col0, const uint32_t (&rows)[2], int lane,
                                                 double2 (&d)[2][NT]) {
+#if PROBE_NOEPI
+  return;
+#endif
 #pragma unroll
   for (int t = 0; t < NH; ++t) {
     const double *drow = dst + (size_t)rows[t] * ldx + col0 + (lane & 3) * 2;
@@ -154,6 +168,17 @@ template <int NH>
 __device__ __forceinline__ void complete_epilogue(double *dst, int ldx, int col0, const uint32_t (&rows)[2],
                                                   const int (&irow)[2], const double *Xbuf, int lane, const Ep &ep,
                                                   const double (&acc)[2][NT][2], const double2 (&d)[2][NT]) {
+#if PROBE_NOEPI
+  {
+    double sacc = 0.0;
+#pragma unroll
+    for (int t = 0; t < NH; ++t)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) sacc += acc[t][nt][0] + acc[t][nt][1];
+    if (sacc == 1234.5678) dst[0] = sacc;
+    return;
+  }
+#endif
 #pragma unroll
   for (int t = 0; t < NH; ++t) {
     if (irow[t] < NODES) {
@@ -193,6 +218,9 @@ __device__ __forceinline__ void warp_items(const double *__restrict__ H2, const 
   }
   double acc0[2][NT][2], acc1[2][NT][2];
   double2 d0[2][NT], d1[2][NT];
+  double ring[APF][2];
+  if ((int)blockIdx.x < nItems)
+    prime(H2 + (size_t)(blockIdx.x / nColTiles) * H2_PER_CELL + (size_t)warp * 2 * H2_PER_HALF + lane * 2, ring);
   uint32_t rows0[2] = {0, 0}, rows1[2] = {0, 0}, prows1[2] = {0, 0};
   int irow0[2], irow1[2];
 #pragma unroll
@@ -216,7 +244,8 @@ __device__ __forceinline__ void warp_items(const double *__restrict__ H2, const 
     }
     mbar_wait(&full[buf], ph);
     // ---- half 0 (d1 of the previous item is in flight)
-    kloop<2>(Aw, xb, acc0);
+    kloop<2>(Aw, xb, acc0, ring);
+    prime(Aw + H2_PER_HALF, ring);  // half 1's first fragments fly under the epilogue work below
     if (pending1) {
       complete_epilogue<NH1>(dst, ldx, pcol0, prows1, irow1, Xs + pbuf * XBUF, lane, ep, acc1, d1);
       __syncwarp();
@@ -232,7 +261,9 @@ __device__ __forceinline__ void warp_items(const double *__restrict__ H2, const 
     }
     issue_dst_loads<2>(dst, ldx, col0, rows0, lane, d0);
     // ---- half 1 (d0 in flight)
-    kloop<NH1>(Aw + H2_PER_HALF, xb, acc1);
+    kloop<NH1>(Aw + H2_PER_HALF, xb, acc1, ring);
+    if (item + (int)gridDim.x < nItems)
+      prime(H2 + (size_t)((item + gridDim.x) / nColTiles) * H2_PER_CELL + (size_t)warp * 2 * H2_PER_HALF + lane * 2, ring);
     complete_epilogue<2>(dst, ldx, col0, rows0, irow0, Xs + buf * XBUF, lane, ep, acc0, d0);
     issue_dst_loads<NH1>(dst, ldx, col0, rows1, lane, d1);
     prows1[0] = rows1[0];
