@@ -51,7 +51,7 @@ def build(force: bool = False, verbose: bool = False) -> Path:
     if failed:
         raise RuntimeError("nvcc compilation failed")
     if force or procs or _stale(LIB, objs):
-        cmd = [NVCC, "-shared", "-o", str(LIB), *map(str, objs), "-L/usr/local/cuda/lib64", "-lcublas",
+        cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", str(LIB), *map(str, objs), "-L/usr/local/cuda/lib64", "-lcublas",
                "-lcusolver", "-ldl", "-Xlinker", "-rpath=/usr/local/cuda/lib64"]
         if verbose:
             print(" ".join(cmd))
