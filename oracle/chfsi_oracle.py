@@ -781,3 +781,35 @@ def compute_rho_from_psi(ranks, X, occupations, shape_values):
         psi = np.einsum("iq,cik->cqk", N, Xc, optimize=True)
         out.append(np.einsum("k,cqk->cq", f, np.abs(psi) ** 2, optimize=True))
     return out
+
+
+def chebyshev_filter_unit_coefficient(ranks, X, m: int, a: float, b: float, a0: float):
+    """The same degree-m filter as ``chebyshev_filter`` with the iterates carried as z_k = x_k / gamma_k,
+    gamma_{k+1} = alpha2_k * gamma_{k-1}: the three-term recurrence becomes
+        z_{k+1} = (alpha1_k gamma_k / gamma_{k+1}) (H~ - c) z_k + z_{k-1},
+    i.e. the previous iterate enters with coefficient 1 (an exploratory restatement for the next cell-kernel
+    epilogue; not a reference routine).  Returns the filtered block (new arrays)."""
+    e = (b - a) / 2.0
+    c = (b + a) / 2.0
+    sigma = e / (a0 - c)
+    sigma1 = sigma
+    gamma = 2.0 / sigma1
+    Zp = [x.copy() for x in X]                      # z_0 = x_0, gamma_0 = 1
+    Y = [np.zeros_like(x) for x in X]
+    HX(ranks, [x.copy() for x in X], Y, False, 1.0)
+    Zc = [(sigma1 / e) * (y - c * x) for x, y in zip(X, Y)]   # z_1 = x_1, gamma_1 = 1
+    g_prev, g_cur = 1.0, 1.0
+    for _degree in range(2, m + 1):
+        sigma2 = 1.0 / (gamma - sigma)
+        alpha1, alpha2 = 2.0 * sigma2 / e, -(sigma * sigma2)
+        g_next = alpha2 * g_prev
+        coef = alpha1 * g_cur / g_next
+        Hz = [np.zeros_like(z) for z in Zc]
+        HX(ranks, [z.copy() for z in Zc], Hz, False, 1.0)
+        Zn = [coef * (h - c * z) + zp for h, z, zp in zip(Hz, Zc, Zp)]
+        for rp, zn in zip(ranks, Zn):
+            zn[rp.M:] = 0
+        Zp, Zc = Zc, Zn
+        g_prev, g_cur = g_cur, g_next
+        sigma = sigma2
+    return [g_cur * z for z in Zc]

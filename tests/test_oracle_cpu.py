@@ -378,3 +378,19 @@ def test_cell_hamiltonian_and_density_statements():
     rho = O.compute_rho_from_psi(ranks, Xfe, occ, np.eye(ref.n))
     total = sum(float((r_ * ref.mass_gll[None, :]).sum()) for r_ in rho)
     assert abs(total - occ.sum()) < 1e-11 * occ.sum()
+
+
+@pytest.mark.parametrize("m", [2, 7, 20])
+def test_unit_coefficient_recurrence_is_the_same_filter(m):
+    """Exploratory restatement for the next epilogue design: carrying z_k = x_k / gamma_k makes the old iterate enter
+    with coefficient 1; the filtered block is the same to rounding."""
+    mesh, ranks = make_problem(3, (3, 3, 2), 1.3, (True, True, False), nranks=2)
+    X = scatter_to_ranks(ranks, random_global(mesh, 4, seed=5), loewdin=True)
+    lo, up = O.lanczos_bounds(ranks)
+    a, a0 = lo + 0.2 * (up - lo), lo - 0.1
+    ref = [x.copy() for x in X]
+    O.chebyshev_filter_inplace(ranks, ref, m, a, up, a0)
+    got = O.chebyshev_filter_unit_coefficient(ranks, X, m, a, up, a0)
+    scale = max(np.abs(r).max() for r in ref)
+    for rp, g, r in zip(ranks, got, ref):
+        assert np.abs(g[:rp.M] - r[:rp.M]).max() < 1e-12 * scale
