@@ -85,6 +85,7 @@ EXPORTED_SYMBOLS = [
     "dftfe_b200_residual_norms", "dftfe_b200_reinit_spectrum_bounds", "dftfe_b200_solve",
     "dftfe_b200_get_spectrum_bounds", "dftfe_b200_solve_no_rr", "dftfe_b200_get_colouring", "dftfe_b200_set_option", "dftfe_b200_profile_enable",
     "dftfe_b200_profile_get", "dftfe_b200_profile_reset", "dftfe_b200_launch_count",
+    "dftfe_b200_measure_fp64_tensor_peak", "dftfe_b200_transport_name",
 ]
 
 
@@ -108,6 +109,8 @@ def load() -> C.CDLL:
     lib.dftfe_b200_last_error.restype = C.c_char_p
     lib.dftfe_b200_launch_count.restype = C.c_int64
     lib.dftfe_b200_launch_count.argtypes = [C.c_void_p]
+    lib.dftfe_b200_transport_name.restype = C.c_char_p
+    lib.dftfe_b200_transport_name.argtypes = [C.c_void_p]
     lib.dftfe_b200_destroy.restype = None
     lib.dftfe_b200_destroy.argtypes = [C.c_void_p]
     _lib = lib
@@ -200,7 +203,7 @@ class Operator:
             self.set_nonlocal(nl)
 
     def set_nonlocal(self, nl, kPointIndex: int = 0):
-        """NonLocalData (dftfe_b200.femesh) -> dftfe_b200_set_nonlocal_kpt (complex C for a complex context)."""
+        """NonLocalData (tools.femesh) -> dftfe_b200_set_nonlocal_kpt (complex C for a complex context)."""
         npj, V = _np(nl.nProjPerAtom, np.int32), _np(nl.V, np.float64)
         assert np.iscomplexobj(nl.C) == self.complex, "projector dtype does not match the context"
         ec, ea = _np(nl.entryCell, np.int32), _np(nl.entryAtom, np.int32)
@@ -404,6 +407,14 @@ class Operator:
         ms, n = C.c_double(), C.c_int64()
         _check(self.lib.dftfe_b200_profile_get(self.h, name.encode(), C.byref(ms), C.byref(n)))
         return ms.value, n.value
+
+    def measure_fp64_tensor_peak(self) -> float:
+        v = C.c_double()
+        _check(self.lib.dftfe_b200_measure_fp64_tensor_peak(self.h, C.byref(v)))
+        return v.value
+
+    def transport_name(self) -> str:
+        return self.lib.dftfe_b200_transport_name(self.h).decode()
 
     def launch_count(self) -> int:
         return int(self.lib.dftfe_b200_launch_count(self.h))

@@ -671,8 +671,9 @@ cell_matvec_persistent_kernel(const double *__restrict__ Ht, const uint32_t *__r
   if (tid == 0) {
     mbar_init(&full[0], 1);
     mbar_init(&full[1], 1);
-    mbar_init(&empty[0], P::MMA_WARPS);
-    mbar_init(&empty[1], P::MMA_WARPS);
+    // only warps that own row tiles run the item loop and release the buffers (FE order 1: one of four)
+    mbar_init(&empty[0], C::MT < P::MMA_WARPS ? C::MT : P::MMA_WARPS);
+    mbar_init(&empty[1], C::MT < P::MMA_WARPS ? C::MT : P::MMA_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // generic-proxy zero fill must be ordered before the async-proxy (TMA) writes
@@ -764,17 +765,10 @@ int launch_impl2(dftfe_b200_ctx *ctx, const double *src, double *dst, int ncols,
                  const EpilogueParams &ep) {
   using C = CellCfg<NODES, CPLX>;
   using P = PersistCfg<NODES, CPLX>;
-  static bool attr_set = false;
-  if (!attr_set) {
-    DB_CUDA(cudaFuncSetAttribute(cell_matvec_kernel<NODES, CPLX>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)C::SMEM));
-    if (P::SMEM <= 227 * 1024) {
-      DB_CUDA(cudaFuncSetAttribute(cell_matvec_persistent_kernel<NODES, CPLX, false>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::SMEM));
-      DB_CUDA(cudaFuncSetAttribute(cell_matvec_persistent_kernel<NODES, CPLX, true>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P::SMEM));
-    }
-    attr_set = true;
+  DB_DYN_SMEM(ctx, (cell_matvec_kernel<NODES, CPLX>), C::SMEM);
+  if (P::SMEM <= 227 * 1024) {
+    DB_DYN_SMEM(ctx, (cell_matvec_persistent_kernel<NODES, CPLX, false>), P::SMEM);
+    DB_DYN_SMEM(ctx, (cell_matvec_persistent_kernel<NODES, CPLX, true>), P::SMEM);
   }
   const int nColTiles = (ncols + BT - 1) / BT;
   // fast path needs an even column count (16-byte row segments and column pairs), 16-byte aligned rows and no

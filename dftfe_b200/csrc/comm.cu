@@ -14,10 +14,14 @@
 // parity-tested on a single B200.
 #include <dlfcn.h>
 
+#include <time.h>
+
 #include <condition_variable>
 #include <cstring>
 #include <memory>
 #include <mutex>
+
+#include <cuda.h>
 
 #include "common.cuh"
 
@@ -35,6 +39,9 @@ int launch_unpack_add(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx, const 
                       const double *rowScale);
 int launch_unpack_add_f32(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx, const float *buf,
                           const double *rowScale);
+int launch_push_rows(dftfe_b200_ctx *ctx, const double *x, int ncols, int ldx, int64_t nRows, const uint32_t *rows,
+                     int64_t row0, const PushSegs &segs, bool fp32);
+int launch_signal_flags(dftfe_b200_ctx *ctx, const SignalList &l, uint32_t value);
 
 const NcclApi *nccl_api() {
   static NcclApi api;
@@ -195,11 +202,305 @@ static int exchange(dftfe_b200_ctx *ctx, bool forward, const char *srcBase, char
   return 0;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// "p2p" transport: the exchange without NCCL's send/recv kernels.
+//
+// NCCL's point-to-point kernels need a whole SM's worth of registers/threads, so they cannot co-reside with the
+// persistent cell kernel of the other filter lane: every exchange queued behind a colour launch (0.5 ms of the
+// 1.26 ms launch exposed per exchange, 169 ms per filter step at 8 GPUs).  Here the packing kernel itself stores
+// the rows into the destination rank's receive buffer through a peer mapping (NVLink / NVSwitch), a one-warp
+// kernel publishes a sequence number in the destination's flag array, and the consumer's STREAM waits for it with
+// cuStreamWaitValue32 - a stream memory operation that holds no SM.  The small row kernels fit beside a resident
+// cell CTA (256 threads, <= 48 registers), so one lane's exchange really runs under the other lane's GEMMs.
+// Semantics are those of MPICommunicatorP2P::updateGhostValues / accumulateAddLocallyOwned
+// (utils/MPICommunicatorP2P.cc:103-418); the arithmetic (unpack-add order, FP32 payload rounding) is unchanged.
+//
+// Hand-shake per (lane, direction), sequence number s = 1, 2, ...:
+//   producer: wait ACK[dst] >= s-1 (receive buffer free)  -> push rows -> signal DATA[me] = s at each destination
+//   consumer: wait DATA[src] >= s from each source        -> unpack    -> signal ACK[me]  = s at each source
+// Every rank issues the same sequence of exchanges (the operator apply is collective), so the counters agree.
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+
+typedef CUresult (*WaitValue32Fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+
+WaitValue32Fn wait_value32_fn() {
+  static WaitValue32Fn fn = nullptr;
+  static bool tried = false;
+  static std::mutex mu;
+  std::lock_guard<std::mutex> lk(mu);
+  if (!tried) {
+    tried = true;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<WaitValue32Fn>(p);
+  }
+  return fn;
+}
+
+enum { P2P_DATA = 0, P2P_ACK = 1 };
+
+inline uint32_t *p2p_flag(char *slab, size_t offFlags, int nranks, int lane, int dir, int kind, int src) {
+  return reinterpret_cast<uint32_t *>(slab + offFlags) + ((size_t)((lane * 2 + dir) * 2 + kind) * nranks + src);
+}
+
+int p2p_wait(dftfe_b200_ctx *ctx, int dir, int kind, int src, uint32_t value) {
+  uint32_t *f = p2p_flag(ctx->p2p.slab, ctx->p2p.offFlags, ctx->nranks, ctx->lane, dir, kind, src);
+  ctx->launches += 0;  // a stream memory operation, not a kernel
+  const CUresult r = wait_value32_fn()(ctx->stream, (CUdeviceptr)f, value, CU_STREAM_WAIT_VALUE_GEQ);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuStreamWaitValue32 failed (%d)", (int)r);
+    return DFTFE_B200_ERR_CUDA;
+  }
+  return 0;
+}
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// record every rank publishes: [0..7] cudaIpc handle (64 bytes), [8] offFlags, [9..10] offRecvF, [11..12] offRecvR,
+// [13 .. 13+nranks) first row of rank q's rows in MY ghost segment, [13+nranks .. 13+2 nranks) first row of rank
+// q's range in MY reverse receive buffer (-1: q is not a neighbour)
+constexpr int P2P_REC_FIXED = 13;
+
+void p2p_fill_starts(const dftfe_b200_ctx *c, int64_t *ghostStart, int64_t *targetStart) {
+  for (int r = 0; r < c->nranks; ++r) ghostStart[r] = targetStart[r] = -1;
+  for (size_t g = 0; g < c->ghostProcs_h.size(); ++g) ghostStart[c->ghostProcs_h[g]] = c->ghostRanges_h[2 * g];
+  for (size_t t = 0; t < c->targetProcs_h.size(); ++t) targetStart[c->targetProcs_h[t]] = c->targetOffsets_h[t];
+}
+
+}  // namespace
+
+void p2p_release(dftfe_b200_ctx *ctx) {
+  auto &p = ctx->p2p;
+  if (p.active && p.slab) {
+    // my neighbours acknowledge my last payloads by storing into THIS slab: wait (bounded) until every expected
+    // acknowledgement has landed before the memory goes away
+    const int nr = ctx->nranks;
+    std::vector<uint32_t> flags((size_t)8 * nr);
+    for (int spin = 0; spin < 2000; ++spin) {
+      if (cudaMemcpy(flags.data(), p.slab + p.offFlags, flags.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost) !=
+          cudaSuccess)
+        break;
+      bool done = true;
+      for (int lane = 0; lane < 2; ++lane)
+        for (int dir = 0; dir < 2; ++dir) {
+          const std::vector<int32_t> &dst = dir == 0 ? ctx->targetProcs_h : ctx->ghostProcs_h;
+          for (int q : dst)
+            done = done && (int32_t)(flags[((size_t)((lane * 2 + dir) * 2 + P2P_ACK)) * nr + q] - p.seq[lane][dir]) >= 0;
+        }
+      if (done) break;
+      struct timespec ts = {0, 1000000};
+      nanosleep(&ts, nullptr);
+    }
+  }
+  if (p.ipc)
+    for (char *q : p.peerSlab)
+      if (q) cudaIpcCloseMemHandle(q);
+  p.peerSlab.clear();
+  if (p.slab) cudaFree(p.slab);
+  p.slab = nullptr;
+  p.active = false;
+}
+
+static int p2p_setup(dftfe_b200_ctx *ctx) {
+  auto &p = ctx->p2p;
+  p.tried = true;
+  LoopbackGroup *grp = loopback_of(ctx);
+  const bool wanted = p.requested == 1 || (p.requested == -1 && ctx->nccl != nullptr);
+  const int nr = ctx->nranks;
+  // all ranks take the same decision: `requested` is set identically by the caller, the rest is agreed below
+  if (!wanted || (!ctx->nccl && !grp)) return 0;
+  bool ok = wait_value32_fn() != nullptr && ctx->targetProcs_h.size() <= (size_t)P2P_MAX_PEERS &&
+            ctx->ghostProcs_h.size() <= (size_t)P2P_MAX_PEERS;
+  // slab layout
+  const size_t rowMax = (size_t)ctx->B * ctx->cm * sizeof(double);
+  p.offFlags = 0;
+  size_t off = align_up((size_t)2 * 2 * 2 * nr * sizeof(uint32_t), 256);
+  for (int l = 0; l < 2; ++l) {
+    p.offRecvF[l] = off;
+    off = align_up(off + (size_t)ctx->G * rowMax, 256);
+    p.offRecvR[l] = off;
+    off = align_up(off + (size_t)ctx->nSend * rowMax, 256);
+  }
+  p.slabBytes = off;
+  DB_CUDA(cudaMalloc(&p.slab, p.slabBytes));
+  DB_CUDA(cudaMemsetAsync(p.slab, 0, align_up((size_t)8 * nr * sizeof(uint32_t), 256), ctx->stream));
+  DB_CUDA(cudaStreamSynchronize(ctx->stream));
+  p.peerSlab.assign(nr, nullptr);
+  p.peerOffFlags.assign(nr, 0);
+  for (int l = 0; l < 2; ++l) {
+    p.peerOffRecvF[l].assign(nr, 0);
+    p.peerOffRecvR[l].assign(nr, 0);
+  }
+  p.peerGhostStartOfMe.assign(nr, -1);
+  p.peerTargetStartOfMe.assign(nr, -1);
+  std::vector<char> neighbour(nr, 0);
+  for (int q : ctx->targetProcs_h) neighbour[q] = 1;
+  for (int q : ctx->ghostProcs_h) neighbour[q] = 1;
+
+  if (grp && !ctx->nccl) {
+    // one process, several ranks on one device: peers' slabs are plain pointers
+    grp->barrier();
+    for (int q = 0; q < nr; ++q) {
+      if (!neighbour[q]) continue;
+      const dftfe_b200_ctx *pc = grp->members[q];
+      if (!pc->p2p.slab) {
+        ok = false;
+        continue;
+      }
+      p.peerSlab[q] = pc->p2p.slab;
+      p.peerOffFlags[q] = pc->p2p.offFlags;
+      for (int l = 0; l < 2; ++l) {
+        p.peerOffRecvF[l][q] = pc->p2p.offRecvF[l];
+        p.peerOffRecvR[l][q] = pc->p2p.offRecvR[l];
+      }
+      std::vector<int64_t> gs(nr), ts(nr);
+      p2p_fill_starts(pc, gs.data(), ts.data());
+      p.peerGhostStartOfMe[q] = gs[ctx->rank];
+      p.peerTargetStartOfMe[q] = ts[ctx->rank];
+    }
+    grp->barrier();
+    p.active = ok;
+    if (!ok) {
+      set_error("p2p exchange requested but not available (stream memory operations / peer slabs missing)");
+      return DFTFE_B200_ERR_UNSUPPORTED;
+    }
+    return 0;
+  }
+
+  // one process per GPU: publish (IPC handle, offsets, range starts) with an all-reduce over a zero-padded table
+  const int W = P2P_REC_FIXED + 2 * nr;
+  std::vector<int64_t> table((size_t)nr * W, 0);
+  int64_t *mine = table.data() + (size_t)ctx->rank * W;
+  cudaIpcMemHandle_t h;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is expected to be 64 bytes");
+  if (cudaIpcGetMemHandle(&h, p.slab) != cudaSuccess) {
+    cudaGetLastError();
+    ok = false;
+    std::memset(&h, 0, sizeof(h));
+  }
+  std::memcpy(mine, &h, 64);
+  mine[8] = (int64_t)p.offFlags;
+  mine[9] = (int64_t)p.offRecvF[0];
+  mine[10] = (int64_t)p.offRecvF[1];
+  mine[11] = (int64_t)p.offRecvR[0];
+  mine[12] = (int64_t)p.offRecvR[1];
+  p2p_fill_starts(ctx, mine + P2P_REC_FIXED, mine + P2P_REC_FIXED + nr);
+  DevBuf<int64_t> dtab;
+  DB_TRY(dtab.upload(table.data(), table.size(), ctx->stream));
+  DB_NCCL(nccl_api()->AllReduce(dtab.p, dtab.p, table.size(), ncclInt64, ncclSum, ctx->nccl, ctx->stream));
+  DB_CUDA(cudaMemcpyAsync(table.data(), dtab.p, table.size() * sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  DB_CUDA(cudaStreamSynchronize(ctx->stream));
+  for (int q = 0; q < nr && ok; ++q) {
+    if (!neighbour[q]) continue;
+    const int64_t *rec = table.data() + (size_t)q * W;
+    cudaIpcMemHandle_t hq;
+    std::memcpy(&hq, rec, 64);
+    void *ptr = nullptr;
+    if (cudaIpcOpenMemHandle(&ptr, hq, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+      cudaGetLastError();
+      ok = false;
+      break;
+    }
+    p.ipc = true;
+    p.peerSlab[q] = static_cast<char *>(ptr);
+    p.peerOffFlags[q] = (size_t)rec[8];
+    p.peerOffRecvF[0][q] = (size_t)rec[9];
+    p.peerOffRecvF[1][q] = (size_t)rec[10];
+    p.peerOffRecvR[0][q] = (size_t)rec[11];
+    p.peerOffRecvR[1][q] = (size_t)rec[12];
+    p.peerGhostStartOfMe[q] = rec[P2P_REC_FIXED + ctx->rank];
+    p.peerTargetStartOfMe[q] = rec[P2P_REC_FIXED + nr + ctx->rank];
+  }
+  // agree: p2p only if EVERY rank could map all of its neighbours
+  int64_t bad = ok ? 0 : 1;
+  DevBuf<int64_t> dbad;
+  DB_TRY(dbad.upload(&bad, 1, ctx->stream));
+  DB_NCCL(nccl_api()->AllReduce(dbad.p, dbad.p, 1, ncclInt64, ncclSum, ctx->nccl, ctx->stream));
+  DB_CUDA(cudaMemcpyAsync(&bad, dbad.p, sizeof(int64_t), cudaMemcpyDeviceToHost, ctx->stream));
+  DB_CUDA(cudaStreamSynchronize(ctx->stream));
+  p.active = bad == 0;
+  if (!p.active) {
+    p2p_release(ctx);
+    if (p.requested == 1) {
+      set_error("p2p exchange requested but %lld rank(s) could not map their neighbours' buffers (no peer access?)",
+                (long long)bad);
+      return DFTFE_B200_ERR_UNSUPPORTED;
+    }
+  }
+  return 0;
+}
+
+const char *transport_name(dftfe_b200_ctx *ctx) {
+  if (ctx->nranks == 1) return "none (single rank)";
+  if (ctx->p2p.active)
+    return ctx->p2p.ipc ? "p2p: rows stored into cudaIpc-mapped peer buffers over NVLink, stream-memory-op hand-shake"
+                        : "p2p (in-process): rows stored into the peer rank's buffers, stream-memory-op hand-shake";
+  if (ctx->nccl) return ctx->p2p.tried ? "nccl send/recv (p2p unavailable or disabled)" : "nccl send/recv";
+  return "loopback (host-synchronised device copies)";
+}
+
+// one exchange over the p2p transport.  forward: owned rows (sendRows) -> the targets' ghost rows;
+// reverse: my ghost rows -> added into the owners' rows.
+static int exchange_p2p(dftfe_b200_ctx *ctx, bool forward, double *x, int ncols, int ldx, const double *rowScale,
+                        bool fp32) {
+  auto &p = ctx->p2p;
+  const int lane = ctx->lane, dir = forward ? 0 : 1, nr = ctx->nranks;
+  const uint32_t seq = ++p.seq[lane][dir];
+  const size_t rowBytes = (size_t)ncols * (fp32 ? 4 : 8);
+  const std::vector<int32_t> &dstProcs = forward ? ctx->targetProcs_h : ctx->ghostProcs_h;
+  const std::vector<int32_t> &srcProcs = forward ? ctx->ghostProcs_h : ctx->targetProcs_h;
+  // 1. the destinations have consumed the previous payload of this (lane, direction)
+  if (seq > 1)
+    for (int q : dstProcs) DB_TRY(p2p_wait(ctx, dir, P2P_ACK, q, seq - 1));
+  // 2. push my rows into their receive buffers, then publish the sequence number
+  PushSegs segs;
+  SignalList sig;
+  segs.n = sig.n = (int)dstProcs.size();
+  for (int s = 0; s < segs.n; ++s) {
+    const int q = dstProcs[s];
+    const int64_t at = forward ? p.peerGhostStartOfMe[q] : p.peerTargetStartOfMe[q];
+    DB_CHECK(at >= 0 && p.peerSlab[q], "p2p exchange: rank %d does not expect rows from rank %d", q, ctx->rank);
+    segs.start[s] = forward ? ctx->targetOffsets_h[s] : ctx->ghostRanges_h[2 * s];
+    segs.dst[s] = p.peerSlab[q] + (forward ? p.peerOffRecvF[lane][q] : p.peerOffRecvR[lane][q]) + (size_t)at * rowBytes;
+    sig.addr[s] = p2p_flag(p.peerSlab[q], p.peerOffFlags[q], nr, lane, dir, P2P_DATA, ctx->rank);
+  }
+  segs.start[segs.n] = forward ? ctx->nSend : ctx->G;
+  if (forward)
+    DB_TRY(launch_push_rows(ctx, x, ncols, ldx, ctx->nSend, ctx->sendRows.p, 0, segs, fp32));
+  else
+    DB_TRY(launch_push_rows(ctx, x, ncols, ldx, ctx->G, nullptr, ctx->M, segs, fp32));
+  DB_TRY(launch_signal_flags(ctx, sig, seq));
+  // 3. wait for every source's payload, unpack, acknowledge
+  for (int q : srcProcs) DB_TRY(p2p_wait(ctx, dir, P2P_DATA, q, seq));
+  char *recv = p.slab + (forward ? p.offRecvF[lane] : p.offRecvR[lane]);
+  if (forward) {
+    if (fp32)
+      DB_TRY(launch_unpack_rows_f32(ctx, x, ncols, ldx, ctx->M, ctx->G, reinterpret_cast<const float *>(recv)));
+    else
+      DB_TRY(launch_unpack_rows(ctx, x, ncols, ldx, ctx->M, ctx->G, reinterpret_cast<const double *>(recv)));
+  } else {
+    if (fp32)
+      DB_TRY(launch_unpack_add_f32(ctx, x, ncols, ldx, reinterpret_cast<const float *>(recv), rowScale));
+    else
+      DB_TRY(launch_unpack_add(ctx, x, ncols, ldx, reinterpret_cast<const double *>(recv), rowScale));
+  }
+  SignalList ack;
+  ack.n = (int)srcProcs.size();
+  for (int s = 0; s < ack.n; ++s)
+    ack.addr[s] = p2p_flag(p.peerSlab[srcProcs[s]], p.peerOffFlags[srcProcs[s]], nr, lane, dir, P2P_ACK, ctx->rank);
+  return launch_signal_flags(ctx, ack, seq);
+}
+
 // forward: owned rows needed by my targets -> their ghost rows.  fp32: the payload travels as floats
 // (HXCheby with chebMixedPrec, kohnShamDFTOperatorDevice.cc:3899-3915): ghost values arrive rounded to FP32.
 int ghost_update(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx, bool fp32) {
   if (ctx->nranks == 1) return 0;
   DB_CHECK(ctx->nccl || loopback_of(ctx), "ghost exchange needs comm_init (NCCL) or a loopback group");
+  if (!ctx->p2p.tried) DB_TRY(p2p_setup(ctx));
+  if (ctx->p2p.active) return exchange_p2p(ctx, true, x, ncols, ldx, nullptr, fp32);
   DB_TRY(ensure_payload(ctx));
   double *sendBuf = ctx->sendB[ctx->lane].p, *recvBuf = ctx->recvB[ctx->lane].p;
   if (fp32) {
@@ -220,6 +521,8 @@ int ghost_update(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx, bool fp32) 
 int ghost_accumulate(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx, const double *rowScale, bool fp32) {
   if (ctx->nranks == 1) return 0;
   DB_CHECK(ctx->nccl || loopback_of(ctx), "ghost exchange needs comm_init (NCCL) or a loopback group");
+  if (!ctx->p2p.tried) DB_TRY(p2p_setup(ctx));
+  if (ctx->p2p.active) return exchange_p2p(ctx, false, x, ncols, ldx, rowScale, fp32);
   DB_TRY(ensure_payload(ctx));
   double *sendBuf = ctx->sendB[ctx->lane].p, *recvBuf = ctx->recvB[ctx->lane].p;
   if (fp32) {

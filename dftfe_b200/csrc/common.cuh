@@ -133,6 +133,19 @@ struct ProfileSlot {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending;
 };
 
+// p2p ghost exchange (comm.cu): destination segments of a push kernel / flag addresses of a signal kernel.
+// At most 32 neighbour ranks per rank (face / edge / corner neighbours of a brick or space-filling-curve partition).
+constexpr int P2P_MAX_PEERS = 32;
+struct PushSegs {
+  int n = 0;
+  int64_t start[P2P_MAX_PEERS + 1];  // first payload row of segment s (start[n] = total rows)
+  char *dst[P2P_MAX_PEERS];          // address of that row in the destination rank's receive buffer
+};
+struct SignalList {
+  int n = 0;
+  uint32_t *addr[P2P_MAX_PEERS];
+};
+
 // Parameters of the fused cell kernel's epilogue (see cell_matvec.cu).
 struct EpilogueParams {
   double a = 0.0;       // first touch: dst = rowA*a*src + rowB*b*dst + s*rowOut*(H src)
@@ -216,6 +229,21 @@ struct dftfe_b200_ctx {
   dftfe_b200::DevBuf<uint32_t> bndRows, bndStarts, bndSlots;
   ncclComm_t nccl = nullptr;
   cudaEvent_t evCompute = nullptr, evComm = nullptr;
+  // "p2p" transport of the ghost exchange (comm.cu): every rank owns one slab (flags + per-lane receive buffers
+  // for the forward and the reverse exchange) that its neighbours map (cudaIpc across processes, plain pointers
+  // inside one process) and write into directly; arrival / buffer-free hand-shakes are sequence numbers in the
+  // slab, waited for with stream memory operations (no SM is held while waiting).
+  struct P2PState {
+    int requested = -1;   // option "p2p_exchange": -1 auto (on over NCCL when every neighbour can be mapped), 0 off, 1 on
+    bool tried = false, active = false, ipc = false;
+    char *slab = nullptr;
+    size_t slabBytes = 0, offFlags = 0, offRecvF[2] = {0, 0}, offRecvR[2] = {0, 0};
+    std::vector<char *> peerSlab;                                   // per rank (nullptr: not a neighbour)
+    std::vector<size_t> peerOffFlags, peerOffRecvF[2], peerOffRecvR[2];
+    std::vector<int64_t> peerGhostStartOfMe;    // first row, in rank r's ghost segment, of the rows I own (-1: none)
+    std::vector<int64_t> peerTargetStartOfMe;   // first row, in rank r's reverse receive buffer, of my ghost range
+    uint32_t seq[2][2] = {{0, 0}, {0, 0}};      // [lane][0 forward, 1 reverse] exchanges issued so far
+  } p2p;
 
   // --- cell Hamiltonian (fragment-major)
   bool have_H = false;
@@ -240,13 +268,14 @@ struct dftfe_b200_ctx {
   };
   std::map<int, NonlocalSet> nlSets;
   NonlocalSet *nl = nullptr;  // active set (nullptr: no non-local term)
-  dftfe_b200::DevBuf<double> nlProj;  // projector block: totalProj x B (x 2 complex), all-reduced
+  dftfe_b200::DevBuf<double> nlProj[2];  // projector block per lane: totalProj x B (x 2 complex), all-reduced
   // --- solver state / scratch
   dftfe_b200::DevBuf<double> blockX, blockY;      // (M+G)*B
   dftfe_b200::DevBuf<double> blockX2;             // second block buffer (host-pipelined filter; lane 1)
   dftfe_b200::DevBuf<double> blockY2;             // lane 1 scratch
   dftfe_b200::DevBuf<double> blockX3, blockX4;    // second buffer set of the host-resident filter loop
   cudaStream_t copyIn = nullptr, copyOut = nullptr;
+  std::vector<cudaEvent_t> hostLoopEvents;        // host-resident filter loop: copy-in / compute / copy-out per block
   dftfe_b200::DevBuf<double> HXfull;              // M*Bw
   dftfe_b200::DevBuf<double> denseA, denseB, denseC, denseW;  // N*N scratch
   dftfe_b200::DevBuf<double> denseG;              // (2N)^2 real embedding scratch of the complex build
@@ -299,6 +328,11 @@ struct ProfScope {
   }
 };
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: set it once per (kernel, device),
+// thread-safe (several contexts / host threads may launch the same kernel on different devices).
+int ensure_dyn_smem(const void *kernel, int device, size_t bytes);
+#define DB_DYN_SMEM(ctx, kernel, bytes) DB_TRY(::dftfe_b200::ensure_dyn_smem((const void *)(kernel), (ctx)->desc.device, (bytes)))
+
 // ---- kernels / launchers implemented across the .cu files -----------------
 int cell_kernel_supported(int nodes_per_cell);
 int retile_cell_hamiltonian(dftfe_b200_ctx *ctx, const double *H_d);
@@ -313,6 +347,8 @@ int launch_set_zero_rows(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx);
 int ghost_update(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx, bool fp32 = false);
 int ghost_accumulate(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx, const double *rowScale, bool fp32 = false);
 int ghost_zero(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx);
+void p2p_release(dftfe_b200_ctx *ctx);
+const char *transport_name(dftfe_b200_ctx *ctx);
 
 int launch_row_scale(dftfe_b200_ctx *ctx, double *x, int64_t rows, int ncols, int ldx, double alpha,
                      const double *rowScale);

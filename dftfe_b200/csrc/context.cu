@@ -2,7 +2,9 @@
 // kohnShamDFTOperatorDeviceClass::reinit (src/dftOperator/kohnShamDFTOperatorDevice.cc:492-933).
 #include <algorithm>
 #include <cstring>
+#include <mutex>
 #include <numeric>
+#include <set>
 
 #include "common.cuh"
 
@@ -15,6 +17,16 @@ void set_error(const char *fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+int ensure_dyn_smem(const void *kernel, int device, size_t bytes) {
+  static std::mutex mu;
+  static std::set<std::pair<const void *, int>> done;
+  std::lock_guard<std::mutex> lk(mu);
+  if (done.count({kernel, device})) return 0;
+  DB_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  done.insert({kernel, device});
+  return 0;
 }
 
 int loopback_join(dftfe_b200_ctx *ctx, int group_id, int rank, int nranks);
@@ -151,8 +163,10 @@ void dftfe_b200_destroy(dftfe_b200_ctx *ctx) {
     if (ctx->laneEvent[l]) cudaEventDestroy(ctx->laneEvent[l]);
   }
   if (ctx->forkEvent) cudaEventDestroy(ctx->forkEvent);
+  for (cudaEvent_t e : ctx->hostLoopEvents) cudaEventDestroy(e);
   if (ctx->copyIn) cudaStreamDestroy(ctx->copyIn);
   if (ctx->copyOut) cudaStreamDestroy(ctx->copyOut);
+  p2p_release(ctx);
   if (ctx->nccl && nccl_api()) nccl_api()->CommDestroy(ctx->nccl);
   if (ctx->cusolver) cusolverDnDestroy(ctx->cusolver);
   if (ctx->cublas) cublasDestroy(ctx->cublas);
@@ -513,10 +527,13 @@ int dftfe_b200_set_cell_hamiltonian_host(dftfe_b200_ctx *ctx, const double *H_h)
 
 int dftfe_b200_update_ghost_values(dftfe_b200_ctx *ctx, double *x_d, int32_t ncols) {
   DB_CTX(ctx);
+  DB_CHECK(ncols >= 1 && ncols <= ctx->B, "update_ghost_values: ncols (%d) must be in [1, cheby_block=%d]", ncols, ctx->B);
   return ghost_update(ctx, x_d, ncols * ctx->cm, ncols * ctx->cm);
 }
 int dftfe_b200_accumulate_add_locally_owned(dftfe_b200_ctx *ctx, double *x_d, int32_t ncols) {
   DB_CTX(ctx);
+  DB_CHECK(ncols >= 1 && ncols <= ctx->B, "accumulate_add_locally_owned: ncols (%d) must be in [1, cheby_block=%d]", ncols,
+           ctx->B);
   return ghost_accumulate(ctx, x_d, ncols * ctx->cm, ncols * ctx->cm, nullptr);
 }
 int dftfe_b200_zero_out_ghosts(dftfe_b200_ctx *ctx, double *x_d, int32_t ncols) {
@@ -586,6 +603,11 @@ int dftfe_b200_set_option(dftfe_b200_ctx *ctx, const char *name, int32_t value) 
     ctx->reserved_sms = value;
     return 0;
   }
+  if (std::strcmp(name, "p2p_exchange") == 0) {
+    DB_CHECK(!ctx->p2p.tried, "set_option: p2p_exchange must be chosen before the first ghost exchange");
+    ctx->p2p.requested = value;
+    return 0;
+  }
   if (std::strcmp(name, "overlap_lanes") == 0) {
     ctx->overlap_lanes = value;
     return 0;
@@ -634,5 +656,7 @@ int dftfe_b200_profile_reset(dftfe_b200_ctx *ctx) {
 }
 
 int64_t dftfe_b200_launch_count(dftfe_b200_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+const char *dftfe_b200_transport_name(dftfe_b200_ctx *ctx) { return ctx ? transport_name(ctx) : ""; }
 
 }  // extern "C"

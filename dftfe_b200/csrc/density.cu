@@ -244,11 +244,7 @@ __global__ void expand_weights_kernel(const double *__restrict__ f, int j0, int 
 template <int NODES>
 int launch_density(dftfe_b200_ctx *ctx, const double *x, int ldx, int nColTiles, int nq, int passes, double *rho) {
   using D = DCfg<NODES>;
-  static bool attr = false;
-  if (!attr) {
-    DB_CUDA(cudaFuncSetAttribute(density_kernel<NODES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)D::SMEM));
-    attr = true;
-  }
+  DB_DYN_SMEM(ctx, density_kernel<NODES>, D::SMEM);
   ProfScope ps(ctx, "density");
   const int grid = (int)std::min<int64_t>(ctx->nC, ctx->num_sms);
   density_kernel<NODES><<<grid, THREADS, D::SMEM, ctx->stream>>>(ctx->denNf.p, ctx->cellRowsFlagged.p, ctx->nC, x, ldx,

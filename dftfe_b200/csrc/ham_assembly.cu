@@ -225,11 +225,7 @@ int compute_cell_hamiltonian(dftfe_b200_ctx *ctx, int nq, const double *shapeVal
   DB_CHECK(!ctx->cplx, "compute_cell_hamiltonian: the k-point (complex) terms are not provided");
   DB_CHECK(nq >= 1 && shapeValues && vEffJxW && gradIntegral && H, "compute_cell_hamiltonian: null argument");
   if (ctx->nC == 0) return 0;
-  static bool attr = false;
-  if (!attr) {
-    DB_CUDA(cudaFuncSetAttribute(ham_assemble_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM));
-    attr = true;
-  }
+  DB_DYN_SMEM(ctx, ham_assemble_kernel, SMEM);
   const int n = ctx->n;
   const int npad = ((n + TM - 1) / TM) * TM;
   const int nqPad = ((nq + KC - 1) / KC) * KC;

@@ -192,7 +192,7 @@ int nonlocal_setup(dftfe_b200_ctx *ctx, int kpt, int32_t nAtoms, const int32_t *
   DB_TRY(ns.rowStart.upload(rowStart.data(), rowStart.size(), ctx->stream));
   DB_TRY(ns.entProj.upload(entProj.data(), entProj.size(), ctx->stream));
   DB_TRY(ns.entVal.upload(entVal.data(), entVal.size(), ctx->stream));
-  DB_TRY(ctx->nlProj.alloc((size_t)std::max(totalProj, 1) * ctx->B * cm));
+  for (int l = 0; l < 2; ++l) DB_TRY(ctx->nlProj[l].alloc((size_t)std::max(totalProj, 1) * ctx->B * cm));
   ctx->nl = totalProj > 0 ? &ns : nullptr;
   return 0;
 }
@@ -207,14 +207,14 @@ int nonlocal_project(dftfe_b200_ctx *ctx, const double *x, int ncols, int ldx, c
     if (ctx->cplx)
       nl_project_kernel<2><<<grid, block, 0, ctx->stream>>>(x, ncols, ldx, ns.atomRowStart.p, ns.atomRows.p,
                                                             ns.atomValStart.p, ns.vals.p, ns.projOffset.p,
-                                                            rowScaleIn, ctx->nlProj.p);
+                                                            rowScaleIn, ctx->nlProj[ctx->lane].p);
     else
       nl_project_kernel<1><<<grid, block, 0, ctx->stream>>>(x, ncols, ldx, ns.atomRowStart.p, ns.atomRows.p,
                                                             ns.atomValStart.p, ns.vals.p, ns.projOffset.p,
-                                                            rowScaleIn, ctx->nlProj.p);
+                                                            rowScaleIn, ctx->nlProj[ctx->lane].p);
     DB_CUDA(cudaGetLastError());
   }
-  return allreduce_sum(ctx, ctx->nlProj.p, (size_t)ns.totalProj * ncols);
+  return allreduce_sum(ctx, ctx->nlProj[ctx->lane].p, (size_t)ns.totalProj * ncols);
 }
 
 // y += s * (out o Chat) V proj
@@ -226,10 +226,10 @@ int nonlocal_apply(dftfe_b200_ctx *ctx, double *y, int ncols, int ldx, const dou
   const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)ctx->num_sms * 16);
   if (ctx->cplx)
     nl_apply_kernel<2><<<grid, 256, 0, ctx->stream>>>(y, ncols, ldx, ns.nRows, ns.rowList.p, ns.rowStart.p,
-                                                      ns.entProj.p, ns.entVal.p, ns.V.p, ctx->nlProj.p, rowScaleOut, s);
+                                                      ns.entProj.p, ns.entVal.p, ns.V.p, ctx->nlProj[ctx->lane].p, rowScaleOut, s);
   else
     nl_apply_kernel<1><<<grid, 256, 0, ctx->stream>>>(y, ncols, ldx, ns.nRows, ns.rowList.p, ns.rowStart.p,
-                                                      ns.entProj.p, ns.entVal.p, ns.V.p, ctx->nlProj.p, rowScaleOut, s);
+                                                      ns.entProj.p, ns.entVal.p, ns.V.p, ctx->nlProj[ctx->lane].p, rowScaleOut, s);
   DB_CUDA(cudaGetLastError());
   return 0;
 }

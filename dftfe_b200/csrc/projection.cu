@@ -340,11 +340,7 @@ bool dmma_projection_usable(const dftfe_b200_ctx *ctx, int N, int lda, int ldb, 
 // iGlobal/jGlobal).
 int launch_xty(dftfe_b200_ctx *ctx, const double *A, int lda, int iOff, const double *B, int ldb, int jOff,
                int nRowsC, int nColsC, int iGlobal, int jGlobal, bool lowerOnly, double *C, int ldc) {
-  static bool attr = false;
-  if (!attr) {
-    DB_CUDA(cudaFuncSetAttribute(xty_partial_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XTY_SMEM));
-    attr = true;
-  }
+  DB_DYN_SMEM(ctx, xty_partial_kernel, XTY_SMEM);
   std::vector<XtyTile> tiles;
   for (int j = 0; j < nColsC; j += TN)
     for (int i = 0; i < nRowsC; i += TM)
@@ -377,11 +373,7 @@ bool dmma_rotation_usable(int N, int Nout, int ldq, int ldo) {
 // Out[rows x Nout] (ld ldo) = X[rows x N] (ld N) * Q[N x Nout] (row-major, ld ldq)
 int launch_xq(dftfe_b200_ctx *ctx, const double *X, int N, int64_t rows, const double *Qrm, int ldq, int Nout,
               double *Out, int ldo) {
-  static bool attr = false;
-  if (!attr) {
-    DB_CUDA(cudaFuncSetAttribute(xq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)XQ_SMEM));
-    attr = true;
-  }
+  DB_DYN_SMEM(ctx, xq_kernel, XQ_SMEM);
   if (rows == 0) return 0;
   ProfScope ps(ctx, "rotation");
   const int64_t items = ((rows + TM - 1) / TM) * (Nout / TN);

@@ -869,16 +869,17 @@ static int filter_blocks_impl(dftfe_b200_ctx *ctx, double *Xd, double *Xh, int N
   double *by[2] = {ctx->blockY.p, ctx->blockY2.p};
   const size_t rowBytes = (size_t)B * cm * sizeof(double), pitchBytes = (size_t)N * cm * sizeof(double);
   const int nGroups = (nb + nl - 1) / nl;
-  std::vector<cudaEvent_t> evIn, evComp, evOut;
+  // events of the host-resident loop live in the context (created once, reused by every call)
+  cudaEvent_t *evIn = nullptr, *evComp = nullptr, *evOut = nullptr;
   if (host) {
-    evIn.resize(nb);
-    evComp.resize(nb);
-    evOut.resize(nb);
-    for (int i = 0; i < nb; ++i) {
-      DB_CUDA(cudaEventCreateWithFlags(&evIn[i], cudaEventDisableTiming));
-      DB_CUDA(cudaEventCreateWithFlags(&evComp[i], cudaEventDisableTiming));
-      DB_CUDA(cudaEventCreateWithFlags(&evOut[i], cudaEventDisableTiming));
+    while ((int)ctx->hostLoopEvents.size() < 3 * nb) {
+      cudaEvent_t e;
+      DB_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      ctx->hostLoopEvents.push_back(e);
     }
+    evIn = ctx->hostLoopEvents.data();
+    evComp = evIn + nb;
+    evOut = evComp + nb;
   }
   DB_CUDA(cudaEventRecord(ctx->forkEvent, mainStream));
   for (int l = 0; l < nl; ++l) DB_CUDA(cudaStreamWaitEvent(ctx->laneStream[l], ctx->forkEvent, 0));
@@ -951,8 +952,6 @@ static int filter_blocks_impl(dftfe_b200_ctx *ctx, double *Xd, double *Xh, int N
   } else {
     cudaDeviceSynchronize();
   }
-  for (auto &v : {&evIn, &evComp, &evOut})
-    for (cudaEvent_t e : *v) cudaEventDestroy(e);
   return rc;
 }
 
@@ -1003,8 +1002,9 @@ static int solve_impl(dftfe_b200_ctx *ctx, double *X, double *XFrac, int N, cons
   unsigned int order = p->chebyshev_order;
   if (order == 0) {
     order = set_chebyshev_order(ctx->bUp);
-    if (p->use_cgs_rr == 0 && !p->is_pseudopotential) {
-      // orthogType == "CGS" on device and all-electron: half degree (solver .cc:314-316)
+    if (!p->is_pseudopotential) {
+      // orthogType is always "CGS" on the device path (Auto -> CGS, GS throws) whichever projection is used:
+      // all-electron runs filter at half the tabulated degree (solver .cc:314-316)
       order = (unsigned int)(order * 0.5);
     }
   }

@@ -305,6 +305,62 @@ pack_rows_vec_kernel(const double *__restrict__ x, int ncols, int ldx, int64_t n
   }
 }
 
+// Peer-memory push of the ghost exchange (comm.cu, "p2p" transport): row i of the outgoing payload (x[rows[i], :] or
+// the contiguous row row0 + i) is stored STRAIGHT into the receive buffer of the rank that needs it - a peer-mapped
+// pointer over NVLink (cudaIpc) - instead of a local send buffer + ncclSend/ncclRecv.  Rows are grouped in
+// segments (one per destination rank, MPIPatternP2P order); segs.dst[s] is the address of segment s's first row in
+// the peer's buffer.  16-byte stores, one warp per row: the NVLink writes are fully coalesced 256-byte+ bursts.
+template <typename TOUT>
+__global__ void __launch_bounds__(256)
+push_rows_vec_kernel(const double *__restrict__ x, int ncols, int ldx, int64_t nRows,
+                     const uint32_t *__restrict__ rows, int64_t row0, PushSegs segs) {
+  const WarpRows w;
+  for (int64_t i = w.first; i < nRows; i += w.step) {
+    int sgm = 0;
+    while (sgm + 1 < segs.n && i >= segs.start[sgm + 1]) ++sgm;
+    const double *in = x + (size_t)(rows ? (int64_t)rows[i] : row0 + i) * ldx;
+    TOUT *out = reinterpret_cast<TOUT *>(segs.dst[sgm]) + (size_t)(i - segs.start[sgm]) * ncols;
+    for (int c0 = w.lane * 2; c0 < ncols; c0 += 64 * VU) {
+      double2 v[VU];
+#pragma unroll
+      for (int u = 0; u < VU; ++u) v[u] = (c0 + 64 * u < ncols) ? ld2(in + c0 + 64 * u) : make_double2(0.0, 0.0);
+#pragma unroll
+      for (int u = 0; u < VU; ++u)
+        if (c0 + 64 * u < ncols) {
+          if constexpr (sizeof(TOUT) == 8)
+            st2(reinterpret_cast<double *>(out) + c0 + 64 * u, v[u]);
+          else
+            *reinterpret_cast<float2 *>(out + c0 + 64 * u) = make_float2((float)v[u].x, (float)v[u].y);
+        }
+    }
+  }
+}
+
+// scalar fallback (odd column counts / unaligned rows), FP64 payload
+__global__ void push_rows_kernel(const double *__restrict__ x, int ncols, int ldx, int64_t nRows,
+                                 const uint32_t *__restrict__ rows, int64_t row0, PushSegs segs) {
+  const int64_t total = nRows * ncols;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t i = idx / ncols;
+    const int c = idx % ncols;
+    int sgm = 0;
+    while (sgm + 1 < segs.n && i >= segs.start[sgm + 1]) ++sgm;
+    reinterpret_cast<double *>(segs.dst[sgm])[(size_t)(i - segs.start[sgm]) * ncols + c] =
+        x[(size_t)(rows ? (int64_t)rows[i] : row0 + i) * ldx + c];
+  }
+}
+
+// flag[t] = value on up to 32 (peer-mapped) addresses, release semantics at system scope: everything the stream
+// wrote before this kernel (the pushed rows) is visible to the peer once it sees the flag
+__global__ void signal_flags_kernel(SignalList l, uint32_t value) {
+  const int t = threadIdx.x;
+  if (t < l.n) {
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(l.addr[t]), "r"(value) : "memory");
+  }
+}
+
 // contiguous rows [row0, row0+nRows) of x <- dense buffer (ghost segment fill)
 template <typename TIN>
 __global__ void __launch_bounds__(256)
@@ -642,6 +698,35 @@ int launch_pack_rows_f32(dftfe_b200_ctx *ctx, const double *x, int ncols, int ld
   DB_CHECK(vec_ok(x, ncols, ldx), "FP32 ghost payload needs an even column count and 16-byte aligned rows");
   ProfScope ps(ctx, "ghost_pack");
   pack_rows_vec_kernel<float><<<grid_rows(ctx, pack_rows_vec_kernel<float>, nRows), 256, 0, ctx->stream>>>(x, ncols, ldx, nRows, rows, row0, buf);
+  DB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// p2p transport: push rows into the peers' receive buffers (see push_rows_vec_kernel)
+int launch_push_rows(dftfe_b200_ctx *ctx, const double *x, int ncols, int ldx, int64_t nRows, const uint32_t *rows,
+                     int64_t row0, const PushSegs &segs, bool fp32) {
+  if (nRows == 0) return 0;
+  ProfScope ps(ctx, "ghost_pack");
+  bool aligned = vec_ok(x, ncols, ldx) && !ctx->force_scalar_row_kernels;
+  for (int s = 0; s < segs.n; ++s) aligned = aligned && ((reinterpret_cast<uintptr_t>(segs.dst[s]) & 15) == 0);
+  if (fp32) {
+    DB_CHECK(vec_ok(x, ncols, ldx), "FP32 ghost payload needs an even column count and 16-byte aligned rows");
+    push_rows_vec_kernel<float><<<grid_rows(ctx, push_rows_vec_kernel<float>, nRows), 256, 0, ctx->stream>>>(
+        x, ncols, ldx, nRows, rows, row0, segs);
+  } else if (aligned) {
+    push_rows_vec_kernel<double><<<grid_rows(ctx, push_rows_vec_kernel<double>, nRows), 256, 0, ctx->stream>>>(
+        x, ncols, ldx, nRows, rows, row0, segs);
+  } else {
+    push_rows_kernel<<<grid_for(ctx, nRows * ncols), 256, 0, ctx->stream>>>(x, ncols, ldx, nRows, rows, row0, segs);
+  }
+  DB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int launch_signal_flags(dftfe_b200_ctx *ctx, const SignalList &l, uint32_t value) {
+  if (l.n == 0) return 0;
+  ctx->launches += 1;
+  signal_flags_kernel<<<1, 32, 0, ctx->stream>>>(l, value);
   DB_CUDA(cudaGetLastError());
   return 0;
 }

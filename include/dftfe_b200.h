@@ -324,7 +324,11 @@ int dftfe_b200_get_spectrum_bounds(dftfe_b200_ctx *ctx, double out_h[3]);
  * taken anyway for ragged column counts, odd leading dimensions and FE order 7);
  * "scalar_row_kernels" = 1 forces the scalar fallbacks of the HBM-bound row kernels (odd column counts);
  * "overlap_lanes" = 0 / 1: one / two (default) wavefunction blocks in flight in the blocked filter loop;
- * "cublas_projections" = 1: cuBLAS Dgemm instead of the DMMA projection / rotation kernels (A/B). */
+ * "cublas_projections" = 1: cuBLAS Dgemm instead of the DMMA projection / rotation kernels (A/B);
+ * "p2p_exchange" = -1 / 0 / 1 (before the first exchange; same value on every rank): transport of the ghost exchange -
+ * auto (default: peer-mapped buffers when every neighbour can be mapped, else NCCL send/recv), NCCL send/recv,
+ * or peer-mapped buffers required (also available between the in-process ranks of a loopback group);
+ * "reserved_sms" = n: the persistent cell kernel uses (SM count - n) CTAs (tests force a tiny grid with it). */
 int dftfe_b200_set_option(dftfe_b200_ctx *ctx, const char *name, int32_t value);
 /* Number of cell colours, and per-colour cell counts (n_out entries filled). */
 int dftfe_b200_get_colouring(dftfe_b200_ctx *ctx, int32_t *n_colours_out, int32_t *cell_colour_out_h);
@@ -334,6 +338,11 @@ int dftfe_b200_get_colouring(dftfe_b200_ctx *ctx, int32_t *n_colours_out, int32_
 int dftfe_b200_profile_enable(dftfe_b200_ctx *ctx, int32_t enable);
 int dftfe_b200_profile_get(dftfe_b200_ctx *ctx, const char *name, double *total_ms_out, int64_t *launches_out);
 int dftfe_b200_profile_reset(dftfe_b200_ctx *ctx);
+/* FP64 tensor-pipe (DMMA.8x8x4) issue rate of the context's device in TFLOP/s, measured now with a register-only
+ * probe kernel (~15 ms): the roofline denominator of the cell kernel and the projections (bench.py). */
+int dftfe_b200_measure_fp64_tensor_peak(dftfe_b200_ctx *ctx, double *tflops_out);
+/* Which transport the ghost exchange uses (decided at the first exchange): static string. */
+const char *dftfe_b200_transport_name(dftfe_b200_ctx *ctx);
 /* Total number of kernels this library launched on the context since creation. */
 int64_t dftfe_b200_launch_count(dftfe_b200_ctx *ctx);
 

@@ -20,7 +20,7 @@ pre-scaled state (linearAlgebraOperationsDevice.cc:531-727), which must agree.
 All ``file:line`` citations are relative to the reference tree (dftfeDevelopers/dftfe).
 
 Multi-rank runs are emulated in one process: ``ranks`` is a list of
-``RankProblem`` (dftfe_b200.femesh) and every distributed multivector is a list
+``RankProblem`` (tools.femesh) and every distributed multivector is a list
 of per-rank arrays of shape ``(M_r + G_r, B)`` - row-major, wavefunction index
 fastest, ghosts after the owned rows (include/MultiVector.h:41-75).
 """

@@ -1,7 +1,7 @@
 """Shared helpers for the parity tests (oracle side lives in oracle/)."""
 import numpy as np
 
-from dftfe_b200.femesh import build_mesh, gaussian_wells_potential
+from tools.femesh import build_mesh, gaussian_wells_potential
 
 
 def make_problem(p, ncells, h=1.0, periodic=(True, True, True), nranks=1, vquad="gauss", potential=True,
@@ -74,7 +74,7 @@ def make_adaptive_problem(p, ncoarse=(3, 3, 3), H=1.4, nranks=1, radius=0.8, n_a
                           half=False):
     """One level of 2:1 refinement around the box centre (real hanging nodes), non-periodic, Dirichlet - the mesh
     class of BASELINE configs[0] / configs[3]."""
-    from dftfe_b200.femesh_adaptive import build_adaptive_mesh
+    from tools.femesh_adaptive import build_adaptive_mesh
 
     box = np.array(ncoarse) * H
 

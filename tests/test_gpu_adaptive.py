@@ -130,7 +130,7 @@ def test_cell_hamiltonian_assembly(capi, p, adaptive):
         mesh, ranks = make_problem(p, (2, 3, 2), 1.2, (True, True, False))
     rp = ranks[0]
     ref = mesh.ref
-    from dftfe_b200.femesh import gaussian_wells_potential
+    from tools.femesh import gaussian_wells_potential
     pot = gaussian_wells_potential(mesh.box, periodic=mesh.periodic)
     cells = mesh.owned_cells(0)
     origin, scale = mesh.cell_origin_scale(cells)

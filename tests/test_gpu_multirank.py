@@ -33,8 +33,11 @@ def _run_ranks(nranks, fn):
     return out
 
 
+@pytest.mark.parametrize("p2p", [0, 1])
 @pytest.mark.parametrize("nranks,rank_grid,group", [(2, None, 11), (4, (2, 2, 1), 12), (8, (2, 2, 2), 13)])
-def test_loopback_multirank_filter_and_projections(lib_built, nranks, rank_grid, group):
+def test_loopback_multirank_filter_and_projections(lib_built, nranks, rank_grid, group, p2p):
+    """p2p = 1: the peer-memory transport (rows pushed into the peer rank's receive buffer, sequence-number
+    hand-shake with stream memory operations) between the in-process ranks; p2p = 0: host-synchronised copies."""
     assert torch.cuda.is_available()
     from dftfe_b200 import capi
     from oracle import chfsi_oracle as O
@@ -55,7 +58,8 @@ def test_loopback_multirank_filter_and_projections(lib_built, nranks, rank_grid,
     def rank_fn(r):
         rp = ranks[r]
         op = capi.Operator(rp, B, use_torch_stream=False)
-        op.comm_init_loopback(group, r, nranks)
+        op.comm_init_loopback(group + 100 * p2p, r, nranks)
+        op.set_option("p2p_exchange", p2p)
         op.set_cell_hamiltonian(rp.H)
         x_d = _dev(X[r][:, :B])
         y_d = torch.empty_like(x_d)
@@ -71,6 +75,7 @@ def test_loopback_multirank_filter_and_projections(lib_built, nranks, rank_grid,
         op.sync()
         H_h = S.cpu().numpy()
         bounds = op.lanczosLowerUpperBoundEigenSpectrum()
+        assert ("p2p" in op.transport_name()) == bool(p2p)
         op.close()
         return filt, S_h, H_h, bounds
 
@@ -120,3 +125,60 @@ def test_loopback_multirank_solve(lib_built):
     for eig, res in out:
         assert np.abs(eig - ev_ref).max() < 1e-8
         assert np.abs(res - res_ref).max() < 1e-6
+
+
+@pytest.mark.parametrize("nranks,rank_grid", [(2, None), (4, (2, 2, 1))])
+def test_p2p_transport_two_lane_filter_fp64_and_fp32_payloads(lib_built, nranks, rank_grid):
+    """Blocked two-lane filter loop over the peer-memory transport: FP64 payloads match the oracle and are
+    bit-identical to the host-synchronised transport and to the single-lane schedule; FP32 payloads
+    (useMixedPrecCheby) match the oracle's FP32 restatement."""
+    from dftfe_b200 import capi
+    from oracle import chfsi_oracle as O
+
+    p, B, N, m = 2, 32, 160, 7   # 5 blocks: the last group holds a single block
+    mesh, ranks = make_problem(p, (4, 4, 4), 1.1, (True, True, True), nranks=nranks, rank_grid=rank_grid,
+                               extra_constraints=hanging_like_constraints(4), n_atoms=2)
+    Xs = scatter_to_ranks(ranks, random_global(mesh, N, seed=10), loewdin=True)
+    a, b, a0 = 5.0, 60.0, -2.0
+    ref64 = [x.copy() for x in Xs]
+    ref32 = [x.copy() for x in Xs]
+    for j in range(0, N, B):
+        blk = [np.ascontiguousarray(x[:, j:j + B]) for x in Xs]
+        o64 = O.chebyshev_filter_device_state(ranks, blk, m, a, b, a0)
+        o32 = O.chebyshev_filter_device_state(ranks, blk, m, a, b, a0, mixed_prec=True)
+        for r in range(nranks):
+            ref64[r][:, j:j + B] = o64[r]
+            ref32[r][:, j:j + B] = o32[r]
+    scale = max(np.abs(x).max() for x in ref64)
+
+    def make_rank_fn(p2p, group):
+        def rank_fn(r):
+            rp = ranks[r]
+            op = capi.Operator(rp, B, use_torch_stream=False)
+            op.comm_init_loopback(group, r, nranks)
+            op.set_option("p2p_exchange", p2p)
+            op.set_cell_hamiltonian(rp.H)
+            res = {}
+            for name, lanes, mixed in (("two_lanes", 1, False), ("one_lane", 0, False), ("fp32", 1, True)):
+                op.set_option("overlap_lanes", lanes)
+                Xd = _dev(Xs[r][:rp.M])
+                for _ in range(2):   # twice: sequence numbers / buffer reuse across calls
+                    Xd.copy_(_dev(Xs[r][:rp.M]))
+                    op.chebyshevFilterAll(Xd, m, a, b, a0, mixedPrec=mixed)
+                    op.sync()
+                res[name] = Xd.cpu().numpy()
+            op.close()
+            return res
+
+        return rank_fn
+
+    out_p2p = _run_ranks(nranks, make_rank_fn(1, 300 + nranks))
+    out_host = _run_ranks(nranks, make_rank_fn(0, 310 + nranks))
+    for r in range(nranks):
+        M = ranks[r].M
+        assert np.abs(out_p2p[r]["two_lanes"] - ref64[r][:M]).max() < m * 1e-12 * scale
+        assert np.array_equal(out_p2p[r]["two_lanes"], out_p2p[r]["one_lane"])
+        assert np.array_equal(out_p2p[r]["two_lanes"], out_host[r]["two_lanes"])
+        assert np.abs(out_p2p[r]["fp32"] - ref32[r][:M]).max() < 2e-5 * scale
+        assert np.array_equal(out_p2p[r]["fp32"], out_host[r]["fp32"])
+        assert np.abs(out_p2p[r]["fp32"] - out_p2p[r]["two_lanes"]).max() > 0

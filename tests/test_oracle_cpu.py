@@ -6,7 +6,7 @@ import os
 import numpy as np
 import pytest
 
-from dftfe_b200.femesh import ReferenceCell, build_mesh, gll_points_weights
+from tools.femesh import ReferenceCell, build_mesh, gll_points_weights
 from oracle import chfsi_oracle as O
 from tests.helpers import hanging_like_constraints, make_problem, random_global, scatter_to_ranks
 
@@ -69,7 +69,7 @@ def test_plane_wave_eigenvalues_periodic_box():
 
 def test_harmonic_oscillator_levels():
     """v = 1/2 r^2 in a large Dirichlet box: levels n + 3/2 (known answer ii)."""
-    from dftfe_b200.femesh import build_mesh
+    from tools.femesh import build_mesh
 
     mesh = build_mesh(6, (2, 2, 2), 6.0, periodic=(False, False, False))
     c = np.array(mesh.box) / 2.0
@@ -225,8 +225,8 @@ def test_golden_fixture():
 
 
 def _adaptive(p=3, nranks=1, ncoarse=(3, 3, 3), H=1.4, potential=True):
-    from dftfe_b200.femesh import gaussian_wells_potential
-    from dftfe_b200.femesh_adaptive import build_adaptive_mesh
+    from tools.femesh import gaussian_wells_potential
+    from tools.femesh_adaptive import build_adaptive_mesh
 
     box = np.array(ncoarse) * H
 
@@ -359,7 +359,7 @@ def test_spectrum_split_and_no_rr_statements():
 def test_cell_hamiltonian_and_density_statements():
     """hamMatrixKernelLDA / computeRhoFromPSI restatements: the assembled matrices equal the generator's, and the
     GLL-sampled density of M-orthonormal vectors integrates to the electron count."""
-    from dftfe_b200.femesh import gaussian_wells_potential
+    from tools.femesh import gaussian_wells_potential
 
     mesh, ranks = make_problem(3, (3, 2, 2), 1.3, (True, True, True), nranks=2)
     ref = mesh.ref

@@ -50,7 +50,7 @@ def main():
     import torch
 
     from dftfe_b200 import capi
-    from dftfe_b200.femesh import build_mesh
+    from tools.femesh import build_mesh
 
     peaks = {}
     try:
