@@ -9,7 +9,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = HERE / "lib" / "libdftfe_b200.so"
-SOURCES = ["context.cu", "cell_matvec.cu", "vector_kernels.cu", "comm.cu", "solver.cu", "projection.cu", "nonlocal.cu", "mixed_precision.cu", "ham_assembly.cu", "density.cu", "diagnostics.cu"]
+SOURCES = ["context.cu", "cell_matvec.cu", "vector_kernels.cu", "comm.cu", "solver.cu", "projection.cu", "nonlocal.cu", "mixed_precision.cu", "ham_assembly.cu", "density.cu", "diagnostics.cu", "tf32_gemm.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -473,6 +473,12 @@ static int exchange_p2p(dftfe_b200_ctx *ctx, bool forward, double *x, int ncols,
   else
     DB_TRY(launch_push_rows(ctx, x, ncols, ldx, ctx->G, nullptr, ctx->M, segs, fp32));
   DB_TRY(launch_signal_flags(ctx, sig, seq));
+  // In-process ranks share ONE device: a device-synchronising call (cudaFree, ...) made by one rank's host thread
+  // waits for every rank's streams, so a stream must never wait on work a sibling thread has not submitted yet.
+  // The host barrier guarantees every rank's signal is enqueued before anyone enqueues the wait (test transport
+  // only - separate processes on separate devices need no host hand-shake).
+  LoopbackGroup *inproc = ctx->nccl ? nullptr : loopback_of(ctx);
+  if (inproc) inproc->barrier();
   // 3. wait for every source's payload, unpack, acknowledge
   for (int q : srcProcs) DB_TRY(p2p_wait(ctx, dir, P2P_DATA, q, seq));
   char *recv = p.slab + (forward ? p.offRecvF[lane] : p.offRecvR[lane]);
@@ -491,7 +497,9 @@ static int exchange_p2p(dftfe_b200_ctx *ctx, bool forward, double *x, int ncols,
   ack.n = (int)srcProcs.size();
   for (int s = 0; s < ack.n; ++s)
     ack.addr[s] = p2p_flag(p.peerSlab[srcProcs[s]], p.peerOffFlags[srcProcs[s]], nr, lane, dir, P2P_ACK, ctx->rank);
-  return launch_signal_flags(ctx, ack, seq);
+  DB_TRY(launch_signal_flags(ctx, ack, seq));
+  if (inproc) inproc->barrier();  // the next exchange's ACK wait must find this acknowledgement submitted
+  return 0;
 }
 
 // forward: owned rows needed by my targets -> their ghost rows.  fp32: the payload travels as floats

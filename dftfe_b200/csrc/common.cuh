@@ -288,6 +288,8 @@ struct dftfe_b200_ctx {
   bool use_cublas_dense = false;                  // option "cublas_projections": A/B against cuBLAS Dgemm
   // mixed-precision projections / rotations (mixed_precision.cu)
   dftfe_b200::DevBuf<float> mpXsp, mpSp, mpBlockSp;
+  dftfe_b200::DevBuf<float> mpThi, mpTlo, mpBhi, mpBlo, mpQhi, mpQlo;  // TF32-exact hi / lo operand copies (tf32_gemm.cu)
+  dftfe_b200::DevBuf<float> tf32Ws;                                    // split-k partial tiles of the tcgen05 GEMM
   dftfe_b200::DevBuf<double> mpDp;
   dftfe_b200::DevBuf<float> arTmpF;
   dftfe_b200::DevBuf<double> hamNt, hamW;
@@ -369,6 +371,7 @@ int nonlocal_project(dftfe_b200_ctx *ctx, const double *x, int ncols, int ldx, c
 int nonlocal_apply(dftfe_b200_ctx *ctx, double *y, int ncols, int ldx, const double *rowScaleOut, double s);
 
 // projection.cu
+inline bool al16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }  // TMA bulk copies need it
 bool dmma_projection_usable(const dftfe_b200_ctx *ctx, int N, int lda, int ldb, int i0, int j0, int nRowsC,
                             int nColsC);
 int launch_xty(dftfe_b200_ctx *ctx, const double *A, int lda, int iOff, const double *B, int ldb, int jOff,
@@ -386,6 +389,16 @@ int compute_cell_hamiltonian(dftfe_b200_ctx *ctx, int nq, const double *shapeVal
 // density.cu
 int compute_density(dftfe_b200_ctx *ctx, const double *X, int N, const double *occ_h, int nq, const double *shapeValues,
                     double *rho);
+
+// tf32_gemm.cu: tcgen05 (kind::tf32, 3xTF32 split) GEMM of the FP32 blocks
+int launch_split_transpose(dftfe_b200_ctx *ctx, const double *X, int64_t ldx, int c0, int ncols, int64_t rows,
+                           float *Thi, float *Tlo, int64_t ldt);
+int launch_split_rows(dftfe_b200_ctx *ctx, const double *X, int64_t ldx, int ncols, int64_t rows, float *Xhi,
+                      float *Xlo, int64_t ldo);
+int launch_tf32x3_gemm(dftfe_b200_ctx *ctx, const float *Ahi, const float *Alo, int64_t nRowsA, int64_t pitchA,
+                       int rowA0, int rowsA, const float *Bhi, const float *Blo, int64_t nRowsB, int64_t pitchB,
+                       int rowB0, int rowsB, int64_t K, float *outRowMajor, int64_t ldo, float *outColMajor,
+                       int64_t ldc);
 
 // mixed_precision.cu
 int xtx_mixed_impl(dftfe_b200_ctx *ctx, const double *X, int N, double *S, bool commOnly = false);

@@ -9,10 +9,11 @@
 //   subspaceRotationCGSMixedPrecScalapack         :2243-2658  X <- X U (U = L^-T): diagonal blocks FP64,
 //                                                             off-diagonal FP32
 //   subspaceRotationRRMixedPrecScalapack          :2660-3076  X <- X diag(Q) (FP64) + X_sp (Q - diag Q)_sp (FP32)
-// The reference issues cuBLAS Sgemm for every FP32 block; so does this file (plain library GEMMs - the FP64
-// diagonal blocks go through the hand-written DMMA kernel of projection.cu).  The FP32 partial sums are
-// all-reduced as floats, like DeviceCCLWrapper::deviceDirectAllReduceMixedPrecGroupWrapper
-// (utils/DeviceDirectCCLWrapper.cc:196-261).
+// The reference issues cuBLAS Sgemm for every FP32 block.  Here they run on the tcgen05 tensor cores (tf32_gemm.cu:
+// kind::tf32 MMAs with TMEM accumulators, 3xTF32 operand split for FP32-class accuracy, TMA-fed stages); the FP64
+// diagonal blocks go through the hand-written DMMA kernel of projection.cu.  Option "cublas_projections" = 1 keeps the
+// cuBLAS Sgemm / Dgemm calls for A/B comparisons.  The FP32 partial sums are all-reduced as floats, like
+// DeviceCCLWrapper::deviceDirectAllReduceMixedPrecGroupWrapper (utils/DeviceDirectCCLWrapper.cc:196-261).
 #include <algorithm>
 
 #include "common.cuh"
@@ -44,15 +45,24 @@ __global__ void to_float_rows_kernel(const double *__restrict__ in, int64_t ldi,
 
 // Qsp (row-major N x N float) = off-diagonal part of Q; mode 1: the Bw x Bw diagonal blocks are dropped,
 // mode 2: only the diagonal entries.  qColMajor: Q(k,j) at k + j*N, else k*N + j.
+// Qthi / Qtlo (optional): the same off-diagonal part TRANSPOSED ([j][k], pitch ldt) and split in TF32-exact hi / lo
+// parts - the K-major B operand of the tcgen05 rotation GEMM.
 __global__ void split_rotation_kernel(const double *__restrict__ Q, int N, int qColMajor, int mode, int Bw,
-                                      float *__restrict__ Qsp, double *__restrict__ diag) {
+                                      float *__restrict__ Qsp, double *__restrict__ diag, float *__restrict__ Qthi,
+                                      float *__restrict__ Qtlo, int64_t ldt) {
   const int64_t total = (int64_t)N * N;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
     const int k = idx / N, j = idx % N;
     const double v = Q[qColMajor ? ((int64_t)k + (int64_t)j * N) : idx];
     const bool onDiag = mode == 1 ? (k / Bw == j / Bw) : (k == j);
-    Qsp[idx] = onDiag ? 0.0f : (float)v;
+    const float f = onDiag ? 0.0f : (float)v;
+    if (Qsp) Qsp[idx] = f;
+    if (Qthi) {
+      const float hi = __uint_as_float(__float_as_uint(f) & 0xffffe000u);
+      Qthi[(int64_t)j * ldt + k] = hi;
+      Qtlo[(int64_t)j * ldt + k] = __uint_as_float(__float_as_uint(f - hi) & 0xffffe000u);
+    }
     if (mode == 2 && k == j) diag[k] = v;
   }
 }
@@ -152,7 +162,7 @@ int xtx_mixed_impl(dftfe_b200_ctx *ctx, const double *X, int N, double *S, bool 
     DB_CUDA(cudaMemsetAsync(ctx->mpSp.p, 0, (size_t)N * N * sizeof(float), ctx->stream));
     DB_CUDA(cudaMemsetAsync(ctx->mpDp.p, 0, (size_t)N * Bw * sizeof(double), ctx->stream));
     if (M > 0) {
-      if (!ctx->use_cublas_dense && dmma_projection_usable(ctx, N, N, N, 0, 0, N, N)) {
+      if (!ctx->use_cublas_dense && al16(X) && dmma_projection_usable(ctx, N, N, N, 0, 0, N, N)) {
         DB_TRY(launch_xty(ctx, X, N, 0, X, N, 0, N, N, 0, 0, true, G, N));
       } else {
         const double one = 1.0, zero = 0.0;
@@ -178,26 +188,40 @@ int xtx_mixed_impl(dftfe_b200_ctx *ctx, const double *X, int N, double *S, bool 
     DB_CUDA(cudaGetLastError());
     return 0;
   }
-  DB_TRY(ctx->mpXsp.alloc((size_t)std::max<int64_t>(M, 1) * N));
+  const bool tc = !ctx->use_cublas_dense;           // tcgen05 3xTF32 kernel for the FP32 blocks
+  const int64_t Mp = (std::max<int64_t>(M, 1) + 3) / 4 * 4;  // pitch of the K-major (transposed) FP32 copies
+  if (tc) {
+    DB_TRY(ctx->mpThi.alloc((size_t)N * Mp));
+    DB_TRY(ctx->mpTlo.alloc((size_t)N * Mp));
+  } else {
+    DB_TRY(ctx->mpXsp.alloc((size_t)std::max<int64_t>(M, 1) * N));
+  }
   DB_TRY(ctx->mpSp.alloc((size_t)N * N));
   DB_TRY(ctx->mpDp.alloc((size_t)N * Bw));
   DB_CUBLAS(cublasSetStream(ctx->cublas, ctx->stream));
   DB_CUDA(cudaMemsetAsync(ctx->mpSp.p, 0, (size_t)N * N * sizeof(float), ctx->stream));
   DB_CUDA(cudaMemsetAsync(ctx->mpDp.p, 0, (size_t)N * Bw * sizeof(double), ctx->stream));
-  DB_TRY(to_float(ctx, X, N, ctx->mpXsp.p, N, N, M));
+  if (tc)
+    DB_TRY(launch_split_transpose(ctx, X, N, 0, N, M, ctx->mpThi.p, ctx->mpTlo.p, Mp));
+  else
+    DB_TRY(to_float(ctx, X, N, ctx->mpXsp.p, N, N, M));
   const double one = 1.0, zero = 0.0;
   const float onef = 1.0f, zerof = 0.0f;
   for (int j = 0; j < N && M > 0; j += Bw) {
     const int Bc = std::min(Bw, N - j), DRem = N - j - Bc;
     double *Cd = ctx->mpDp.p + (size_t)j * Bw;
-    if (!ctx->use_cublas_dense && dmma_projection_usable(ctx, N, N, N, j, j, Bc, Bc)) {
+    if (!ctx->use_cublas_dense && al16(X) && dmma_projection_usable(ctx, N, N, N, j, j, Bc, Bc)) {
       DB_TRY(launch_xty(ctx, X, N, j, X, N, j, Bc, Bc, j, j, true, Cd, Bw));
     } else {
       ProfScope ps(ctx, "projection");
       DB_CUBLAS(cublasDgemm(ctx->cublas, CUBLAS_OP_N, CUBLAS_OP_T, Bc, Bc, (int)M, &one, X + j, N, X + j, N, &zero, Cd,
                             Bw));
     }
-    if (DRem > 0) {
+    if (DRem > 0 && tc) {
+      // S(j+Bc.., j..j+Bc) = X[:, j+Bc:]^T X[:, j:j+Bc], k = local DoFs (split-k)
+      DB_TRY(launch_tf32x3_gemm(ctx, ctx->mpThi.p, ctx->mpTlo.p, N, Mp, j + Bc, DRem, ctx->mpThi.p, ctx->mpTlo.p, N, Mp,
+                                j, Bc, M, nullptr, 0, ctx->mpSp.p + (j + Bc) + (size_t)j * N, N));
+    } else if (DRem > 0) {
       ProfScope ps(ctx, "projection_fp32");
       DB_CUBLAS(cublasSgemm(ctx->cublas, CUBLAS_OP_N, CUBLAS_OP_T, DRem, Bc, (int)M, &onef, ctx->mpXsp.p + j + Bc, N,
                             ctx->mpXsp.p + j, N, &zerof, ctx->mpSp.p + (j + Bc) + (size_t)j * N, N));
@@ -215,14 +239,26 @@ int xtx_mixed_impl(dftfe_b200_ctx *ctx, const double *X, int N, double *S, bool 
 int xthx_mixed_impl(dftfe_b200_ctx *ctx, const double *X, int N, int Noc, double *Hp, bool commOnly) {
   const int Bw = std::min(ctx->B, N);
   const int64_t M = ctx->M;
-  DB_TRY(ctx->mpXsp.alloc(commOnly ? 1 : (size_t)std::max<int64_t>(M, 1) * N));
+  const bool tc = !ctx->use_cublas_dense && !commOnly;
+  const int64_t Mp = (std::max<int64_t>(M, 1) + 3) / 4 * 4;
+  if (tc) {
+    DB_TRY(ctx->mpThi.alloc((size_t)N * Mp));
+    DB_TRY(ctx->mpTlo.alloc((size_t)N * Mp));
+    DB_TRY(ctx->mpBhi.alloc((size_t)Bw * Mp));
+    DB_TRY(ctx->mpBlo.alloc((size_t)Bw * Mp));
+  } else {
+    DB_TRY(ctx->mpXsp.alloc(commOnly ? 1 : (size_t)std::max<int64_t>(M, 1) * N));
+    DB_TRY(ctx->mpBlockSp.alloc((size_t)std::max<int64_t>(M, 1) * Bw));
+  }
   DB_TRY(ctx->mpSp.alloc((size_t)N * N));
-  DB_TRY(ctx->mpBlockSp.alloc((size_t)std::max<int64_t>(M, 1) * Bw));
   DB_TRY(ctx->denseW.alloc((size_t)N * N));
   double *G = ctx->denseW.p;
   DB_CUDA(cudaMemsetAsync(ctx->mpSp.p, 0, (size_t)N * N * sizeof(float), ctx->stream));
   DB_CUDA(cudaMemsetAsync(G, 0, (size_t)N * N * sizeof(double), ctx->stream));
-  if (!commOnly) DB_TRY(to_float(ctx, X, N, ctx->mpXsp.p, N, N, M));
+  if (tc && Noc >= Bw)  // only the columns an FP32 block touches: rows j.. of X^T for blocks ending inside Noc
+    DB_TRY(launch_split_transpose(ctx, X, N, 0, N, M, ctx->mpThi.p, ctx->mpTlo.p, Mp));
+  else if (!commOnly && !tc)
+    DB_TRY(to_float(ctx, X, N, ctx->mpXsp.p, N, N, M));
   const double one = 1.0, zero = 0.0;
   const float onef = 1.0f, zerof = 0.0f;
   for (int j = 0; j < N; j += Bw) {
@@ -230,12 +266,17 @@ int xthx_mixed_impl(dftfe_b200_ctx *ctx, const double *X, int N, int Noc, double
     DB_TRY(apply_H_to_columns(ctx, X, N, j, Bc));  // blockY = H~ X[:, j:j+Bc]  (M x Bc)
     if (M == 0) continue;
     DB_CUBLAS(cublasSetStream(ctx->cublas, ctx->stream));
-    if (j + Bc <= Noc && !commOnly) {
+    if (j + Bc <= Noc && tc) {
+      // Hp(j.., j..j+Bc) = X[:, j:]^T (H~ X)[:, j:j+Bc] in FP32 on the tcgen05 tensor cores
+      DB_TRY(launch_split_transpose(ctx, ctx->blockY.p, Bc, 0, Bc, M, ctx->mpBhi.p, ctx->mpBlo.p, Mp));
+      DB_TRY(launch_tf32x3_gemm(ctx, ctx->mpThi.p, ctx->mpTlo.p, N, Mp, j, D, ctx->mpBhi.p, ctx->mpBlo.p, Bc, Mp, 0, Bc,
+                                M, nullptr, 0, ctx->mpSp.p + j + (size_t)j * N, N));
+    } else if (j + Bc <= Noc && !commOnly) {
       DB_TRY(to_float(ctx, ctx->blockY.p, Bc, ctx->mpBlockSp.p, Bc, Bc, M));
       ProfScope ps(ctx, "projection_fp32");
       DB_CUBLAS(cublasSgemm(ctx->cublas, CUBLAS_OP_N, CUBLAS_OP_T, D, Bc, (int)M, &onef, ctx->mpXsp.p + j, N,
                             ctx->mpBlockSp.p, Bc, &zerof, ctx->mpSp.p + j + (size_t)j * N, N));
-    } else if (!ctx->use_cublas_dense && dmma_projection_usable(ctx, N, N, Bc, j, 0, D, Bc)) {
+    } else if (!ctx->use_cublas_dense && al16(X) && dmma_projection_usable(ctx, N, N, Bc, j, 0, D, Bc)) {
       DB_TRY(launch_xty(ctx, X, N, j, ctx->blockY.p, Bc, 0, D, Bc, j, j, true, G + j + (size_t)j * N, N));
     } else {
       ProfScope ps(ctx, "projection");
@@ -273,14 +314,27 @@ int rotate_mixed_impl(dftfe_b200_ctx *ctx, double *X, int N, const double *Q, bo
   if (M == 0) return 0;
   const int Bw = std::min(ctx->B, N);
   const int64_t chunk = std::min<int64_t>(M, 148 * 128);
+  const bool tc = !ctx->use_cublas_dense;
+  const int64_t Np = ((int64_t)N + 3) / 4 * 4;       // pitch of the K-major FP32 operands (k = wavefunction index)
   DB_TRY(ctx->mpSp.alloc((size_t)N * N));            // Q off-diagonal part, FP32 row-major
   DB_TRY(ctx->mpDp.alloc((size_t)N * std::max(Bw, 1)));  // diag(Q) (mode 2)
   DB_TRY(ctx->mpXsp.alloc((size_t)chunk * N * 2));   // [chunk x N] FP32 copy of X, then the FP32 product
   float *Xsp = ctx->mpXsp.p, *Tsp = ctx->mpXsp.p + (size_t)chunk * N;
+  if (tc) {
+    DB_TRY(ctx->mpQhi.alloc((size_t)N * Np));
+    DB_TRY(ctx->mpQlo.alloc((size_t)N * Np));
+    DB_TRY(ctx->mpThi.alloc((size_t)chunk * Np));
+    DB_TRY(ctx->mpTlo.alloc((size_t)chunk * Np));
+    if (Np != N) {  // pad columns of Q^T must read as zero
+      DB_CUDA(cudaMemsetAsync(ctx->mpQhi.p, 0, (size_t)N * Np * sizeof(float), ctx->stream));
+      DB_CUDA(cudaMemsetAsync(ctx->mpQlo.p, 0, (size_t)N * Np * sizeof(float), ctx->stream));
+    }
+  }
   if (mode == 1) DB_TRY(ctx->rotScratch.alloc((size_t)chunk * N));
   ctx->launches += 1;
-  split_rotation_kernel<<<grid_for(ctx, (int64_t)N * N), 256, 0, ctx->stream>>>(Q, N, qColMajor ? 1 : 0, mode, Bw,
-                                                                               ctx->mpSp.p, ctx->mpDp.p);
+  split_rotation_kernel<<<grid_for(ctx, (int64_t)N * N), 256, 0, ctx->stream>>>(
+      Q, N, qColMajor ? 1 : 0, mode, Bw, ctx->mpSp.p, ctx->mpDp.p, tc ? ctx->mpQhi.p : nullptr,
+      tc ? ctx->mpQlo.p : nullptr, Np);
   DB_CUDA(cudaGetLastError());
   DB_CUBLAS(cublasSetStream(ctx->cublas, ctx->stream));
   const float onef = 1.0f, zerof = 0.0f;
@@ -288,8 +342,13 @@ int rotate_mixed_impl(dftfe_b200_ctx *ctx, double *X, int N, const double *Q, bo
   for (int64_t r0 = 0; r0 < M; r0 += chunk) {
     const int mc = (int)std::min<int64_t>(chunk, M - r0);
     double *Xc = X + (size_t)r0 * N;
-    DB_TRY(to_float(ctx, Xc, N, Xsp, N, N, mc));
-    {
+    if (tc) {
+      // T (row-major mc x N) = X (Q - diagonal part): A = X rows (k = wavefunction index), B = Q^T, no split-k
+      DB_TRY(launch_split_rows(ctx, Xc, N, N, mc, ctx->mpThi.p, ctx->mpTlo.p, Np));
+      DB_TRY(launch_tf32x3_gemm(ctx, ctx->mpThi.p, ctx->mpTlo.p, mc, Np, 0, mc, ctx->mpQhi.p, ctx->mpQlo.p, N, Np, 0, N,
+                                N, Tsp, N, nullptr, 0));
+    } else {
+      DB_TRY(to_float(ctx, Xc, N, Xsp, N, N, mc));
       ProfScope ps(ctx, "rotation_fp32");
       // T (row-major mc x N) = Xsp * Qsp  <=>  T_cm (N x mc) = Qsp_rm-as-cm (N x N) * Xsp_cm (N x mc)
       DB_CUBLAS(cublasSgemm(ctx->cublas, CUBLAS_OP_N, CUBLAS_OP_N, N, mc, N, &onef, ctx->mpSp.p, N, Xsp, N, &zerof,

@@ -68,6 +68,8 @@ constexpr size_t XTY_SMEM = XTY_STAGES * XTY_STAGE_DOUBLES * sizeof(double) + 2 
 
 struct XtyTile {
   int i0, j0;  // column offsets into A and B
+  int wa, wb;  // columns that exist (<= TM / TN, even): a ragged last tile copies only these; the stale (finite)
+               // values beyond them only reach rows / columns of the tile that the reduction masks
 };
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -116,12 +118,12 @@ xty_partial_kernel(const double *__restrict__ A, int lda, const double *__restri
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
         }
-        if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)(rows * (TM + TN) * sizeof(double)));
+        if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)(rows * (t.wa + t.wb) * sizeof(double)));
         __syncwarp();
         if (lane < rows)
-          tma_bulk_g2s(sA + lane * PITCH, A + (size_t)(m0 + lane) * lda + t.i0, TM * sizeof(double), &full[s]);
+          tma_bulk_g2s(sA + lane * PITCH, A + (size_t)(m0 + lane) * lda + t.i0, t.wa * sizeof(double), &full[s]);
         else if (lane >= 16 && lane - 16 < rows)
-          tma_bulk_g2s(sB + (lane - 16) * PITCH, B + (size_t)(m0 + lane - 16) * ldb + t.j0, TN * sizeof(double),
+          tma_bulk_g2s(sB + (lane - 16) * PITCH, B + (size_t)(m0 + lane - 16) * ldb + t.j0, t.wb * sizeof(double),
                        &full[s]);
       }
     }
@@ -207,10 +209,10 @@ xq_kernel(const double *__restrict__ X, int N, int64_t rows, const double *__res
   uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + XQ_STAGES * XQ_STAGE_DOUBLES * sizeof(double));
   uint64_t *empty = full + XQ_STAGES;
   const int tid = threadIdx.x, lane = tid & 31, pwarp = tid >> 5;
-  const int nColTiles = Nout / TN;
+  const int nColTiles = (Nout + TN - 1) / TN;
   const int64_t nRowBlocks = (rows + TM - 1) / TM;
   const int64_t nItems = nRowBlocks * nColTiles;
-  const int nK = N / XQ_KC;
+  const int nK = (N + XQ_KC - 1) / XQ_KC;
 
   for (int i = tid; i < (int)(XQ_STAGES * XQ_STAGE_DOUBLES); i += THREADS) st[i] = 0.0;
   if (tid == 0) {
@@ -229,23 +231,30 @@ xq_kernel(const double *__restrict__ X, int N, int64_t rows, const double *__res
       const int64_t m0 = (item / nColTiles) * TM;
       const int j0 = (int)(item % nColTiles) * TN;
       const int vrows = (int)min((long long)TM, (long long)(rows - m0));
+      const int nw = min(TN, Nout - j0);  // ragged last column tile: stale columns beyond nw are masked at the store
       for (int kc = 0; kc < nK; ++kc, ++n) {
         const int s = n % XQ_STAGES;
         const uint32_t ph = (n / XQ_STAGES) & 1;
         mbar_wait(&empty[s], ph ^ 1);
         double *sA = st + s * XQ_STAGE_DOUBLES;
         double *sB = sA + TM * XQ_PA;
-        if (vrows < TM) {  // ragged last row block: rows beyond the end must read as zero
-          for (int i = lane; i < (TM - vrows) * XQ_PA; i += 32) sA[vrows * XQ_PA + i] = 0.0;
+        const int kw = min(XQ_KC, N - kc * XQ_KC);  // ragged last k chunk
+        if (vrows < TM || kw < XQ_KC) {
+          // rows of X beyond the end must read as zero; a short k chunk zeroes the Q rows it does not load (the
+          // matching stale columns of the X stage are finite and multiply those zeros)
+          if (vrows < TM)
+            for (int i = lane; i < (TM - vrows) * XQ_PA; i += 32) sA[vrows * XQ_PA + i] = 0.0;
+          if (kw < XQ_KC)
+            for (int i = lane; i < (XQ_KC - kw) * PITCH; i += 32) sB[kw * PITCH + i] = 0.0;
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
           __syncwarp();
         }
-        if (lane == 0)
-          mbar_arrive_expect_tx(&full[s], (uint32_t)((vrows * XQ_KC + XQ_KC * TN) * sizeof(double)));
+        if (lane == 0) mbar_arrive_expect_tx(&full[s], (uint32_t)((vrows * kw + kw * nw) * sizeof(double)));
         __syncwarp();
         for (int r = lane; r < vrows; r += 32)
-          tma_bulk_g2s(sA + r * XQ_PA, X + (size_t)(m0 + r) * N + kc * XQ_KC, XQ_KC * sizeof(double), &full[s]);
-        tma_bulk_g2s(sB + lane * PITCH, Q + (size_t)(kc * XQ_KC + lane) * ldq + j0, TN * sizeof(double), &full[s]);
+          tma_bulk_g2s(sA + r * XQ_PA, X + (size_t)(m0 + r) * N + kc * XQ_KC, kw * sizeof(double), &full[s]);
+        if (lane < kw)
+          tma_bulk_g2s(sB + lane * PITCH, Q + (size_t)(kc * XQ_KC + lane) * ldq + j0, nw * sizeof(double), &full[s]);
       }
     }
   } else {
@@ -289,7 +298,8 @@ xq_kernel(const double *__restrict__ X, int N, int64_t rows, const double *__res
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
             const int col = j0 + wn * 32 + j * 8 + (lane & 3) * 2;
-            *reinterpret_cast<double2 *>(Out + (size_t)r * ldo + col) = make_double2(acc[i][j][0], acc[i][j][1]);
+            if (col < Nout)
+              *reinterpret_cast<double2 *>(Out + (size_t)r * ldo + col) = make_double2(acc[i][j][0], acc[i][j][1]);
           }
         }
       }
@@ -330,9 +340,9 @@ int pick_segments(int nTiles, int64_t nChunks, int nSms) {
 bool dmma_projection_usable(const dftfe_b200_ctx *ctx, int N, int lda, int ldb, int i0, int j0, int nRowsC,
                             int nColsC) {
   (void)ctx;
-  // full 128-wide tiles and 16-byte aligned row segments
-  return (nRowsC % TM == 0) && (nColsC % TN == 0) && (lda % 2 == 0) && (ldb % 2 == 0) && (i0 % 2 == 0) &&
-         (j0 % 2 == 0) && N > 0;
+  // 16-byte aligned row segments of even length (the last tile of a row / column of tiles may be ragged)
+  return (nRowsC % 2 == 0) && (nColsC % 2 == 0) && (lda % 2 == 0) && (ldb % 2 == 0) && (i0 % 2 == 0) &&
+         (j0 % 2 == 0) && N > 0 && nRowsC > 0 && nColsC > 0;
 }
 
 // C[iBase.., jBase..] (column-major, ld = ldc) = A[:, iBase:iBase+nRowsC]^T B[:, jBase:jBase+nColsC], lower tiles
@@ -344,13 +354,16 @@ int launch_xty(dftfe_b200_ctx *ctx, const double *A, int lda, int iOff, const do
   std::vector<XtyTile> tiles;
   for (int j = 0; j < nColsC; j += TN)
     for (int i = 0; i < nRowsC; i += TM)
-      if (!lowerOnly || (iGlobal + i + TM > jGlobal + j)) tiles.push_back(XtyTile{iOff + i, jOff + j});
+      if (!lowerOnly || (iGlobal + std::min(i + TM, nRowsC) > jGlobal + j))
+        tiles.push_back(XtyTile{iOff + i, jOff + j, std::min(TM, nRowsC - i), std::min(TN, nColsC - j)});
   const int nTiles = (int)tiles.size();
   if (nTiles == 0 || ctx->M == 0) return 0;
   const int64_t nChunks = (ctx->M + XTY_KC - 1) / XTY_KC;
   const int nSeg = pick_segments(nTiles, nChunks, ctx->num_sms);
   const int64_t chunksPerSeg = (nChunks + nSeg - 1) / nSeg;
-  DB_TRY(ctx->projTiles.upload(reinterpret_cast<const int32_t *>(tiles.data()), (size_t)nTiles * 2, ctx->stream));
+  DB_CHECK(((reinterpret_cast<uintptr_t>(A) | reinterpret_cast<uintptr_t>(B)) & 15) == 0,
+           "DMMA projection: operand base pointers must be 16-byte aligned");
+  DB_TRY(ctx->projTiles.upload(reinterpret_cast<const int32_t *>(tiles.data()), (size_t)nTiles * 4, ctx->stream));
   DB_TRY(ctx->projWs.alloc((size_t)nTiles * nSeg * TM * TN));
   {
     ProfScope ps(ctx, "projection", 2);
@@ -367,7 +380,7 @@ int launch_xty(dftfe_b200_ctx *ctx, const double *A, int lda, int iOff, const do
 }
 
 bool dmma_rotation_usable(int N, int Nout, int ldq, int ldo) {
-  return N % XQ_KC == 0 && Nout % TN == 0 && Nout > 0 && N % 2 == 0 && ldq % 2 == 0 && ldo % 2 == 0;
+  return Nout > 0 && N > 0 && Nout % 2 == 0 && N % 2 == 0 && ldq % 2 == 0 && ldo % 2 == 0;
 }
 
 // Out[rows x Nout] (ld ldo) = X[rows x N] (ld N) * Q[N x Nout] (row-major, ld ldq)
@@ -376,7 +389,9 @@ int launch_xq(dftfe_b200_ctx *ctx, const double *X, int N, int64_t rows, const d
   DB_DYN_SMEM(ctx, xq_kernel, XQ_SMEM);
   if (rows == 0) return 0;
   ProfScope ps(ctx, "rotation");
-  const int64_t items = ((rows + TM - 1) / TM) * (Nout / TN);
+  DB_CHECK(((reinterpret_cast<uintptr_t>(X) | reinterpret_cast<uintptr_t>(Qrm) | reinterpret_cast<uintptr_t>(Out)) & 15) == 0,
+           "DMMA rotation: operand base pointers must be 16-byte aligned");
+  const int64_t items = ((rows + TM - 1) / TM) * ((Nout + TN - 1) / TN);
   const int grid = (int)std::min<int64_t>(items, ctx->num_sms);
   xq_kernel<<<grid, THREADS, XQ_SMEM, ctx->stream>>>(X, N, rows, Qrm, ldq, Nout, Out, ldo);
   DB_CUDA(cudaGetLastError());

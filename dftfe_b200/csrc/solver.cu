@@ -297,7 +297,7 @@ static int xtx_impl(dftfe_b200_ctx *ctx, const double *X, int N, double *S) {
   }
   DB_CUBLAS(cublasSetStream(ctx->cublas, ctx->stream));
   DB_CUDA(cudaMemsetAsync(G, 0, (size_t)Nr * Nr * sizeof(double), ctx->stream));
-  if (ctx->M > 0 && !ctx->use_cublas_dense && dmma_projection_usable(ctx, Nr, Nr, Nr, 0, 0, Nr, Nr)) {
+  if (ctx->M > 0 && !ctx->use_cublas_dense && al16(X) && dmma_projection_usable(ctx, Nr, Nr, Nr, 0, 0, Nr, Nr)) {
     // hand-written DMMA kernel, lower-triangular 128x128 tiles of the whole matrix in one pass
     DB_TRY(launch_xty(ctx, X, Nr, 0, X, Nr, 0, Nr, Nr, 0, 0, true, G, Nr));
   } else if (ctx->M > 0) {
@@ -347,7 +347,7 @@ static int xthx_impl(dftfe_b200_ctx *ctx, const double *X, int N, double *Hp) {
     const int Bc = std::min(Bc0, N - j);
     const int jr = j * cm, Bcr = Bc * cm, D = Nr - jr;
     DB_TRY(apply_H_to_columns(ctx, X, N, j, Bc));
-    if (ctx->M > 0 && !ctx->use_cublas_dense && dmma_projection_usable(ctx, Nr, Nr, Bcr, jr, 0, D, Bcr)) {
+    if (ctx->M > 0 && !ctx->use_cublas_dense && al16(X) && dmma_projection_usable(ctx, Nr, Nr, Bcr, jr, 0, D, Bcr)) {
       DB_TRY(launch_xty(ctx, X, Nr, jr, ctx->blockY.p, Bcr, 0, D, Bcr, jr, jr, true, G + jr + (size_t)jr * Nr, Nr));
     } else if (ctx->M > 0) {
       ProfScope ps(ctx, "projection");
@@ -379,7 +379,8 @@ static int rotate_real(dftfe_b200_ctx *ctx, double *X, int N, const double *Q, b
   if (inPlace) DB_TRY(ctx->rotScratch.alloc((size_t)chunk * N));
   const double one = 1.0, zero = 0.0;
   DB_CUBLAS(cublasSetStream(ctx->cublas, ctx->stream));
-  const bool dmma = !ctx->use_cublas_dense && dmma_rotation_usable(N, Nout, N, ldo) && (c0 % 2 == 0);
+  const bool dmma = !ctx->use_cublas_dense && al16(X) && al16(Q) && (Out == nullptr || al16(Out)) &&
+                    dmma_rotation_usable(N, Nout, N, ldo) && (c0 % 2 == 0);
   const double *Qrm = Q;
   if (dmma && qColMajor) {  // the kernel wants Q(k, j) with j fastest
     DB_TRY(ctx->denseC.alloc((size_t)N * N));

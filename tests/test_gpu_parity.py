@@ -194,9 +194,10 @@ def test_projections_rotation_and_solve(capi):
     op.close()
 
 
-@pytest.mark.parametrize("N,B", [(128, 128), (256, 128), (384, 128)])
+@pytest.mark.parametrize("N,B", [(128, 128), (256, 128), (384, 128), (200, 100), (328, 164), (180, 90), (180, 45)])
 def test_dmma_projection_and_rotation_kernels(capi, N, B):
-    """Hand-written DMMA GEMMs (128-wide tiles, split-m partials, ragged last chunk) against the oracle
+    """Hand-written DMMA GEMMs (128-wide tiles, split-m partials, ragged last chunk, ragged last tile for N / B that
+    are not multiples of 128 - the reference's N = 1600 / B = 200 and N = 180 / B = 45 classes) against the oracle
     and against the cuBLAS path of the same entry points."""
     from oracle import chfsi_oracle as O
 

@@ -1,0 +1,251 @@
+"""-m gpu: this repository's CUDA path AND its oracle against the REFERENCE'S OWN device kernels.
+
+oracle/_ref/libdftfe_ref_kernels.so holds the reference's kernels for this path compiled unmodified from
+/root/reference (oracle/Makefile.ref, oracle/ref_kernels_driver.cc): constraintMatrixInfoDevice (initialize,
+distribute, distribute_slave_to_master, set_zero), MPICommunicatorP2PKernels (pack / accumulate-add),
+deviceKernelsGeneric (index-map gather, atomic scatter, mass scaling, block slices) and the cuBLAS
+gemmStridedBatched wrapper.  These tests run the same inputs through (1) the reference kernels, (2) the product's C
+ABI, (3) the numpy oracle, and require bit-exact agreement for the integer / copy / constraint work and 1e-12 for
+the floating-point contractions (the reference's atomicAdd order is not deterministic).  This is what pins the
+oracle: its statements of K1-K3, K5, K8, K11-K15 are checked against outputs of the reference itself.
+"""
+import numpy as np
+import pytest
+
+from tests.helpers import hanging_like_constraints, make_adaptive_problem, make_problem, random_global, scatter_to_ranks
+
+pytestmark = pytest.mark.gpu
+
+torch = pytest.importorskip("torch")
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def _relerr(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-300))
+
+
+@pytest.fixture(scope="module")
+def ref(lib_built):
+    assert torch.cuda.is_available(), "these tests need a CUDA device"
+    from oracle import ref_kernels
+
+    assert ref_kernels.available(), ("oracle/_ref/libdftfe_ref_kernels.so is missing: build it where /root/reference "
+                                     "exists with `make -f oracle/Makefile.ref` (it travels to the GPU box prebuilt)")
+    ref_kernels.load()
+    return ref_kernels
+
+
+@pytest.fixture(scope="module")
+def capi(lib_built):
+    from dftfe_b200 import capi
+
+    return capi
+
+
+def _problems():
+    # periodic + Dirichlet + injected multi-column rows, two ranks (ghost constrained rows) ...
+    mesh, ranks = make_problem(3, (4, 3, 3), 1.0, (True, False, True), nranks=2,
+                               extra_constraints=hanging_like_constraints(8))
+    yield "structured-2rank", ranks
+    # ... and real hanging nodes on a 2:1 refined mesh, three ranks
+    mesh, ranks = make_adaptive_problem(2, (3, 3, 3), 1.4, nranks=3)
+    yield "adaptive-3rank", ranks
+
+
+def test_constraint_csr_construction_matches_reference_initialize(ref):
+    """a7 / a9 (integer work, bit-exact): the CSR the C ABI is fed (rowIdsLocal, rowSizes, rowSizesAccumulated,
+    columnIdsLocal, columnValues, inhomogenities - owned constrained rows first, then ghost rows, each ascending) is
+    exactly what constraintMatrixInfoDevice::initialize (utils/constraintMatrixInfoDevice.cc:446-542) builds from the
+    same constraint lines handed over in scrambled order."""
+    for name, ranks in _problems():
+        for rp in ranks:
+            rc = ref.RefConstraints(rp)
+            rows, sizes, starts, cols, vals, inh = rc.csr()
+            assert np.array_equal(rows, np.asarray(rp.rowIdsLocal, np.uint32)), name
+            assert np.array_equal(sizes, np.asarray(rp.rowSizes, np.uint32)), name
+            assert np.array_equal(starts, np.asarray(rp.rowStarts, np.uint32)), name
+            assert np.array_equal(cols, np.asarray(rp.colIdsLocal, np.uint32)), name
+            assert np.array_equal(vals, np.asarray(rp.colValues, np.float64)), name
+            assert np.array_equal(inh, np.asarray(rp.inhomogeneities, np.float64)), name
+            rc.close()
+
+
+@pytest.mark.parametrize("B", [24, 7])
+def test_constraint_kernels_match_reference(ref, capi, B):
+    """K11 distribute and K13 set_zero: reference kernel == product == oracle, bit for bit.  K12
+    distribute_slave_to_master: the reference accumulates with atomicAdd in arbitrary order, the product and the
+    oracle in ascending constraint order - equal to a few ulp."""
+    from oracle import chfsi_oracle as O
+
+    for name, ranks in _problems():
+        for rp in ranks:
+            rc = ref.RefConstraints(rp)
+            op = capi.Operator(rp, B)
+            x0 = np.random.default_rng(5).uniform(-1, 1, size=(rp.M + rp.G, B))
+            for fn in ("distribute", "set_zero", "distribute_slave_to_master"):
+                want = _dev(x0)
+                getattr(rc, fn)(want, B)
+                want = want.cpu().numpy()
+                got = _dev(x0)
+                getattr(op, fn)(got)
+                got = got.cpu().numpy()
+                orc = x0.copy()
+                getattr(O, fn)(rp, orc)
+                if fn == "distribute_slave_to_master":
+                    assert _relerr(got, want) < 4e-16 * 8, (name, fn)
+                    assert _relerr(orc, want) < 4e-16 * 8, (name, fn)
+                else:
+                    assert np.array_equal(got, want), (name, fn)
+                    assert np.array_equal(orc, want), (name, fn)
+            op.close()
+            rc.close()
+
+
+@pytest.mark.parametrize("p,ncells,periodic,B,cplx", [
+    (6, (2, 2, 2), (True, True, True), 32, False),
+    (3, (3, 3, 2), (True, False, True), 40, False),
+    (4, (2, 2, 3), (True, True, True), 24, True),
+])
+def test_hxcheby_matches_reference_kernel_sequence(ref, capi, p, ncells, periodic, B, cplx):
+    """a4 / a5: HXCheby on one rank = distribute -> computeLocalHamiltonianTimesX -> distribute_slave_to_master
+    (kohnShamDFTOperatorDevice.cc:3874-3997), replayed on the reference's own kernels (K11, K1, its cuBLAS
+    gemmStridedBatched call incl. the complex transB = 'T' convention, K3 atomicAdd, K12), against the fused DMMA
+    kernel through the C ABI and against the oracle."""
+    from oracle import chfsi_oracle as O
+
+    mesh, ranks = make_problem(p, ncells, 1.1, periodic, extra_constraints=hanging_like_constraints(4),
+                               kpoint=(0.2, -0.1, 0.3) if cplx else None)
+    rp = ranks[0]
+    X = scatter_to_ranks(ranks, random_global(mesh, B, seed=3, cplx=cplx), loewdin=True)[0]
+    Y0 = scatter_to_ranks(ranks, random_global(mesh, B, seed=4, cplx=cplx), loewdin=True)[0]
+    # reference kernels
+    rc = ref.RefConstraints(rp)
+    src, dst = _dev(X), _dev(Y0)
+    if cplx:   # the reference distributes complex vectors with the same kernel on (re, im) pairs: 2B real columns
+        rc.distribute(torch.view_as_real(src), 2 * B)
+    else:
+        rc.distribute(src, B)
+    ref.local_hamiltonian_times_x(_dev(rp.H), rp.index_map(B), src, dst)
+    if cplx:
+        v = torch.view_as_real(dst).reshape(rp.M + rp.G, 2 * B).contiguous()
+        rc.distribute_slave_to_master(v, 2 * B)
+        want = torch.view_as_complex(v.reshape(rp.M + rp.G, B, 2)).cpu().numpy()
+    else:
+        rc.distribute_slave_to_master(dst, B)
+        want = dst.cpu().numpy()
+    # product
+    op = capi.Operator(rp, B, complex=cplx)
+    op.set_cell_hamiltonian(rp.H)
+    s_d, d_d = _dev(X), _dev(Y0)
+    op.HXCheby(s_d, d_d)
+    got = d_d.cpu().numpy()
+    # oracle
+    osrc, odst = [X.copy()], [Y0.copy()]
+    O.HXCheby(ranks, osrc, odst)
+    assert _relerr(got, want) < 1e-12
+    assert _relerr(odst[0], want) < 1e-12
+    op.close()
+    rc.close()
+
+
+def test_mass_scaling_and_block_slices_match_reference(ref, capi):
+    """K5 stridedBlockScale and K8 stridedCopyTo/FromBlockConstantStride: bit-exact against the reference kernels."""
+    mesh, ranks = make_problem(2, (3, 3, 3), 1.0, (True, True, False))
+    rp = ranks[0]
+    B, N = 16, 48
+    op = capi.Operator(rp, B)
+    rng = np.random.default_rng(2)
+    x0 = rng.uniform(-1, 1, size=(rp.M + rp.G, B))
+    for which, s in ((1, rp.sqrtMass), (2, rp.invSqrtMass)):
+        want = _dev(x0[:rp.M])
+        ref.strided_block_scale(want, 0.77, _dev(s[:rp.M]))
+        got = _dev(x0)
+        op.stridedBlockScale(got, 0.77, which)
+        assert np.array_equal(got.cpu().numpy()[:rp.M], want.cpu().numpy()), which
+    X0 = rng.uniform(-1, 1, size=(rp.M, N))
+    for j0 in (0, 16, 32):
+        Xd = _dev(X0)
+        want = torch.zeros((rp.M, B), dtype=torch.float64, device="cuda")
+        ref.strided_copy_to_block_constant_stride(Xd, j0, want)
+        got = torch.zeros((rp.M + rp.G, B), dtype=torch.float64, device="cuda")
+        op.stridedCopyToBlock(Xd, j0, got)
+        assert np.array_equal(got.cpu().numpy()[:rp.M], want.cpu().numpy())
+        blk = _dev(rng.uniform(-1, 1, size=(rp.M + rp.G, B)))
+        Xw, Xg = _dev(X0), _dev(X0)
+        ref.strided_copy_from_block_constant_stride(Xw, j0, blk[:rp.M].contiguous())
+        op.stridedCopyFromBlock(Xg, j0, blk)
+        assert np.array_equal(Xg.cpu().numpy(), Xw.cpu().numpy())
+    op.close()
+
+
+def test_ghost_exchange_matches_reference_pack_and_accumulate(ref, capi):
+    """a8: updateGhostValues / accumulateAddLocallyOwned between two in-process ranks against the reference's
+    gather-to-send-buffer (K14) and accumulate-add-from-recv-buffer (K15) kernels, moved by hand between the ranks
+    (MPICommunicatorP2P.cc:103-418 semantics): bit-exact."""
+    import threading
+
+    nranks, B = 2, 12
+    mesh, ranks = make_problem(2, (4, 3, 3), 1.0, (True, True, False), nranks=nranks)
+    rng = np.random.default_rng(9)
+    X = [rng.uniform(-1, 1, size=(rp.M + rp.G, B)) for rp in ranks]
+    for x, rp in zip(X, ranks):
+        x[rp.M:] = 0.0
+    # reference: forward
+    want_fwd = [x.copy() for x in X]
+    for r, rp in enumerate(ranks):
+        send = ref.gather_send_buffer(_dev(X[r]), _dev(rp.ownedLocalIdxForTargets.astype(np.uint32)), B).cpu().numpy()
+        off = 0
+        for t, q in enumerate(rp.targetProcIds):
+            cnt = int(rp.numOwnedForTargets[t])
+            rq = ranks[q]
+            g = list(rq.ghostProcIds).index(r)
+            s, e = rq.ghostLocalRanges[2 * g], rq.ghostLocalRanges[2 * g + 1]
+            assert e - s == cnt
+            want_fwd[q][rq.M + s:rq.M + e] = send[off:off + cnt]
+            off += cnt
+    # reference: reverse (on vectors whose ghost rows carry contributions)
+    Yin = [rng.uniform(-1, 1, size=(rp.M + rp.G, B)) for rp in ranks]
+    want_rev = []
+    for r, rp in enumerate(ranks):
+        recv = np.zeros((rp.ownedLocalIdxForTargets.size, B))
+        off = 0
+        for t, q in enumerate(rp.targetProcIds):
+            cnt = int(rp.numOwnedForTargets[t])
+            rq = ranks[q]
+            g = list(rq.ghostProcIds).index(r)
+            s, e = rq.ghostLocalRanges[2 * g], rq.ghostLocalRanges[2 * g + 1]
+            recv[off:off + cnt] = Yin[q][rq.M + s:rq.M + e]
+            off += cnt
+        data = _dev(Yin[r])
+        ref.accum_add_recv_buffer(_dev(recv), _dev(rp.ownedLocalIdxForTargets.astype(np.uint32)), B, rp.M, rp.G, data)
+        want_rev.append(data.cpu().numpy())
+
+    out = [None] * nranks
+    errs = []
+
+    def rank_fn(r):
+        try:
+            rp = ranks[r]
+            op = capi.Operator(rp, B, use_torch_stream=False)
+            op.comm_init_loopback(77, r, nranks)
+            x_d = _dev(X[r])
+            op.update_ghost_values(x_d)
+            op.sync()
+            y_d = _dev(Yin[r])
+            op.accumulate_add_locally_owned(y_d)
+            op.sync()
+            out[r] = (x_d.cpu().numpy(), y_d.cpu().numpy())
+            op.close()
+        except Exception as e:  # noqa: BLE001
+            errs.append(repr(e))
+
+    th = [threading.Thread(target=rank_fn, args=(r,)) for r in range(nranks)]
+    [t.start() for t in th]
+    [t.join(timeout=300) for t in th]
+    assert not errs, errs
+    for r, rp in enumerate(ranks):
+        assert np.array_equal(out[r][0], want_fwd[r])
+        assert np.array_equal(out[r][1][:rp.M], want_rev[r][:rp.M])
