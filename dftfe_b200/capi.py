@@ -85,7 +85,7 @@ EXPORTED_SYMBOLS = [
     "dftfe_b200_residual_norms", "dftfe_b200_reinit_spectrum_bounds", "dftfe_b200_solve",
     "dftfe_b200_get_spectrum_bounds", "dftfe_b200_solve_no_rr", "dftfe_b200_get_colouring", "dftfe_b200_set_option", "dftfe_b200_profile_enable",
     "dftfe_b200_profile_get", "dftfe_b200_profile_reset", "dftfe_b200_launch_count",
-    "dftfe_b200_measure_fp64_tensor_peak", "dftfe_b200_transport_name",
+    "dftfe_b200_measure_fp64_tensor_peak", "dftfe_b200_transport_name", "dftfe_b200_compute_density_grad",
 ]
 
 
@@ -282,6 +282,21 @@ class Operator:
         _check(self.lib.dftfe_b200_compute_density(self.h, _dptr(X), C.c_int32(X.shape[1]), _ptr(occ), C.c_int32(nq),
                                                    _dptr(shapeValues), _dptr(rho)))
         return rho
+
+    def computeRhoGradRhoFromPSI(self, X, occupations, shapeValues, shapeGradValues, invJacobian=None):
+        """rho[c][q] and gradRho[c][q][3] (computeRhoFromPSI with isEvaluateGradRho, src/dft/densityCalculator.cc).
+        shapeGradValues: [3][n][nq] reference-cell derivatives; invJacobian: [nCells][3][3] or None (identity)."""
+        import torch
+
+        occ = _np(occupations, np.float64)
+        nq = int(shapeValues.shape[1])
+        nC = int(self.prob.nCells)
+        rho = torch.empty((nC, nq), dtype=torch.float64, device=X.device)
+        grad = torch.empty((nC, nq, 3), dtype=torch.float64, device=X.device)
+        _check(self.lib.dftfe_b200_compute_density_grad(
+            self.h, _dptr(X), C.c_int32(X.shape[1]), _ptr(occ), C.c_int32(nq), _dptr(shapeValues), _dptr(shapeGradValues),
+            _dptr(invJacobian) if invJacobian is not None else C.c_void_p(), _dptr(rho), _dptr(grad)))
+        return rho, grad
 
     def reinitkPointSpinIndex(self, kPointIndex: int, spinIndex: int = 0):
         """kohnShamDFTOperatorDevice.cc:1033-1058: switch to a stored (k-point, spin) Hamiltonian set and to the

@@ -388,7 +388,8 @@ int compute_cell_hamiltonian(dftfe_b200_ctx *ctx, int nq, const double *shapeVal
 
 // density.cu
 int compute_density(dftfe_b200_ctx *ctx, const double *X, int N, const double *occ_h, int nq, const double *shapeValues,
-                    double *rho);
+                    double *rho, const double *shapeGradValues = nullptr, const double *invJac = nullptr,
+                    double *gradRho = nullptr);
 
 // tf32_gemm.cu: tcgen05 (kind::tf32, 3xTF32 split) GEMM of the FP32 blocks
 int launch_split_transpose(dftfe_b200_ctx *ctx, const double *X, int64_t ldx, int c0, int ncols, int64_t rows,

@@ -516,6 +516,16 @@ int dftfe_b200_compute_density(dftfe_b200_ctx *ctx, const double *X_d, int32_t N
   return compute_density(ctx, X_d, N, occupations_h, n_quad, shape_values_d, rho_out_d);
 }
 
+int dftfe_b200_compute_density_grad(dftfe_b200_ctx *ctx, const double *X_d, int32_t N, const double *occupations_h,
+                                    int32_t n_quad, const double *shape_values_d, const double *shape_grad_values_d,
+                                    const double *inv_jacobian_d, double *rho_out_d, double *grad_rho_out_d) {
+  DB_CTX(ctx);
+  DB_CHECK(X_d && occupations_h && shape_values_d && shape_grad_values_d && rho_out_d && grad_rho_out_d && N >= 1,
+           "compute_density_grad: null argument");
+  return compute_density(ctx, X_d, N, occupations_h, n_quad, shape_values_d, rho_out_d, shape_grad_values_d,
+                         inv_jacobian_d, grad_rho_out_d);
+}
+
 int dftfe_b200_set_cell_hamiltonian_host(dftfe_b200_ctx *ctx, const double *H_h) {
   DB_CTX(ctx);
   const size_t count = (size_t)ctx->nC * ctx->n * ctx->n * ctx->cm;

@@ -12,7 +12,15 @@
 // quadrature rows (m8 tiles of q, three per warp per pass) as FP64 DMMA accumulators, square them in registers,
 // weight by f_i and add into per-thread partial sums that live across the tiles; one shuffle reduction and one
 // store per (cell, q) at the end.  psi(q) never touches memory.  Complex build: columns are interleaved (re, im), so
-// re^2 + im^2 falls out of the same column sum.  rho only (LDA-type functionals); grad rho is not provided.
+// re^2 + im^2 falls out of the same column sum.
+//
+// grad rho (GGA functionals; computeRhoGradRhoFromInterpolatedValues with isEvaluateGradRho,
+// densityCalculatorDeviceKernels.cc:35-140: gradRho[c][q][d] = sum_i f_i 2 Re(conj(psi_i) d_d psi_i)): a second
+// kernel of the same structure that, per (cell, pass over 192 quadrature points, column tile), runs four k-loops -
+// psi and the three reference-cell derivatives d_e psi = sum_I (d_e N_I)(q) x_I - keeps f*2*psi in registers,
+// accumulates rho and the three reference-coordinate components, and applies the cell's inverse Jacobian once at the
+// end (the map to physical derivatives is linear: grad_d = sum_e Jinv[c][e][d] d_e).  The interpolated gradients
+// (3 x nC x nq x B doubles per block in the reference) never touch memory either.
 #include "common.cuh"
 
 namespace dftfe_b200 {
@@ -253,26 +261,250 @@ int launch_density(dftfe_b200_ctx *ctx, const double *x, int ldx, int nColTiles,
   return 0;
 }
 
+
+// ---------------------------------------------------------------------------
+// rho AND grad rho
+// ---------------------------------------------------------------------------
+constexpr int GTPW = 2;                        // q tiles per warp per pass (two: psi and one derivative stay in registers)
+constexpr int GQT_PER_PASS = WARPS * GTPW;     // 24 m8 tiles = 192 quadrature points per pass
+constexpr int GMAX_PASSES = 6;                 // nq <= 1152
+#ifndef DB_GAPF
+#define DB_GAPF 4
+#endif
+constexpr int GAPF = DB_GAPF;                  // A-fragment prefetch depth of the gradient kernel
+
+__device__ __forceinline__ void load2(const double *p, double (&a)[GTPW]) {
+  asm volatile("ld.global.nc.v2.f64 {%0,%1}, [%2];" : "=d"(a[0]), "=d"(a[1]) : "l"(p));
+}
+
+// values N[I][q] and reference-cell derivatives dN[e][I][q] -> fragment-major
+//   Nf[comp][pass][warp][ks][lane][t] = A_comp[(pass*24 + warp + t*12)*8 + lane/4][ks*4 + lane%4],  comp 0 = N, 1..3 = d_e N
+__global__ void tile_shape_grad_kernel(const double *__restrict__ N, const double *__restrict__ dN, int n, int nq,
+                                       int KS, int passes, double *__restrict__ Nf) {
+  const int64_t per = (int64_t)passes * WARPS * KS * 32 * GTPW;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < 4 * per;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int comp = (int)(idx / per);
+    int64_t r = idx % per;
+    const int t = r % GTPW;
+    r /= GTPW;
+    const int lane = r % 32;
+    r /= 32;
+    const int ks = r % KS;
+    r /= KS;
+    const int w = r % WARPS;
+    const int pass = (int)(r / WARPS);
+    const int q = (pass * GQT_PER_PASS + w + t * WARPS) * 8 + lane / 4;
+    const int k = ks * 4 + lane % 4;
+    double v = 0.0;
+    if (q < nq && k < n) v = comp == 0 ? N[(size_t)k * nq + q] : dN[((size_t)(comp - 1) * n + k) * nq + q];
+    Nf[idx] = v;
+  }
+}
+
+template <int NODES>
+__global__ void __launch_bounds__(THREADS, 1)
+density_grad_kernel(const double *__restrict__ Nf, const uint32_t *__restrict__ cellRows, int64_t nCells,
+                    const double *__restrict__ x, int ldx, int nColTiles, const double *__restrict__ fcol, int nq,
+                    int passes, const double *__restrict__ invJac, double *__restrict__ rho,
+                    double *__restrict__ gradRho) {
+  using D = DCfg<NODES>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double *Xs = reinterpret_cast<double *>(smem_raw);
+  uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + 2 * D::XBUF * sizeof(double));
+  uint64_t *empty = full + 2;
+  const int tid = threadIdx.x, lane = tid & 31, pwarp = tid >> 5, warp = pwarp - 1;
+  constexpr uint32_t ROW_MASK = 0x3fffffffu;
+  const size_t perComp = (size_t)passes * WARPS * D::KS * 32 * GTPW;
+
+  for (int i = tid; i < (int)(2 * D::XBUF); i += THREADS) Xs[i] = 0.0;
+  if (tid == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    mbar_init(&empty[0], WARPS);
+    mbar_init(&empty[1], WARPS);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+
+  if (pwarp == 0) {
+    // ===== producer: the block's column tiles are walked once per pass =====
+    uint32_t it = 0;
+    for (int64_t cell = blockIdx.x; cell < nCells; cell += gridDim.x) {
+      uint32_t myRows[(NODES + 31) / 32];
+#pragma unroll
+      for (int j = 0; j < (NODES + 31) / 32; ++j) {
+        const int k = lane + 32 * j;
+        myRows[j] = (k < NODES) ? (__ldg(cellRows + (size_t)cell * NODES + k) & ROW_MASK) : 0u;
+      }
+      for (int p = 0; p < passes; ++p)
+        for (int tile = 0; tile < nColTiles; ++tile, ++it) {
+          const int buf = it & 1;
+          const uint32_t ph = (it >> 1) & 1;
+          mbar_wait(&empty[buf], ph ^ 1);
+          double *xs = Xs + buf * D::XBUF;
+          if (lane == 0) mbar_arrive_expect_tx(&full[buf], (uint32_t)(NODES * BT * sizeof(double)));
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < (NODES + 31) / 32; ++j) {
+            const int k = lane + 32 * j;
+            if (k < NODES)
+              tma_bulk_g2s(xs + k * LDS, x + (size_t)myRows[j] * ldx + tile * BT, BT * sizeof(double), &full[buf]);
+          }
+        }
+    }
+  } else {
+    const double *xb0 = Xs + (lane & 3) * LDS + (lane >> 2);
+    uint32_t it = 0;
+    for (int64_t cell = blockIdx.x; cell < nCells; cell += gridDim.x) {
+      for (int p = 0; p < passes; ++p) {
+        double part[GTPW], gpart[3][GTPW];
+#pragma unroll
+        for (int t = 0; t < GTPW; ++t) part[t] = gpart[0][t] = gpart[1][t] = gpart[2][t] = 0.0;
+        for (int tile = 0; tile < nColTiles; ++tile, ++it) {
+          const int buf = it & 1;
+          const uint32_t ph = (it >> 1) & 1;
+          const double *xb = xb0 + buf * D::XBUF;
+          mbar_wait(&full[buf], ph);
+          double w2[GTPW][NT][2];  // f * 2 * psi of this lane's accumulator elements
+#pragma unroll
+          for (int comp = 0; comp < 4; ++comp) {
+            const double *Ap = Nf + comp * perComp + ((size_t)(p * WARPS + warp) * D::KS) * 32 * GTPW + lane * GTPW;
+            double acc[GTPW][NT][2];
+#pragma unroll
+            for (int t = 0; t < GTPW; ++t)
+#pragma unroll
+              for (int nt = 0; nt < NT; ++nt) acc[t][nt][0] = acc[t][nt][1] = 0.0;
+            double a[GAPF][GTPW];
+#pragma unroll
+            for (int s = 0; s < GAPF; ++s) load2(Ap + (size_t)min(s, D::KS - 1) * 32 * GTPW, a[s]);
+            int ks = 0;
+            for (; ks + GAPF <= D::KS; ks += GAPF) {
+#pragma unroll
+              for (int s = 0; s < GAPF; ++s) {
+                double b[NT];
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) b[nt] = xb[(ks + s) * 4 * LDS + nt * 8];
+#pragma unroll
+                for (int t = 0; t < GTPW; ++t)
+#pragma unroll
+                  for (int nt = 0; nt < NT; ++nt) dmma884(acc[t][nt][0], acc[t][nt][1], a[s][t], b[nt]);
+                if (ks + s + GAPF < D::KS) load2(Ap + (size_t)(ks + s + GAPF) * 32 * GTPW, a[s]);
+              }
+            }
+#pragma unroll
+            for (int s = 0; s < D::KS % GAPF; ++s) {
+              double b[NT];
+#pragma unroll
+              for (int nt = 0; nt < NT; ++nt) b[nt] = xb[(ks + s) * 4 * LDS + nt * 8];
+#pragma unroll
+              for (int t = 0; t < GTPW; ++t)
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) dmma884(acc[t][nt][0], acc[t][nt][1], a[s][t], b[nt]);
+            }
+            if (comp == 0) {
+              // rho contribution; keep f * 2 * psi for the three derivative products
+#pragma unroll
+              for (int t = 0; t < GTPW; ++t) {
+                double s = 0.0;
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+                  for (int e = 0; e < 2; ++e) {
+                    const double f = __ldg(fcol + tile * BT + nt * 8 + (lane & 3) * 2 + e);
+                    const double fp = f * acc[t][nt][e];
+                    s += fp * acc[t][nt][e];
+                    w2[t][nt][e] = 2.0 * fp;
+                  }
+                part[t] += s;
+              }
+            } else {
+#pragma unroll
+              for (int t = 0; t < GTPW; ++t) {
+                double s = 0.0;
+#pragma unroll
+                for (int nt = 0; nt < NT; ++nt) s += w2[t][nt][0] * acc[t][nt][0] + w2[t][nt][1] * acc[t][nt][1];
+                gpart[comp - 1][t] += s;
+              }
+            }
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[buf]);
+        }
+        // ---- reduce over the four lanes of a quadrature row; reference -> physical derivatives; one RMW per (cell, q)
+        double J[9];
+#pragma unroll
+        for (int e = 0; e < 9; ++e) J[e] = invJac ? __ldg(invJac + (size_t)cell * 9 + e) : ((e % 4 == 0) ? 1.0 : 0.0);
+#pragma unroll
+        for (int t = 0; t < GTPW; ++t) {
+          double s = part[t], g0 = gpart[0][t], g1 = gpart[1][t], g2 = gpart[2][t];
+#pragma unroll
+          for (int m = 1; m <= 2; m <<= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, m);
+            g0 += __shfl_xor_sync(0xffffffffu, g0, m);
+            g1 += __shfl_xor_sync(0xffffffffu, g1, m);
+            g2 += __shfl_xor_sync(0xffffffffu, g2, m);
+          }
+          const int q = (p * GQT_PER_PASS + warp + t * WARPS) * 8 + (lane >> 2);
+          if ((lane & 3) == 0 && q < nq) {
+            rho[(size_t)cell * nq + q] += s;
+            double *g = gradRho + ((size_t)cell * nq + q) * 3;
+            g[0] += J[0] * g0 + J[3] * g1 + J[6] * g2;
+            g[1] += J[1] * g0 + J[4] * g1 + J[7] * g2;
+            g[2] += J[2] * g0 + J[5] * g1 + J[8] * g2;
+          }
+        }
+      }
+    }
+  }
+}
+
+template <int NODES>
+int launch_density_grad(dftfe_b200_ctx *ctx, const double *x, int ldx, int nColTiles, int nq, int passes,
+                        const double *invJac, double *rho, double *gradRho) {
+  using D = DCfg<NODES>;
+  DB_DYN_SMEM(ctx, density_grad_kernel<NODES>, D::SMEM);
+  ProfScope ps(ctx, "density");
+  const int grid = (int)std::min<int64_t>(ctx->nC, ctx->num_sms);
+  density_grad_kernel<NODES><<<grid, THREADS, D::SMEM, ctx->stream>>>(ctx->denNf.p, ctx->cellRowsFlagged.p, ctx->nC, x,
+                                                                     ldx, nColTiles, ctx->denF.p, nq, passes, invJac, rho,
+                                                                     gradRho);
+  DB_CUDA(cudaGetLastError());
+  return 0;
+}
+
 }  // namespace
 
 // rho_out[c][q] = sum_i f_i |psi_i(x_q)|^2 over the N columns of X (row-major M x N, FE basis), cells owned by this rank
+// shapeGradValues [3][n][nq] (reference-cell derivatives), invJac [nC][3][3] (Jinv[c][e][d] = d xi_e / d x_d; nullptr:
+// identity) and gradRho [nC][nq][3] non-null: also grad rho (GGA)
 int compute_density(dftfe_b200_ctx *ctx, const double *X, int N, const double *occ_h, int nq, const double *shapeValues,
-                    double *rho) {
+                    double *rho, const double *shapeGradValues, const double *invJac, double *gradRho) {
   DB_CHECK(ctx->have_map, "compute_density: set_index_map first");
-  DB_CHECK(nq >= 1 && nq <= MAX_PASSES * QT_PER_PASS * 8, "compute_density: n_quad (%d) must be in [1, %d]", nq,
-           MAX_PASSES * QT_PER_PASS * 8);
+  const bool grad = gradRho != nullptr;
+  DB_CHECK(!grad || shapeGradValues, "compute_density: grad rho needs the shape-function derivatives");
+  const int maxq = grad ? GMAX_PASSES * GQT_PER_PASS * 8 : MAX_PASSES * QT_PER_PASS * 8;
+  DB_CHECK(nq >= 1 && nq <= maxq, "compute_density: n_quad (%d) must be in [1, %d]", nq, maxq);
   DB_CHECK(ctx->n != 512, "compute_density: FE order 7 does not fit the double-buffered tile");
   const int cm = ctx->cm, n = ctx->n;
   const int KS = (n + 3) / 4;
-  const int passes = ((nq + 7) / 8 + QT_PER_PASS - 1) / QT_PER_PASS;
+  const int qtPerPass = grad ? GQT_PER_PASS : QT_PER_PASS;
+  const int passes = ((nq + 7) / 8 + qtPerPass - 1) / qtPerPass;
   const int B = std::min(ctx->B, N);
   const int Bpad = ((B * cm + BT - 1) / BT) * BT;  // real columns per block, padded to full 32-column tiles
-  DB_TRY(ctx->denNf.alloc((size_t)passes * WARPS * KS * 32 * TPWP));
+  DB_TRY(ctx->denNf.alloc(grad ? (size_t)4 * passes * WARPS * KS * 32 * GTPW : (size_t)passes * WARPS * KS * 32 * TPWP));
   DB_TRY(ctx->denOcc.upload(occ_h, N, ctx->stream));
   DB_TRY(ctx->denF.alloc(Bpad));
   DB_TRY(ctx->denBlock.alloc((size_t)(ctx->M + ctx->G) * Bpad));
   ctx->launches += 2;
-  tile_shape_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(shapeValues, n, nq, KS, passes, ctx->denNf.p);
+  if (grad) {
+    tile_shape_grad_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(shapeValues, shapeGradValues, n, nq, KS, passes,
+                                                                     ctx->denNf.p);
+    DB_CUDA(cudaMemsetAsync(gradRho, 0, (size_t)ctx->nC * nq * 3 * sizeof(double), ctx->stream));
+  } else {
+    tile_shape_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(shapeValues, n, nq, KS, passes, ctx->denNf.p);
+  }
   DB_CUDA(cudaMemsetAsync(rho, 0, (size_t)ctx->nC * nq * sizeof(double), ctx->stream));
   const bool padded = Bpad != B * cm;
   if (padded)
@@ -286,6 +518,17 @@ int compute_density(dftfe_b200_ctx *ctx, const double *X, int N, const double *o
     ctx->launches += 1;
     expand_weights_kernel<<<(Bpad + 127) / 128, 128, 0, ctx->stream>>>(ctx->denOcc.p, j, Bcr, cm, Bpad, ctx->denF.p);
     const int nColTiles = (Bcr + BT - 1) / BT;
+    if (grad) {
+#define DB_DG(NN) case NN: DB_TRY(launch_density_grad<NN>(ctx, ctx->denBlock.p, Bpad, nColTiles, nq, passes, invJac, rho, gradRho)); break;
+      switch (n) {
+        DB_DG(8) DB_DG(27) DB_DG(64) DB_DG(125) DB_DG(216) DB_DG(343)
+        default:
+          set_error("compute_density: no kernel for %d nodes per cell", n);
+          return DFTFE_B200_ERR_UNSUPPORTED;
+      }
+#undef DB_DG
+      continue;
+    }
     switch (n) {
       case 8: DB_TRY(launch_density<8>(ctx, ctx->denBlock.p, Bpad, nColTiles, nq, passes, rho)); break;
       case 27: DB_TRY(launch_density<27>(ctx, ctx->denBlock.p, Bpad, nColTiles, nq, passes, rho)); break;

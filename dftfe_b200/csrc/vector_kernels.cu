@@ -22,8 +22,10 @@ inline int grid_for(const dftfe_b200_ctx *ctx, int64_t work, int block = 256) {
   return (int)g;
 }
 
-// K11 distributeKernel: x[row,:] = inhom + sum_j w_j * x[col_j,:]
-// Products and sums are rounded separately, in CSR order (the oracle's statement).
+// K11 distributeKernel: x[row,:] = inhom + sum_j w_j * x[col_j,:], accumulated in CSR order with ONE rounding per
+// term (fused multiply-add): the reference's `xVec[row] += w * xVec[col]` (utils/constraintMatrixInfoDevice.cc:71-74)
+// is compiled by nvcc with its default -fmad=true into DFMA, and bit-exact parity is against that build
+// (tests/test_gpu_reference_kernels.py runs the reference kernel itself).
 __global__ void distribute_kernel(double *__restrict__ x, int ncols, int ldx, int64_t nCon,
                                   const uint32_t *__restrict__ rows, const uint32_t *__restrict__ sizes,
                                   const uint32_t *__restrict__ starts, const uint32_t *__restrict__ cols,
@@ -40,7 +42,7 @@ __global__ void distribute_kernel(double *__restrict__ x, int ncols, int ldx, in
       const uint32_t cj = cols[s + j];
       double xv = x[(size_t)cj * ldx + c];
       if (colScale) xv = __dmul_rn(xv, colScale[cj]);
-      v = __dadd_rn(v, __dmul_rn(vals[s + j], xv));
+      v = __fma_rn(vals[s + j], xv, v);
     }
     x[(size_t)rows[i] * ldx + c] = v;
   }
@@ -220,8 +222,8 @@ distribute_vec_kernel(double *__restrict__ x, int ncols, int ldx, int64_t nCon, 
             xv[u].x = __dmul_rn(xv[u].x, sc);
             xv[u].y = __dmul_rn(xv[u].y, sc);
           }
-          v[u].x = __dadd_rn(v[u].x, __dmul_rn(wj, xv[u].x));
-          v[u].y = __dadd_rn(v[u].y, __dmul_rn(wj, xv[u].y));
+          v[u].x = __fma_rn(wj, xv[u].x, v[u].x);
+          v[u].y = __fma_rn(wj, xv[u].y, v[u].y);
         }
       }
 #pragma unroll

@@ -209,6 +209,14 @@ int dftfe_b200_compute_cell_hamiltonian(dftfe_b200_ctx *ctx, int32_t n_quad, con
  * kernel per block (gather + FP64 tensor-core GEMM + square + weighted sum); rho only, no grad rho.  FE orders 1-6. */
 int dftfe_b200_compute_density(dftfe_b200_ctx *ctx, const double *X_d, int32_t N, const double *occupations_h,
                                int32_t n_quad, const double *shape_values_d, double *rho_out_d);
+/* The same with the density gradient for GGA functionals (computeRhoGradRhoFromInterpolatedValues with
+ * isEvaluateGradRho, src/dft/densityCalculatorDeviceKernels.cc:35-140; gradient interpolation of
+ * src/dft/densityCalculator.cc): grad_rho_out_d[c][q][d] = sum_i f_i 2 Re(conj(psi_i) d psi_i / d x_d).
+ * shape_grad_values_d: [3][n][n_quad] derivatives of the shape functions on the REFERENCE cell;
+ * inv_jacobian_d: [n_cells][3][3] with J[c][e][d] = d xi_e / d x_d (affine cells; NULL = identity). */
+int dftfe_b200_compute_density_grad(dftfe_b200_ctx *ctx, const double *X_d, int32_t N, const double *occupations_h,
+                                    int32_t n_quad, const double *shape_values_d, const double *shape_grad_values_d,
+                                    const double *inv_jacobian_d, double *rho_out_d, double *grad_rho_out_d);
 
 /* ---- distributed-vector primitives (MultiVector / MPICommunicatorP2P) ---- */
 int dftfe_b200_update_ghost_values(dftfe_b200_ctx *ctx, double *x_d, int32_t ncols);

@@ -113,6 +113,11 @@ void oracle_local_hx(int n, int B, int64_t nCells, const double *H, const uint32
   (void)nCells;
 }
 
+/* acc[i] = fma(w, x[i], acc[i]): exact fused multiply-add for the numpy oracle (numpy has none) */
+void oracle_fma_axpy(int64_t n, double w, const double *x, double *acc) {
+  for (int64_t i = 0; i < n; ++i) acc[i] = fma(w, x[i], acc[i]);
+}
+
 /* utils/constraintMatrixInfo.cc:247-293 */
 void oracle_distribute(int B, int64_t nCon, const uint32_t *rows, const uint32_t *sizes, const uint32_t *starts,
                        const uint32_t *cols, const double *vals, const double *inhom, double *x) {
@@ -122,10 +127,9 @@ void oracle_distribute(int B, int64_t nCon, const uint32_t *rows, const uint32_t
     for (uint32_t k = 0; k < sizes[i]; ++k) {
       const double w = vals[starts[i] + k];
       const double *xc = x + (size_t)cols[starts[i] + k] * B;
-      for (int j = 0; j < B; ++j) {
-        volatile double prod = w * xc[j]; /* separately rounded product, as the numpy oracle */
-        tmp[j] = tmp[j] + prod;
-      }
+      /* one rounding per term: the device kernel's `x[row] += w * x[col]` is a DFMA under nvcc's default
+       * -fmad=true (utils/constraintMatrixInfoDevice.cc:71-74); the same as the numpy oracle (oracle_fma_axpy) */
+      for (int j = 0; j < B; ++j) tmp[j] = fma(w, xc[j], tmp[j]);
     }
     memcpy(x + (size_t)rows[i] * B, tmp, sizeof(double) * B);
   }

@@ -115,13 +115,30 @@ def zero_out_ghosts(ranks, vecs):
 # constraints (a7) - utils/constraintMatrixInfo.cc
 # --------------------------------------------------------------------------
 
+def _fma_axpy(w: float, xrow: np.ndarray, acc: np.ndarray):
+    """acc <- fma(w, xrow, acc) elementwise with ONE rounding per element (complex: on the (re, im) doubles).  numpy has
+    no fused multiply-add; the exact one comes from libm through the C oracle (oracle_fma_axpy)."""
+    import ctypes as C
+
+    from oracle import c_oracle
+
+    lib = c_oracle.load()
+    xr = np.ascontiguousarray(xrow).view(np.float64)
+    av = acc.view(np.float64)
+    lib.oracle_fma_axpy(C.c_int64(av.size), C.c_double(float(w)), xr.ctypes.data_as(C.c_void_p),
+                        av.ctypes.data_as(C.c_void_p))
+
+
 def distribute(rp, x: np.ndarray):
-    """utils/constraintMatrixInfo.cc:247-293: x[row] = inhom + sum_j w_j x[col_j]."""
+    """x[row] = inhom + sum_j w_j x[col_j], accumulated in CSR order with one rounding per term: the device kernel's
+    `xVec[row] += w * xVec[col]` (utils/constraintMatrixInfoDevice.cc:32-80) is a DFMA under nvcc's default
+    -fmad=true - pinned bit for bit against the reference kernel itself in tests/test_gpu_reference_kernels.py.
+    (CPU twin: utils/constraintMatrixInfo.cc:247-293.)"""
     for i in range(rp.rowIdsLocal.size):
         new = np.full(x.shape[1], rp.inhomogeneities[i], dtype=x.dtype)
         s = int(rp.rowStarts[i])
         for j in range(int(rp.rowSizes[i])):
-            new += rp.colValues[s + j] * x[rp.colIdsLocal[s + j]]
+            _fma_axpy(rp.colValues[s + j], x[rp.colIdsLocal[s + j]], new)
         x[rp.rowIdsLocal[i]] = new
 
 
@@ -780,6 +797,30 @@ def compute_rho_from_psi(ranks, X, occupations, shape_values):
         Xc = x[rp.cellLocalDofs]                       # [nC, n, Ncols]
         psi = np.einsum("iq,cik->cqk", N, Xc, optimize=True)
         out.append(np.einsum("k,cqk->cq", f, np.abs(psi) ** 2, optimize=True))
+    return out
+
+
+def compute_rho_grad_rho_from_psi(ranks, X, occupations, shape_values, shape_grad_values, inv_jacobians):
+    """computeRhoFromPSI with isEvaluateGradRho (src/dft/densityCalculator.cc:39-560, kernel
+    computeRhoGradRhoFromInterpolatedValues, densityCalculatorDeviceKernels.cc:35-140): besides rho,
+        gradRho[c, q, d] = sum_i f_i 2 Re(conj(psi_i(x_q)) d psi_i / d x_d (x_q)),
+        d psi / d x_d = sum_e Jinv[c][e][d] sum_I (d N_I / d xi_e)(q) x_i[row(c, I)].
+    shape_grad_values: [3, n, nq] reference-cell derivatives; inv_jacobians: per rank [nC, 3, 3]."""
+    N = np.asarray(shape_values)
+    dN = np.asarray(shape_grad_values)
+    f = np.asarray(occupations, dtype=np.float64)
+    X = [x.copy() for x in X]
+    update_ghost_values(ranks, X)
+    out = []
+    for rp, x, J in zip(ranks, X, inv_jacobians):
+        distribute(rp, x)
+        Xc = x[rp.cellLocalDofs]                                        # [nC, n, Ncols]
+        psi = np.einsum("iq,cik->cqk", N, Xc, optimize=True)
+        dref = np.einsum("eiq,cik->ceqk", dN, Xc, optimize=True)        # reference-coordinate derivatives
+        dphys = np.einsum("ced,ceqk->cdqk", np.asarray(J), dref, optimize=True)
+        rho = np.einsum("k,cqk->cq", f, np.abs(psi) ** 2, optimize=True)
+        grad = np.einsum("k,cdqk->cqd", f, 2.0 * np.real(np.conj(psi)[:, None] * dphys), optimize=True)
+        out.append((rho, grad))
     return out
 
 

@@ -39,6 +39,8 @@ def main():
         ids = [capi.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(ids, src=0)
         op.comm_init(ids[0], rank, world)
+        if os.environ.get("DFTFE_B200_TRANSPORT") == "nccl":   # default: peer-mapped buffers when available
+            op.set_option("p2p_exchange", 0)
         op.set_cell_hamiltonian(rp.H)
         dev = lambda a_: torch.from_numpy(np.ascontiguousarray(a_)).cuda()
         # blocked filter loop over all N columns: FP64 (two lanes and one) and FP32 ghost payloads
@@ -88,6 +90,7 @@ def main():
         ev_ref, res_ref = O.solve(ranks, Xo, B, 12, (ev_ref[0], ev_ref[-1], b0[2]))
         errs["solve_eig_pass2"] = np.abs(eig - ev_ref).max()
         errs["solve_res_pass2"] = np.abs(res - res_ref).max()
+        transport = op.transport_name()
         op.close()
     tol = {"filter_fp64": 1e-11, "filter_lanes_bitident": 0.5, "filter_fp32comm": 2e-5, "xtx": 1e-13, "xthx": 1e-12,
            "xtx_mixed": 2e-5, "solve_eig_pass1": 1e-8, "solve_eig_pass2": 1e-8, "solve_res_pass2": 1e-6}
@@ -97,7 +100,7 @@ def main():
     allbad = [None] * world
     dist.all_gather_object(allbad, bad)
     if rank == 0:
-        print("NCCL_PARITY", "world", world, {k: float(v) for k, v in errs.items()})
+        print("NCCL_PARITY", "world", world, "transport:", transport, {k: float(v) for k, v in errs.items()})
         print("NCCL_PARITY_RESULT", "FAIL" if any(allbad) else "OK", allbad)
     dist.barrier()
     dist.destroy_process_group()

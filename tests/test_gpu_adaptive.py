@@ -212,6 +212,46 @@ def test_density_from_wavefunctions(capi, p, N, B, cplx, nranks):
     assert outs[0].min() >= 0.0
 
 
+@pytest.mark.parametrize("p,N,B,cplx,adaptive", [(3, 24, 8, False, True), (6, 64, 32, False, False), (2, 20, 10, True, False),
+                                                 (4, 40, 40, False, True)])
+def test_density_and_gradient_from_wavefunctions(capi, p, N, B, cplx, adaptive):
+    """SURVEY 8f rank 3 with the GGA part: rho and grad rho (computeRhoGradRhoFromInterpolatedValues with
+    isEvaluateGradRho, densityCalculatorDeviceKernels.cc:35-140) against the oracle; cells of two sizes (adaptive mesh:
+    different inverse Jacobians), ragged blocks and complex vectors included (the oracle's gradient is pinned on the CPU
+    by the known answer rho = |r|^4, grad rho = 4 |r|^2 r for psi = |r|^2, tests/test_oracle_cpu.py)."""
+    from oracle import chfsi_oracle as O
+    from tests.helpers import make_problem, random_global, scatter_to_ranks
+
+    if adaptive:
+        mesh, ranks = make_adaptive_problem(p, (3, 3, 3), 1.4)
+    else:
+        mesh, ranks = make_problem(p, (2, 2, 2) if p == 6 else (3, 2, 2), 1.2, (True, True, True),
+                                   kpoint=(0.2, 0.1, -0.3) if cplx else None)
+    rp = ranks[0]
+    ref = mesh.ref
+    shape = np.ascontiguousarray(ref.phi3.T)                                   # [n, nq]
+    dshape = np.ascontiguousarray(np.transpose(ref.dphi3, (0, 2, 1)))          # [3, n, nq]
+    _, scale = mesh.cell_origin_scale(mesh.owned_cells(0))
+    J = np.zeros((rp.nCells, 3, 3))
+    for d in range(3):
+        J[:, d, d] = 2.0 / (np.asarray(scale) * ref.h)
+    occ = np.linspace(2.0, 0.1, N)
+    if adaptive:
+        X = [field_on_nodes(rp, N, seed=2)]
+        X[0][rp.M:] = 0
+    else:
+        X = scatter_to_ranks(ranks, random_global(mesh, N, seed=4, cplx=cplx), zero_constrained=False)
+    (rho_ref, grad_ref), = O.compute_rho_grad_rho_from_psi(ranks, X, occ, shape, dshape, [J])
+    op = capi.Operator(rp, B, complex=cplx)
+    rho, grad = op.computeRhoGradRhoFromPSI(_dev(X[0][:rp.M]), occ, _dev(shape), _dev(dshape), _dev(J))
+    assert _relerr(rho.cpu().numpy(), rho_ref) < 1e-12
+    assert _relerr(grad.cpu().numpy(), grad_ref) < 1e-12
+    # rho alone through the gradient-free entry point agrees
+    rho_only = op.computeRhoFromPSI(_dev(X[0][:rp.M]), occ, _dev(shape))
+    assert _relerr(rho_only.cpu().numpy(), rho_ref) < 1e-12
+    op.close()
+
+
 def test_density_integrates_to_electron_count(capi):
     """Known answer tying solve() and the density kernel together: for M-orthonormal wavefunctions the density
     sampled at the GLL nodes and integrated with the GLL weights gives exactly sum_i f_i (the lumped mass matrix IS

@@ -394,3 +394,32 @@ def test_unit_coefficient_recurrence_is_the_same_filter(m):
     scale = max(np.abs(r).max() for r in ref)
     for rp, g, r in zip(ranks, got, ref):
         assert np.abs(g[:rp.M] - r[:rp.M]).max() < 1e-12 * scale
+
+
+def test_density_gradient_known_answer():
+    """psi = |r|^2 is in the FE space (order >= 2): rho = |r|^4 and grad rho = 4 |r|^2 r at every quadrature point, on a
+    mesh with cells of two sizes (pins the reference-derivative / inverse-Jacobian convention of the oracle)."""
+    from tests.helpers import make_adaptive_problem
+
+    mesh, ranks = make_adaptive_problem(3, (5, 5, 5), 1.4)
+    rp = ranks[0]
+    ref = mesh.ref
+    shape = np.ascontiguousarray(ref.phi3.T)
+    dshape = np.ascontiguousarray(np.transpose(ref.dphi3, (0, 2, 1)))
+    origin, scale = mesh.cell_origin_scale(mesh.owned_cells(0))
+    J = np.zeros((rp.nCells, 3, 3))
+    for d in range(3):
+        J[:, d, d] = 2.0 / (np.asarray(scale) * ref.h)
+    x = np.zeros((rp.M + rp.G, 1))
+    x[:, 0] = (rp.nodeXYZ ** 2).sum(axis=1)
+    (rho, grad), = O.compute_rho_grad_rho_from_psi(ranks, [x], [1.0], shape, dshape, [J])
+    xyz_q = origin[:, None, :] + np.asarray(scale)[:, None, None] * ref.quad_xyz[None, :, :]
+    r2 = (xyz_q ** 2).sum(axis=2)
+    # cells that touch the Dirichlet boundary see psi = 0 there (distribute): check the interior cells, coarse and fine
+    dirichlet = np.zeros(rp.M + rp.G, dtype=bool)
+    dirichlet[rp.rowIdsLocal[rp.rowSizes == 0]] = True
+    inner = ~dirichlet[rp.cellLocalDofs].any(axis=1)
+    assert inner.sum() > 4 and np.unique(np.asarray(scale)[inner]).size == 2
+    want = 4.0 * r2[:, :, None] * xyz_q
+    assert np.abs(rho - r2 ** 2)[inner].max() < 1e-10 * (r2 ** 2).max()
+    assert np.abs(grad - want)[inner].max() < 1e-10 * np.abs(want).max()

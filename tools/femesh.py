@@ -147,6 +147,10 @@ class ReferenceCell:
         wq1 = self.wq * (h / 2.0)
         self.quad_w = np.kron(wq1, np.kron(wq1, wq1))
         self.phi3 = np.kron(phi, np.kron(phi, phi))  # (nq^3, n)
+        # derivatives with respect to the reference coordinates xi_e in [-1, 1] (x fastest): (3, nq^3, n); the physical
+        # derivative on a cell of edge s*h is (2 / (s*h)) times these (the diagonal inverse Jacobian of a Cartesian cell)
+        self.dphi3 = np.stack([np.kron(phi, np.kron(phi, dphi)), np.kron(phi, np.kron(dphi, phi)),
+                               np.kron(dphi, np.kron(phi, phi))])
 
 
 def gaussian_wells_potential(box: Sequence[float], nwells: int = 8, seed: int = 1234,
