@@ -86,6 +86,7 @@ EXPORTED_SYMBOLS = [
     "dftfe_b200_get_spectrum_bounds", "dftfe_b200_solve_no_rr", "dftfe_b200_get_colouring", "dftfe_b200_set_option", "dftfe_b200_profile_enable",
     "dftfe_b200_profile_get", "dftfe_b200_profile_reset", "dftfe_b200_launch_count",
     "dftfe_b200_measure_fp64_tensor_peak", "dftfe_b200_transport_name", "dftfe_b200_compute_density_grad",
+    "dftfe_b200_compute_cell_hamiltonian_gga", "dftfe_b200_compute_cell_hamiltonian_kpoints",
 ]
 
 
@@ -271,6 +272,35 @@ class Operator:
             _dptr(cellKScale) if cellKScale is not None else None, _dptr(extPotCorr) if extPotCorr is not None else None,
             _dptr(H)))
         return H
+
+    def computeHamiltonianMatrixGGA(self, shapeValues, shapeGradValues, invJacobian, vEffJxW, derExcSigmaGradRhoJxW,
+                                    gradIntegral, cellKScale=None, extPotCorr=None):
+        """hamMatrixKernelGGAMemOpt, real part: [nC, n, n] (see dftfe_b200_compute_cell_hamiltonian_gga)."""
+        import torch
+
+        n, nq = shapeValues.shape
+        H = torch.empty((self.prob.nCells, n, n), dtype=torch.float64, device=shapeValues.device)
+        null = C.c_void_p()
+        _check(self.lib.dftfe_b200_compute_cell_hamiltonian_gga(
+            self.h, C.c_int32(nq), _dptr(shapeValues), _dptr(shapeGradValues),
+            _dptr(invJacobian) if invJacobian is not None else null, _dptr(vEffJxW), _dptr(derExcSigmaGradRhoJxW),
+            _dptr(gradIntegral), C.c_int32(1 if gradIntegral.dim() == 3 else 0),
+            _dptr(cellKScale) if cellKScale is not None else null, _dptr(extPotCorr) if extPotCorr is not None else null,
+            _dptr(H)))
+        return H
+
+    def computeHamiltonianMatricesAllkpt(self, shapeValues, shapeGradValues, invJacobian, JxW, Hreal, kpoints):
+        """k-point terms of the complex build: complex [nk, nC, n, n] (dftfe_b200_compute_cell_hamiltonian_kpoints)."""
+        import torch
+
+        n, nq = shapeValues.shape
+        kp = _np(kpoints, np.float64).reshape(-1, 3)
+        Hk = torch.empty((kp.shape[0], self.prob.nCells, n, n), dtype=torch.complex128, device=shapeValues.device)
+        _check(self.lib.dftfe_b200_compute_cell_hamiltonian_kpoints(
+            self.h, C.c_int32(nq), _dptr(shapeValues), _dptr(shapeGradValues),
+            _dptr(invJacobian) if invJacobian is not None else C.c_void_p(), _dptr(JxW), _dptr(Hreal),
+            C.c_int32(kp.shape[0]), _ptr(kp), _dptr(Hk)))
+        return Hk
 
     def computeRhoFromPSI(self, X, occupations, shapeValues):
         """computeRhoFromPSI (src/dft/densityCalculator.cc:39-560): rho [nC, nq] from X [M, N] (FE basis)."""

@@ -292,7 +292,7 @@ struct dftfe_b200_ctx {
   dftfe_b200::DevBuf<float> tf32Ws;                                    // split-k partial tiles of the tcgen05 GEMM
   dftfe_b200::DevBuf<double> mpDp;
   dftfe_b200::DevBuf<float> arTmpF;
-  dftfe_b200::DevBuf<double> hamNt, hamW;
+  dftfe_b200::DevBuf<double> hamNt, hamW, hamTabs, hamMc, hamE;
   dftfe_b200::DevBuf<double> denNf, denOcc, denF, denBlock;  // density: tiled shape values, occupancies, block         // cell-Hamiltonian assembly: padded N^T and weights
   dftfe_b200::DevBuf<int> devInfo;
   dftfe_b200::DevBuf<double> cusolverWork;
@@ -385,6 +385,14 @@ int launch_transpose_square(dftfe_b200_ctx *ctx, const double *in, double *out, 
 int compute_cell_hamiltonian(dftfe_b200_ctx *ctx, int nq, const double *shapeValues, const double *vEffJxW,
                              const double *gradIntegral, int gradPerCell, const double *cellKScale,
                              const double *extPotCorr, double *H);
+
+int compute_cell_hamiltonian_gga(dftfe_b200_ctx *ctx, int nq, const double *shapeValues, const double *shapeGradValues,
+                                 const double *invJac, const double *vEffJxW, const double *derExcSigmaGradRhoJxW,
+                                 const double *gradIntegral, int gradPerCell, const double *cellKScale,
+                                 const double *extPotCorr, double *H);
+int compute_cell_hamiltonian_kpoints(dftfe_b200_ctx *ctx, int nq, const double *shapeValues,
+                                     const double *shapeGradValues, const double *invJac, const double *JxW,
+                                     const double *Hreal, int nk, const double *kpoints_h, double *Hk);
 
 // density.cu
 int compute_density(dftfe_b200_ctx *ctx, const double *X, int N, const double *occ_h, int nq, const double *shapeValues,

@@ -509,6 +509,27 @@ int dftfe_b200_compute_cell_hamiltonian(dftfe_b200_ctx *ctx, int32_t n_quad, con
                                   cell_kscale_d, ext_pot_corr_d, H_out_d);
 }
 
+int dftfe_b200_compute_cell_hamiltonian_gga(dftfe_b200_ctx *ctx, int32_t n_quad, const double *shape_values_d,
+                                            const double *shape_grad_values_d, const double *inv_jacobian_d,
+                                            const double *veff_jxw_d, const double *der_exc_sigma_grad_rho_jxw_d,
+                                            const double *grad_integral_d, int32_t grad_integral_per_cell,
+                                            const double *cell_kscale_d, const double *ext_pot_corr_d,
+                                            double *H_out_d) {
+  DB_CTX(ctx);
+  return compute_cell_hamiltonian_gga(ctx, n_quad, shape_values_d, shape_grad_values_d, inv_jacobian_d, veff_jxw_d,
+                                      der_exc_sigma_grad_rho_jxw_d, grad_integral_d, grad_integral_per_cell,
+                                      cell_kscale_d, ext_pot_corr_d, H_out_d);
+}
+
+int dftfe_b200_compute_cell_hamiltonian_kpoints(dftfe_b200_ctx *ctx, int32_t n_quad, const double *shape_values_d,
+                                                const double *shape_grad_values_d, const double *inv_jacobian_d,
+                                                const double *jxw_d, const double *H_real_d, int32_t n_kpoints,
+                                                const double *kpoint_coords_h, double *H_k_out_d) {
+  DB_CTX(ctx);
+  return compute_cell_hamiltonian_kpoints(ctx, n_quad, shape_values_d, shape_grad_values_d, inv_jacobian_d, jxw_d,
+                                          H_real_d, n_kpoints, kpoint_coords_h, H_k_out_d);
+}
+
 int dftfe_b200_compute_density(dftfe_b200_ctx *ctx, const double *X_d, int32_t N, const double *occupations_h,
                                int32_t n_quad, const double *shape_values_d, double *rho_out_d) {
   DB_CTX(ctx);

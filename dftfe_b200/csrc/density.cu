@@ -19,7 +19,7 @@
 // kernel of the same structure that, per (cell, pass over 192 quadrature points, column tile), runs four k-loops -
 // psi and the three reference-cell derivatives d_e psi = sum_I (d_e N_I)(q) x_I - keeps f*2*psi in registers,
 // accumulates rho and the three reference-coordinate components, and applies the cell's inverse Jacobian once at the
-// end (the map to physical derivatives is linear: grad_d = sum_e Jinv[c][e][d] d_e).  The interpolated gradients
+// end (the map to physical derivatives is linear: grad_d = sum_e Jinv[c][d][e] d_e).  The interpolated gradients
 // (3 x nC x nq x B doubles per block in the reference) never touch memory either.
 #include "common.cuh"
 
@@ -450,9 +450,9 @@ density_grad_kernel(const double *__restrict__ Nf, const uint32_t *__restrict__ 
           if ((lane & 3) == 0 && q < nq) {
             rho[(size_t)cell * nq + q] += s;
             double *g = gradRho + ((size_t)cell * nq + q) * 3;
-            g[0] += J[0] * g0 + J[3] * g1 + J[6] * g2;
-            g[1] += J[1] * g0 + J[4] * g1 + J[7] * g2;
-            g[2] += J[2] * g0 + J[5] * g1 + J[8] * g2;
+            g[0] += J[0] * g0 + J[1] * g1 + J[2] * g2;
+            g[1] += J[3] * g0 + J[4] * g1 + J[5] * g2;
+            g[2] += J[6] * g0 + J[7] * g1 + J[8] * g2;
           }
         }
       }
@@ -477,8 +477,8 @@ int launch_density_grad(dftfe_b200_ctx *ctx, const double *x, int ldx, int nColT
 }  // namespace
 
 // rho_out[c][q] = sum_i f_i |psi_i(x_q)|^2 over the N columns of X (row-major M x N, FE basis), cells owned by this rank
-// shapeGradValues [3][n][nq] (reference-cell derivatives), invJac [nC][3][3] (Jinv[c][e][d] = d xi_e / d x_d; nullptr:
-// identity) and gradRho [nC][nq][3] non-null: also grad rho (GGA)
+// shapeGradValues [3][n][nq] (reference-cell derivatives), invJac [nC][3][3] (Jinv[c][d][e] = d xi_e / d x_d, the
+// reference's inverseJacobianValues layout; nullptr: identity) and gradRho [nC][nq][3] non-null: also grad rho (GGA)
 int compute_density(dftfe_b200_ctx *ctx, const double *X, int N, const double *occ_h, int nq, const double *shapeValues,
                     double *rho, const double *shapeGradValues, const double *invJac, double *gradRho) {
   DB_CHECK(ctx->have_map, "compute_density: set_index_map first");

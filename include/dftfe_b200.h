@@ -199,6 +199,26 @@ int dftfe_b200_compute_cell_hamiltonian(dftfe_b200_ctx *ctx, int32_t n_quad, con
                                         const double *veff_jxw_d, const double *grad_integral_d,
                                         int32_t grad_integral_per_cell, const double *cell_kscale_d,
                                         const double *ext_pot_corr_d, double *H_out_d);
+/* GGA functionals: hamMatrixKernelGGAMemOpt (hamiltonianMatrixCalculatorFlattenedDevice.cc:281-440), real part:
+ *   H_c(I,J) = 1/2 K_c(I,J) + sum_q [ vEffJxW N_I N_J + 2 sum_d g_d (d_d N_I N_J + N_I d_d N_J) ]   (+ correction),
+ * g = der_exc_sigma_grad_rho_jxw_d [n_cells][n_quad][3] (derExcWithSigmaTimesGradRhoJxW); shape_grad_values_d:
+ * [3][n][n_quad] derivatives on the reference cell; inv_jacobian_d: [n_cells][3][3], J[c][d][e] = d xi_e / d x_d
+ * (affine cells, the reference's inverseJacobianValues layout; NULL = identity).  Other arguments as above. */
+int dftfe_b200_compute_cell_hamiltonian_gga(dftfe_b200_ctx *ctx, int32_t n_quad, const double *shape_values_d,
+                                            const double *shape_grad_values_d, const double *inv_jacobian_d,
+                                            const double *veff_jxw_d, const double *der_exc_sigma_grad_rho_jxw_d,
+                                            const double *grad_integral_d, int32_t grad_integral_per_cell,
+                                            const double *cell_kscale_d, const double *ext_pot_corr_d,
+                                            double *H_out_d);
+/* k-point dependent terms of the complex kernels (same file :119-278, 442-657): for each of the n_kpoints k-points
+ *   H_k(I,J) = H_real(I,J) + 1/2 |k|^2 sum_q JxW N_I N_J  -  i sum_d k_d sum_q JxW d_d N_I N_J ,
+ * H_real_d: [n_cells][n][n] from dftfe_b200_compute_cell_hamiltonian / _gga (one spin channel); jxw_d: [n_cells][n_quad];
+ * kpoint_coords_h: [3 * n_kpoints] Cartesian; H_k_out_d: [n_kpoints][n_cells][n][n] complex (re, im), the layout
+ * dftfe_b200_set_cell_hamiltonian_kpt consumes (cellHamiltonianMatrixFlattened of the complex build). */
+int dftfe_b200_compute_cell_hamiltonian_kpoints(dftfe_b200_ctx *ctx, int32_t n_quad, const double *shape_values_d,
+                                                const double *shape_grad_values_d, const double *inv_jacobian_d,
+                                                const double *jxw_d, const double *H_real_d, int32_t n_kpoints,
+                                                const double *kpoint_coords_h, double *H_k_out_d);
 
 /* Electron density from the wavefunctions, the step right after solve() in the SCF (computeRhoFromPSI,
  * src/dft/densityCalculator.cc:39-560; densityCalculatorDeviceKernels.cc:35-140):
@@ -213,7 +233,8 @@ int dftfe_b200_compute_density(dftfe_b200_ctx *ctx, const double *X_d, int32_t N
  * isEvaluateGradRho, src/dft/densityCalculatorDeviceKernels.cc:35-140; gradient interpolation of
  * src/dft/densityCalculator.cc): grad_rho_out_d[c][q][d] = sum_i f_i 2 Re(conj(psi_i) d psi_i / d x_d).
  * shape_grad_values_d: [3][n][n_quad] derivatives of the shape functions on the REFERENCE cell;
- * inv_jacobian_d: [n_cells][3][3] with J[c][e][d] = d xi_e / d x_d (affine cells; NULL = identity). */
+ * inv_jacobian_d: [n_cells][3][3] with J[c][d][e] = d xi_e / d x_d - the reference's inverseJacobianValues layout for
+ * affine cells (hamiltonianMatrixCalculatorFlattenedDevice.cc:212-229); NULL = identity. */
 int dftfe_b200_compute_density_grad(dftfe_b200_ctx *ctx, const double *X_d, int32_t N, const double *occupations_h,
                                     int32_t n_quad, const double *shape_values_d, const double *shape_grad_values_d,
                                     const double *inv_jacobian_d, double *rho_out_d, double *grad_rho_out_d);

@@ -783,6 +783,39 @@ def compute_cell_hamiltonian(shape_values, veff_jxw, grad_integral, cell_kscale=
     return H
 
 
+def _physical_shape_gradients(shape_grad_values, inv_jacobians):
+    """gradN[c, d, I, q] = sum_e Jinv[c][d][e] (d N_I / d xi_e)(q): the affine-cell branch of the reference kernels
+    (hamiltonianMatrixCalculatorFlattenedDevice.cc:212-229; inverseJacobianValues[cell*9 + 3*d + e])."""
+    return np.einsum("cde,eiq->cdiq", np.asarray(inv_jacobians), np.asarray(shape_grad_values), optimize=True)
+
+
+def compute_cell_hamiltonian_gga(shape_values, shape_grad_values, inv_jacobians, veff_jxw, der_exc_sigma_grad_rho_jxw,
+                                 grad_integral, cell_kscale=None, ext_pot_corr=None):
+    """hamMatrixKernelGGAMemOpt, real build (hamiltonianMatrixCalculatorFlattenedDevice.cc:281-440):
+    H_c(I,J) = 1/2 K + sum_q [vEffJxW N_I N_J + 2 sum_d g_d (d_d N_I N_J + d_d N_J N_I)] (+ correction)."""
+    N = np.asarray(shape_values)
+    gN = _physical_shape_gradients(shape_grad_values, inv_jacobians)          # [nC, 3, n, nq]
+    g = np.asarray(der_exc_sigma_grad_rho_jxw)                                # [nC, nq, 3]
+    H = compute_cell_hamiltonian(N, veff_jxw, grad_integral, cell_kscale, ext_pot_corr)
+    P = 2.0 * np.einsum("cqd,cdiq->ciq", g, gN, optimize=True)                # sum_d 2 g_d d_d N_I
+    T = np.einsum("ciq,jq->cij", P, N, optimize=True)
+    return H + T + np.transpose(T, (0, 2, 1))
+
+
+def compute_cell_hamiltonian_kpoints(shape_values, shape_grad_values, inv_jacobians, jxw, H_real, kpoints):
+    """k-point terms of the complex kernels (same file :119-278): for each k
+    H_k(I,J) = H_real + 1/2 |k|^2 sum_q JxW N_I N_J - i sum_d k_d sum_q JxW d_d N_I N_J ; returns [nk, nC, n, n]."""
+    N = np.asarray(shape_values)
+    gN = _physical_shape_gradients(shape_grad_values, inv_jacobians)
+    w = np.asarray(jxw)
+    Mc = np.einsum("cq,iq,jq->cij", w, N, N, optimize=True)
+    D = np.einsum("cq,cdiq,jq->cdij", w, gN, N, optimize=True)                # sum_q JxW d_d N_I N_J
+    out = []
+    for k in np.asarray(kpoints, dtype=np.float64).reshape(-1, 3):
+        out.append((np.asarray(H_real) + 0.5 * float(k @ k) * Mc) - 1j * np.einsum("d,cdij->cij", k, D))
+    return np.stack(out)
+
+
 def compute_rho_from_psi(ranks, X, occupations, shape_values):
     """computeRhoFromPSI (src/dft/densityCalculator.cc:39-560): per rank rho[c, q] = sum_i f_i |psi_i(x_q)|^2 with
     psi_i(x_q) = sum_I N_I(q) x_i[row(c, I)] after updateGhostValues + distribute (:296-303).  X: list of
@@ -804,7 +837,7 @@ def compute_rho_grad_rho_from_psi(ranks, X, occupations, shape_values, shape_gra
     """computeRhoFromPSI with isEvaluateGradRho (src/dft/densityCalculator.cc:39-560, kernel
     computeRhoGradRhoFromInterpolatedValues, densityCalculatorDeviceKernels.cc:35-140): besides rho,
         gradRho[c, q, d] = sum_i f_i 2 Re(conj(psi_i(x_q)) d psi_i / d x_d (x_q)),
-        d psi / d x_d = sum_e Jinv[c][e][d] sum_I (d N_I / d xi_e)(q) x_i[row(c, I)].
+        d psi / d x_d = sum_e Jinv[c][d][e] sum_I (d N_I / d xi_e)(q) x_i[row(c, I)]   (Jinv[c][d][e] = d xi_e / d x_d).
     shape_grad_values: [3, n, nq] reference-cell derivatives; inv_jacobians: per rank [nC, 3, 3]."""
     N = np.asarray(shape_values)
     dN = np.asarray(shape_grad_values)
@@ -817,7 +850,7 @@ def compute_rho_grad_rho_from_psi(ranks, X, occupations, shape_values, shape_gra
         Xc = x[rp.cellLocalDofs]                                        # [nC, n, Ncols]
         psi = np.einsum("iq,cik->cqk", N, Xc, optimize=True)
         dref = np.einsum("eiq,cik->ceqk", dN, Xc, optimize=True)        # reference-coordinate derivatives
-        dphys = np.einsum("ced,ceqk->cdqk", np.asarray(J), dref, optimize=True)
+        dphys = np.einsum("cde,ceqk->cdqk", np.asarray(J), dref, optimize=True)
         rho = np.einsum("k,cqk->cq", f, np.abs(psi) ** 2, optimize=True)
         grad = np.einsum("k,cdqk->cqd", f, 2.0 * np.real(np.conj(psi)[:, None] * dphys), optimize=True)
         out.append((rho, grad))

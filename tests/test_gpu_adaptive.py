@@ -160,6 +160,73 @@ def test_cell_hamiltonian_assembly(capi, p, adaptive):
     op.close()
 
 
+@pytest.mark.parametrize("p,adaptive", [(6, False), (3, True)])
+def test_cell_hamiltonian_assembly_gga_and_kpoints(capi, p, adaptive):
+    """SURVEY 8f rank 1, the rest of hamiltonianMatrixCalculatorFlattenedDevice.cc: the GGA gradient terms
+    (hamMatrixKernelGGAMemOpt) and the k-point terms of the complex kernels, as DMMA contractions with the derivative
+    tables, against the oracle's statement of those kernels (random full inverse Jacobians pin the index convention)
+    and against the generator's analytic k-point cell matrices; then a complex operator apply with the result."""
+    from oracle import chfsi_oracle as O
+    from tests.helpers import make_problem, random_global, scatter_to_ranks
+    from tools.femesh import gaussian_wells_potential
+
+    if adaptive:
+        mesh, ranks = make_adaptive_problem(p, (3, 3, 3), 1.4)
+    else:
+        mesh, ranks = make_problem(p, (2, 2, 2), 1.2, (True, True, True))
+    rp = ranks[0]
+    ref = mesh.ref
+    pot = gaussian_wells_potential(mesh.box, periodic=mesh.periodic)
+    cells = mesh.owned_cells(0)
+    origin, scale = mesh.cell_origin_scale(cells)
+    scale = np.asarray(scale, dtype=np.float64)
+    xyz = origin[:, None, :] + scale[:, None, None] * ref.quad_xyz[None, :, :]
+    jxw = ref.quad_w[None, :] * (scale ** 3)[:, None]                       # [nC, nq]
+    vjxw = pot(xyz) * jxw
+    shape = np.ascontiguousarray(ref.phi3.T)
+    dshape = np.ascontiguousarray(np.transpose(ref.dphi3, (0, 2, 1)))       # [3, n, nq]
+    Jdiag = np.zeros((rp.nCells, 3, 3))
+    for d in range(3):
+        Jdiag[:, d, d] = 2.0 / (scale * ref.h)
+    rng = np.random.default_rng(11)
+    Jfull = Jdiag + rng.uniform(-0.2, 0.2, size=Jdiag.shape)
+    g = rng.uniform(-0.3, 0.3, size=(rp.nCells, shape.shape[1], 3)) * jxw[:, :, None]
+    op = capi.Operator(rp, 32)
+    # ---- GGA
+    for J in (Jdiag, Jfull):
+        want = O.compute_cell_hamiltonian_gga(shape, dshape, J, vjxw, g, ref.K3, cell_kscale=scale)
+        got = op.computeHamiltonianMatrixGGA(_dev(shape), _dev(dshape), _dev(J), _dev(vjxw), _dev(g), _dev(ref.K3),
+                                             cellKScale=_dev(scale)).cpu().numpy()
+        assert _relerr(got, want) < 1e-12
+        assert np.array_equal(got, np.transpose(got, (0, 2, 1)))
+    # ---- k-points
+    H_lda = op.computeHamiltonianMatrix(_dev(shape), _dev(vjxw), _dev(ref.K3), cellKScale=_dev(scale))
+    kpts = np.array([[0.0, 0.0, 0.0], [0.21, -0.13, 0.34], [0.5, 0.25, -0.4]])
+    for J in (Jdiag, Jfull):
+        want = O.compute_cell_hamiltonian_kpoints(shape, dshape, J, jxw, H_lda.cpu().numpy(), kpts)
+        got = op.computeHamiltonianMatricesAllkpt(_dev(shape), _dev(dshape), _dev(J), _dev(jxw), H_lda, kpts).cpu().numpy()
+        assert _relerr(got, want) < 1e-12
+    # Cartesian cells: the assembled k-point matrices ARE the generator's analytic ones (Gauss quadrature is exact)
+    got = op.computeHamiltonianMatricesAllkpt(_dev(shape), _dev(dshape), _dev(Jdiag), _dev(jxw), H_lda, kpts)
+    H_gen = mesh.cell_hamiltonians_kpoint(cells, pot, kpts[1], "gauss")
+    assert _relerr(got[1].cpu().numpy(), H_gen) < 1e-11
+    assert np.abs(got[0].cpu().numpy().imag).max() == 0.0   # Gamma point: purely real
+    op.close()
+    # ---- feed one k-point set to a complex operator
+    mesh_k, ranks_k = (mesh, ranks)
+    rpk = ranks_k[0]
+    rpk.H = H_gen
+    opc = capi.Operator(rpk, 8, complex=True)
+    opc.set_cell_hamiltonian(got[1].contiguous())
+    X = scatter_to_ranks(ranks_k, random_global(mesh_k, 8, seed=5, cplx=True), loewdin=True)
+    src, dst = [X[0].copy()], [np.zeros_like(X[0])]
+    O.HX(ranks_k, src, dst, False, 1.0)
+    s_d, d_d = _dev(X[0]), torch.zeros(rpk.M + rpk.G, 8, dtype=torch.complex128, device="cuda")
+    opc.HX(s_d, d_d, False, 1.0)
+    assert _relerr(d_d.cpu().numpy()[:rpk.M], dst[0][:rpk.M]) < 1e-11
+    opc.close()
+
+
 @pytest.mark.parametrize("p,N,B,cplx,nranks", [(3, 15, 15, False, 1), (6, 64, 32, False, 1), (3, 24, 8, True, 1),
                                                (4, 48, 32, False, 2)])
 def test_density_from_wavefunctions(capi, p, N, B, cplx, nranks):
@@ -235,6 +302,8 @@ def test_density_and_gradient_from_wavefunctions(capi, p, N, B, cplx, adaptive):
     J = np.zeros((rp.nCells, 3, 3))
     for d in range(3):
         J[:, d, d] = 2.0 / (np.asarray(scale) * ref.h)
+    if p == 4:   # full (sheared) inverse Jacobians: pins the [d][e] index convention of the kernel against the oracle
+        J += np.random.default_rng(3).uniform(-0.2, 0.2, size=J.shape)
     occ = np.linspace(2.0, 0.1, N)
     if adaptive:
         X = [field_on_nodes(rp, N, seed=2)]

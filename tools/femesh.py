@@ -463,18 +463,27 @@ class GlobalMesh:
         V = rng.uniform(-1.5, 1.5, size=int(n_proj.sum()))
         sig = 0.45 * rc
         eCell, eAtom, Cs = [], [], []
+        # cells whose centre is farther than rc + half a cell diagonal from the atom cannot hold a node inside rc
+        centre = xyz.mean(axis=1)
+        halfdiag = 0.5 * np.sqrt(3.0) * (scale * ref.h)
         for a, R in enumerate(np.asarray(atoms_xyz, dtype=np.float64)):
-            d = xyz - R
-            d = np.where(per, d - box * np.round(d / box), d)
-            r2 = np.sum(d * d, axis=-1)
-            inside = r2 < rc * rc
-            hit = np.nonzero(inside.any(axis=1))[0]
-            if hit.size == 0:
+            dc = centre - R
+            dc = np.where(per, dc - box * np.round(dc / box), dc)
+            cand = np.nonzero(np.sqrt(np.sum(dc * dc, axis=-1)) < rc + halfdiag)[0]
+            if cand.size == 0:
                 continue
-            g = np.exp(-r2[hit] / (2 * sig * sig)) * inside[hit] * wnode[hit]
-            dd = d[hit]
+            d = xyz[cand] - R
+            d = np.where(per, d - box * np.round(d / box), d)
+            r2c = np.sum(d * d, axis=-1)
+            insidec = r2c < rc * rc
+            sel = np.nonzero(insidec.any(axis=1))[0]
+            if sel.size == 0:
+                continue
+            hit = cand[sel]
+            r2h, inside_h, dd = r2c[sel], insidec[sel], d[sel]
+            g = np.exp(-r2h / (2 * sig * sig)) * inside_h * wnode[hit]
             polys = [np.ones_like(g), dd[..., 0], dd[..., 1], dd[..., 2], dd[..., 0] * dd[..., 1],
-                     dd[..., 1] * dd[..., 2], dd[..., 0] * dd[..., 2], r2[hit] - 1.0]
+                     dd[..., 1] * dd[..., 2], dd[..., 0] * dd[..., 2], r2h - 1.0]
             blk = np.zeros((hit.size, ref.n, pmax), dtype=np.complex128 if kpoint is not None else np.float64)
             for p in range(int(n_proj[a])):
                 blk[:, :, p] = polys[p % len(polys)] * g * (1.0 + 0.25 * (p // len(polys)))
