@@ -87,6 +87,8 @@ EXPORTED_SYMBOLS = [
     "dftfe_b200_profile_get", "dftfe_b200_profile_reset", "dftfe_b200_launch_count",
     "dftfe_b200_measure_fp64_tensor_peak", "dftfe_b200_transport_name", "dftfe_b200_compute_density_grad",
     "dftfe_b200_compute_cell_hamiltonian_gga", "dftfe_b200_compute_cell_hamiltonian_kpoints",
+    "dftfe_b200_band_comm_init", "dftfe_b200_band_comm_init_loopback", "dftfe_b200_band_group_indices",
+    "dftfe_b200_band_group_merge",
 ]
 
 
@@ -151,6 +153,13 @@ def build_index_map(cell_global_dofs: np.ndarray, owned_start: int, owned_end: i
     _check(lib.dftfe_b200_build_index_map(_ptr(cg), C.c_int64(nC), C.c_int32(n), C.c_int64(owned_start),
                                           C.c_int64(owned_end), _ptr(gh), C.c_int64(gh.size), C.c_int32(block),
                                           _ptr(out)))
+    return out
+
+
+def band_group_indices(n_band_groups: int, N: int) -> np.ndarray:
+    """dftUtils::createBandParallelizationIndices: [2 * n_band_groups] low / high-plus-one column indices."""
+    out = np.zeros(2 * n_band_groups, dtype=np.int32)
+    _check(load().dftfe_b200_band_group_indices(C.c_int32(n_band_groups), C.c_int32(N), _ptr(out)))
     return out
 
 
@@ -242,6 +251,17 @@ class Operator:
         _check(self.lib.dftfe_b200_comm_init_loopback(self.h, C.c_int32(group_id), C.c_int32(rank), C.c_int32(nranks)))
 
     # ---- Hamiltonian ------------------------------------------------------
+    def band_comm_init(self, unique_id: bytes, band_group_id: int, n_band_groups: int):
+        buf = (C.c_uint8 * 128).from_buffer_copy(unique_id)
+        _check(self.lib.dftfe_b200_band_comm_init(self.h, buf, C.c_int32(band_group_id), C.c_int32(n_band_groups)))
+
+    def band_comm_init_loopback(self, group_id: int, band_group_id: int, n_band_groups: int):
+        _check(self.lib.dftfe_b200_band_comm_init_loopback(self.h, C.c_int32(group_id), C.c_int32(band_group_id),
+                                                           C.c_int32(n_band_groups)))
+
+    def band_group_merge(self, X):
+        _check(self.lib.dftfe_b200_band_group_merge(self.h, _dptr(X), C.c_int32(X.shape[1])))
+
     def set_cell_hamiltonian(self, H, kPointIndex: int = 0, spinIndex: int = 0):
         """H: torch CUDA tensor or numpy array [nCells, n, n] (mem[c,I,J] = H_c(I,J)); stored as the
         (k-point, spin) set and made active."""

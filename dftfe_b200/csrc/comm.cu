@@ -60,11 +60,12 @@ const NcclApi *nccl_api() {
       DB_SYM(Send, "ncclSend");
       DB_SYM(Recv, "ncclRecv");
       DB_SYM(AllReduce, "ncclAllReduce");
+      DB_SYM(Broadcast, "ncclBroadcast");
       DB_SYM(GroupStart, "ncclGroupStart");
       DB_SYM(GroupEnd, "ncclGroupEnd");
       DB_SYM(GetErrorString, "ncclGetErrorString");
 #undef DB_SYM
-      if (api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.Send && api.Recv && api.AllReduce &&
+      if (api.GetUniqueId && api.CommInitRank && api.CommDestroy && api.Send && api.Recv && api.AllReduce && api.Broadcast &&
           api.GroupStart && api.GroupEnd && api.GetErrorString)
         state = 1;
     }
@@ -101,6 +102,8 @@ struct LoopbackHandle {
   std::shared_ptr<LoopbackGroup> grp;
 };
 static std::map<dftfe_b200_ctx *, LoopbackHandle> g_handles;
+static std::map<int, std::shared_ptr<LoopbackGroup>> g_band_groups;       // in-process band-group communicators
+static std::map<dftfe_b200_ctx *, LoopbackHandle> g_band_handles;
 
 static LoopbackGroup *loopback_of(dftfe_b200_ctx *ctx) {
   std::lock_guard<std::mutex> lk(g_groups_mu);
@@ -111,6 +114,27 @@ static LoopbackGroup *loopback_of(dftfe_b200_ctx *ctx) {
 void loopback_forget(dftfe_b200_ctx *ctx) {
   std::lock_guard<std::mutex> lk(g_groups_mu);
   g_handles.erase(ctx);
+  g_band_handles.erase(ctx);
+}
+
+static LoopbackGroup *band_loopback_of(dftfe_b200_ctx *ctx) {
+  std::lock_guard<std::mutex> lk(g_groups_mu);
+  auto it = g_band_handles.find(ctx);
+  return it == g_band_handles.end() ? nullptr : it->second.grp.get();
+}
+
+int band_loopback_join(dftfe_b200_ctx *ctx, int group_id, int band_id, int n_groups) {
+  std::lock_guard<std::mutex> lk(g_groups_mu);
+  auto &g = g_band_groups[group_id];
+  if (!g || g->nranks != n_groups || (int)g->members.size() != n_groups || g->members[band_id] != nullptr) {
+    g = std::make_shared<LoopbackGroup>();
+    g->nranks = n_groups;
+    g->members.assign(n_groups, nullptr);
+    g->pub.assign(n_groups, nullptr);
+  }
+  g->members[band_id] = ctx;
+  g_band_handles[ctx] = LoopbackHandle{g};
+  return 0;
 }
 
 int loopback_join(dftfe_b200_ctx *ctx, int group_id, int rank, int nranks) {
@@ -581,6 +605,63 @@ int allreduce_sum(dftfe_b200_ctx *ctx, double *buf, size_t count) {
   DB_CUDA(cudaMemcpyAsync(buf, ctx->arTmp.p, count * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
   DB_CUDA(cudaStreamSynchronize(ctx->stream));
   grp->barrier();
+  return 0;
+}
+
+// dftUtils::createBandParallelizationIndices (utils/dftUtils.cc:219-240): group g owns the wavefunction columns
+// [g * (N / nGroups), (g + 1) * (N / nGroups)), the last group up to N
+void band_group_range(int nGroups, int N, int g, int &lo, int &hi) {
+  const int w = N / nGroups;
+  lo = g * w;
+  hi = (g == nGroups - 1) ? N : (g + 1) * w;
+}
+
+// Merge of the band groups after the filter (solver .cc:539-567, pseudoGSDevice.cc:370-452): every group holds its own
+// filtered columns of X; afterwards all groups hold all columns.  The reference copies the whole zero-padded X to the
+// host and MPI_Allreduce-sums it; here each group's column slice is packed (M x w, contiguous) and broadcast from its
+// owner over NCCL (one grouped call), i.e. an all-gather that moves every element once instead of summing zeros.
+int band_group_merge(dftfe_b200_ctx *ctx, double *X, int N) {
+  const int ng = ctx->nBandGroups;
+  if (ng <= 1) return 0;
+  LoopbackGroup *grp = band_loopback_of(ctx);
+  DB_CHECK(ctx->bandNccl || grp, "band_group_merge needs band_comm_init (NCCL) or a band loopback group");
+  DB_CHECK(N / ng >= 1, "band_group_merge: more band groups (%d) than wavefunctions (%d)", ng, N);
+  const int cm = ctx->cm;
+  const int64_t M = ctx->M;
+  DB_TRY(ctx->bandBuf.alloc((size_t)std::max<int64_t>(M, 1) * N * cm));
+  std::vector<size_t> off(ng + 1, 0);
+  for (int g = 0; g < ng; ++g) {
+    int lo, hi;
+    band_group_range(ng, N, g, lo, hi);
+    off[g + 1] = off[g] + (size_t)M * (hi - lo) * cm;
+  }
+  int lo, hi;
+  band_group_range(ng, N, ctx->bandId, lo, hi);
+  double *mine = ctx->bandBuf.p + off[ctx->bandId];
+  DB_TRY(launch_block_copy_from_full(ctx, X, N * cm, lo * cm, mine, (hi - lo) * cm, M, nullptr));
+  if (ctx->bandNccl) {
+    DB_NCCL(nccl_api()->GroupStart());
+    for (int g = 0; g < ng; ++g)
+      DB_NCCL(nccl_api()->Broadcast(ctx->bandBuf.p + off[g], ctx->bandBuf.p + off[g], off[g + 1] - off[g], ncclDouble, g,
+                                    ctx->bandNccl, ctx->stream));
+    DB_NCCL(nccl_api()->GroupEnd());
+  } else {
+    DB_CUDA(cudaStreamSynchronize(ctx->stream));
+    grp->pub[ctx->bandId] = mine;
+    grp->barrier();
+    for (int g = 0; g < ng; ++g)
+      if (g != ctx->bandId)
+        DB_CUDA(cudaMemcpyAsync(ctx->bandBuf.p + off[g], grp->pub[g], (off[g + 1] - off[g]) * sizeof(double),
+                                cudaMemcpyDeviceToDevice, ctx->stream));
+    DB_CUDA(cudaStreamSynchronize(ctx->stream));
+    grp->barrier();
+  }
+  for (int g = 0; g < ng; ++g) {
+    if (g == ctx->bandId) continue;
+    int glo, ghi;
+    band_group_range(ng, N, g, glo, ghi);
+    DB_TRY(launch_block_copy_to_full(ctx, X, N * cm, glo * cm, ctx->bandBuf.p + off[g], (ghi - glo) * cm, M, nullptr));
+  }
   return 0;
 }
 

@@ -59,6 +59,7 @@ struct NcclApi {
   ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
   ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+  ncclResult_t (*Broadcast)(const void *, void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t);
   ncclResult_t (*GroupStart)();
   ncclResult_t (*GroupEnd)();
   const char *(*GetErrorString)(ncclResult_t);
@@ -245,6 +246,11 @@ struct dftfe_b200_ctx {
     uint32_t seq[2][2] = {{0, 0}, {0, 0}};      // [lane][0 forward, 1 reverse] exchanges issued so far
   } p2p;
 
+  // --- band parallelisation (interBandGroupComm): contexts that hold the same mesh partition in different band groups
+  ncclComm_t bandNccl = nullptr;
+  int bandId = 0, nBandGroups = 1;
+  dftfe_b200::DevBuf<double> bandBuf;   // packed column slices of every band group: M x N doubles in total
+
   // --- cell Hamiltonian (fragment-major)
   bool have_H = false;
   bool force_generic_cell_kernel = false;  // test hook: run the non-persistent kernel
@@ -362,6 +368,8 @@ int launch_orphan_first_touch(dftfe_b200_ctx *ctx, const double *src, double *ds
                               const EpilogueParams &ep);
 
 int allreduce_sum(dftfe_b200_ctx *ctx, double *buf, size_t count);
+void band_group_range(int nGroups, int N, int g, int &lo, int &hi);
+int band_group_merge(dftfe_b200_ctx *ctx, double *X, int N);
 int allreduce_sum_f32(dftfe_b200_ctx *ctx, float *buf, size_t count);
 
 // nonlocal.cu

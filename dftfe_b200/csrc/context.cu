@@ -30,6 +30,7 @@ int ensure_dyn_smem(const void *kernel, int device, size_t bytes) {
 }
 
 int loopback_join(dftfe_b200_ctx *ctx, int group_id, int rank, int nranks);
+int band_loopback_join(dftfe_b200_ctx *ctx, int group_id, int band_id, int n_groups);
 void loopback_forget(dftfe_b200_ctx *ctx);
 
 // row words of the flagged index map: row | live<<30 | first<<31 (see cell_matvec.cu)
@@ -167,6 +168,7 @@ void dftfe_b200_destroy(dftfe_b200_ctx *ctx) {
   if (ctx->copyIn) cudaStreamDestroy(ctx->copyIn);
   if (ctx->copyOut) cudaStreamDestroy(ctx->copyOut);
   p2p_release(ctx);
+  if (ctx->bandNccl && nccl_api()) nccl_api()->CommDestroy(ctx->bandNccl);
   if (ctx->nccl && nccl_api()) nccl_api()->CommDestroy(ctx->nccl);
   if (ctx->cusolver) cusolverDnDestroy(ctx->cusolver);
   if (ctx->cublas) cublasDestroy(ctx->cublas);
@@ -440,6 +442,48 @@ int dftfe_b200_comm_init_loopback(dftfe_b200_ctx *ctx, int32_t group_id, int32_t
   ctx->rank = rank;
   ctx->nranks = nranks;
   return loopback_join(ctx, group_id, rank, nranks);
+}
+
+int dftfe_b200_band_comm_init(dftfe_b200_ctx *ctx, const uint8_t id_h[128], int32_t band_group_id,
+                              int32_t n_band_groups) {
+  DB_CTX(ctx);
+  DB_CHECK(!ctx->bandNccl, "band_comm_init: communicator already initialised");
+  DB_CHECK(n_band_groups >= 1 && band_group_id >= 0 && band_group_id < n_band_groups, "band_comm_init: bad group id");
+  ncclUniqueId id;
+  std::memcpy(&id, id_h, 128);
+  if (!nccl_api()) return DFTFE_B200_ERR_NCCL;
+  DB_NCCL(nccl_api()->CommInitRank(&ctx->bandNccl, n_band_groups, id, band_group_id));
+  ctx->bandId = band_group_id;
+  ctx->nBandGroups = n_band_groups;
+  return 0;
+}
+
+int dftfe_b200_band_comm_init_loopback(dftfe_b200_ctx *ctx, int32_t group_id, int32_t band_group_id,
+                                       int32_t n_band_groups) {
+  DB_CTX(ctx);
+  DB_CHECK(n_band_groups >= 1 && band_group_id >= 0 && band_group_id < n_band_groups,
+           "band_comm_init_loopback: bad group id");
+  ctx->bandId = band_group_id;
+  ctx->nBandGroups = n_band_groups;
+  return band_loopback_join(ctx, group_id, band_group_id, n_band_groups);
+}
+
+int dftfe_b200_band_group_indices(int32_t n_band_groups, int32_t N, int32_t *low_high_plus_one_out_h) {
+  DB_CHECK(n_band_groups >= 1 && N / n_band_groups >= 1 && low_high_plus_one_out_h,
+           "band_group_indices: NPBAND is more than the number of bands");
+  for (int g = 0; g < n_band_groups; ++g) {
+    int lo, hi;
+    band_group_range(n_band_groups, N, g, lo, hi);
+    low_high_plus_one_out_h[2 * g] = lo;
+    low_high_plus_one_out_h[2 * g + 1] = hi;
+  }
+  return 0;
+}
+
+int dftfe_b200_band_group_merge(dftfe_b200_ctx *ctx, double *X_d, int32_t N) {
+  DB_CTX(ctx);
+  DB_CHECK(X_d && N >= 1, "band_group_merge: null argument");
+  return band_group_merge(ctx, X_d, N);
 }
 
 int dftfe_b200_set_nonlocal_kpt(dftfe_b200_ctx *ctx, int32_t kpoint_index, int32_t n_atoms,

@@ -859,7 +859,16 @@ static int filter_blocks_impl(dftfe_b200_ctx *ctx, double *Xd, double *Xh, int N
   DB_CHECK(N % B == 0, "number of wavefunctions (%d) must be a multiple of the Chebyshev block size (%d)", N, B);
   DB_CHECK(m >= 1, "Chebyshev degree must be >= 1");
   DB_TRY(ensure_block_scratch(ctx));
-  const int cm = ctx->cm, nb = N / B;
+  const int cm = ctx->cm;
+  // band parallelisation: this band group filters the blocks that end inside its column range (solver .cc:394-400)
+  std::vector<int> myBlocks;
+  {
+    int lo = 0, hi = N;
+    if (ctx->nBandGroups > 1) band_group_range(ctx->nBandGroups, N, ctx->bandId, lo, hi);
+    for (int j = 0; j < N; j += B)
+      if (j + B <= hi && j + B > lo) myBlocks.push_back(j / B);
+  }
+  const int nb = (int)myBlocks.size();
   const bool host = Xh != nullptr;
   const bool lanes = ctx->overlap_lanes != 0 && nb >= 2;
   const int nl = lanes ? 2 : 1;
@@ -895,7 +904,8 @@ static int filter_blocks_impl(dftfe_b200_ctx *ctx, double *Xd, double *Xh, int N
       const int nCur = std::min(nl, nb - g * nl);
       ChebState st[2];
       for (int l = 0; l < nCur; ++l) {
-        const int blkIdx = g * nl + l;
+        const int blkIdx = myBlocks[g * nl + l];
+        const int ev = g * nl + l;  // event slot
         double *buf = bx[set][l];
         on_lane(l);
         if (host) {
@@ -903,8 +913,8 @@ static int filter_blocks_impl(dftfe_b200_ctx *ctx, double *Xd, double *Xh, int N
           if (g >= 2) DB_CUDA(cudaStreamWaitEvent(ctx->copyIn, evOut[(g - 2) * nl + l], 0));
           DB_CUDA(cudaMemcpy2DAsync(buf, rowBytes, Xh + (size_t)blkIdx * B * cm, pitchBytes, rowBytes, (size_t)ctx->M,
                                     cudaMemcpyHostToDevice, ctx->copyIn));
-          DB_CUDA(cudaEventRecord(evIn[blkIdx], ctx->copyIn));
-          DB_CUDA(cudaStreamWaitEvent(ctx->stream, evIn[blkIdx], 0));
+          DB_CUDA(cudaEventRecord(evIn[ev], ctx->copyIn));
+          DB_CUDA(cudaStreamWaitEvent(ctx->stream, evIn[ev], 0));
           if (inScale) DB_TRY(launch_row_scale(ctx, buf, ctx->M, B * cm, B * cm, 1.0, inScale));
         } else {
           DB_TRY(launch_block_copy_from_full(ctx, Xd, N * cm, blkIdx * B * cm, buf, B * cm, ctx->M, inScale));
@@ -918,16 +928,17 @@ static int filter_blocks_impl(dftfe_b200_ctx *ctx, double *Xd, double *Xh, int N
           DB_TRY(cheb_step(ctx, st[l], B, m, mixedPrec));
         }
       for (int l = 0; l < nCur; ++l) {
-        const int blkIdx = g * nl + l;
+        const int blkIdx = myBlocks[g * nl + l];
+        const int ev = g * nl + l;
         double *buf = bx[set][l];
         on_lane(l);
         DB_TRY(cheb_end(ctx, st[l], buf, B));
         if (host) {
-          DB_CUDA(cudaEventRecord(evComp[blkIdx], ctx->stream));
-          DB_CUDA(cudaStreamWaitEvent(ctx->copyOut, evComp[blkIdx], 0));
+          DB_CUDA(cudaEventRecord(evComp[ev], ctx->stream));
+          DB_CUDA(cudaStreamWaitEvent(ctx->copyOut, evComp[ev], 0));
           DB_CUDA(cudaMemcpy2DAsync(Xh + (size_t)blkIdx * B * cm, pitchBytes, buf, rowBytes, rowBytes, (size_t)ctx->M,
                                     cudaMemcpyDeviceToHost, ctx->copyOut));
-          DB_CUDA(cudaEventRecord(evOut[blkIdx], ctx->copyOut));
+          DB_CUDA(cudaEventRecord(evOut[ev], ctx->copyOut));
         } else {
           DB_TRY(launch_block_copy_to_full(ctx, Xd, N * cm, blkIdx * B * cm, buf, B * cm, ctx->M, nullptr));
         }
@@ -958,11 +969,15 @@ static int filter_blocks_impl(dftfe_b200_ctx *ctx, double *Xd, double *Xh, int N
 
 static int filter_all_impl(dftfe_b200_ctx *ctx, double *X, int N, int m, double a, double b, double a0,
                            const double *inScale, bool mixedPrec = false) {
-  return filter_blocks_impl(ctx, X, nullptr, N, m, a, b, a0, inScale, mixedPrec);
+  DB_TRY(filter_blocks_impl(ctx, X, nullptr, N, m, a, b, a0, inScale, mixedPrec));
+  // band groups: the columns of the other groups (untouched here, not even by the M^1/2 scaling folded into the
+  // copy-in) are replaced by their owners' filtered columns; a no-op for one band group
+  return band_group_merge(ctx, X, N);
 }
 
 static int filter_all_host_impl(dftfe_b200_ctx *ctx, double *X_h, int N, int m, double a, double b, double a0,
                                 bool mixedPrec) {
+  DB_CHECK(ctx->nBandGroups == 1, "cheb_filter_all_host: band groups need the device-resident X (band_group_merge)");
   return filter_blocks_impl(ctx, nullptr, X_h, N, m, a, b, a0, nullptr, mixedPrec);
 }
 

@@ -152,6 +152,23 @@ int dftfe_b200_comm_init(dftfe_b200_ctx *ctx, const uint8_t id_h[128], int32_t r
  * Test facility for the multi-rank path; production uses dftfe_b200_comm_init. */
 int dftfe_b200_comm_init_loopback(dftfe_b200_ctx *ctx, int32_t group_id, int32_t rank, int32_t nranks);
 
+/* ---- band parallelisation (NPBAND > 1) --------------------------------------------------------------------------
+ * The reference distributes the wavefunction blocks of the filter over "band groups" - replicas of the whole domain
+ * decomposition linked by interBandGroupComm - and merges them afterwards by copying the zero-padded X to the host and
+ * MPI_Allreduce-ing it (chebyshevOrthogonalizedSubspaceIterationSolverDevice.cc:376-400, 539-567;
+ * pseudoGSDevice.cc:370-452).  Here the communicator links the contexts that hold the SAME mesh partition in the
+ * different band groups; cheb_filter_all / solve filter only the blocks of this group's column range and merge with one
+ * grouped NCCL broadcast per group slice (an all-gather: every element moves once, nothing is summed). */
+int dftfe_b200_band_comm_init(dftfe_b200_ctx *ctx, const uint8_t id_h[128], int32_t band_group_id,
+                              int32_t n_band_groups);
+/* In-process twin for single-GPU tests (one context + one host thread per band group). */
+int dftfe_b200_band_comm_init_loopback(dftfe_b200_ctx *ctx, int32_t group_id, int32_t band_group_id,
+                                       int32_t n_band_groups);
+/* dftUtils::createBandParallelizationIndices (utils/dftUtils.cc:219-240): out[2g], out[2g+1] = column range of group g. */
+int dftfe_b200_band_group_indices(int32_t n_band_groups, int32_t N, int32_t *low_high_plus_one_out_h);
+/* The merge alone: every group holds its own columns of X_d (M x N, owned rows) -> all groups hold all columns. */
+int dftfe_b200_band_group_merge(dftfe_b200_ctx *ctx, double *X_d, int32_t N);
+
 /* Non-local (separable pseudopotential) projectors, the data reinit() packs at
  * kohnShamDFTOperatorDevice.cc:626-927: for each (owned cell, atom) pair in the compact support an
  * n x p_max block C[e][i][p] = <N_i | phi_{atom,p}> (zero padded), the coupling constants V (atom-major)

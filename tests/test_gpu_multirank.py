@@ -182,3 +182,55 @@ def test_p2p_transport_two_lane_filter_fp64_and_fp32_payloads(lib_built, nranks,
         assert np.abs(out_p2p[r]["fp32"] - ref32[r][:M]).max() < 2e-5 * scale
         assert np.array_equal(out_p2p[r]["fp32"], out_host[r]["fp32"])
         assert np.abs(out_p2p[r]["fp32"] - out_p2p[r]["two_lanes"]).max() > 0
+
+
+@pytest.mark.parametrize("n_band,n_dom", [(2, 1), (3, 1), (2, 2)])
+def test_band_groups_filter_and_merge(lib_built, n_band, n_dom):
+    """Band parallelisation: every band group filters the blocks of its own column range
+    (createBandParallelizationIndices) and the groups are merged by the all-gather that replaces the reference's host
+    MPI_Allreduce of the zero-padded X (solver .cc:539-567): bit-identical to one band group, equal to the oracle."""
+    from dftfe_b200 import capi
+    from oracle import chfsi_oracle as O
+
+    p, B, N, m = 2, 16, 96, 6
+    mesh, ranks = make_problem(p, (4, 3, 3), 1.1, (True, True, False), nranks=n_dom,
+                               extra_constraints=hanging_like_constraints(3))
+    Xs = scatter_to_ranks(ranks, random_global(mesh, N, seed=12), loewdin=True)
+    a, b, a0 = 5.0, 60.0, -2.0
+    ref = [x.copy() for x in Xs]
+    for j in range(0, N, B):
+        blk = [np.ascontiguousarray(x[:, j:j + B]) for x in Xs]
+        out = O.chebyshev_filter_device_state(ranks, blk, m, a, b, a0)
+        for r in range(n_dom):
+            ref[r][:, j:j + B] = out[r]
+    scale = max(np.abs(x).max() for x in ref)
+    idx = capi.band_group_indices(n_band, N)
+    assert idx[0] == 0 and idx[-1] == N and all(idx[2 * g + 1] == idx[2 * g + 2] for g in range(n_band - 1))
+    assert idx[1] == N // n_band
+
+    def run(nb, base):
+        def fn(t):
+            g, r = t // n_dom, t % n_dom
+            rp = ranks[r]
+            op = capi.Operator(rp, B, use_torch_stream=False)
+            if n_dom > 1:
+                op.comm_init_loopback(base + g, r, n_dom)            # domain decomposition inside band group g
+            if nb > 1:
+                op.band_comm_init_loopback(base + 50 + r, g, nb)     # the same partition r across the band groups
+            op.set_cell_hamiltonian(rp.H)
+            Xd = _dev(Xs[r][:rp.M])
+            op.chebyshevFilterAll(Xd, m, a, b, a0)
+            op.sync()
+            res = Xd.cpu().numpy()
+            op.close()
+            return res
+
+        return _run_ranks(nb * n_dom, fn)
+
+    multi = run(n_band, 500 + 10 * n_band)
+    single = run(1, 700 + 10 * n_band)
+    for g in range(n_band):
+        for r in range(n_dom):
+            got = multi[g * n_dom + r]
+            assert np.array_equal(got, single[r]), (g, r)
+            assert np.abs(got - ref[r][:ranks[r].M]).max() < m * 1e-12 * scale
