@@ -555,6 +555,8 @@ def main_ours(args):
         else:
             ms_roof = ms_total
         k_ms, k_launches = op.profile_get("cell_matvec")
+        other_ms = {nm: op.profile_get(nm)[0] for nm in ("nonlocal", "distribute", "slave_to_master", "ghost_pack",
+                                                          "ghost_unpack", "block_copy")}
         finite = bool(torch.isfinite(torch.view_as_real(X) if cplx else X).all().item())
 
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
@@ -584,7 +586,8 @@ def main_ours(args):
                     "peak_measured_in_run": peak_now, "peak_committed": peak_committed,
                     "launches_timed": int(k_launches), "avg_launch_ms": avg_launch_s * 1e3,
                     "kernel_share_of_step": k_ms / ms_roof, "timed_in": roofline_pass,
-                    "flops_per_launch": flops_per_launch, "cells_per_launch": rp.nCells / ncol}
+                    "flops_per_launch": flops_per_launch, "cells_per_launch": rp.nCells / ncol,
+                    "other_kernels_ms_in_that_step": {k: v for k, v in other_ms.items() if v > 0}}
 
         # ---- second BASELINE metric: wall seconds per SCF iteration's eigen-solve = one solve() pass
         # (filter + X^T X + Cholesky + X^T H X + eigh + rotation + residuals) on fresh random wavefunctions
