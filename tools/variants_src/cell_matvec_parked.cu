@@ -36,7 +36,7 @@
 // stored, odd ones take Ai and the partner column with the sign of the real part flipped
 // (one integer XOR per fragment).  No split re/im temporaries (the reference needs them
 // around its atomics, matrixVectorProductImplementationsDevice.cc:86-108).
-#include "common.cuh"
+#include "../../dftfe_b200/csrc/common.cuh"
 
 namespace dftfe_b200 {
 
@@ -294,10 +294,15 @@ cell_matvec_kernel(const double *__restrict__ Ht, const uint32_t *__restrict__ c
 //     (cp.async.bulk, one 256-byte row segment each, completion on an mbarrier)
 //     into the other half of a double-buffered shared-memory tile while
 //   * twelve MMA warps run the DMMA k-loop of the current item with a 4-deep
-//     register prefetch of their A fragments (one LDG.E.256 per k-step) and then do
-//     the recurrence / assembly epilogue straight from registers.
-// No CTA-wide barrier inside the loop: warps drift, so one warp's epilogue
-// overlaps its SMSP neighbours' DMMAs.
+//     register prefetch of their A fragments (one LDG.E.256 per k-step), then PARK
+//     their accumulators (already scaled, with the a*src term of first touches) in the
+//     rows of the X tile they own - the tile is dead once every MMA warp has left the
+//     k-loop - and go straight to the next item;
+//   * three epilogue warps (one per remaining scheduler) drain the parked tile: the
+//     recurrence's b*dst term and the coloured read-modify-write of dst, eight rows in
+//     flight per warp, then hand the buffer back to the producer.
+// The dst round trip (long-scoreboard stalls of all twelve MMA warps at once in the
+// round-1 kernel) now runs under the next item's DMMAs.
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -335,22 +340,166 @@ template <int NODES, bool CPLX>
 struct PersistCfg {
   using C = CellCfg<NODES, CPLX>;
   static constexpr int MMA_WARPS = C::WARPS;
-  static constexpr int THREADS = (MMA_WARPS + 1) * 32;  // + one producer warp
-  static constexpr size_t XBUF = (size_t)C::KPAD * LDS;  // doubles per buffer
-  static constexpr size_t SMEM = 2 * XBUF * sizeof(double) + 2 * NODES * sizeof(uint32_t) + 4 * sizeof(uint64_t);
-#ifndef DB_APF
-#define DB_APF 4
+  static constexpr int ACTIVE_MMA_WARPS = C::MT < C::WARPS ? C::MT : C::WARPS;  // warps that own row tiles
+#ifndef DB_EPI_WARPS
+#define DB_EPI_WARPS 3
 #endif
-// what-if switches for profiling (results are wrong when set): skip the A-fragment refills / the epilogue's global
-// traffic to measure what each costs (profiles/r01_cell_kernel_variants.txt)
-#ifndef DB_WHATIF_NOA
-#define DB_WHATIF_NOA 0
+#ifndef DB_EROWS
+#define DB_EROWS 40
 #endif
+// what-if switches for profiling (results are wrong when set): skip the epilogue warps' global traffic / the parking
 #ifndef DB_WHATIF_NOEPI
 #define DB_WHATIF_NOEPI 0
 #endif
+#ifndef DB_WHATIF_NOLOAD
+#define DB_WHATIF_NOLOAD 0
+#endif
+#ifndef DB_WHATIF_NOSTORE
+#define DB_WHATIF_NOSTORE 0
+#endif
+#ifndef DB_WHATIF_HALFGATHER
+#define DB_WHATIF_HALFGATHER 0
+#endif
+#ifndef DB_WHATIF_NOFP64
+#define DB_WHATIF_NOFP64 0
+#endif
+#ifndef DB_DST_PREFETCH
+#define DB_DST_PREFETCH 1
+#endif
+#ifndef DB_WHATIF_NOPARK
+#define DB_WHATIF_NOPARK 0
+#endif
+  static constexpr int EPI_WARPS = DB_EPI_WARPS;         // drain the parked accumulators (see the kernel)
+  static constexpr int THREADS = (MMA_WARPS + 1 + EPI_WARPS) * 32;  // producer + MMA + epilogue warps
+  static constexpr size_t XBUF = (size_t)C::KPAD * LDS;  // doubles per buffer
+  // X tiles, row words, barriers, and per-row epilogue records {cb, row} (16 B) the MMA warps leave for the epilogue warps
+  static constexpr size_t ROWS_BYTES = ((2 * NODES * sizeof(uint32_t) + 15) / 16) * 16;
+  static constexpr size_t SMEM = 2 * XBUF * sizeof(double) + ROWS_BYTES + 2 * NODES * 16 + 8 * sizeof(uint64_t);
+#ifndef DB_APF
+#define DB_APF 4
+#endif
   static constexpr int APF = DB_APF;  // A-fragment prefetch depth in (virtual) k-steps
 };
+
+// Column tiling of a block of `ncols` columns: nColTiles = ceil(ncols / 32) tiles; the ceil(ncols / 8) n8 tiles
+// are dealt as evenly as possible (e.g. 100 columns -> 4,3,3,3), because every item streams the whole H_c and a
+// narrow tile would make that stream the bottleneck.
+struct ColTiling {
+  int base, rem;  // tiles [0, rem) hold base+1 n8 tiles, the others base
+  __host__ __device__ ColTiling(int ncols, int nColTiles) {
+    const int total8 = (ncols + 7) >> 3;
+    base = total8 / nColTiles;
+    rem = total8 % nColTiles;
+  }
+  __host__ __device__ int ntl(int tile) const { return base + (tile < rem ? 1 : 0); }
+  __host__ __device__ int col0(int tile) const { return 8 * (tile * base + (tile < rem ? tile : rem)); }
+};
+
+
+// named barrier over the MMA warps that own row tiles (ids 1.. are free: __syncthreads uses 0)
+template <int COUNT>
+__device__ __forceinline__ void mma_warps_barrier() {
+  asm volatile("bar.sync 1, %0;" ::"n"(COUNT) : "memory");
+}
+
+// End of an item for one MMA warp.  Every MMA warp has finished reading the X tile (barrier), so the tile is dead
+// except for the rows the epilogue still needs as the a*src operand - and those are exactly the rows this warp
+// overwrites: row i of the tile receives  o = s*rowOut*(H x)_i + live*a*rowA*src_i  (src_i is read from the same
+// shared-memory location first).  The epilogue warps then finish  dst = o + cb*dst  with the global read-modify-
+// write while the MMA warps are already in the next item's k-loop: the tensor pipe no longer idles while 12 warps
+// wait on their dst rows (22 % of an MMA warp's time in the round-1 kernel, profiles/r01_cell_kernel_stall_regions.csv).
+template <int NODES, bool CPLX, int NTILE, int NTL>
+__device__ __forceinline__ void park_accumulators(double (&acc)[NTILE][NTL][2], double *Xs_buf, const uint32_t *rowsS_buf,
+                                                  double2 *rec_buf, const EpilogueParams &ep, uint64_t *accReady,
+                                                  int warp, int lane) {
+  using C = CellCfg<NODES, CPLX>;
+  using P = PersistCfg<NODES, CPLX>;
+  mma_warps_barrier<P::ACTIVE_MMA_WARPS * 32>();
+#pragma unroll
+  for (int t = 0; t < NTILE; ++t) {
+    const int i = (warp + t * C::WARPS) * 8 + (lane >> 2);
+    if (i < NODES && !DB_WHATIF_NOPARK) {
+      const uint32_t word = rowsS_buf[i];
+      const uint32_t r = word & ROW_MASK;
+      const double so = ep.s * (ep.rowOut ? __ldg(ep.rowOut + r) : 1.0);
+      double ca, cb;
+      epilogue_coeffs(word, ep, ca, cb);
+      // the epilogue warps get the row's b coefficient and its dst row ready-made: a single warp draining 343 rows
+      // per item cannot afford to decode flags and look coefficients up per row (measured: 2x slower)
+      if ((lane & 3) == 0) rec_buf[i] = make_double2(cb, __longlong_as_double((long long)r));
+      double *row = Xs_buf + i * LDS + (lane & 3) * 2;
+#pragma unroll
+      for (int nt = 0; nt < NTL; ++nt) {
+        double2 o = make_double2(so * acc[t][nt][0], so * acc[t][nt][1]);
+        if (ca != 0.0) {
+          const double2 sv = *reinterpret_cast<const double2 *>(row + nt * 8);
+          o.x += ca * sv.x;
+          o.y += ca * sv.y;
+        }
+        *reinterpret_cast<double2 *>(row + nt * 8) = o;
+      }
+    }
+  }
+  // these generic-proxy stores are later overwritten by the producer's TMA copies (async proxy) of another item
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncwarp();
+  if (lane == 0) mbar_arrive(accReady);  // release semantics: the stores above are visible to the waiting warps
+}
+
+// Epilogue warps: dst[row(c,i), tile] = o_i + cb_i * dst[...] for the rows of the finished item, 8 bytes per lane
+// (one 256-byte row segment per warp instruction), EROWS rows in flight per warp.
+template <int NODES, bool CPLX, bool RAGGED>
+__device__ __forceinline__ void epilogue_warp_items(int nItems, double *__restrict__ dst, int ncols, int ldx,
+                                                    int nColTiles, const double *Xs, const double2 *recs,
+                                                    uint64_t *accReady, uint64_t *empty, int ewarp, int lane) {
+  using P = PersistCfg<NODES, CPLX>;
+  constexpr int EROWS = DB_EROWS;
+  const ColTiling ct(ncols, nColTiles);
+  int it = 0;
+  for (int item = blockIdx.x; item < nItems; item += gridDim.x, ++it) {
+    const int buf = it & 1;
+    const uint32_t ph = (it >> 1) & 1;
+    const int tile = item % nColTiles;
+    const int col0 = RAGGED ? ct.col0(tile) : tile * BT;
+    const int width = RAGGED ? min(8 * ct.ntl(tile), ncols - col0) : BT;
+    const double *xs = Xs + buf * P::XBUF + lane;
+    const double2 *rc = recs + buf * NODES;
+    double *dcol = dst + col0 + lane;
+    mbar_wait(&accReady[buf], ph);
+    const bool colOk = lane < width;
+#if !DB_WHATIF_NOEPI
+    // EROWS rows per warp in flight (two registers each): 3 warps x 40 rows x 256 B = 30 KB of loads per SM cover the
+    // HBM round trip of the dst rows; ~10 instructions per row
+    for (int i0 = ewarp * EROWS; i0 < NODES; i0 += P::EPI_WARPS * EROWS) {
+      double d[EROWS];
+#pragma unroll
+      for (int e = 0; e < EROWS; ++e) {
+        const int i = min(i0 + e, NODES - 1);
+        const double2 r = rc[i];
+        d[e] = 0.0;
+        // (integer test of cb != 0: the FP64 pipe belongs to the DMMAs)
+        if (colOk && (__double_as_longlong(r.x) << 1) != 0 && !DB_WHATIF_NOLOAD) d[e] = dcol[(size_t)__double_as_longlong(r.y) * ldx];
+      }
+#pragma unroll
+      for (int e = 0; e < EROWS; ++e) {
+        const int i = i0 + e;
+        if (i < NODES && colOk) {
+          const double2 r = rc[i];
+#if DB_WHATIF_NOFP64
+          const double v = __longlong_as_double(__double_as_longlong(xs[i * LDS]) ^ __double_as_longlong(d[e]));
+#else
+          const double v = xs[i * LDS] + r.x * d[e];
+#endif
+          if (!DB_WHATIF_NOSTORE || __double_as_longlong(v) == 12345) dcol[(size_t)__double_as_longlong(r.y) * ldx] = v;
+        }
+      }
+    }
+#endif
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[buf]);  // the X tile may be refilled
+  }
+}
 
 // Item loop of an MMA warp for blocks whose column count is a multiple of 32 (every tile full): kept as ONE
 // function - splitting it into per-item pieces as the ragged variant below does costs registers (64 B of spills,
@@ -360,8 +509,8 @@ template <int NODES, bool CPLX, int NTILE>
 __device__ __forceinline__ void mma_warp_items_full(const double *__restrict__ Ht, const int32_t *__restrict__ cells,
                                                int nItems, const double *__restrict__ src,
                                                double *__restrict__ dst, int ldx, int nColTiles,
-                                               const EpilogueParams &ep, const double *Xs, const uint32_t *rowsS,
-                                               uint64_t *full, uint64_t *empty, int warp, int lane) {
+                                               const EpilogueParams &ep, double *Xs, const uint32_t *rowsS,
+                                               double2 *recs, uint64_t *full, uint64_t *accReady, int warp, int lane) {
   using C = CellCfg<NODES, CPLX>;
   using P = PersistCfg<NODES, CPLX>;
   static_assert(P::APF % 2 == 0, "the parity of a virtual k-step must be that of its ring slot");
@@ -426,58 +575,11 @@ __device__ __forceinline__ void mma_warp_items_full(const double *__restrict__ H
         for (int nt = 0; nt < NT; ++nt) dmma884(acc[t][nt][0], acc[t][nt][1], a[s][t], b[nt]);
     }
 
-    // rows of this warp's tiles, then release the buffer to the producer
-    uint32_t fr[NTILE];
-#pragma unroll
-    for (int t = 0; t < NTILE; ++t) {
-      const int i = (warp + t * C::WARPS) * 8 + (lane >> 2);
-      fr[t] = (i < NODES) ? rowsS[buf * NODES + i] : 0u;
-    }
-    // next item's first A fragments fly while this item's epilogue runs
+    // next item's first A fragments fly while the accumulators are parked
     if (item + (int)gridDim.x < nItems) prime(item + gridDim.x);
-
-    // ---- epilogue (full tiles, even ldx: guaranteed by the launcher)
-#if DB_WHATIF_NOEPI
-    {
-      double sacc = 0.0;
-#pragma unroll
-      for (int t = 0; t < NTILE; ++t)
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) sacc += acc[t][nt][0] + acc[t][nt][1];
-      if (sacc == 1234.5678) dst[0] = sacc;
-    }
-#else
-#pragma unroll
-    for (int t = 0; t < NTILE; ++t) {
-      const int i = (warp + t * C::WARPS) * 8 + (lane >> 2);
-      if (i < NODES) {
-        const uint32_t r = fr[t] & ROW_MASK;
-        const double so = ep.s * (ep.rowOut ? __ldg(ep.rowOut + r) : 1.0);
-        double ca, cb;
-        epilogue_coeffs(fr[t], ep, ca, cb);
-        double *drow = dst + (size_t)r * ldx + col0 + (lane & 3) * 2;
-        // src[row(c,i), tile] is row i of the X tile still sitting in shared memory (the buffer is released
-        // after the epilogue): the a*src term of a first touch costs no global read
-        const double *srow = Xs + buf * P::XBUF + i * LDS + (lane & 3) * 2;
-        double2 d[NT], sv[NT];
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-          d[nt] = (cb != 0.0) ? *reinterpret_cast<const double2 *>(drow + nt * 8) : make_double2(0.0, 0.0);
-          sv[nt] = (ca != 0.0) ? *reinterpret_cast<const double2 *>(srow + nt * 8) : make_double2(0.0, 0.0);
-        }
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt) {
-          double2 o;
-          o.x = so * acc[t][nt][0] + ca * sv[nt].x + cb * d[nt].x;
-          o.y = so * acc[t][nt][1] + ca * sv[nt].y + cb * d[nt].y;
-          *reinterpret_cast<double2 *>(drow + nt * 8) = o;
-        }
-      }
-    }
-#endif
-    // release the X tile to the producer (its rows were the epilogue's src operand)
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[buf]);
+    // park the accumulators in the (now dead) X tile and hand the item to the epilogue warps
+    park_accumulators<NODES, CPLX, NTILE, NT>(acc, Xs + buf * P::XBUF, rowsS + buf * NODES, recs + buf * NODES, ep,
+                                              &accReady[buf], warp, lane);
   }
 }
 
@@ -490,8 +592,8 @@ __device__ __forceinline__ void mma_one_item(const double *__restrict__ Ht, cons
                                              int nItems, int item, int it, int col0,
                                              const double *__restrict__ src,
                                              double *__restrict__ dst, int ncols, int ldx, int nColTiles,
-                                             const EpilogueParams &ep, const double *Xs, const uint32_t *rowsS,
-                                             uint64_t *full, uint64_t *empty, int warp, int lane,
+                                             const EpilogueParams &ep, double *Xs, const uint32_t *rowsS,
+                                             double2 *recs, uint64_t *full, uint64_t *accReady, int warp, int lane,
                                              double (&a)[PersistCfg<NODES, CPLX>::APF][CellCfg<NODES, CPLX>::TPWP]) {
   using C = CellCfg<NODES, CPLX>;
   using P = PersistCfg<NODES, CPLX>;
@@ -540,74 +642,24 @@ __device__ __forceinline__ void mma_one_item(const double *__restrict__ Ht, cons
       for (int nt = 0; nt < NTL; ++nt) dmma884(acc[t][nt][0], acc[t][nt][1], a[s][t], b[nt]);
   }
 
-  // rows of this warp's tiles, then release the buffer to the producer
-  uint32_t fr[NTILE];
-#pragma unroll
-  for (int t = 0; t < NTILE; ++t) {
-    const int i = (warp + t * C::WARPS) * 8 + (lane >> 2);
-    fr[t] = (i < NODES) ? rowsS[buf * NODES + i] : 0u;
-  }
-  // next item's first A fragments fly while this item's epilogue runs
+  // next item's first A fragments fly while the accumulators are parked
   if (item + (int)gridDim.x < nItems) {
     const int ncell = cells[(item + gridDim.x) / nColTiles];
     const double *Hn = Ht + (size_t)ncell * C::HT_PER_CELL + (size_t)warp * C::HT_PER_WARP + lane * C::TPWP;
 #pragma unroll
     for (int s = 0; s < P::APF; ++s) load_frags<C::TPWP>(Hn + (size_t)min(s, C::KSV - 1) * 32 * C::TPWP, a[s]);
   }
-
-  // ---- epilogue (even ncols / ldx: guaranteed by the launcher; a ragged tile masks its missing column pairs)
-#pragma unroll
-  for (int t = 0; t < NTILE; ++t) {
-    const int i = (warp + t * C::WARPS) * 8 + (lane >> 2);
-    if (i < NODES) {
-      const uint32_t r = fr[t] & ROW_MASK;
-      const double so = ep.s * (ep.rowOut ? __ldg(ep.rowOut + r) : 1.0);
-      double ca, cb;
-      epilogue_coeffs(fr[t], ep, ca, cb);
-      const int cl = col0 + (lane & 3) * 2;
-      double *drow = dst + (size_t)r * ldx + cl;
-      const double *srow = Xs + buf * P::XBUF + i * LDS + (lane & 3) * 2;  // src rows = the X tile (see above)
-      double2 d[NTL], sv[NTL];
-#pragma unroll
-      for (int nt = 0; nt < NTL; ++nt) {
-        const bool ok = !RAGGED || (cl + nt * 8 < ncols);
-        d[nt] = (cb != 0.0 && ok) ? *reinterpret_cast<const double2 *>(drow + nt * 8) : make_double2(0.0, 0.0);
-        sv[nt] = (ca != 0.0 && ok) ? *reinterpret_cast<const double2 *>(srow + nt * 8) : make_double2(0.0, 0.0);
-      }
-#pragma unroll
-      for (int nt = 0; nt < NTL; ++nt) {
-        double2 o;
-        o.x = so * acc[t][nt][0] + ca * sv[nt].x + cb * d[nt].x;
-        o.y = so * acc[t][nt][1] + ca * sv[nt].y + cb * d[nt].y;
-        if (!RAGGED || (cl + nt * 8 < ncols)) *reinterpret_cast<double2 *>(drow + nt * 8) = o;
-      }
-    }
-  }
-  // release the X tile to the producer (its rows were the epilogue's src operand)
-  __syncwarp();
-  if (lane == 0) mbar_arrive(&empty[buf]);
+  // park the accumulators (the columns that exist) and hand the item to the epilogue warps
+  park_accumulators<NODES, CPLX, NTILE, NTL>(acc, Xs + buf * P::XBUF, rowsS + buf * NODES, recs + buf * NODES, ep,
+                                             &accReady[buf], warp, lane);
 }
-
-// Column tiling of a block of `ncols` columns: nColTiles = ceil(ncols / 32) tiles; the ceil(ncols / 8) n8 tiles
-// are dealt as evenly as possible (e.g. 100 columns -> 4,3,3,3), because every item streams the whole H_c and a
-// narrow tile would make that stream the bottleneck.
-struct ColTiling {
-  int base, rem;  // tiles [0, rem) hold base+1 n8 tiles, the others base
-  __host__ __device__ ColTiling(int ncols, int nColTiles) {
-    const int total8 = (ncols + 7) >> 3;
-    base = total8 / nColTiles;
-    rem = total8 % nColTiles;
-  }
-  __host__ __device__ int ntl(int tile) const { return base + (tile < rem ? 1 : 0); }
-  __host__ __device__ int col0(int tile) const { return 8 * (tile * base + (tile < rem ? tile : rem)); }
-};
 
 template <int NODES, bool CPLX, int NTILE, bool RAGGED>
 __device__ __forceinline__ void mma_warp_items(const double *__restrict__ Ht, const int32_t *__restrict__ cells,
                                                int nItems, const double *__restrict__ src,
                                                double *__restrict__ dst, int ncols, int ldx, int nColTiles,
-                                               const EpilogueParams &ep, const double *Xs, const uint32_t *rowsS,
-                                               uint64_t *full, uint64_t *empty, int warp, int lane) {
+                                               const EpilogueParams &ep, double *Xs, const uint32_t *rowsS,
+                                               double2 *recs, uint64_t *full, uint64_t *accReady, int warp, int lane) {
   using C = CellCfg<NODES, CPLX>;
   using P = PersistCfg<NODES, CPLX>;
   static_assert(P::APF % 2 == 0, "the parity of a virtual k-step must be that of its ring slot");
@@ -624,7 +676,7 @@ __device__ __forceinline__ void mma_warp_items(const double *__restrict__ Ht, co
   for (int item = blockIdx.x; item < nItems; item += gridDim.x, ++it) {
 #define DB_ITEM(NTL, COL0)                                                                                          \
   mma_one_item<NODES, CPLX, NTILE, NTL, RAGGED>(Ht, cells, nItems, item, it, COL0, src, dst, ncols, ldx, nColTiles, ep, Xs, \
-                                        rowsS, full, empty, warp, lane, a)
+                                        rowsS, recs, full, accReady, warp, lane, a)
     if (!RAGGED) {
       DB_ITEM(4, (item % nColTiles) * BT);
     } else {
@@ -655,14 +707,16 @@ cell_matvec_persistent_kernel(const double *__restrict__ Ht, const uint32_t *__r
   extern __shared__ __align__(128) unsigned char smem_raw[];
   double *Xs = reinterpret_cast<double *>(smem_raw);                                  // [2][KPAD][LDS]
   uint32_t *rowsS = reinterpret_cast<uint32_t *>(smem_raw + 2 * P::XBUF * sizeof(double));  // [2][NODES]
-  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + 2 * P::XBUF * sizeof(double) +
-                                                ((2 * NODES * sizeof(uint32_t) + 7) / 8) * 8);
-  uint64_t *full = bars, *empty = bars + 2;
+  double2 *recs = reinterpret_cast<double2 *>(smem_raw + 2 * P::XBUF * sizeof(double) + P::ROWS_BYTES);  // [2][NODES]
+  uint64_t *bars = reinterpret_cast<uint64_t *>(smem_raw + 2 * P::XBUF * sizeof(double) + P::ROWS_BYTES +
+                                                2 * NODES * 16);
+  uint64_t *full = bars, *empty = bars + 2, *accReady = bars + 4;
 
   const int tid = threadIdx.x;
   const int lane = tid & 31;
   // physical warp 0 is the producer; MMA warp ids 0..11 sit on physical warps 1..12, which puts the
-  // three lightest MMA warps (ids 3, 7, 11: 4+3+3 row tiles) on the producer's scheduler (SMSP 0)
+  // three lightest MMA warps (ids 3, 7, 11: 4+3+3 row tiles) on the producer's scheduler (SMSP 0); the
+  // three epilogue warps (physical 13..15) land on SMSPs 1, 2, 3: every scheduler holds three MMA warps and one helper
   const int pwarp = tid >> 5;
   const int warp = pwarp - 1;
 
@@ -671,9 +725,11 @@ cell_matvec_persistent_kernel(const double *__restrict__ Ht, const uint32_t *__r
   if (tid == 0) {
     mbar_init(&full[0], 1);
     mbar_init(&full[1], 1);
-    // only warps that own row tiles run the item loop and release the buffers (FE order 1: one of four)
-    mbar_init(&empty[0], C::MT < P::MMA_WARPS ? C::MT : P::MMA_WARPS);
-    mbar_init(&empty[1], C::MT < P::MMA_WARPS ? C::MT : P::MMA_WARPS);
+    // the epilogue warps release a buffer; the MMA warps that own row tiles (FE order 1: one of four) hand it over
+    mbar_init(&empty[0], P::EPI_WARPS);
+    mbar_init(&empty[1], P::EPI_WARPS);
+    mbar_init(&accReady[0], P::ACTIVE_MMA_WARPS);
+    mbar_init(&accReady[1], P::ACTIVE_MMA_WARPS);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   // generic-proxy zero fill must be ordered before the async-proxy (TMA) writes
@@ -711,31 +767,48 @@ cell_matvec_persistent_kernel(const double *__restrict__ Ht, const uint32_t *__r
       // a ragged last tile copies only the columns that exist (even count -> multiple of 16 bytes); the
       // shared-memory columns beyond them keep finite values of earlier tiles and are masked in the epilogue
       const uint32_t rowBytes = (uint32_t)(width * sizeof(double));
-      if (lane == 0) mbar_arrive_expect_tx(&full[buf], (uint32_t)NODES * rowBytes);
+      if (lane == 0) mbar_arrive_expect_tx(&full[buf], (uint32_t)(DB_WHATIF_HALFGATHER ? (NODES + 1) / 2 : NODES) * rowBytes);
       __syncwarp();
 #pragma unroll
       for (int j = 0; j < (NODES + 31) / 32; ++j) {
         const int k = lane + 32 * j;
-        if (k < NODES)
+        if (k < NODES && (!DB_WHATIF_HALFGATHER || k < (NODES + 1) / 2))
           tma_bulk_g2s(xs + k * LDS, src + (size_t)(myRows[j] & ROW_MASK) * ldx + col0, rowBytes, &full[buf]);
       }
+#if DB_DST_PREFETCH
+      // the epilogue warps will read-modify-write these dst rows one and a half items from now, a few rows at a
+      // time: pull them into L2 now (bulk L2 prefetch, one instruction per 256-byte row segment) so that their
+      // round trip is an L2 hit instead of a scattered HBM access under load
+#pragma unroll
+      for (int j = 0; j < (NODES + 31) / 32; ++j) {
+        const int k = lane + 32 * j;
+        if (k < NODES)
+          asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(dst + (size_t)(myRows[j] & ROW_MASK) * ldx + col0),
+                       "r"(rowBytes)
+                       : "memory");
+      }
+#endif
     }
+  } else if (pwarp > P::MMA_WARPS) {
+    // ===== epilogue warps: finish the read-modify-write of the parked accumulators =====
+    epilogue_warp_items<NODES, CPLX, RAGGED>(nItems, dst, ncols, ldx, nColTiles, Xs, recs, accReady, empty,
+                                             pwarp - P::MMA_WARPS - 1, lane);
   } else {
     constexpr int FULL_WARPS = C::MT - (C::TPW - 1) * C::WARPS;  // warps that own TPW tiles
     if (!RAGGED) {
       if (warp < FULL_WARPS)
-        mma_warp_items_full<NODES, CPLX, C::TPW>(Ht, cells, nItems, src, dst, ldx, nColTiles, ep, Xs, rowsS, full,
-                                                 empty, warp, lane);
+        mma_warp_items_full<NODES, CPLX, C::TPW>(Ht, cells, nItems, src, dst, ldx, nColTiles, ep, Xs, rowsS, recs, full,
+                                                 accReady, warp, lane);
       else if (C::TPW > 1)
         mma_warp_items_full<NODES, CPLX, (C::TPW > 1 ? C::TPW - 1 : 1)>(Ht, cells, nItems, src, dst, ldx, nColTiles,
-                                                                        ep, Xs, rowsS, full, empty, warp, lane);
+                                                                        ep, Xs, rowsS, recs, full, accReady, warp, lane);
     } else {
       if (warp < FULL_WARPS)
         mma_warp_items<NODES, CPLX, C::TPW, true>(Ht, cells, nItems, src, dst, ncols, ldx, nColTiles, ep, Xs, rowsS,
-                                                  full, empty, warp, lane);
+                                                  recs, full, accReady, warp, lane);
       else if (C::TPW > 1)
         mma_warp_items<NODES, CPLX, (C::TPW > 1 ? C::TPW - 1 : 1), true>(Ht, cells, nItems, src, dst, ncols, ldx,
-                                                                         nColTiles, ep, Xs, rowsS, full, empty, warp,
+                                                                         nColTiles, ep, Xs, rowsS, recs, full, accReady, warp,
                                                                          lane);
     }
   }

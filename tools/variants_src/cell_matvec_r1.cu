@@ -36,7 +36,7 @@
 // stored, odd ones take Ai and the partner column with the sign of the real part flipped
 // (one integer XOR per fragment).  No split re/im temporaries (the reference needs them
 // around its atomics, matrixVectorProductImplementationsDevice.cc:86-108).
-#include "common.cuh"
+#include "../../dftfe_b200/csrc/common.cuh"
 
 namespace dftfe_b200 {
 
