@@ -46,6 +46,8 @@ def main():
     ap.add_argument("--rows", type=int, default=36000)
     ap.add_argument("--block", type=int, default=256)
     ap.add_argument("--reps", type=int, default=20)
+    ap.add_argument("--shape", default="", help="global cells nx,ny,nz (default cells^3); split over two ranks along x")
+    ap.add_argument("--p2p", type=int, default=0, help="1: peer-memory transport (push kernel + flags) for the exchange")
     args = ap.parse_args()
     import torch
 
@@ -61,7 +63,8 @@ def main():
     peak_src = "MEASURED_PEAKS.json hbm_gbs (copy, burst)" if "hbm_gbs" in peaks else "fallback 6546.6 GB/s"
 
     nranks, B = 2, args.block
-    mesh = build_mesh(6, (args.cells,) * 3, 1.0, periodic=(True, True, True), nranks=nranks, rank_grid=(2, 1, 1),
+    shape = tuple(int(v) for v in args.shape.split(",")) if args.shape else (args.cells,) * 3
+    mesh = build_mesh(6, shape, 1.0, periodic=(True, True, True), nranks=nranks, rank_grid=(2, 1, 1),
                       extra_constraints=many_constraints(args.rows))
     ranks = [mesh.rank_problem(r, potential=None, build_H=False, with_xyz=False) for r in range(nranks)]
     results = [None] * nranks
@@ -70,7 +73,8 @@ def main():
     def rank_fn(r):
         rp = ranks[r]
         op = capi.Operator(rp, B, use_torch_stream=False)
-        op.comm_init_loopback(77, r, nranks)
+        op.comm_init_loopback(77 + args.p2p, r, nranks)
+        op.set_option("p2p_exchange", args.p2p)
         g = torch.Generator(device="cuda")
         g.manual_seed(r)
         x = torch.rand((rp.M + rp.G, B), dtype=torch.float64, device="cuda", generator=g)
