@@ -267,6 +267,9 @@ struct dftfe_b200_ctx {
   struct NonlocalSet {
     int nAtoms = 0, totalProj = 0;
     int64_t nRows = 0;
+    int nAtomColours = 0, maxProj = 0;            // atoms that share a row have different colours
+    std::vector<int32_t> colourStart_h;
+    dftfe_b200::DevBuf<int32_t> colourAtoms;      // atom ids grouped by colour
     dftfe_b200::DevBuf<int32_t> projOffset, atomRowStart, entProj;
     dftfe_b200::DevBuf<int64_t> atomValStart, rowStart;
     dftfe_b200::DevBuf<uint32_t> atomRows, rowList;

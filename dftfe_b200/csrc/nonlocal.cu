@@ -15,7 +15,10 @@
 //   2. all-reduce of proj over the ranks (atoms whose support spans several ranks)
 //   3. nl_apply_kernel   : y[row, :] += s * out(row) * sum_e Chat[row,e] V[e] proj[e, :]           (row-parallel)
 // Both are coalesced along the wavefunction index, atomics-free and deterministic; the projector block
-// (totalProj x B doubles) stays L2 resident between 1 and 3.
+// (totalProj x B doubles) stays L2 resident between 1 and 3.  For even column counts both steps run in
+// bandwidth-shaped ATOM-parallel kernels (16-byte accesses, four rows in flight per lane): the apply keeps the
+// atom's V-weighted projector rows in registers and streams its y rows once - atoms that share a row carry different
+// colours (greedy colouring at set_nonlocal) and each colour is its own launch, in a fixed order.
 //
 // Complex (k-point) build: C carries the Bloch phase, one set per k-point; vectors are interleaved (re, im) and
 //   proj = Chat^H x  (zgemm with d_nonLocalProjectorElementMatricesConjugate, ...MemoryOpt.cc:98-112),
@@ -115,6 +118,146 @@ __global__ void nl_apply_kernel(double *__restrict__ y, int ncols, int ldx, int6
   }
 }
 
+
+// ---- bandwidth-shaped variants (even column counts, 16-byte aligned rows) ---------------------------------------
+// One CTA per (atom, 64-column chunk), four warps; a lane owns two adjacent real columns (one complex column in the
+// k-point build) and walks every fourth row of the atom, four rows in flight (16-byte loads): the x rows of an atom
+// are streamed once at HBM speed, the projector values of a row are broadcast loads.
+constexpr int NLV_WARPS = 4;
+constexpr int NLV_UNROLL = 4;
+
+template <int CM, int PMAX>
+__global__ void __launch_bounds__(NLV_WARPS * 32)
+nl_project_vec_kernel(const double *__restrict__ x, int ncols, int ldx, const int32_t *__restrict__ atomRowStart,
+                      const uint32_t *__restrict__ atomRows, const int64_t *__restrict__ atomValStart,
+                      const double *__restrict__ vals, const int32_t *__restrict__ projOffset,
+                      const double *__restrict__ rowScale, double *__restrict__ proj) {
+  __shared__ double2 red[NLV_WARPS][PMAX][32];
+  const int a = blockIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col = blockIdx.y * 64 + lane * 2;
+  const int P = projOffset[a + 1] - projOffset[a];
+  const int r0 = atomRowStart[a], r1 = atomRowStart[a + 1];
+  const double *va = vals + atomValStart[a] * CM;
+  double2 acc[PMAX];
+#pragma unroll
+  for (int p = 0; p < PMAX; ++p) acc[p] = make_double2(0.0, 0.0);
+  if (col < ncols) {
+    for (int rb = r0 + warp * NLV_UNROLL; rb < r1; rb += NLV_WARPS * NLV_UNROLL) {
+      double2 xv[NLV_UNROLL];
+      double sc[NLV_UNROLL];
+#pragma unroll
+      for (int u = 0; u < NLV_UNROLL; ++u) {
+        const int r = rb + u;
+        xv[u] = make_double2(0.0, 0.0);
+        sc[u] = 1.0;
+        if (r < r1) {
+          const uint32_t row = atomRows[r];
+          xv[u] = *reinterpret_cast<const double2 *>(x + (size_t)row * ldx + col);
+          if (rowScale) sc[u] = rowScale[row];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < NLV_UNROLL; ++u) {
+        const int r = rb + u;
+        if (r < r1) {
+          const double xr = xv[u].x * sc[u], xi = xv[u].y * sc[u];
+          const double *v = va + (size_t)(r - r0) * P * CM;
+#pragma unroll
+          for (int p = 0; p < PMAX; ++p)
+            if (p < P) {
+              if (CM == 2) {  // conj(c) x: re = cr xr + ci xi, im = cr xi - ci xr
+                const double cr = v[2 * p], ci = v[2 * p + 1];
+                acc[p].x += cr * xr + ci * xi;
+                acc[p].y += cr * xi - ci * xr;
+              } else {
+                acc[p].x += v[p] * xr;
+                acc[p].y += v[p] * xi;
+              }
+            }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int p = 0; p < PMAX; ++p)
+    if (p < P) red[warp][p][lane] = acc[p];
+  __syncthreads();
+  if (col < ncols)
+    for (int p = warp; p < P; p += NLV_WARPS) {
+      double2 s = red[0][p][lane];
+#pragma unroll
+      for (int g = 1; g < NLV_WARPS; ++g) {
+        s.x += red[g][p][lane].x;
+        s.y += red[g][p][lane].y;
+      }
+      *reinterpret_cast<double2 *>(proj + (size_t)(projOffset[a] + p) * ncols + col) = s;
+    }
+}
+
+// y[row, :] += s * out(row) * sum_p C_a[row][p] V[a,p] proj[(a,p), :] for the atoms of ONE colour (atoms of a colour
+// share no row, so the read-modify-write needs no atomics; the colours run in a fixed order -> deterministic).
+// The V-weighted projector rows of the atom sit in registers; y rows stream through once (16-byte accesses).
+template <int CM, int PMAX>
+__global__ void __launch_bounds__(NLV_WARPS * 32)
+nl_apply_vec_kernel(double *__restrict__ y, int ncols, int ldx, const int32_t *__restrict__ colourAtoms,
+                    const int32_t *__restrict__ atomRowStart, const uint32_t *__restrict__ atomRows,
+                    const int64_t *__restrict__ atomValStart, const double *__restrict__ vals,
+                    const int32_t *__restrict__ projOffset, const double *__restrict__ V,
+                    const double *__restrict__ proj, const double *__restrict__ rowScale, double s) {
+  const int a = colourAtoms[blockIdx.x];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col = blockIdx.y * 64 + lane * 2;
+  if (col >= ncols) return;
+  const int P = projOffset[a + 1] - projOffset[a];
+  const int r0 = atomRowStart[a], r1 = atomRowStart[a + 1];
+  const double *va = vals + atomValStart[a] * CM;
+  double2 q[PMAX];  // V * proj of this atom, this lane's column pair
+#pragma unroll
+  for (int p = 0; p < PMAX; ++p) {
+    q[p] = make_double2(0.0, 0.0);
+    if (p < P) {
+      const double2 t = *reinterpret_cast<const double2 *>(proj + (size_t)(projOffset[a] + p) * ncols + col);
+      const double v = V[projOffset[a] + p];
+      q[p] = make_double2(v * t.x, v * t.y);
+    }
+  }
+  for (int rb = r0 + warp * NLV_UNROLL; rb < r1; rb += NLV_WARPS * NLV_UNROLL) {
+    double2 yv[NLV_UNROLL];
+    uint32_t rows[NLV_UNROLL];
+#pragma unroll
+    for (int u = 0; u < NLV_UNROLL; ++u) {
+      const int r = rb + u;
+      rows[u] = r < r1 ? atomRows[r] : 0u;
+      if (r < r1) yv[u] = *reinterpret_cast<const double2 *>(y + (size_t)rows[u] * ldx + col);
+    }
+#pragma unroll
+    for (int u = 0; u < NLV_UNROLL; ++u) {
+      const int r = rb + u;
+      if (r < r1) {
+        const double *v = va + (size_t)(r - r0) * P * CM;
+        double sr = 0.0, si = 0.0;
+#pragma unroll
+        for (int p = 0; p < PMAX; ++p)
+          if (p < P) {
+            if (CM == 2) {  // c q: re = cr qr - ci qi, im = cr qi + ci qr
+              const double cr = v[2 * p], ci = v[2 * p + 1];
+              sr += cr * q[p].x - ci * q[p].y;
+              si += cr * q[p].y + ci * q[p].x;
+            } else {
+              sr += v[p] * q[p].x;
+              si += v[p] * q[p].y;
+            }
+          }
+        const double f = rowScale ? s * rowScale[rows[u]] : s;
+        yv[u].x += f * sr;
+        yv[u].y += f * si;
+        *reinterpret_cast<double2 *>(y + (size_t)rows[u] * ldx + col) = yv[u];
+      }
+    }
+  }
+}
+
 }  // namespace
 
 // C: [nEntries][n][pMax] doubles (real build) or (re, im) pairs (complex build)
@@ -178,7 +321,43 @@ int nonlocal_setup(dftfe_b200_ctx *ctx, int kpt, int32_t nAtoms, const int32_t *
     }
     rowStart.push_back((int64_t)entProj.size());
   }
+  // atoms that share a row get different colours (greedy, atom order): the atom-parallel apply kernel runs one
+  // launch per colour and needs no atomics
+  std::vector<int32_t> atomColour(nAtoms, -1), colourStart, colourAtoms;
+  int nAtomColours = 0;
+  {
+    std::map<uint32_t, std::vector<int32_t>> atomsOfRow;
+    for (int a = 0; a < nAtoms; ++a)
+      for (int r = atomRowStart[a]; r < atomRowStart[a + 1]; ++r) atomsOfRow[atomRows[r]].push_back(a);
+    std::vector<std::vector<int32_t>> nb(nAtoms);
+    for (auto &kv : atomsOfRow)
+      for (int32_t a : kv.second)
+        for (int32_t b : kv.second)
+          if (a != b) nb[a].push_back(b);
+    for (int a = 0; a < nAtoms; ++a) {
+      std::vector<char> used(nAtomColours + 1, 0);
+      for (int32_t b : nb[a])
+        if (atomColour[b] >= 0) used[atomColour[b]] = 1;
+      int c = 0;
+      while (c < nAtomColours && used[c]) ++c;
+      atomColour[a] = c;
+      nAtomColours = std::max(nAtomColours, c + 1);
+    }
+    colourStart.assign(nAtomColours + 1, 0);
+    for (int a = 0; a < nAtoms; ++a)
+      if (atomRowStart[a + 1] > atomRowStart[a]) colourStart[atomColour[a] + 1]++;
+    for (int c = 0; c < nAtomColours; ++c) colourStart[c + 1] += colourStart[c];
+    colourAtoms.assign(colourStart[nAtomColours], 0);
+    std::vector<int32_t> fill(colourStart.begin(), colourStart.end() - 1);
+    for (int a = 0; a < nAtoms; ++a)
+      if (atomRowStart[a + 1] > atomRowStart[a]) colourAtoms[fill[atomColour[a]]++] = a;
+  }
   dftfe_b200_ctx::NonlocalSet &ns = ctx->nlSets[kpt];
+  ns.nAtomColours = nAtomColours;
+  ns.maxProj = 0;
+  for (int a = 0; a < nAtoms; ++a) ns.maxProj = std::max(ns.maxProj, (int)nProj[a]);
+  ns.colourStart_h = colourStart;
+  DB_TRY(ns.colourAtoms.upload(colourAtoms.data(), colourAtoms.size(), ctx->stream));
   ns.nAtoms = nAtoms;
   ns.totalProj = totalProj;
   ns.nRows = (int64_t)rows.size();
@@ -201,7 +380,23 @@ int nonlocal_setup(dftfe_b200_ctx *ctx, int kpt, int32_t nAtoms, const int32_t *
 int nonlocal_project(dftfe_b200_ctx *ctx, const double *x, int ncols, int ldx, const double *rowScaleIn) {
   if (!ctx->nl) return 0;
   const dftfe_b200_ctx::NonlocalSet &ns = *ctx->nl;
-  {
+  const bool vec = (ncols % 2 == 0) && (ldx % 2 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
+                   !ctx->force_scalar_row_kernels && ns.maxProj <= 16;
+  if (vec) {
+    ProfScope ps(ctx, "nonlocal");
+    dim3 grid(ns.nAtoms, (ncols + 63) / 64);
+#define DB_NLP(CM, PM)                                                                                               \
+  nl_project_vec_kernel<CM, PM><<<grid, NLV_WARPS * 32, 0, ctx->stream>>>(x, ncols, ldx, ns.atomRowStart.p, ns.atomRows.p, \
+                                                                         ns.atomValStart.p, ns.vals.p, ns.projOffset.p,  \
+                                                                         rowScaleIn, ctx->nlProj[ctx->lane].p)
+    if (ctx->cplx) {
+      if (ns.maxProj <= 8) DB_NLP(2, 8); else DB_NLP(2, 16);
+    } else {
+      if (ns.maxProj <= 8) DB_NLP(1, 8); else DB_NLP(1, 16);
+    }
+#undef DB_NLP
+    DB_CUDA(cudaGetLastError());
+  } else {
     ProfScope ps(ctx, "nonlocal");
     dim3 grid(ns.nAtoms, (ncols + NL_COLS - 1) / NL_COLS), block(NL_COLS, NL_RG);
     if (ctx->cplx)
@@ -221,6 +416,29 @@ int nonlocal_project(dftfe_b200_ctx *ctx, const double *x, int ncols, int ldx, c
 int nonlocal_apply(dftfe_b200_ctx *ctx, double *y, int ncols, int ldx, const double *rowScaleOut, double s) {
   if (!ctx->nl || ctx->nl->nRows == 0) return 0;
   const dftfe_b200_ctx::NonlocalSet &ns = *ctx->nl;
+  const bool vec = (ncols % 2 == 0) && (ldx % 2 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0) &&
+                   !ctx->force_scalar_row_kernels && ns.maxProj <= 16;
+  if (vec) {
+    // atom-parallel, one launch per atom colour (fixed order)
+    for (int c = 0; c < ns.nAtomColours; ++c) {
+      const int nA = ns.colourStart_h[c + 1] - ns.colourStart_h[c];
+      if (nA == 0) continue;
+      ProfScope ps(ctx, "nonlocal");
+      dim3 grid(nA, (ncols + 63) / 64);
+#define DB_NLA(CM, PM)                                                                                              \
+  nl_apply_vec_kernel<CM, PM><<<grid, NLV_WARPS * 32, 0, ctx->stream>>>(                                              \
+      y, ncols, ldx, ns.colourAtoms.p + ns.colourStart_h[c], ns.atomRowStart.p, ns.atomRows.p, ns.atomValStart.p,  \
+      ns.vals.p, ns.projOffset.p, ns.V.p, ctx->nlProj[ctx->lane].p, rowScaleOut, s)
+      if (ctx->cplx) {
+        if (ns.maxProj <= 8) DB_NLA(2, 8); else DB_NLA(2, 16);
+      } else {
+        if (ns.maxProj <= 8) DB_NLA(1, 8); else DB_NLA(1, 16);
+      }
+#undef DB_NLA
+    }
+    DB_CUDA(cudaGetLastError());
+    return 0;
+  }
   ProfScope ps(ctx, "nonlocal");
   const int64_t total = ns.nRows * ncols;
   const int grid = (int)std::min<int64_t>((total + 255) / 256, (int64_t)ctx->num_sms * 16);

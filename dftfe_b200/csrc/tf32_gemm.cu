@@ -152,7 +152,11 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_cons
     if (lane == 0) {
       uint32_t n = 0;
       for (int item = blockIdx.x; item < nItems; item += gridDim.x) {
-        const int tile = item / P.nSeg, seg = item % P.nSeg;
+        // segment-major item order: the CTAs of a wave work on the same few k-segments of ALL tiles, so every
+        // operand panel is fetched from HBM once and shared through L2 (tile-major order re-read them: ncu showed
+        // 2x the algorithmic DRAM bytes)
+        const int nTiles = P.tilesM * P.tilesN;
+        const int tile = item % nTiles, seg = item / nTiles;
         const int tm = tile / P.tilesN, tn = tile % P.tilesN;
         const int kb0 = seg * P.kBlocksPerSeg, kb1 = min(P.kBlocks, kb0 + P.kBlocksPerSeg);
         for (int kb = kb0; kb < kb1; ++kb, ++n) {
@@ -172,7 +176,7 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_cons
     if (lane == 0) {
       uint32_t n = 0, it = 0;
       for (int item = blockIdx.x; item < nItems; item += gridDim.x, ++it) {
-        const int seg = item % P.nSeg;
+        const int seg = item / (P.tilesM * P.tilesN);
         const int kb0 = seg * P.kBlocksPerSeg, kb1 = min(P.kBlocks, kb0 + P.kBlocksPerSeg);
         const int as = it % ACC_STAGES;
         mbar_wait(&accEmpty[as], ((it / ACC_STAGES) & 1) ^ 1);  // epilogue has drained this accumulator stage
@@ -204,7 +208,8 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_cons
     const int q = warp & 3;
     uint32_t it = 0;
     for (int item = blockIdx.x; item < nItems; item += gridDim.x, ++it) {
-      const int tile = item / P.nSeg;
+      const int nTiles = P.tilesM * P.tilesN;
+      const int tile = item % nTiles, seg = item / nTiles;
       const int tm = tile / P.tilesN, tn = tile % P.tilesN;
       const int as = it % ACC_STAGES;
       mbar_wait(&accFull[as], (it / ACC_STAGES) & 1);
@@ -242,7 +247,7 @@ tf32x3_gemm_kernel(const __grid_constant__ CUtensorMap mapAhi, const __grid_cons
             }
           }
         } else {
-          float *o = P.ws + ((size_t)item * TILE + r) * TILE + c0;
+          float *o = P.ws + (((size_t)tile * P.nSeg + seg) * TILE + r) * TILE + c0;
 #pragma unroll
           for (int j = 0; j < 32; j += 4)
             *reinterpret_cast<float4 *>(o + j) = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]),
