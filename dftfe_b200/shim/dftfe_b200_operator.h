@@ -70,6 +70,42 @@ class operatorDFTDeviceClass {
   void setStream(cudaStream_t s) { check(dftfe_b200_set_stream(d_ctx, (void *)s), "set_stream"); }
   // DeviceCCLWrapper::init equivalent: id produced by dftfe_b200_nccl_unique_id on rank 0 and MPI_Bcast by the caller
   void initComm(const uint8_t id[128], int rank, int nranks) { check(dftfe_b200_comm_init(d_ctx, id, rank, nranks), "comm_init"); }
+  // interBandGroupComm (NPBAND > 1): filter_all / solve then filter this group's blocks only and merge the groups
+  void initBandComm(const uint8_t id[128], int bandGroupTaskId, int numberBandGroups) {
+    check(dftfe_b200_band_comm_init(d_ctx, id, bandGroupTaskId, numberBandGroups), "band_comm_init");
+  }
+  // the merge of chebyshevOrthogonalizedSubspaceIterationSolverDevice.cc:539-567 on its own
+  void mergeBandGroups(double *eigenVectorsFlattenedDevice, const unsigned int totalNumberWaveFunctions) {
+    check(dftfe_b200_band_group_merge(d_ctx, eigenVectorsFlattenedDevice, (int32_t)totalNumberWaveFunctions), "band_group_merge");
+  }
+  // computeHamiltonianMatricesAllkpt pieces (hamiltonianMatrixCalculatorFlattenedDevice.cc): GGA real part, k-point terms
+  void computeHamiltonianMatrixGGA(int numQuadPoints, const double *shapeFunctionValues, const double *shapeFunctionGradientValuesRef,
+                                   const double *inverseJacobianValues, const double *vEffJxW,
+                                   const double *derExcWithSigmaTimesGradRhoJxW, const double *cellShapeFunctionGradientIntegral,
+                                   const double *externalPotCorr, double *cellHamiltonianMatrixFlattened) {
+    check(dftfe_b200_compute_cell_hamiltonian_gga(d_ctx, numQuadPoints, shapeFunctionValues, shapeFunctionGradientValuesRef,
+                                                  inverseJacobianValues, vEffJxW, derExcWithSigmaTimesGradRhoJxW,
+                                                  cellShapeFunctionGradientIntegral, 1, nullptr, externalPotCorr,
+                                                  cellHamiltonianMatrixFlattened),
+          "compute_cell_hamiltonian_gga");
+  }
+  void computeHamiltonianMatricesAllkpt(int numQuadPoints, const double *shapeFunctionValues,
+                                        const double *shapeFunctionGradientValuesRef, const double *inverseJacobianValues,
+                                        const double *JxW, const double *cellHamiltonianReal, int numkPoints,
+                                        const double *kPointCoordsVec, double *cellHamiltonianMatrixFlattenedComplex) {
+    check(dftfe_b200_compute_cell_hamiltonian_kpoints(d_ctx, numQuadPoints, shapeFunctionValues, shapeFunctionGradientValuesRef,
+                                                      inverseJacobianValues, JxW, cellHamiltonianReal, numkPoints,
+                                                      kPointCoordsVec, cellHamiltonianMatrixFlattenedComplex),
+          "compute_cell_hamiltonian_kpoints");
+  }
+  // computeRhoFromPSI with isEvaluateGradRho (densityCalculator.cc, densityCalculatorDeviceKernels.cc:35-140)
+  void computeRhoGradRhoFromPSI(const double *X, int N, const double *partialOccupancies, int numQuadPoints,
+                                const double *shapeFunctionValues, const double *shapeFunctionGradientValuesRef,
+                                const double *inverseJacobianValues, double *rho, double *gradRho) {
+    check(dftfe_b200_compute_density_grad(d_ctx, X, N, partialOccupancies, numQuadPoints, shapeFunctionValues,
+                                          shapeFunctionGradientValuesRef, inverseJacobianValues, rho, gradRho),
+          "compute_density_grad");
+  }
 
   // computeHamiltonianMatricesAllkpt output (kohnShamDFTOperatorDevice.cc:1060-3606): the flattened
   // d_cellHamiltonianMatrixFlattenedDevice holds nKptSpin sets of nC*n*n entries; hand each one over once per SCF
