@@ -16,6 +16,8 @@ over all N columns (8 blocks x 20 fused operator applies).
        non-local projectors, N = 1600, B = 200 (the reference's ragged AUTO block size)
     5  spin-polarised periodic cell with 2 k-points: complex build, 4 (k-point, spin) cell-Hamiltonian sets
     1  demo/ex1-like: non-periodic adaptive mesh with hanging nodes, non-local projectors, 15 states
+    4  non-periodic cluster on an adaptive mesh (hanging nodes, ghost exchange across irregular partitions), scaled down to
+       ~2.5 M DoFs / 1024 states so that the Python mesh generator finishes in a minute
 
 `--impl reference` times the CPU restatement of the reference's own CPU path (oracle/, all host cores) on a
 bounded sample of the same workload; the reference itself cannot be built in this image (deal.II, p4est, MPI,
@@ -50,7 +52,10 @@ CONFIGS = {
     "5": dict(name="spin-polarised periodic cell, 2 k-points (complex build)", cells=10, scaling="weak", nwfc=256,
               block=128, degree=20, cplx=True, atoms=0, sets=4),
     "1": dict(name="demo/ex1-like adaptive non-periodic mesh, 15 states", cells=10, scaling="strong", nwfc=15, block=15,
-              degree=20, cplx=False, atoms=2, sets=1, adaptive=True),
+              degree=20, cplx=False, atoms=2, sets=1, adaptive=True, refine_radius=2.2),
+    "4": dict(name="non-periodic cluster on an adaptive mesh with hanging nodes (scaled-down Mg/Mo-style cluster)", cells=20,
+              scaling="strong", nwfc=1024, block=256, degree=20, cplx=False, atoms=64, sets=1, adaptive=True,
+              refine_radius=5.0),
 }
 KPOINTS = [(0.0, 0.0, 0.0), (0.25, 0.25, 0.25)]  # fractional -> scaled by 2 pi / L below
 
@@ -92,6 +97,8 @@ def rank_grid_for(n):
 
 def global_cells(args, nranks):
     grid = rank_grid_for(nranks)
+    if args.cfg.get("adaptive"):
+        return (args.cells,) * 3
     if args.cfg["scaling"] == "weak":
         return tuple(args.cells * g for g in grid)
     return (args.cells,) * 3
@@ -107,12 +114,17 @@ def build_rank_problem(args, rank, nranks, build_H_host=False):
         nc = (args.cells, args.cells, args.cells)
         Hc = 1.5
         box = np.array(nc) * Hc
-        mesh = build_adaptive_mesh(P_ORDER, nc, Hc, lambda ctr: np.linalg.norm(ctr - box / 2.0, axis=1) < 2.2 * Hc,
+        rad = cfg.get("refine_radius", 2.2)
+        mesh = build_adaptive_mesh(P_ORDER, nc, Hc, lambda ctr: np.linalg.norm(ctr - box / 2.0, axis=1) < rad * Hc,
                                    nranks=nranks)
         pot = gaussian_wells_potential(mesh.box, periodic=(False, False, False))
         rp = mesh.rank_problem(rank, potential=pot, vquad="gll")
-        if cfg["atoms"]:
+        if cfg["atoms"] and cfg["atoms"] <= 2:
             atoms = box / 2.0 + np.array([[-1.04, 0.0, 0.0], [1.04, 0.0, 0.0]])[:cfg["atoms"]]   # N2 bond length
+            rp.nonlocal_data = mesh.nonlocal_data(rank, atoms, [8] * len(atoms), rc=1.6)
+        elif cfg["atoms"]:
+            rng = np.random.default_rng(2026)   # a compact cluster inside the refined region
+            atoms = box / 2.0 + rng.uniform(-0.8, 0.8, size=(cfg["atoms"], 3)) * rad * Hc * 0.8
             rp.nonlocal_data = mesh.nonlocal_data(rank, atoms, [8] * len(atoms), rc=1.6)
         return mesh, rp, pot
     from tools.femesh import build_mesh, gaussian_wells_potential
@@ -560,8 +572,11 @@ def main_ours(args):
         finite = bool(torch.isfinite(torch.view_as_real(X) if cplx else X).all().item())
 
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        ncell_t = torch.tensor([float(rp.nCells)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dist.all_reduce(ncell_t, op=dist.ReduceOp.SUM)
+        cells_global = int(ncell_t.item())
         ms_step = float(t.item()) / args.steps
         dofs_global = int(mesh.nFreeDofs)
         applies_per_step = dofs_global * N * m * nsets
@@ -730,8 +745,8 @@ def main_ours(args):
             "config": workload_config(args, world), "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches),
             "roofline": roofline, "scf_iteration": scf, "finite": finite, "spectrum_bounds": [A0, A_LOW, up],
             "ghost_transport": transport,
-            "tflops_fp64_filter": cflop * 2.0 * rp.n ** 2 * N * m * nsets * int(np.prod(global_cells(args, world)))
-                                  / (ms_step * 1e-3) / 1e12,
+            "tflops_fp64_filter": cflop * 2.0 * rp.n ** 2 * N * m * nsets * cells_global / (ms_step * 1e-3) / 1e12,
+            "cells_global": cells_global,
         }
         if nccl_parity is not None:
             line["parity_multi_gpu"] = nccl_parity

@@ -116,3 +116,34 @@ def test_cpp_adapter_compiles_and_links(capi, tmp_path):
     subprocess.check_call(cmd)
     out = subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout
     assert "dftfe_b200" in out
+
+
+def test_band_group_indices_match_reference_rule(capi):
+    """dftUtils::createBandParallelizationIndices (utils/dftUtils.cc:219-240): equal slices of N / nGroups columns, the
+    last group takes the remainder (host-only entry point: no GPU needed)."""
+    for ng, N in ((1, 15), (2, 96), (3, 100), (4, 2048), (7, 1600)):
+        got = capi.band_group_indices(ng, N)
+        w = N // ng
+        want = []
+        for g in range(ng):
+            want += [g * w, (g + 1) * w]
+        want[-1] = N
+        assert got.tolist() == want
+    with pytest.raises(capi.DftfeB200Error):
+        capi.band_group_indices(5, 3)   # NPBAND larger than the number of bands
+
+
+def test_reference_kernel_library_exports():
+    """oracle/_ref/libdftfe_ref_kernels.so (the reference's own device kernels, built by oracle/Makefile.ref where
+    /root/reference exists): when present it must load without a GPU and export the entry points the GPU tests use."""
+    from oracle import ref_kernels
+
+    if not ref_kernels.available():
+        pytest.skip("oracle/_ref not built in this checkout")
+    lib = ref_kernels.load()
+    for sym in ("ref_strided_copy_to_block", "ref_axpy_strided_block_atomic_add", "ref_strided_block_scale",
+                "ref_local_hamiltonian_times_x", "ref_local_hamiltonian_times_x_complex", "ref_gather_send_buffer",
+                "ref_accum_add_recv_buffer", "ref_constraints_create", "ref_constraints_distribute",
+                "ref_constraints_distribute_slave_to_master", "ref_constraints_set_zero", "ref_constraints_csr"):
+        assert hasattr(lib, sym), sym
+    assert b"constraintMatrixInfoDevice" in lib.ref_kernels_about()
