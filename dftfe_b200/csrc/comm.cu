@@ -352,6 +352,14 @@ static int p2p_setup(dftfe_b200_ctx *ctx) {
   DB_CUDA(cudaMalloc(&p.slab, p.slabBytes));
   DB_CUDA(cudaMemsetAsync(p.slab, 0, align_up((size_t)8 * nr * sizeof(uint32_t), 256), ctx->stream));
   DB_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (ok) {
+    // probe: a stream wait on an already satisfied flag must be accepted by this driver / device (else: NCCL transport)
+    const CUresult pr = wait_value32_fn()(ctx->stream, (CUdeviceptr)(p.slab + p.offFlags), 0, CU_STREAM_WAIT_VALUE_GEQ);
+    if (pr != CUDA_SUCCESS || cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+      cudaGetLastError();
+      ok = false;
+    }
+  }
   p.peerSlab.assign(nr, nullptr);
   p.peerOffFlags.assign(nr, 0);
   for (int l = 0; l < 2; ++l) {
