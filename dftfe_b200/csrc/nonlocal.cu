@@ -222,7 +222,9 @@ nl_apply_vec_kernel(double *__restrict__ y, int ncols, int ldx, const int32_t *_
       q[p] = make_double2(v * t.x, v * t.y);
     }
   }
-  for (int rb = r0 + warp * NLV_UNROLL; rb < r1; rb += NLV_WARPS * NLV_UNROLL) {
+  // the atom's rows are dealt over gridDim.z CTAs (row slices): a colour holds few atoms, and one CTA per (atom,
+  // column chunk) would leave most SMs without work
+  for (int rb = r0 + (blockIdx.z * NLV_WARPS + warp) * NLV_UNROLL; rb < r1; rb += gridDim.z * NLV_WARPS * NLV_UNROLL) {
     double2 yv[NLV_UNROLL];
     uint32_t rows[NLV_UNROLL];
 #pragma unroll
@@ -424,7 +426,9 @@ int nonlocal_apply(dftfe_b200_ctx *ctx, double *y, int ncols, int ldx, const dou
       const int nA = ns.colourStart_h[c + 1] - ns.colourStart_h[c];
       if (nA == 0) continue;
       ProfScope ps(ctx, "nonlocal");
-      dim3 grid(nA, (ncols + 63) / 64);
+      const int chunks = (ncols + 63) / 64;
+      const int slices = std::max(1, std::min(32, (6 * ctx->num_sms + nA * chunks - 1) / (nA * chunks)));
+      dim3 grid(nA, chunks, slices);
 #define DB_NLA(CM, PM)                                                                                              \
   nl_apply_vec_kernel<CM, PM><<<grid, NLV_WARPS * 32, 0, ctx->stream>>>(                                              \
       y, ncols, ldx, ns.colourAtoms.p + ns.colourStart_h[c], ns.atomRowStart.p, ns.atomRows.p, ns.atomValStart.p,  \
