@@ -265,9 +265,11 @@ WaitValue32Fn wait_value32_fn() {
 }
 
 enum { P2P_DATA = 0, P2P_ACK = 1 };
+enum { P2P_FWD = 0, P2P_REV = 1, P2P_AR = 2 };  // flag banks: forward / reverse exchange, projector all-reduce
+constexpr int P2P_NFLAGS = 2 * 3 * 2;              // [lane][bank][DATA | ACK] x nranks
 
 inline uint32_t *p2p_flag(char *slab, size_t offFlags, int nranks, int lane, int dir, int kind, int src) {
-  return reinterpret_cast<uint32_t *>(slab + offFlags) + ((size_t)((lane * 2 + dir) * 2 + kind) * nranks + src);
+  return reinterpret_cast<uint32_t *>(slab + offFlags) + ((size_t)((lane * 3 + dir) * 2 + kind) * nranks + src);
 }
 
 int p2p_wait(dftfe_b200_ctx *ctx, int dir, int kind, int src, uint32_t value) {
@@ -286,7 +288,7 @@ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 // record every rank publishes: [0..7] cudaIpc handle (64 bytes), [8] offFlags, [9..10] offRecvF, [11..12] offRecvR,
 // [13 .. 13+nranks) first row of rank q's rows in MY ghost segment, [13+nranks .. 13+2 nranks) first row of rank
 // q's range in MY reverse receive buffer (-1: q is not a neighbour)
-constexpr int P2P_REC_FIXED = 13;
+constexpr int P2P_REC_FIXED = 16;  // ... [13..14] offAr, [15] arMax
 
 void p2p_fill_starts(const dftfe_b200_ctx *c, int64_t *ghostStart, int64_t *targetStart) {
   for (int r = 0; r < c->nranks; ++r) ghostStart[r] = targetStart[r] = -1;
@@ -302,18 +304,23 @@ void p2p_release(dftfe_b200_ctx *ctx) {
     // my neighbours acknowledge my last payloads by storing into THIS slab: wait (bounded) until every expected
     // acknowledgement has landed before the memory goes away
     const int nr = ctx->nranks;
-    std::vector<uint32_t> flags((size_t)8 * nr);
+    std::vector<uint32_t> flags((size_t)P2P_NFLAGS * nr);
     for (int spin = 0; spin < 2000; ++spin) {
       if (cudaMemcpy(flags.data(), p.slab + p.offFlags, flags.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost) !=
           cudaSuccess)
         break;
       bool done = true;
-      for (int lane = 0; lane < 2; ++lane)
+      for (int lane = 0; lane < 2; ++lane) {
         for (int dir = 0; dir < 2; ++dir) {
           const std::vector<int32_t> &dst = dir == 0 ? ctx->targetProcs_h : ctx->ghostProcs_h;
           for (int q : dst)
-            done = done && (int32_t)(flags[((size_t)((lane * 2 + dir) * 2 + P2P_ACK)) * nr + q] - p.seq[lane][dir]) >= 0;
+            done = done && (int32_t)(flags[((size_t)((lane * 3 + dir) * 2 + P2P_ACK)) * nr + q] - p.seq[lane][dir]) >= 0;
         }
+        if (p.arMax > 0)
+          for (int q = 0; q < nr; ++q)
+            if (q != ctx->rank)
+              done = done && (int32_t)(flags[((size_t)((lane * 3 + P2P_AR) * 2 + P2P_ACK)) * nr + q] - p.seqAr[lane]) >= 0;
+      }
       if (done) break;
       struct timespec ts = {0, 1000000};
       nanosleep(&ts, nullptr);
@@ -341,16 +348,23 @@ static int p2p_setup(dftfe_b200_ctx *ctx) {
   // slab layout
   const size_t rowMax = (size_t)ctx->B * ctx->cm * sizeof(double);
   p.offFlags = 0;
-  size_t off = align_up((size_t)2 * 2 * 2 * nr * sizeof(uint32_t), 256);
+  size_t off = align_up((size_t)P2P_NFLAGS * nr * sizeof(uint32_t), 256);
   for (int l = 0; l < 2; ++l) {
     p.offRecvF[l] = off;
     off = align_up(off + (size_t)ctx->G * rowMax, 256);
     p.offRecvR[l] = off;
     off = align_up(off + (size_t)ctx->nSend * rowMax, 256);
   }
+  // projector all-reduce slots (only when projectors are already set: the block size is the same on every rank)
+  p.arMax = 0;
+  for (auto &kv : ctx->nlSets) p.arMax = std::max<size_t>(p.arMax, (size_t)kv.second.totalProj * ctx->B * ctx->cm);
+  for (int l = 0; l < 2; ++l) {
+    p.offAr[l] = off;
+    off = align_up(off + (size_t)nr * p.arMax * sizeof(double), 256);
+  }
   p.slabBytes = off;
   DB_CUDA(cudaMalloc(&p.slab, p.slabBytes));
-  DB_CUDA(cudaMemsetAsync(p.slab, 0, align_up((size_t)8 * nr * sizeof(uint32_t), 256), ctx->stream));
+  DB_CUDA(cudaMemsetAsync(p.slab, 0, align_up((size_t)P2P_NFLAGS * nr * sizeof(uint32_t), 256), ctx->stream));
   DB_CUDA(cudaStreamSynchronize(ctx->stream));
   if (ok) {
     // probe: a stream wait on an already satisfied flag must be accepted by this driver / device (else: NCCL transport)
@@ -365,12 +379,16 @@ static int p2p_setup(dftfe_b200_ctx *ctx) {
   for (int l = 0; l < 2; ++l) {
     p.peerOffRecvF[l].assign(nr, 0);
     p.peerOffRecvR[l].assign(nr, 0);
+    p.peerOffAr[l].assign(nr, 0);
   }
   p.peerGhostStartOfMe.assign(nr, -1);
   p.peerTargetStartOfMe.assign(nr, -1);
   std::vector<char> neighbour(nr, 0);
   for (int q : ctx->targetProcs_h) neighbour[q] = 1;
   for (int q : ctx->ghostProcs_h) neighbour[q] = 1;
+  if (p.arMax > 0)  // the all-reduce talks to every rank
+    for (int q = 0; q < nr; ++q) neighbour[q] = (q != ctx->rank);
+  neighbour[ctx->rank] = 0;
 
   if (grp && !ctx->nccl) {
     // one process, several ranks on one device: peers' slabs are plain pointers
@@ -387,7 +405,9 @@ static int p2p_setup(dftfe_b200_ctx *ctx) {
       for (int l = 0; l < 2; ++l) {
         p.peerOffRecvF[l][q] = pc->p2p.offRecvF[l];
         p.peerOffRecvR[l][q] = pc->p2p.offRecvR[l];
+        p.peerOffAr[l][q] = pc->p2p.offAr[l];
       }
+      if (pc->p2p.arMax != p.arMax) ok = false;
       std::vector<int64_t> gs(nr), ts(nr);
       p2p_fill_starts(pc, gs.data(), ts.data());
       p.peerGhostStartOfMe[q] = gs[ctx->rank];
@@ -419,6 +439,9 @@ static int p2p_setup(dftfe_b200_ctx *ctx) {
   mine[10] = (int64_t)p.offRecvF[1];
   mine[11] = (int64_t)p.offRecvR[0];
   mine[12] = (int64_t)p.offRecvR[1];
+  mine[13] = (int64_t)p.offAr[0];
+  mine[14] = (int64_t)p.offAr[1];
+  mine[15] = (int64_t)p.arMax;
   p2p_fill_starts(ctx, mine + P2P_REC_FIXED, mine + P2P_REC_FIXED + nr);
   DevBuf<int64_t> dtab;
   DB_TRY(dtab.upload(table.data(), table.size(), ctx->stream));
@@ -443,6 +466,9 @@ static int p2p_setup(dftfe_b200_ctx *ctx) {
     p.peerOffRecvF[1][q] = (size_t)rec[10];
     p.peerOffRecvR[0][q] = (size_t)rec[11];
     p.peerOffRecvR[1][q] = (size_t)rec[12];
+    p.peerOffAr[0][q] = (size_t)rec[13];
+    p.peerOffAr[1][q] = (size_t)rec[14];
+    if ((size_t)rec[15] != p.arMax) ok = false;  // (projectors set on some ranks only: keep NCCL)
     p.peerGhostStartOfMe[q] = rec[P2P_REC_FIXED + ctx->rank];
     p.peerTargetStartOfMe[q] = rec[P2P_REC_FIXED + nr + ctx->rank];
   }
@@ -589,8 +615,59 @@ int ghost_zero(dftfe_b200_ctx *ctx, double *x, int ncols, int ldx) {
   return 0;
 }
 
+namespace {
+// buf[i] = sum over the ranks, in rank order (identical bits on every rank), of the slots; my own contribution is buf
+__global__ void p2p_sum_slots_kernel(double *__restrict__ buf, const double *__restrict__ slots, size_t slotStride,
+                                     size_t count, int nranks, int me) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+    double s = 0.0;
+    for (int r = 0; r < nranks; ++r) s += (r == me) ? buf[i] : slots[(size_t)r * slotStride + i];
+    buf[i] = s;
+  }
+}
+}  // namespace
+
+// All-reduce over the peer-mapped slabs: every rank copies its block into its slot of every other rank's slab (peer
+// copies on the copy engines, no SM), publishes the sequence number, waits for the others with stream memory
+// operations and sums the slots in rank order.  Replaces ncclAllReduce for the per-apply projector block, whose
+// kernels - like NCCL's send/recv - cannot co-reside with the persistent cell CTAs of the other filter lane.
+static int allreduce_p2p(dftfe_b200_ctx *ctx, double *buf, size_t count) {
+  auto &p = ctx->p2p;
+  const int lane = ctx->lane, nr = ctx->nranks, me = ctx->rank;
+  const uint32_t seq = ++p.seqAr[lane];
+  if (seq > 1)
+    for (int q = 0; q < nr; ++q)
+      if (q != me) DB_TRY(p2p_wait(ctx, P2P_AR, P2P_ACK, q, seq - 1));
+  SignalList sig, ack;
+  sig.n = ack.n = 0;
+  for (int q = 0; q < nr; ++q) {
+    if (q == me) continue;
+    DB_CHECK(p.peerSlab[q], "p2p all-reduce: rank %d is not mapped", q);
+    ctx->launches += 1;
+    DB_CUDA(cudaMemcpyAsync(p.peerSlab[q] + p.peerOffAr[lane][q] + (size_t)me * p.arMax * sizeof(double), buf,
+                            count * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    sig.addr[sig.n++] = p2p_flag(p.peerSlab[q], p.peerOffFlags[q], nr, lane, P2P_AR, P2P_DATA, me);
+    ack.addr[ack.n++] = p2p_flag(p.peerSlab[q], p.peerOffFlags[q], nr, lane, P2P_AR, P2P_ACK, me);
+  }
+  DB_TRY(launch_signal_flags(ctx, sig, seq));
+  LoopbackGroup *inproc = ctx->nccl ? nullptr : loopback_of(ctx);
+  if (inproc) inproc->barrier();
+  for (int q = 0; q < nr; ++q)
+    if (q != me) DB_TRY(p2p_wait(ctx, P2P_AR, P2P_DATA, q, seq));
+  ctx->launches += 1;
+  const int grid = (int)std::max<size_t>(1, std::min<size_t>((count + 255) / 256, (size_t)ctx->num_sms * 4));
+  p2p_sum_slots_kernel<<<grid, 256, 0, ctx->stream>>>(buf, reinterpret_cast<const double *>(p.slab + p.offAr[lane]),
+                                                     p.arMax, count, nr, me);
+  DB_CUDA(cudaGetLastError());
+  DB_TRY(launch_signal_flags(ctx, ack, seq));
+  if (inproc) inproc->barrier();
+  return 0;
+}
+
 int allreduce_sum(dftfe_b200_ctx *ctx, double *buf, size_t count) {
   if (ctx->nranks == 1) return 0;
+  if (ctx->p2p.active && ctx->p2p.arMax >= count && count > 0 && ctx->nranks <= P2P_MAX_PEERS)
+    return allreduce_p2p(ctx, buf, count);
   if (ctx->nccl) {
     DB_NCCL(nccl_api()->AllReduce(buf, buf, count, ncclDouble, ncclSum, ctx->nccl, ctx->stream));
     return 0;

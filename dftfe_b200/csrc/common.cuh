@@ -244,6 +244,11 @@ struct dftfe_b200_ctx {
     std::vector<int64_t> peerGhostStartOfMe;    // first row, in rank r's ghost segment, of the rows I own (-1: none)
     std::vector<int64_t> peerTargetStartOfMe;   // first row, in rank r's reverse receive buffer, of my ghost range
     uint32_t seq[2][2] = {{0, 0}, {0, 0}};      // [lane][0 forward, 1 reverse] exchanges issued so far
+    // all-reduce of the non-local projector block over the same slabs (every rank mapped): per lane one slot of
+    // arMax doubles per source rank; 0 = not provisioned (no projectors at setup time) -> NCCL all-reduce
+    size_t arMax = 0, offAr[2] = {0, 0};
+    std::vector<size_t> peerOffAr[2];
+    uint32_t seqAr[2] = {0, 0};
   } p2p;
 
   // --- band parallelisation (interBandGroupComm): contexts that hold the same mesh partition in different band groups
