@@ -426,9 +426,9 @@ int launch_tf32x3_gemm(dftfe_b200_ctx *ctx, const float *Ahi, const float *Alo, 
                        int64_t ldc);
 
 // mixed_precision.cu
-int xtx_mixed_impl(dftfe_b200_ctx *ctx, const double *X, int N, double *S, bool commOnly = false);
+int xtx_mixed_impl(dftfe_b200_ctx *ctx, const double *X, int Nreal, int BwReal, double *S, bool commOnly = false);
 int xthx_mixed_impl(dftfe_b200_ctx *ctx, const double *X, int N, int Noc, double *Hp, bool commOnly = false);
-int rotate_mixed_impl(dftfe_b200_ctx *ctx, double *X, int N, const double *Q, bool qColMajor, int mode);
+int rotate_mixed_impl(dftfe_b200_ctx *ctx, double *X, int Nreal, int BwReal, const double *Q, bool qColMajor, int mode);
 
 // high-level pieces (solver.cu)
 int apply_H_to_columns(dftfe_b200_ctx *ctx, const double *X, int N, int j0, int ncols);

@@ -1,4 +1,7 @@
-// Mixed-precision variants of the subspace projections and rotations (real build).
+// Mixed-precision variants of the subspace projections and rotations.  Real build: as described below.  Complex build:
+// the same routines run on the REAL VIEW of the interleaved storage (2N real columns, block width 2 Bw) and solver.cu
+// recombines the real 2N x 2N result into the complex N x N matrix - a complex FP32 block of the reference (cgemm on
+// cuFloatComplex copies) becomes the four real FP32 blocks of its real / imaginary parts.
 //
 // Reference (all under src/linAlg/linearAlgebraOperationsDevice.cc unless stated):
 //   fillParallelOverlapMatMixedPrecScalapack      :3543-3798  S = X^T X, diagonal Bw x Bw blocks FP64, the blocks
@@ -44,7 +47,8 @@ __global__ void to_float_rows_kernel(const double *__restrict__ in, int64_t ldi,
 }
 
 // Qsp (row-major N x N float) = off-diagonal part of Q; mode 1: the Bw x Bw diagonal blocks are dropped,
-// mode 2: only the diagonal entries.  qColMajor: Q(k,j) at k + j*N, else k*N + j.
+// mode 2: only the diagonal entries, mode 3: the 2 x 2 diagonal blocks (= the complex diagonal entries of the real
+// embedding of a complex Q; diag[4 c + 2 r + s] = Q(2c + r, 2c + s)).  qColMajor: Q(k,j) at k + j*N, else k*N + j.
 // Qthi / Qtlo (optional): the same off-diagonal part TRANSPOSED ([j][k], pitch ldt) and split in TF32-exact hi / lo
 // parts - the K-major B operand of the tcgen05 rotation GEMM.
 __global__ void split_rotation_kernel(const double *__restrict__ Q, int N, int qColMajor, int mode, int Bw,
@@ -55,7 +59,7 @@ __global__ void split_rotation_kernel(const double *__restrict__ Q, int N, int q
        idx += (int64_t)gridDim.x * blockDim.x) {
     const int k = idx / N, j = idx % N;
     const double v = Q[qColMajor ? ((int64_t)k + (int64_t)j * N) : idx];
-    const bool onDiag = mode == 1 ? (k / Bw == j / Bw) : (k == j);
+    const bool onDiag = mode == 1 ? (k / Bw == j / Bw) : (mode == 3 ? (k / 2 == j / 2) : (k == j));
     const float f = onDiag ? 0.0f : (float)v;
     if (Qsp) Qsp[idx] = f;
     if (Qthi) {
@@ -64,6 +68,7 @@ __global__ void split_rotation_kernel(const double *__restrict__ Q, int N, int q
       Qtlo[(int64_t)j * ldt + k] = __uint_as_float(__float_as_uint(f - hi) & 0xffffe000u);
     }
     if (mode == 2 && k == j) diag[k] = v;
+    if (mode == 3 && onDiag) diag[4 * (k / 2) + 2 * (k & 1) + (j & 1)] = v;
   }
 }
 
@@ -74,6 +79,22 @@ __global__ void combine_diag_kernel(double *__restrict__ X, int N, int64_t rows,
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x)
     X[idx] = X[idx] * diag[idx % N] + (double)T[idx];
+}
+
+// complex diagonal through the real embedding: (X[r, 2c], X[r, 2c+1]) <- (X[r, 2c], X[r, 2c+1]) D_c + T, D_c 2 x 2
+// (computeDiagQTimesXKernel, complex overload, linearAlgebraOperationsDevice.cc:220-237)
+__global__ void combine_diag2_kernel(double *__restrict__ X, int N, int64_t rows, const double *__restrict__ diag,
+                                     const float *__restrict__ T) {
+  const int64_t total = rows * (N / 2);
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int c = idx % (N / 2);
+    const int64_t at = (idx / (N / 2)) * N + 2 * c;
+    const double x0 = X[at], x1 = X[at + 1];
+    const double *d = diag + 4 * c;
+    X[at] = x0 * d[0] + x1 * d[2] + (double)T[at];
+    X[at + 1] = x0 * d[1] + x1 * d[3] + (double)T[at + 1];
+  }
 }
 
 // X[r, :] = D[r, :] + T[r, :]
@@ -99,14 +120,15 @@ __global__ void merge_overlap_kernel(const double *__restrict__ dp, const float 
 }
 
 // full symmetric Hp from the FP64 lower blocks (G, column-major N x N) and the FP32 column blocks (sp) that end
-// inside the first Noc states
+// inside the first Noc states.  mirror = 0 (real view of a complex build, not symmetric): element-wise copy of the
+// block-lower part, the rest is never read.
 __global__ void merge_projham_kernel(const double *__restrict__ G, const float *__restrict__ sp, int N, int Bw,
-                                     int Noc, double *__restrict__ Hp) {
+                                     int Noc, double *__restrict__ Hp, int mirror) {
   const int64_t total = (int64_t)N * N;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
        idx += (int64_t)gridDim.x * blockDim.x) {
     const int a = idx % N, b = idx / N;
-    const int i = max(a, b), j = min(a, b);
+    const int i = mirror ? max(a, b) : a, j = mirror ? min(a, b) : b;
     const int j0 = (j / Bw) * Bw;
     const bool single = (j0 + min(Bw, N - j0)) <= Noc;
     const int64_t src = (int64_t)i + (int64_t)j * N;
@@ -146,9 +168,9 @@ int to_float(dftfe_b200_ctx *ctx, const double *in, int64_t ldi, float *out, int
 
 }  // namespace
 
-// S = X^T X with FP64 diagonal blocks and FP32 off-diagonal blocks; full symmetric result, all-reduced
-int xtx_mixed_impl(dftfe_b200_ctx *ctx, const double *X, int N, double *S, bool commOnly) {
-  const int Bw = std::min(ctx->B, N);
+// S = X^T X with FP64 diagonal blocks and FP32 off-diagonal blocks; full symmetric result, all-reduced.
+// N, Bw: REAL columns / block width (complex build: twice the wavefunction counts, S = the real 2N x 2N Gram matrix)
+int xtx_mixed_impl(dftfe_b200_ctx *ctx, const double *X, int N, int Bw, double *S, bool commOnly) {
   const int64_t M = ctx->M;
   if (commOnly) {
     // FP64 arithmetic, FP32 only on the wire (fillParallelOverlapMatMixedPrecCommunScalapackAsyncComputeCommun,
@@ -235,89 +257,96 @@ int xtx_mixed_impl(dftfe_b200_ctx *ctx, const double *X, int N, double *S, bool 
   return 0;
 }
 
-// Hp = X^T (H~ X): column blocks [j, j+Bc) with j + Bc <= Noc entirely in FP32, the others FP64
-int xthx_mixed_impl(dftfe_b200_ctx *ctx, const double *X, int N, int Noc, double *Hp, bool commOnly) {
-  const int Bw = std::min(ctx->B, N);
+// Hp = X^H (H~ X): column blocks [j, j+Bc) with j + Bc <= Noc entirely in FP32, the others FP64.  N, Noc, j count
+// wavefunctions; all matrix indices below are REAL columns (x cm).  Real build: Hout = full symmetric Hp.  Complex
+// build: Hout = the block-lower part of the real 2N x 2N matrix G(a,b) = sum_m Xr[m,a] (H~X)r[m,b] (not symmetric;
+// the caller combines it into the complex lower triangle).
+int xthx_mixed_impl(dftfe_b200_ctx *ctx, const double *X, int N, int Noc, double *Hout, bool commOnly) {
+  const int cm = ctx->cm, Nr = N * cm, Nocr = Noc * cm;
+  const int Bw0 = std::min(ctx->B, N), Bw = Bw0 * cm;
   const int64_t M = ctx->M;
   const bool tc = !ctx->use_cublas_dense && !commOnly;
   const int64_t Mp = (std::max<int64_t>(M, 1) + 3) / 4 * 4;
   if (tc) {
-    DB_TRY(ctx->mpThi.alloc((size_t)N * Mp));
-    DB_TRY(ctx->mpTlo.alloc((size_t)N * Mp));
+    DB_TRY(ctx->mpThi.alloc((size_t)Nr * Mp));
+    DB_TRY(ctx->mpTlo.alloc((size_t)Nr * Mp));
     DB_TRY(ctx->mpBhi.alloc((size_t)Bw * Mp));
     DB_TRY(ctx->mpBlo.alloc((size_t)Bw * Mp));
   } else {
-    DB_TRY(ctx->mpXsp.alloc(commOnly ? 1 : (size_t)std::max<int64_t>(M, 1) * N));
+    DB_TRY(ctx->mpXsp.alloc(commOnly ? 1 : (size_t)std::max<int64_t>(M, 1) * Nr));
     DB_TRY(ctx->mpBlockSp.alloc((size_t)std::max<int64_t>(M, 1) * Bw));
   }
-  DB_TRY(ctx->mpSp.alloc((size_t)N * N));
-  DB_TRY(ctx->denseW.alloc((size_t)N * N));
+  DB_TRY(ctx->mpSp.alloc((size_t)Nr * Nr));
+  DB_TRY(ctx->denseW.alloc((size_t)Nr * Nr));
   double *G = ctx->denseW.p;
-  DB_CUDA(cudaMemsetAsync(ctx->mpSp.p, 0, (size_t)N * N * sizeof(float), ctx->stream));
-  DB_CUDA(cudaMemsetAsync(G, 0, (size_t)N * N * sizeof(double), ctx->stream));
-  if (tc && Noc >= Bw)  // only the columns an FP32 block touches: rows j.. of X^T for blocks ending inside Noc
-    DB_TRY(launch_split_transpose(ctx, X, N, 0, N, M, ctx->mpThi.p, ctx->mpTlo.p, Mp));
+  DB_CUDA(cudaMemsetAsync(ctx->mpSp.p, 0, (size_t)Nr * Nr * sizeof(float), ctx->stream));
+  DB_CUDA(cudaMemsetAsync(G, 0, (size_t)Nr * Nr * sizeof(double), ctx->stream));
+  if (tc && Noc >= Bw0)  // only the columns an FP32 block touches: rows j.. of X^T for blocks ending inside Noc
+    DB_TRY(launch_split_transpose(ctx, X, Nr, 0, Nr, M, ctx->mpThi.p, ctx->mpTlo.p, Mp));
   else if (!commOnly && !tc)
-    DB_TRY(to_float(ctx, X, N, ctx->mpXsp.p, N, N, M));
+    DB_TRY(to_float(ctx, X, Nr, ctx->mpXsp.p, Nr, Nr, M));
   const double one = 1.0, zero = 0.0;
   const float onef = 1.0f, zerof = 0.0f;
-  for (int j = 0; j < N; j += Bw) {
-    const int Bc = std::min(Bw, N - j), D = N - j;
-    DB_TRY(apply_H_to_columns(ctx, X, N, j, Bc));  // blockY = H~ X[:, j:j+Bc]  (M x Bc)
+  for (int j0 = 0; j0 < N; j0 += Bw0) {
+    const int Bc0 = std::min(Bw0, N - j0);
+    const int j = j0 * cm, Bc = Bc0 * cm, D = Nr - j;
+    DB_TRY(apply_H_to_columns(ctx, X, N, j0, Bc0));  // blockY = H~ X[:, j0:j0+Bc0]  (M x Bc real columns)
     if (M == 0) continue;
     DB_CUBLAS(cublasSetStream(ctx->cublas, ctx->stream));
-    if (j + Bc <= Noc && tc) {
+    if (j0 + Bc0 <= Noc && tc) {
       // Hp(j.., j..j+Bc) = X[:, j:]^T (H~ X)[:, j:j+Bc] in FP32 on the tcgen05 tensor cores
       DB_TRY(launch_split_transpose(ctx, ctx->blockY.p, Bc, 0, Bc, M, ctx->mpBhi.p, ctx->mpBlo.p, Mp));
-      DB_TRY(launch_tf32x3_gemm(ctx, ctx->mpThi.p, ctx->mpTlo.p, N, Mp, j, D, ctx->mpBhi.p, ctx->mpBlo.p, Bc, Mp, 0, Bc,
-                                M, nullptr, 0, ctx->mpSp.p + j + (size_t)j * N, N));
-    } else if (j + Bc <= Noc && !commOnly) {
+      DB_TRY(launch_tf32x3_gemm(ctx, ctx->mpThi.p, ctx->mpTlo.p, Nr, Mp, j, D, ctx->mpBhi.p, ctx->mpBlo.p, Bc, Mp, 0,
+                                Bc, M, nullptr, 0, ctx->mpSp.p + j + (size_t)j * Nr, Nr));
+    } else if (j0 + Bc0 <= Noc && !commOnly) {
       DB_TRY(to_float(ctx, ctx->blockY.p, Bc, ctx->mpBlockSp.p, Bc, Bc, M));
       ProfScope ps(ctx, "projection_fp32");
-      DB_CUBLAS(cublasSgemm(ctx->cublas, CUBLAS_OP_N, CUBLAS_OP_T, D, Bc, (int)M, &onef, ctx->mpXsp.p + j, N,
-                            ctx->mpBlockSp.p, Bc, &zerof, ctx->mpSp.p + j + (size_t)j * N, N));
-    } else if (!ctx->use_cublas_dense && al16(X) && dmma_projection_usable(ctx, N, N, Bc, j, 0, D, Bc)) {
-      DB_TRY(launch_xty(ctx, X, N, j, ctx->blockY.p, Bc, 0, D, Bc, j, j, true, G + j + (size_t)j * N, N));
+      DB_CUBLAS(cublasSgemm(ctx->cublas, CUBLAS_OP_N, CUBLAS_OP_T, D, Bc, (int)M, &onef, ctx->mpXsp.p + j, Nr,
+                            ctx->mpBlockSp.p, Bc, &zerof, ctx->mpSp.p + j + (size_t)j * Nr, Nr));
+    } else if (!ctx->use_cublas_dense && al16(X) && dmma_projection_usable(ctx, Nr, Nr, Bc, j, 0, D, Bc)) {
+      DB_TRY(launch_xty(ctx, X, Nr, j, ctx->blockY.p, Bc, 0, D, Bc, j, j, true, G + j + (size_t)j * Nr, Nr));
     } else {
       ProfScope ps(ctx, "projection");
-      DB_CUBLAS(cublasDgemm(ctx->cublas, CUBLAS_OP_N, CUBLAS_OP_T, D, Bc, (int)M, &one, X + j, N, ctx->blockY.p, Bc,
-                            &zero, G + j + (size_t)j * N, N));
+      DB_CUBLAS(cublasDgemm(ctx->cublas, CUBLAS_OP_N, CUBLAS_OP_T, D, Bc, (int)M, &one, X + j, Nr, ctx->blockY.p, Bc,
+                            &zero, G + j + (size_t)j * Nr, Nr));
     }
   }
   if (commOnly) {
     // FP64 blocks that end inside the core states travel as FP32 (XtHXMixedPrecCommunOverlapComputeCommun,
     // kohnShamDFTOperatorDevice.cc:5082-5536: copyValueType1ArrToValueType2Arr before the all-reduce)
-    for (int j = 0; j < N; j += Bw) {
-      const int Bc = std::min(Bw, N - j);
-      if (j + Bc > Noc) break;
+    for (int j = 0; j < Nr; j += Bw) {
+      const int Bc = std::min(Bw, Nr - j);
+      if (j + Bc > Nocr) break;
       ctx->launches += 2;
-      split_dp_sp_kernel<<<grid_for(ctx, (int64_t)(N - j) * Bc), 256, 0, ctx->stream>>>(G, N, j, Bc, Bw, 0, nullptr,
-                                                                                         ctx->mpSp.p);
-      DB_CUDA(cudaMemset2DAsync(G + j + (size_t)j * N, (size_t)N * sizeof(double), 0, (size_t)(N - j) * sizeof(double),
-                                (size_t)Bc, ctx->stream));
+      split_dp_sp_kernel<<<grid_for(ctx, (int64_t)(Nr - j) * Bc), 256, 0, ctx->stream>>>(G, Nr, j, Bc, Bw, 0, nullptr,
+                                                                                          ctx->mpSp.p);
+      DB_CUDA(cudaMemset2DAsync(G + j + (size_t)j * Nr, (size_t)Nr * sizeof(double), 0,
+                                (size_t)(Nr - j) * sizeof(double), (size_t)Bc, ctx->stream));
     }
     DB_CUDA(cudaGetLastError());
   }
-  DB_TRY(allreduce_sum(ctx, G, (size_t)N * N));
-  DB_TRY(allreduce_sum_f32(ctx, ctx->mpSp.p, (size_t)N * N));
+  DB_TRY(allreduce_sum(ctx, G, (size_t)Nr * Nr));
+  DB_TRY(allreduce_sum_f32(ctx, ctx->mpSp.p, (size_t)Nr * Nr));
   ctx->launches += 1;
-  merge_projham_kernel<<<grid_for(ctx, (int64_t)N * N), 256, 0, ctx->stream>>>(G, ctx->mpSp.p, N, Bw, Noc, Hp);
+  merge_projham_kernel<<<grid_for(ctx, (int64_t)Nr * Nr), 256, 0, ctx->stream>>>(G, ctx->mpSp.p, Nr, Bw, Nocr, Hout,
+                                                                                 cm == 1 ? 1 : 0);
   DB_CUDA(cudaGetLastError());
   return 0;
 }
 
 // X <- X Q in mixed precision.  mode 1 (CGS): FP64 diagonal Bw x Bw blocks + FP32 off-diagonal;
-// mode 2 (RR): FP64 diag(Q) + FP32 (Q - diag Q).  Row chunks, in place.
-int rotate_mixed_impl(dftfe_b200_ctx *ctx, double *X, int N, const double *Q, bool qColMajor, int mode) {
-  DB_CHECK(mode == 1 || mode == 2, "rotate: unknown mixed-precision mode %d", mode);
+// mode 2 (RR): FP64 diag(Q) + FP32 (Q - diag Q); mode 3: mode 2 for the real embedding of a complex Q (2 x 2
+// diagonal blocks).  N, Bw: REAL columns / block width.  Row chunks, in place.
+int rotate_mixed_impl(dftfe_b200_ctx *ctx, double *X, int N, int Bw, const double *Q, bool qColMajor, int mode) {
+  DB_CHECK(mode >= 1 && mode <= 3, "rotate: unknown mixed-precision mode %d", mode);
+  DB_CHECK(mode != 3 || N % 2 == 0, "rotate: mode 3 needs an even (embedded complex) column count");
   const int64_t M = ctx->M;
   if (M == 0) return 0;
-  const int Bw = std::min(ctx->B, N);
   const int64_t chunk = std::min<int64_t>(M, 148 * 128);
   const bool tc = !ctx->use_cublas_dense;
   const int64_t Np = ((int64_t)N + 3) / 4 * 4;       // pitch of the K-major FP32 operands (k = wavefunction index)
   DB_TRY(ctx->mpSp.alloc((size_t)N * N));            // Q off-diagonal part, FP32 row-major
-  DB_TRY(ctx->mpDp.alloc((size_t)N * std::max(Bw, 1)));  // diag(Q) (mode 2)
+  DB_TRY(ctx->mpDp.alloc((size_t)N * std::max(Bw, 2)));  // diag(Q) (mode 2), 2 x 2 diagonal blocks (mode 3)
   DB_TRY(ctx->mpXsp.alloc((size_t)chunk * N * 2));   // [chunk x N] FP32 copy of X, then the FP32 product
   float *Xsp = ctx->mpXsp.p, *Tsp = ctx->mpXsp.p + (size_t)chunk * N;
   if (tc) {
@@ -357,6 +386,9 @@ int rotate_mixed_impl(dftfe_b200_ctx *ctx, double *X, int N, const double *Q, bo
     if (mode == 2) {
       ctx->launches += 1;
       combine_diag_kernel<<<grid_for(ctx, (int64_t)mc * N), 256, 0, ctx->stream>>>(Xc, N, mc, ctx->mpDp.p, Tsp);
+    } else if (mode == 3) {
+      ctx->launches += 1;
+      combine_diag2_kernel<<<grid_for(ctx, (int64_t)mc * N / 2), 256, 0, ctx->stream>>>(Xc, N, mc, ctx->mpDp.p, Tsp);
     } else {
       ProfScope ps(ctx, "rotation", N / Bw + 1);
       for (int j = 0; j < N; j += Bw) {

@@ -412,10 +412,12 @@ static int rotate_real(dftfe_b200_ctx *ctx, double *X, int N, const double *Q, b
 }
 
 // X <- X * Q for N wavefunction columns (complex: through the real 2N x 2N embedding of Q).
-// mixedMode 0: FP64; 1 / 2: the reference's CGS / RR mixed-precision rotations (real build only).
+// mixedMode 0: FP64; 1 / 2: the reference's CGS / RR mixed-precision rotations (complex: block width 2 Bw for the
+// CGS variant, the complex diagonal = 2 x 2 diagonal blocks of the embedding for the RR variant).
 static int rotate_impl(dftfe_b200_ctx *ctx, double *X, int N, const double *Q, bool qColMajor, int mixedMode = 0) {
+  const int Bw = std::min(ctx->B, N);
   if (!ctx->cplx) {
-    if (mixedMode != 0) return rotate_mixed_impl(ctx, X, N, Q, qColMajor, mixedMode);
+    if (mixedMode != 0) return rotate_mixed_impl(ctx, X, N, Bw, Q, qColMajor, mixedMode);
     return rotate_real(ctx, X, N, Q, qColMajor);
   }
   const int Nr = 2 * N;
@@ -423,6 +425,8 @@ static int rotate_impl(dftfe_b200_ctx *ctx, double *X, int N, const double *Q, b
   ctx->launches += 1;
   cplx_embed_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(Q, N, qColMajor ? 1 : 0, ctx->denseG.p);
   DB_CUDA(cudaGetLastError());
+  if (mixedMode == 1) return rotate_mixed_impl(ctx, X, Nr, 2 * Bw, ctx->denseG.p, false, 1);
+  if (mixedMode == 2) return rotate_mixed_impl(ctx, X, Nr, 2, ctx->denseG.p, false, 3);
   return rotate_real(ctx, X, Nr, ctx->denseG.p, false);
 }
 
@@ -647,49 +651,6 @@ static int dense_eigh_cplx(dftfe_b200_ctx *ctx, double *A, int N, double *W) {
   return dense_check_info(ctx, "eigendecomposition of the projected Hamiltonian (cusolverDnZheevd)");
 }
 
-// complex build of rayleighRitzGEP / CGS+RR: S = X^H X = L L^H, Hs = L^-1 Hp L^-H = Q' D Q'^H, X <- X L^-H Q'
-static int rr_cplx(dftfe_b200_ctx *ctx, double *X, int N, double *eig_h, bool cgsFirst) {
-  const size_t nn = (size_t)N * N * 2;
-  DB_TRY(ctx->denseA.alloc(nn));
-  DB_TRY(ctx->denseB.alloc(nn));
-  DB_TRY(ctx->eigDev.alloc(N));
-  double *S = ctx->denseA.p, *Hp = ctx->denseB.p;
-  cuDoubleComplex *Sz = reinterpret_cast<cuDoubleComplex *>(S), *Hz = reinterpret_cast<cuDoubleComplex *>(Hp);
-  const cuDoubleComplex one = make_cuDoubleComplex(1.0, 0.0);
-  DB_TRY(xtx_impl(ctx, X, N, S));
-  DB_TRY(dense_cholesky_cplx(ctx, S, N));
-  DB_CUBLAS(cublasSetStream(ctx->cublas, ctx->stream));
-  if (cgsFirst) {
-    // X <- X L^-H, then plain RR
-    std::vector<double> eye(nn, 0.0);
-    for (int i = 0; i < N; ++i) eye[((size_t)i * N + i) * 2] = 1.0;
-    DB_CUDA(cudaMemcpyAsync(Hp, eye.data(), nn * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-    DB_CUDA(cudaStreamSynchronize(ctx->stream));
-    ctx->launches += 1;
-    DB_CUBLAS(cublasZtrsm(ctx->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_C, CUBLAS_DIAG_NON_UNIT, N,
-                          N, &one, Sz, N, Hz, N));
-    DB_TRY(rotate_impl(ctx, X, N, Hp, true));
-    DB_TRY(xthx_impl(ctx, X, N, Hp));
-    DB_TRY(dense_eigh_cplx(ctx, Hp, N, ctx->eigDev.p));
-    DB_TRY(rotate_impl(ctx, X, N, Hp, true));
-  } else {
-    DB_TRY(xthx_impl(ctx, X, N, Hp));
-    DB_CUBLAS(cublasSetStream(ctx->cublas, ctx->stream));
-    ctx->launches += 3;
-    DB_CUBLAS(cublasZtrsm(ctx->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, N,
-                          N, &one, Sz, N, Hz, N));
-    DB_CUBLAS(cublasZtrsm(ctx->cublas, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_C, CUBLAS_DIAG_NON_UNIT,
-                          N, N, &one, Sz, N, Hz, N));
-    DB_TRY(dense_eigh_cplx(ctx, Hp, N, ctx->eigDev.p));
-    DB_CUBLAS(cublasZtrsm(ctx->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_C, CUBLAS_DIAG_NON_UNIT, N,
-                          N, &one, Sz, N, Hz, N));
-    DB_TRY(rotate_impl(ctx, X, N, Hp, true));
-  }
-  DB_CUDA(cudaMemcpyAsync(eig_h, ctx->eigDev.p, N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
-  DB_CUDA(cudaStreamSynchronize(ctx->stream));
-  return 0;
-}
-
 // Which pieces run in mixed precision (dftParameters::useMixedPrec*, all gated by useMixedPrecOverall) and the
 // number of "core" states whose XtHX blocks may be FP32 (numCoreWfcXtHX / Noc).
 struct RRFlags {
@@ -701,13 +662,72 @@ struct RRFlags {
   int nCore = 0;
 };
 
+// complex results: column-major interleaved, like xtx_impl / xthx_impl
 static int overlap_any(dftfe_b200_ctx *ctx, const double *X, int N, double *S, bool mixed, bool commOnly = false) {
-  return (mixed && !ctx->cplx) ? xtx_mixed_impl(ctx, X, N, S, commOnly) : xtx_impl(ctx, X, N, S);
+  if (!mixed) return xtx_impl(ctx, X, N, S);
+  const int Bw = std::min(ctx->B, N);
+  if (!ctx->cplx) return xtx_mixed_impl(ctx, X, N, Bw, S, commOnly);
+  // real 2N x 2N Gram matrix of the interleaved storage in mixed precision, then S = its complex combination
+  DB_TRY(ctx->denseG.alloc((size_t)4 * N * N));
+  DB_TRY(xtx_mixed_impl(ctx, X, 2 * N, 2 * Bw, ctx->denseG.p, commOnly));
+  ctx->launches += 1;
+  cplx_combine_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(ctx->denseG.p, N, S, 0);
+  DB_CUDA(cudaGetLastError());
+  return 0;
 }
 static int projham_any(dftfe_b200_ctx *ctx, const double *X, int N, double *Hp, bool mixed, int nCore,
                        bool commOnly = false) {
-  return (mixed && !ctx->cplx && nCore > 0) ? xthx_mixed_impl(ctx, X, N, nCore, Hp, commOnly)
-                                            : xthx_impl(ctx, X, N, Hp);
+  if (!mixed || nCore <= 0) return xthx_impl(ctx, X, N, Hp);
+  if (!ctx->cplx) return xthx_mixed_impl(ctx, X, N, nCore, Hp, commOnly);
+  DB_TRY(ctx->denseG.alloc((size_t)4 * N * N));
+  DB_TRY(xthx_mixed_impl(ctx, X, N, nCore, ctx->denseG.p, commOnly));
+  ctx->launches += 1;
+  cplx_combine_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(ctx->denseG.p, N, Hp, 1);
+  DB_CUDA(cudaGetLastError());
+  return 0;
+}
+
+// complex build of rayleighRitzGEP / CGS+RR: S = X^H X = L L^H, Hs = L^-1 Hp L^-H = Q' D Q'^H, X <- X L^-H Q'
+static int rr_cplx(dftfe_b200_ctx *ctx, double *X, int N, double *eig_h, bool cgsFirst, const RRFlags &f) {
+  const size_t nn = (size_t)N * N * 2;
+  DB_TRY(ctx->denseA.alloc(nn));
+  DB_TRY(ctx->denseB.alloc(nn));
+  DB_TRY(ctx->eigDev.alloc(N));
+  double *S = ctx->denseA.p, *Hp = ctx->denseB.p;
+  cuDoubleComplex *Sz = reinterpret_cast<cuDoubleComplex *>(S), *Hz = reinterpret_cast<cuDoubleComplex *>(Hp);
+  const cuDoubleComplex one = make_cuDoubleComplex(1.0, 0.0);
+  DB_TRY(overlap_any(ctx, X, N, S, f.mpOverlap, f.commOnly));
+  DB_TRY(dense_cholesky_cplx(ctx, S, N));
+  DB_CUBLAS(cublasSetStream(ctx->cublas, ctx->stream));
+  if (cgsFirst) {
+    // X <- X L^-H, then plain RR
+    std::vector<double> eye(nn, 0.0);
+    for (int i = 0; i < N; ++i) eye[((size_t)i * N + i) * 2] = 1.0;
+    DB_CUDA(cudaMemcpyAsync(Hp, eye.data(), nn * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+    DB_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->launches += 1;
+    DB_CUBLAS(cublasZtrsm(ctx->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_C, CUBLAS_DIAG_NON_UNIT, N,
+                          N, &one, Sz, N, Hz, N));
+    DB_TRY(rotate_impl(ctx, X, N, Hp, true, f.mpCgsRot ? 1 : 0));
+    DB_TRY(projham_any(ctx, X, N, Hp, f.mpXtHX, f.nCore, f.commOnly));
+    DB_TRY(dense_eigh_cplx(ctx, Hp, N, ctx->eigDev.p));
+    DB_TRY(rotate_impl(ctx, X, N, Hp, true, f.mpRRRot ? 2 : 0));
+  } else {
+    DB_TRY(xthx_impl(ctx, X, N, Hp));
+    DB_CUBLAS(cublasSetStream(ctx->cublas, ctx->stream));
+    ctx->launches += 3;
+    DB_CUBLAS(cublasZtrsm(ctx->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_N, CUBLAS_DIAG_NON_UNIT, N,
+                          N, &one, Sz, N, Hz, N));
+    DB_CUBLAS(cublasZtrsm(ctx->cublas, CUBLAS_SIDE_RIGHT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_C, CUBLAS_DIAG_NON_UNIT,
+                          N, N, &one, Sz, N, Hz, N));
+    DB_TRY(dense_eigh_cplx(ctx, Hp, N, ctx->eigDev.p));
+    DB_CUBLAS(cublasZtrsm(ctx->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_C, CUBLAS_DIAG_NON_UNIT, N,
+                          N, &one, Sz, N, Hz, N));
+    DB_TRY(rotate_impl(ctx, X, N, Hp, true, f.mpRRRot ? 2 : 0));
+  }
+  DB_CUDA(cudaMemcpyAsync(eig_h, ctx->eigDev.p, N * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  DB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
 }
 
 static int identity_to(dftfe_b200_ctx *ctx, double *A, int N) {
@@ -721,7 +741,7 @@ static int identity_to(dftfe_b200_ctx *ctx, double *A, int N) {
 
 // rayleighRitzGEP (src/linAlg/rayleighRitzDevice.cc:355-819)
 static int rr_gep(dftfe_b200_ctx *ctx, double *X, int N, double *eig_h, const RRFlags &f = RRFlags()) {
-  if (ctx->cplx) return rr_cplx(ctx, X, N, eig_h, false);
+  if (ctx->cplx) return rr_cplx(ctx, X, N, eig_h, false, f);
   const size_t nn = (size_t)N * N;
   DB_TRY(ctx->denseA.alloc(nn));
   DB_TRY(ctx->denseB.alloc(nn));
@@ -769,7 +789,7 @@ static int cgs_orthogonalise(dftfe_b200_ctx *ctx, double *X, int N, const RRFlag
 // pseudoGramSchmidtOrthogonalization + rayleighRitz
 // (src/linAlg/pseudoGSDevice.cc:81-463, src/linAlg/rayleighRitzDevice.cc:81-353)
 static int cgs_rr(dftfe_b200_ctx *ctx, double *X, int N, double *eig_h, const RRFlags &f = RRFlags()) {
-  if (ctx->cplx) return rr_cplx(ctx, X, N, eig_h, true);
+  if (ctx->cplx) return rr_cplx(ctx, X, N, eig_h, true, f);
   DB_TRY(ctx->eigDev.alloc(N));
   DB_TRY(cgs_orthogonalise(ctx, X, N, f));
   double *Hp = ctx->denseB.p;
@@ -797,7 +817,7 @@ static int rr_spectrum_split(dftfe_b200_ctx *ctx, double *X, double *XFrac, int 
     Hp = ctx->denseB.p;
     cuDoubleComplex *Sz = reinterpret_cast<cuDoubleComplex *>(S), *Hz = reinterpret_cast<cuDoubleComplex *>(Hp);
     const cuDoubleComplex one = make_cuDoubleComplex(1.0, 0.0);
-    DB_TRY(xtx_impl(ctx, X, N, S));
+    DB_TRY(overlap_any(ctx, X, N, S, f.mpOverlap, f.commOnly));
     DB_TRY(dense_cholesky_cplx(ctx, S, N));
     std::vector<double> eye(nn, 0.0);
     for (int i = 0; i < N; ++i) eye[((size_t)i * N + i) * 2] = 1.0;
@@ -807,8 +827,8 @@ static int rr_spectrum_split(dftfe_b200_ctx *ctx, double *X, double *XFrac, int 
     ctx->launches += 1;
     DB_CUBLAS(cublasZtrsm(ctx->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_C, CUBLAS_DIAG_NON_UNIT, N,
                           N, &one, Sz, N, Hz, N));
-    DB_TRY(rotate_impl(ctx, X, N, Hp, true));
-    DB_TRY(xthx_impl(ctx, X, N, Hp));
+    DB_TRY(rotate_impl(ctx, X, N, Hp, true, f.mpCgsRot ? 1 : 0));
+    DB_TRY(projham_any(ctx, X, N, Hp, f.mpXtHX, Noc, f.commOnly));
     DB_TRY(dense_eigh_cplx(ctx, Hp, N, ctx->eigDev.p));
   } else {
     DB_TRY(cgs_orthogonalise(ctx, X, N, f));
@@ -1090,7 +1110,7 @@ static int solve_no_rr_impl(dftfe_b200_ctx *ctx, double *X, int N, const dftfe_b
       cuDoubleComplex *Sz = reinterpret_cast<cuDoubleComplex *>(ctx->denseA.p);
       cuDoubleComplex *Uz = reinterpret_cast<cuDoubleComplex *>(ctx->denseB.p);
       const cuDoubleComplex one = make_cuDoubleComplex(1.0, 0.0);
-      DB_TRY(xtx_impl(ctx, X, N, ctx->denseA.p));
+      DB_TRY(overlap_any(ctx, X, N, ctx->denseA.p, f.mpOverlap, f.commOnly));
       DB_TRY(dense_cholesky_cplx(ctx, ctx->denseA.p, N));
       std::vector<double> eye(nn, 0.0);
       for (int i = 0; i < N; ++i) eye[((size_t)i * N + i) * 2] = 1.0;
@@ -1100,7 +1120,7 @@ static int solve_no_rr_impl(dftfe_b200_ctx *ctx, double *X, int N, const dftfe_b
       ctx->launches += 1;
       DB_CUBLAS(cublasZtrsm(ctx->cublas, CUBLAS_SIDE_LEFT, CUBLAS_FILL_MODE_LOWER, CUBLAS_OP_C, CUBLAS_DIAG_NON_UNIT, N,
                             N, &one, Sz, N, Uz, N));
-      DB_TRY(rotate_impl(ctx, X, N, ctx->denseB.p, true));
+      DB_TRY(rotate_impl(ctx, X, N, ctx->denseB.p, true, f.mpCgsRot ? 1 : 0));
     } else {
       DB_TRY(cgs_orthogonalise(ctx, X, N, f));
     }

@@ -463,8 +463,17 @@ def rayleigh_ritz(ranks, X, block: int):
 
 
 # --------------------------------------------------------------------------
-# mixed-precision projections / rotations and spectrum splitting (real build)
+# mixed-precision projections / rotations and spectrum splitting (real and complex build: the reference's
+# dataTypes::numberFP32 is float / complex<float>)
 # --------------------------------------------------------------------------
+
+def _f32_of(dtype):
+    return np.complex64 if np.issubdtype(dtype, np.complexfloating) else np.float32
+
+
+def _hermitian_from_lower(A):
+    return np.tril(A) + np.tril(A, -1).conj().T
+
 
 def xtx_mixed(ranks, X, block: int, comm_only: bool = False) -> np.ndarray:
     """fillParallelOverlapMatMixedPrecScalapack (linearAlgebraOperationsDevice.cc:3543-3798): per column block
@@ -473,23 +482,24 @@ def xtx_mixed(ranks, X, block: int, comm_only: bool = False) -> np.ndarray:
     comm_only = fillParallelOverlapMatMixedPrecCommunScalapackAsyncComputeCommun (:4233-4608): every rank's
     partial block is computed in FP64 and only rounded to FP32 for the sum over ranks."""
     N = X[0].shape[1]
-    S = np.zeros((N, N))
+    f32 = _f32_of(X[0].dtype)
+    S = np.zeros((N, N), dtype=X[0].dtype)
     Xo = _owned(ranks, X)
-    Xs = [x.astype(np.float32) for x in Xo]
+    Xs = [x.astype(f32) for x in Xo]
     for j in range(0, N, block):
         B = min(block, N - j)
         dp = 0
-        sp = np.zeros((N - j - B, B), dtype=np.float32)
+        sp = np.zeros((N - j - B, B), dtype=f32)
         for x, xs in zip(Xo, Xs):
-            dp = dp + x[:, j:j + B].T @ x[:, j:j + B]
+            dp = dp + x[:, j:j + B].conj().T @ x[:, j:j + B]
             if N - j - B > 0:
                 if comm_only:
-                    sp = sp + (x[:, j + B:].T @ x[:, j:j + B]).astype(np.float32)
+                    sp = sp + (x[:, j + B:].conj().T @ x[:, j:j + B]).astype(f32)
                 else:
-                    sp = sp + xs[:, j + B:].T @ xs[:, j:j + B]
+                    sp = sp + xs[:, j + B:].conj().T @ xs[:, j:j + B]
         S[j:j + B, j:j + B] = dp
         S[j + B:, j:j + B] = sp
-    return np.tril(S) + np.tril(S, -1).T
+    return _hermitian_from_lower(S)
 
 
 def xthx_mixed(ranks, X, block: int, n_core: int, comm_only: bool = False) -> np.ndarray:
@@ -497,24 +507,25 @@ def xthx_mixed(ranks, X, block: int, n_core: int, comm_only: bool = False) -> np
     the first ``n_core`` states are computed entirely in FP32 (FP32 copy of X times the FP32-rounded H~X block,
     FP32 sum over ranks), the others in FP64."""
     N = X[0].shape[1]
+    f32 = _f32_of(X[0].dtype)
     HXf = apply_HX_blocked(ranks, X, block)
-    Hp = np.zeros((N, N))
+    Hp = np.zeros((N, N), dtype=X[0].dtype)
     Xo, Ho = _owned(ranks, X), _owned(ranks, HXf)
     for j in range(0, N, block):
         B = min(block, N - j)
         if j + B <= n_core:
-            acc = np.zeros((N - j, B), dtype=np.float32)
+            acc = np.zeros((N - j, B), dtype=f32)
             for x, h in zip(Xo, Ho):
                 if comm_only:   # XtHXMixedPrecCommunOverlapComputeCommun (:5082-5536): FP64 GEMM, FP32 on the wire
-                    acc = acc + (x[:, j:].T @ h[:, j:j + B]).astype(np.float32)
+                    acc = acc + (x[:, j:].conj().T @ h[:, j:j + B]).astype(f32)
                 else:
-                    acc = acc + x[:, j:].astype(np.float32).T @ h[:, j:j + B].astype(np.float32)
+                    acc = acc + x[:, j:].astype(f32).conj().T @ h[:, j:j + B].astype(f32)
         else:
             acc = 0
             for x, h in zip(Xo, Ho):
-                acc = acc + x[:, j:].T @ h[:, j:j + B]
+                acc = acc + x[:, j:].conj().T @ h[:, j:j + B]
         Hp[j:, j:j + B] = acc
-    return np.tril(Hp) + np.tril(Hp, -1).T
+    return _hermitian_from_lower(Hp)
 
 
 def subspace_rotation_cgs_mixed(ranks, X, U: np.ndarray, block: int):
@@ -523,28 +534,30 @@ def subspace_rotation_cgs_mixed(ranks, X, U: np.ndarray, block: int):
     N = U.shape[0]
     blk = np.arange(N) // block
     on = blk[:, None] == blk[None, :]
+    f32 = _f32_of(X[0].dtype)
     Ud = np.where(on, U, 0.0)
-    Us = np.where(on, 0.0, U).astype(np.float32)
+    Us = np.where(on, 0.0, U).astype(f32)
     for rp, x in zip(ranks, X):
         xo = x[:rp.M]
-        x[:rp.M] = xo @ Ud + (xo.astype(np.float32) @ Us).astype(np.float64)
+        x[:rp.M] = xo @ Ud + (xo.astype(f32) @ Us).astype(x.dtype)
 
 
 def subspace_rotation_rr_mixed(ranks, X, Q: np.ndarray):
     """subspaceRotationRRMixedPrecScalapack (linearAlgebraOperationsDevice.cc:2660-3076):
     X <- X diag(Q) (FP64, computeDiagQTimesXKernel) + X_fp32 (Q - diag Q)_fp32."""
+    f32 = _f32_of(X[0].dtype)
     d = np.diag(Q).copy()
-    Qs = (Q - np.diag(d)).astype(np.float32)
+    Qs = (Q - np.diag(d)).astype(f32)
     for rp, x in zip(ranks, X):
         xo = x[:rp.M]
-        x[:rp.M] = xo * d[None, :] + (xo.astype(np.float32) @ Qs).astype(np.float64)
+        x[:rp.M] = xo * d[None, :] + (xo.astype(f32) @ Qs).astype(x.dtype)
 
 
 def rayleigh_ritz_gep_spectrum_split(ranks, X, block: int, n_core: int, mixed=()):
     """rayleighRitzGEPSpectrumSplitDirect (src/linAlg/rayleighRitzDevice.cc:821-1454): S = X^H X = L L^H,
     X <- X L^-H (kept, NOT rotated), Hp = X^H H~ X, only eigenpairs n_core..N-1 of Hp are computed,
     XFrac = X Q[:, n_core:].  Returns (eigenvalues[N - n_core], XFrac list).  ``mixed``: subset of
-    {"cgs_o", "cgs_sr", "xthx"} (real build)."""
+    {"cgs_o", "cgs_sr", "xthx"}."""
     mixed = set(mixed)
     S = xtx_mixed(ranks, X, block) if "cgs_o" in mixed else xtx(ranks, X)
     L = np.linalg.cholesky(S)

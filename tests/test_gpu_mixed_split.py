@@ -167,6 +167,55 @@ def test_mixed_precision_projections_and_rotations(capi):
     op.close()
 
 
+def test_complex_mixed_precision_projections_and_rotations(capi):
+    """Complex build of the mixed-precision projections / rotations (the reference's numberFP32 = complex<float>
+    blocks): here through the real view of the interleaved storage - FP64 (complex) diagonal blocks exact, FP32
+    blocks at FP32 accuracy against the oracle's complex64 restatement."""
+    from oracle import chfsi_oracle as O
+
+    p, B, N, Noc = 2, 32, 96, 64
+    mesh, ranks = make_problem(p, (4, 3, 3), 1.3, (True, True, True), kpoint=(0.15, -0.2, 0.3))
+    rp = ranks[0]
+    op = capi.Operator(rp, B, complex=True)
+    op.set_cell_hamiltonian(rp.H)
+    X = scatter_to_ranks(ranks, random_global(mesh, N, seed=5, cplx=True), loewdin=True)
+    X_d = _dev(X[0][:rp.M])
+    out = torch.full((N, N), float("nan"), dtype=torch.complex128, device="cuda")
+    S64 = O.xtx(ranks, X)
+    for flag, comm_only, tol in ((True, False, TOL_FP32_GEMM), (2, True, 2e-7)):
+        op.XtX(X_d, out, mixedPrec=flag)
+        S_gpu = out.cpu().numpy()
+        assert _relerr(S_gpu, O.xtx_mixed(ranks, X, B, comm_only=comm_only)) < tol
+        for j in range(0, N, B):
+            assert _relerr(S_gpu[j:j + B, j:j + B], S64[j:j + B, j:j + B]) < 1e-13
+        assert np.abs(S_gpu - S64).max() > 0.0
+        assert np.array_equal(S_gpu, S_gpu.conj().T)
+
+    H64 = O.xthx(ranks, [x.copy() for x in X], B)
+    for flag, comm_only, tol in ((True, False, TOL_FP32_GEMM), (2, True, 2e-7)):
+        op.XtHX(X_d, out, Noc=Noc, mixedPrec=flag)
+        H_gpu = out.cpu().numpy()
+        H_ref = O.xthx_mixed(ranks, [x.copy() for x in X], B, Noc, comm_only=comm_only)
+        assert _relerr(np.tril(H_gpu), np.tril(H_ref)) < tol
+        assert _relerr(np.tril(H_gpu[Noc:, Noc:]), np.tril(H64[Noc:, Noc:])) < 1e-12
+        assert np.abs(np.tril(H_gpu[:, :Noc] - H64[:, :Noc])).max() > 0.0
+
+    rng = np.random.default_rng(2)
+    Q = np.linalg.qr(rng.normal(size=(N, N)) + 1j * rng.normal(size=(N, N)))[0]
+    U = np.triu(rng.normal(size=(N, N)) + 1j * rng.normal(size=(N, N))) / np.sqrt(N) + np.eye(N)
+    for mode, mat, ref_fn in ((1, U, lambda Xc: O.subspace_rotation_cgs_mixed(ranks, Xc, U, B)),
+                              (2, Q, lambda Xc: O.subspace_rotation_rr_mixed(ranks, Xc, Q))):
+        Xr = X_d.clone()
+        op.subspaceRotation(Xr, _dev(mat), mixedMode=mode)
+        Xc = [x.copy() for x in X]
+        ref_fn(Xc)
+        exact = X[0][:rp.M] @ mat
+        got = Xr.cpu().numpy()
+        assert _relerr(got, Xc[0][:rp.M]) < TOL_FP32_GEMM, mode
+        assert 0.0 < _relerr(got, exact) < 1e-5, mode
+    op.close()
+
+
 @pytest.mark.parametrize("mixed", [(), ("cheby", "cgs_o", "cgs_sr", "xthx")])
 def test_spectrum_split_solve(capi, mixed):
     """rayleighRitzGEPSpectrumSplitDirect through solve(): top Nfr eigenpairs, XFrac, X left orthonormal."""
@@ -385,7 +434,8 @@ def test_complex_nonlocal_kpoints_and_spin_sets(capi):
     assert _relerr(a, b) > 1e-3
 
 
-def test_complex_spectrum_split(capi):
+@pytest.mark.parametrize("mixed", [(), ("cgs_o", "cgs_sr", "xthx")])
+def test_complex_spectrum_split(capi, mixed):
     from oracle import chfsi_oracle as O
 
     p, B, N, Noc = 2, 8, 24, 8
@@ -398,16 +448,20 @@ def test_complex_spectrum_split(capi):
     Xo = scatter_to_ranks(ranks, Xg, zero_constrained=False)
     Xd = _dev(Xo[0][:rp.M])
     XF = torch.zeros((rp.M, N - Noc), dtype=torch.complex128, device="cuda")
-    eig, res, ub = solver.solve(Xd, isFirstFilteringCall=True, chebyshevOrder=10, reuseLanczos=True, XFrac=XF)
+    eig, res, ub = solver.solve(Xd, isFirstFilteringCall=True, chebyshevOrder=10, reuseLanczos=True, XFrac=XF,
+                                useMixedPrecOverall=bool(mixed), mixedPrec=mixed)
     a0, blow, bup = solver.spectrumBounds()
-    ev_ref, res_ref, XF_ref = O.solve(ranks, Xo, B, 10, (a0, blow, bup), n_core=Noc)
-    assert np.abs(eig - ev_ref).max() < 1e-8
-    assert np.abs(res - res_ref).max() < 1e-7
+    ev_ref, res_ref, XF_ref = O.solve(ranks, Xo, B, 10, (a0, blow, bup), n_core=Noc, mixed=mixed)
+    # mixed: FP32 roundings amplified by cond(X^H X), see test_spectrum_split_solve
+    tol_e, tol_r = (1e-8, 1e-7) if not mixed else (5e-3, 5e-2)
+    assert np.abs(eig - ev_ref).max() < tol_e
+    assert np.abs(res - res_ref).max() < tol_r
     Xn = Xd.cpu().numpy() * rp.sqrtMass[:rp.M, None]
-    assert np.abs(Xn.conj().T @ Xn - np.eye(N)).max() < 1e-10
+    assert np.abs(Xn.conj().T @ Xn - np.eye(N)).max() < (1e-10 if not mixed else 1e-2)
     # XFrac spans the same subspace as the oracle's: projector difference
     F, Fr = XF.cpu().numpy() * rp.sqrtMass[:rp.M, None], XF_ref[0][:rp.M] * rp.sqrtMass[:rp.M, None]
-    assert np.abs(F @ F.conj().T - Fr @ Fr.conj().T).max() < 1e-7
+    if not mixed:
+        assert np.abs(F @ F.conj().T - Fr @ Fr.conj().T).max() < 1e-7
     op.close()
 
 

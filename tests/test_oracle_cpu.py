@@ -335,6 +335,33 @@ def test_mixed_precision_restatements_are_fp32_perturbations():
     assert np.array_equal(a[0], b[0])
 
 
+def test_mixed_precision_restatements_complex_build():
+    """complex build (numberFP32 = complex<float>): same structure - FP64 diagonal blocks / non-core blocks exact,
+    FP32-accurate elsewhere, Hermitian results."""
+    mesh, ranks = make_problem(2, (3, 3, 3), 1.0, (True, True, True), nranks=2, kpoint=(0.2, 0.1, -0.3))
+    N, B = 16, 4
+    X = scatter_to_ranks(ranks, random_global(mesh, N, seed=2, cplx=True), loewdin=True)
+    S, Sm = O.xtx(ranks, X), O.xtx_mixed(ranks, X, B)
+    assert np.iscomplexobj(Sm) and np.array_equal(Sm, Sm.conj().T)
+    for j in range(0, N, B):
+        assert np.abs(np.tril(S[j:j + B, j:j + B] - Sm[j:j + B, j:j + B])).max() < 1e-13 * np.abs(S).max()
+    assert 0.0 < np.abs(S - Sm).max() / np.abs(S).max() < 1e-6
+    H = O.xthx(ranks, [x.copy() for x in X], B)
+    Hm = O.xthx_mixed(ranks, [x.copy() for x in X], B, 2 * B)
+    assert np.abs(np.tril(H[2 * B:, 2 * B:] - Hm[2 * B:, 2 * B:])).max() < 1e-12 * np.abs(H).max()
+    assert 0.0 < np.abs(H - Hm).max() / np.abs(H).max() < 1e-5
+    rng = np.random.default_rng(0)
+    Q = np.linalg.qr(rng.normal(size=(N, N)) + 1j * rng.normal(size=(N, N)))[0]
+    Xa, Xb = ([x.copy() for x in X] for _ in range(2))
+    O.subspace_rotation_rr_mixed(ranks, Xa, Q)
+    O.subspace_rotation_cgs_mixed(ranks, Xb, Q, B)
+    for rp, xa, xb, x in zip(ranks, Xa, Xb, X):
+        exact = x[:rp.M] @ Q
+        for y in (xa, xb):
+            assert y.dtype == np.complex128
+            assert 0.0 < np.abs(y[:rp.M] - exact).max() / np.abs(exact).max() < 1e-5
+
+
 def test_spectrum_split_and_no_rr_statements():
     mesh, ranks = make_problem(3, (3, 3, 2), 1.4, (True, True, True), nranks=2)
     N, B, Noc = 16, 8, 8
