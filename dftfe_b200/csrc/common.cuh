@@ -273,6 +273,7 @@ struct dftfe_b200_ctx {
     int nAtoms = 0, totalProj = 0;
     int64_t nRows = 0;
     int nAtomColours = 0, maxProj = 0;            // atoms that share a row have different colours
+    int maxAtomRows = 0;                          // rows in the largest atom support
     std::vector<int32_t> colourStart_h;
     dftfe_b200::DevBuf<int32_t> colourAtoms;      // atom ids grouped by colour
     dftfe_b200::DevBuf<int32_t> projOffset, atomRowStart, entProj;
@@ -283,6 +284,7 @@ struct dftfe_b200_ctx {
   std::map<int, NonlocalSet> nlSets;
   NonlocalSet *nl = nullptr;  // active set (nullptr: no non-local term)
   dftfe_b200::DevBuf<double> nlProj[2];  // projector block per lane: totalProj x B (x 2 complex), all-reduced
+  dftfe_b200::DevBuf<double> nlPart[2];  // per-lane partial blocks of the row-sliced projection (few atoms)
   // --- solver state / scratch
   dftfe_b200::DevBuf<double> blockX, blockY;      // (M+G)*B
   dftfe_b200::DevBuf<double> blockX2;             // second block buffer (host-pipelined filter; lane 1)

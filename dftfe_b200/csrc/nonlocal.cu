@@ -44,8 +44,9 @@ __global__ void __launch_bounds__(NL_COLS *NL_RG)
 nl_project_kernel(const double *__restrict__ x, int ncols, int ldx, const int32_t *__restrict__ atomRowStart,
                   const uint32_t *__restrict__ atomRows, const int64_t *__restrict__ atomValStart,
                   const double *__restrict__ vals, const int32_t *__restrict__ projOffset,
-                  const double *__restrict__ rowScale, double *__restrict__ proj) {
+                  const double *__restrict__ rowScale, double *__restrict__ proj, size_t sliceStride) {
   __shared__ double red[NL_RG][NL_MAXP][NL_COLS + 1];
+  proj += blockIdx.z * sliceStride;  // row slice z of every atom -> its own partial block (summed in slice order)
   const int a = blockIdx.x;
   const int col = blockIdx.y * NL_COLS + threadIdx.x;
   const int rg = threadIdx.y;
@@ -57,7 +58,7 @@ nl_project_kernel(const double *__restrict__ x, int ncols, int ldx, const int32_
 #pragma unroll
   for (int p = 0; p < NL_MAXP; ++p) acc[p] = 0.0;
   if (col < ncols) {
-    for (int r = r0 + rg; r < r1; r += NL_RG) {
+    for (int r = r0 + blockIdx.z * NL_RG + rg; r < r1; r += NL_RG * gridDim.z) {
       const uint32_t row = atomRows[r];
       double xv = x[(size_t)row * ldx + col];
       double xp = CM == 2 ? x[(size_t)row * ldx + (col ^ 1)] : 0.0;
@@ -131,8 +132,9 @@ __global__ void __launch_bounds__(NLV_WARPS * 32)
 nl_project_vec_kernel(const double *__restrict__ x, int ncols, int ldx, const int32_t *__restrict__ atomRowStart,
                       const uint32_t *__restrict__ atomRows, const int64_t *__restrict__ atomValStart,
                       const double *__restrict__ vals, const int32_t *__restrict__ projOffset,
-                      const double *__restrict__ rowScale, double *__restrict__ proj) {
+                      const double *__restrict__ rowScale, double *__restrict__ proj, size_t sliceStride) {
   __shared__ double2 red[NLV_WARPS][PMAX][32];
+  proj += blockIdx.z * sliceStride;
   const int a = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int col = blockIdx.y * 64 + lane * 2;
@@ -143,7 +145,8 @@ nl_project_vec_kernel(const double *__restrict__ x, int ncols, int ldx, const in
 #pragma unroll
   for (int p = 0; p < PMAX; ++p) acc[p] = make_double2(0.0, 0.0);
   if (col < ncols) {
-    for (int rb = r0 + warp * NLV_UNROLL; rb < r1; rb += NLV_WARPS * NLV_UNROLL) {
+    for (int rb = r0 + (blockIdx.z * NLV_WARPS + warp) * NLV_UNROLL; rb < r1;
+         rb += gridDim.z * NLV_WARPS * NLV_UNROLL) {
       double2 xv[NLV_UNROLL];
       double sc[NLV_UNROLL];
 #pragma unroll
@@ -193,6 +196,16 @@ nl_project_vec_kernel(const double *__restrict__ x, int ncols, int ldx, const in
       }
       *reinterpret_cast<double2 *>(proj + (size_t)(projOffset[a] + p) * ncols + col) = s;
     }
+}
+
+// proj[i] = sum over the row slices z, in slice order, of part[z][i]
+__global__ void nl_sum_slices_kernel(const double *__restrict__ part, size_t stride, int slices,
+                                     double *__restrict__ proj, size_t count) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < count; i += (size_t)gridDim.x * blockDim.x) {
+    double s = part[i];
+    for (int z = 1; z < slices; ++z) s += part[(size_t)z * stride + i];
+    proj[i] = s;
+  }
 }
 
 // y[row, :] += s * out(row) * sum_p C_a[row][p] V[a,p] proj[(a,p), :] for the atoms of ONE colour (atoms of a colour
@@ -357,7 +370,11 @@ int nonlocal_setup(dftfe_b200_ctx *ctx, int kpt, int32_t nAtoms, const int32_t *
   dftfe_b200_ctx::NonlocalSet &ns = ctx->nlSets[kpt];
   ns.nAtomColours = nAtomColours;
   ns.maxProj = 0;
-  for (int a = 0; a < nAtoms; ++a) ns.maxProj = std::max(ns.maxProj, (int)nProj[a]);
+  ns.maxAtomRows = 0;
+  for (int a = 0; a < nAtoms; ++a) {
+    ns.maxProj = std::max(ns.maxProj, (int)nProj[a]);
+    ns.maxAtomRows = std::max(ns.maxAtomRows, atomRowStart[a + 1] - atomRowStart[a]);
+  }
   ns.colourStart_h = colourStart;
   DB_TRY(ns.colourAtoms.upload(colourAtoms.data(), colourAtoms.size(), ctx->stream));
   ns.nAtoms = nAtoms;
@@ -384,34 +401,49 @@ int nonlocal_project(dftfe_b200_ctx *ctx, const double *x, int ncols, int ldx, c
   const dftfe_b200_ctx::NonlocalSet &ns = *ctx->nl;
   const bool vec = (ncols % 2 == 0) && (ldx % 2 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
                    !ctx->force_scalar_row_kernels && ns.maxProj <= 16;
-  if (vec) {
-    ProfScope ps(ctx, "nonlocal");
-    dim3 grid(ns.nAtoms, (ncols + 63) / 64);
-#define DB_NLP(CM, PM)                                                                                               \
+  // few atoms (small systems, many ranks): the rows of an atom are dealt over `slices` CTAs whose partial blocks are
+  // summed in slice order, so that the launch fills the SMs
+  const int chunks = (ncols + 63) / 64;
+  const int wantSlices = (4 * ctx->num_sms + ns.nAtoms * chunks - 1) / std::max(1, ns.nAtoms * chunks);
+  const int slices = std::max(1, std::min({32, wantSlices, ns.maxAtomRows / 64}));
+  const size_t count = (size_t)ns.totalProj * ncols;
+  double *out = ctx->nlProj[ctx->lane].p;
+  if (slices > 1) {
+    DB_TRY(ctx->nlPart[ctx->lane].alloc((size_t)slices * count));
+    out = ctx->nlPart[ctx->lane].p;
+  }
+  {
+    ProfScope ps(ctx, "nonlocal", slices > 1 ? 2 : 1);
+    if (vec) {
+      dim3 grid(ns.nAtoms, chunks, slices);
+#define DB_NLP(CM, PM)                                                                                                 \
   nl_project_vec_kernel<CM, PM><<<grid, NLV_WARPS * 32, 0, ctx->stream>>>(x, ncols, ldx, ns.atomRowStart.p, ns.atomRows.p, \
                                                                          ns.atomValStart.p, ns.vals.p, ns.projOffset.p,  \
-                                                                         rowScaleIn, ctx->nlProj[ctx->lane].p)
-    if (ctx->cplx) {
-      if (ns.maxProj <= 8) DB_NLP(2, 8); else DB_NLP(2, 16);
-    } else {
-      if (ns.maxProj <= 8) DB_NLP(1, 8); else DB_NLP(1, 16);
-    }
+                                                                         rowScaleIn, out, count)
+      if (ctx->cplx) {
+        if (ns.maxProj <= 8) DB_NLP(2, 8); else DB_NLP(2, 16);
+      } else {
+        if (ns.maxProj <= 8) DB_NLP(1, 8); else DB_NLP(1, 16);
+      }
 #undef DB_NLP
-    DB_CUDA(cudaGetLastError());
-  } else {
-    ProfScope ps(ctx, "nonlocal");
-    dim3 grid(ns.nAtoms, (ncols + NL_COLS - 1) / NL_COLS), block(NL_COLS, NL_RG);
-    if (ctx->cplx)
-      nl_project_kernel<2><<<grid, block, 0, ctx->stream>>>(x, ncols, ldx, ns.atomRowStart.p, ns.atomRows.p,
-                                                            ns.atomValStart.p, ns.vals.p, ns.projOffset.p,
-                                                            rowScaleIn, ctx->nlProj[ctx->lane].p);
-    else
-      nl_project_kernel<1><<<grid, block, 0, ctx->stream>>>(x, ncols, ldx, ns.atomRowStart.p, ns.atomRows.p,
-                                                            ns.atomValStart.p, ns.vals.p, ns.projOffset.p,
-                                                            rowScaleIn, ctx->nlProj[ctx->lane].p);
+    } else {
+      dim3 grid(ns.nAtoms, (ncols + NL_COLS - 1) / NL_COLS, slices), block(NL_COLS, NL_RG);
+      if (ctx->cplx)
+        nl_project_kernel<2><<<grid, block, 0, ctx->stream>>>(x, ncols, ldx, ns.atomRowStart.p, ns.atomRows.p,
+                                                              ns.atomValStart.p, ns.vals.p, ns.projOffset.p,
+                                                              rowScaleIn, out, count);
+      else
+        nl_project_kernel<1><<<grid, block, 0, ctx->stream>>>(x, ncols, ldx, ns.atomRowStart.p, ns.atomRows.p,
+                                                              ns.atomValStart.p, ns.vals.p, ns.projOffset.p,
+                                                              rowScaleIn, out, count);
+    }
+    if (slices > 1) {
+      const int grid = (int)std::max<size_t>(1, std::min<size_t>((count + 255) / 256, (size_t)ctx->num_sms * 4));
+      nl_sum_slices_kernel<<<grid, 256, 0, ctx->stream>>>(out, count, slices, ctx->nlProj[ctx->lane].p, count);
+    }
     DB_CUDA(cudaGetLastError());
   }
-  return allreduce_sum(ctx, ctx->nlProj[ctx->lane].p, (size_t)ns.totalProj * ncols);
+  return allreduce_sum(ctx, ctx->nlProj[ctx->lane].p, count);
 }
 
 // y += s * (out o Chat) V proj
