@@ -70,6 +70,7 @@ class SolveParams(C.Structure):
 
 # every symbol include/dftfe_b200.h declares (checked by tests/test_abi.py)
 EXPORTED_SYMBOLS = [
+    "dftfe_b200_density_matrix_first_order_response",
     "dftfe_b200_version", "dftfe_b200_last_error", "dftfe_b200_create", "dftfe_b200_destroy",
     "dftfe_b200_set_stream", "dftfe_b200_sync", "dftfe_b200_build_index_map", "dftfe_b200_set_index_map",
     "dftfe_b200_set_constraints", "dftfe_b200_set_mass", "dftfe_b200_set_ghost_pattern",
@@ -387,11 +388,19 @@ class Operator:
                                                        C.c_int32(which)))
 
     # ---- operatorDFTDeviceClass -------------------------------------------
-    def HX(self, src, dst, scaleFlag: bool, scalar: float, doUnscalingSrc: bool = True, singlePrecCommun: bool = False):
-        """kohnShamDFTOperatorDevice.cc:3765-3860; singlePrecCommun: the FP32-exchange overload (:3609-3761)."""
-        _check(self.lib.dftfe_b200_hx(self.h, _dptr(src), _dptr(dst), C.c_int32(src.shape[1]), C.c_int32(int(scaleFlag)),
-                                      C.c_double(scalar), C.c_int32(int(doUnscalingSrc)),
-                                      C.c_int32(int(singlePrecCommun))))
+    def HX(self, src, dst, scaleFlag: bool, scalar: float, doUnscalingSrc: bool = True, singlePrecCommun: bool = False,
+           onlyHPrimePartForFirstOrderDensityMatResponse: bool = False):
+        """kohnShamDFTOperatorDevice.cc:3765-3860; singlePrecCommun: the FP32-exchange overload (:3609-3761);
+        onlyHPrime...: the selected cell matrices are H', the non-local term is skipped (:3680-3688)."""
+        if onlyHPrimePartForFirstOrderDensityMatResponse:
+            self.set_option("only_h_prime", 1)
+        try:
+            _check(self.lib.dftfe_b200_hx(self.h, _dptr(src), _dptr(dst), C.c_int32(src.shape[1]),
+                                          C.c_int32(int(scaleFlag)), C.c_double(scalar), C.c_int32(int(doUnscalingSrc)),
+                                          C.c_int32(int(singlePrecCommun))))
+        finally:
+            if onlyHPrimePartForFirstOrderDensityMatResponse:
+                self.set_option("only_h_prime", 0)
 
     def HXCheby(self, src, dst, mixPrecFlag: bool = False):
         """kohnShamDFTOperatorDevice.cc:3874-3997; mixPrecFlag: FP32 ghost payloads."""
@@ -426,10 +435,16 @@ class Operator:
         """fillParallelOverlapMat[MixedPrec]Scalapack (linearAlgebraOperationsDevice.cc:3078-3240, 3543-3798)."""
         _check(self.lib.dftfe_b200_xtx(self.h, _dptr(X), C.c_int32(X.shape[1]), _dptr(S), C.c_int32(int(mixedPrec))))
 
-    def XtHX(self, X, Hp, Noc: int = 0, mixedPrec: int = 0):
+    def XtHX(self, X, Hp, Noc: int = 0, mixedPrec: int = 0, onlyHPrimePartForFirstOrderDensityMatResponse: bool = False):
         """kohnShamDFTOperatorDevice.cc:4001-4157; mixedPrec + Noc: XtHXMixedPrecOverlapComputeCommun (:4550-5080)."""
-        _check(self.lib.dftfe_b200_xthx(self.h, _dptr(X), C.c_int32(X.shape[1]), C.c_int32(Noc), _dptr(Hp),
-                                        C.c_int32(int(mixedPrec))))
+        if onlyHPrimePartForFirstOrderDensityMatResponse:
+            self.set_option("only_h_prime", 1)
+        try:
+            _check(self.lib.dftfe_b200_xthx(self.h, _dptr(X), C.c_int32(X.shape[1]), C.c_int32(Noc), _dptr(Hp),
+                                            C.c_int32(int(mixedPrec))))
+        finally:
+            if onlyHPrimePartForFirstOrderDensityMatResponse:
+                self.set_option("only_h_prime", 0)
 
     def subspaceRotation(self, X, Q, mixedMode: int = 0):
         """X <- X Q.  mixedMode 1 / 2: subspaceRotationCGSMixedPrec / RRMixedPrec."""
@@ -512,6 +527,19 @@ class ChebyshevSolver:
         _check(self.op.lib.dftfe_b200_solve_no_rr(self.op.h, _dptr(X), C.c_int32(X.shape[1]), C.byref(p),
                                                   C.c_int32(numberPasses), C.byref(ub)))
         return ub.value
+
+    def densityMatrixEigenBasisFirstOrderResponse(self, X, eigenValues: Sequence[float], fermiEnergy: float,
+                                                  TVal: float, singlePrecLRD: bool = False) -> np.ndarray:
+        """solver .cc:1084-1196: X <- X D (first-order density-matrix response in the eigenbasis) for the H' cell
+        matrices currently selected, non-local term skipped.  Returns densityMatDerFermiEnergy [N]."""
+        N = X.shape[1]
+        e = _np(eigenValues, np.float64)
+        assert e.shape == (N,)
+        out = np.empty(N)
+        _check(self.op.lib.dftfe_b200_density_matrix_first_order_response(
+            self.op.h, _dptr(X), C.c_int32(N), _ptr(e), C.c_double(fermiEnergy), C.c_double(TVal),
+            C.c_int32(int(singlePrecLRD)), _ptr(out)))
+        return out
 
     def solve(self, X, isFirstFilteringCall: bool, computeResidual: bool = True, chebyshevOrder: int = 0,
               isFirstScf: bool = False, isPseudopotential: bool = True, useCgsRR: bool = False,

@@ -261,6 +261,7 @@ struct dftfe_b200_ctx {
   bool force_generic_cell_kernel = false;  // test hook: run the non-persistent kernel
   int reserved_sms = 0;  // option "reserved_sms": SMs the persistent cell kernel leaves free (for NCCL's kernels)
   bool force_scalar_row_kernels = false;   // test hook: scalar fallbacks of the HBM-bound row kernels
+  bool skip_nonlocal = false;              // onlyHPrime applies: the non-local term is left out
   std::map<const void *, int> rowKernelCtasPerSm;  // resident CTAs per SM of each row kernel (occupancy API)
   // one re-tiled set per (k-point, spin) index (reinitkPointSpinIndex, kohnShamDFTOperatorDevice.cc:1033-1058)
   std::map<int, dftfe_b200::DevBuf<double>> Hsets;

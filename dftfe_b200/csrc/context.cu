@@ -691,6 +691,12 @@ int dftfe_b200_set_option(dftfe_b200_ctx *ctx, const char *name, int32_t value) 
     ctx->use_cublas_dense = value != 0;
     return 0;
   }
+  if (std::strcmp(name, "only_h_prime") == 0) {
+    // onlyHPrimePartForFirstOrderDensityMatResponse of HX / XtHX (kohnShamDFTOperatorDevice.cc:3680-3688): the cell
+    // matrices are the caller's H' matrices and the non-local term is skipped
+    ctx->skip_nonlocal = value != 0;
+    return 0;
+  }
   set_error("set_option: unknown option '%s'", name);
   return DFTFE_B200_ERR_INVALID;
 }

@@ -397,7 +397,7 @@ int nonlocal_setup(dftfe_b200_ctx *ctx, int kpt, int32_t nAtoms, const int32_t *
 
 // proj = Chat^H (in o x), all-reduced over ranks
 int nonlocal_project(dftfe_b200_ctx *ctx, const double *x, int ncols, int ldx, const double *rowScaleIn) {
-  if (!ctx->nl) return 0;
+  if (!ctx->nl || ctx->skip_nonlocal) return 0;
   const dftfe_b200_ctx::NonlocalSet &ns = *ctx->nl;
   const bool vec = (ncols % 2 == 0) && (ldx % 2 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0) &&
                    !ctx->force_scalar_row_kernels && ns.maxProj <= 16;
@@ -448,7 +448,7 @@ int nonlocal_project(dftfe_b200_ctx *ctx, const double *x, int ncols, int ldx, c
 
 // y += s * (out o Chat) V proj
 int nonlocal_apply(dftfe_b200_ctx *ctx, double *y, int ncols, int ldx, const double *rowScaleOut, double s) {
-  if (!ctx->nl || ctx->nl->nRows == 0) return 0;
+  if (!ctx->nl || ctx->nl->nRows == 0 || ctx->skip_nonlocal) return 0;
   const dftfe_b200_ctx::NonlocalSet &ns = *ctx->nl;
   const bool vec = (ncols % 2 == 0) && (ldx % 2 == 0) && ((reinterpret_cast<uintptr_t>(y) & 15) == 0) &&
                    !ctx->force_scalar_row_kernels && ns.maxProj <= 16;

@@ -275,6 +275,38 @@ __global__ void scale_copy_kernel(double *__restrict__ y, const double *__restri
     y[i] = alpha * x[i];
 }
 
+// densityMatrixEigenBasisFirstOrderResponse, the N x N step (src/linAlg/rayleighRitzDevice.cc:1559-1668): the recursive
+// Fermi-operator expansion applied to -c H' is an element-wise factor, because every ScaLAPACK operation of the
+// reference (row / column scalings by the x0 recurrences and sums of those) acts on element (i,j) alone:
+//   per level:  D(i,j) <- Y0_i [ (x0_i + x0_j)(1 - 2 x0'_j) + 2 x0'_j ] D(i,j),  Y0 = 1/(2 x0 (x0 - 1) + 1),  x0' = Y0 x0^2
+// on the lower triangle XtHX filled (i >= j), followed by D <- D + D^H with the diagonal halved (:1634-1668).
+// Hp, D: column-major N x N (complex: interleaved); x0: the N start values 0.5 - c (eps_i - mu).
+__global__ void fermi_response_kernel(const double *__restrict__ Hp, int N, int cm, const double *__restrict__ x0,
+                                      double c, int levels, double *__restrict__ D) {
+  const int64_t total = (int64_t)N * N;
+  for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total;
+       idx += (int64_t)gridDim.x * blockDim.x) {
+    const int a = idx % N, b = idx / N;           // element (a, b) of the output
+    const int i = max(a, b), j = min(a, b);        // its lower-triangle source (i, j)
+    double xi = x0[i], xj = x0[j], f = -c;
+    for (int l = 0; l < levels; ++l) {
+      const double yi = 1.0 / (2.0 * xi * (xi - 1.0) + 1.0), yj = 1.0 / (2.0 * xj * (xj - 1.0) + 1.0);
+      const double xin = yi * xi * xi, xjn = yj * xj * xj;
+      f *= yi * ((xi + xj) * (1.0 - 2.0 * xjn) + 2.0 * xjn);
+      xi = xin;
+      xj = xjn;
+    }
+    const int64_t src = (int64_t)i + (int64_t)j * N;
+    if (cm == 1) {
+      D[idx] = f * Hp[src];
+    } else {
+      const double re = f * Hp[2 * src], im = f * Hp[2 * src + 1];
+      D[2 * idx] = re;
+      D[2 * idx + 1] = (a == b) ? 0.0 : (a > b ? im : -im);  // upper = conjugate of lower, real diagonal
+    }
+  }
+}
+
 }  // namespace
 
 static int ensure_block_scratch(dftfe_b200_ctx *ctx) {
@@ -842,6 +874,46 @@ static int rr_spectrum_split(dftfe_b200_ctx *ctx, double *X, double *XFrac, int 
   return 0;
 }
 
+// chebyshevOrthogonalizedSubspaceIterationSolverDevice::densityMatrixEigenBasisFirstOrderResponse (solver .cc:1084-1196
+// -> src/linAlg/rayleighRitzDevice.cc:1456-1737): X <- M^1/2 X;  H'p = X^H H' X with the caller's H' cell matrices and
+// without the non-local term (onlyHPrime);  D = first-order response of the Fermi operator in the eigenbasis
+// (recursive expansion, m = 10 levels);  X <- X D;  X <- M^-1/2 X.  densityMatDerFermiEnergy = beta x0 (1 - x0).
+static int first_order_response_impl(dftfe_b200_ctx *ctx, double *X, int N, const double *eig_h, double fermiEnergy,
+                                     double temperature, bool singlePrec, double *dmDer_h) {
+  const int cm = ctx->cm;
+  const size_t nn = (size_t)N * N * cm;
+  DB_TRY(ctx->denseA.alloc(nn));
+  DB_TRY(ctx->denseB.alloc(nn));
+  DB_TRY(ctx->eigDev.alloc(N));
+  const int levels = 10;
+  const double kb = 3.166811429e-06;  // C_kb, include/constants.h:30 (Ha / K)
+  const double beta = 1.0 / kb / temperature;
+  const double c = std::pow(2.0, -2.0 - levels) * beta;
+  std::vector<double> x0(N);
+  for (int i = 0; i < N; ++i) x0[i] = 0.5 - c * (eig_h[i] - fermiEnergy);
+  DB_CUDA(cudaMemcpyAsync(ctx->eigDev.p, x0.data(), N * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  for (int l = 0; l < levels; ++l)
+    for (int i = 0; i < N; ++i) x0[i] = x0[i] * x0[i] / (2.0 * x0[i] * (x0[i] - 1.0) + 1.0);
+  if (dmDer_h)
+    for (int i = 0; i < N; ++i) dmDer_h[i] = beta * x0[i] * (1.0 - x0[i]);
+  DB_TRY(launch_row_scale(ctx, X, ctx->M, N * cm, N * cm, 1.0, ctx->sqrtM.p));
+  const bool skipWas = ctx->skip_nonlocal;
+  ctx->skip_nonlocal = true;
+  // singlePrecLRD: XtHXMixedPrecOverlapComputeCommun with Noc = N, i.e. every block in FP32 (rayleighRitzDevice.cc:1509-1523)
+  int rc = projham_any(ctx, X, N, ctx->denseB.p, singlePrec, N);
+  ctx->skip_nonlocal = skipWas;
+  if (rc != 0) return rc;
+  ctx->launches += 1;
+  fermi_response_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(ctx->denseB.p, N, cm, ctx->eigDev.p, c, levels,
+                                                                   ctx->denseA.p);
+  DB_CUDA(cudaGetLastError());
+  // subspaceRotation[RRMixedPrec]Scalapack with D^H (:1670-1700): X <- X D
+  DB_TRY(rotate_impl(ctx, X, N, ctx->denseA.p, true, singlePrec ? 2 : 0));
+  DB_TRY(launch_row_scale(ctx, X, ctx->M, N * cm, N * cm, 1.0, ctx->invSqrtM.p));
+  DB_CUDA(cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
 // HOT LOOP 1 of solve() (solver .cc:376-526): slice block -> filter -> write back, for every block of B
 // columns of X (row-major M x N), X resident in HBM (Xd) or in host memory (Xh, pinned recommended).
 //
@@ -1261,6 +1333,14 @@ int dftfe_b200_solve_no_rr(dftfe_b200_ctx *ctx, double *X_d, int32_t N, const df
   DB_CTX(ctx);
   DB_CHECK(params, "solve_no_rr: params are required");
   return solve_no_rr_impl(ctx, X_d, N, params, number_passes, upper_bound_out_h);
+}
+
+int dftfe_b200_density_matrix_first_order_response(dftfe_b200_ctx *ctx, double *X_d, int32_t N, const double *eig_h,
+                                                   double fermi_energy, double temperature, int32_t single_prec,
+                                                   double *dm_der_fermi_out_h) {
+  DB_CTX(ctx);
+  DB_CHECK(X_d && eig_h && N > 0 && temperature > 0.0, "first_order_response: bad arguments");
+  return first_order_response_impl(ctx, X_d, N, eig_h, fermi_energy, temperature, single_prec != 0, dm_der_fermi_out_h);
 }
 
 int dftfe_b200_get_spectrum_bounds(dftfe_b200_ctx *ctx, double out_h[3]) {

@@ -120,13 +120,16 @@ class operatorDFTDeviceClass {
     check(dftfe_b200_reinit_kpoint_spin_index(d_ctx, (int32_t)kPointIndex, (int32_t)spinIndex), "reinit_kpoint_spin_index");
   }
 
+  // onlyHPrimePartForFirstOrderDensityMatResponse for the XtHX family (their trailing reference arguments are ignored
+  // by the adapters below): bracket the call with setOnlyHPrime(true) / setOnlyHPrime(false)
+  void setOnlyHPrime(const bool on) { check(dftfe_b200_set_option(d_ctx, "only_h_prime", on ? 1 : 0), "set_option"); }
+
   // kohnShamDFTOperatorDevice.cc:3765-3860
   template <class Vec>
   void HX(Vec &src, Vec & /*projectorKetTimesVector*/, const unsigned int /*localVectorSize*/,
           const unsigned int numberComponents, const bool scaleFlag, const double scalar, Vec &dst,
           const bool doUnscalingX = true, const bool onlyHPrimePartForFirstOrderDensityMatResponse = false) {
-    if (onlyHPrimePartForFirstOrderDensityMatResponse)
-      throw std::runtime_error("HX: onlyHPrime is outside the ChFSI hot path and not provided");
+    OnlyHPrime guard(d_ctx, onlyHPrimePartForFirstOrderDensityMatResponse);
     check(dftfe_b200_hx(d_ctx, src.begin(), dst.begin(), (int32_t)numberComponents, scaleFlag ? 1 : 0, scalar,
                         doUnscalingX ? 1 : 0, 0),
           "HX");
@@ -137,8 +140,7 @@ class operatorDFTDeviceClass {
           const unsigned int numberComponents, const bool scaleFlag, const double scalar, Vec &dst,
           const bool doUnscalingX = true, const bool singlePrecCommun = false,
           const bool onlyHPrimePartForFirstOrderDensityMatResponse = false) {
-    if (onlyHPrimePartForFirstOrderDensityMatResponse)
-      throw std::runtime_error("HX: onlyHPrime is outside the ChFSI hot path and not provided");
+    OnlyHPrime guard(d_ctx, onlyHPrimePartForFirstOrderDensityMatResponse);
     check(dftfe_b200_hx(d_ctx, src.begin(), dst.begin(), (int32_t)numberComponents, scaleFlag ? 1 : 0, scalar,
                         doUnscalingX ? 1 : 0, singlePrecCommun ? 1 : 0),
           "HX");
@@ -220,6 +222,18 @@ class operatorDFTDeviceClass {
   }
 
  private:
+  // onlyHPrimePartForFirstOrderDensityMatResponse (kohnShamDFTOperatorDevice.cc:3680-3688): the caller has selected the
+  // H' cell matrices (reinitkPointSpinIndex on the set it stored them in); the non-local term is left out for the call
+  struct OnlyHPrime {
+    OnlyHPrime(dftfe_b200_ctx *c, bool on) : ctx(c), active(on) {
+      if (active) dftfe_b200_set_option(ctx, "only_h_prime", 1);
+    }
+    ~OnlyHPrime() {
+      if (active) dftfe_b200_set_option(ctx, "only_h_prime", 0);
+    }
+    dftfe_b200_ctx *ctx;
+    bool active;
+  };
   template <class Matrix>
   static void fillLowerTriangle(const std::vector<double> &full, unsigned int N, Matrix &mat) {
     for (unsigned int jl = 0; jl < mat.local_n(); ++jl) {
@@ -291,6 +305,24 @@ class chebyshevOrthogonalizedSubspaceIterationSolverDevice {
     check(dftfe_b200_solve_no_rr(operatorMatrix.context(), eigenVectorsFlattenedDevice, (int32_t)totalNumberWaveFunctions,
                                  &p, (int32_t)numberPasses, &d_upperUnwanted),
           "solveNoRR");
+  }
+
+  // densityMatrixEigenBasisFirstOrderResponse(operatorMatrix, BLASWrapperPtr, eigenVectorsFlattenedDevice, flattenedSize,
+  //   totalNumberWaveFunctions, eigenValues, fermiEnergy, densityMatDerFermiEnergy, devicecclMpiCommDomain,
+  //   interBandGroupComm, elpaScala)  (:1084-1196).  TVal / singlePrecLRD come from dftParameters in the reference.
+  void densityMatrixEigenBasisFirstOrderResponse(operatorDFTDeviceClass &operatorMatrix, double *eigenVectorsFlattenedDevice,
+                                                 const unsigned int /*flattenedSize*/,
+                                                 const unsigned int totalNumberWaveFunctions,
+                                                 const std::vector<double> &eigenValues, const double fermiEnergy,
+                                                 std::vector<double> &densityMatDerFermiEnergy, const double TVal,
+                                                 const bool singlePrecLRD = false) {
+    if (eigenValues.size() != totalNumberWaveFunctions)
+      throw std::runtime_error("densityMatrixEigenBasisFirstOrderResponse: one eigenvalue per wavefunction is required");
+    densityMatDerFermiEnergy.resize(totalNumberWaveFunctions);
+    check(dftfe_b200_density_matrix_first_order_response(operatorMatrix.context(), eigenVectorsFlattenedDevice,
+                                                         (int32_t)totalNumberWaveFunctions, eigenValues.data(), fermiEnergy,
+                                                         TVal, singlePrecLRD ? 1 : 0, densityMatDerFermiEnergy.data()),
+          "densityMatrixEigenBasisFirstOrderResponse");
   }
 
  private:

@@ -362,6 +362,17 @@ int dftfe_b200_solve(dftfe_b200_ctx *ctx, double *X_d, double *X_frac_d, int32_t
  * bounds of an earlier solve() (the reference calls it after the first SCF's solve). */
 int dftfe_b200_solve_no_rr(dftfe_b200_ctx *ctx, double *X_d, int32_t N, const dftfe_b200_solve_params *params,
                            int32_t number_passes, double *upper_bound_out_h);
+/* chebyshevOrthogonalizedSubspaceIterationSolverDevice::densityMatrixEigenBasisFirstOrderResponse
+ * (solver .cc:1084-1196 -> src/linAlg/rayleighRitzDevice.cc:1456-1737).  The cell matrices currently selected
+ * (set_cell_hamiltonian + reinit_kpoint_spin) must be the H' matrices (hamPrimeMatrixKernel*,
+ * hamiltonianMatrixCalculatorFlattenedDevice.cc:1138-1260); the non-local term is skipped as with onlyHPrime.
+ * X_d (M x N eigenvectors) <- X D with D the first-order density-matrix response in the eigenbasis;
+ * dm_der_fermi_out_h[N] = densityMatDerFermiEnergy (may be NULL).  temperature in K (dftParameters::TVal);
+ * single_prec = dftParameters::singlePrecLRD.  Option "only_h_prime" = 1 gives the same onlyHPrime behaviour to the
+ * bare HX / HXCheby / XtHX entry points. */
+int dftfe_b200_density_matrix_first_order_response(dftfe_b200_ctx *ctx, double *X_d, int32_t N, const double *eig_h,
+                                                   double fermi_energy, double temperature, int32_t single_prec,
+                                                   double *dm_der_fermi_out_h);
 /* bounds currently held by the solver object: {a0, bLow, bUp}. */
 int dftfe_b200_get_spectrum_bounds(dftfe_b200_ctx *ctx, double out_h[3]);
 

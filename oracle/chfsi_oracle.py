@@ -210,13 +210,15 @@ def compute_nonlocal_hamiltonian_times_x(ranks, src, dst, scalar: float = 1.0):
 
 
 def HX(ranks, src, dst, scale_flag: bool, scalar: float, do_unscaling_src: bool = True,
-       single_prec_commun: bool = False):
+       single_prec_commun: bool = False, only_h_prime: bool = False):
     """src/dftOperator/kohnShamDFTOperator.cc:950-1044 (CPU) with the device
     variant's ``doUnscalingSrc`` switch and ``scalar`` placement
     (src/dftOperator/kohnShamDFTOperatorDevice.cc:3765-3860: src *= scalar*M^-1/2).
 
     dst (+)= M^-1/2 H M^-1/2 (scalar*src); on exit src has its ghosts zeroed and is
-    rescaled back when do_unscaling_src.  single_prec_commun: the overload at :3609-3761 (FP32 exchanges)."""
+    rescaled back when do_unscaling_src.  single_prec_commun: the overload at :3609-3761 (FP32 exchanges).
+    only_h_prime = onlyHPrimePartForFirstOrderDensityMatResponse (:3680-3688): rp.H holds the H' cell matrices and the
+    non-local term is skipped."""
     for rp, s, d in zip(ranks, src, dst):
         M = rp.M
         s[:M] *= (scalar * rp.invSqrtMass[:M])[:, None]
@@ -226,7 +228,8 @@ def HX(ranks, src, dst, scale_flag: bool, scalar: float, do_unscaling_src: bool 
     for rp, s, d in zip(ranks, src, dst):
         distribute(rp, s)
         compute_local_hamiltonian_times_x(rp, s, d, 1.0)
-    compute_nonlocal_hamiltonian_times_x(ranks, src, dst, 1.0)
+    if not only_h_prime:
+        compute_nonlocal_hamiltonian_times_x(ranks, src, dst, 1.0)
     for rp, d in zip(ranks, dst):
         distribute_slave_to_master(rp, d)
     zero_out_ghosts(ranks, src)
@@ -402,7 +405,7 @@ def xtx(ranks, X) -> np.ndarray:
     return S
 
 
-def apply_HX_blocked(ranks, X, block: int):
+def apply_HX_blocked(ranks, X, block: int, only_h_prime: bool = False):
     """H~ X for a full N-column X by blocks of ``block`` columns, as XtHX does
     (src/dftOperator/kohnShamDFTOperatorDevice.cc:4051-4090)."""
     N = X[0].shape[1]
@@ -411,15 +414,15 @@ def apply_HX_blocked(ranks, X, block: int):
         Xb = [x[:, j:j + block].copy() for x in X]
         zero_out_ghosts(ranks, Xb)
         Yb = [np.zeros_like(x) for x in Xb]
-        HX(ranks, Xb, Yb, False, 1.0, do_unscaling_src=False)
+        HX(ranks, Xb, Yb, False, 1.0, do_unscaling_src=False, only_h_prime=only_h_prime)
         for h, y in zip(HXf, Yb):
             h[:, j:j + block] = y
     return HXf
 
 
-def xthx(ranks, X, block: int) -> np.ndarray:
+def xthx(ranks, X, block: int, only_h_prime: bool = False) -> np.ndarray:
     """Hp = X^H H~ X (kohnShamDFTOperatorDevice.cc:4001-4157)."""
-    HXf = apply_HX_blocked(ranks, X, block)
+    HXf = apply_HX_blocked(ranks, X, block, only_h_prime)
     Hp = 0
     for x, h in zip(_owned(ranks, X), _owned(ranks, HXf)):
         Hp = Hp + x.conj().T @ h
@@ -576,6 +579,51 @@ def rayleigh_ritz_gep_spectrum_split(ranks, X, block: int, n_core: int, mixed=()
         xf[:rp.M] = x[:rp.M] @ Q[:, n_core:]
         XFrac.append(xf)
     return evals[n_core:], XFrac
+
+
+C_KB = 3.166811429e-06   # include/constants.h:30, Ha / K
+
+
+def density_matrix_eigen_basis_first_order_response(ranks, X, block: int, evals, fermi_energy: float, t_val: float):
+    """chebyshevOrthogonalizedSubspaceIterationSolverDevice::densityMatrixEigenBasisFirstOrderResponse (solver
+    .cc:1084-1196) -> linearAlgebraOperationsDevice::densityMatrixEigenBasisFirstOrderResponse
+    (src/linAlg/rayleighRitzDevice.cc:1456-1737), restated operation by operation on the lower-triangle-filled
+    matrix XtHX leaves (ScaLAPACKMatrix::add(B, a, b) is A = a A + b B; scale_rows / scale_columns_realfactors,
+    src/linAlg/scalapackWrapper.cc:1669-1702).  rp.H holds the H' cell matrices.  X (FE basis) <- X D in place;
+    returns (densityMatDerFermiEnergy, D)."""
+    evals = np.asarray(evals, dtype=np.float64)
+    N = evals.size
+    for rp, x in zip(ranks, X):
+        x[:rp.M] *= rp.sqrtMass[:rp.M, None]
+    Hp = np.tril(xthx(ranks, X, block, only_h_prime=True))       # projHamPrimePar: lower triangle only
+    m = 10
+    beta = 1.0 / C_KB / t_val
+    c = 2.0 ** (-2.0 - m) * beta
+    X0 = 0.5 - c * (evals - fermi_energy)
+    D = -c * Hp
+    for _ in range(m):
+        X1 = D.copy()
+        X1b = D.copy()
+        X1 = X0[:, None] * X1                                    # scale_rows_realfactors(X0)
+        X1b = X1b * X0[None, :]                                  # scale_columns_realfactors(X0)
+        X1 = X1 + X1b
+        Y0 = 1.0 / (2.0 * X0 * (X0 - 1.0) + 1.0)
+        X0 = Y0 * X0 * X0
+        X1c = X1.copy()
+        X1 = Y0[:, None] * X1
+        X1c = X1c * X0[None, :]
+        X1c = Y0[:, None] * X1c
+        X1 = X1 - 2.0 * X1c
+        X1b = D * X0[None, :]
+        X1b = Y0[:, None] * X1b
+        D = X1 + 2.0 * X1b
+    pmu0 = beta * X0 * (1.0 - X0)
+    D = D + D.conj().T
+    D[np.diag_indices(N)] *= 0.5
+    # subspaceRotationScalapack with D^H, rotationMatTranspose = false: X <- X D
+    for rp, x in zip(ranks, X):
+        x[:rp.M] = (x[:rp.M] @ D) * rp.invSqrtMass[:rp.M, None]
+    return pmu0, D
 
 
 def eigen_residual_norm(ranks, X, evals, block: int) -> np.ndarray:

@@ -465,6 +465,56 @@ def test_complex_spectrum_split(capi, mixed):
     op.close()
 
 
+@pytest.mark.parametrize("cplx", [False, True])
+def test_first_order_density_matrix_response(capi, cplx):
+    """densityMatrixEigenBasisFirstOrderResponse and the onlyHPrime operator variants (non-local term skipped, the
+    selected cell matrices are H'), two in-process ranks, against the oracle's operation-by-operation restatement."""
+    from oracle import chfsi_oracle as O
+
+    p, B, N, nranks = 2, 8, 24, 2
+    mesh, ranks = make_problem(p, (4, 3, 3), 1.2, (True, True, True), nranks=nranks, n_atoms=2,
+                               kpoint=(0.1, -0.2, 0.15) if cplx else None)
+    X = scatter_to_ranks(ranks, random_global(mesh, N, seed=11, cplx=cplx), loewdin=False)
+    ev = np.linspace(-0.25, 0.35, N)
+    mu, T = 0.02, 4000.0
+    Xref = [x.copy() for x in X]
+    pmu_ref, D_ref = O.density_matrix_eigen_basis_first_order_response(ranks, Xref, B, ev, mu, T)
+    src = [x[:, :B].copy() for x in X]
+    dst = [np.zeros_like(x) for x in src]
+    O.HX(ranks, src, dst, False, 1.0, only_h_prime=True)
+    dst_full = [np.zeros_like(x) for x in src]
+    O.HX(ranks, [x[:, :B].copy() for x in X], dst_full, False, 1.0)
+
+    def rank_fn(r):
+        rp = ranks[r]
+        op = capi.Operator(rp, B, use_torch_stream=False, complex=cplx)
+        op.comm_init_loopback(71 + int(cplx), r, nranks)
+        op.set_cell_hamiltonian(rp.H)
+        solver = capi.ChebyshevSolver(op)
+        dt = torch.complex128 if cplx else torch.float64
+        s_d, d_d = _dev(X[r][:, :B]), torch.zeros(rp.M + rp.G, B, dtype=dt, device="cuda")
+        op.HX(s_d, d_d, False, 1.0, onlyHPrimePartForFirstOrderDensityMatResponse=True)
+        op.sync()
+        hx = d_d.cpu().numpy()[:rp.M]
+        outs = []
+        for single in (False, True):
+            Xd = _dev(X[r][:rp.M])
+            pmu = solver.densityMatrixEigenBasisFirstOrderResponse(Xd, ev, mu, T, singlePrecLRD=single)
+            outs.append((Xd.cpu().numpy(), pmu))
+        op.close()
+        return hx, outs
+
+    scale = max(np.abs(x[:rp.M]).max() for rp, x in zip(ranks, Xref))
+    for r, (hx, outs) in enumerate(_run_ranks(nranks, rank_fn)):
+        rp = ranks[r]
+        assert _relerr(hx, dst[r][:rp.M]) < 1e-12
+        assert _relerr(hx, dst_full[r][:rp.M]) > 1e-6          # the projectors were really left out
+        (x64, pmu64), (x32, pmu32) = outs
+        assert np.abs(x64 - Xref[r][:rp.M]).max() < 1e-11 * scale
+        assert np.abs(pmu64 - pmu_ref).max() < 1e-12 * np.abs(pmu_ref).max()
+        assert 0.0 < np.abs(x32 - Xref[r][:rp.M]).max() < 2e-5 * scale   # singlePrecLRD: FP32 blocks
+
+
 def test_solve_no_rr(capi):
     """solveNoRR: two passes of filter + Cholesky-Gram-Schmidt; the result is a deterministic function of the
     input (triangular orthonormalisation), so the vectors themselves are compared."""

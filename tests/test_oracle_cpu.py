@@ -362,6 +362,34 @@ def test_mixed_precision_restatements_complex_build():
             assert 0.0 < np.abs(y[:rp.M] - exact).max() / np.abs(exact).max() < 1e-5
 
 
+def test_first_order_density_matrix_response_known_answer():
+    """densityMatrixEigenBasisFirstOrderResponse: the recursive Fermi-operator expansion (10 levels) reproduces the
+    analytic first-order response of the Fermi-Dirac density matrix in the eigenbasis,
+    D_ij = (f_i - f_j) / (eps_i - eps_j) H'_ij, D_ii = f'(eps_i) H'_ii, up to its start-value linearisation (~1e-6);
+    the non-local term is NOT part of H' (onlyHPrime)."""
+    mesh, ranks = make_problem(2, (3, 3, 3), 1.2, (True, True, True), nranks=2, n_atoms=2)
+    N, B = 12, 4
+    X = scatter_to_ranks(ranks, random_global(mesh, N, seed=1), loewdin=False)
+    ev = np.linspace(-0.3, 0.4, N)
+    mu, T = 0.05, 5000.0
+    Xc = [x.copy() for x in X]
+    pmu, D = O.density_matrix_eigen_basis_first_order_response(ranks, Xc, B, ev, mu, T)
+    beta = 1.0 / O.C_KB / T
+    f = 1.0 / (1.0 + np.exp(beta * (ev - mu)))
+    Xs = [x * rp.sqrtMass[:, None] for rp, x in zip(ranks, X)]
+    Hp = O.xthx(ranks, [x.copy() for x in Xs], B, only_h_prime=True)
+    Hfull = O.xthx(ranks, [x.copy() for x in Xs], B)
+    assert np.abs(Hp - Hfull).max() > 1e-6 * np.abs(Hfull).max()      # the projectors would have contributed
+    de = ev[:, None] - ev[None, :]
+    dd = np.where(np.eye(N, dtype=bool), (-beta * f * (1 - f))[:, None], (f[:, None] - f[None, :]) / np.where(de == 0, 1, de))
+    ref = dd * Hp
+    assert np.abs(D - ref).max() < 5e-6 * np.abs(ref).max()
+    assert np.abs(pmu - beta * f * (1 - f)).max() < 5e-6 * np.abs(pmu).max()
+    for rp, x, xc in zip(ranks, X, Xc):
+        want = ((x[:rp.M] * rp.sqrtMass[:rp.M, None]) @ D) * rp.invSqrtMass[:rp.M, None]
+        assert np.abs(xc[:rp.M] - want).max() < 1e-13 * max(np.abs(want).max(), 1e-300)
+
+
 def test_spectrum_split_and_no_rr_statements():
     mesh, ranks = make_problem(3, (3, 3, 2), 1.4, (True, True, True), nranks=2)
     N, B, Noc = 16, 8, 8
