@@ -288,6 +288,73 @@ cell_matvec_kernel(const double *__restrict__ Ht, const uint32_t *__restrict__ c
 }
 
 // ---------------------------------------------------------------------------
+// One wavefunction column (real build): y_c = H~_c x_c is a matrix-vector product bound by the stream of H~_c
+// (941 KB per cell at FE order 6).  The Lanczos bounds (linearAlgebraOperationsDevice.cc:340-527: 20 single-vector
+// applies per SCF step) come through here.  Same fragment-major H~ as the DMMA kernels: a lane's 32-byte vector of
+// k-step ks holds A[(warp + t*WARPS)*8 + lane/4][ks*4 + lane%4] for its TPWP row tiles, so the lane accumulates those
+// rows against x[ks*4 + lane%4] and the four lanes of a row are summed by two shuffles.  One CTA per cell of the
+// colour, several CTAs per SM, eight 32-byte loads in flight per lane.
+// ---------------------------------------------------------------------------
+template <int NODES>
+__global__ void __launch_bounds__(CellCfg<NODES, false>::THREADS)
+cell_gemv_kernel(const double *__restrict__ Ht, const uint32_t *__restrict__ cellRows,
+                 const int32_t *__restrict__ cells, const double *__restrict__ src, double *__restrict__ dst, int ldx,
+                 EpilogueParams ep) {
+  using C = CellCfg<NODES, false>;
+  __shared__ double xs[C::KPAD];
+  __shared__ uint32_t rowsS[NODES];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cell = cells[blockIdx.x];
+  for (int i = tid; i < NODES; i += C::THREADS) rowsS[i] = cellRows[(size_t)cell * NODES + i];
+  __syncthreads();
+  for (int k = tid; k < C::KPAD; k += C::THREADS) {
+    double v = 0.0;
+    if (k < NODES) {
+      const uint32_t r = rowsS[k] & ROW_MASK;
+      v = __ldg(src + (size_t)r * ldx);
+      if (ep.rowIn) v *= __ldg(ep.rowIn + r);
+    }
+    xs[k] = v;
+  }
+  __syncthreads();
+  const double *Hc = Ht + (size_t)cell * C::HT_PER_CELL + (size_t)warp * C::HT_PER_WARP + lane * C::TPWP;
+  const double *xk = xs + (lane & 3);
+  double acc[C::TPWP];
+#pragma unroll
+  for (int t = 0; t < C::TPWP; ++t) acc[t] = 0.0;
+#pragma unroll 8
+  for (int ks = 0; ks < C::KS; ++ks) {
+    double a[C::TPWP];
+    load_frags<C::TPWP>(Hc + (size_t)ks * 32 * C::TPWP, a);
+    const double x = xk[ks * 4];
+#pragma unroll
+    for (int t = 0; t < C::TPWP; ++t) acc[t] = fma(a[t], x, acc[t]);
+  }
+#pragma unroll
+  for (int t = 0; t < C::TPWP; ++t) {
+    acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], 1);
+    acc[t] += __shfl_xor_sync(0xffffffffu, acc[t], 2);
+  }
+  // epilogue (recurrence + scaling + coloured assembly, as in cell_matvec_kernel): lane%4 == t%4 writes row tile t
+#pragma unroll
+  for (int t = 0; t < C::TPW; ++t) {
+    const int mt = warp + t * C::WARPS;
+    const int i = mt * 8 + (lane >> 2);
+    if ((lane & 3) == (t & 3) && mt < C::MT && i < NODES) {
+      const uint32_t fr = rowsS[i];
+      const uint32_t r = fr & ROW_MASK;
+      const double so = ep.s * (ep.rowOut ? __ldg(ep.rowOut + r) : 1.0);
+      double ca, cb;
+      epilogue_coeffs(fr, ep, ca, cb);
+      double o = so * acc[t];
+      if (ca != 0.0) o += ca * src[(size_t)r * ldx];
+      if (cb != 0.0) o += cb * dst[(size_t)r * ldx];
+      dst[(size_t)r * ldx] = o;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // Fast path: persistent, warp-specialised version of the kernel above.
 //   * one CTA per SM loops over the (cell, column-tile) items of a colour;
 //   * a producer warp gathers the NEXT item's X tile with 1-D TMA bulk copies
@@ -781,6 +848,13 @@ int launch_impl2(dftfe_b200_ctx *ctx, const double *src, double *dst, int ncols,
     if (nCellsK == 0) continue;
     ProfScope ps(ctx, "cell_matvec");
     const int nItems = nCellsK * nColTiles;
+    if constexpr (!CPLX) {
+      if (ncols == 1 && !ctx->force_generic_cell_kernel) {  // single vector: H-stream-bound matrix-vector kernel
+        cell_gemv_kernel<NODES><<<nCellsK, C::THREADS, 0, ctx->stream>>>(
+            ctx->Hactive, ctx->cellRowsFlagged.p, ctx->colourCells.p + ctx->colourStart_h[k], src, dst, ldx, ep);
+        continue;
+      }
+    }
     if (fast) {
       const int grid = std::min(nItems, std::max(1, ctx->num_sms - ctx->reserved_sms));
       if (ncols % BT == 0)

@@ -39,6 +39,12 @@ def capi(lib_built):
     (5, (2, 2, 3), (True, True, True), 16),
     (6, (2, 2, 2), (True, True, True), 32),
     (7, (2, 2, 2), (False, True, True), 8),
+    # one column: the H-stream-bound matrix-vector kernel of the Lanczos applies (generic = 0) vs the DMMA kernel
+    (6, (3, 2, 2), (True, True, False), 1),
+    (5, (2, 2, 2), (False, True, True), 1),
+    (3, (3, 3, 2), (True, True, True), 1),
+    (2, (3, 3, 3), (False, False, False), 1),
+    (7, (2, 2, 2), (True, True, True), 1),
 ])
 @pytest.mark.parametrize("generic", [0, 1])
 def test_hx_and_hxcheby_single_rank(capi, p, ncells, periodic, B, generic):
