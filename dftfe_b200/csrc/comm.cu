@@ -526,10 +526,21 @@ static int exchange_p2p(dftfe_b200_ctx *ctx, bool forward, double *x, int ncols,
     sig.addr[s] = p2p_flag(p.peerSlab[q], p.peerOffFlags[q], nr, lane, dir, P2P_DATA, ctx->rank);
   }
   segs.start[segs.n] = forward ? ctx->nSend : ctx->G;
-  if (forward)
+  if (forward) {
     DB_TRY(launch_push_rows(ctx, x, ncols, ldx, ctx->nSend, ctx->sendRows.p, 0, segs, fp32));
-  else
+  } else if (!fp32 && ldx == ncols && ctx->G > 0) {
+    // reverse, FP64, dense rows: a neighbour's rows are one contiguous run of my ghost segment - peer copies on the
+    // copy engines, no SM (the forward direction gathers scattered owned rows and needs the push kernel)
+    ProfScope ps(ctx, "ghost_pack", segs.n);
+    for (int s = 0; s < segs.n; ++s) {
+      const int64_t r0 = ctx->ghostRanges_h[2 * s], r1 = ctx->ghostRanges_h[2 * s + 1];
+      if (r1 > r0)
+        DB_CUDA(cudaMemcpyAsync(segs.dst[s], x + (size_t)(ctx->M + r0) * ldx, (size_t)(r1 - r0) * rowBytes,
+                                cudaMemcpyDeviceToDevice, ctx->stream));
+    }
+  } else {
     DB_TRY(launch_push_rows(ctx, x, ncols, ldx, ctx->G, nullptr, ctx->M, segs, fp32));
+  }
   DB_TRY(launch_signal_flags(ctx, sig, seq));
   // In-process ranks share ONE device: a device-synchronising call (cudaFree, ...) made by one rank's host thread
   // waits for every rank's streams, so a stream must never wait on work a sibling thread has not submitted yet.
