@@ -404,7 +404,7 @@ int nonlocal_project(dftfe_b200_ctx *ctx, const double *x, int ncols, int ldx, c
   // few atoms (small systems, many ranks): the rows of an atom are dealt over `slices` CTAs whose partial blocks are
   // summed in slice order, so that the launch fills the SMs
   const int chunks = (ncols + 63) / 64;
-  const int wantSlices = (8 * ctx->num_sms + ns.nAtoms * chunks - 1) / std::max(1, ns.nAtoms * chunks);
+  const int wantSlices = (4 * ctx->num_sms + ns.nAtoms * chunks - 1) / std::max(1, ns.nAtoms * chunks);
   const int slices = std::max(1, std::min({32, wantSlices, ns.maxAtomRows / 64}));
   const size_t count = (size_t)ns.totalProj * ncols;
   double *out = ctx->nlProj[ctx->lane].p;
