@@ -194,7 +194,7 @@ __device__ __forceinline__ void st2_stream(double *p, double2 v) {
   asm volatile("st.global.cs.v2.f64 [%0], {%1,%2};" ::"l"(p), "d"(v.x), "d"(v.y) : "memory");
 }
 
-__global__ void __launch_bounds__(256, 5)  // <= 48 registers: fits beside a resident cell CTA of the other lane
+__global__ void __launch_bounds__(256, 5)  // <= 48 registers: 8 warps within what a resident cell CTA leaves of the SM's registers
 distribute_vec_kernel(double *__restrict__ x, int ncols, int ldx, int64_t nCon, const uint32_t *__restrict__ rows,
                       const uint32_t *__restrict__ sizes, const uint32_t *__restrict__ starts,
                       const uint32_t *__restrict__ cols, const double *__restrict__ vals,
@@ -233,7 +233,7 @@ distribute_vec_kernel(double *__restrict__ x, int ncols, int ldx, int64_t nCon, 
   }
 }
 
-__global__ void __launch_bounds__(256, 5)  // <= 48 registers: fits beside a resident cell CTA of the other lane
+__global__ void __launch_bounds__(256, 5)  // <= 48 registers: 8 warps within what a resident cell CTA leaves of the SM's registers
 slave_to_master_vec_kernel(double *__restrict__ x, int ncols, int ldx, int64_t nMasters,
                            const uint32_t *__restrict__ masters, const uint32_t *__restrict__ mstarts,
                            const uint32_t *__restrict__ slaves, const double *__restrict__ vals,
@@ -388,7 +388,7 @@ unpack_rows_vec_kernel(double *__restrict__ x, int ncols, int ldx, int64_t row0,
 // are copied back as doubles, kohnShamDFTOperatorDevice.cc:3953-3990):
 //   x[r,:] = double( float(x[r,:]) +f float(scale[r]*slot_1) +f float(scale[r]*slot_2) ... )   (FP32 adds)
 template <typename TIN>
-__global__ void __launch_bounds__(256, 5)  // <= 48 registers: fits beside a resident cell CTA of the other lane
+__global__ void __launch_bounds__(256, 5)  // <= 48 registers: 8 warps within what a resident cell CTA leaves of the SM's registers
 unpack_add_vec_kernel(double *__restrict__ x, int ncols, int ldx, int64_t nRows, const uint32_t *__restrict__ rows,
                       const uint32_t *__restrict__ starts, const uint32_t *__restrict__ slots,
                       const TIN *__restrict__ buf, const double *__restrict__ rowScale) {
