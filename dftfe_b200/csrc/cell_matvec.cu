@@ -67,7 +67,10 @@ struct CellCfg {
   static constexpr int KS = (NODES + 3) / 4;  // k4 steps
   static constexpr int KSV = CPLX ? 2 * KS : KS;  // virtual k-steps (complex: Ar / Ai interleaved)
   static constexpr int KPAD = KS * 4;
-  static constexpr int WARPS = MT >= 12 ? 12 : (MT >= 8 ? 8 : 4);
+#ifndef DB_MMA_WARPS_MAX
+#define DB_MMA_WARPS_MAX 12  // A/B hook (tools/build_variants.sh): 11 leaves the CTA at 12 warps incl. the producer
+#endif
+  static constexpr int WARPS = MT >= 12 ? DB_MMA_WARPS_MAX : (MT >= 8 ? 8 : 4);
   static constexpr int TPW = (MT + WARPS - 1) / WARPS;  // row tiles per warp (max)
   static constexpr int THREADS = WARPS * 32;
   static constexpr size_t SMEM = (size_t)KPAD * LDS * sizeof(double);
