@@ -121,11 +121,34 @@ __global__ void nl_apply_kernel(double *__restrict__ y, int ncols, int ldx, int6
 
 
 // ---- bandwidth-shaped variants (even column counts, 16-byte aligned rows) ---------------------------------------
-// One CTA per (atom, 64-column chunk), four warps; a lane owns two adjacent real columns (one complex column in the
-// k-point build) and walks every fourth row of the atom, four rows in flight (16-byte loads): the x rows of an atom
-// are streamed once at HBM speed, the projector values of a row are broadcast loads.
+// One CTA per (atom, 64-column chunk[, row slice]), four warps; a lane owns two adjacent real columns (one complex
+// column in the k-point build); a warp walks the atom's rows in groups of four (16-byte loads, four rows in flight).
+// Nothing on the per-group path waits for a second memory latency: the row ids and the projector values of the NEXT
+// group are fetched while this group is processed - the values as one coalesced warp load (the rows of an atom are
+// consecutive in `vals`), handed to the other lanes through a per-warp shared-memory slot.  (ncu before this: every row
+// stalled on its own broadcast load of the projector values, 1.5-1.8 TB/s; profiles/r02_nonlocal_ncu_summary*.csv.)
 constexpr int NLV_WARPS = 4;
 constexpr int NLV_UNROLL = 4;
+
+template <int CM, int PMAX>
+struct NlStage {
+  static constexpr int VPI = NLV_UNROLL * PMAX * CM;  // projector values of one group of rows (at most)
+  static constexpr int VPL = (VPI + 31) / 32;         // ... per lane
+};
+
+// values of the rows [rb, rb + NLV_UNROLL) of the atom: lane l takes elements l, l + 32, ... of the contiguous run
+template <int CM, int PMAX>
+__device__ __forceinline__ void nl_fetch_vals(const double *__restrict__ va, int rb, int r0, int r1, int P, int lane,
+                                              double (&v)[NlStage<CM, PMAX>::VPL]) {
+  const int64_t base = (int64_t)(rb - r0) * P * CM;
+  const int64_t avail = (int64_t)(r1 - rb) * P * CM;  // <= 0 beyond the atom's last row
+  const int n = NLV_UNROLL * P * CM;
+#pragma unroll
+  for (int k = 0; k < NlStage<CM, PMAX>::VPL; ++k) {
+    const int e = lane + 32 * k;
+    v[k] = (e < n && e < avail) ? va[base + e] : 0.0;
+  }
+}
 
 template <int CM, int PMAX>
 __global__ void __launch_bounds__(NLV_WARPS * 32)
@@ -133,68 +156,81 @@ nl_project_vec_kernel(const double *__restrict__ x, int ncols, int ldx, const in
                       const uint32_t *__restrict__ atomRows, const int64_t *__restrict__ atomValStart,
                       const double *__restrict__ vals, const int32_t *__restrict__ projOffset,
                       const double *__restrict__ rowScale, double *__restrict__ proj, size_t sliceStride) {
+  using S = NlStage<CM, PMAX>;
   __shared__ double2 red[NLV_WARPS][PMAX][32];
+  __shared__ double vsh[NLV_WARPS][S::VPI];
   proj += blockIdx.z * sliceStride;
   const int a = blockIdx.x;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int col = blockIdx.y * 64 + lane * 2;
+  const bool active = col < ncols;
   const int P = projOffset[a + 1] - projOffset[a];
   const int r0 = atomRowStart[a], r1 = atomRowStart[a + 1];
   const double *va = vals + atomValStart[a] * CM;
   double2 acc[PMAX];
 #pragma unroll
   for (int p = 0; p < PMAX; ++p) acc[p] = make_double2(0.0, 0.0);
-  if (col < ncols) {
-    for (int rb = r0 + (blockIdx.z * NLV_WARPS + warp) * NLV_UNROLL; rb < r1;
-         rb += gridDim.z * NLV_WARPS * NLV_UNROLL) {
-      double2 xv[NLV_UNROLL];
-      double sc[NLV_UNROLL];
+  const int stride = gridDim.z * NLV_WARPS * NLV_UNROLL;
+  int rb = r0 + (blockIdx.z * NLV_WARPS + warp) * NLV_UNROLL;
+  uint32_t nextRows[NLV_UNROLL];
+  double vnext[S::VPL];
 #pragma unroll
-      for (int u = 0; u < NLV_UNROLL; ++u) {
-        const int r = rb + u;
-        xv[u] = make_double2(0.0, 0.0);
-        sc[u] = 1.0;
-        if (r < r1) {
-          const uint32_t row = atomRows[r];
-          xv[u] = *reinterpret_cast<const double2 *>(x + (size_t)row * ldx + col);
-          if (rowScale) sc[u] = rowScale[row];
-        }
-      }
+  for (int u = 0; u < NLV_UNROLL; ++u) nextRows[u] = (rb + u < r1) ? atomRows[rb + u] : 0u;
+  nl_fetch_vals<CM, PMAX>(va, rb, r0, r1, P, lane, vnext);
+  for (; rb < r1; rb += stride) {  // warp-uniform trip count: every lane stages values, inactive lanes skip the data
 #pragma unroll
-      for (int u = 0; u < NLV_UNROLL; ++u) {
-        const int r = rb + u;
-        if (r < r1) {
-          const double xr = xv[u].x * sc[u], xi = xv[u].y * sc[u];
-          const double *v = va + (size_t)(r - r0) * P * CM;
+    for (int k = 0; k < S::VPL; ++k)
+      if (lane + 32 * k < S::VPI) vsh[warp][lane + 32 * k] = vnext[k];
+    __syncwarp();
+    double2 xv[NLV_UNROLL];
+    double sc[NLV_UNROLL];
 #pragma unroll
-          for (int p = 0; p < PMAX; ++p)
-            if (p < P) {
-              if (CM == 2) {  // conj(c) x: re = cr xr + ci xi, im = cr xi - ci xr
-                const double cr = v[2 * p], ci = v[2 * p + 1];
-                acc[p].x += cr * xr + ci * xi;
-                acc[p].y += cr * xi - ci * xr;
-              } else {
-                acc[p].x += v[p] * xr;
-                acc[p].y += v[p] * xi;
-              }
-            }
-        }
+    for (int u = 0; u < NLV_UNROLL; ++u) {
+      xv[u] = make_double2(0.0, 0.0);
+      sc[u] = 1.0;
+      if (active && rb + u < r1) {
+        const uint32_t row = nextRows[u];
+        xv[u] = *reinterpret_cast<const double2 *>(x + (size_t)row * ldx + col);
+        if (rowScale) sc[u] = rowScale[row];
       }
     }
+#pragma unroll
+    for (int u = 0; u < NLV_UNROLL; ++u) nextRows[u] = (rb + stride + u < r1) ? atomRows[rb + stride + u] : 0u;
+    nl_fetch_vals<CM, PMAX>(va, rb + stride, r0, r1, P, lane, vnext);
+#pragma unroll
+    for (int u = 0; u < NLV_UNROLL; ++u) {
+      if (rb + u < r1) {
+        const double xr = xv[u].x * sc[u], xi = xv[u].y * sc[u];
+        const double *v = vsh[warp] + u * P * CM;
+#pragma unroll
+        for (int p = 0; p < PMAX; ++p)
+          if (p < P) {
+            if (CM == 2) {  // conj(c) x: re = cr xr + ci xi, im = cr xi - ci xr
+              const double cr = v[2 * p], ci = v[2 * p + 1];
+              acc[p].x += cr * xr + ci * xi;
+              acc[p].y += cr * xi - ci * xr;
+            } else {
+              acc[p].x += v[p] * xr;
+              acc[p].y += v[p] * xi;
+            }
+          }
+      }
+    }
+    __syncwarp();  // the slot is rewritten at the top of the next iteration
   }
 #pragma unroll
   for (int p = 0; p < PMAX; ++p)
     if (p < P) red[warp][p][lane] = acc[p];
   __syncthreads();
-  if (col < ncols)
+  if (active)
     for (int p = warp; p < P; p += NLV_WARPS) {
-      double2 s = red[0][p][lane];
+      double2 sum = red[0][p][lane];
 #pragma unroll
       for (int g = 1; g < NLV_WARPS; ++g) {
-        s.x += red[g][p][lane].x;
-        s.y += red[g][p][lane].y;
+        sum.x += red[g][p][lane].x;
+        sum.y += red[g][p][lane].y;
       }
-      *reinterpret_cast<double2 *>(proj + (size_t)(projOffset[a] + p) * ncols + col) = s;
+      *reinterpret_cast<double2 *>(proj + (size_t)(projOffset[a] + p) * ncols + col) = sum;
     }
 }
 
@@ -218,10 +254,12 @@ nl_apply_vec_kernel(double *__restrict__ y, int ncols, int ldx, const int32_t *_
                     const int64_t *__restrict__ atomValStart, const double *__restrict__ vals,
                     const int32_t *__restrict__ projOffset, const double *__restrict__ V,
                     const double *__restrict__ proj, const double *__restrict__ rowScale, double s) {
+  using S = NlStage<CM, PMAX>;
+  __shared__ double vsh[NLV_WARPS][S::VPI];
   const int a = colourAtoms[blockIdx.x];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int col = blockIdx.y * 64 + lane * 2;
-  if (col >= ncols) return;
+  const bool active = col < ncols;
   const int P = projOffset[a + 1] - projOffset[a];
   const int r0 = atomRowStart[a], r1 = atomRowStart[a + 1];
   const double *va = vals + atomValStart[a] * CM;
@@ -229,7 +267,7 @@ nl_apply_vec_kernel(double *__restrict__ y, int ncols, int ldx, const int32_t *_
 #pragma unroll
   for (int p = 0; p < PMAX; ++p) {
     q[p] = make_double2(0.0, 0.0);
-    if (p < P) {
+    if (p < P && active) {
       const double2 t = *reinterpret_cast<const double2 *>(proj + (size_t)(projOffset[a] + p) * ncols + col);
       const double v = V[projOffset[a] + p];
       q[p] = make_double2(v * t.x, v * t.y);
@@ -237,20 +275,33 @@ nl_apply_vec_kernel(double *__restrict__ y, int ncols, int ldx, const int32_t *_
   }
   // the atom's rows are dealt over gridDim.z CTAs (row slices): a colour holds few atoms, and one CTA per (atom,
   // column chunk) would leave most SMs without work
-  for (int rb = r0 + (blockIdx.z * NLV_WARPS + warp) * NLV_UNROLL; rb < r1; rb += gridDim.z * NLV_WARPS * NLV_UNROLL) {
+  const int stride = gridDim.z * NLV_WARPS * NLV_UNROLL;
+  int rb = r0 + (blockIdx.z * NLV_WARPS + warp) * NLV_UNROLL;
+  uint32_t nextRows[NLV_UNROLL];
+  double vnext[S::VPL];
+#pragma unroll
+  for (int u = 0; u < NLV_UNROLL; ++u) nextRows[u] = (rb + u < r1) ? atomRows[rb + u] : 0u;
+  nl_fetch_vals<CM, PMAX>(va, rb, r0, r1, P, lane, vnext);
+  for (; rb < r1; rb += stride) {
+#pragma unroll
+    for (int k = 0; k < S::VPL; ++k)
+      if (lane + 32 * k < S::VPI) vsh[warp][lane + 32 * k] = vnext[k];
+    __syncwarp();
     double2 yv[NLV_UNROLL];
     uint32_t rows[NLV_UNROLL];
 #pragma unroll
     for (int u = 0; u < NLV_UNROLL; ++u) {
-      const int r = rb + u;
-      rows[u] = r < r1 ? atomRows[r] : 0u;
-      if (r < r1) yv[u] = *reinterpret_cast<const double2 *>(y + (size_t)rows[u] * ldx + col);
+      rows[u] = nextRows[u];
+      yv[u] = make_double2(0.0, 0.0);
+      if (active && rb + u < r1) yv[u] = *reinterpret_cast<const double2 *>(y + (size_t)rows[u] * ldx + col);
     }
 #pragma unroll
+    for (int u = 0; u < NLV_UNROLL; ++u) nextRows[u] = (rb + stride + u < r1) ? atomRows[rb + stride + u] : 0u;
+    nl_fetch_vals<CM, PMAX>(va, rb + stride, r0, r1, P, lane, vnext);
+#pragma unroll
     for (int u = 0; u < NLV_UNROLL; ++u) {
-      const int r = rb + u;
-      if (r < r1) {
-        const double *v = va + (size_t)(r - r0) * P * CM;
+      if (active && rb + u < r1) {
+        const double *v = vsh[warp] + u * P * CM;
         double sr = 0.0, si = 0.0;
 #pragma unroll
         for (int p = 0; p < PMAX; ++p)
@@ -270,6 +321,7 @@ nl_apply_vec_kernel(double *__restrict__ y, int ncols, int ldx, const int32_t *_
         *reinterpret_cast<double2 *>(y + (size_t)rows[u] * ldx + col) = yv[u];
       }
     }
+    __syncwarp();
   }
 }
 
