@@ -128,7 +128,10 @@ __global__ void nl_apply_kernel(double *__restrict__ y, int ncols, int ldx, int6
 // consecutive in `vals`), handed to the other lanes through a per-warp shared-memory slot.  (ncu before this: every row
 // stalled on its own broadcast load of the projector values, 1.5-1.8 TB/s; profiles/r02_nonlocal_ncu_summary*.csv.)
 constexpr int NLV_WARPS = 4;
-constexpr int NLV_UNROLL = 4;
+#ifndef DB_NLV_UNROLL
+#define DB_NLV_UNROLL 4  // A/B hook: rows in flight per warp
+#endif
+constexpr int NLV_UNROLL = DB_NLV_UNROLL;
 
 template <int CM, int PMAX>
 struct NlStage {
